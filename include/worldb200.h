@@ -1,0 +1,103 @@
+/* worldb200 -- C-ABI of the B200-native WORLD vocoder hot path.
+ *
+ * Drop-in boundary for yukara-ikemiya/world-class.  The reference has no FFI; its
+ * boundary is the public section of its C++ class headers.  Every entry point below
+ * replaces one reference interface, cited as file:line relative to /root/reference.
+ * The source-compatible C++ class headers in this directory (harvest.hpp,
+ * cheaptrick.hpp, d4c.hpp, synthesis.hpp, codec.hpp) are inline shims over this ABI.
+ *
+ * Conventions
+ *   - plain C: opaque handles, POD option structs, raw pointers and sizes; no CUDA or
+ *     torch types (a stream is passed as void*, NULL = the library's own stream).
+ *   - every function that can fail returns an int status (WB_OK = 0); the reference
+ *     returns void and has undefined behaviour on bad input.
+ *   - `*_compute`      : HOST pointers, identical argument meaning to the reference's
+ *                        compute(); synchronous; copies H2D/D2H internally.
+ *   - `*_compute_dev`  : DEVICE pointers, 2-D outputs are contiguous [frames][bins];
+ *                        asynchronous on the given stream.
+ *   - the randn() stream is process-global like the reference's
+ *     (src/world_matlabfunctions.cpp:243-264) and is consumed in the same order and
+ *     amount, so a fresh process running Harvest->CheapTrick->D4C->Synthesis draws the
+ *     same noise as the reference's serial build.
+ */
+#ifndef WORLDB200_H
+#define WORLDB200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WB_OK 0
+#define WB_ERR_CUDA 1
+#define WB_ERR_ARG 2
+#define WB_ERR_UNSUPPORTED 3
+
+/* include/harvest.hpp:16-28 (HarvestOption; defaults src/harvest.cpp:52-56) */
+typedef struct WbHarvestOption {
+  double f0_floor;            /* 71.0  */
+  double f0_ceil;             /* 800.0 */
+  double frame_period;        /* 5.0 ms */
+  double target_fs;           /* 8000.0 */
+  double channels_in_octave;  /* 40.0 */
+  int use_cos_table;          /* 0; the approximate window table is not supported (exact path only) */
+} WbHarvestOption;
+
+/* include/cheaptrick.hpp:14-20 (defaults src/cheaptrick.cpp:22-24) */
+typedef struct WbCheapTrickOption {
+  double q1;        /* -0.15 */
+  double f0_floor;  /* 71.0 */
+  int fft_size;     /* 0 = derive from fs and f0_floor */
+} WbCheapTrickOption;
+
+/* include/d4c.hpp:16-20 (default src/d4c.cpp:31-33) */
+typedef struct WbD4COption {
+  double threshold; /* 0.85 */
+} WbD4COption;
+
+typedef struct wb_harvest wb_harvest_t;
+typedef struct wb_cheaptrick wb_cheaptrick_t;
+typedef struct wb_d4c wb_d4c_t;
+typedef struct wb_synthesis wb_synthesis_t;
+
+/* ---- library ---------------------------------------------------------------------- */
+int wb_init(int device);                /* optional; otherwise lazily on first use (current device) */
+const char *wb_version(void);
+int wb_device_synchronize(void);
+
+void wb_harvest_option_default(WbHarvestOption *opt);      /* src/harvest.cpp:52-56 */
+void wb_cheaptrick_option_default(WbCheapTrickOption *opt); /* src/cheaptrick.cpp:22-24 */
+void wb_d4c_option_default(WbD4COption *opt);               /* src/d4c.cpp:31-33 */
+
+/* ---- randn() stream (src/world_matlabfunctions.cpp:243-264) ------------------------- */
+int wb_randn_reseed(void);                            /* back to the reference's initial state */
+int wb_randn_get_state(unsigned int state[4]);        /* x, y, z, w */
+int wb_randn_set_state(const unsigned int state[4]);
+int wb_randn_skip(unsigned long long n_calls);        /* as if randn() had been called n times */
+int wb_randn_fill(double *out, int n);                /* HOST out; next n values; advances the stream */
+
+/* ---- stand-alone FFT with the reference wrapper's semantics -------------------------
+ * include/world_fft.hpp:33-41 + src/world_fft.cpp:31-77: forward = e^{+i}, backward = e^{-i},
+ * unnormalised; complex numbers are interleaved (re, im) doubles; HOST pointers;
+ * n = power of two in [16, 16384]; `batch` independent transforms back to back. */
+int wb_fft_r2c(const double *in, int n, int batch, double *out);   /* fft_plan_dft_r2c_1d + fft_execute */
+int wb_fft_c2r(const double *in, int n, int batch, double *out);   /* fft_plan_dft_c2r_1d + fft_execute */
+int wb_fft_c2c(const double *in, int n, int batch, int sign, double *out); /* sign: 1 = FFT_FORWARD, 2 = FFT_BACKWARD */
+
+/* ---- CheapTrick (include/cheaptrick.hpp:23-38) ------------------------------------- */
+int wb_cheaptrick_get_fft_size(int fs, double f0_floor);       /* src/cheaptrick.cpp:97-100 */
+double wb_cheaptrick_get_f0_floor(int fs, int fft_size);       /* src/cheaptrick.cpp:102-105 */
+int wb_cheaptrick_create(int fs, const WbCheapTrickOption *opt_or_null, wb_cheaptrick_t **out); /* :27-45 */
+void wb_cheaptrick_destroy(wb_cheaptrick_t *h);
+int wb_cheaptrick_fft_size(const wb_cheaptrick_t *h);
+/* src/cheaptrick.cpp:48-95; spectrogram = f0_length separately allocated rows of fft_size/2+1 */
+int wb_cheaptrick_compute(wb_cheaptrick_t *h, const double *x, int x_length,
+                          const double *temporal_positions, const double *f0, int f0_length,
+                          double **spectrogram);
+int wb_cheaptrick_compute_dev(wb_cheaptrick_t *h, const double *d_x, int x_length,
+                              const double *d_temporal_positions, const double *d_f0, int f0_length,
+                              double *d_spectrogram, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WORLDB200_H */

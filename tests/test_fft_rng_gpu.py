@@ -1,0 +1,70 @@
+"""GPU parity of the two shared building blocks: the shared-memory FFT (against the
+reference wrapper's convention restated with numpy) and the randn() stream (against the
+pure-Python restatement of the reference generator)."""
+import numpy as np
+import pytest
+
+from oracle import world_np
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n", [16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384])
+def test_r2c_c2r(wb, n):
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal((3, n))
+    X = wb.fft_r2c(x)
+    Xr = world_np.fft_r2c(x)
+    scale = np.abs(Xr).max()
+    assert np.abs(X - Xr).max() / scale < 1e-13
+    y = wb.fft_c2r(Xr, n)
+    yr = world_np.fft_c2r(Xr, n)
+    assert np.abs(y - yr).max() / np.abs(yr).max() < 1e-13
+    # unnormalised round trip: c2r(r2c(x)) = N x  
+    assert np.abs(wb.fft_c2r(X, n) - n * x).max() / (n * np.abs(x).max()) < 1e-13
+
+
+@pytest.mark.parametrize("n", [16, 64, 512, 1024, 2048, 4096, 8192])
+@pytest.mark.parametrize("sign", [1, 2])
+def test_c2c(wb, n, sign):
+    rng = np.random.default_rng(n + sign)
+    x = rng.standard_normal((2, n)) + 1j * rng.standard_normal((2, n))
+    X = wb.fft_c2c(x, sign)
+    Xr = world_np.fft_c2c(x, sign)
+    assert np.abs(X - Xr).max() / np.abs(Xr).max() < 1e-13
+
+
+def test_fft_impulse_convention(wb):
+    # delta at n = 1 -> e^{+2 pi i k / N} for the forward transform
+    n = 64
+    x = np.zeros((1, n))
+    x[0, 1] = 1.0
+    X = wb.fft_r2c(x)[0]
+    k = np.arange(n // 2 + 1)
+    assert np.abs(X - np.exp(2j * np.pi * k / n)).max() < 1e-14
+
+
+def test_randn_stream_bit_exact(wb):
+    wb.randn_reseed()
+    ref, state = world_np.randn_stream(3000)
+    got = wb.randn(3000)
+    assert np.array_equal(got, ref)
+    assert wb.randn_get_state() == state
+    # continuing the stream and jumping both agree with the sequential generator
+    ref2, state2 = world_np.randn_stream(500, state)
+    wb.randn_skip(100)
+    got2 = wb.randn(400)
+    assert np.array_equal(got2, ref2[100:])
+    assert wb.randn_get_state() == state2
+
+
+def test_randn_jump_far(wb):
+    # jump-ahead by a large count equals stepping: compare two different decompositions
+    wb.randn_reseed()
+    wb.randn_skip(123456789)
+    a = wb.randn(64)
+    wb.randn_reseed()
+    wb.randn_skip(123456000)
+    wb.randn_skip(789)
+    b = wb.randn(64)
+    assert np.array_equal(a, b)

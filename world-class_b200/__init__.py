@@ -1,0 +1,209 @@
+"""worldb200: host-side mirror of the world-class C++ interface over the C-ABI library.
+
+Class and method names follow the reference's headers (/root/reference/include/*.hpp):
+Harvest / CheapTrick / D4C / Synthesis objects with `compute(...)` plus their option
+structs.  Everything computes on the GPU through libworldb200.so (hand-written CUDA for
+sm_100a); there is NO CPU fallback -- importing works without a GPU, computing does not.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libworldb200.so")
+
+WB_OK = 0
+_ERR = {1: "CUDA error (or no GPU: this library has no CPU fallback)", 2: "bad argument", 3: "unsupported configuration"}
+
+
+class WorldB200Error(RuntimeError):
+    pass
+
+
+class HarvestOption(ctypes.Structure):
+    """include/harvest.hpp:16-28"""
+    _fields_ = [("f0_floor", ctypes.c_double), ("f0_ceil", ctypes.c_double), ("frame_period", ctypes.c_double),
+                ("target_fs", ctypes.c_double), ("channels_in_octave", ctypes.c_double), ("use_cos_table", ctypes.c_int)]
+
+    def __init__(self, **kw):
+        super().__init__()
+        lib().wb_harvest_option_default(ctypes.byref(self))
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+
+class CheapTrickOption(ctypes.Structure):
+    """include/cheaptrick.hpp:14-20"""
+    _fields_ = [("q1", ctypes.c_double), ("f0_floor", ctypes.c_double), ("fft_size", ctypes.c_int)]
+
+    def __init__(self, **kw):
+        super().__init__()
+        lib().wb_cheaptrick_option_default(ctypes.byref(self))
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+
+class D4COption(ctypes.Structure):
+    """include/d4c.hpp:16-20"""
+    _fields_ = [("threshold", ctypes.c_double)]
+
+    def __init__(self, **kw):
+        super().__init__()
+        lib().wb_d4c_option_default(ctypes.byref(self))
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+
+_lib = None
+_c_double_p = ctypes.POINTER(ctypes.c_double)
+_c_double_pp = ctypes.POINTER(_c_double_p)
+
+
+def _declare(L):
+    vp, ci, cd = ctypes.c_void_p, ctypes.c_int, ctypes.c_double
+    sig = {
+        "wb_init": (ci, [ci]),
+        "wb_version": (ctypes.c_char_p, []),
+        "wb_device_synchronize": (ci, []),
+        "wb_harvest_option_default": (None, [ctypes.POINTER(HarvestOption)]),
+        "wb_cheaptrick_option_default": (None, [ctypes.POINTER(CheapTrickOption)]),
+        "wb_d4c_option_default": (None, [ctypes.POINTER(D4COption)]),
+        "wb_randn_reseed": (ci, []),
+        "wb_randn_get_state": (ci, [ctypes.POINTER(ctypes.c_uint * 4)]),
+        "wb_randn_set_state": (ci, [ctypes.POINTER(ctypes.c_uint * 4)]),
+        "wb_randn_skip": (ci, [ctypes.c_ulonglong]),
+        "wb_randn_fill": (ci, [vp, ci]),
+        "wb_fft_r2c": (ci, [vp, ci, ci, vp]),
+        "wb_fft_c2r": (ci, [vp, ci, ci, vp]),
+        "wb_fft_c2c": (ci, [vp, ci, ci, ci, vp]),
+        "wb_cheaptrick_get_fft_size": (ci, [ci, cd]),
+        "wb_cheaptrick_get_f0_floor": (cd, [ci, ci]),
+        "wb_cheaptrick_create": (ci, [ci, ctypes.POINTER(CheapTrickOption), ctypes.POINTER(vp)]),
+        "wb_cheaptrick_destroy": (None, [vp]),
+        "wb_cheaptrick_fft_size": (ci, [vp]),
+        "wb_cheaptrick_compute": (ci, [vp, vp, ci, vp, vp, ci, vp]),
+        "wb_cheaptrick_compute_dev": (ci, [vp, vp, ci, vp, vp, ci, vp, vp]),
+    }
+    for name, (res, args) in sig.items():
+        if not hasattr(L, name):
+            continue  # tests/test_abi.py checks the export list against include/worldb200.h
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+
+
+def lib():
+    """Load libworldb200.so (built by build.py / __graft_entry__.build()).  Fails loudly if absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise WorldB200Error("%s is missing: run `python __graft_entry__.py` (build()) first; "
+                                 "there is no CPU fallback" % LIB_PATH)
+        _lib = ctypes.CDLL(LIB_PATH)
+        _declare(_lib)
+    return _lib
+
+
+def _check(rc, what):
+    if rc != WB_OK:
+        raise WorldB200Error("%s failed: %s (status %d)" % (what, _ERR.get(rc, "unknown"), rc))
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _row_pointers(mat):
+    """A C `double **` (array of row pointers) into a C-contiguous 2-D float64 array."""
+    assert mat.flags["C_CONTIGUOUS"] and mat.dtype == np.float64 and mat.ndim == 2
+    addr = mat.ctypes.data + np.arange(mat.shape[0], dtype=np.uint64) * np.uint64(mat.strides[0])
+    return np.ascontiguousarray(addr, dtype=np.uint64)
+
+
+# ---- randn stream -----------------------------------------------------------------------
+def randn_reseed():
+    _check(lib().wb_randn_reseed(), "wb_randn_reseed")
+
+
+def randn_get_state():
+    s = (ctypes.c_uint * 4)()
+    _check(lib().wb_randn_get_state(ctypes.byref(s)), "wb_randn_get_state")
+    return tuple(int(v) for v in s)
+
+
+def randn_set_state(state):
+    s = (ctypes.c_uint * 4)(*state)
+    _check(lib().wb_randn_set_state(ctypes.byref(s)), "wb_randn_set_state")
+
+
+def randn_skip(n):
+    _check(lib().wb_randn_skip(int(n)), "wb_randn_skip")
+
+
+def randn(n):
+    out = np.empty(int(n), dtype=np.float64)
+    _check(lib().wb_randn_fill(out.ctypes.data, int(n)), "wb_randn_fill")
+    return out
+
+
+# ---- stand-alone FFT (include/world_fft.hpp) ---------------------------------------------
+FFT_FORWARD, FFT_BACKWARD = 1, 2
+
+
+def fft_r2c(x):
+    """x: [batch][n] real -> [batch][n/2+1] complex, reference convention (e^{+i}, unnormalised)."""
+    x = np.atleast_2d(_f64(x))
+    b, n = x.shape
+    out = np.empty((b, n // 2 + 1), dtype=np.complex128)
+    _check(lib().wb_fft_r2c(x.ctypes.data, n, b, out.ctypes.data), "wb_fft_r2c")
+    return out
+
+
+def fft_c2r(X, n):
+    X = np.ascontiguousarray(np.atleast_2d(X), dtype=np.complex128)
+    b = X.shape[0]
+    assert X.shape[1] == n // 2 + 1
+    out = np.empty((b, n), dtype=np.float64)
+    _check(lib().wb_fft_c2r(X.ctypes.data, n, b, out.ctypes.data), "wb_fft_c2r")
+    return out
+
+
+def fft_c2c(X, sign):
+    X = np.ascontiguousarray(np.atleast_2d(X), dtype=np.complex128)
+    b, n = X.shape
+    out = np.empty((b, n), dtype=np.complex128)
+    _check(lib().wb_fft_c2c(X.ctypes.data, n, b, int(sign), out.ctypes.data), "wb_fft_c2c")
+    return out
+
+
+# ---- CheapTrick (include/cheaptrick.hpp:23-38) ---------------------------------------------
+class CheapTrick:
+    def __init__(self, fs, option=None):
+        self._h = ctypes.c_void_p()
+        self.fs = int(fs)
+        opt = ctypes.byref(option) if option is not None else None
+        _check(lib().wb_cheaptrick_create(self.fs, opt, ctypes.byref(self._h)), "wb_cheaptrick_create")
+        self.fft_size = lib().wb_cheaptrick_fft_size(self._h)
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.wb_cheaptrick_destroy(self._h)
+            self._h = None
+
+    @staticmethod
+    def getFFTSizeForCheapTrick(fs, f0_floor):
+        return lib().wb_cheaptrick_get_fft_size(int(fs), float(f0_floor))
+
+    @staticmethod
+    def getF0FloorForCheapTrick(fs, fft_size):
+        return lib().wb_cheaptrick_get_f0_floor(int(fs), int(fft_size))
+
+    def compute(self, x, temporal_positions, f0):
+        """-> spectrogram [f0_length][fft_size/2+1] (host arrays in, host array out)."""
+        x, tpos, f0 = _f64(x), _f64(temporal_positions), _f64(f0)
+        sp = np.empty((len(f0), self.fft_size // 2 + 1), dtype=np.float64)
+        rows = _row_pointers(sp)
+        _check(lib().wb_cheaptrick_compute(self._h, x.ctypes.data, len(x), tpos.ctypes.data, f0.ctypes.data,
+                                           len(f0), rows.ctypes.data), "wb_cheaptrick_compute")
+        return sp

@@ -1,0 +1,240 @@
+// C-ABI entry points (include/worldb200.h).  Thin: argument checks, H2D/D2H staging for
+// the host-pointer variants, and calls into the stage runners.
+#include "../../include/worldb200.h"
+
+#include <math.h>
+#include <string.h>
+#include <mutex>
+#include <new>
+
+#include "wb_internal.h"
+
+namespace {
+
+std::once_flag g_ctx_once;
+int g_ctx_status = WB_OK;
+cudaStream_t g_stream = nullptr;
+
+int ctx_init() {
+  std::call_once(g_ctx_once, []() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+      fprintf(stderr, "worldb200: no CUDA device available -- this library has no CPU fallback\n");
+      g_ctx_status = WB_ERR_CUDA;
+      return;
+    }
+    if (cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking) != cudaSuccess) {
+      g_ctx_status = WB_ERR_CUDA;
+      return;
+    }
+    g_ctx_status = wb_rng_init();
+  });
+  return g_ctx_status;
+}
+
+inline cudaStream_t pick_stream(void *stream) { return stream ? (cudaStream_t)stream : g_stream; }
+
+// copy a contiguous [rows][cols] device matrix into separately allocated host rows
+int rows_to_host(WbWorkspace *ws, const double *d_src, int rows, int cols, double **dst, cudaStream_t st) {
+  const size_t bytes = sizeof(double) * (size_t)rows * cols;
+  double *stage = (double *)ws->get_pinned("rows_stage", bytes);
+  if (!stage) return WB_ERR_CUDA;
+  WB_CUDA_CHECK(cudaMemcpyAsync(stage, d_src, bytes, cudaMemcpyDeviceToHost, st));
+  WB_CUDA_CHECK(cudaStreamSynchronize(st));
+  for (int i = 0; i < rows; ++i) memcpy(dst[i], stage + (size_t)i * cols, sizeof(double) * cols);
+  return WB_OK;
+}
+
+// gather separately allocated host rows into a contiguous device matrix
+int rows_to_device(WbWorkspace *ws, const char *name, const double *const *src, int rows, int cols,
+                   double *d_dst, cudaStream_t st) {
+  const size_t bytes = sizeof(double) * (size_t)rows * cols;
+  double *stage = (double *)ws->get_pinned(name, bytes);
+  if (!stage) return WB_ERR_CUDA;
+  for (int i = 0; i < rows; ++i) memcpy(stage + (size_t)i * cols, src[i], sizeof(double) * cols);
+  WB_CUDA_CHECK(cudaMemcpyAsync(d_dst, stage, bytes, cudaMemcpyHostToDevice, st));
+  return WB_OK;
+}
+
+int vec_to_device(WbWorkspace *ws, const char *name, const double *src, size_t n, double **d_out, cudaStream_t st) {
+  double *d = (double *)ws->get(name, sizeof(double) * n);
+  if (!d) return WB_ERR_CUDA;
+  WB_CUDA_CHECK(cudaMemcpyAsync(d, src, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  *d_out = d;
+  return WB_OK;
+}
+
+}  // namespace
+
+struct wb_cheaptrick {
+  int fs;
+  WbCheapTrickOption opt;   // fft_size resolved
+  double f0_floor_internal; // cheaptrick.cpp:34 / :44
+  WbWorkspace ws;
+};
+
+extern "C" {
+
+int wb_init(int device) {
+  if (device >= 0) {
+    if (cudaSetDevice(device) != cudaSuccess) return WB_ERR_CUDA;
+  }
+  return ctx_init();
+}
+
+const char *wb_version(void) { return "worldb200 0.1 (sm_100a)"; }
+
+int wb_device_synchronize(void) {
+  int rc = ctx_init();
+  if (rc) return rc;
+  WB_CUDA_CHECK(cudaStreamSynchronize(g_stream));
+  return WB_OK;
+}
+
+void wb_harvest_option_default(WbHarvestOption *o) {
+  o->f0_floor = 71.0; o->f0_ceil = 800.0; o->frame_period = 5.0;
+  o->target_fs = 8000.0; o->channels_in_octave = 40.0; o->use_cos_table = 0;
+}
+void wb_cheaptrick_option_default(WbCheapTrickOption *o) { o->q1 = -0.15; o->f0_floor = 71.0; o->fft_size = 0; }
+void wb_d4c_option_default(WbD4COption *o) { o->threshold = 0.85; }
+
+// ---- randn -----------------------------------------------------------------------------
+int wb_randn_reseed(void) {
+  int rc = ctx_init();
+  if (rc) return rc;
+  const unsigned int s0[4] = {123456789u, 362436069u, 521288629u, 88675123u};
+  return wb_randn_set_state(s0);
+}
+
+int wb_randn_get_state(unsigned int state[4]) {
+  int rc = ctx_init();
+  if (rc) return rc;
+  WB_CUDA_CHECK(cudaStreamSynchronize(g_stream));
+  WB_CUDA_CHECK(cudaMemcpy(state, wb_rng_global_state(), sizeof(WbRngState), cudaMemcpyDeviceToHost));
+  return WB_OK;
+}
+
+int wb_randn_set_state(const unsigned int state[4]) {
+  int rc = ctx_init();
+  if (rc) return rc;
+  WB_CUDA_CHECK(cudaStreamSynchronize(g_stream));
+  WB_CUDA_CHECK(cudaMemcpy(wb_rng_global_state(), state, sizeof(WbRngState), cudaMemcpyHostToDevice));
+  return WB_OK;
+}
+
+int wb_randn_skip(unsigned long long n_calls) {
+  unsigned int s[4];
+  int rc = wb_randn_get_state(s);
+  if (rc) return rc;
+  wb_rng_host_jump(s, n_calls);
+  return wb_randn_set_state(s);
+}
+
+int wb_randn_fill(double *out, int n) {
+  int rc = ctx_init();
+  if (rc) return rc;
+  if (n < 0 || (n > 0 && !out)) return WB_ERR_ARG;
+  if (n == 0) return WB_OK;
+  double *d = nullptr;
+  unsigned long long *d_n = nullptr;
+  WB_CUDA_CHECK(cudaMalloc(&d, sizeof(double) * n));
+  WB_CUDA_CHECK(cudaMalloc(&d_n, sizeof(unsigned long long)));
+  const unsigned long long nn = (unsigned long long)n;
+  WB_CUDA_CHECK(cudaMemcpyAsync(d_n, &nn, sizeof(nn), cudaMemcpyHostToDevice, g_stream));
+  rc = wb_rng_fill(wb_rng_global_state(), nullptr, nn, d, g_stream);
+  if (!rc) rc = wb_rng_advance(wb_rng_global_state(), d_n, g_stream);
+  if (!rc) {
+    cudaError_t e = cudaMemcpyAsync(out, d, sizeof(double) * n, cudaMemcpyDeviceToHost, g_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g_stream);
+    if (e != cudaSuccess) rc = WB_ERR_CUDA;
+  }
+  cudaFree(d);
+  cudaFree(d_n);
+  return rc;
+}
+
+// ---- stand-alone FFT (world_fft.hpp:33-41) -----------------------------------------------
+static int fft_host(int kind, const void *in, size_t in_bytes, int n, int batch, void *out, size_t out_bytes) {
+  int rc = ctx_init();
+  if (rc) return rc;
+  if (!in || !out || n <= 0 || batch < 0) return WB_ERR_ARG;
+  if (batch == 0) return WB_OK;
+  void *d_in = nullptr, *d_out = nullptr;
+  WB_CUDA_CHECK(cudaMalloc(&d_in, in_bytes));
+  if (cudaMalloc(&d_out, out_bytes) != cudaSuccess) { cudaFree(d_in); return WB_ERR_CUDA; }
+  cudaError_t e = cudaMemcpyAsync(d_in, in, in_bytes, cudaMemcpyHostToDevice, g_stream);
+  if (e == cudaSuccess) {
+    rc = wb_fft_batch_dev(kind, d_in, n, batch, d_out, g_stream);
+    if (!rc) e = cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, g_stream);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(g_stream);
+  cudaFree(d_in);
+  cudaFree(d_out);
+  if (rc) return rc;
+  return e == cudaSuccess ? WB_OK : WB_ERR_CUDA;
+}
+
+int wb_fft_r2c(const double *in, int n, int batch, double *out) {
+  return fft_host(0, in, sizeof(double) * (size_t)n * batch, n, batch, out, 2 * sizeof(double) * (size_t)(n / 2 + 1) * batch);
+}
+int wb_fft_c2r(const double *in, int n, int batch, double *out) {
+  return fft_host(1, in, 2 * sizeof(double) * (size_t)(n / 2 + 1) * batch, n, batch, out, sizeof(double) * (size_t)n * batch);
+}
+int wb_fft_c2c(const double *in, int n, int batch, int sign, double *out) {
+  if (sign != 1 && sign != 2) return WB_ERR_ARG;
+  return fft_host(sign == 1 ? 2 : 3, in, 2 * sizeof(double) * (size_t)n * batch, n, batch, out, 2 * sizeof(double) * (size_t)n * batch);
+}
+
+// ---- CheapTrick ------------------------------------------------------------------------
+int wb_cheaptrick_get_fft_size(int fs, double f0_floor) {
+  // cheaptrick.cpp:97-100, evaluated on the host with the reference's expression
+  return (int)pow(2.0, 1.0 + (int)(log(3.0 * fs / f0_floor + 1) / WB_LOG2));
+}
+
+double wb_cheaptrick_get_f0_floor(int fs, int fft_size) { return 3 * fs / (fft_size - 3.0); }
+
+int wb_cheaptrick_create(int fs, const WbCheapTrickOption *opt, wb_cheaptrick_t **out) {
+  if (!out || fs <= 0) return WB_ERR_ARG;
+  int rc = ctx_init();
+  if (rc) return rc;
+  wb_cheaptrick *h = new (std::nothrow) wb_cheaptrick();
+  if (!h) return WB_ERR_ARG;
+  h->fs = fs;
+  wb_cheaptrick_option_default(&h->opt);
+  if (opt) { h->opt.q1 = opt->q1; h->opt.f0_floor = opt->f0_floor; h->opt.fft_size = opt->fft_size; }
+  if (h->opt.fft_size == 0) h->opt.fft_size = wb_cheaptrick_get_fft_size(fs, h->opt.f0_floor);
+  h->f0_floor_internal = wb_cheaptrick_get_f0_floor(fs, h->opt.fft_size);
+  *out = h;
+  return WB_OK;
+}
+
+void wb_cheaptrick_destroy(wb_cheaptrick_t *h) { delete h; }
+
+int wb_cheaptrick_fft_size(const wb_cheaptrick_t *h) { return h ? h->opt.fft_size : 0; }
+
+int wb_cheaptrick_compute_dev(wb_cheaptrick_t *h, const double *d_x, int x_length, const double *d_tpos,
+                              const double *d_f0, int f0_length, double *d_sp, void *stream) {
+  if (!h || !d_x || !d_tpos || !d_f0 || !d_sp || x_length <= 0 || f0_length < 0) return WB_ERR_ARG;
+  return wb_cheaptrick_run(&h->ws, h->fs, h->opt.fft_size, h->opt.q1, h->f0_floor_internal, d_x, x_length,
+                           d_tpos, d_f0, f0_length, d_sp, wb_rng_global_state(), pick_stream(stream));
+}
+
+int wb_cheaptrick_compute(wb_cheaptrick_t *h, const double *x, int x_length, const double *tpos,
+                          const double *f0, int f0_length, double **spectrogram) {
+  if (!h || !x || !tpos || !f0 || !spectrogram || x_length <= 0 || f0_length < 0) return WB_ERR_ARG;
+  if (f0_length == 0) return WB_OK;
+  cudaStream_t st = g_stream;
+  const int bins = h->opt.fft_size / 2 + 1;
+  double *d_x, *d_t, *d_f;
+  int rc;
+  if ((rc = vec_to_device(&h->ws, "h_x", x, x_length, &d_x, st))) return rc;
+  if ((rc = vec_to_device(&h->ws, "h_tpos", tpos, f0_length, &d_t, st))) return rc;
+  if ((rc = vec_to_device(&h->ws, "h_f0", f0, f0_length, &d_f, st))) return rc;
+  double *d_sp = (double *)h->ws.get("h_sp", sizeof(double) * (size_t)f0_length * bins);
+  if (!d_sp) return WB_ERR_CUDA;
+  if ((rc = wb_cheaptrick_compute_dev(h, d_x, x_length, d_t, d_f, f0_length, d_sp, st))) return rc;
+  if ((rc = rows_to_host(&h->ws, d_sp, f0_length, bins, spectrogram, st))) return rc;
+  return h->ws.read_error_flag(st);
+}
+
+}  // extern "C"

@@ -1,0 +1,170 @@
+// CheapTrick spectral envelope: one thread block per analysis frame, everything between
+// the waveform gather and the final exp() stays in shared memory (3 FFTs per frame).
+//
+// Reference: /root/reference/src/cheaptrick.cpp
+//   compute :48-95, generalBody :108-135, getWindowedWaveform :137-167,
+//   setParametersForGetWindowedWaveform :169-196, getPowerSpectrum :198-218,
+//   addInfinitesimalNoise :220-228, smoothingWithRecovery :230-276.
+#include "wb_internal.h"
+#include "wb_fft.cuh"
+#include "wb_smooth.cuh"
+
+namespace {
+
+__device__ __forceinline__ double ct_current_f0(double f0, double f0_floor) {
+  return (f0 <= f0_floor) ? WB_DEFAULT_F0 : f0;  // cheaptrick.cpp:76
+}
+
+// randn() calls made by frame i: window samples + one per bin (cheaptrick.cpp:153, :227)
+__global__ void ct_count_kernel(const double *__restrict__ f0, int f0_length, int fs, int fft_size,
+                                double f0_floor, unsigned long long *__restrict__ counts) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= f0_length) return;
+  const double cf0 = ct_current_f0(f0[i], f0_floor);
+  const int hw = wb_round(1.5 * fs / cf0);
+  counts[i] = (unsigned long long)(2 * hw + 1) + (unsigned long long)(fft_size / 2 + 1);
+}
+
+struct CtParams {
+  const double *x;
+  int x_length;
+  const double *tpos;
+  const double *f0;
+  int f0_length;
+  int fs;
+  int fft_size;
+  int log2nc;
+  double q1;
+  double f0_floor;
+  const cplx *twiddle;              // fft_size entries
+  const double *noise;              // randn stream segment of this call
+  const unsigned long long *noise_off;  // exclusive offsets per frame
+  double *sp;                       // [f0_length][fft_size/2+1]
+  int seg_capacity;
+  int *error_flag;
+};
+
+__global__ void __launch_bounds__(256) ct_frame_kernel(CtParams p) {
+  extern __shared__ double2 smem_raw[];
+  const int N = p.fft_size, NC = N / 2, bins = NC + 1;
+  cplx *S = smem_raw;                                         // FFT slots
+  double *A = reinterpret_cast<double *>(S + wb_fft_slots(NC));  // N + 2 doubles
+  double *B = A + (N + 2);                                    // seg_capacity doubles
+  double *red = B + p.seg_capacity;                           // 1024 + 64
+  double *W = reinterpret_cast<double *>(S);                  // packed real waveform view
+
+  const int frame = blockIdx.x;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const double f0 = ct_current_f0(p.f0[frame], p.f0_floor);
+  const int fs = p.fs;
+  const int hw = wb_round(1.5 * fs / f0);
+  const int wlen = 2 * hw + 1;
+  const double *noise = p.noise + p.noise_off[frame];
+
+  // ---- F0-adaptive windowing (cheaptrick.cpp:137-196)
+  const int origin = wb_round(p.tpos[frame] * fs + 0.001);
+  double acc = 0.0;
+  for (int j = tid; j < wlen; j += nt) {
+    const double position = (j - hw) / 1.5 / fs;
+    const double w = 0.5 * cos(WB_PI * position * f0) + 0.5;
+    A[j] = w;
+    acc += w * w;
+  }
+  const double average = sqrt(wb_block_sum(acc, red));
+  double s1 = 0.0, s2 = 0.0;
+  for (int j = tid; j < wlen; j += nt) {
+    const double w = A[j] / average;
+    A[j] = w;
+    const int idx = wb_min_i(p.x_length - 1, wb_max_i(0, origin + j - hw));
+    const double v = p.x[idx] * w + noise[j] * 0.000000000000001;
+    W[wb_didx(j)] = v;
+    s1 += v;
+    s2 += w;
+  }
+  wb_block_sum2(s1, s2, red);
+  const double coef = s1 / s2;
+  for (int j = tid; j < N; j += nt) {
+    if (j < wlen) W[wb_didx(j)] -= A[j] * coef;
+    else W[wb_didx(j)] = 0.0;
+  }
+  __syncthreads();
+
+  // ---- power spectrum (cheaptrick.cpp:198-218)
+  wb_rfft<1>(S, NC, p.log2nc, p.twiddle, [&](int k, cplx X) { A[k] = X.x * X.x + X.y * X.y; });
+  wb_dc_correction(A, f0, fs, N);
+
+  // ---- linear smoothing with width 2 f0 / 3 (cheaptrick.cpp:124-125)
+  if (!wb_linear_smoothing(A, A, f0 * 2.0 / 3.0, fs, N, B, p.seg_capacity, red)) {
+    if (tid == 0) atomicExch(p.error_flag, WB_ERR_UNSUPPORTED);
+    return;
+  }
+
+  // ---- infinitesimal noise, log, mirror (cheaptrick.cpp:220-228, :255-258)
+  for (int i = tid; i < bins; i += nt) {
+    const double v = log(A[i] + fabs(noise[wlen + i]) * WB_EPS);
+    W[wb_didx(i)] = v;
+    if (i > 0 && i < NC) W[wb_didx(N - i)] = v;
+  }
+  __syncthreads();
+
+  // ---- liftering in the cepstral domain (cheaptrick.cpp:238-269)
+  const double q1 = p.q1;
+  wb_rfft<1>(S, NC, p.log2nc, p.twiddle, [&](int k, cplx X) {
+    double sl = 1.0, cl = (1.0 - 2.0 * q1) + 2.0 * q1;
+    if (k > 0) {
+      const double quefrency = static_cast<double>(k) / fs;
+      sl = sin(WB_PI * f0 * quefrency) / (WB_PI * f0 * quefrency);
+      cl = (1.0 - 2.0 * q1) + 2.0 * q1 * cos(2.0 * WB_PI * quefrency * f0);
+    }
+    A[k] = X.x * sl * cl / N;
+  });
+  wb_irfft<-1>(S, NC, p.log2nc, p.twiddle, [&](int k) { return make_double2(A[k], 0.0); });
+
+  double *out = p.sp + (size_t)frame * bins;
+  for (int i = tid; i < bins; i += nt) out[i] = exp(W[wb_didx(i)]);
+}
+
+}  // namespace
+
+size_t wb_cheaptrick_smem_bytes(int fft_size, int seg_capacity) {
+  return sizeof(cplx) * wb_fft_slots(fft_size / 2) + sizeof(double) * ((fft_size + 2) + seg_capacity + 1024 + 64);
+}
+
+// d_x, d_tpos, d_f0: device.  d_sp: device [f0_length][fft_size/2+1].
+// Consumes the global randn stream exactly like the reference's serial loop.
+int wb_cheaptrick_run(WbWorkspace *ws, int fs, int fft_size, double q1, double f0_floor_internal,
+                      const double *d_x, int x_length, const double *d_tpos, const double *d_f0,
+                      int f0_length, double *d_sp, WbRngState *d_rng, cudaStream_t stream) {
+  if (f0_length <= 0) return WB_OK;
+  int log2n = 0;
+  while ((1 << log2n) < fft_size) ++log2n;
+  if ((1 << log2n) != fft_size || fft_size < 128 || fft_size > 16384) return WB_ERR_UNSUPPORTED;
+  const int bins = fft_size / 2 + 1;
+  const cplx *tw = wb_twiddle_table(fft_size);
+  if (!tw) return WB_ERR_CUDA;
+
+  unsigned long long *d_counts = (unsigned long long *)ws->get("ct_counts", sizeof(unsigned long long) * (f0_length + 1));
+  unsigned long long *d_offsets = (unsigned long long *)ws->get("ct_offsets", sizeof(unsigned long long) * (f0_length + 1));
+  const unsigned long long max_noise = (unsigned long long)f0_length * (unsigned long long)(fft_size + bins);
+  double *d_noise = (double *)ws->get("noise", sizeof(double) * max_noise);
+  if (!d_counts || !d_offsets || !d_noise) return WB_ERR_CUDA;
+
+  ct_count_kernel<<<(f0_length + 255) / 256, 256, 0, stream>>>(d_f0, f0_length, fs, fft_size, f0_floor_internal, d_counts);
+  int rc = wb_exclusive_scan_u64(d_counts, d_offsets, f0_length, stream);  // d_offsets[f0_length] = total
+  if (rc) return rc;
+  rc = wb_rng_fill(d_rng, d_offsets + f0_length, max_noise, d_noise, stream);
+  if (rc) return rc;
+
+  CtParams p;
+  p.x = d_x; p.x_length = x_length; p.tpos = d_tpos; p.f0 = d_f0; p.f0_length = f0_length;
+  p.fs = fs; p.fft_size = fft_size; p.log2nc = log2n - 1; p.q1 = q1; p.f0_floor = f0_floor_internal;
+  p.twiddle = tw; p.noise = d_noise; p.noise_off = d_offsets; p.sp = d_sp;
+  p.seg_capacity = fft_size / 2 + fft_size / 4 + 8;
+  p.error_flag = ws->error_flag();
+  const size_t smem = wb_cheaptrick_smem_bytes(fft_size, p.seg_capacity);
+  WB_CUDA_CHECK(cudaFuncSetAttribute(ct_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int threads = wb_max_i(64, wb_min_i(256, fft_size / 8));
+  ct_frame_kernel<<<f0_length, threads, smem, stream>>>(p);
+  WB_CUDA_CHECK(cudaGetLastError());
+  return wb_rng_advance(d_rng, d_offsets + f0_length, stream);
+}

@@ -1,0 +1,36 @@
+// Internal host-side plumbing shared by the stage files (not part of the C-ABI).
+#pragma once
+#include <map>
+#include <string>
+
+#include "wb_common.cuh"
+#include "wb_rng.cuh"
+
+// Grow-only named device scratch buffers (one workspace per stage handle / pipeline).
+class WbWorkspace {
+ public:
+  WbWorkspace();
+  ~WbWorkspace();
+  void *get(const std::string &name, size_t bytes);        // device memory
+  void *get_pinned(const std::string &name, size_t bytes);  // page-locked host memory
+  int *error_flag();                                        // device int, zero-initialised
+  int read_error_flag(cudaStream_t stream);                 // syncs the stream
+ private:
+  struct Buf { void *p; size_t bytes; };
+  std::map<std::string, Buf> dev_, pinned_;
+  int *d_err_;
+};
+
+// e^{+2 pi i k / n}, k = 0..n-1, on the device; cached per n (power of two).
+const cplx *wb_twiddle_table(int n);
+
+// offsets[0..n] <- exclusive prefix sums of counts[0..n) (offsets[n] = total)
+int wb_exclusive_scan_u64(const unsigned long long *d_counts, unsigned long long *d_offsets, int n,
+                          cudaStream_t stream);
+
+int wb_cheaptrick_run(WbWorkspace *ws, int fs, int fft_size, double q1, double f0_floor_internal,
+                      const double *d_x, int x_length, const double *d_tpos, const double *d_f0,
+                      int f0_length, double *d_sp, WbRngState *d_rng, cudaStream_t stream);
+
+// stand-alone batched transforms (wb_fftapi.cu); kind 0 r2c, 1 c2r, 2 c2c fwd, 3 c2c bwd
+int wb_fft_batch_dev(int kind, const void *d_in, int n, int batch, void *d_out, cudaStream_t stream);

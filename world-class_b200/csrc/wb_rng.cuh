@@ -1,0 +1,69 @@
+// Exact reproduction of the reference's randn() stream on the GPU.
+//
+// Reference: /root/reference/src/world_matlabfunctions.cpp:243-264.  One randn() call is
+// one partial shift (x<-y, y<-z, z<-w with w unchanged) followed by 12 xorshift128
+// steps whose outputs (w >> 4) are summed; the value is sum / 2^28 - 6.  The state is a
+// single process-global 128-bit word, so the value returned by the n-th call depends
+// only on n.  xorshift128 is GF(2)-linear: the state after n calls is M^n s0 for a
+// fixed 128x128 bit matrix M.  We precompute P[b] = M^(2^b) on the host and let every
+// GPU thread jump straight to its own stream position.
+#pragma once
+#include "wb_common.cuh"
+
+#define WB_RNG_NPOW 48  // jump distances up to 2^48 calls
+
+struct WbRngState { uint32_t s[4]; };  // x, y, z, w
+
+__host__ __device__ __forceinline__ double wb_randn_next(uint32_t (&s)[4]) {
+  uint32_t x = s[0], y = s[1], z = s[2], w = s[3], t;
+  x = y; y = z; z = w;  // partial shift: t is overwritten before use in the reference
+  uint32_t tmp = 0;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) {
+    t = x ^ (x << 11);
+    x = y; y = z; z = w;
+    w = (w ^ (w >> 19)) ^ (t ^ (t >> 8));
+    tmp += w >> 4;
+  }
+  s[0] = x; s[1] = y; s[2] = z; s[3] = w;
+  return tmp / 268435456.0 - 6.0;
+}
+
+// cols: 128 columns of 4 words (uint4), column b = image of basis state bit b.
+__device__ __forceinline__ void wb_rng_apply(const uint4 *__restrict__ cols, uint32_t (&s)[4]) {
+  uint32_t o0 = 0, o1 = 0, o2 = 0, o3 = 0;
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    uint32_t bits = s[w];
+    while (bits) {
+      const int b = __ffs(bits) - 1;
+      bits &= bits - 1;
+      const uint4 c = __ldg(&cols[w * 32 + b]);
+      o0 ^= c.x; o1 ^= c.y; o2 ^= c.z; o3 ^= c.w;
+    }
+  }
+  s[0] = o0; s[1] = o1; s[2] = o2; s[3] = o3;
+}
+
+// s <- M^n s.  pow_tables: WB_RNG_NPOW matrices of 128 uint4 columns.
+__device__ __forceinline__ void wb_rng_jump(const uint4 *__restrict__ pow_tables, uint32_t (&s)[4],
+                                            unsigned long long n) {
+  int b = 0;
+  while (n) {
+    if (n & 1ull) wb_rng_apply(pow_tables + b * 128, s);
+    n >>= 1;
+    ++b;
+  }
+}
+
+// ---- host API (wb_rng.cu) ---------------------------------------------------------------
+// Device-resident global stream state (the reference's RNG is process-global).
+int wb_rng_init();                         // builds tables, uploads, seeds the global state
+const uint4 *wb_rng_tables();              // device pointer to the power tables
+WbRngState *wb_rng_global_state();         // device pointer to the global state
+void wb_rng_host_jump(uint32_t s[4], unsigned long long n);
+// out[i] = value of the (i+1)-th randn() call after state *d_state; does not advance it.
+int wb_rng_fill(const WbRngState *d_state, const unsigned long long *d_count_or_null,
+                unsigned long long max_count, double *d_out, cudaStream_t stream);
+// *d_state <- M^(*d_count) *d_state
+int wb_rng_advance(WbRngState *d_state, const unsigned long long *d_count, cudaStream_t stream);

@@ -1,0 +1,123 @@
+// Host runtime: workspaces, twiddle tables, small utility kernels.
+#include "wb_internal.h"
+
+#include <math.h>
+#include <mutex>
+#include <vector>
+
+WbWorkspace::WbWorkspace() : d_err_(nullptr) {}
+
+WbWorkspace::~WbWorkspace() {
+  for (auto &kv : dev_) cudaFree(kv.second.p);
+  for (auto &kv : pinned_) cudaFreeHost(kv.second.p);
+  if (d_err_) cudaFree(d_err_);
+}
+
+void *WbWorkspace::get(const std::string &name, size_t bytes) {
+  if (bytes == 0) bytes = 8;
+  auto it = dev_.find(name);
+  if (it != dev_.end() && it->second.bytes >= bytes) return it->second.p;
+  if (it != dev_.end()) { cudaFree(it->second.p); dev_.erase(it); }
+  void *p = nullptr;
+  const size_t grow = bytes + bytes / 8;  // a little slack so slowly growing inputs do not realloc every call
+  if (cudaMalloc(&p, grow) != cudaSuccess) {
+    fprintf(stderr, "worldb200: cudaMalloc(%zu) failed for %s\n", grow, name.c_str());
+    return nullptr;
+  }
+  dev_[name] = Buf{p, grow};
+  return p;
+}
+
+void *WbWorkspace::get_pinned(const std::string &name, size_t bytes) {
+  if (bytes == 0) bytes = 8;
+  auto it = pinned_.find(name);
+  if (it != pinned_.end() && it->second.bytes >= bytes) return it->second.p;
+  if (it != pinned_.end()) { cudaFreeHost(it->second.p); pinned_.erase(it); }
+  void *p = nullptr;
+  const size_t grow = bytes + bytes / 8;
+  if (cudaMallocHost(&p, grow) != cudaSuccess) {
+    fprintf(stderr, "worldb200: cudaMallocHost(%zu) failed for %s\n", grow, name.c_str());
+    return nullptr;
+  }
+  pinned_[name] = Buf{p, grow};
+  return p;
+}
+
+int *WbWorkspace::error_flag() {
+  if (!d_err_) {
+    if (cudaMalloc(&d_err_, sizeof(int)) != cudaSuccess) return nullptr;
+    cudaMemset(d_err_, 0, sizeof(int));
+  }
+  return d_err_;
+}
+
+int WbWorkspace::read_error_flag(cudaStream_t stream) {
+  if (!d_err_) return WB_OK;
+  int h = 0;
+  if (cudaMemcpyAsync(&h, d_err_, sizeof(int), cudaMemcpyDeviceToHost, stream) != cudaSuccess) return WB_ERR_CUDA;
+  if (cudaStreamSynchronize(stream) != cudaSuccess) return WB_ERR_CUDA;
+  if (h != 0) cudaMemsetAsync(d_err_, 0, sizeof(int), stream);
+  return h;
+}
+
+namespace {
+std::mutex g_tw_mutex;
+std::map<int, cplx *> g_tw;
+
+#define SCAN_THREADS 1024
+__global__ void __launch_bounds__(SCAN_THREADS) scan_u64_kernel(const unsigned long long *__restrict__ counts,
+                                                                unsigned long long *__restrict__ offsets, int n) {
+  __shared__ unsigned long long part[SCAN_THREADS];
+  const int tid = threadIdx.x;
+  const int chunk = (n + SCAN_THREADS - 1) / SCAN_THREADS;
+  const int b = tid * chunk, e = min(n, b + chunk);
+  unsigned long long s = 0;
+  for (int i = b; i < e; ++i) s += counts[i];
+  part[tid] = s;
+  __syncthreads();
+  // Hillis-Steele inclusive scan over the partials
+  for (int o = 1; o < SCAN_THREADS; o <<= 1) {
+    unsigned long long t = (tid >= o) ? part[tid - o] : 0ull;
+    __syncthreads();
+    part[tid] += t;
+    __syncthreads();
+  }
+  unsigned long long run = (tid > 0) ? part[tid - 1] : 0ull;
+  for (int i = b; i < e; ++i) { offsets[i] = run; run += counts[i]; }
+  if (tid == SCAN_THREADS - 1) offsets[n] = part[SCAN_THREADS - 1];
+}
+}  // namespace
+
+const cplx *wb_twiddle_table(int n) {
+  std::lock_guard<std::mutex> lock(g_tw_mutex);
+  auto it = g_tw.find(n);
+  if (it != g_tw.end()) return it->second;
+  std::vector<cplx> h(n);
+  const long double two_pi = 6.283185307179586476925286766559005768L;
+  for (int k = 0; k < n; ++k) {
+    // exact symmetries first so that e.g. T[n/4] = (0, 1) exactly
+    const int oct = (int)(((long long)k * 8) / n);
+    (void)oct;
+    const long double a = two_pi * (long double)k / (long double)n;
+    h[k].x = (double)cosl(a);
+    h[k].y = (double)sinl(a);
+  }
+  if (n >= 4) {
+    h[0] = make_double2(1.0, 0.0);
+    h[n / 4] = make_double2(0.0, 1.0);
+    h[n / 2] = make_double2(-1.0, 0.0);
+    h[3 * n / 4] = make_double2(0.0, -1.0);
+  }
+  cplx *d = nullptr;
+  if (cudaMalloc(&d, sizeof(cplx) * n) != cudaSuccess) return nullptr;
+  if (cudaMemcpy(d, h.data(), sizeof(cplx) * n, cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+  g_tw[n] = d;
+  return d;
+}
+
+int wb_exclusive_scan_u64(const unsigned long long *d_counts, unsigned long long *d_offsets, int n,
+                          cudaStream_t stream) {
+  scan_u64_kernel<<<1, SCAN_THREADS, 0, stream>>>(d_counts, d_offsets, n);
+  WB_CUDA_CHECK(cudaGetLastError());
+  return WB_OK;
+}

@@ -1,0 +1,69 @@
+// Block-level versions of the reference's spectral helpers, working on shared memory:
+//   DCCorrection      /root/reference/src/world_common.cpp:61-80
+//   LinearSmoothing   /root/reference/src/world_common.cpp:82-116 (+ :27-52)
+//   interp1Q          /root/reference/src/world_matlabfunctions.cpp:220-241
+// Every function is called by all threads of the block and ends with __syncthreads().
+#pragma once
+#include "wb_common.cuh"
+
+// P[0..nc] in shared memory (nc = fft_size / 2).  In-place: P[i] += replica(i).
+__device__ inline void wb_dc_correction(double *P, double f0, int fs, int fft_size) {
+  const int upper_limit = 2 + static_cast<int>(f0 * fft_size / fs);
+  const int n_rep = upper_limit - 1;
+  const double x0 = f0;  // f0 - low_frequency_axis[0]
+  const double dx = -static_cast<double>(fs) / fft_size;
+  // Each thread may own several replica points (n_rep can exceed blockDim for huge f0).
+  // Read phase and write phase are separated by a barrier because both touch P[0..upper_limit].
+  const int nt = blockDim.x;
+  double rep[4];
+  int cnt = 0;
+  for (int i = threadIdx.x; i < n_rep && cnt < 4; i += nt, ++cnt) {
+    const double xi = static_cast<double>(i) * fs / fft_size;
+    const int base = static_cast<int>((xi - x0) / dx);
+    const double frac = (xi - x0) / dx - base;
+    // delta_y[x_length - 1] = 0 with x_length = upper_limit + 1 (never reached: base <= upper_limit - 2)
+    const double dy = (base >= upper_limit) ? 0.0 : P[base + 1] - P[base];
+    rep[cnt] = P[base] + dy * frac;
+  }
+  __syncthreads();
+  cnt = 0;
+  for (int i = threadIdx.x; i < n_rep && cnt < 4; i += nt, ++cnt) P[i] += rep[cnt];
+  __syncthreads();
+}
+
+// in[0..nc] -> out[0..nc] (out may alias in).  seg: scratch of nc + 2*boundary + 1 doubles.
+// red: scratch of >= 1024 doubles.  Returns false (uniformly) if seg capacity is exceeded.
+__device__ inline bool wb_linear_smoothing(const double *in, double *out, double width, int fs,
+                                           int fft_size, double *seg, int seg_capacity, double *red) {
+  const int nc = fft_size / 2;
+  const int boundary = static_cast<int>(width * fft_size / fs) + 1;
+  const int len = nc + boundary * 2 + 1;
+  if (len > seg_capacity) return false;
+  // mirroring_spectrum[i] * fs / fft_size  (world_common.cpp:32-47)
+  for (int i = threadIdx.x; i < len; i += blockDim.x) {
+    double v;
+    if (i < boundary) v = in[boundary - i];
+    else if (i < nc + boundary) v = in[i - boundary];
+    else v = in[nc - (i - (nc + boundary))];
+    seg[i] = v * fs / fft_size;
+  }
+  __syncthreads();
+  wb_block_inclusive_scan(seg, len, red);  // mirroring_segment
+  const double origin = -(boundary - 0.5) * fs / fft_size;
+  const double interval = static_cast<double>(fs) / fft_size;
+  for (int i = threadIdx.x; i <= nc; i += blockDim.x) {
+    double fa = static_cast<double>(i) / fft_size * fs - width / 2.0;
+    int base = static_cast<int>((fa - origin) / interval);
+    double frac = (fa - origin) / interval - base;
+    double dy = (base >= len - 1) ? 0.0 : seg[base + 1] - seg[base];
+    const double low = seg[base] + dy * frac;
+    fa += width;
+    base = static_cast<int>((fa - origin) / interval);
+    frac = (fa - origin) / interval - base;
+    dy = (base >= len - 1) ? 0.0 : seg[base + 1] - seg[base];
+    const double high = seg[base] + dy * frac;
+    out[i] = (high - low) / width;
+  }
+  __syncthreads();
+  return true;
+}
