@@ -97,6 +97,16 @@ int wb_cheaptrick_compute_dev(wb_cheaptrick_t *h, const double *d_x, int x_lengt
                               const double *d_temporal_positions, const double *d_f0, int f0_length,
                               double *d_spectrogram, void *stream);
 
+/* ---- D4C (include/d4c.hpp:23-36) ---------------------------------------------------- */
+int wb_get_number_of_aperiodicities(int fs);                    /* src/d4c.cpp:65-67, src/codec.cpp:211-214 */
+int wb_d4c_create(int fs, const WbD4COption *opt_or_null, wb_d4c_t **out);   /* src/d4c.cpp:35-44 */
+void wb_d4c_destroy(wb_d4c_t *h);
+/* src/d4c.cpp:113-173; aperiodicity = f0_length separately allocated rows of fft_size/2+1 */
+int wb_d4c_compute(wb_d4c_t *h, const double *x, int x_length, const double *temporal_positions,
+                   const double *f0, int f0_length, int fft_size, double **aperiodicity);
+int wb_d4c_compute_dev(wb_d4c_t *h, const double *d_x, int x_length, const double *d_temporal_positions,
+                       const double *d_f0, int f0_length, int fft_size, double *d_aperiodicity, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -84,6 +84,11 @@ def _declare(L):
         "wb_cheaptrick_fft_size": (ci, [vp]),
         "wb_cheaptrick_compute": (ci, [vp, vp, ci, vp, vp, ci, vp]),
         "wb_cheaptrick_compute_dev": (ci, [vp, vp, ci, vp, vp, ci, vp, vp]),
+        "wb_get_number_of_aperiodicities": (ci, [ci]),
+        "wb_d4c_create": (ci, [ci, ctypes.POINTER(D4COption), ctypes.POINTER(vp)]),
+        "wb_d4c_destroy": (None, [vp]),
+        "wb_d4c_compute": (ci, [vp, vp, ci, vp, vp, ci, ci, vp]),
+        "wb_d4c_compute_dev": (ci, [vp, vp, ci, vp, vp, ci, ci, vp, vp]),
     }
     for name, (res, args) in sig.items():
         if not hasattr(L, name):
@@ -207,3 +212,26 @@ class CheapTrick:
         _check(lib().wb_cheaptrick_compute(self._h, x.ctypes.data, len(x), tpos.ctypes.data, f0.ctypes.data,
                                            len(f0), rows.ctypes.data), "wb_cheaptrick_compute")
         return sp
+
+
+# ---- D4C (include/d4c.hpp:23-36) ---------------------------------------------------------
+class D4C:
+    def __init__(self, fs, option=None):
+        self._h = ctypes.c_void_p()
+        self.fs = int(fs)
+        opt = ctypes.byref(option) if option is not None else None
+        _check(lib().wb_d4c_create(self.fs, opt, ctypes.byref(self._h)), "wb_d4c_create")
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.wb_d4c_destroy(self._h)
+            self._h = None
+
+    def compute(self, x, temporal_positions, f0, fft_size):
+        """-> aperiodicity [f0_length][fft_size/2+1]"""
+        x, tpos, f0 = _f64(x), _f64(temporal_positions), _f64(f0)
+        ap = np.empty((len(f0), int(fft_size) // 2 + 1), dtype=np.float64)
+        rows = _row_pointers(ap)
+        _check(lib().wb_d4c_compute(self._h, x.ctypes.data, len(x), tpos.ctypes.data, f0.ctypes.data,
+                                    len(f0), int(fft_size), rows.ctypes.data), "wb_d4c_compute")
+        return ap

@@ -73,6 +73,12 @@ struct wb_cheaptrick {
   WbWorkspace ws;
 };
 
+struct wb_d4c {
+  int fs;
+  WbD4COption opt;
+  WbWorkspace ws;
+};
+
 extern "C" {
 
 int wb_init(int device) {
@@ -234,6 +240,49 @@ int wb_cheaptrick_compute(wb_cheaptrick_t *h, const double *x, int x_length, con
   if (!d_sp) return WB_ERR_CUDA;
   if ((rc = wb_cheaptrick_compute_dev(h, d_x, x_length, d_t, d_f, f0_length, d_sp, st))) return rc;
   if ((rc = rows_to_host(&h->ws, d_sp, f0_length, bins, spectrogram, st))) return rc;
+  return h->ws.read_error_flag(st);
+}
+
+// ---- D4C --------------------------------------------------------------------------------
+int wb_get_number_of_aperiodicities(int fs) { return wb_number_of_aperiodicities(fs); }
+
+int wb_d4c_create(int fs, const WbD4COption *opt, wb_d4c_t **out) {
+  if (!out || fs <= 0) return WB_ERR_ARG;
+  int rc = ctx_init();
+  if (rc) return rc;
+  wb_d4c *h = new (std::nothrow) wb_d4c();
+  if (!h) return WB_ERR_ARG;
+  h->fs = fs;
+  wb_d4c_option_default(&h->opt);
+  if (opt) h->opt.threshold = opt->threshold;
+  *out = h;
+  return WB_OK;
+}
+
+void wb_d4c_destroy(wb_d4c_t *h) { delete h; }
+
+int wb_d4c_compute_dev(wb_d4c_t *h, const double *d_x, int x_length, const double *d_tpos, const double *d_f0,
+                       int f0_length, int fft_size, double *d_ap, void *stream) {
+  if (!h || !d_x || !d_tpos || !d_f0 || !d_ap || x_length <= 0 || f0_length < 0 || fft_size < 2) return WB_ERR_ARG;
+  return wb_d4c_run(&h->ws, h->fs, h->opt.threshold, d_x, x_length, d_tpos, d_f0, f0_length, fft_size, d_ap,
+                    wb_rng_global_state(), pick_stream(stream));
+}
+
+int wb_d4c_compute(wb_d4c_t *h, const double *x, int x_length, const double *tpos, const double *f0,
+                   int f0_length, int fft_size, double **aperiodicity) {
+  if (!h || !x || !tpos || !f0 || !aperiodicity || x_length <= 0 || f0_length < 0 || fft_size < 2) return WB_ERR_ARG;
+  if (f0_length == 0) return WB_OK;
+  cudaStream_t st = g_stream;
+  const int bins = fft_size / 2 + 1;
+  double *d_x, *d_t, *d_f;
+  int rc;
+  if ((rc = vec_to_device(&h->ws, "h_x", x, x_length, &d_x, st))) return rc;
+  if ((rc = vec_to_device(&h->ws, "h_tpos", tpos, f0_length, &d_t, st))) return rc;
+  if ((rc = vec_to_device(&h->ws, "h_f0", f0, f0_length, &d_f, st))) return rc;
+  double *d_ap = (double *)h->ws.get("h_ap", sizeof(double) * (size_t)f0_length * bins);
+  if (!d_ap) return WB_ERR_CUDA;
+  if ((rc = wb_d4c_compute_dev(h, d_x, x_length, d_t, d_f, f0_length, fft_size, d_ap, st))) return rc;
+  if ((rc = rows_to_host(&h->ws, d_ap, f0_length, bins, aperiodicity, st))) return rc;
   return h->ws.read_error_flag(st);
 }
 

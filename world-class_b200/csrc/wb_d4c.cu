@@ -1,0 +1,441 @@
+// D4C band aperiodicity with the "Love Train" voiced/unvoiced detector.
+// One thread block per frame; every FFT, smoothing pass and the order statistic of the
+// band power spectrum stay in shared memory.
+//
+// Reference: /root/reference/src/d4c.cpp
+//   prepareForD4c :60-111, compute :113-173, loveTrain/loveTrainSub :181-240,
+//   getWindowedWaveform :246-303, generalBody :308-333, getStaticCentroid :339-360,
+//   getCentroid :366-405, getSmoothedPowerSpectrum :411-434, getStaticGroupDelay :440-460,
+//   getCoarseAperiodicity :466-503.
+#include "wb_internal.h"
+#include "wb_fft.cuh"
+#include "wb_smooth.cuh"
+
+#include <math.h>
+#include <vector>
+
+namespace {
+
+#define D4C_HANNING 1
+#define D4C_BLACKMAN 2
+#define D4C_MAX_AP 8
+
+__device__ __forceinline__ int d4c_half_window(double ratio, int fs, double f0) {
+  return wb_round(ratio * fs / f0 / 2.0);  // d4c.cpp:250
+}
+
+// d4c.cpp:246-303.  at(j) -> reference to destination sample j.  `win` >= 2*hw+1 doubles.
+// All threads must call; ends with __syncthreads().  Returns the window length.
+template <typename At>
+__device__ inline int d4c_windowed_waveform(const double *__restrict__ x, int x_length, int fs, double f0,
+                                            double position_s, int window_type, double ratio,
+                                            const double *__restrict__ noise, double *win, double *red, At at) {
+  const int hw = d4c_half_window(ratio, fs, f0);
+  const int wlen = 2 * hw + 1;
+  const int origin = wb_round(position_s * fs + 0.001);
+  const double c1 = 2.0 / ratio / fs;
+  const double c2 = WB_PI * f0;
+  double s1 = 0.0, s2 = 0.0;
+  for (int j = threadIdx.x; j < wlen; j += blockDim.x) {
+    const double position = c1 * (j - hw);
+    double w;
+    if (window_type == D4C_HANNING) w = 0.5 * cos(c2 * position) + 0.5;
+    else w = 0.42 + 0.5 * cos(c2 * position) + 0.08 * cos(c2 * position * 2);
+    win[j] = w;
+    const int idx = wb_min_i(x_length - 1, wb_max_i(0, origin + j - hw));
+    const double v = x[idx] * w + noise[j] * WB_SAFEGUARD;
+    at(j) = v;
+    s1 += v;
+    s2 += w;
+  }
+  wb_block_sum2(s1, s2, red);
+  const double coef = s1 / s2;
+  for (int j = threadIdx.x; j < wlen; j += blockDim.x) at(j) -= win[j] * coef;
+  __syncthreads();
+  return wlen;
+}
+
+// ---- randn() call counts ------------------------------------------------------------------
+__global__ void lt_count_kernel(const double *__restrict__ f0, int n, int fs, double lowest_f0,
+                                unsigned long long *__restrict__ counts) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long c = 0;
+  if (f0[i] != 0.0) {
+    const double cf0 = f0[i] > lowest_f0 ? f0[i] : lowest_f0;
+    c = 2ull * d4c_half_window(3.0, fs, cf0) + 1ull;
+  }
+  counts[i] = c;
+}
+
+__global__ void body_count_kernel(const double *__restrict__ f0, const double *__restrict__ ap0, int n, int fs,
+                                  double threshold, unsigned long long *__restrict__ counts) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long c = 0;
+  if (!(f0[i] == 0 || ap0[i] <= threshold)) {
+    const double cf0 = f0[i] > WB_FLOOR_F0_D4C ? f0[i] : WB_FLOOR_F0_D4C;
+    c = 3ull * (2ull * d4c_half_window(4.0, fs, cf0) + 1ull);
+  }
+  counts[i] = c;
+}
+
+// ---- Love Train (d4c.cpp:181-240) ---------------------------------------------------------
+struct LtParams {
+  const double *x; int x_length;
+  const double *tpos; const double *f0; int f0_length;
+  int fs; int fft_size; int log2nc; double lowest_f0;
+  int boundary0, boundary1, boundary2;
+  const cplx *twiddle;
+  const double *noise; const unsigned long long *noise_off;
+  double *ap0;
+};
+
+__global__ void __launch_bounds__(256) lt_frame_kernel(LtParams p) {
+  extern __shared__ double2 smem_raw[];
+  const int N = p.fft_size, NC = N / 2;
+  cplx *S = smem_raw;
+  double *win = reinterpret_cast<double *>(S + wb_fft_slots(NC));  // N doubles
+  double *red = win + N;                                          // 128
+  double *W = reinterpret_cast<double *>(S);
+  const int frame = blockIdx.x;
+  const double f0 = p.f0[frame];
+  if (f0 == 0.0) {
+    if (threadIdx.x == 0) p.ap0[frame] = 0.0;
+    return;
+  }
+  const double cf0 = f0 > p.lowest_f0 ? f0 : p.lowest_f0;
+  const int wlen = d4c_windowed_waveform(p.x, p.x_length, p.fs, cf0, p.tpos[frame], D4C_BLACKMAN, 3.0,
+                                         p.noise + p.noise_off[frame], win, red,
+                                         [&](int j) -> double & { return W[wb_didx(j)]; });
+  for (int j = wlen + threadIdx.x; j < N; j += blockDim.x) W[wb_didx(j)] = 0.0;
+  __syncthreads();
+  // power in (boundary0, boundary1] and (boundary0, boundary2]; bins above N/2 count as zero
+  double a = 0.0, b = 0.0;
+  const int b0 = p.boundary0, b1 = p.boundary1, b2 = p.boundary2;
+  // wb_rfft's emit runs once per k on some thread: accumulate per thread, reduce afterwards
+  wb_rfft<1>(S, NC, p.log2nc, p.twiddle, [&](int k, cplx X) {
+    if (k > b0 && k <= b2) {
+      const double pw = X.x * X.x + X.y * X.y;
+      b += pw;
+      if (k <= b1) a += pw;
+    }
+  });
+  wb_block_sum2(a, b, red);
+  if (threadIdx.x == 0) p.ap0[frame] = a / b;
+}
+
+// ---- order statistic: sum of the m smallest of v[0..n) (d4c.cpp:494-499) ---------------------
+// hist: 256 ints, ctl: 4 unsigned long long, red: reduction scratch.  Returns the sum of the m
+// smallest values to all threads.  Values must be non-negative.
+__device__ inline double d4c_sum_smallest(const double *v, int n, int m, int *hist, unsigned long long *ctl,
+                                          double *red) {
+  unsigned long long prefix = 0ull, mask = 0ull;
+  if (threadIdx.x == 0) ctl[1] = (unsigned long long)m;  // remaining rank (1-based)
+  for (int pass = 0; pass < 8; ++pass) {
+    const int shift = 56 - 8 * pass;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const unsigned long long key = (unsigned long long)__double_as_longlong(v[i]);
+      if ((key & mask) == prefix) atomicAdd(&hist[(int)((key >> shift) & 255ull)], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const int lane = threadIdx.x;
+      int c = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) c += hist[lane * 8 + q];
+      int incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const int excl = incl - c;
+      const int remaining = (int)ctl[1];
+      if (remaining > excl && remaining <= incl) {
+        int r = remaining - excl;
+        int d = lane * 8;
+        for (int q = 0; q < 8; ++q) {
+          const int h = hist[lane * 8 + q];
+          if (r <= h) { d = lane * 8 + q; break; }
+          r -= h;
+        }
+        ctl[0] = (unsigned long long)d;
+        ctl[2] = (unsigned long long)r;
+      }
+    }
+    __syncthreads();
+    prefix |= ctl[0] << shift;
+    mask |= 255ull << shift;
+    __syncthreads();
+    if (threadIdx.x == 0) ctl[1] = ctl[2];
+  }
+  // prefix is now the bit pattern of the m-th smallest value
+  const double t = __longlong_as_double((long long)prefix);
+  double s = 0.0, cnt = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double x = v[i];
+    if (x < t) { s += x; cnt += 1.0; }
+  }
+  wb_block_sum2(s, cnt, red);
+  return s + (m - cnt) * t;
+}
+
+// ---- body (d4c.cpp:308-503 + :155-168) -------------------------------------------------------
+struct BodyParams {
+  const double *x; int x_length;
+  const double *tpos; const double *f0; const double *ap0; int f0_length;
+  int fs; int fft_size_d4c; int log2n; double threshold;
+  int n_ap; int window_length;         // Nuttall window of the band analysis
+  const double *nuttall;               // device, window_length doubles
+  const cplx *tw_n;                    // fft_size_d4c entries (real transforms)
+  const cplx *tw_2n;                   // 2*fft_size_d4c entries (complex transform of size N)
+  const double *noise; const unsigned long long *noise_off;
+  int out_fft_size;                    // bins of the output rows
+  double *ap;                          // [f0_length][out_fft_size/2+1]
+  int seg_capacity;
+  int *error_flag;
+};
+
+__global__ void __launch_bounds__(512) d4c_body_kernel(BodyParams p) {
+  extern __shared__ double2 smem_raw[];
+  const int N = p.fft_size_d4c, NC = N / 2, bins = NC + 1;
+  const int binsp = (bins + 1) & ~1;  // keep 16-byte alignment
+  cplx *S = smem_raw;                                            // slots for an N-point complex FFT
+  double *SC = reinterpret_cast<double *>(S + wb_fft_slots(N));   // static centroid / group delay
+  double *SP = SC + binsp;                                        // smoothed power | window scratch (with SG)
+  double *SG = SP + binsp;                                        // smoothed group delay | band power
+  double *seg = SG + binsp;                                       // seg_capacity
+  double *red = seg + p.seg_capacity;                             // 1024 + 64
+  int *hist = reinterpret_cast<int *>(red + 1088);                // 256 ints
+  unsigned long long *ctl = reinterpret_cast<unsigned long long *>(hist + 256);  // 4
+  double *coarse = reinterpret_cast<double *>(ctl + 4);           // D4C_MAX_AP + 2
+  double *W = reinterpret_cast<double *>(S);
+  double *win = SP;  // SP..SG: >= N doubles of scratch while neither is live
+
+  const int frame = blockIdx.x;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const double f0_in = p.f0[frame];
+  if (f0_in == 0 || p.ap0[frame] <= p.threshold) return;  // row already initialised (d4c.cpp:146)
+  const double f0 = f0_in > WB_FLOOR_F0_D4C ? f0_in : WB_FLOOR_F0_D4C;
+  const int fs = p.fs;
+  const double pos = p.tpos[frame];
+  const double *noise = p.noise + p.noise_off[frame];
+  const int log2n = p.log2n;
+
+  // ---- static centroid: two windows at pos -/+ 0.25/f0 (d4c.cpp:339-405)
+  // The reference transforms w[n] and (n+1) w[n] separately; both are real, so one complex
+  // transform of z[n] = w[n] + i (n+1) w[n] yields both spectra.
+  for (int c = 0; c < 2; ++c) {
+    const double cpos = (c == 0) ? pos - 0.25 / f0 : pos + 0.25 / f0;
+    const int wlen = d4c_windowed_waveform(p.x, p.x_length, fs, f0, cpos, D4C_BLACKMAN, 4.0, noise, win, red,
+                                           [&](int j) -> double & { return S[wb_sidx(j)].x; });
+    noise += wlen;
+    double pw = 0.0;
+    for (int j = tid; j < wlen; j += nt) { const double v = S[wb_sidx(j)].x; pw += v * v; }
+    const double power = sqrt(wb_block_sum(pw, red));
+    for (int j = tid; j < N; j += nt) {
+      cplx z = make_double2(0.0, 0.0);
+      if (j < wlen) { z.x = S[wb_sidx(j)].x / power; z.y = z.x * (j + 1.0); }
+      S[wb_sidx(j)] = z;
+    }
+    __syncthreads();
+    wb_cfft_dif<1>(S, N, log2n, p.tw_2n, 2 * N);
+    for (int k = tid; k <= NC; k += nt) {
+      const cplx zk = S[wb_sidx(wb_brev(k, log2n))];
+      const cplx zc = S[wb_sidx(wb_brev((N - k) & (N - 1), log2n))];
+      const double x1r = 0.5 * (zk.x + zc.x), x1i = 0.5 * (zk.y - zc.y);   // spectrum of w
+      const double x2r = 0.5 * (zk.y + zc.y), x2i = -0.5 * (zk.x - zc.x);  // spectrum of (n+1) w
+      const double cen = x2r * x1r + x1i * x2i;  // d4c.cpp:400
+      SC[k] = (c == 0) ? cen : SC[k] + cen;
+    }
+    __syncthreads();
+  }
+  wb_dc_correction(SC, f0, fs, N);
+
+  // ---- smoothed power spectrum (d4c.cpp:411-434)
+  {
+    const int wlen = d4c_windowed_waveform(p.x, p.x_length, fs, f0, pos, D4C_HANNING, 4.0, noise, win, red,
+                                           [&](int j) -> double & { return W[wb_didx(j)]; });
+    for (int j = wlen + tid; j < N; j += nt) W[wb_didx(j)] = 0.0;
+    __syncthreads();
+    // `win` (= SP..SG) is dead from here on
+    wb_rfft<1>(S, NC, log2n - 1, p.tw_n, [&](int k, cplx X) { SP[k] = X.x * X.x + X.y * X.y; });
+    wb_dc_correction(SP, f0, fs, N);
+    if (!wb_linear_smoothing(SP, SP, f0, fs, N, seg, p.seg_capacity, red)) {
+      if (tid == 0) atomicExch(p.error_flag, WB_ERR_UNSUPPORTED);
+      return;
+    }
+  }
+
+  // ---- static group delay (d4c.cpp:440-460)
+  for (int k = tid; k < bins; k += nt) SC[k] = SC[k] / SP[k];
+  __syncthreads();
+  wb_linear_smoothing(SC, SC, f0 / 2.0, fs, N, seg, p.seg_capacity, red);
+  wb_linear_smoothing(SC, SG, f0, fs, N, seg, p.seg_capacity, red);
+  for (int k = tid; k < bins; k += nt) SC[k] -= SG[k];
+  __syncthreads();
+
+  // ---- coarse aperiodicity per 3 kHz band (d4c.cpp:466-503)
+  const int wl = p.window_length, hwl = wl / 2;
+  const int boundary = wb_round(N * 8.0 / wl);
+  const int m_small = bins - boundary - 1;  // cumulative-sum index bins - boundary - 2
+  for (int b = 0; b < p.n_ap; ++b) {
+    const int center = static_cast<int>(WB_FREQ_INTERVAL * (b + 1) * N / fs);
+    for (int j = tid; j < N; j += nt)
+      W[wb_didx(j)] = (j < wl) ? SC[center - hwl + j] * __ldg(&p.nuttall[j]) : 0.0;
+    __syncthreads();
+    double tot = 0.0;
+    wb_rfft<1>(S, NC, log2n - 1, p.tw_n, [&](int k, cplx X) {
+      const double pw = X.x * X.x + X.y * X.y;
+      SG[k] = pw;
+      tot += pw;
+    });
+    const double total = wb_block_sum(tot, red);
+    const double low = d4c_sum_smallest(SG, bins, m_small, hist, ctl, red);
+    if (tid == 0) {
+      double ca = 10 * log10(low / total);
+      const double rev = (f0 - 100) / 50.0;  // d4c.cpp:325-327
+      ca = ca + rev;
+      coarse[b + 1] = ca < 0.0 ? ca : 0.0;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    coarse[0] = -60.0;                      // d4c.cpp:84
+    coarse[p.n_ap + 1] = -WB_SAFEGUARD;     // d4c.cpp:85
+  }
+  __syncthreads();
+
+  // ---- interp1 to the output bins + 10^(v/20) (d4c.cpp:160-168)
+  const int out_bins = p.out_fft_size / 2 + 1;
+  double *out = p.ap + (size_t)frame * out_bins;
+  const int nk = p.n_ap + 2;
+  for (int i = tid; i < out_bins; i += nt) {
+    const double xi = static_cast<double>(i) * fs / p.out_fft_size;
+    // histc (world_matlabfunctions.cpp:136-156): first knot strictly above xi, clamped to [1, nk-1]
+    int k = 1;
+    while (k < nk - 1) {
+      const double knot = (k == nk - 1) ? fs / 2.0 : k * WB_FREQ_INTERVAL;
+      if (xi < knot) break;
+      ++k;
+    }
+    const double x0 = (k - 1) * WB_FREQ_INTERVAL;
+    const double x1 = (k == nk - 1) ? fs / 2.0 : k * WB_FREQ_INTERVAL;
+    const double s = (xi - x0) / (x1 - x0);
+    const double v = coarse[k - 1] + s * (coarse[k] - coarse[k - 1]);
+    out[i] = pow(10.0, v / 20.0);
+  }
+}
+
+__global__ void fill_kernel(double *__restrict__ p, size_t n, double v) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+int ilog2_exact(int n) {
+  int l = 0;
+  while ((1 << l) < n) ++l;
+  return ((1 << l) == n) ? l : -1;
+}
+
+}  // namespace
+
+int wb_d4c_fft_size(int fs) {  // d4c.cpp:63-64
+  return (int)pow(2.0, 1.0 + (int)(log(4.0 * fs / WB_FLOOR_F0_D4C + 1) / WB_LOG2));
+}
+int wb_d4c_lt_fft_size(int fs) {  // d4c.cpp:101-103
+  return (int)pow(2.0, 1.0 + (int)(log(3.0 * fs / 40.0 + 1) / WB_LOG2));
+}
+int wb_number_of_aperiodicities(int fs) {  // d4c.cpp:65-67, codec.cpp:211-214
+  const double a = fs / 2.0 - WB_FREQ_INTERVAL;
+  return static_cast<int>((WB_UPPER_LIMIT < a ? WB_UPPER_LIMIT : a) / WB_FREQ_INTERVAL);
+}
+
+int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int x_length, const double *d_tpos,
+               const double *d_f0, int f0_length, int out_fft_size, double *d_ap, WbRngState *d_rng,
+               cudaStream_t stream) {
+  if (f0_length <= 0) return WB_OK;
+  const int N = wb_d4c_fft_size(fs), N_lt = wb_d4c_lt_fft_size(fs);
+  const int l = ilog2_exact(N), l_lt = ilog2_exact(N_lt);
+  if (l < 7 || N > 8192 || l_lt < 7 || N_lt > 16384) return WB_ERR_UNSUPPORTED;
+  const int n_ap = wb_number_of_aperiodicities(fs);
+  if (n_ap < 0 || n_ap > D4C_MAX_AP) return WB_ERR_UNSUPPORTED;
+  const int out_bins = out_fft_size / 2 + 1;
+
+  // rows start as 1 - kMySafeGuardMinimum (d4c.cpp:127-132)
+  const size_t n_out = (size_t)f0_length * out_bins;
+  fill_kernel<<<(unsigned)((n_out + 1023) / 1024 < 4096 ? (n_out + 1023) / 1024 : 4096), 256, 0, stream>>>(
+      d_ap, n_out, 1.0 - WB_SAFEGUARD);
+
+  unsigned long long *d_counts = (unsigned long long *)ws->get("d4c_counts", sizeof(unsigned long long) * (f0_length + 1));
+  unsigned long long *d_offsets = (unsigned long long *)ws->get("d4c_offsets", sizeof(unsigned long long) * (f0_length + 1));
+  double *d_ap0 = (double *)ws->get("d4c_ap0", sizeof(double) * f0_length);
+  const unsigned long long max_noise_lt = (unsigned long long)f0_length * N_lt;
+  const unsigned long long max_noise_body = (unsigned long long)f0_length * 3ull * N;
+  double *d_noise = (double *)ws->get("noise", sizeof(double) * (max_noise_body > max_noise_lt ? max_noise_body : max_noise_lt));
+  if (!d_counts || !d_offsets || !d_ap0 || !d_noise) return WB_ERR_CUDA;
+  const cplx *tw_lt = wb_twiddle_table(N_lt);
+  const cplx *tw_n = wb_twiddle_table(N);
+  const cplx *tw_2n = wb_twiddle_table(2 * N);
+  if (!tw_lt || !tw_n || !tw_2n) return WB_ERR_CUDA;
+
+  // Nuttall window of the band analysis (d4c.cpp:69-72, world_common.cpp:118-126), host libm like the reference
+  const int window_length = static_cast<int>(WB_FREQ_INTERVAL * N / fs) * 2 + 1;
+  double *d_nuttall = (double *)ws->get("d4c_nuttall", sizeof(double) * window_length);
+  if (!d_nuttall) return WB_ERR_CUDA;
+  {
+    double *h = (double *)ws->get_pinned("d4c_nuttall_h", sizeof(double) * window_length);
+    if (!h) return WB_ERR_CUDA;
+    for (int i = 0; i < window_length; ++i) {
+      const double tmp = i / (window_length - 1.0);
+      h[i] = 0.355768 - 0.487396 * cos(2.0 * WB_PI * tmp) + 0.144232 * cos(4.0 * WB_PI * tmp) -
+             0.012604 * cos(6.0 * WB_PI * tmp);
+    }
+    WB_CUDA_CHECK(cudaMemcpyAsync(d_nuttall, h, sizeof(double) * window_length, cudaMemcpyHostToDevice, stream));
+  }
+
+  const int cb = (f0_length + 255) / 256;
+  // ---- Love Train
+  lt_count_kernel<<<cb, 256, 0, stream>>>(d_f0, f0_length, fs, 40.0, d_counts);
+  int rc = wb_exclusive_scan_u64(d_counts, d_offsets, f0_length, stream);
+  if (rc) return rc;
+  if ((rc = wb_rng_fill(d_rng, d_offsets + f0_length, max_noise_lt, d_noise, stream))) return rc;
+  {
+    LtParams p;
+    p.x = d_x; p.x_length = x_length; p.tpos = d_tpos; p.f0 = d_f0; p.f0_length = f0_length;
+    p.fs = fs; p.fft_size = N_lt; p.log2nc = l_lt - 1; p.lowest_f0 = 40.0;
+    p.boundary0 = static_cast<int>(ceil(100.0 * N_lt / fs));
+    p.boundary1 = static_cast<int>(ceil(4000.0 * N_lt / fs));
+    p.boundary2 = static_cast<int>(ceil(7900.0 * N_lt / fs));
+    p.twiddle = tw_lt; p.noise = d_noise; p.noise_off = d_offsets; p.ap0 = d_ap0;
+    const size_t smem = sizeof(cplx) * wb_fft_slots(N_lt / 2) + sizeof(double) * (N_lt + 128);
+    WB_CUDA_CHECK(cudaFuncSetAttribute(lt_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lt_frame_kernel<<<f0_length, 256, smem, stream>>>(p);
+    WB_CUDA_CHECK(cudaGetLastError());
+  }
+  if ((rc = wb_rng_advance(d_rng, d_offsets + f0_length, stream))) return rc;
+
+  // ---- body
+  body_count_kernel<<<cb, 256, 0, stream>>>(d_f0, d_ap0, f0_length, fs, threshold, d_counts);
+  if ((rc = wb_exclusive_scan_u64(d_counts, d_offsets, f0_length, stream))) return rc;
+  if ((rc = wb_rng_fill(d_rng, d_offsets + f0_length, max_noise_body, d_noise, stream))) return rc;
+  {
+    BodyParams p;
+    p.x = d_x; p.x_length = x_length; p.tpos = d_tpos; p.f0 = d_f0; p.ap0 = d_ap0; p.f0_length = f0_length;
+    p.fs = fs; p.fft_size_d4c = N; p.log2n = l; p.threshold = threshold;
+    p.n_ap = n_ap; p.window_length = window_length; p.nuttall = d_nuttall;
+    p.tw_n = tw_n; p.tw_2n = tw_2n; p.noise = d_noise; p.noise_off = d_offsets;
+    p.out_fft_size = out_fft_size; p.ap = d_ap;
+    p.seg_capacity = N / 2 + N / 4 + 8;
+    p.error_flag = ws->error_flag();
+    const int binsp = ((N / 2 + 1) + 1) & ~1;
+    const size_t smem = sizeof(cplx) * wb_fft_slots(N) + sizeof(double) * (3 * binsp + p.seg_capacity + 1088) +
+                        sizeof(int) * 256 + sizeof(unsigned long long) * 4 + sizeof(double) * (D4C_MAX_AP + 2);
+    WB_CUDA_CHECK(cudaFuncSetAttribute(d4c_body_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    d4c_body_kernel<<<f0_length, 512, smem, stream>>>(p);
+    WB_CUDA_CHECK(cudaGetLastError());
+  }
+  return wb_rng_advance(d_rng, d_offsets + f0_length, stream);
+}

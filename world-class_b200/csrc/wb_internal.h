@@ -34,3 +34,11 @@ int wb_cheaptrick_run(WbWorkspace *ws, int fs, int fft_size, double q1, double f
 
 // stand-alone batched transforms (wb_fftapi.cu); kind 0 r2c, 1 c2r, 2 c2c fwd, 3 c2c bwd
 int wb_fft_batch_dev(int kind, const void *d_in, int n, int batch, void *d_out, cudaStream_t stream);
+
+// D4C (wb_d4c.cu)
+int wb_d4c_fft_size(int fs);
+int wb_d4c_lt_fft_size(int fs);
+int wb_number_of_aperiodicities(int fs);
+int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int x_length, const double *d_tpos,
+               const double *d_f0, int f0_length, int out_fft_size, double *d_ap, WbRngState *d_rng,
+               cudaStream_t stream);
