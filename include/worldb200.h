@@ -107,6 +107,19 @@ int wb_d4c_compute(wb_d4c_t *h, const double *x, int x_length, const double *tem
 int wb_d4c_compute_dev(wb_d4c_t *h, const double *d_x, int x_length, const double *d_temporal_positions,
                        const double *d_f0, int f0_length, int fft_size, double *d_aperiodicity, void *stream);
 
+/* ---- Synthesis (include/synthesis.hpp:29-51) ------------------------------------------ */
+int wb_synthesis_create(int fs, int fft_size, double frame_period_ms, wb_synthesis_t **out); /* src/synthesis.cpp:30-56 */
+void wb_synthesis_destroy(wb_synthesis_t *h);
+/* src/synthesis.cpp:77-177; `out` (out_length samples) is fully overwritten */
+int wb_synthesis_compute(wb_synthesis_t *h, const double *f0, int f0_length,
+                         const double *const *spectrogram, const double *const *aperiodicity,
+                         int out_length, double *out);
+/* f0_upper_bound: host-known upper bound of max(f0) (sizes the pulse buffers without a
+ * device->host round trip); <= 0 = unknown (one stream synchronisation inside the call). */
+int wb_synthesis_compute_dev(wb_synthesis_t *h, const double *d_f0, int f0_length,
+                             const double *d_spectrogram, const double *d_aperiodicity,
+                             int out_length, double *d_out, double f0_upper_bound, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -85,6 +85,10 @@ def _declare(L):
         "wb_cheaptrick_compute": (ci, [vp, vp, ci, vp, vp, ci, vp]),
         "wb_cheaptrick_compute_dev": (ci, [vp, vp, ci, vp, vp, ci, vp, vp]),
         "wb_get_number_of_aperiodicities": (ci, [ci]),
+        "wb_synthesis_create": (ci, [ci, ci, cd, ctypes.POINTER(vp)]),
+        "wb_synthesis_destroy": (None, [vp]),
+        "wb_synthesis_compute": (ci, [vp, vp, ci, vp, vp, ci, vp]),
+        "wb_synthesis_compute_dev": (ci, [vp, vp, ci, vp, vp, ci, vp, cd, vp]),
         "wb_d4c_create": (ci, [ci, ctypes.POINTER(D4COption), ctypes.POINTER(vp)]),
         "wb_d4c_destroy": (None, [vp]),
         "wb_d4c_compute": (ci, [vp, vp, ci, vp, vp, ci, ci, vp]),
@@ -235,3 +239,33 @@ class D4C:
         _check(lib().wb_d4c_compute(self._h, x.ctypes.data, len(x), tpos.ctypes.data, f0.ctypes.data,
                                     len(f0), int(fft_size), rows.ctypes.data), "wb_d4c_compute")
         return ap
+
+
+# ---- Synthesis (include/synthesis.hpp:29-51) -----------------------------------------------
+class Synthesis:
+    def __init__(self, fs, fft_size, frame_period):
+        self._h = ctypes.c_void_p()
+        self.fs, self.fft_size, self.frame_period = int(fs), int(fft_size), float(frame_period)
+        _check(lib().wb_synthesis_create(self.fs, self.fft_size, self.frame_period, ctypes.byref(self._h)),
+               "wb_synthesis_create")
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.wb_synthesis_destroy(self._h)
+            self._h = None
+
+    def compute(self, f0, spectrogram, aperiodicity, out_length):
+        """-> waveform of out_length samples"""
+        f0 = _f64(f0)
+        sp, ap = _f64(spectrogram), _f64(aperiodicity)
+        assert sp.shape == ap.shape == (len(f0), self.fft_size // 2 + 1)
+        out = np.empty(int(out_length), dtype=np.float64)
+        rs, ra = _row_pointers(sp), _row_pointers(ap)
+        _check(lib().wb_synthesis_compute(self._h, f0.ctypes.data, len(f0), rs.ctypes.data, ra.ctypes.data,
+                                          len(out), out.ctypes.data), "wb_synthesis_compute")
+        return out
+
+
+def synthesis_length(f0_length, frame_period, fs):
+    """test/test.cpp:362-363"""
+    return int((f0_length - 1) * frame_period / 1000.0 * fs) + 1

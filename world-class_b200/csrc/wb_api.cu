@@ -79,6 +79,13 @@ struct wb_d4c {
   WbWorkspace ws;
 };
 
+struct wb_synthesis {
+  int fs;
+  int fft_size;
+  double frame_period_ms;
+  WbWorkspace ws;
+};
+
 extern "C" {
 
 int wb_init(int device) {
@@ -283,6 +290,51 @@ int wb_d4c_compute(wb_d4c_t *h, const double *x, int x_length, const double *tpo
   if (!d_ap) return WB_ERR_CUDA;
   if ((rc = wb_d4c_compute_dev(h, d_x, x_length, d_t, d_f, f0_length, fft_size, d_ap, st))) return rc;
   if ((rc = rows_to_host(&h->ws, d_ap, f0_length, bins, aperiodicity, st))) return rc;
+  return h->ws.read_error_flag(st);
+}
+
+// ---- Synthesis ---------------------------------------------------------------------------
+int wb_synthesis_create(int fs, int fft_size, double frame_period_ms, wb_synthesis_t **out) {
+  if (!out || fs <= 0 || fft_size <= 0 || !(frame_period_ms > 0)) return WB_ERR_ARG;
+  int rc = ctx_init();
+  if (rc) return rc;
+  wb_synthesis *h = new (std::nothrow) wb_synthesis();
+  if (!h) return WB_ERR_ARG;
+  h->fs = fs; h->fft_size = fft_size; h->frame_period_ms = frame_period_ms;
+  *out = h;
+  return WB_OK;
+}
+
+void wb_synthesis_destroy(wb_synthesis_t *h) { delete h; }
+
+int wb_synthesis_compute_dev(wb_synthesis_t *h, const double *d_f0, int f0_length, const double *d_sp,
+                             const double *d_ap, int out_length, double *d_out, double f0_upper_bound,
+                             void *stream) {
+  if (!h || !d_f0 || !d_sp || !d_ap || !d_out || f0_length < 2 || out_length < 0) return WB_ERR_ARG;
+  return wb_synthesis_run(&h->ws, h->fs, h->fft_size, h->frame_period_ms, d_f0, f0_length, d_sp, d_ap,
+                          out_length, d_out, f0_upper_bound, wb_rng_global_state(), pick_stream(stream));
+}
+
+int wb_synthesis_compute(wb_synthesis_t *h, const double *f0, int f0_length, const double *const *spectrogram,
+                         const double *const *aperiodicity, int out_length, double *out) {
+  if (!h || !f0 || !spectrogram || !aperiodicity || !out || f0_length < 2 || out_length < 0) return WB_ERR_ARG;
+  if (out_length == 0) return WB_OK;
+  cudaStream_t st = g_stream;
+  const int bins = h->fft_size / 2 + 1;
+  double max_f0 = 0.0;
+  for (int i = 0; i < f0_length; ++i) if (f0[i] > max_f0) max_f0 = f0[i];
+  double *d_f;
+  int rc;
+  if ((rc = vec_to_device(&h->ws, "h_f0", f0, f0_length, &d_f, st))) return rc;
+  double *d_sp = (double *)h->ws.get("h_sp", sizeof(double) * (size_t)f0_length * bins);
+  double *d_ap = (double *)h->ws.get("h_ap", sizeof(double) * (size_t)f0_length * bins);
+  double *d_out = (double *)h->ws.get("h_out", sizeof(double) * (size_t)out_length);
+  if (!d_sp || !d_ap || !d_out) return WB_ERR_CUDA;
+  if ((rc = rows_to_device(&h->ws, "rows_stage_sp", spectrogram, f0_length, bins, d_sp, st))) return rc;
+  if ((rc = rows_to_device(&h->ws, "rows_stage_ap", aperiodicity, f0_length, bins, d_ap, st))) return rc;
+  if ((rc = wb_synthesis_compute_dev(h, d_f, f0_length, d_sp, d_ap, out_length, d_out, max_f0 + 1.0, st))) return rc;
+  WB_CUDA_CHECK(cudaMemcpyAsync(out, d_out, sizeof(double) * out_length, cudaMemcpyDeviceToHost, st));
+  WB_CUDA_CHECK(cudaStreamSynchronize(st));
   return h->ws.read_error_flag(st);
 }
 

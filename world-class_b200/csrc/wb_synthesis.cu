@@ -1,0 +1,576 @@
+// WORLD synthesis: time base -> pulse list -> one impulse response per pulse (7 FFTs in
+// shared memory) -> deterministic overlap-add.
+//
+// Reference: /root/reference/src/synthesis.cpp
+//   ctor :30-56, compute :77-177, getTimeBase :180-223, getTemporalParametersForTimeBase
+//   :225-243, getPulseLocationsForTimeBase :245-288, getDCRemover :290-303,
+//   getOneFrameSegment :308-344, getSpectralEnvelope :346-370, getAperiodicRatio :372-393,
+//   getPeriodicResponse :403-437, getSpectrumWithFractionalTimeShift :443-457,
+//   removeDCComponent :459-474, getAperiodicResponse :479-512, getNoiseSpectrum :514-530;
+//   MinimumPhaseAnalysis::compute /root/reference/src/world_common.cpp:192-233.
+//
+// The reference's running phase sum (synthesis.cpp:257-264) is a sequential fp64
+// recurrence whose rounding decides pulse sample indices.  phase_scan_kernel reproduces
+// it BIT-EXACTLY in parallel: inside one binade every addition rounds to a multiple of a
+// fixed ulp, so s <- fl(s + a) is an integer map S -> S + c(parity(S)) (the parity only
+// matters for round-half-even ties); such maps compose associatively and are scanned.
+// Binade crossings are detected and replayed with a genuine fp64 add.
+#include "wb_internal.h"
+#include "wb_fft.cuh"
+
+#include <math.h>
+#include <vector>
+
+namespace {
+
+// ---- K1: per-sample phase increment and VUV (synthesis.cpp:180-243) --------------------------
+__global__ void timebase_kernel(const double *__restrict__ f0, int f0_length, int fs, double frame_period,
+                                double lowest_f0, int y_length, double *__restrict__ incr,
+                                unsigned char *__restrict__ vuv) {
+  const int ii = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ii >= y_length) return;
+  const double t = ii / (double)fs;
+  // histc over coarse_time_axis[k] = k * frame_period, k = 0..f0_length:
+  // index = first k with coarse_time_axis[k] > t, clamped to [1, f0_length]
+  int k = (int)(t / frame_period) + 1;
+  if (k < 1) k = 1;
+  if (k > f0_length) k = f0_length;
+  while (k > 1 && !(t >= (k - 1) * frame_period)) --k;           // ensure x[k-1] <= t
+  while (k < f0_length && !(t < k * frame_period)) ++k;           // ensure t < x[k] (or clamp)
+  const double x0 = (k - 1) * frame_period, x1 = k * frame_period;
+  const double s = (t - x0) / (x1 - x0);
+  auto coarse_f0 = [&](int i) -> double {
+    if (i < f0_length) { const double v = f0[i]; return (v < lowest_f0) ? 0.0 : v; }
+    const double a = f0[f0_length - 1], b = f0[f0_length - 2];
+    const double ca = (a < lowest_f0) ? 0.0 : a, cb = (b < lowest_f0) ? 0.0 : b;
+    return ca * 2 - cb;
+  };
+  auto coarse_vuv = [&](int i) -> double {
+    if (i < f0_length) { const double v = f0[i]; return (v < lowest_f0) ? 0.0 : 1.0; }
+    const double a = f0[f0_length - 1], b = f0[f0_length - 2];
+    const double va = (a < lowest_f0) ? 0.0 : 1.0, vb = (b < lowest_f0) ? 0.0 : 1.0;
+    return va * 2 - vb;
+  };
+  const double f_lo = coarse_f0(k - 1), f_hi = coarse_f0(k);
+  const double v_lo = coarse_vuv(k - 1), v_hi = coarse_vuv(k);
+  const double fi = f_lo + s * (f_hi - f_lo);
+  const double vi = v_lo + s * (v_hi - v_lo);
+  const bool voiced = vi > 0.5;
+  const double f = voiced ? fi : WB_DEFAULT_F0;
+  const double two_pi = 2.0 * WB_PI;
+  const double const_val = two_pi / fs;
+  incr[ii] = f * const_val;
+  vuv[ii] = voiced ? 1 : 0;
+}
+
+// ---- K2: exact parallel emulation of the sequential fp64 running sum -------------------------
+#define PS_THREADS 1024
+#define PS_PER 8
+#define PS_CHUNK (PS_THREADS * PS_PER)
+
+struct IncFn { unsigned long long ce, co; };  // increment if S is even / odd
+
+__device__ __forceinline__ IncFn ps_compose(IncFn f, IncFn g) {  // apply f, then g
+  IncFn h;
+  h.ce = f.ce + ((f.ce & 1ull) ? g.co : g.ce);
+  h.co = f.co + (((f.co + 1ull) & 1ull) ? g.co : g.ce);
+  return h;
+}
+
+// increment function of adding `a` to a sum in binade e (ulp 2^(e-52)); flags elements that
+// cannot be handled inside the binade model by returning a huge increment.
+__device__ __forceinline__ IncFn ps_incfn(double a, int e) {
+  const unsigned long long HUGE_INC = 1ull << 53;
+  IncFn f;
+  const long long bits = __double_as_longlong(a);
+  const int ea = (int)((bits >> 52) & 0x7ff) - 1023;
+  if (!(a > 0.0) || ea == -1023 || ea == 1024) { f.ce = f.co = HUGE_INC; return f; }  // <=0, subnormal, inf/nan
+  const unsigned long long m = ((unsigned long long)bits & 0xfffffffffffffull) | (1ull << 52);
+  const int shift = e - ea;
+  if (shift < 0) { f.ce = f.co = HUGE_INC; return f; }
+  if (shift == 0) { f.ce = f.co = m; return f; }
+  if (shift > 62) { f.ce = f.co = 0ull; return f; }
+  const unsigned long long q = m >> shift;
+  const unsigned long long rem = m & ((1ull << shift) - 1ull);
+  const unsigned long long half = 1ull << (shift - 1);
+  if (rem > half) { f.ce = f.co = q + 1ull; }
+  else if (rem < half) { f.ce = f.co = q; }
+  else { f.ce = q + (q & 1ull); f.co = q + 1ull - (q & 1ull); }  // tie: round half to even
+  return f;
+}
+
+__global__ void __launch_bounds__(PS_THREADS) phase_scan_kernel(const double *__restrict__ incr, int n,
+                                                                double *__restrict__ wrap_phase) {
+  __shared__ IncFn warp_fn[32];
+  __shared__ int s_first_bad;
+  __shared__ double s_sum;   // current running sum (exact double)
+  __shared__ int s_pos;      // next element to process
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double two_pi = 2.0 * WB_PI;
+  if (tid == 0) {
+    const double s0 = incr[0];  // total_phase[0] = interpolated_f0[0] * const_val
+    wrap_phase[0] = fmod(s0, two_pi);
+    s_sum = s0;
+    s_pos = 1;
+  }
+  __syncthreads();
+  while (true) {
+    const int pos = s_pos;
+    if (pos >= n) break;
+    const double sum = s_sum;
+    const long long sbits = __double_as_longlong(sum);
+    const int e = (int)((sbits >> 52) & 0x7ff) - 1023;
+    const bool state_ok = (sum > 0.0) && e != -1023 && e != 1024;
+    if (!state_ok) {
+      // degenerate running sum (zero/negative/subnormal/non-finite): genuine sequential add
+      if (tid == 0) {
+        const double s = sum + incr[pos];
+        wrap_phase[pos] = fmod(s, two_pi);
+        s_sum = s;
+        s_pos = pos + 1;
+      }
+      __syncthreads();
+      continue;
+    }
+    const unsigned long long S0 = ((unsigned long long)sbits & 0xfffffffffffffull) | (1ull << 52);
+    if (tid == 0) s_first_bad = 0x7fffffff;
+    // local composition
+    const int base = pos + tid * PS_PER;
+    IncFn fn[PS_PER];
+    IncFn acc; acc.ce = 0ull; acc.co = 0ull;
+#pragma unroll
+    for (int q = 0; q < PS_PER; ++q) {
+      const int i = base + q;
+      if (i < n) fn[q] = ps_incfn(incr[i], e);
+      else { fn[q].ce = 0ull; fn[q].co = 0ull; }
+      acc = ps_compose(acc, fn[q]);
+    }
+    // block exclusive scan of the composed functions
+    IncFn incl = acc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      IncFn t;
+      t.ce = __shfl_up_sync(0xffffffffu, incl.ce, o);
+      t.co = __shfl_up_sync(0xffffffffu, incl.co, o);
+      if (lane >= o) incl = ps_compose(t, incl);
+    }
+    if (lane == 31) warp_fn[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      IncFn w = warp_fn[lane];
+      IncFn wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        IncFn t;
+        t.ce = __shfl_up_sync(0xffffffffu, wi.ce, o);
+        t.co = __shfl_up_sync(0xffffffffu, wi.co, o);
+        if (lane >= o) wi = ps_compose(t, wi);
+      }
+      warp_fn[lane] = wi;  // inclusive over warps
+    }
+    __syncthreads();
+    // exclusive prefix function for this thread = (warps before) then (lanes before in warp)
+    IncFn pre; pre.ce = 0ull; pre.co = 0ull;
+    if (warp > 0) pre = warp_fn[warp - 1];
+    {
+      IncFn lane_excl;
+      lane_excl.ce = __shfl_up_sync(0xffffffffu, incl.ce, 1);
+      lane_excl.co = __shfl_up_sync(0xffffffffu, incl.co, 1);
+      if (lane > 0) pre = ps_compose(pre, lane_excl);
+    }
+    unsigned long long S = S0 + ((S0 & 1ull) ? pre.co : pre.ce);
+    const unsigned long long LIMIT = 1ull << 53;
+    const double ulp = __longlong_as_double((long long)(e - 52 + 1023) << 52);  // 2^(e-52), e-52 > -1023 here
+    const bool ulp_ok = (e - 52) > -1022;
+    int my_bad = 0x7fffffff;
+    if (S >= LIMIT || !ulp_ok) my_bad = base;  // prefix already left the binade
+#pragma unroll
+    for (int q = 0; q < PS_PER; ++q) {
+      const int i = base + q;
+      if (i < n && my_bad == 0x7fffffff) {
+        S += (S & 1ull) ? fn[q].co : fn[q].ce;
+        if (S >= LIMIT) my_bad = i;
+        else wrap_phase[i] = fmod((double)S * ulp, two_pi);
+      }
+    }
+    if (my_bad != 0x7fffffff) atomicMin(&s_first_bad, my_bad);
+    __syncthreads();
+    const int first_bad = s_first_bad;
+    const int chunk_end = min(n, pos + PS_CHUNK);
+    if (first_bad >= chunk_end) {
+      // whole chunk valid: the last thread that owns a valid element publishes the sum
+      const int last = chunk_end - 1;
+      if (last >= base && last < base + PS_PER) { s_sum = (double)S * ulp; s_pos = chunk_end; }
+    } else {
+      // replay element first_bad with a genuine fp64 add on top of the exact sum before it
+      const int owner = (first_bad - pos) / PS_PER;
+      if (tid == owner) {
+        // recompute the sum just before first_bad
+        unsigned long long Sb = S0 + ((S0 & 1ull) ? pre.co : pre.ce);
+        for (int q = 0; q < PS_PER; ++q) {
+          const int i = base + q;
+          if (i >= first_bad) break;
+          Sb += (Sb & 1ull) ? fn[q].co : fn[q].ce;
+        }
+        const double before = (double)Sb * ulp;
+        const double s = before + incr[first_bad];
+        wrap_phase[first_bad] = fmod(s, two_pi);
+        s_sum = s;
+        s_pos = first_bad + 1;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---- K3: pulse detection + ordered compaction (synthesis.cpp:266-281) -------------------------
+#define PD_THREADS 256
+__global__ void pulse_count_kernel(const double *__restrict__ wrap, int y_length,
+                                   unsigned long long *__restrict__ block_counts) {
+  __shared__ int s_cnt;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  const int ii = blockIdx.x * PD_THREADS + threadIdx.x;
+  bool flag = false;
+  if (ii < y_length - 1) flag = fabs(wrap[ii + 1] - wrap[ii]) > WB_PI;
+  const unsigned m = __ballot_sync(0xffffffffu, flag);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(&s_cnt, __popc(m));
+  __syncthreads();
+  if (threadIdx.x == 0) block_counts[blockIdx.x] = (unsigned long long)s_cnt;
+}
+
+__global__ void pulse_write_kernel(const double *__restrict__ wrap, int y_length, int fs,
+                                   const unsigned long long *__restrict__ block_offsets,
+                                   int *__restrict__ pulse_index, double *__restrict__ pulse_shift, int max_pulses) {
+  __shared__ int warp_cnt[PD_THREADS / 32];
+  const int ii = blockIdx.x * PD_THREADS + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  bool flag = false;
+  double w0 = 0.0, w1 = 0.0;
+  if (ii < y_length - 1) {
+    w0 = wrap[ii]; w1 = wrap[ii + 1];
+    flag = fabs(w1 - w0) > WB_PI;
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, flag);
+  if (lane == 0) warp_cnt[warp] = __popc(m);
+  __syncthreads();
+  int before = 0;
+  for (int w = 0; w < warp; ++w) before += warp_cnt[w];
+  if (flag) {
+    const long long slot = (long long)block_offsets[blockIdx.x] + before + __popc(m & ((1u << lane) - 1u));
+    if (slot < max_pulses) {
+      const double two_pi = 2.0 * WB_PI;
+      const double y1 = w0 - two_pi;
+      const double y2 = w1;
+      const double x = -y1 / (y2 - y1);
+      pulse_index[slot] = ii;
+      pulse_shift[slot] = x / fs;
+    }
+  }
+}
+
+// total number of pulses and of randn() calls (sum of noise_size = idx[P-1] - idx[0])
+__global__ void pulse_finalize_kernel(const unsigned long long *__restrict__ block_offsets, int n_blocks,
+                                      const int *__restrict__ pulse_index, int max_pulses,
+                                      int *__restrict__ n_pulses, unsigned long long *__restrict__ noise_count,
+                                      int *__restrict__ error_flag) {
+  unsigned long long P = block_offsets[n_blocks];
+  if (P > (unsigned long long)max_pulses) { P = max_pulses; atomicExch(error_flag, WB_ERR_UNSUPPORTED); }
+  *n_pulses = (int)P;
+  *noise_count = (P >= 2) ? (unsigned long long)(pulse_index[P - 1] - pulse_index[0]) : 0ull;
+}
+
+// ---- K5: impulse response per pulse -----------------------------------------------------------
+struct RespParams {
+  const double *sp; const double *ap; int f0_length;
+  int fs; int fft_size; int log2n; double frame_period;
+  const int *pulse_index; const double *pulse_shift; const unsigned char *vuv;
+  const int *n_pulses;
+  const double *noise;           // randn stream starting at the first pulse
+  const double *dc_remover;      // fft_size doubles (only the first half is used, Q9)
+  const cplx *tw_n;              // fft_size entries
+  const cplx *tw_2n;             // 2*fft_size entries
+  double *response;              // [max_resp_pulses][fft_size]
+  int max_resp_pulses;
+  int *error_flag;
+};
+
+// MinimumPhaseAnalysis::compute (world_common.cpp:192-233).  On entry the packed real view W of
+// S holds log_spectrum[0..NC] (this function mirrors it); on exit MP[k], k = 0..NC, holds the
+// minimum phase spectrum.  S needs wb_fft_slots(N) slots.
+__device__ inline void minimum_phase(cplx *S, cplx *MP, int N, int log2n, const cplx *tw_n, const cplx *tw_2n) {
+  const int NC = N / 2;
+  double *W = reinterpret_cast<double *>(S);
+  for (int i = NC + 1 + threadIdx.x; i < N; i += blockDim.x) W[wb_didx(i)] = W[wb_didx(N - i)];
+  __syncthreads();
+  // "inverse_fft" is a forward r2c in the reference; sign flips / doubling at :203-209
+  wb_rfft<1>(S, NC, log2n - 1, tw_n, [&](int k, cplx X) {
+    if (k == 0 || k == NC) MP[k] = make_double2(X.x, X.y * -1.0);
+    else MP[k] = make_double2(X.x * 2.0, X.y * -2.0);
+  });
+  for (int i = threadIdx.x; i < N; i += blockDim.x) S[wb_sidx(i)] = (i <= NC) ? MP[i] : make_double2(0.0, 0.0);
+  __syncthreads();
+  wb_cfft_dif<1>(S, N, log2n, tw_2n, 2 * N);  // c2c FFT_FORWARD
+  for (int k = threadIdx.x; k <= NC; k += blockDim.x) {
+    const cplx v = S[wb_sidx(wb_brev(k, log2n))];
+    const double tmp = exp(v.x / N);
+    double sn, cs;
+    sincos(v.y / N, &sn, &cs);
+    MP[k] = make_double2(tmp * cs, tmp * sn);
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) response_kernel(RespParams p) {
+  extern __shared__ double2 smem_raw[];
+  const int N = p.fft_size, NC = N / 2, bins = NC + 1;
+  const int binsp = (bins + 1) & ~1;
+  cplx *S = smem_raw;                         // wb_fft_slots(N)
+  cplx *MP = S + wb_fft_slots(N);             // bins
+  cplx *NS = MP + binsp;                      // bins: noise spectrum
+  double *SE = reinterpret_cast<double *>(NS + binsp);  // spectral envelope
+  double *AR = SE + binsp;                    // aperiodic ratio
+  double *PR = AR + binsp;                    // periodic response (N)
+  double *red = PR + N;                       // 128
+  double *W = reinterpret_cast<double *>(S);
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int P = *p.n_pulses;
+  const int log2n = p.log2n;
+  if (P > p.max_resp_pulses) {  // f0 exceeded the caller's bound: refuse rather than overrun
+    if (tid == 0 && blockIdx.x == 0) atomicExch(p.error_flag, WB_ERR_ARG);
+    return;
+  }
+
+  for (int pulse = blockIdx.x; pulse < P; pulse += gridDim.x) {
+    double *resp = p.response + (size_t)pulse * N;
+    const int idx = p.pulse_index[pulse];
+    const int idx_next = p.pulse_index[wb_min_i(P - 1, pulse + 1)];
+    const int noise_size = idx_next - idx;
+    if (noise_size <= 0) {  // last pulse: 0 * periodic + 0 (synthesis.cpp:339-343)
+      for (int i = tid; i < N; i += nt) resp[i] = 0.0;
+      continue;
+    }
+    const double current_vuv = p.vuv[idx] ? 1.0 : 0.0;
+    const double current_time = idx / (double)p.fs;
+    const double frac_shift = p.pulse_shift[pulse];
+
+    // ---- interpolated spectral envelope / aperiodic ratio (synthesis.cpp:346-398)
+    const double tf = current_time / p.frame_period;
+    const int fl = wb_min_i(p.f0_length - 1, (int)floor(tf));
+    const int cl = wb_min_i(p.f0_length - 1, (int)ceil(tf));
+    const double interp = tf - fl;
+    const double *sp_f = p.sp + (size_t)fl * bins, *sp_c = p.sp + (size_t)cl * bins;
+    const double *ap_f = p.ap + (size_t)fl * bins, *ap_c = p.ap + (size_t)cl * bins;
+    for (int k = tid; k < bins; k += nt) {
+      double se, ar;
+      const double af = fmax(0.001, fmin(0.999999999999, ap_f[k]));
+      if (fl == cl) {
+        se = fabs(sp_f[k]);
+        ar = af * af;
+      } else {
+        const double ac = fmax(0.001, fmin(0.999999999999, ap_c[k]));
+        se = (1.0 - interp) * fabs(sp_f[k]) + interp * fabs(sp_c[k]);
+        const double a = (1.0 - interp) * af + interp * ac;
+        ar = a * a;
+      }
+      SE[k] = se;
+      AR[k] = ar;
+    }
+    __syncthreads();
+
+    // ---- periodic response (synthesis.cpp:403-474)
+    const bool periodic_on = !(current_vuv <= 0.5 || AR[0] > 0.999);
+    if (periodic_on) {
+      for (int k = tid; k < bins; k += nt) W[wb_didx(k)] = log(SE[k] * (1.0 - AR[k]) + WB_SAFEGUARD) / 2.0;
+      __syncthreads();
+      minimum_phase(S, MP, N, log2n, p.tw_n, p.tw_2n);
+      const double coefficient = 2.0 * WB_PI * frac_shift * p.fs / N;
+      wb_irfft<-1>(S, NC, log2n - 1, p.tw_n, [&](int k) {
+        const cplx v = MP[k];
+        const double re2 = cos(coefficient * k);
+        const double im2 = sqrt(1.0 - re2 * re2);  // Q8: always >= 0
+        return make_double2(v.x * re2 - v.y * im2, v.x * im2 + v.y * re2);
+      });
+      // fftshift + removeDCComponent (Q9): first half <- -dc * r[i]; second half <- out[i] - dc * r[i]
+      double part = 0.0;
+      for (int i = tid; i < NC; i += nt) part += W[wb_didx(i)];
+      const double dc = wb_block_sum(part, red);
+      for (int i = tid; i < NC; i += nt) {
+        const double rm = -dc * p.dc_remover[i];
+        PR[i] = rm;
+        PR[i + NC] = W[wb_didx(i)] + rm;
+      }
+    } else {
+      for (int i = tid; i < N; i += nt) PR[i] = 0.0;
+    }
+    __syncthreads();
+
+    // ---- aperiodic response (synthesis.cpp:479-530)
+    {
+      const double *nz = p.noise + (idx - p.pulse_index[0]);
+      double part = 0.0;
+      for (int i = tid; i < noise_size; i += nt) part += nz[i];
+      const double average = wb_block_sum(part, red) / noise_size;
+      for (int i = tid; i < N; i += nt) W[wb_didx(i)] = (i < noise_size) ? nz[i] - average : 0.0;
+      __syncthreads();
+      wb_rfft<1>(S, NC, log2n - 1, p.tw_n, [&](int k, cplx X) { NS[k] = X; });
+      if (current_vuv != 0.0) {
+        for (int k = tid; k < bins; k += nt) W[wb_didx(k)] = log(SE[k] * AR[k]) / 2.0;
+      } else {
+        for (int k = tid; k < bins; k += nt) W[wb_didx(k)] = log(SE[k]) / 2.0;
+      }
+      __syncthreads();
+      minimum_phase(S, MP, N, log2n, p.tw_n, p.tw_2n);
+      wb_irfft<-1>(S, NC, log2n - 1, p.tw_n, [&](int k) {
+        const cplx a = MP[k], b = NS[k];
+        return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+      });
+    }
+    // ---- combine (synthesis.cpp:339-343) with the aperiodic fftshift folded in
+    const double sqrt_noise_size = sqrt((double)noise_size);
+    for (int i = tid; i < N; i += nt) {
+      const double aper = W[wb_didx(i < NC ? i + NC : i - NC)];
+      resp[i] = (PR[i] * sqrt_noise_size + aper) / N;
+    }
+    __syncthreads();
+  }
+}
+
+// ---- K6: deterministic overlap-add (synthesis.cpp:118-139) -------------------------------------
+// out[n] = sum over pulses (in pulse order, like the serial reference) of
+// response[p][n - (idx_p - N/2 + 1)].
+__global__ void ola_kernel(const double *__restrict__ response, const int *__restrict__ pulse_index,
+                           const int *__restrict__ n_pulses, int max_resp_pulses, int fft_size, int out_length,
+                           double *__restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= out_length) return;
+  const int P = *n_pulses;
+  if (P > max_resp_pulses) { out[n] = 0.0; return; }
+  const int half = fft_size / 2;
+  // pulses with 0 <= n - (idx - half + 1) < fft_size  <=>  n - half - ... :
+  // idx in [n + half + 1 - fft_size, n + half - 1 + 1 - 0] -> idx >= n - half + 1 ... derive:
+  // j = n - idx + half - 1 in [0, fft_size)  <=>  idx in (n + half - 1 - fft_size, n + half - 1]
+  const int lo_val = n + half - 1 - fft_size;  // exclusive
+  const int hi_val = n + half - 1;             // inclusive
+  // first pulse with idx > lo_val
+  int lo = 0, hi = P;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (pulse_index[mid] > lo_val) hi = mid; else lo = mid + 1;
+  }
+  double acc = 0.0;
+  for (int q = lo; q < P; ++q) {
+    const int idx = pulse_index[q];
+    if (idx > hi_val) break;
+    const int index = idx - half;
+    // the reference skips pulses with index + fft_size < 0 or index + 1 >= out_length entirely
+    if (index + fft_size < 0 || index + 1 >= out_length) continue;
+    const int j = n - index - 1;
+    acc += response[(size_t)q * fft_size + j];
+  }
+  out[n] = acc;
+}
+
+}  // namespace
+
+// Host-side tables: dc_remover (synthesis.cpp:290-303), computed with host libm and the
+// reference's sequential accumulate.
+static void make_dc_remover(int fft_size, std::vector<double> &r) {
+  r.assign(fft_size, 0.0);
+  const double const_val = 2.0 * WB_PI / (1.0 + fft_size);
+  for (int ii = 0; ii < fft_size / 2; ii++) r[ii] = 0.5 - 0.5 * cos(const_val * (ii + 1.0));
+  double acc = 0.0;
+  for (int ii = 0; ii < fft_size / 2; ii++) acc += r[ii];
+  const double dc_component = acc * 2;
+  for (int ii = 0; ii < fft_size / 2; ii++) {
+    r[ii] /= dc_component;
+    r[fft_size - ii - 1] = r[ii];
+  }
+}
+
+// f0_upper_bound: an upper bound of max(f0) known to the host (e.g. Harvest's f0_ceil); <= 0 if
+// unknown, in which case the pulse count is read back (one stream synchronisation).
+int wb_synthesis_run(WbWorkspace *ws, int fs, int fft_size, double frame_period_ms, const double *d_f0,
+                     int f0_length, const double *d_sp, const double *d_ap, int out_length, double *d_out,
+                     double f0_upper_bound, WbRngState *d_rng, cudaStream_t stream) {
+  if (out_length <= 0) return WB_OK;
+  if (f0_length < 2) return WB_ERR_ARG;
+  int log2n = 0;
+  while ((1 << log2n) < fft_size) ++log2n;
+  if ((1 << log2n) != fft_size || fft_size < 128 || fft_size > 8192) return WB_ERR_UNSUPPORTED;
+  const double frame_period = frame_period_ms / 1000.;      // synthesis.cpp:31
+  const double lowest_f0 = fs / fft_size + 1.0;             // synthesis.cpp:97 (integer division)
+  // Every pulse needs a 2 pi phase advance and one sample adds at most 2 pi max(f0, 500) / fs,
+  // so pulses <= out_length * max(f0_max, 500) / fs + 1.  The index/shift lists are sized for
+  // f0 <= fs / 4; the response buffer for the tighter bound (or the exact count).
+  const int max_pulses = out_length / 4 + 16;
+
+  double *d_incr = (double *)ws->get("syn_incr", sizeof(double) * out_length);
+  double *d_wrap = (double *)ws->get("syn_wrap", sizeof(double) * out_length);
+  unsigned char *d_vuv = (unsigned char *)ws->get("syn_vuv", out_length);
+  const int n_blocks = (out_length + PD_THREADS - 1) / PD_THREADS;
+  unsigned long long *d_bc = (unsigned long long *)ws->get("syn_bcount", sizeof(unsigned long long) * (n_blocks + 1));
+  unsigned long long *d_bo = (unsigned long long *)ws->get("syn_boff", sizeof(unsigned long long) * (n_blocks + 1));
+  int *d_pidx = (int *)ws->get("syn_pidx", sizeof(int) * max_pulses);
+  double *d_pshift = (double *)ws->get("syn_pshift", sizeof(double) * max_pulses);
+  int *d_np = (int *)ws->get("syn_np", sizeof(int) * 4);
+  unsigned long long *d_ncount = (unsigned long long *)ws->get("syn_ncount", sizeof(unsigned long long));
+  double *d_noise = (double *)ws->get("noise", sizeof(double) * out_length);
+  double *d_dcr = (double *)ws->get("syn_dcr", sizeof(double) * fft_size);
+  if (!d_incr || !d_wrap || !d_vuv || !d_bc || !d_bo || !d_pidx || !d_pshift || !d_np || !d_ncount || !d_noise ||
+      !d_dcr)
+    return WB_ERR_CUDA;
+  const cplx *tw_n = wb_twiddle_table(fft_size);
+  const cplx *tw_2n = wb_twiddle_table(2 * fft_size);
+  if (!tw_n || !tw_2n) return WB_ERR_CUDA;
+  {
+    double *h = (double *)ws->get_pinned("syn_dcr_h", sizeof(double) * fft_size);
+    if (!h) return WB_ERR_CUDA;
+    std::vector<double> r;
+    make_dc_remover(fft_size, r);
+    for (int i = 0; i < fft_size; ++i) h[i] = r[i];
+    WB_CUDA_CHECK(cudaMemcpyAsync(d_dcr, h, sizeof(double) * fft_size, cudaMemcpyHostToDevice, stream));
+  }
+
+  timebase_kernel<<<(out_length + 255) / 256, 256, 0, stream>>>(d_f0, f0_length, fs, frame_period, lowest_f0,
+                                                                out_length, d_incr, d_vuv);
+  phase_scan_kernel<<<1, PS_THREADS, 0, stream>>>(d_incr, out_length, d_wrap);
+  pulse_count_kernel<<<n_blocks, PD_THREADS, 0, stream>>>(d_wrap, out_length, d_bc);
+  int rc = wb_exclusive_scan_u64(d_bc, d_bo, n_blocks, stream);
+  if (rc) return rc;
+  pulse_write_kernel<<<n_blocks, PD_THREADS, 0, stream>>>(d_wrap, out_length, fs, d_bo, d_pidx, d_pshift, max_pulses);
+  pulse_finalize_kernel<<<1, 1, 0, stream>>>(d_bo, n_blocks, d_pidx, max_pulses, d_np, d_ncount, ws->error_flag());
+  WB_CUDA_CHECK(cudaGetLastError());
+  if ((rc = wb_rng_fill(d_rng, d_ncount, (unsigned long long)out_length, d_noise, stream))) return rc;
+
+  int resp_pulses;
+  if (f0_upper_bound > 0.0) {
+    const double fmax = f0_upper_bound > WB_DEFAULT_F0 ? f0_upper_bound : WB_DEFAULT_F0;
+    const double bound = (double)out_length * fmax / fs + 2.0;
+    resp_pulses = bound < (double)max_pulses ? (int)bound : max_pulses;
+  } else {
+    int *h_np = (int *)ws->get_pinned("syn_np_h", sizeof(int));
+    if (!h_np) return WB_ERR_CUDA;
+    WB_CUDA_CHECK(cudaMemcpyAsync(h_np, d_np, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    WB_CUDA_CHECK(cudaStreamSynchronize(stream));
+    resp_pulses = *h_np > 0 ? *h_np : 1;
+  }
+  double *d_resp = (double *)ws->get("syn_resp", sizeof(double) * (size_t)resp_pulses * fft_size);
+  if (!d_resp) return WB_ERR_CUDA;
+
+  RespParams p;
+  p.sp = d_sp; p.ap = d_ap; p.f0_length = f0_length; p.fs = fs; p.fft_size = fft_size; p.log2n = log2n;
+  p.frame_period = frame_period; p.pulse_index = d_pidx; p.pulse_shift = d_pshift; p.vuv = d_vuv;
+  p.n_pulses = d_np; p.noise = d_noise; p.dc_remover = d_dcr; p.tw_n = tw_n; p.tw_2n = tw_2n; p.response = d_resp;
+  const int binsp = ((fft_size / 2 + 1) + 1) & ~1;
+  const size_t smem = sizeof(cplx) * (wb_fft_slots(fft_size) + 2 * binsp) + sizeof(double) * (2 * binsp + fft_size + 128);
+  WB_CUDA_CHECK(cudaFuncSetAttribute(response_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  p.max_resp_pulses = resp_pulses;
+  p.error_flag = ws->error_flag();
+  const int grid = wb_min_i(resp_pulses, 148 * 8);
+  response_kernel<<<grid, 256, smem, stream>>>(p);
+  WB_CUDA_CHECK(cudaGetLastError());
+  ola_kernel<<<(out_length + 255) / 256, 256, 0, stream>>>(d_resp, d_pidx, d_np, resp_pulses, fft_size, out_length, d_out);
+  WB_CUDA_CHECK(cudaGetLastError());
+  return wb_rng_advance(d_rng, d_ncount, stream);
+}
