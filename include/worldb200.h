@@ -83,6 +83,17 @@ int wb_fft_r2c(const double *in, int n, int batch, double *out);   /* fft_plan_d
 int wb_fft_c2r(const double *in, int n, int batch, double *out);   /* fft_plan_dft_c2r_1d + fft_execute */
 int wb_fft_c2c(const double *in, int n, int batch, int sign, double *out); /* sign: 1 = FFT_FORWARD, 2 = FFT_BACKWARD */
 
+/* ---- Harvest (include/harvest.hpp:31-44) ------------------------------------------------ */
+int wb_harvest_get_samples(int fs, int x_length, double frame_period);          /* src/harvest.cpp:173-181 */
+int wb_harvest_create(int fs, const WbHarvestOption *opt_or_null, wb_harvest_t **out); /* src/harvest.cpp:69-103 */
+void wb_harvest_destroy(wb_harvest_t *h);
+/* src/harvest.cpp:183-208; temporal_positions and f0 hold wb_harvest_get_samples() entries */
+int wb_harvest_compute(wb_harvest_t *h, const double *x, int x_length, double *temporal_positions, double *f0);
+int wb_harvest_compute_dev(wb_harvest_t *h, const double *d_x, int x_length, double *d_temporal_positions,
+                           double *d_f0, void *stream);
+/* test hook: copies n_bytes of a named internal device buffer of the last compute() to `out` */
+int wb_harvest_debug_read(wb_harvest_t *h, const char *name, void *out, unsigned long long n_bytes);
+
 /* ---- CheapTrick (include/cheaptrick.hpp:23-38) ------------------------------------- */
 int wb_cheaptrick_get_fft_size(int fs, double f0_floor);       /* src/cheaptrick.cpp:97-100 */
 double wb_cheaptrick_get_f0_floor(int fs, int fft_size);       /* src/cheaptrick.cpp:102-105 */

@@ -77,6 +77,12 @@ def _declare(L):
         "wb_fft_r2c": (ci, [vp, ci, ci, vp]),
         "wb_fft_c2r": (ci, [vp, ci, ci, vp]),
         "wb_fft_c2c": (ci, [vp, ci, ci, ci, vp]),
+        "wb_harvest_get_samples": (ci, [ci, ci, cd]),
+        "wb_harvest_create": (ci, [ci, ctypes.POINTER(HarvestOption), ctypes.POINTER(vp)]),
+        "wb_harvest_destroy": (None, [vp]),
+        "wb_harvest_compute": (ci, [vp, vp, ci, vp, vp]),
+        "wb_harvest_compute_dev": (ci, [vp, vp, ci, vp, vp, vp]),
+        "wb_harvest_debug_read": (ci, [vp, ctypes.c_char_p, vp, ctypes.c_ulonglong]),
         "wb_cheaptrick_get_fft_size": (ci, [ci, cd]),
         "wb_cheaptrick_get_f0_floor": (cd, [ci, ci]),
         "wb_cheaptrick_create": (ci, [ci, ctypes.POINTER(CheapTrickOption), ctypes.POINTER(vp)]),
@@ -184,6 +190,39 @@ def fft_c2c(X, sign):
     out = np.empty((b, n), dtype=np.complex128)
     _check(lib().wb_fft_c2c(X.ctypes.data, n, b, int(sign), out.ctypes.data), "wb_fft_c2c")
     return out
+
+
+# ---- Harvest (include/harvest.hpp:31-44) ---------------------------------------------------
+class Harvest:
+    def __init__(self, fs, option=None):
+        self._h = ctypes.c_void_p()
+        self.fs = int(fs)
+        self.option = option if option is not None else HarvestOption()
+        _check(lib().wb_harvest_create(self.fs, ctypes.byref(self.option), ctypes.byref(self._h)), "wb_harvest_create")
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.wb_harvest_destroy(self._h)
+            self._h = None
+
+    def getSamples(self, fs, x_length, frame_period=None):
+        fp = self.option.frame_period if frame_period is None else frame_period
+        return lib().wb_harvest_get_samples(int(fs), int(x_length), float(fp))
+
+    def compute(self, x):
+        """-> (temporal_positions, f0)"""
+        x = _f64(x)
+        n = self.getSamples(self.fs, len(x))
+        tpos = np.empty(n, dtype=np.float64)
+        f0 = np.empty(n, dtype=np.float64)
+        _check(lib().wb_harvest_compute(self._h, x.ctypes.data, len(x), tpos.ctypes.data, f0.ctypes.data),
+               "wb_harvest_compute")
+        return tpos, f0
+
+    def debug_read(self, name, shape, dtype=np.float64):
+        out = np.empty(shape, dtype=dtype)
+        _check(lib().wb_harvest_debug_read(self._h, name.encode(), out.ctypes.data, out.nbytes), "wb_harvest_debug_read")
+        return out
 
 
 # ---- CheapTrick (include/cheaptrick.hpp:23-38) ---------------------------------------------

@@ -8,6 +8,7 @@
 #include <new>
 
 #include "wb_internal.h"
+#include "wb_harvest.h"
 
 namespace {
 
@@ -70,6 +71,11 @@ struct wb_cheaptrick {
   int fs;
   WbCheapTrickOption opt;   // fft_size resolved
   double f0_floor_internal; // cheaptrick.cpp:34 / :44
+  WbWorkspace ws;
+};
+
+struct wb_harvest {
+  WbHarvestPlan plan;
   WbWorkspace ws;
 };
 
@@ -336,6 +342,78 @@ int wb_synthesis_compute(wb_synthesis_t *h, const double *f0, int f0_length, con
   WB_CUDA_CHECK(cudaMemcpyAsync(out, d_out, sizeof(double) * out_length, cudaMemcpyDeviceToHost, st));
   WB_CUDA_CHECK(cudaStreamSynchronize(st));
   return h->ws.read_error_flag(st);
+}
+
+// ---- Harvest -----------------------------------------------------------------------------
+int wb_harvest_get_samples(int fs, int x_length, double frame_period) {
+  return static_cast<int>(1000.0 * x_length / fs / frame_period) + 1;  // harvest.cpp:173-176
+}
+
+int wb_harvest_create(int fs, const WbHarvestOption *opt, wb_harvest_t **out) {
+  if (!out || fs <= 0) return WB_ERR_ARG;
+  int rc = ctx_init();
+  if (rc) return rc;
+  WbHarvestOption o;
+  wb_harvest_option_default(&o);
+  if (opt) o = *opt;
+  if (o.use_cos_table) return WB_ERR_UNSUPPORTED;  // approximate window table: not offered (exact path only)
+  if (!(o.f0_floor > 0) || !(o.f0_ceil > o.f0_floor) || !(o.frame_period > 0) || !(o.target_fs > 0) ||
+      !(o.channels_in_octave > 0))
+    return WB_ERR_ARG;
+  wb_harvest *h = new (std::nothrow) wb_harvest();
+  if (!h) return WB_ERR_ARG;
+  WbHarvestOptionInternal oi = {o.f0_floor, o.f0_ceil, o.frame_period, o.target_fs, o.channels_in_octave};
+  rc = wb_harvest_plan_init(&h->plan, fs, oi);
+  if (rc) { delete h; return rc; }
+  *out = h;
+  return WB_OK;
+}
+
+void wb_harvest_destroy(wb_harvest_t *h) { delete h; }
+
+int wb_harvest_compute_dev(wb_harvest_t *h, const double *d_x, int x_length, double *d_tpos, double *d_f0,
+                           void *stream) {
+  if (!h || !d_x || !d_tpos || !d_f0 || x_length <= 0) return WB_ERR_ARG;
+  cudaStream_t st = pick_stream(stream);
+  const double fp = h->plan.opt.frame_period;
+  int rc, Lb = 0;
+  if (fp == 1.0) {  // harvest.cpp:185-189
+    if ((rc = wb_harvest_run_basic(&h->plan, &h->ws, d_x, x_length, 1, d_f0, &Lb, st))) return rc;
+    return wb_harvest_pick(d_f0, Lb, 1.0, Lb, d_tpos, d_f0, st);  // identity pick; fills temporal positions
+  }
+  const int Lb_expected = wb_harvest_get_samples(h->plan.fs, x_length, 1.0);
+  double *d_basic = (double *)h->ws.get("hv_basic_f0", sizeof(double) * Lb_expected);
+  if (!d_basic) return WB_ERR_CUDA;
+  if ((rc = wb_harvest_run_basic(&h->plan, &h->ws, d_x, x_length, 1, d_basic, &Lb, st))) return rc;
+  const int f0_length = wb_harvest_get_samples(h->plan.fs, x_length, fp);
+  return wb_harvest_pick(d_basic, Lb, fp, f0_length, d_tpos, d_f0, st);
+}
+
+int wb_harvest_compute(wb_harvest_t *h, const double *x, int x_length, double *tpos, double *f0) {
+  if (!h || !x || !tpos || !f0 || x_length <= 0) return WB_ERR_ARG;
+  cudaStream_t st = g_stream;
+  const int f0_length = wb_harvest_get_samples(h->plan.fs, x_length, h->plan.opt.frame_period);
+  double *d_x;
+  int rc;
+  if ((rc = vec_to_device(&h->ws, "h_x", x, x_length, &d_x, st))) return rc;
+  double *d_t = (double *)h->ws.get("h_tpos", sizeof(double) * f0_length);
+  double *d_f = (double *)h->ws.get("h_f0", sizeof(double) * f0_length);
+  if (!d_t || !d_f) return WB_ERR_CUDA;
+  if ((rc = wb_harvest_compute_dev(h, d_x, x_length, d_t, d_f, st))) return rc;
+  WB_CUDA_CHECK(cudaMemcpyAsync(tpos, d_t, sizeof(double) * f0_length, cudaMemcpyDeviceToHost, st));
+  WB_CUDA_CHECK(cudaMemcpyAsync(f0, d_f, sizeof(double) * f0_length, cudaMemcpyDeviceToHost, st));
+  WB_CUDA_CHECK(cudaStreamSynchronize(st));
+  return h->ws.read_error_flag(st);
+}
+
+/* debug: copy the first n_bytes of a named internal device buffer of the last compute() */
+int wb_harvest_debug_read(wb_harvest_t *h, const char *name, void *out, unsigned long long n_bytes) {
+  if (!h || !name || !out) return WB_ERR_ARG;
+  void *d = h->ws.get(name, 0);
+  if (!d) return WB_ERR_ARG;
+  WB_CUDA_CHECK(cudaStreamSynchronize(g_stream));
+  WB_CUDA_CHECK(cudaMemcpy(out, d, n_bytes, cudaMemcpyDeviceToHost));
+  return WB_OK;
 }
 
 }  // extern "C"

@@ -1,0 +1,714 @@
+// Harvest F0 estimation, part 1: everything up to the refined, pruned candidate table.
+// (part 2, the contour fixing / smoothing tail, is in wb_harvest_tail.cu)
+//
+// Reference: /root/reference/src/harvest.cpp
+//   ctor :69-103, getSamples :173-181, compute :183-208, getWaveformAndSpectrum :213-248,
+//   decimate/FilterForDecimate /root/reference/src/world_matlabfunctions.cpp:27-125,184-210,
+//   getFilteredSignal :1261-1305, zeroCrossingEngine :1179-1219,
+//   getFourZeroCrossingIntervals :1228-1255, getF0CandidateContour :1098-1143,
+//   detectOfficialF0Candidates :1005-1083, overlapF0Candidates :987-1000,
+//   refineF0Candidates :932-982, getMeanF0 :883-927 (getBaseIndex :750-757, getMainWindow
+//   :762-788, getDiffWindow :794-803, getSpectra :809-842), fixF0 :844-878,
+//   removeUnreliableCandidates :708-744, generalBody :1380-1453.
+//
+// B200 design notes
+//  * decimation: the zero-phase 3rd-order IIR is evaluated in parallel chunks, each chunk
+//    warmed up over the preceding 400 samples from a zero state (the slowest pole has
+//    radius 0.889 -> the state error is < 1e-18 relative after 353 samples).
+//  * band-pass bank: the reference convolves by one whole-signal FFT per channel
+//    (131072 points for 10 s).  Here the signal is cut into overlap-save blocks of NB
+//    samples whose spectra are computed ONCE and shared by all channels; one CTA per
+//    channel multiplies by the channel's filter spectrum, inverse-transforms in shared
+//    memory and extracts the four kinds of zero crossings straight from shared memory, so
+//    the filtered signals (nch x fft_size doubles in the reference) never exist in HBM.
+//  * refinement: only <= 6 harmonic bins of each candidate's two spectra are used
+//    (fixF0), so a warp evaluates those bins directly instead of two FFTs per candidate.
+#include "wb_harvest.h"
+#include "wb_fft.cuh"
+
+#include <math.h>
+#include <string.h>
+#include <vector>
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// H1: decimation
+// ---------------------------------------------------------------------------------------------
+struct DecimCoef { double a[3]; double b[2]; };
+
+// world_matlabfunctions.cpp:29-111
+bool decimate_coefficients(int r, DecimCoef *c) {
+  switch (r) {
+    case 11: *c = {{2.450743295230728, -2.06794904601978, 0.59574774438332101}, {0.0026822508007163792, 0.0080467524021491377}}; return true;
+    case 12: *c = {{2.4981398605924205, -2.1368928194784025, 0.62187513816221485}, {0.0021097275904709001, 0.0063291827714127002}}; return true;
+    case 10: *c = {{2.3936475118069387, -1.9873904075111861, 0.5658879979027055}, {0.0034818622251927556, 0.010445586675578267}}; return true;
+    case 9: *c = {{2.3236003491759578, -1.8921545617463598, 0.53148928133729068}, {0.0046331164041389372, 0.013899349212416812}}; return true;
+    case 8: *c = {{2.2357462340187593, -1.7780899984041358, 0.49152555365968692}, {0.0063522763407111993, 0.019056829022133598}}; return true;
+    case 7: *c = {{2.1225239019534703, -1.6395144861046302, 0.44469707800587366}, {0.0090366882681608418, 0.027110064804482525}}; return true;
+    case 6: *c = {{1.9715352749512141, -1.4686795689225347, 0.3893908434965701}, {0.013469181309343825, 0.040407543928031475}}; return true;
+    case 5: *c = {{1.7610939654280557, -1.2554914843859768, 0.3237186507788215}, {0.021334858522387423, 0.06400457556716227}}; return true;
+    case 4: *c = {{1.4499664446880227, -0.98943497080950582, 0.24578252340690215}, {0.036710750339322612, 0.11013225101796784}}; return true;
+    case 3: *c = {{0.95039378983237421, -0.67429146741526791, 0.15412211621346475}, {0.071221945171178636, 0.21366583551353591}}; return true;
+    case 2: *c = {{0.041156734567757189, -0.42599112459189636, 0.041037215479961225}, {0.16797464681802227, 0.50392394045406674}}; return true;
+    default: *c = {{0.0, 0.0, 0.0}, {0.0, 0.0}}; return false;
+  }
+}
+
+#define DEC_NFACT 9
+#define DEC_CHUNK 128
+#define DEC_WARM 400
+
+// tmp1 of decimate() (world_matlabfunctions.cpp:189-193) over new_x of
+// getWaveformAndSpectrum (harvest.cpp:222-229), evaluated on the fly from x.
+__device__ __forceinline__ double dec_new_x(const double *__restrict__ x, int x_length, int lag, int j) {
+  const int k = j - lag;
+  return x[k < 0 ? 0 : (k >= x_length ? x_length - 1 : k)];
+}
+__device__ __forceinline__ double dec_tmp1(const double *__restrict__ x, int x_length, int lag, int len1, int i) {
+  if (i < DEC_NFACT) return 2 * dec_new_x(x, x_length, lag, 0) - dec_new_x(x, x_length, lag, DEC_NFACT - i);
+  if (i < DEC_NFACT + len1) return dec_new_x(x, x_length, lag, i - DEC_NFACT);
+  return 2 * dec_new_x(x, x_length, lag, len1 - 1) - dec_new_x(x, x_length, lag, len1 - 2 - (i - (DEC_NFACT + len1)));
+}
+
+// forward pass: out[i] = FilterForDecimate(tmp1)[i], i in [0, len2)
+__global__ void dec_forward_kernel(const double *__restrict__ x, int x_length, int lag, int len1, int len2,
+                                   DecimCoef c, double *__restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int begin = t * DEC_CHUNK;
+  if (begin >= len2) return;
+  const int end = min(len2, begin + DEC_CHUNK);
+  int i = max(0, begin - DEC_WARM);
+  double w0 = 0.0, w1 = 0.0, w2 = 0.0;
+  for (; i < end; ++i) {
+    const double xi = dec_tmp1(x, x_length, lag, len1, i);
+    const double wt = xi + c.a[0] * w0 + c.a[1] * w1 + c.a[2] * w2;
+    if (i >= begin) out[i] = c.b[0] * wt + c.b[1] * w0 + c.b[1] * w1 + c.b[0] * w2;
+    w2 = w1; w1 = w0; w0 = wt;
+  }
+}
+
+// backward pass over `fwd` (the reference reverses, filters, reverses) fused with the pick of
+// every r-th sample (world_matlabfunctions.cpp:201-207) and the lag removal + zero padding of
+// harvest.cpp:231-232,242.  y[m], m in [0, y_length).
+__global__ void dec_backward_kernel(const double *__restrict__ fwd, int len1, int len2, int r, int lag,
+                                    DecimCoef c, int y_length, double *__restrict__ y) {
+  // reversed index u = len2 - 1 - i runs forward in filter time
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int begin = t * DEC_CHUNK;
+  if (begin >= len2) return;
+  const int end = min(len2, begin + DEC_CHUNK);
+  const int nout = len1 / r + 1;
+  const int nbeg = r - r * nout + len1;
+  int u = max(0, begin - DEC_WARM);
+  double w0 = 0.0, w1 = 0.0, w2 = 0.0;
+  for (; u < end; ++u) {
+    const double xi = fwd[len2 - 1 - u];
+    const double wt = xi + c.a[0] * w0 + c.a[1] * w1 + c.a[2] * w2;
+    if (u >= begin) {
+      const double v = c.b[0] * wt + c.b[1] * w0 + c.b[1] * w1 + c.b[0] * w2;
+      // tmp1_final[j] with j = len2 - 1 - u; picked when j = i + NFACT - 1, i = nbeg + cnt * r, i < len1 + NFACT
+      const int j = len2 - 1 - u;
+      const int i = j - DEC_NFACT + 1;
+      if (i >= nbeg && i < len1 + DEC_NFACT && (i - nbeg) % r == 0) {
+        const int cnt = (i - nbeg) / r;
+        const int m = cnt - lag / r;
+        if (m >= 0 && m < y_length) y[m] = v;
+      }
+    }
+    w2 = w1; w1 = w0; w0 = wt;
+  }
+}
+
+__global__ void copy_kernel(const double *__restrict__ x, int n, double *__restrict__ y) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = x[i];
+}
+
+// harvest.cpp:238-241: `accumulate(y_, y_ + y_length_, 0)` has an int accumulator, i.e. the
+// running sum is truncated towards zero after every addition.  If every |y| < 1 the result is
+// exactly 0 (the normal case); otherwise replay the truncating recurrence sequentially.
+__global__ void dc_absmax_kernel(const double *__restrict__ y, int n, unsigned long long *__restrict__ absmax_bits) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double v = (i < n) ? fabs(y[i]) : 0.0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(absmax_bits, (unsigned long long)__double_as_longlong(v));
+}
+__global__ void dc_mean_kernel(const double *__restrict__ y, int n, const unsigned long long *__restrict__ absmax_bits,
+                               double *__restrict__ mean_out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double amax = __longlong_as_double((long long)*absmax_bits);
+  if (amax < 1.0) { *mean_out = 0.0; return; }
+  int acc = 0;
+  for (int i = 0; i < n; ++i) acc = (int)(acc + y[i]);
+  double mean_y = acc;
+  mean_y /= n;
+  *mean_out = mean_y;
+}
+__global__ void dc_subtract_kernel(double *__restrict__ y, int n, const double *__restrict__ mean) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] -= *mean;
+}
+
+// ---------------------------------------------------------------------------------------------
+// H3/H4: overlap-save block spectra and per-channel filter spectra
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) yspec_kernel(const double *__restrict__ y, int y_length, int NB, int log2nc,
+                                                    int V, int h_max, const cplx *__restrict__ tw,
+                                                    cplx *__restrict__ Yb) {
+  extern __shared__ double2 smem_raw[];
+  cplx *S = smem_raw;
+  double *W = reinterpret_cast<double *>(S);
+  const int NC = NB / 2;
+  const int b = blockIdx.x;
+  const long long s_b = (long long)b * V + 1 - h_max;
+  for (int i = threadIdx.x; i < NB; i += blockDim.x) {
+    const long long n = s_b + i;
+    W[wb_didx(i)] = (n >= 0 && n < y_length) ? y[n] : 0.0;
+  }
+  __syncthreads();
+  cplx *dst = Yb + (size_t)b * (NC + 1);
+  wb_rfft<1>(S, NC, log2nc, tw, [&](int k, cplx X) { dst[k] = X; });
+}
+
+// getFilteredSignal (harvest.cpp:1264-1274): Nuttall(2h+1) x cos(2 pi bf i / fs), then r2c
+__global__ void __launch_bounds__(512) filter_spec_kernel(const double *__restrict__ boundary_f0, const int *__restrict__ half_len,
+                                                          double actual_fs, int NB, int log2nc,
+                                                          const cplx *__restrict__ tw, cplx *__restrict__ Hc) {
+  extern __shared__ double2 smem_raw[];
+  cplx *S = smem_raw;
+  double *W = reinterpret_cast<double *>(S);
+  const int NC = NB / 2;
+  const int c = blockIdx.x;
+  const double bf = boundary_f0[c];
+  const int h = half_len[c];
+  const int flen = 2 * h + 1;
+  for (int i = threadIdx.x; i < NB; i += blockDim.x) {
+    double v = 0.0;
+    if (i < flen) {
+      const double tmp = i / (flen - 1.0);
+      const double win = 0.355768 - 0.487396 * cos(2.0 * WB_PI * tmp) + 0.144232 * cos(4.0 * WB_PI * tmp) -
+                         0.012604 * cos(6.0 * WB_PI * tmp);
+      v = win * cos(2 * WB_PI * bf * (i - h) / actual_fs);
+    }
+    W[wb_didx(i)] = v;
+  }
+  __syncthreads();
+  cplx *dst = Hc + (size_t)c * (NC + 1);
+  wb_rfft<1>(S, NC, log2nc, tw, [&](int k, cplx X) { dst[k] = X; });
+}
+
+// ---------------------------------------------------------------------------------------------
+// H5: per-channel band-pass + zero crossings
+// ---------------------------------------------------------------------------------------------
+struct ChanParams {
+  const cplx *Yb; const cplx *Hc; const int *half_len;
+  int n_blocks; int NB; int log2nc; int V; int h_max; int y_length;
+  const cplx *tw;
+  double *edges;      // [nch][4][ecap]
+  int *ecount;        // [nch][4]
+  int ecap;
+};
+
+// Appends, in increasing order, the fine edges found by the calling block for sample range
+// [n_begin, n_end).  f(n) must be valid for n .. n+2.  type 0: negative-going of f, 1: of -f,
+// 2: of d = f[n+1]-f[n] (peaks), 3: of -d (dips).   harvest.cpp:1179-1255
+template <typename F>
+__device__ inline void emit_edges(F f, int n_begin, int n_end, int y_length, double *edges, int ecap,
+                                  int *s_count /*[4] shared*/, int *s_warp /*[4][32] shared*/) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int base = n_begin; base < n_end; base += blockDim.x) {
+    const int n = base + threadIdx.x;
+    bool flag[4] = {false, false, false, false};
+    double fine[4] = {0.0, 0.0, 0.0, 0.0};
+    if (n < n_end) {
+      const double a = f(n), b = f(n + 1);
+      if (n < y_length - 1) {
+        if (0.0 < a && b <= 0.0) { flag[0] = true; fine[0] = (n + 1) - a / (b - a); }
+        if (a < 0.0 && b >= 0.0) { flag[1] = true; fine[1] = (n + 1) - a / (b - a); }
+      }
+      if (n < y_length - 2) {
+        const double c = f(n + 2);
+        const double d0 = b - a, d1 = c - b;
+        if (0.0 < d0 && d1 <= 0.0) { flag[2] = true; fine[2] = (n + 1) - d0 / (d1 - d0); }
+        if (d0 < 0.0 && d1 >= 0.0) { flag[3] = true; fine[3] = (n + 1) - d0 / (d1 - d0); }
+      }
+    }
+    unsigned m[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      m[t] = __ballot_sync(0xffffffffu, flag[t]);
+      if (lane == 0) s_warp[t * 32 + warp] = __popc(m[t]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      if (flag[t]) {
+        int before = s_count[t];
+        for (int w = 0; w < warp; ++w) before += s_warp[t * 32 + w];
+        const int slot = before + __popc(m[t] & ((1u << lane) - 1u));
+        if (slot < ecap) edges[(size_t)t * ecap + slot] = fine[t];
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+      int tot = 0;
+      for (int w = 0; w < nw; ++w) tot += s_warp[threadIdx.x * 32 + w];
+      s_count[threadIdx.x] += tot;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(512) channel_kernel(ChanParams p) {
+  extern __shared__ double2 smem_raw[];
+  __shared__ int s_count[4];
+  __shared__ int s_warp[4 * 32];
+  cplx *S = smem_raw;
+  double *W = reinterpret_cast<double *>(S);
+  const int NC = p.NB / 2;
+  const int c = blockIdx.x;
+  const int h = p.half_len[c];
+  const cplx *H = p.Hc + (size_t)c * (NC + 1);
+  double *edges = p.edges + (size_t)c * 4 * p.ecap;
+  if (threadIdx.x < 4) s_count[threadIdx.x] = 0;
+  __syncthreads();
+  for (int b = 0; b < p.n_blocks; ++b) {
+    const cplx *Y = p.Yb + (size_t)b * (NC + 1);
+    // convolution theorem, harvest.cpp:1277-1291
+    wb_irfft<-1>(S, NC, p.log2nc, p.tw, [&](int k) {
+      const cplx yv = Y[k], hv = H[k];
+      return make_double2(yv.x * hv.x - yv.y * hv.y, yv.x * hv.y + yv.y * hv.x);
+    });
+    // filtered[n] = seg[n + 1 + h - s_b], s_b = b V + 1 - h_max   (delay compensation :1297-1299)
+    const int n0 = b * p.V;
+    const int off = h + p.h_max - n0;  // n + off = n + 1 + h - s_b
+    const int n_end = min(n0 + p.V, p.y_length);
+    emit_edges([&](int n) { return W[wb_didx(n + off)]; }, n0, n_end, p.y_length, edges, p.ecap, s_count, s_warp);
+  }
+  if (threadIdx.x < 4) p.ecount[c * 4 + threadIdx.x] = min(s_count[threadIdx.x], p.ecap);
+}
+
+// ---------------------------------------------------------------------------------------------
+// getF0CandidateContour (harvest.cpp:1098-1143): interp1 of the four interval sequences to the
+// 1 ms frame grid + gating.  One thread per (channel, frame).
+// ---------------------------------------------------------------------------------------------
+struct RawParams {
+  const double *edges; const int *ecount; int ecap;
+  const double *boundary_f0; int nch; int f0_length; double actual_fs;
+  double f0_floor; double f0_ceil; int frame_period;
+  double *raw;  // [nch][f0_length]
+};
+
+__device__ __forceinline__ double hv_loc(const double *e, int k, double fs) { return (e[k] + e[k + 1]) / 2.0 / fs; }
+__device__ __forceinline__ double hv_val(const double *e, int k, double fs) { return fs / (e[k + 1] - e[k]); }
+
+__global__ void raw_candidate_kernel(RawParams p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.y;
+  if (i >= p.f0_length) return;
+  const int *cnt = p.ecount + c * 4;
+  double *out = p.raw + (size_t)c * p.f0_length;
+  // number of intervals = edges - 1 (0 if fewer than 2 edges); all four must exceed 2
+  bool ok = true;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int ni = cnt[t] < 2 ? 0 : cnt[t] - 1;
+    if (ni - 2 <= 0) ok = false;
+  }
+  if (!ok) { out[i] = 0.0; return; }
+  const double t_i = i * p.frame_period / 1000.0;
+  double v[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const double *e = p.edges + ((size_t)c * 4 + t) * p.ecap;
+    const int ni = cnt[t] - 1;
+    // histc: first k with loc[k] > t_i, clamped to [1, ni - 1]
+    int lo = 0, hi = ni;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (hv_loc(e, mid, p.actual_fs) > t_i) hi = mid; else lo = mid + 1;
+    }
+    int k = lo;
+    if (k < 1) k = 1;
+    if (k > ni - 1) k = ni - 1;
+    const double x0 = hv_loc(e, k - 1, p.actual_fs), x1 = hv_loc(e, k, p.actual_fs);
+    const double y0 = hv_val(e, k - 1, p.actual_fs), y1 = hv_val(e, k, p.actual_fs);
+    const double s = (t_i - x0) / (x1 - x0);
+    v[t] = y0 + s * (y1 - y0);
+  }
+  const double bf = p.boundary_f0[c];
+  const double upper = bf * 1.1, lower = bf * 0.9;
+  double f = (v[0] + v[1] + v[2] + v[3]) / 4.0;
+  if (f > upper || f < lower || f > p.f0_ceil || f < p.f0_floor) f = 0.0;
+  out[i] = f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// detectOfficialF0Candidates (harvest.cpp:1005-1083): one thread per frame
+// ---------------------------------------------------------------------------------------------
+__global__ void detect_kernel(const double *__restrict__ raw, int nch, int f0_length, int own_cap,
+                              double *__restrict__ own /*[f0_length][own_cap]*/, int *__restrict__ nc_max) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= f0_length) return;
+  double *dst = own + (size_t)i * own_cap;
+  int count = 0;
+  int prev = 0, st = 0;
+  double acc = 0.0;
+  for (int j = 1; j < nch; ++j) {
+    // vuv[0] = vuv[nch-1] = 0
+    const double r = raw[(size_t)j * f0_length + i];
+    const int cur = (j == nch - 1) ? 0 : (r > 0 ? 1 : 0);
+    if (cur - prev == 1) { st = j; acc = 0.0; }
+    if (cur == 1) acc += r;
+    if (cur - prev == -1) {
+      const int ed = j;
+      if (ed - st >= 10 && count < own_cap) dst[count++] = acc / (ed - st);
+    }
+    prev = cur;
+  }
+  for (int k = count; k < own_cap; ++k) dst[k] = 0.0;
+  if (count > 0) atomicMax(nc_max, count);
+}
+
+// overlapF0Candidates (harvest.cpp:987-1000) + work list of the non-zero candidates
+__global__ void overlap_kernel(const double *__restrict__ own, int own_cap, const int *__restrict__ nc_ptr,
+                               int f0_length, int max_candidates, double *__restrict__ cand /*[f0_length][max_candidates]*/,
+                               double *__restrict__ score, int *__restrict__ work, int *__restrict__ work_count) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (long long)f0_length * max_candidates) return;
+  const int k = (int)(g / max_candidates), slot = (int)(g % max_candidates);
+  const int nc = *nc_ptr;
+  double v = 0.0;
+  if (nc > 0 && slot < nc * 7) {
+    const int o = slot / nc, j = slot % nc;
+    int src = k;
+    if (o >= 1 && o <= 3) src = k - o;         // copies from earlier frames
+    else if (o >= 4) src = k + (o - 3);        // copies from later frames
+    if (src >= 0 && src < f0_length) v = own[(size_t)src * own_cap + j];
+  }
+  cand[g] = v;
+  score[g] = 0.0;
+  if (v > 0.0) work[atomicAdd(work_count, 1)] = k * 128 + slot;  // max_candidates <= 128 checked on the host
+}
+
+// ---------------------------------------------------------------------------------------------
+// refineF0Candidates / getMeanF0 / fixF0 (harvest.cpp:844-982): one warp per candidate
+// ---------------------------------------------------------------------------------------------
+struct RefineParams {
+  const double *y; int y_length; double actual_fs;
+  double f0_floor, f0_ceil; int frame_period;
+  const int *work; const int *work_count;
+  int max_candidates;
+  double *cand; double *score;
+  const cplx *tw[16];   // twiddle tables by log2(fft_size)
+  int max_wlen;         // shared window buffer length per warp
+};
+
+#define RF_WARPS 8
+__global__ void __launch_bounds__(RF_WARPS * 32) refine_kernel(RefineParams p) {
+  extern __shared__ double rf_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double *mw = rf_smem + (size_t)warp * (p.max_wlen + 2);  // main window, index shifted by +1 (mw[0] = mw[len+1] = pad)
+  const int n_work = *p.work_count;
+  const int total_warps = gridDim.x * RF_WARPS;
+  const double fs = p.actual_fs;
+  for (int wi = blockIdx.x * RF_WARPS + warp; wi < n_work; wi += total_warps) {
+    const int item = p.work[wi];
+    const int frame = item >> 7, slot = item & 127;
+    const size_t at = (size_t)frame * p.max_candidates + slot;
+    const double current_f0 = p.cand[at];
+    const double current_position = frame * p.frame_period / 1000.0;
+    const int hw = static_cast<int>(1.5 * fs / current_f0 + 1.0);
+    const int len = 2 * hw + 1;
+    const double window_length_in_time = (2.0 * hw + 1.0) / fs;
+    const int log2fft = 2 + (31 - __clz(len));  // 2 + int(log2(len)), len odd
+    const int fft_size = 1 << log2fft;
+    const double base_time0 = (-hw + 0) / fs;
+    const int basic_index = wb_round((current_position + base_time0) * fs + 0.001);
+    // main window (harvest.cpp:762-774)
+    const double two_pi = 2.0 * WB_PI;
+    for (int i = lane; i < len; i += 32) {
+      const double tmp = ((basic_index + i) - 1.0) / fs - current_position;
+      const double tmp2 = two_pi * tmp / window_length_in_time;
+      mw[i + 1] = 0.42 + 0.5 * cos(tmp2) + 0.08 * cos(2 * tmp2);
+    }
+    __syncwarp();
+    const int nh = wb_min_i(static_cast<int>(fs / 2.0 / current_f0), 6);
+    int idx[6];
+#pragma unroll
+    for (int hh = 0; hh < 6; ++hh) idx[hh] = wb_round(current_f0 * fft_size / fs * (hh + 1));
+    double mr[6], mi[6], dr[6], di[6];
+#pragma unroll
+    for (int hh = 0; hh < 6; ++hh) { mr[hh] = mi[hh] = dr[hh] = di[hh] = 0.0; }
+    const cplx *T = p.tw[log2fft];
+    const int mask = fft_size - 1;
+    for (int i = lane; i < len; i += 32) {
+      const int safe = wb_max_i(0, wb_min_i(p.y_length - 1, basic_index + i - 1));
+      const double yv = p.y[safe];
+      // diff window (harvest.cpp:794-803)
+      double dwin;
+      if (i == 0) dwin = -mw[2] / 2.0;
+      else if (i == len - 1) dwin = mw[len - 1] / 2.0;
+      else dwin = -(mw[i + 2] - mw[i]) / 2.0;
+      const double vm = mw[i + 1] * yv, vd = dwin * yv;
+#pragma unroll
+      for (int hh = 0; hh < 6; ++hh) {
+        if (hh < nh) {
+          const cplx w = __ldg(&T[(idx[hh] * i) & mask]);  // e^{+2 pi i idx n / fft}
+          mr[hh] = fma(vm, w.x, mr[hh]); mi[hh] = fma(vm, w.y, mi[hh]);
+          dr[hh] = fma(vd, w.x, dr[hh]); di[hh] = fma(vd, w.y, di[hh]);
+        }
+      }
+    }
+#pragma unroll
+    for (int hh = 0; hh < 6; ++hh) {
+      mr[hh] = wb_warp_sum(mr[hh]); mi[hh] = wb_warp_sum(mi[hh]);
+      dr[hh] = wb_warp_sum(dr[hh]); di[hh] = wb_warp_sum(di[hh]);
+    }
+    if (lane == 0) {
+      // spectra are conjugated by the reference (harvest.cpp:829-841): main = (mr, -mi), diff = (dr, -di)
+      double numerator = 0.0, denominator = 0.0, score = 0.0;
+      for (int hh = 0; hh < nh; ++hh) {
+        const double m_re = mr[hh], m_im = -mi[hh], d_re = dr[hh], d_im = -di[hh];
+        const double power = m_re * m_re + m_im * m_im;
+        const double num_i = m_re * d_im - m_im * d_re;
+        const double inst = (power == 0.0) ? 0.0
+                            : static_cast<double>(idx[hh]) * fs / fft_size + num_i / power * fs / 2.0 / WB_PI;
+        const double amp = sqrt(power);
+        numerator += amp * inst;
+        denominator += amp * (hh + 1.0);
+        score += fabs((inst / (hh + 1.0) - current_f0) / current_f0);
+      }
+      double refined = numerator / (denominator + WB_SAFEGUARD);
+      double sc = 1.0 / (score / nh + WB_SAFEGUARD);
+      if (refined < p.f0_floor || refined > p.f0_ceil || sc < 2.5) { refined = 0.0; sc = 0.0; }
+      p.cand[at] = refined;
+      p.score[at] = sc;
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// removeUnreliableCandidates (harvest.cpp:708-744): one thread per (frame, slot)
+// ---------------------------------------------------------------------------------------------
+__global__ void remove_kernel(const double *__restrict__ cand_in, const double *__restrict__ score_in,
+                              const int *__restrict__ nc_ptr, int f0_length, int max_candidates,
+                              double *__restrict__ cand_out, double *__restrict__ score_out) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (long long)f0_length * max_candidates) return;
+  const int i = (int)(g / max_candidates), j = (int)(g % max_candidates);
+  const int nc7 = *nc_ptr * 7;
+  double c = cand_in[g], s = score_in[g];
+  if (i >= 1 && i < f0_length - 1 && j < nc7 && c != 0) {
+    const double reference_f0 = c;
+    double err[2];
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+      const int nb = (side == 0) ? i + 1 : i - 1;
+      // tmp_f0_candidates_ rows 0 and f0_length-1 are never filled (zero)
+      const bool zero_row = (nb == 0 || nb == f0_length - 1);
+      const double *row = cand_in + (size_t)nb * max_candidates;
+      double best_error = 1.0;
+      for (int k = 0; k < nc7; ++k) {
+        const double v = zero_row ? 0.0 : row[k];
+        const double tmp = fabs(reference_f0 - v) / reference_f0;
+        if (tmp > best_error) continue;
+        best_error = tmp;
+      }
+      err[side] = best_error;
+    }
+    const double min_error = err[0] < err[1] ? err[0] : err[1];
+    if (min_error > 0.05) { c = 0; s = 0; }
+  }
+  cand_out[g] = c;
+  score_out[g] = s;
+}
+
+int ilog2_exact(int n) {
+  int l = 0;
+  while ((1 << l) < n) ++l;
+  return ((1 << l) == n) ? l : -1;
+}
+
+}  // namespace
+
+// =============================================================================================
+// host side
+// =============================================================================================
+int wb_harvest_plan_init(WbHarvestPlan *pl, int fs, const WbHarvestOptionInternal &opt) {
+  pl->fs = fs;
+  pl->opt = opt;
+  // harvest.cpp:81-83
+  int r = wb_round(fs / opt.target_fs);
+  r = wb_max_i(wb_min_i(r, 12), 1);
+  pl->decimation_ratio = r;
+  pl->actual_fs = static_cast<double>(fs) / r;
+  // harvest.cpp:1388-1396
+  const double adjusted_f0_floor = opt.f0_floor * 0.9;
+  const double adjusted_f0_ceil = opt.f0_ceil * 1.1;
+  pl->nch = 1 + static_cast<int>(log(adjusted_f0_ceil / adjusted_f0_floor) / WB_LOG2 * opt.channels_in_octave);
+  if (pl->nch < 2 || pl->nch > 4096) return WB_ERR_UNSUPPORTED;
+  pl->boundary_f0.resize(pl->nch);
+  pl->half_len.resize(pl->nch);
+  int h_max = 0;
+  for (int i = 0; i < pl->nch; ++i) {
+    pl->boundary_f0[i] = adjusted_f0_floor * pow(2.0, static_cast<double>(i + 1) / opt.channels_in_octave);
+    pl->half_len[i] = wb_round(pl->actual_fs / pl->boundary_f0[i] * 2.0);  // harvest.cpp:1264
+    if (pl->half_len[i] > h_max) h_max = pl->half_len[i];
+  }
+  pl->h_max = h_max;
+  pl->max_candidates = wb_round(pl->nch / 10) * 7;  // harvest.cpp:1418-1419 (integer division)
+  if (pl->max_candidates > 128 || pl->max_candidates < 7) return WB_ERR_UNSUPPORTED;
+  pl->NB = 8192;
+  while (pl->NB < 8 * (h_max + 1) && pl->NB < 16384) pl->NB *= 2;
+  if (2 * h_max + 2 >= pl->NB / 2) return WB_ERR_UNSUPPORTED;
+  pl->V = pl->NB - 2 - 2 * h_max;
+  if (r > 1 && !decimate_coefficients(r, (DecimCoef *)pl->decim_coef)) return WB_ERR_UNSUPPORTED;
+  pl->filters_ready = false;
+  return WB_OK;
+}
+
+static int harvest_prepare_filters(WbHarvestPlan *pl, WbWorkspace *ws, cudaStream_t stream) {
+  if (pl->filters_ready) return WB_OK;
+  const int NC = pl->NB / 2;
+  double *d_bf = (double *)ws->get("hv_bf", sizeof(double) * pl->nch);
+  int *d_hl = (int *)ws->get("hv_hl", sizeof(int) * pl->nch);
+  cplx *d_Hc = (cplx *)ws->get("hv_Hc", sizeof(cplx) * (size_t)pl->nch * (NC + 1));
+  if (!d_bf || !d_hl || !d_Hc) return WB_ERR_CUDA;
+  WB_CUDA_CHECK(cudaMemcpyAsync(d_bf, pl->boundary_f0.data(), sizeof(double) * pl->nch, cudaMemcpyHostToDevice, stream));
+  WB_CUDA_CHECK(cudaMemcpyAsync(d_hl, pl->half_len.data(), sizeof(int) * pl->nch, cudaMemcpyHostToDevice, stream));
+  const cplx *tw = wb_twiddle_table(pl->NB);
+  if (!tw) return WB_ERR_CUDA;
+  const size_t smem = sizeof(cplx) * wb_fft_slots(NC);
+  WB_CUDA_CHECK(cudaFuncSetAttribute(filter_spec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  filter_spec_kernel<<<pl->nch, 512, smem, stream>>>(d_bf, d_hl, pl->actual_fs, pl->NB, ilog2_exact(NC), tw, d_Hc);
+  WB_CUDA_CHECK(cudaGetLastError());
+  WB_CUDA_CHECK(cudaStreamSynchronize(stream));  // host vectors are pageable; make the plan self-contained
+  pl->filters_ready = true;
+  return WB_OK;
+}
+
+// Runs Harvest at a 1 ms (frame_period = 1) grid up to the pruned candidate table and then the
+// tail; writes d_f0_basic[Lb].
+int wb_harvest_run_basic(WbHarvestPlan *pl, WbWorkspace *ws, const double *d_x, int x_length, int frame_period,
+                         double *d_f0_basic, int *f0_length_out, cudaStream_t stream) {
+  const int fs = pl->fs, r = pl->decimation_ratio;
+  const double afs = pl->actual_fs;
+  int rc;
+  if ((rc = harvest_prepare_filters(pl, ws, stream))) return rc;
+  const int NB = pl->NB, NC = NB / 2, log2nc = ilog2_exact(NC);
+  const int y_length = 1 + static_cast<int>(x_length / r);                               // harvest.cpp:1399
+  const int Lb = static_cast<int>(1000.0 * x_length / fs / frame_period) + 1;            // harvest.cpp:173-176
+  *f0_length_out = Lb;
+  const int nch = pl->nch, MC = pl->max_candidates, own_cap = MC / 7;
+
+  // ---- H1/H2: decimated, DC-"corrected" waveform
+  double *d_y = (double *)ws->get("hv_y", sizeof(double) * (y_length + 8));
+  if (!d_y) return WB_ERR_CUDA;
+  if (r == 1) {
+    copy_kernel<<<(x_length + 255) / 256, 256, 0, stream>>>(d_x, x_length, d_y);  // y_length = x_length + 1: last is zero
+    WB_CUDA_CHECK(cudaMemsetAsync(d_y + x_length, 0, sizeof(double) * (y_length - x_length), stream));
+  } else {
+    const int lag = static_cast<int>(ceil(140.0 / r) * r);                               // harvest.cpp:222
+    const int len1 = x_length + lag * 2;
+    const int len2 = len1 + 2 * DEC_NFACT;
+    double *d_fwd = (double *)ws->get("hv_fwd", sizeof(double) * len2);
+    if (!d_fwd) return WB_ERR_CUDA;
+    DecimCoef dc;
+    memcpy(&dc, pl->decim_coef, sizeof(dc));
+    const int n_thr = (len2 + DEC_CHUNK - 1) / DEC_CHUNK;
+    WB_CUDA_CHECK(cudaMemsetAsync(d_y, 0, sizeof(double) * y_length, stream));            // new_y is zero-initialised
+    dec_forward_kernel<<<(n_thr + 127) / 128, 128, 0, stream>>>(d_x, x_length, lag, len1, len2, dc, d_fwd);
+    dec_backward_kernel<<<(n_thr + 127) / 128, 128, 0, stream>>>(d_fwd, len1, len2, r, lag, dc, y_length, d_y);
+  }
+  unsigned long long *d_absmax = (unsigned long long *)ws->get("hv_absmax", 16);
+  double *d_mean = (double *)ws->get("hv_mean", 16);
+  if (!d_absmax || !d_mean) return WB_ERR_CUDA;
+  WB_CUDA_CHECK(cudaMemsetAsync(d_absmax, 0, 8, stream));
+  dc_absmax_kernel<<<(y_length + 255) / 256, 256, 0, stream>>>(d_y, y_length, d_absmax);
+  dc_mean_kernel<<<1, 32, 0, stream>>>(d_y, y_length, d_absmax, d_mean);
+  dc_subtract_kernel<<<(y_length + 255) / 256, 256, 0, stream>>>(d_y, y_length, d_mean);
+  WB_CUDA_CHECK(cudaGetLastError());
+
+  // ---- H3: overlap-save block spectra
+  const int n_blocks = (y_length + pl->V - 1) / pl->V;
+  cplx *d_Yb = (cplx *)ws->get("hv_Yb", sizeof(cplx) * (size_t)n_blocks * (NC + 1));
+  if (!d_Yb) return WB_ERR_CUDA;
+  const cplx *tw = wb_twiddle_table(NB);
+  const size_t smem_fft = sizeof(cplx) * wb_fft_slots(NC);
+  WB_CUDA_CHECK(cudaFuncSetAttribute(yspec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
+  yspec_kernel<<<n_blocks, 512, smem_fft, stream>>>(d_y, y_length, NB, log2nc, pl->V, pl->h_max, tw, d_Yb);
+  WB_CUDA_CHECK(cudaGetLastError());
+
+  // ---- H5: channels
+  const int ecap = y_length / 2 + 4;
+  double *d_edges = (double *)ws->get("hv_edges", sizeof(double) * (size_t)nch * 4 * ecap);
+  int *d_ecount = (int *)ws->get("hv_ecount", sizeof(int) * nch * 4);
+  if (!d_edges || !d_ecount) return WB_ERR_CUDA;
+  {
+    ChanParams p;
+    p.Yb = d_Yb; p.Hc = (const cplx *)ws->get("hv_Hc", 0); p.half_len = (const int *)ws->get("hv_hl", 0);
+    p.n_blocks = n_blocks; p.NB = NB; p.log2nc = log2nc; p.V = pl->V; p.h_max = pl->h_max; p.y_length = y_length;
+    p.tw = tw; p.edges = d_edges; p.ecount = d_ecount; p.ecap = ecap;
+    WB_CUDA_CHECK(cudaFuncSetAttribute(channel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
+    channel_kernel<<<nch, 512, smem_fft, stream>>>(p);
+    WB_CUDA_CHECK(cudaGetLastError());
+  }
+
+  // ---- raw candidates on the frame grid
+  double *d_raw = (double *)ws->get("hv_raw", sizeof(double) * (size_t)nch * Lb);
+  if (!d_raw) return WB_ERR_CUDA;
+  {
+    RawParams p;
+    p.edges = d_edges; p.ecount = d_ecount; p.ecap = ecap; p.boundary_f0 = (const double *)ws->get("hv_bf", 0);
+    p.nch = nch; p.f0_length = Lb; p.actual_fs = afs; p.f0_floor = pl->opt.f0_floor; p.f0_ceil = pl->opt.f0_ceil;
+    p.frame_period = frame_period; p.raw = d_raw;
+    dim3 grid((Lb + 255) / 256, nch);
+    raw_candidate_kernel<<<grid, 256, 0, stream>>>(p);
+    WB_CUDA_CHECK(cudaGetLastError());
+  }
+
+  // ---- official candidates, overlap, refine, prune
+  double *d_own = (double *)ws->get("hv_own", sizeof(double) * (size_t)Lb * own_cap);
+  int *d_nc = (int *)ws->get("hv_nc", 16);
+  int *d_work = (int *)ws->get("hv_work", sizeof(int) * (size_t)Lb * MC);
+  double *d_candA = (double *)ws->get("hv_candA", sizeof(double) * (size_t)Lb * MC);
+  double *d_scoreA = (double *)ws->get("hv_scoreA", sizeof(double) * (size_t)Lb * MC);
+  double *d_candB = (double *)ws->get("hv_candB", sizeof(double) * (size_t)Lb * MC);
+  double *d_scoreB = (double *)ws->get("hv_scoreB", sizeof(double) * (size_t)Lb * MC);
+  if (!d_own || !d_nc || !d_work || !d_candA || !d_scoreA || !d_candB || !d_scoreB) return WB_ERR_CUDA;
+  WB_CUDA_CHECK(cudaMemsetAsync(d_nc, 0, 16, stream));  // [0] = nc, [1] = work count
+  detect_kernel<<<(Lb + 127) / 128, 128, 0, stream>>>(d_raw, nch, Lb, own_cap, d_own, d_nc);
+  const long long n_cs = (long long)Lb * MC;
+  overlap_kernel<<<(unsigned)((n_cs + 255) / 256), 256, 0, stream>>>(d_own, own_cap, d_nc, Lb, MC, d_candA, d_scoreA,
+                                                                    d_work, d_nc + 1);
+  WB_CUDA_CHECK(cudaGetLastError());
+  {
+    RefineParams p;
+    p.y = d_y; p.y_length = y_length; p.actual_fs = afs; p.f0_floor = pl->opt.f0_floor; p.f0_ceil = pl->opt.f0_ceil;
+    p.frame_period = frame_period; p.work = d_work; p.work_count = d_nc + 1; p.max_candidates = MC;
+    p.cand = d_candA; p.score = d_scoreA;
+    // candidates are in [f0_floor, f0_ceil] of the raw stage: half window <= 1.5 fs / (0.9 floor) + 1
+    const int max_hw = static_cast<int>(1.5 * afs / (pl->opt.f0_floor * 0.9) + 1.0) + 1;
+    p.max_wlen = 2 * max_hw + 1;
+    const int max_log2 = 2 + (int)floor(log2((double)p.max_wlen));
+    if (max_log2 > 15) return WB_ERR_UNSUPPORTED;
+    for (int l = 0; l < 16; ++l) p.tw[l] = nullptr;
+    for (int l = 3; l <= max_log2; ++l) {
+      p.tw[l] = wb_twiddle_table(1 << l);
+      if (!p.tw[l]) return WB_ERR_CUDA;
+    }
+    const size_t smem = sizeof(double) * RF_WARPS * (p.max_wlen + 2);
+    WB_CUDA_CHECK(cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    refine_kernel<<<148 * 4, RF_WARPS * 32, smem, stream>>>(p);
+    WB_CUDA_CHECK(cudaGetLastError());
+  }
+  remove_kernel<<<(unsigned)((n_cs + 255) / 256), 256, 0, stream>>>(d_candA, d_scoreA, d_nc, Lb, MC, d_candB, d_scoreB);
+  WB_CUDA_CHECK(cudaGetLastError());
+
+  // ---- contour fixing + smoothing
+  return wb_harvest_tail(ws, d_candB, d_scoreB, d_nc, Lb, MC, d_f0_basic, stream);
+}

@@ -1,0 +1,443 @@
+// Harvest, part 2: from the pruned candidate table to the smoothed F0 contour.
+//
+// Reference: /root/reference/src/harvest.cpp
+//   searchF0Base :254-272, fixStep1 :277-291, getBoundaryList :296-314, fixStep2 :319-334,
+//   selectBestF0 :347-365, extendF0 :371-404, swapArray :410-424, extend :429-458,
+//   searchScore :463-470, mergeF0Sub :475-497, mergeF0 :502-536, getMultiChannelF0 :542-555,
+//   fixStep3 :560-585, fixStep4 :590-614, fixF0Contour :619-634, filteringF0 :639-665,
+//   smoothF0Contour :670-703.
+//
+// This is branchy, mostly serial bookkeeping over a few dozen voiced sections.  It runs as
+// ONE thread block so that the whole Harvest stage stays on the device with no host round
+// trip: per-frame work is spread over the 1024 threads, per-section work over warps, and the
+// two zero-phase Butterworth passes are evaluated in parallel chunks with a 300-sample
+// warm-up (pole radius 0.875 -> 4e-18 residual), which is also the padding the reference uses.
+//
+// Voiced sections are stored sparsely (section range +-104 frames) instead of the reference's
+// f0_length-sized row per section; reads outside the stored range return the 0.0 the
+// reference's rows hold there.
+#include "wb_harvest.h"
+
+namespace {
+
+#define TL_THREADS 1024
+#define TL_MARGIN 104
+#define TL_LAG 300
+#define TL_CHUNK 64
+
+struct TailParams {
+  const double *cand; const double *score; const int *nc; int L; int MC;
+  double *base, *s1, *s2, *s3, *s4, *out;
+  int *blist;          // L + 2*TL_LAG + 2
+  int maxsec;
+  int *sec_st, *sec_ed, *sec_lo, *sec_len, *sec_off;  // maxsec each (sec_off: maxsec + 1)
+  double *sec_sum;     // maxsec
+  double *secbuf; long long secbuf_cap;
+  int *kb;             // 2 * maxsec (+2)
+  int *kslot;          // maxsec (+1)
+  int *order;          // maxsec
+  double *pad;         // L + 2*TL_LAG
+  double *fw; long long fw_cap;
+  int *error_flag;
+};
+
+__device__ __forceinline__ int tl_vuv(const double *f0, int n, int i) {
+  return (i <= 0 || i >= n - 1) ? 0 : (f0[i] > 0 ? 1 : 0);
+}
+
+// getBoundaryList (harvest.cpp:296-314).  All threads; returns the number of boundaries.
+__device__ int tl_boundaries(const double *f0, int n, int *blist, int *s_scan) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int chunk = (n + nt - 1) / nt;
+  const int b = max(1, tid * chunk), e = min(n, (tid + 1) * chunk);
+  int cnt = 0;
+  for (int i = b; i < e; ++i) cnt += (tl_vuv(f0, n, i) - tl_vuv(f0, n, i - 1) != 0) ? 1 : 0;
+  __syncthreads();
+  s_scan[tid] = cnt;
+  __syncthreads();
+  for (int o = 1; o < nt; o <<= 1) {
+    const int t = (tid >= o) ? s_scan[tid - o] : 0;
+    __syncthreads();
+    s_scan[tid] += t;
+    __syncthreads();
+  }
+  int k = s_scan[tid] - cnt;
+  const int total = s_scan[nt - 1];
+  for (int i = b; i < e; ++i) {
+    if (tl_vuv(f0, n, i) - tl_vuv(f0, n, i - 1) != 0) { blist[k] = i - k % 2; ++k; }
+  }
+  __syncthreads();
+  return total;
+}
+
+__device__ __forceinline__ double tl_getsec(const TailParams &p, int s, int i) {
+  const int lo = p.sec_lo[s];
+  const int j = i - lo;
+  return (j >= 0 && j < p.sec_len[s]) ? p.secbuf[p.sec_off[s] + j] : 0.0;
+}
+
+// selectBestF0 (harvest.cpp:347-365) by one warp: minimum error, ties -> the LAST candidate
+__device__ __forceinline__ double tl_select_best(double reference_f0, const double *cands, int n, double allowed) {
+  const int lane = threadIdx.x & 31;
+  double best_err = allowed;
+  int best_idx = -1;
+  for (int i = lane; i < n; i += 32) {
+    const double tmp = fabs(reference_f0 - cands[i]) / reference_f0;
+    if (tmp > best_err) continue;
+    best_err = tmp;
+    best_idx = i;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double e2 = __shfl_xor_sync(0xffffffffu, best_err, o);
+    const int i2 = __shfl_xor_sync(0xffffffffu, best_idx, o);
+    // valid entries only (idx >= 0); smaller error wins, equal error -> larger index
+    if (i2 >= 0 && (best_idx < 0 || e2 < best_err || (e2 == best_err && i2 > best_idx))) { best_err = e2; best_idx = i2; }
+  }
+  return best_idx >= 0 ? cands[best_idx] : 0.0;
+}
+
+// extendF0 (harvest.cpp:371-404) by one warp on sparse section s
+__device__ int tl_extend_f0(const TailParams &p, int s, int origin, int last_point, int shift, int nc7) {
+  const int lane = threadIdx.x & 31;
+  double *f = p.secbuf + p.sec_off[s] - p.sec_lo[s];  // f[i] valid for lo <= i <= hi
+  const int threshold = 4;
+  double tmp_f0 = f[origin];
+  int shifted_origin = origin;
+  const int distance = abs(last_point - origin);
+  int count = 0;
+  for (int i = 0; i <= distance; ++i) {
+    const int pos = origin + shift * i + shift;
+    const double v = tl_select_best(tmp_f0, p.cand + (size_t)pos * p.MC, nc7, 0.18);
+    if (lane == 0) f[pos] = v;
+    if (v == 0.0) {
+      count++;
+    } else {
+      tmp_f0 = v;
+      count = 0;
+      shifted_origin = pos;
+    }
+    if (count == threshold) break;
+  }
+  __syncwarp();
+  return shifted_origin;
+}
+
+// searchScore (harvest.cpp:463-470)
+__device__ __forceinline__ double tl_search_score(double f0, const double *cands, const double *scores, int n) {
+  double score = 0.0;
+  for (int i = 0; i < n; ++i)
+    if (f0 == cands[i] && score < scores[i]) score = scores[i];
+  return score;
+}
+
+__device__ __forceinline__ double tl_block_sum(double v, double *red) {
+  return wb_block_sum(v, red);
+}
+
+__global__ void __launch_bounds__(TL_THREADS) harvest_tail_kernel(TailParams p) {
+  __shared__ int s_scan[TL_THREADS];
+  __shared__ double s_red[64];
+  __shared__ int s_i[8];
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+  const int L = p.L, MC = p.MC;
+  const int nc7 = *p.nc * 7;
+
+  // ---- searchF0Base + fixStep1
+  for (int i = tid; i < L; i += nt) {
+    const double *c = p.cand + (size_t)i * MC, *sc = p.score + (size_t)i * MC;
+    double best = 0.0, best_score = 0.0;
+    for (int j = 0; j < nc7; ++j)
+      if (sc[j] > best_score) { best = c[j]; best_score = sc[j]; }
+    p.base[i] = best;
+  }
+  __syncthreads();
+  for (int i = tid; i < L; i += nt) {
+    double v = 0.0;  // entries the reference leaves unwritten read as 0 (zero-filled heap)
+    if (i >= 2 && p.base[i] != 0.0) {
+      const double reference_f0 = p.base[i - 1] * 2 - p.base[i - 2];
+      v = (fabs((p.base[i] - reference_f0) / reference_f0) > 0.008 &&
+           fabs((p.base[i] - p.base[i - 1])) / p.base[i - 1] > 0.008) ? 0.0 : p.base[i];
+    }
+    p.s1[i] = v;
+    p.s2[i] = v;
+  }
+  __syncthreads();
+
+  // ---- fixStep2: drop voiced sections shorter than 6
+  {
+    const int nb = tl_boundaries(p.s1, L, p.blist, s_scan);
+    for (int k = tid; k < nb / 2; k += nt) {
+      const int st = p.blist[2 * k], ed = p.blist[2 * k + 1];
+      if (ed - st >= 6) continue;
+      for (int j = st; j <= ed; ++j) p.s2[j] = 0.0;
+    }
+    __syncthreads();
+  }
+
+  // ---- fixStep3
+  int nsec;
+  {
+    const int nb = tl_boundaries(p.s2, L, p.blist, s_scan);
+    nsec = nb / 2;
+    if (nsec > p.maxsec) {
+      if (tid == 0) atomicExch(p.error_flag, WB_ERR_UNSUPPORTED);
+      nsec = 0;
+    }
+  }
+  if (nsec == 0) {
+    // no voiced section: the reference reads multi_channel_f0[0] of an empty array (undefined);
+    // we define the result as the all-unvoiced contour.
+    for (int i = tid; i < L; i += nt) p.out[i] = 0.0;
+    return;
+  }
+  for (int s = tid; s < nsec; s += nt) {
+    const int st = p.blist[2 * s], ed = p.blist[2 * s + 1];
+    const int lo = max(0, st - TL_MARGIN), hi = min(L - 1, ed + TL_MARGIN);
+    p.sec_st[s] = st; p.sec_ed[s] = ed; p.sec_lo[s] = lo; p.sec_len[s] = hi - lo + 1;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    long long off = 0;
+    for (int s = 0; s < nsec; ++s) { p.sec_off[s] = (int)off; off += p.sec_len[s]; }
+    p.sec_off[nsec] = (int)off;
+    s_i[0] = (off > p.secbuf_cap) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_i[0]) {
+    if (tid == 0) atomicExch(p.error_flag, WB_ERR_UNSUPPORTED);
+    for (int i = tid; i < L; i += nt) p.out[i] = 0.0;
+    return;
+  }
+  // getMultiChannelF0
+  for (int s = 0; s < nsec; ++s) {
+    const int st = p.sec_st[s], ed = p.sec_ed[s], lo = p.sec_lo[s], len = p.sec_len[s], off = p.sec_off[s];
+    for (int j = tid; j < len; j += nt) {
+      const int i = lo + j;
+      p.secbuf[off + j] = (i >= st && i <= ed) ? p.s2[i] : 0.0;
+    }
+  }
+  __syncthreads();
+  // extend (forward first, then backward) + per-section sums for extendSub
+  for (int s = warp; s < nsec; s += nwarps) {
+    const int ed0 = p.sec_ed[s], st0 = p.sec_st[s];
+    const int ed1 = tl_extend_f0(p, s, ed0, min(L - 2, ed0 + 100), 1, nc7);
+    const int st1 = tl_extend_f0(p, s, st0, max(1, st0 - 100), -1, nc7);
+    const double *f = p.secbuf + p.sec_off[s] - p.sec_lo[s];
+    double acc = 0.0;
+    for (int j = st1 + lane; j < ed1; j += 32) acc += f[j];
+    acc = wb_warp_sum(acc);
+    if (lane == 0) { p.sec_st[s] = st1; p.sec_ed[s] = ed1; p.sec_sum[s] = acc; }
+  }
+  __syncthreads();
+  // extendSub (harvest.cpp:443-455); mean_f0 is carried across sections
+  if (tid == 0) {
+    const double threshold2 = 2200.0;
+    int count = 0;
+    double mean_f0 = 0.0;
+    for (int s = 0; s < nsec; ++s) {
+      const int st = p.sec_st[s], ed = p.sec_ed[s];
+      mean_f0 += p.sec_sum[s];
+      mean_f0 /= ed - st;
+      if (threshold2 / mean_f0 < ed - st) {
+        p.kslot[count] = s; p.kb[2 * count] = st; p.kb[2 * count + 1] = ed;
+        count++;
+      }
+    }
+    if (count == 0) { p.kslot[0] = 0; p.kb[0] = p.sec_st[0]; p.kb[1] = p.sec_ed[0]; }
+    s_i[1] = count;
+    // argsort by start (harvest.cpp:510-514); stable insertion sort
+    for (int i = 0; i < count; ++i) p.order[i] = i;
+    for (int i = 1; i < count; ++i) {
+      const int v = p.order[i];
+      int j = i - 1;
+      while (j >= 0 && p.kb[2 * p.order[j]] > p.kb[2 * v]) { p.order[j + 1] = p.order[j]; --j; }
+      p.order[j + 1] = v;
+    }
+  }
+  __syncthreads();
+  const int nkeep = s_i[1];
+  // mergeF0 (harvest.cpp:502-536)
+  {
+    const int s0 = p.kslot[0];
+    for (int i = tid; i < L; i += nt) p.s3[i] = tl_getsec(p, s0, i);
+    __syncthreads();
+    for (int it = 1; it < nkeep; ++it) {
+      const int o = p.order[it];
+      const int so = p.kslot[o];
+      const int index1 = p.kb[2 * o], index2 = p.kb[2 * o + 1];
+      const int st1 = p.kb[0], ed1 = p.kb[1];
+      int new_b0 = st1, new_b1 = ed1;
+      if (index1 - ed1 > 0) {
+        for (int i = index1 + tid; i <= index2; i += nt) p.s3[i] = tl_getsec(p, so, i);
+        new_b0 = index1; new_b1 = index2;
+      } else if (!(st1 <= index1 && ed1 >= index2)) {
+        // mergeF0Sub
+        double sc1 = 0.0, sc2 = 0.0;
+        for (int i = index1 + tid; i <= ed1; i += nt) {
+          const double *c = p.cand + (size_t)i * MC, *sc = p.score + (size_t)i * MC;
+          sc1 += tl_search_score(p.s3[i], c, sc, nc7);
+          sc2 += tl_search_score(tl_getsec(p, so, i), c, sc, nc7);
+        }
+        wb_block_sum2(sc1, sc2, s_red);
+        __syncthreads();
+        if (sc1 > sc2) { for (int i = ed1 + tid; i <= index2; i += nt) p.s3[i] = tl_getsec(p, so, i); }
+        else { for (int i = index1 + tid; i <= index2; i += nt) p.s3[i] = tl_getsec(p, so, i); }
+        new_b1 = index2;
+      }
+      __syncthreads();
+      if (tid == 0) { p.kb[0] = new_b0; p.kb[1] = new_b1; }
+      __syncthreads();
+    }
+  }
+
+  // ---- fixStep4: bridge unvoiced gaps shorter than 9
+  for (int i = tid; i < L; i += nt) p.s4[i] = p.s3[i];
+  __syncthreads();
+  {
+    const int nb = tl_boundaries(p.s3, L, p.blist, s_scan);
+    for (int g = tid; g < nb / 2 - 1; g += nt) {
+      const int ed = p.blist[2 * g + 1], st_next = p.blist[2 * (g + 1)];
+      const int distance = st_next - ed - 1;
+      if (distance >= 9) continue;
+      const double tmp0 = p.s3[ed] + 1;
+      const double tmp1 = p.s3[st_next] - 1;
+      const double coefficient = (tmp1 - tmp0) / (distance + 1.0);
+      int count = 1;
+      for (int j = ed + 1; j <= st_next - 1; ++j) p.s4[j] = tmp0 + coefficient * count++;
+    }
+    __syncthreads();
+  }
+
+  // ---- smoothF0Contour
+  const int Lp = L + 2 * TL_LAG;
+  for (int i = tid; i < Lp; i += nt) p.pad[i] = (i >= TL_LAG && i < TL_LAG + L) ? p.s4[i - TL_LAG] : 0.0;
+  for (int i = tid; i < L; i += nt) p.out[i] = 0.0;
+  __syncthreads();
+  const int nbs = tl_boundaries(p.pad, Lp, p.blist, s_scan);
+  const int nsm = nbs / 2;
+  if (nsm > p.maxsec) {
+    if (tid == 0) atomicExch(p.error_flag, WB_ERR_UNSUPPORTED);
+    return;
+  }
+  // per section: forward outputs on [st, min(ed + LAG, Lp - 1)], stored at fw[fwoff + (i - st)]
+  if (tid == 0) {
+    long long off = 0;
+    int items = 0;
+    for (int s = 0; s < nsm; ++s) {
+      const int st = p.blist[2 * s], ed = p.blist[2 * s + 1];
+      const int flen = min(ed + TL_LAG, Lp - 1) - st + 1;
+      p.sec_st[s] = st; p.sec_ed[s] = ed; p.sec_len[s] = flen; p.sec_off[s] = (int)off;
+      p.sec_lo[s] = items;  // first forward work item of this section
+      off += flen;
+      items += (flen + TL_CHUNK - 1) / TL_CHUNK;
+    }
+    p.sec_lo[nsm] = items;
+    s_i[2] = items;
+    s_i[3] = (off > p.fw_cap) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_i[3]) {
+    if (tid == 0) atomicExch(p.error_flag, WB_ERR_UNSUPPORTED);
+    return;
+  }
+  const double b0 = 0.0078202080334971724, b1 = 0.015640416066994345;
+  const double a0 = 1.7347257688092754, a1 = -0.76600660094326412;
+  const int n_items = s_i[2];
+  // forward pass (harvest.cpp:649-654)
+  for (int item = tid; item < n_items; item += nt) {
+    int lo = 0, hi = nsm - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (p.sec_lo[mid] <= item) lo = mid; else hi = mid - 1; }
+    const int s = lo;
+    const int st = p.sec_st[s], ed = p.sec_ed[s], flen = p.sec_len[s];
+    const int c = item - p.sec_lo[s];
+    const int begin = st + c * TL_CHUNK, end = min(st + flen, begin + TL_CHUNK);
+    double *fw = p.fw + p.sec_off[s] - st;
+    const double x_st = p.pad[st], x_ed = p.pad[ed];
+    double w0 = 0.0, w1 = 0.0;
+    for (int i = max(0, begin - TL_LAG); i < end; ++i) {
+      const double xi = (i < st) ? x_st : (i > ed ? x_ed : p.pad[i]);
+      const double wt = xi + a0 * w0 + a1 * w1;
+      if (i >= begin) fw[i] = b0 * wt + b1 * w0 + b0 * w1;
+      w1 = w0; w0 = wt;
+    }
+  }
+  __syncthreads();
+  // backward pass (harvest.cpp:656-662): outputs on [st, ed]
+  if (tid == 0) {
+    int items = 0;
+    for (int s = 0; s < nsm; ++s) {
+      p.kb[s] = items;
+      items += (p.sec_ed[s] - p.sec_st[s] + 1 + TL_CHUNK - 1) / TL_CHUNK;
+    }
+    p.kb[nsm] = items;
+    s_i[4] = items;
+  }
+  __syncthreads();
+  const int n_items_b = s_i[4];
+  for (int item = tid; item < n_items_b; item += nt) {
+    int lo = 0, hi = nsm - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (p.kb[mid] <= item) lo = mid; else hi = mid - 1; }
+    const int s = lo;
+    const int st = p.sec_st[s], ed = p.sec_ed[s], flen = p.sec_len[s];
+    const int c = item - p.kb[s];
+    const int begin = st + c * TL_CHUNK, end = min(ed + 1, begin + TL_CHUNK);  // outputs [begin, end)
+    const double *fw = p.fw + p.sec_off[s] - st;
+    const int top = min(st + flen - 1, end - 1 + TL_LAG);
+    double w0 = 0.0, w1 = 0.0;
+    for (int j = top; j >= begin; --j) {
+      const double wt = fw[j] + a0 * w0 + a1 * w1;
+      if (j < end) p.out[j - TL_LAG] = b0 * wt + b1 * w0 + b0 * w1;
+      w1 = w0; w0 = wt;
+    }
+  }
+}
+
+// compute(): pick basic_f0 at the frame_period grid (harvest.cpp:199-204)
+__global__ void harvest_pick_kernel(const double *__restrict__ basic_f0, int basic_len, double frame_period,
+                                    int f0_length, double *__restrict__ tpos, double *__restrict__ f0) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= f0_length) return;
+  const double t = i * frame_period / 1000.0;
+  tpos[i] = t;
+  f0[i] = basic_f0[wb_min_i(basic_len - 1, wb_round(t * 1000.0))];
+}
+
+}  // namespace
+
+int wb_harvest_tail(WbWorkspace *ws, const double *d_cand, const double *d_score, const int *d_nc, int L,
+                    int MC, double *d_f0_out, cudaStream_t stream) {
+  TailParams p;
+  p.cand = d_cand; p.score = d_score; p.nc = d_nc; p.L = L; p.MC = MC;
+  double *c = (double *)ws->get("tl_contours", sizeof(double) * (size_t)L * 5);
+  if (!c) return WB_ERR_CUDA;
+  p.base = c; p.s1 = c + L; p.s2 = c + 2 * (size_t)L; p.s3 = c + 3 * (size_t)L; p.s4 = c + 4 * (size_t)L;
+  p.out = d_f0_out;
+  p.blist = (int *)ws->get("tl_blist", sizeof(int) * (L + 2 * TL_LAG + 2));
+  p.maxsec = L / 8 + 4;
+  int *si = (int *)ws->get("tl_secint", sizeof(int) * (size_t)(p.maxsec + 2) * 9);
+  p.sec_sum = (double *)ws->get("tl_secsum", sizeof(double) * (p.maxsec + 2));
+  if (!p.blist || !si || !p.sec_sum) return WB_ERR_CUDA;
+  const int m = p.maxsec + 2;
+  p.sec_st = si; p.sec_ed = si + m; p.sec_lo = si + 2 * m; p.sec_len = si + 3 * m; p.sec_off = si + 4 * m;
+  p.kb = si + 5 * m;  // 2 * m
+  p.kslot = si + 7 * m; p.order = si + 8 * m;
+  p.secbuf_cap = (long long)L + 2LL * (TL_MARGIN + 1) * p.maxsec;
+  p.secbuf = (double *)ws->get("tl_secbuf", sizeof(double) * p.secbuf_cap);
+  p.pad = (double *)ws->get("tl_pad", sizeof(double) * (L + 2 * TL_LAG));
+  p.fw_cap = (long long)L + 2 * TL_LAG + (long long)TL_LAG * p.maxsec;
+  p.fw = (double *)ws->get("tl_fw", sizeof(double) * p.fw_cap);
+  p.error_flag = ws->error_flag();
+  if (!p.secbuf || !p.pad || !p.fw || !p.error_flag) return WB_ERR_CUDA;
+  harvest_tail_kernel<<<1, TL_THREADS, 0, stream>>>(p);
+  WB_CUDA_CHECK(cudaGetLastError());
+  return WB_OK;
+}
+
+int wb_harvest_pick(const double *d_basic_f0, int basic_len, double frame_period, int f0_length, double *d_tpos,
+                    double *d_f0, cudaStream_t stream) {
+  harvest_pick_kernel<<<(f0_length + 255) / 256, 256, 0, stream>>>(d_basic_f0, basic_len, frame_period, f0_length,
+                                                                  d_tpos, d_f0);
+  WB_CUDA_CHECK(cudaGetLastError());
+  return WB_OK;
+}
