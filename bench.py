@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the WORLD hot path on B200.
+
+Metric (BASELINE.json): frames/s (and x real-time) of the full Harvest -> CheapTrick -> D4C ->
+Synthesis chain at 48 kHz / 5 ms frame period.  Workload = BASELINE.json configs[1]: one 10 s
+48 kHz utterance (2001 frames) per GPU per step, synthetic sinusoid-plus-noise speech
+(SURVEY.md section 8d).  With N GPUs every rank analyses/synthesises its own utterance (the path
+shards by utterance with no data-path collective): weak scaling.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One JSON line on stdout (rank 0).  `value` is timed with the inputs already resident in HBM;
+`e2e` goes through the reference-facing class API (four compute() calls, HOST buffers, H2D/D2H
+inside the timed region); `roofline` is the dominant kernel's algorithmic FFT-I/O bytes over its
+live CUDA-event duration; `cpu_baseline` is the reference's own OpenMP build on this host.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FS = 48000
+SECONDS = 10.0
+FRAME_PERIOD = 5.0
+METRIC = "frames/sec, full Harvest->CheapTrick->D4C->Synthesis @48kHz/5ms"
+WORKLOAD = "single 10 s utterance @48 kHz, 5 ms frame period, FFT size 2048 (BASELINE configs[1])"
+
+
+def r2c_bytes(n):  # fp64 input + output of one real transform
+    return 8 * n + 16 * (n // 2 + 1)
+
+
+def c2c_bytes(n):
+    return 32 * n
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                r = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5)
+                parts = [p.strip() for p in r.stdout.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(s[2 + k].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def cpu_reference_run(x, repeat, omp=True):
+    """The reference's own CPU implementation (oracle/_ref, built from /root/reference) on this host."""
+    from oracle import refbin
+    if not refbin.available(omp=omp):
+        return None
+    _, timings = refbin.run_reference(x, FS, stages="hcds", omp=omp, repeat=repeat, write=False)
+    per = [t["harvest_ms"] + t["cheaptrick_ms"] + t["d4c_ms"] + t["synthesis_ms"] for t in timings]
+    return {"ms": per, "threads": timings[0]["threads"], "frames": timings[0]["f0_length"], "stages": timings}
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's OpenMP build, all host threads, same config/metric."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import worldb200  # noqa: F401
+    from worldb200 import signals
+    x = signals.synth_speech(FS, SECONDS, seed=0)
+    res = cpu_reference_run(x, repeat=args.warmup + args.steps, omp=True)
+    if res is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/refrun_omp is not built (run make -C oracle where /root/reference exists)"}))
+        return 0
+    ms = res["ms"][args.warmup:]
+    ms_per_step = float(np.mean(ms))
+    fps = res["frames"] / (ms_per_step / 1e3)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "x_realtime": SECONDS / (ms_per_step / 1e3),
+        "config": {"workload": WORKLOAD, "note": "reference OpenMP build (Makefile flags -O3 -mavx -fopenmp) of /root/reference, one utterance per step"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": res["threads"], "kind": "reference",
+                         "sample": "%d x one 10 s / 48 kHz utterance through refrun_omp (all host threads)" % args.steps},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the worldb200 hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import worldb200 as wb
+    from worldb200 import signals
+    wb._check(wb.lib().wb_init(local_rank), "wb_init")
+    lib_stream = torch.cuda.ExternalStream(wb.stream_handle())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- workload: every rank gets its own utterance (seed = rank)
+    x_host = signals.synth_speech(FS, SECONDS, seed=rank)
+    x_pinned = torch.from_numpy(x_host).pin_memory()
+    d_x = x_pinned.cuda()
+    hopt = wb.HarvestOption(f0_floor=40.0, frame_period=FRAME_PERIOD)     # test/test.cpp:83-87
+    copt = wb.CheapTrickOption(f0_floor=71.0)                             # test/test.cpp:130
+    dopt = wb.D4COption(threshold=0.85)                                   # test/test.cpp:181
+    pl = wb.Pipeline(FS, hopt, copt, dopt)
+    n = len(x_host)
+    L, ny, fft_size = pl.f0_length(n), pl.out_length(n), pl.fft_size
+    bins = fft_size // 2 + 1
+    d_y = torch.empty(ny, dtype=torch.float64, device="cuda")
+    d_f0 = torch.empty(L, dtype=torch.float64, device="cuda")
+    d_tpos = torch.empty(L, dtype=torch.float64, device="cuda")
+    d_sp = torch.empty((L, bins), dtype=torch.float64, device="cuda")
+    d_ap = torch.empty((L, bins), dtype=torch.float64, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def step_resident():
+        pl.run_dev(d_x.data_ptr(), n, d_y=d_y.data_ptr(), y_length=ny, d_tpos=d_tpos.data_ptr(), d_f0=d_f0.data_ptr(),
+                   d_sp=d_sp.data_ptr(), d_ap=d_ap.data_ptr())
+
+    # ---- device-resident throughput (`value`)
+    for _ in range(args.warmup):
+        step_resident()
+    wb.device_synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    launches0 = wb.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.zero_()                      # L2 flush between timed iterations (outside the timed span)
+        torch.cuda.synchronize()
+        ev[k][0].record(lib_stream)
+        step_resident()
+        ev[k][1].record(lib_stream)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = wb.launch_count() - launches0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(sum(step_ms))
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * L / (ms_per_step / 1e3)
+
+    # ---- end to end through the reference-facing class API with HOST buffers (`e2e`)
+    harvest = wb.Harvest(FS, hopt)
+    cheaptrick = wb.CheapTrick(FS, copt)
+    d4c = wb.D4C(FS, dopt)
+    synthesis = wb.Synthesis(FS, cheaptrick.fft_size, FRAME_PERIOD)
+    x_np = x_pinned.numpy()
+
+    def step_e2e():
+        tpos, f0 = harvest.compute(x_np)
+        sp = cheaptrick.compute(x_np, tpos, f0)
+        ap = d4c.compute(x_np, tpos, f0, cheaptrick.fft_size)
+        return synthesis.compute(f0, sp, ap, ny)
+
+    for _ in range(args.warmup):
+        step_e2e()
+    barrier()
+    e2e_ms = 0.0
+    for k in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        y_host = step_e2e()                # synchronous: returns after the D2H of the waveform
+        e2e_ms += (time.perf_counter() - t0) * 1e3
+    barrier()
+    if world > 1:
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = world * L / (e2e_ms / args.steps / 1e3)
+    h2d = 8 * (3 * n + 2 * 2 * L + L + 2 * L * bins)      # x x3, (tpos,f0) x2, f0, sp+ap rows for Synthesis
+    d2h = 8 * (2 * L + 2 * L * bins + ny)                 # tpos,f0; sp; ap; y
+    if rank == 0:
+        sampler.stop_flag.set()
+        sampler.join(timeout=2)
+
+    # ---- per-kernel live timing for the roofline line (separate pass, CUDA events per launch)
+    roofline = None
+    kernel_table = {}
+    if rank == 0:
+        wb.profile_reset()
+        wb.profile(True)
+        for _ in range(args.steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            step_resident()
+        kernel_table = wb.profile_results()
+        wb.profile(False)
+        f0_h = d_f0.cpu().numpy()
+        ap_h = d_ap.cpu().numpy()
+        voiced_lt = int(np.sum(f0_h != 0))
+        voiced_body = int(np.sum(np.any(ap_h != 1.0 - 1e-12, axis=1)))
+        n_ap = wb.lib().wb_get_number_of_aperiodicities(FS)
+        n_d4c = 1 << int(np.floor(np.log2(4.0 * FS / 47.0 + 1)) + 1)
+        n_lt = 1 << int(np.floor(np.log2(3.0 * FS / 40.0 + 1)) + 1)
+        # Harvest: counts from the last run's device buffers
+        r = min(max(int(FS / 8000.0 + 0.5), 1), 12)
+        afs = FS / r
+        Lb = int(1000.0 * n / FS / 1) + 1
+        nch = 1 + int(np.log(800.0 * 1.1 / (40.0 * 0.9)) / 0.69314718055994529 * 40.0)
+        mc = int(nch // 10) * 7
+        own_cap = mc // 7
+        nc = int(pl.debug_read("hv_nc", (4,), dtype=np.int32)[0])
+        own = pl.debug_read("hv_own", (Lb, own_cap))[:, :max(nc, 1)]
+        # overlapF0Candidates replicates every own candidate to frames k-3..k+3 (harvest.cpp:987-1000)
+        refine_bytes = 0
+        f = own[own > 0]
+        if f.size:
+            hw = (1.5 * afs / f + 1.0).astype(np.int64)
+            n_i = 1 << (2 + np.floor(np.log2(2 * hw + 1)).astype(np.int64))
+            per = 2 * (8 * n_i + 16 * (n_i // 2 + 1))
+            refine_bytes = int(7 * per.sum())   # edge frames lose a few copies: <0.1 %
+        y_len = 1 + n // r
+        n_h = 1 << int(np.floor(np.log2(y_len + 4 * int(1.0 + afs / (40.0 * 0.9 * 2 ** (1 / 40.0)) / 2.0))) + 1)
+        n_pulses = int(pl.debug_read("syn_np", (1,), dtype=np.int32)[0])
+        alg = {
+            "ct_frame_kernel": 3 * L * r2c_bytes(fft_size),
+            "lt_frame_kernel": voiced_lt * r2c_bytes(n_lt),
+            "d4c_body_kernel": voiced_body * (5 + n_ap) * r2c_bytes(n_d4c),
+            "channel_kernel": 2 * nch * r2c_bytes(n_h),          # reference: r2c + c2r of N_h per channel
+            "yspec_kernel": r2c_bytes(n_h),
+            "refine_kernel": refine_bytes,
+            "response_kernel": n_pulses * (5 * r2c_bytes(fft_size) + 2 * c2c_bytes(fft_size)),
+        }
+        dom = max(kernel_table.items(), key=lambda kv: kv[1][0])[0] if kernel_table else None
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dom)
+        except Exception:
+            pass
+        if dom is not None:
+            tot_ms, cnt = kernel_table[dom]
+            avg_ms = tot_ms / max(cnt, 1)
+            a_bytes = alg.get(dom)
+            achieved = (a_bytes / (avg_ms / 1e3) / 1e9) if a_bytes else None
+            roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                        "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                        "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                        "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": a_bytes,
+                        "kernel_share_of_step": tot_ms / max(sum(v[0] for v in kernel_table.values()), 1e-9),
+                        "algorithmic_bytes_per_step_all_kernels": int(sum(alg.values())),
+                        "whole_chain_frac": (sum(alg.values()) / (ms_per_step / 1e3) / 1e9) / peak}
+
+    # ---- CPU baseline: the reference's OpenMP build on this host, bounded sample
+    cpu_baseline = None
+    if rank == 0 and not args.no_cpu_baseline:
+        res = cpu_reference_run(x_host, repeat=3, omp=True)
+        if res is not None:
+            ms = float(np.median(res["ms"]))
+            cpu_baseline = {"value": res["frames"] / (ms / 1e3), "unit": "frames/s", "cores": res["threads"],
+                            "kind": "reference", "ms_per_utterance": ms,
+                            "sample": "3 x the same 10 s / 48 kHz utterance through oracle/_ref/refrun_omp (reference OpenMP build), median"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "x_realtime": world * SECONDS / (ms_per_step / 1e3),
+            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": L, "utterances_per_step_per_gpu": 1,
+                       "parallelism": "one utterance per GPU, no data-path collective",
+                       "l2": "256 MiB device memset between timed iterations (flush); inputs 3.8 MB"},
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / args.steps, "x_realtime": world * SECONDS / (e2e_ms / args.steps / 1e3),
+                    "path": "Harvest/CheapTrick/D4C/Synthesis compute() with host buffers (pinned x), 4 calls per step"},
+            "gpu_launches": launches,
+            "clocks": sampler.summary(),
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+            "kernels_ms_per_step": {k: v[0] / args.steps for k, v in sorted(kernel_table.items(), key=lambda kv: -kv[1][0])},
+            "wall_s_timed_region": t_wall,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

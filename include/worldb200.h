@@ -58,6 +58,7 @@ typedef struct wb_harvest wb_harvest_t;
 typedef struct wb_cheaptrick wb_cheaptrick_t;
 typedef struct wb_d4c wb_d4c_t;
 typedef struct wb_synthesis wb_synthesis_t;
+typedef struct wb_pipeline wb_pipeline_t;
 
 /* ---- library ---------------------------------------------------------------------- */
 int wb_init(int device);                /* optional; otherwise lazily on first use (current device) */
@@ -130,6 +131,35 @@ int wb_synthesis_compute(wb_synthesis_t *h, const double *f0, int f0_length,
 int wb_synthesis_compute_dev(wb_synthesis_t *h, const double *d_f0, int f0_length,
                              const double *d_spectrogram, const double *d_aperiodicity,
                              int out_length, double *d_out, double f0_upper_bound, void *stream);
+
+/* ---- whole chain, device resident -----------------------------------------------------
+ * The call sequence of test/test.cpp:288-384 (Harvest -> CheapTrick -> D4C -> Synthesis) with
+ * every intermediate kept in HBM.  NULL option pointers = defaults; NULL output pointers in
+ * *_run_dev = internal buffers.  spectrogram / aperiodicity are contiguous [f0_length][fft_size/2+1]. */
+int wb_pipeline_create(int fs, const WbHarvestOption *hopt, const WbCheapTrickOption *copt,
+                       const WbD4COption *dopt, wb_pipeline_t **out);
+void wb_pipeline_destroy(wb_pipeline_t *p);
+int wb_pipeline_fft_size(const wb_pipeline_t *p);
+int wb_pipeline_f0_length(const wb_pipeline_t *p, int x_length);      /* src/harvest.cpp:173-181 */
+int wb_pipeline_out_length(const wb_pipeline_t *p, int x_length);     /* test/test.cpp:362-363 */
+int wb_pipeline_run_dev(wb_pipeline_t *p, const double *d_x, int x_length, double *d_temporal_positions,
+                        double *d_f0, double *d_spectrogram, double *d_aperiodicity, double *d_y,
+                        int y_length, void *stream);
+int wb_pipeline_run(wb_pipeline_t *p, const double *x, int x_length, double *temporal_positions_or_null,
+                    double *f0_or_null, double *spectrogram_or_null, double *aperiodicity_or_null,
+                    double *y, int y_length);
+
+/* test / bench hook: copies n_bytes of a named internal device buffer of the last run to `out` */
+int wb_pipeline_debug_read(wb_pipeline_t *p, const char *name, void *out, unsigned long long n_bytes);
+
+/* ---- measurement hooks (bench.py) ------------------------------------------------------ */
+unsigned long long wb_launch_count(void);  /* kernels launched by this library so far */
+void *wb_stream(void);                     /* the library's own cudaStream_t */
+void wb_profile_enable(int on);            /* bracket every kernel launch with CUDA events */
+void wb_profile_reset(void);
+int wb_profile_collect(void);              /* synchronises; folds pending events into totals */
+int wb_profile_query(const char *kernel_name, double *total_ms, int *count);
+int wb_profile_names(char *buf, int buf_len);  /* ';'-separated kernel names seen so far */
 
 #ifdef __cplusplus
 }

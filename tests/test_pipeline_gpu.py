@@ -1,0 +1,59 @@
+"""GPU parity of the whole chain (test/test.cpp call sequence) against one reference process."""
+import numpy as np
+import pytest
+
+from oracle import refbin
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+
+
+def _check_chain(out, ref):
+    assert np.array_equal(out["tpos"], ref["tpos"])
+    assert np.array_equal(out["f0"] > 0, ref["f0"] > 0)           # voicing decisions: exact
+    v = ref["f0"] > 0
+    assert np.max(np.abs(out["f0"][v] - ref["f0"][v]) / ref["f0"][v]) < RTOL
+    assert np.max(np.abs(out["sp"] - ref["sp"]) / ref["sp"]) < RTOL
+    assert np.max(np.abs(out["ap"] - ref["ap"]) / ref["ap"]) < RTOL
+    peak = np.abs(ref["y"]).max()
+    assert np.max(np.abs(out["y"] - ref["y"])) / peak < RTOL
+
+
+@pytest.mark.parametrize("fs,seconds,seed", [(16000, 1.0, 0), (22050, 5.0, 1000), (48000, 10.0, 0)])
+def test_pipeline_matches_reference(wb, signals, fs, seconds, seed):
+    """configs[0] (16 kHz / 1 s), one utterance of configs[2] (22.05 kHz / 5 s) and configs[1] (48 kHz / 10 s)."""
+    x = signals.synth_speech(fs, seconds, seed=seed)
+    ref, _ = refbin.run_reference(x, fs, stages="hcds")
+    wb.randn_reseed()
+    pl = wb.Pipeline(fs, wb.HarvestOption(f0_floor=40.0, frame_period=5.0), wb.CheapTrickOption(f0_floor=71.0),
+                     wb.D4COption(threshold=0.85))
+    out = pl.run(x)
+    assert pl.fft_size == ref["fft_size"]
+    _check_chain(out, ref)
+
+
+def test_class_api_chain_matches_reference(wb, signals):
+    """The four stage objects called like test.cpp does, host buffers throughout."""
+    fs = 16000
+    x = signals.synth_speech(fs, 1.0, seed=7)
+    ref, _ = refbin.run_reference(x, fs, stages="hcds")
+    wb.randn_reseed()
+    tpos, f0 = wb.Harvest(fs, wb.HarvestOption(f0_floor=40.0, frame_period=5.0)).compute(x)
+    ct = wb.CheapTrick(fs, wb.CheapTrickOption(f0_floor=71.0))
+    sp = ct.compute(x, tpos, f0)
+    ap = wb.D4C(fs, wb.D4COption(threshold=0.85)).compute(x, tpos, f0, ct.fft_size)
+    y = wb.Synthesis(fs, ct.fft_size, 5.0).compute(f0, sp, ap, wb.synthesis_length(len(f0), 5.0, fs))
+    _check_chain(dict(tpos=tpos, f0=f0, sp=sp, ap=ap, y=y), ref)
+
+
+def test_silence_edges(wb, signals):
+    """Digital silence at both ends (SURVEY section 8d parity-only case): envelope and aperiodicity of
+    silent frames are pure functions of the randn() stream, so this pins the exact noise placement."""
+    fs = 16000
+    x = signals.silence_edge(fs, 1.0, seed=8)
+    ref, _ = refbin.run_reference(x, fs, stages="hcds")
+    wb.randn_reseed()
+    pl = wb.Pipeline(fs, wb.HarvestOption(f0_floor=40.0, frame_period=5.0), wb.CheapTrickOption(f0_floor=71.0))
+    out = pl.run(x)
+    _check_chain(out, ref)

@@ -91,6 +91,22 @@ def _declare(L):
         "wb_cheaptrick_compute": (ci, [vp, vp, ci, vp, vp, ci, vp]),
         "wb_cheaptrick_compute_dev": (ci, [vp, vp, ci, vp, vp, ci, vp, vp]),
         "wb_get_number_of_aperiodicities": (ci, [ci]),
+        "wb_pipeline_create": (ci, [ci, ctypes.POINTER(HarvestOption), ctypes.POINTER(CheapTrickOption),
+                                    ctypes.POINTER(D4COption), ctypes.POINTER(vp)]),
+        "wb_pipeline_destroy": (None, [vp]),
+        "wb_pipeline_fft_size": (ci, [vp]),
+        "wb_pipeline_f0_length": (ci, [vp, ci]),
+        "wb_pipeline_out_length": (ci, [vp, ci]),
+        "wb_pipeline_run_dev": (ci, [vp, vp, ci, vp, vp, vp, vp, vp, ci, vp]),
+        "wb_pipeline_run": (ci, [vp, vp, ci, vp, vp, vp, vp, vp, ci]),
+        "wb_pipeline_debug_read": (ci, [vp, ctypes.c_char_p, vp, ctypes.c_ulonglong]),
+        "wb_launch_count": (ctypes.c_ulonglong, []),
+        "wb_stream": (vp, []),
+        "wb_profile_enable": (None, [ci]),
+        "wb_profile_reset": (None, []),
+        "wb_profile_collect": (ci, []),
+        "wb_profile_query": (ci, [ctypes.c_char_p, ctypes.POINTER(cd), ctypes.POINTER(ci)]),
+        "wb_profile_names": (ci, [ctypes.c_char_p, ci]),
         "wb_synthesis_create": (ci, [ci, ci, cd, ctypes.POINTER(vp)]),
         "wb_synthesis_destroy": (None, [vp]),
         "wb_synthesis_compute": (ci, [vp, vp, ci, vp, vp, ci, vp]),
@@ -308,3 +324,85 @@ class Synthesis:
 def synthesis_length(f0_length, frame_period, fs):
     """test/test.cpp:362-363"""
     return int((f0_length - 1) * frame_period / 1000.0 * fs) + 1
+
+
+# ---- whole chain, device resident (test/test.cpp:288-384) ------------------------------------
+class Pipeline:
+    """Harvest -> CheapTrick -> D4C -> Synthesis with every intermediate kept in HBM."""
+
+    def __init__(self, fs, harvest_option=None, cheaptrick_option=None, d4c_option=None):
+        self._h = ctypes.c_void_p()
+        self.fs = int(fs)
+        ref = lambda o: ctypes.byref(o) if o is not None else None
+        _check(lib().wb_pipeline_create(self.fs, ref(harvest_option), ref(cheaptrick_option), ref(d4c_option),
+                                        ctypes.byref(self._h)), "wb_pipeline_create")
+        self.fft_size = lib().wb_pipeline_fft_size(self._h)
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.wb_pipeline_destroy(self._h)
+            self._h = None
+
+    def f0_length(self, x_length):
+        return lib().wb_pipeline_f0_length(self._h, int(x_length))
+
+    def out_length(self, x_length):
+        return lib().wb_pipeline_out_length(self._h, int(x_length))
+
+    def run(self, x, want_params=True):
+        """host x -> dict(tpos, f0, sp, ap, y) on the host"""
+        x = _f64(x)
+        L, bins, ny = self.f0_length(len(x)), self.fft_size // 2 + 1, self.out_length(len(x))
+        y = np.empty(ny, dtype=np.float64)
+        out = {"y": y}
+        ptr = lambda a: a.ctypes.data if a is not None else None
+        if want_params:
+            out.update(tpos=np.empty(L), f0=np.empty(L), sp=np.empty((L, bins)), ap=np.empty((L, bins)))
+        _check(lib().wb_pipeline_run(self._h, x.ctypes.data, len(x), ptr(out.get("tpos")), ptr(out.get("f0")),
+                                     ptr(out.get("sp")), ptr(out.get("ap")), y.ctypes.data, ny), "wb_pipeline_run")
+        return out
+
+    def debug_read(self, name, shape, dtype=np.float64):
+        out = np.empty(shape, dtype=dtype)
+        _check(lib().wb_pipeline_debug_read(self._h, name.encode(), out.ctypes.data, out.nbytes), "wb_pipeline_debug_read")
+        return out
+
+    def run_dev(self, d_x, x_length, d_y=0, y_length=None, stream=0, d_tpos=0, d_f0=0, d_sp=0, d_ap=0):
+        """device pointers (ints); asynchronous on `stream` (0 = the library's stream)"""
+        ny = self.out_length(x_length) if y_length is None else int(y_length)
+        _check(lib().wb_pipeline_run_dev(self._h, d_x, int(x_length), d_tpos or None, d_f0 or None, d_sp or None,
+                                         d_ap or None, d_y or None, ny, stream or None), "wb_pipeline_run_dev")
+
+
+# ---- measurement hooks ------------------------------------------------------------------------
+def launch_count():
+    return int(lib().wb_launch_count())
+
+
+def stream_handle():
+    return lib().wb_stream()
+
+
+def device_synchronize():
+    _check(lib().wb_device_synchronize(), "wb_device_synchronize")
+
+
+def profile(enable):
+    lib().wb_profile_enable(1 if enable else 0)
+
+
+def profile_reset():
+    lib().wb_profile_reset()
+
+
+def profile_results():
+    """{kernel name: (total_ms, launches)} of everything launched while profiling was enabled."""
+    _check(lib().wb_profile_collect(), "wb_profile_collect")
+    buf = ctypes.create_string_buffer(1 << 16)
+    _check(lib().wb_profile_names(buf, len(buf)), "wb_profile_names")
+    res = {}
+    for name in [n for n in buf.value.decode().split(";") if n]:
+        ms, cnt = ctypes.c_double(), ctypes.c_int()
+        _check(lib().wb_profile_query(name.encode(), ctypes.byref(ms), ctypes.byref(cnt)), "wb_profile_query")
+        res[name] = (ms.value, cnt.value)
+    return res

@@ -79,6 +79,15 @@ struct wb_harvest {
   WbWorkspace ws;
 };
 
+struct wb_pipeline {
+  int fs;
+  WbHarvestPlan plan;
+  WbCheapTrickOption ct;
+  double ct_f0_floor_internal;
+  WbD4COption d4c;
+  WbWorkspace ws;
+};
+
 struct wb_d4c {
   int fs;
   WbD4COption opt;
@@ -415,5 +424,130 @@ int wb_harvest_debug_read(wb_harvest_t *h, const char *name, void *out, unsigned
   WB_CUDA_CHECK(cudaMemcpy(out, d, n_bytes, cudaMemcpyDeviceToHost));
   return WB_OK;
 }
+
+// ---- whole chain, device resident (test/test.cpp:288-384 call sequence) -----------------------
+int wb_pipeline_create(int fs, const WbHarvestOption *hopt, const WbCheapTrickOption *copt, const WbD4COption *dopt,
+                       wb_pipeline_t **out) {
+  if (!out || fs <= 0) return WB_ERR_ARG;
+  int rc = ctx_init();
+  if (rc) return rc;
+  WbHarvestOption ho;
+  wb_harvest_option_default(&ho);
+  if (hopt) ho = *hopt;
+  if (ho.use_cos_table) return WB_ERR_UNSUPPORTED;
+  wb_pipeline *p = new (std::nothrow) wb_pipeline();
+  if (!p) return WB_ERR_ARG;
+  p->fs = fs;
+  WbHarvestOptionInternal oi = {ho.f0_floor, ho.f0_ceil, ho.frame_period, ho.target_fs, ho.channels_in_octave};
+  rc = wb_harvest_plan_init(&p->plan, fs, oi);
+  if (rc) { delete p; return rc; }
+  wb_cheaptrick_option_default(&p->ct);
+  if (copt) p->ct = *copt;
+  if (p->ct.fft_size == 0) p->ct.fft_size = wb_cheaptrick_get_fft_size(fs, p->ct.f0_floor);
+  p->ct_f0_floor_internal = wb_cheaptrick_get_f0_floor(fs, p->ct.fft_size);
+  wb_d4c_option_default(&p->d4c);
+  if (dopt) p->d4c = *dopt;
+  *out = p;
+  return WB_OK;
+}
+
+void wb_pipeline_destroy(wb_pipeline_t *p) { delete p; }
+int wb_pipeline_fft_size(const wb_pipeline_t *p) { return p ? p->ct.fft_size : 0; }
+int wb_pipeline_f0_length(const wb_pipeline_t *p, int x_length) {
+  return p ? wb_harvest_get_samples(p->fs, x_length, p->plan.opt.frame_period) : 0;
+}
+int wb_pipeline_out_length(const wb_pipeline_t *p, int x_length) {  // test/test.cpp:362-363
+  if (!p) return 0;
+  const int f0_length = wb_pipeline_f0_length(p, x_length);
+  return static_cast<int>((f0_length - 1) * p->plan.opt.frame_period / 1000.0 * p->fs) + 1;
+}
+
+int wb_pipeline_run_dev(wb_pipeline_t *p, const double *d_x, int x_length, double *d_tpos, double *d_f0,
+                        double *d_sp, double *d_ap, double *d_y, int y_length, void *stream) {
+  if (!p || !d_x || x_length <= 0 || y_length < 0) return WB_ERR_ARG;
+  cudaStream_t st = pick_stream(stream);
+  const int fs = p->fs;
+  const double fp = p->plan.opt.frame_period;
+  const int f0_length = wb_pipeline_f0_length(p, x_length);
+  const int bins = p->ct.fft_size / 2 + 1;
+  if (!d_tpos) d_tpos = (double *)p->ws.get("pl_tpos", sizeof(double) * f0_length);
+  if (!d_f0) d_f0 = (double *)p->ws.get("pl_f0", sizeof(double) * f0_length);
+  if (!d_sp) d_sp = (double *)p->ws.get("pl_sp", sizeof(double) * (size_t)f0_length * bins);
+  if (!d_ap) d_ap = (double *)p->ws.get("pl_ap", sizeof(double) * (size_t)f0_length * bins);
+  if (!d_y && y_length > 0) d_y = (double *)p->ws.get("pl_y", sizeof(double) * (size_t)y_length);
+  if (!d_tpos || !d_f0 || !d_sp || !d_ap) return WB_ERR_CUDA;
+  int rc, Lb = 0;
+  // Harvest (always analysed on the 1 ms grid, harvest.cpp:185-204)
+  if (fp == 1.0) {
+    if ((rc = wb_harvest_run_basic(&p->plan, &p->ws, d_x, x_length, 1, d_f0, &Lb, st))) return rc;
+    if ((rc = wb_harvest_pick(d_f0, Lb, 1.0, Lb, d_tpos, d_f0, st))) return rc;
+  } else {
+    const int Lb_expected = wb_harvest_get_samples(fs, x_length, 1.0);
+    double *d_basic = (double *)p->ws.get("hv_basic_f0", sizeof(double) * Lb_expected);
+    if (!d_basic) return WB_ERR_CUDA;
+    if ((rc = wb_harvest_run_basic(&p->plan, &p->ws, d_x, x_length, 1, d_basic, &Lb, st))) return rc;
+    if ((rc = wb_harvest_pick(d_basic, Lb, fp, f0_length, d_tpos, d_f0, st))) return rc;
+  }
+  WbRngState *rng = wb_rng_global_state();
+  if ((rc = wb_cheaptrick_run(&p->ws, fs, p->ct.fft_size, p->ct.q1, p->ct_f0_floor_internal, d_x, x_length, d_tpos,
+                              d_f0, f0_length, d_sp, rng, st)))
+    return rc;
+  if ((rc = wb_d4c_run(&p->ws, fs, p->d4c.threshold, d_x, x_length, d_tpos, d_f0, f0_length, p->ct.fft_size, d_ap,
+                       rng, st)))
+    return rc;
+  if (y_length > 0) {
+    if (!d_y) return WB_ERR_CUDA;
+    // Harvest's contour is bounded by f0_ceil up to the smoothing overshoot
+    const double f0_bound = p->plan.opt.f0_ceil * 1.25;
+    if ((rc = wb_synthesis_run(&p->ws, fs, p->ct.fft_size, fp, d_f0, f0_length, d_sp, d_ap, y_length, d_y, f0_bound,
+                               rng, st)))
+      return rc;
+  }
+  return WB_OK;
+}
+
+int wb_pipeline_run(wb_pipeline_t *p, const double *x, int x_length, double *tpos, double *f0, double *sp,
+                    double *ap, double *y, int y_length) {
+  if (!p || !x || x_length <= 0 || y_length < 0 || (y_length > 0 && !y)) return WB_ERR_ARG;
+  cudaStream_t st = g_stream;
+  const int f0_length = wb_pipeline_f0_length(p, x_length);
+  const int bins = p->ct.fft_size / 2 + 1;
+  double *d_x;
+  int rc;
+  if ((rc = vec_to_device(&p->ws, "h_x", x, x_length, &d_x, st))) return rc;
+  double *d_t = (double *)p->ws.get("pl_tpos", sizeof(double) * f0_length);
+  double *d_f = (double *)p->ws.get("pl_f0", sizeof(double) * f0_length);
+  double *d_sp = (double *)p->ws.get("pl_sp", sizeof(double) * (size_t)f0_length * bins);
+  double *d_ap = (double *)p->ws.get("pl_ap", sizeof(double) * (size_t)f0_length * bins);
+  double *d_y = (double *)p->ws.get("pl_y", sizeof(double) * (size_t)(y_length > 0 ? y_length : 1));
+  if (!d_t || !d_f || !d_sp || !d_ap || !d_y) return WB_ERR_CUDA;
+  if ((rc = wb_pipeline_run_dev(p, d_x, x_length, d_t, d_f, d_sp, d_ap, d_y, y_length, st))) return rc;
+  if (tpos) WB_CUDA_CHECK(cudaMemcpyAsync(tpos, d_t, sizeof(double) * f0_length, cudaMemcpyDeviceToHost, st));
+  if (f0) WB_CUDA_CHECK(cudaMemcpyAsync(f0, d_f, sizeof(double) * f0_length, cudaMemcpyDeviceToHost, st));
+  if (sp) WB_CUDA_CHECK(cudaMemcpyAsync(sp, d_sp, sizeof(double) * (size_t)f0_length * bins, cudaMemcpyDeviceToHost, st));
+  if (ap) WB_CUDA_CHECK(cudaMemcpyAsync(ap, d_ap, sizeof(double) * (size_t)f0_length * bins, cudaMemcpyDeviceToHost, st));
+  if (y_length > 0) WB_CUDA_CHECK(cudaMemcpyAsync(y, d_y, sizeof(double) * (size_t)y_length, cudaMemcpyDeviceToHost, st));
+  WB_CUDA_CHECK(cudaStreamSynchronize(st));
+  return p->ws.read_error_flag(st);
+}
+
+/* test / bench hook: copies n_bytes of a named internal device buffer of the last run */
+int wb_pipeline_debug_read(wb_pipeline_t *p, const char *name, void *out, unsigned long long n_bytes) {
+  if (!p || !name || !out) return WB_ERR_ARG;
+  void *d = p->ws.get(name, 0);
+  if (!d) return WB_ERR_ARG;
+  WB_CUDA_CHECK(cudaDeviceSynchronize());
+  WB_CUDA_CHECK(cudaMemcpy(out, d, n_bytes, cudaMemcpyDeviceToHost));
+  return WB_OK;
+}
+
+// ---- measurement hooks ---------------------------------------------------------------------
+unsigned long long wb_launch_count(void) { return wb_launch_counter(); }
+void *wb_stream(void) { return ctx_init() ? nullptr : (void *)g_stream; }
+void wb_profile_enable(int on) { wb_prof_set_enabled(on); }
+void wb_profile_reset(void) { wb_prof_reset(); }
+int wb_profile_collect(void) { return wb_prof_collect(); }
+int wb_profile_query(const char *kernel_name, double *total_ms, int *count) { return wb_prof_query(kernel_name, total_ms, count); }
+int wb_profile_names(char *buf, int buf_len) { return wb_prof_names(buf, buf_len); }
 
 }  // extern "C"

@@ -149,7 +149,7 @@ int wb_cheaptrick_run(WbWorkspace *ws, int fs, int fft_size, double q1, double f
   double *d_noise = (double *)ws->get("noise", sizeof(double) * max_noise);
   if (!d_counts || !d_offsets || !d_noise) return WB_ERR_CUDA;
 
-  ct_count_kernel<<<(f0_length + 255) / 256, 256, 0, stream>>>(d_f0, f0_length, fs, fft_size, f0_floor_internal, d_counts);
+  WB_LAUNCH("ct_count_kernel", ct_count_kernel<<<(f0_length + 255) / 256, 256, 0, stream>>>(d_f0, f0_length, fs, fft_size, f0_floor_internal, d_counts));
   int rc = wb_exclusive_scan_u64(d_counts, d_offsets, f0_length, stream);  // d_offsets[f0_length] = total
   if (rc) return rc;
   rc = wb_rng_fill(d_rng, d_offsets + f0_length, max_noise, d_noise, stream);
@@ -164,7 +164,7 @@ int wb_cheaptrick_run(WbWorkspace *ws, int fs, int fft_size, double q1, double f
   const size_t smem = wb_cheaptrick_smem_bytes(fft_size, p.seg_capacity);
   WB_CUDA_CHECK(cudaFuncSetAttribute(ct_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int threads = wb_max_i(64, wb_min_i(256, fft_size / 8));
-  ct_frame_kernel<<<f0_length, threads, smem, stream>>>(p);
+  WB_LAUNCH("ct_frame_kernel", ct_frame_kernel<<<f0_length, threads, smem, stream>>>(p));
   WB_CUDA_CHECK(cudaGetLastError());
   return wb_rng_advance(d_rng, d_offsets + f0_length, stream);
 }

@@ -115,3 +115,27 @@ __device__ inline void wb_block_inclusive_scan(double *a, int n, double *red) {
   }
   __syncthreads();
 }
+
+// ---- launch accounting / per-kernel timing (wb_runtime.cu) ---------------------------------
+// Every kernel launch of the library goes through WB_LAUNCH: it counts launches (bench.py's
+// gpu_launches) and, when profiling is enabled, brackets the launch with CUDA events on the
+// launching stream so that bench.py can report the dominant kernel's live duration.
+struct WbLaunchScope {
+  WbLaunchScope(const char *name, cudaStream_t stream);
+  ~WbLaunchScope();
+  const char *name_;
+  cudaStream_t stream_;
+  void *ev0_;
+};
+#define WB_LAUNCH(NAME, ...)               \
+  do {                                     \
+    WbLaunchScope _wb_scope(NAME, stream); \
+    __VA_ARGS__;                           \
+  } while (0)
+unsigned long long wb_launch_counter();
+void wb_prof_set_enabled(int on);
+// synchronises the device, folds all pending event pairs into per-name totals
+int wb_prof_collect();
+int wb_prof_query(const char *name, double *total_ms, int *count);
+int wb_prof_names(char *buf, int buf_len);  // ';'-separated
+void wb_prof_reset();

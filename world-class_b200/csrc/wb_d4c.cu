@@ -366,8 +366,8 @@ int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int
 
   // rows start as 1 - kMySafeGuardMinimum (d4c.cpp:127-132)
   const size_t n_out = (size_t)f0_length * out_bins;
-  fill_kernel<<<(unsigned)((n_out + 1023) / 1024 < 4096 ? (n_out + 1023) / 1024 : 4096), 256, 0, stream>>>(
-      d_ap, n_out, 1.0 - WB_SAFEGUARD);
+  WB_LAUNCH("fill_kernel", fill_kernel<<<(unsigned)((n_out + 1023) / 1024 < 4096 ? (n_out + 1023) / 1024 : 4096), 256, 0, stream>>>(
+      d_ap, n_out, 1.0 - WB_SAFEGUARD));
 
   unsigned long long *d_counts = (unsigned long long *)ws->get("d4c_counts", sizeof(unsigned long long) * (f0_length + 1));
   unsigned long long *d_offsets = (unsigned long long *)ws->get("d4c_offsets", sizeof(unsigned long long) * (f0_length + 1));
@@ -398,7 +398,7 @@ int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int
 
   const int cb = (f0_length + 255) / 256;
   // ---- Love Train
-  lt_count_kernel<<<cb, 256, 0, stream>>>(d_f0, f0_length, fs, 40.0, d_counts);
+  WB_LAUNCH("lt_count_kernel", lt_count_kernel<<<cb, 256, 0, stream>>>(d_f0, f0_length, fs, 40.0, d_counts));
   int rc = wb_exclusive_scan_u64(d_counts, d_offsets, f0_length, stream);
   if (rc) return rc;
   if ((rc = wb_rng_fill(d_rng, d_offsets + f0_length, max_noise_lt, d_noise, stream))) return rc;
@@ -412,13 +412,13 @@ int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int
     p.twiddle = tw_lt; p.noise = d_noise; p.noise_off = d_offsets; p.ap0 = d_ap0;
     const size_t smem = sizeof(cplx) * wb_fft_slots(N_lt / 2) + sizeof(double) * (N_lt + 128);
     WB_CUDA_CHECK(cudaFuncSetAttribute(lt_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    lt_frame_kernel<<<f0_length, 256, smem, stream>>>(p);
+    WB_LAUNCH("lt_frame_kernel", lt_frame_kernel<<<f0_length, 256, smem, stream>>>(p));
     WB_CUDA_CHECK(cudaGetLastError());
   }
   if ((rc = wb_rng_advance(d_rng, d_offsets + f0_length, stream))) return rc;
 
   // ---- body
-  body_count_kernel<<<cb, 256, 0, stream>>>(d_f0, d_ap0, f0_length, fs, threshold, d_counts);
+  WB_LAUNCH("body_count_kernel", body_count_kernel<<<cb, 256, 0, stream>>>(d_f0, d_ap0, f0_length, fs, threshold, d_counts));
   if ((rc = wb_exclusive_scan_u64(d_counts, d_offsets, f0_length, stream))) return rc;
   if ((rc = wb_rng_fill(d_rng, d_offsets + f0_length, max_noise_body, d_noise, stream))) return rc;
   {
@@ -434,7 +434,7 @@ int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int
     const size_t smem = sizeof(cplx) * wb_fft_slots(N) + sizeof(double) * (3 * binsp + p.seg_capacity + 1088) +
                         sizeof(int) * 256 + sizeof(unsigned long long) * 4 + sizeof(double) * (D4C_MAX_AP + 2);
     WB_CUDA_CHECK(cudaFuncSetAttribute(d4c_body_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    d4c_body_kernel<<<f0_length, 512, smem, stream>>>(p);
+    WB_LAUNCH("d4c_body_kernel", d4c_body_kernel<<<f0_length, 512, smem, stream>>>(p));
     WB_CUDA_CHECK(cudaGetLastError());
   }
   return wb_rng_advance(d_rng, d_offsets + f0_length, stream);

@@ -67,10 +67,10 @@ int wb_fft_batch_dev(int kind, const void *d_in, int n, int batch, void *d_out, 
     const size_t smem = sizeof(cplx) * wb_fft_slots(n / 2);
     if (kind == 0) {
       WB_CUDA_CHECK(cudaFuncSetAttribute(r2c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      r2c_kernel<<<batch, threads, smem, stream>>>((const double *)d_in, n, l - 1, T, (cplx *)d_out);
+      WB_LAUNCH("r2c_kernel", r2c_kernel<<<batch, threads, smem, stream>>>((const double *)d_in, n, l - 1, T, (cplx *)d_out));
     } else {
       WB_CUDA_CHECK(cudaFuncSetAttribute(c2r_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      c2r_kernel<<<batch, threads, smem, stream>>>((const cplx *)d_in, n, l - 1, T, (double *)d_out);
+      WB_LAUNCH("c2r_kernel", c2r_kernel<<<batch, threads, smem, stream>>>((const cplx *)d_in, n, l - 1, T, (double *)d_out));
     }
   } else {
     const cplx *T = wb_twiddle_table(2 * n);
@@ -78,10 +78,10 @@ int wb_fft_batch_dev(int kind, const void *d_in, int n, int batch, void *d_out, 
     const size_t smem = sizeof(cplx) * wb_fft_slots(n);
     if (kind == 2) {
       WB_CUDA_CHECK(cudaFuncSetAttribute(c2c_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      c2c_kernel<1><<<batch, threads, smem, stream>>>((const cplx *)d_in, n, l, T, (cplx *)d_out);
+      WB_LAUNCH("c2c_kernel", c2c_kernel<1><<<batch, threads, smem, stream>>>((const cplx *)d_in, n, l, T, (cplx *)d_out));
     } else {
       WB_CUDA_CHECK(cudaFuncSetAttribute(c2c_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      c2c_kernel<-1><<<batch, threads, smem, stream>>>((const cplx *)d_in, n, l, T, (cplx *)d_out);
+      WB_LAUNCH("c2c_kernel", c2c_kernel<-1><<<batch, threads, smem, stream>>>((const cplx *)d_in, n, l, T, (cplx *)d_out));
     }
   }
   WB_CUDA_CHECK(cudaGetLastError());

@@ -584,7 +584,7 @@ static int harvest_prepare_filters(WbHarvestPlan *pl, WbWorkspace *ws, cudaStrea
   if (!tw) return WB_ERR_CUDA;
   const size_t smem = sizeof(cplx) * wb_fft_slots(NC);
   WB_CUDA_CHECK(cudaFuncSetAttribute(filter_spec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  filter_spec_kernel<<<pl->nch, 512, smem, stream>>>(d_bf, d_hl, pl->actual_fs, pl->NB, ilog2_exact(NC), tw, d_Hc);
+  WB_LAUNCH("filter_spec_kernel", filter_spec_kernel<<<pl->nch, 512, smem, stream>>>(d_bf, d_hl, pl->actual_fs, pl->NB, ilog2_exact(NC), tw, d_Hc));
   WB_CUDA_CHECK(cudaGetLastError());
   WB_CUDA_CHECK(cudaStreamSynchronize(stream));  // host vectors are pageable; make the plan self-contained
   pl->filters_ready = true;
@@ -609,7 +609,7 @@ int wb_harvest_run_basic(WbHarvestPlan *pl, WbWorkspace *ws, const double *d_x, 
   double *d_y = (double *)ws->get("hv_y", sizeof(double) * (y_length + 8));
   if (!d_y) return WB_ERR_CUDA;
   if (r == 1) {
-    copy_kernel<<<(x_length + 255) / 256, 256, 0, stream>>>(d_x, x_length, d_y);  // y_length = x_length + 1: last is zero
+    WB_LAUNCH("copy_kernel", copy_kernel<<<(x_length + 255) / 256, 256, 0, stream>>>(d_x, x_length, d_y));  // y_length = x_length + 1: last is zero
     WB_CUDA_CHECK(cudaMemsetAsync(d_y + x_length, 0, sizeof(double) * (y_length - x_length), stream));
   } else {
     const int lag = static_cast<int>(ceil(140.0 / r) * r);                               // harvest.cpp:222
@@ -621,16 +621,16 @@ int wb_harvest_run_basic(WbHarvestPlan *pl, WbWorkspace *ws, const double *d_x, 
     memcpy(&dc, pl->decim_coef, sizeof(dc));
     const int n_thr = (len2 + DEC_CHUNK - 1) / DEC_CHUNK;
     WB_CUDA_CHECK(cudaMemsetAsync(d_y, 0, sizeof(double) * y_length, stream));            // new_y is zero-initialised
-    dec_forward_kernel<<<(n_thr + 127) / 128, 128, 0, stream>>>(d_x, x_length, lag, len1, len2, dc, d_fwd);
-    dec_backward_kernel<<<(n_thr + 127) / 128, 128, 0, stream>>>(d_fwd, len1, len2, r, lag, dc, y_length, d_y);
+    WB_LAUNCH("dec_forward_kernel", dec_forward_kernel<<<(n_thr + 127) / 128, 128, 0, stream>>>(d_x, x_length, lag, len1, len2, dc, d_fwd));
+    WB_LAUNCH("dec_backward_kernel", dec_backward_kernel<<<(n_thr + 127) / 128, 128, 0, stream>>>(d_fwd, len1, len2, r, lag, dc, y_length, d_y));
   }
   unsigned long long *d_absmax = (unsigned long long *)ws->get("hv_absmax", 16);
   double *d_mean = (double *)ws->get("hv_mean", 16);
   if (!d_absmax || !d_mean) return WB_ERR_CUDA;
   WB_CUDA_CHECK(cudaMemsetAsync(d_absmax, 0, 8, stream));
-  dc_absmax_kernel<<<(y_length + 255) / 256, 256, 0, stream>>>(d_y, y_length, d_absmax);
-  dc_mean_kernel<<<1, 32, 0, stream>>>(d_y, y_length, d_absmax, d_mean);
-  dc_subtract_kernel<<<(y_length + 255) / 256, 256, 0, stream>>>(d_y, y_length, d_mean);
+  WB_LAUNCH("dc_absmax_kernel", dc_absmax_kernel<<<(y_length + 255) / 256, 256, 0, stream>>>(d_y, y_length, d_absmax));
+  WB_LAUNCH("dc_mean_kernel", dc_mean_kernel<<<1, 32, 0, stream>>>(d_y, y_length, d_absmax, d_mean));
+  WB_LAUNCH("dc_subtract_kernel", dc_subtract_kernel<<<(y_length + 255) / 256, 256, 0, stream>>>(d_y, y_length, d_mean));
   WB_CUDA_CHECK(cudaGetLastError());
 
   // ---- H3: overlap-save block spectra
@@ -640,7 +640,7 @@ int wb_harvest_run_basic(WbHarvestPlan *pl, WbWorkspace *ws, const double *d_x, 
   const cplx *tw = wb_twiddle_table(NB);
   const size_t smem_fft = sizeof(cplx) * wb_fft_slots(NC);
   WB_CUDA_CHECK(cudaFuncSetAttribute(yspec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
-  yspec_kernel<<<n_blocks, 512, smem_fft, stream>>>(d_y, y_length, NB, log2nc, pl->V, pl->h_max, tw, d_Yb);
+  WB_LAUNCH("yspec_kernel", yspec_kernel<<<n_blocks, 512, smem_fft, stream>>>(d_y, y_length, NB, log2nc, pl->V, pl->h_max, tw, d_Yb));
   WB_CUDA_CHECK(cudaGetLastError());
 
   // ---- H5: channels
@@ -654,7 +654,7 @@ int wb_harvest_run_basic(WbHarvestPlan *pl, WbWorkspace *ws, const double *d_x, 
     p.n_blocks = n_blocks; p.NB = NB; p.log2nc = log2nc; p.V = pl->V; p.h_max = pl->h_max; p.y_length = y_length;
     p.tw = tw; p.edges = d_edges; p.ecount = d_ecount; p.ecap = ecap;
     WB_CUDA_CHECK(cudaFuncSetAttribute(channel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
-    channel_kernel<<<nch, 512, smem_fft, stream>>>(p);
+    WB_LAUNCH("channel_kernel", channel_kernel<<<nch, 512, smem_fft, stream>>>(p));
     WB_CUDA_CHECK(cudaGetLastError());
   }
 
@@ -667,7 +667,7 @@ int wb_harvest_run_basic(WbHarvestPlan *pl, WbWorkspace *ws, const double *d_x, 
     p.nch = nch; p.f0_length = Lb; p.actual_fs = afs; p.f0_floor = pl->opt.f0_floor; p.f0_ceil = pl->opt.f0_ceil;
     p.frame_period = frame_period; p.raw = d_raw;
     dim3 grid((Lb + 255) / 256, nch);
-    raw_candidate_kernel<<<grid, 256, 0, stream>>>(p);
+    WB_LAUNCH("raw_candidate_kernel", raw_candidate_kernel<<<grid, 256, 0, stream>>>(p));
     WB_CUDA_CHECK(cudaGetLastError());
   }
 
@@ -681,10 +681,10 @@ int wb_harvest_run_basic(WbHarvestPlan *pl, WbWorkspace *ws, const double *d_x, 
   double *d_scoreB = (double *)ws->get("hv_scoreB", sizeof(double) * (size_t)Lb * MC);
   if (!d_own || !d_nc || !d_work || !d_candA || !d_scoreA || !d_candB || !d_scoreB) return WB_ERR_CUDA;
   WB_CUDA_CHECK(cudaMemsetAsync(d_nc, 0, 16, stream));  // [0] = nc, [1] = work count
-  detect_kernel<<<(Lb + 127) / 128, 128, 0, stream>>>(d_raw, nch, Lb, own_cap, d_own, d_nc);
+  WB_LAUNCH("detect_kernel", detect_kernel<<<(Lb + 127) / 128, 128, 0, stream>>>(d_raw, nch, Lb, own_cap, d_own, d_nc));
   const long long n_cs = (long long)Lb * MC;
-  overlap_kernel<<<(unsigned)((n_cs + 255) / 256), 256, 0, stream>>>(d_own, own_cap, d_nc, Lb, MC, d_candA, d_scoreA,
-                                                                    d_work, d_nc + 1);
+  WB_LAUNCH("overlap_kernel", overlap_kernel<<<(unsigned)((n_cs + 255) / 256), 256, 0, stream>>>(d_own, own_cap, d_nc, Lb, MC, d_candA, d_scoreA,
+                                                                    d_work, d_nc + 1));
   WB_CUDA_CHECK(cudaGetLastError());
   {
     RefineParams p;
@@ -703,10 +703,10 @@ int wb_harvest_run_basic(WbHarvestPlan *pl, WbWorkspace *ws, const double *d_x, 
     }
     const size_t smem = sizeof(double) * RF_WARPS * (p.max_wlen + 2);
     WB_CUDA_CHECK(cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    refine_kernel<<<148 * 4, RF_WARPS * 32, smem, stream>>>(p);
+    WB_LAUNCH("refine_kernel", refine_kernel<<<148 * 4, RF_WARPS * 32, smem, stream>>>(p));
     WB_CUDA_CHECK(cudaGetLastError());
   }
-  remove_kernel<<<(unsigned)((n_cs + 255) / 256), 256, 0, stream>>>(d_candA, d_scoreA, d_nc, Lb, MC, d_candB, d_scoreB);
+  WB_LAUNCH("remove_kernel", remove_kernel<<<(unsigned)((n_cs + 255) / 256), 256, 0, stream>>>(d_candA, d_scoreA, d_nc, Lb, MC, d_candB, d_scoreB));
   WB_CUDA_CHECK(cudaGetLastError());
 
   // ---- contour fixing + smoothing

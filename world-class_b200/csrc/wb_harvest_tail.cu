@@ -429,15 +429,15 @@ int wb_harvest_tail(WbWorkspace *ws, const double *d_cand, const double *d_score
   p.fw = (double *)ws->get("tl_fw", sizeof(double) * p.fw_cap);
   p.error_flag = ws->error_flag();
   if (!p.secbuf || !p.pad || !p.fw || !p.error_flag) return WB_ERR_CUDA;
-  harvest_tail_kernel<<<1, TL_THREADS, 0, stream>>>(p);
+  WB_LAUNCH("harvest_tail_kernel", harvest_tail_kernel<<<1, TL_THREADS, 0, stream>>>(p));
   WB_CUDA_CHECK(cudaGetLastError());
   return WB_OK;
 }
 
 int wb_harvest_pick(const double *d_basic_f0, int basic_len, double frame_period, int f0_length, double *d_tpos,
                     double *d_f0, cudaStream_t stream) {
-  harvest_pick_kernel<<<(f0_length + 255) / 256, 256, 0, stream>>>(d_basic_f0, basic_len, frame_period, f0_length,
-                                                                  d_tpos, d_f0);
+  WB_LAUNCH("harvest_pick_kernel", harvest_pick_kernel<<<(f0_length + 255) / 256, 256, 0, stream>>>(d_basic_f0, basic_len, frame_period, f0_length,
+                                                                  d_tpos, d_f0));
   WB_CUDA_CHECK(cudaGetLastError());
   return WB_OK;
 }

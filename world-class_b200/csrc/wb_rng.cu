@@ -102,13 +102,13 @@ int wb_rng_fill(const WbRngState *d_state, const unsigned long long *d_count_or_
   const unsigned long long threads = (max_count + WB_RNG_CHUNK - 1) / WB_RNG_CHUNK;
   const int block = 128;
   const unsigned long long grid = (threads + block - 1) / block;
-  rng_fill_kernel<<<(unsigned)grid, block, 0, stream>>>(d_state, g_d_pow, d_count_or_null, max_count, d_out);
+  WB_LAUNCH("rng_fill_kernel", rng_fill_kernel<<<(unsigned)grid, block, 0, stream>>>(d_state, g_d_pow, d_count_or_null, max_count, d_out));
   WB_CUDA_CHECK(cudaGetLastError());
   return WB_OK;
 }
 
 int wb_rng_advance(WbRngState *d_state, const unsigned long long *d_count, cudaStream_t stream) {
-  rng_advance_kernel<<<1, 32, 0, stream>>>(d_state, g_d_pow, d_count);
+  WB_LAUNCH("rng_advance_kernel", rng_advance_kernel<<<1, 32, 0, stream>>>(d_state, g_d_pow, d_count));
   WB_CUDA_CHECK(cudaGetLastError());
   return WB_OK;
 }

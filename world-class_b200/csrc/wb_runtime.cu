@@ -2,6 +2,7 @@
 #include "wb_internal.h"
 
 #include <math.h>
+#include <string.h>
 #include <mutex>
 #include <vector>
 
@@ -117,7 +118,85 @@ const cplx *wb_twiddle_table(int n) {
 
 int wb_exclusive_scan_u64(const unsigned long long *d_counts, unsigned long long *d_offsets, int n,
                           cudaStream_t stream) {
-  scan_u64_kernel<<<1, SCAN_THREADS, 0, stream>>>(d_counts, d_offsets, n);
+  WB_LAUNCH("scan_u64_kernel", scan_u64_kernel<<<1, SCAN_THREADS, 0, stream>>>(d_counts, d_offsets, n));
   WB_CUDA_CHECK(cudaGetLastError());
   return WB_OK;
+}
+
+// ---- launch accounting / per-kernel timing -------------------------------------------------
+#include <atomic>
+#include <string>
+namespace {
+std::atomic<unsigned long long> g_launches{0};
+std::atomic<int> g_prof_on{0};
+struct Pending { std::string name; cudaEvent_t e0, e1; };
+std::mutex g_prof_mutex;
+std::vector<Pending> g_pending;
+struct Tot { double ms; int count; };
+std::map<std::string, Tot> g_totals;
+}  // namespace
+
+WbLaunchScope::WbLaunchScope(const char *name, cudaStream_t stream) : name_(name), stream_(stream), ev0_(nullptr) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (g_prof_on.load(std::memory_order_relaxed)) {
+    cudaEvent_t e0;
+    if (cudaEventCreate(&e0) == cudaSuccess) {
+      cudaEventRecord(e0, stream_);
+      ev0_ = e0;
+    }
+  }
+}
+
+WbLaunchScope::~WbLaunchScope() {
+  if (ev0_) {
+    cudaEvent_t e1;
+    if (cudaEventCreate(&e1) == cudaSuccess) {
+      cudaEventRecord(e1, stream_);
+      std::lock_guard<std::mutex> lock(g_prof_mutex);
+      g_pending.push_back(Pending{name_, (cudaEvent_t)ev0_, e1});
+    }
+  }
+}
+
+unsigned long long wb_launch_counter() { return g_launches.load(); }
+void wb_prof_set_enabled(int on) { g_prof_on.store(on ? 1 : 0); }
+
+int wb_prof_collect() {
+  if (cudaDeviceSynchronize() != cudaSuccess) return WB_ERR_CUDA;
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
+  for (auto &p : g_pending) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, p.e0, p.e1) == cudaSuccess) {
+      Tot &t = g_totals[p.name];
+      t.ms += ms;
+      t.count += 1;
+    }
+    cudaEventDestroy(p.e0);
+    cudaEventDestroy(p.e1);
+  }
+  g_pending.clear();
+  return WB_OK;
+}
+
+int wb_prof_query(const char *name, double *total_ms, int *count) {
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
+  auto it = g_totals.find(name);
+  if (it == g_totals.end()) return WB_ERR_ARG;
+  *total_ms = it->second.ms;
+  *count = it->second.count;
+  return WB_OK;
+}
+
+int wb_prof_names(char *buf, int buf_len) {
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
+  std::string s;
+  for (auto &kv : g_totals) { if (!s.empty()) s += ";"; s += kv.first; }
+  if ((int)s.size() + 1 > buf_len) return WB_ERR_ARG;
+  memcpy(buf, s.c_str(), s.size() + 1);
+  return WB_OK;
+}
+
+void wb_prof_reset() {
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
+  g_totals.clear();
 }

@@ -532,14 +532,14 @@ int wb_synthesis_run(WbWorkspace *ws, int fs, int fft_size, double frame_period_
     WB_CUDA_CHECK(cudaMemcpyAsync(d_dcr, h, sizeof(double) * fft_size, cudaMemcpyHostToDevice, stream));
   }
 
-  timebase_kernel<<<(out_length + 255) / 256, 256, 0, stream>>>(d_f0, f0_length, fs, frame_period, lowest_f0,
-                                                                out_length, d_incr, d_vuv);
-  phase_scan_kernel<<<1, PS_THREADS, 0, stream>>>(d_incr, out_length, d_wrap);
-  pulse_count_kernel<<<n_blocks, PD_THREADS, 0, stream>>>(d_wrap, out_length, d_bc);
+  WB_LAUNCH("timebase_kernel", timebase_kernel<<<(out_length + 255) / 256, 256, 0, stream>>>(d_f0, f0_length, fs, frame_period, lowest_f0,
+                                                                out_length, d_incr, d_vuv));
+  WB_LAUNCH("phase_scan_kernel", phase_scan_kernel<<<1, PS_THREADS, 0, stream>>>(d_incr, out_length, d_wrap));
+  WB_LAUNCH("pulse_count_kernel", pulse_count_kernel<<<n_blocks, PD_THREADS, 0, stream>>>(d_wrap, out_length, d_bc));
   int rc = wb_exclusive_scan_u64(d_bc, d_bo, n_blocks, stream);
   if (rc) return rc;
-  pulse_write_kernel<<<n_blocks, PD_THREADS, 0, stream>>>(d_wrap, out_length, fs, d_bo, d_pidx, d_pshift, max_pulses);
-  pulse_finalize_kernel<<<1, 1, 0, stream>>>(d_bo, n_blocks, d_pidx, max_pulses, d_np, d_ncount, ws->error_flag());
+  WB_LAUNCH("pulse_write_kernel", pulse_write_kernel<<<n_blocks, PD_THREADS, 0, stream>>>(d_wrap, out_length, fs, d_bo, d_pidx, d_pshift, max_pulses));
+  WB_LAUNCH("pulse_finalize_kernel", pulse_finalize_kernel<<<1, 1, 0, stream>>>(d_bo, n_blocks, d_pidx, max_pulses, d_np, d_ncount, ws->error_flag()));
   WB_CUDA_CHECK(cudaGetLastError());
   if ((rc = wb_rng_fill(d_rng, d_ncount, (unsigned long long)out_length, d_noise, stream))) return rc;
 
@@ -568,9 +568,9 @@ int wb_synthesis_run(WbWorkspace *ws, int fs, int fft_size, double frame_period_
   p.max_resp_pulses = resp_pulses;
   p.error_flag = ws->error_flag();
   const int grid = wb_min_i(resp_pulses, 148 * 8);
-  response_kernel<<<grid, 256, smem, stream>>>(p);
+  WB_LAUNCH("response_kernel", response_kernel<<<grid, 256, smem, stream>>>(p));
   WB_CUDA_CHECK(cudaGetLastError());
-  ola_kernel<<<(out_length + 255) / 256, 256, 0, stream>>>(d_resp, d_pidx, d_np, resp_pulses, fft_size, out_length, d_out);
+  WB_LAUNCH("ola_kernel", ola_kernel<<<(out_length + 255) / 256, 256, 0, stream>>>(d_resp, d_pidx, d_np, resp_pulses, fft_size, out_length, d_out));
   WB_CUDA_CHECK(cudaGetLastError());
   return wb_rng_advance(d_rng, d_ncount, stream);
 }
