@@ -86,6 +86,13 @@ struct wb_pipeline {
   double ct_f0_floor_internal;
   WbD4COption d4c;
   WbWorkspace ws;
+  cudaStream_t side = nullptr;       // Synthesis time base overlaps CheapTrick / D4C here
+  cudaEvent_t ev_f0 = nullptr, ev_tb = nullptr;
+  ~wb_pipeline() {
+    if (ev_f0) cudaEventDestroy(ev_f0);
+    if (ev_tb) cudaEventDestroy(ev_tb);
+    if (side) cudaStreamDestroy(side);
+  }
 };
 
 struct wb_d4c {
@@ -447,6 +454,12 @@ int wb_pipeline_create(int fs, const WbHarvestOption *hopt, const WbCheapTrickOp
   p->ct_f0_floor_internal = wb_cheaptrick_get_f0_floor(fs, p->ct.fft_size);
   wb_d4c_option_default(&p->d4c);
   if (dopt) p->d4c = *dopt;
+  if (cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&p->ev_f0, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&p->ev_tb, cudaEventDisableTiming) != cudaSuccess) {
+    delete p;
+    return WB_ERR_CUDA;
+  }
   *out = p;
   return WB_OK;
 }
@@ -489,6 +502,13 @@ int wb_pipeline_run_dev(wb_pipeline_t *p, const double *d_x, int x_length, doubl
     if ((rc = wb_harvest_pick(d_basic, Lb, fp, f0_length, d_tpos, d_f0, st))) return rc;
   }
   WbRngState *rng = wb_rng_global_state();
+  // The pulse list depends on f0 only: compute it on the side stream, concurrently with CheapTrick / D4C
+  if (y_length > 0) {
+    WB_CUDA_CHECK(cudaEventRecord(p->ev_f0, st));
+    WB_CUDA_CHECK(cudaStreamWaitEvent(p->side, p->ev_f0, 0));
+    if ((rc = wb_synthesis_timebase(&p->ws, fs, p->ct.fft_size, fp, d_f0, f0_length, y_length, p->side))) return rc;
+    WB_CUDA_CHECK(cudaEventRecord(p->ev_tb, p->side));
+  }
   if ((rc = wb_cheaptrick_run(&p->ws, fs, p->ct.fft_size, p->ct.q1, p->ct_f0_floor_internal, d_x, x_length, d_tpos,
                               d_f0, f0_length, d_sp, rng, st)))
     return rc;
@@ -499,8 +519,9 @@ int wb_pipeline_run_dev(wb_pipeline_t *p, const double *d_x, int x_length, doubl
     if (!d_y) return WB_ERR_CUDA;
     // Harvest's contour is bounded by f0_ceil up to the smoothing overshoot
     const double f0_bound = p->plan.opt.f0_ceil * 1.25;
-    if ((rc = wb_synthesis_run(&p->ws, fs, p->ct.fft_size, fp, d_f0, f0_length, d_sp, d_ap, y_length, d_y, f0_bound,
-                               rng, st)))
+    WB_CUDA_CHECK(cudaStreamWaitEvent(st, p->ev_tb, 0));
+    if ((rc = wb_synthesis_render(&p->ws, fs, p->ct.fft_size, fp, f0_length, d_sp, d_ap, y_length, d_y, f0_bound,
+                                  rng, st)))
       return rc;
   }
   return WB_OK;

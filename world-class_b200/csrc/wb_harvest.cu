@@ -206,88 +206,122 @@ struct ChanParams {
   const cplx *Yb; const cplx *Hc; const int *half_len;
   int n_blocks; int NB; int log2nc; int V; int h_max; int y_length;
   const cplx *tw;
-  double *edges;      // [nch][4][ecap]
-  int *ecount;        // [nch][4]
-  int ecap;
+  double *seg_edges;  // [nch][4][n_blocks][bcap]
+  int *seg_count;     // [nch][4][n_blocks]
+  int bcap;
 };
 
-// Appends, in increasing order, the fine edges found by the calling block for sample range
-// [n_begin, n_end).  f(n) must be valid for n .. n+2.  type 0: negative-going of f, 1: of -f,
-// 2: of d = f[n+1]-f[n] (peaks), 3: of -d (dips).   harvest.cpp:1179-1255
-template <typename F>
-__device__ inline void emit_edges(F f, int n_begin, int n_end, int y_length, double *edges, int ecap,
-                                  int *s_count /*[4] shared*/, int *s_warp /*[4][32] shared*/) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int base = n_begin; base < n_end; base += blockDim.x) {
-    const int n = base + threadIdx.x;
-    bool flag[4] = {false, false, false, false};
-    double fine[4] = {0.0, 0.0, 0.0, 0.0};
-    if (n < n_end) {
-      const double a = f(n), b = f(n + 1);
-      if (n < y_length - 1) {
-        if (0.0 < a && b <= 0.0) { flag[0] = true; fine[0] = (n + 1) - a / (b - a); }
-        if (a < 0.0 && b >= 0.0) { flag[1] = true; fine[1] = (n + 1) - a / (b - a); }
-      }
-      if (n < y_length - 2) {
-        const double c = f(n + 2);
-        const double d0 = b - a, d1 = c - b;
-        if (0.0 < d0 && d1 <= 0.0) { flag[2] = true; fine[2] = (n + 1) - d0 / (d1 - d0); }
-        if (d0 < 0.0 && d1 >= 0.0) { flag[3] = true; fine[3] = (n + 1) - d0 / (d1 - d0); }
-      }
-    }
-    unsigned m[4];
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      m[t] = __ballot_sync(0xffffffffu, flag[t]);
-      if (lane == 0) s_warp[t * 32 + warp] = __popc(m[t]);
-    }
-    __syncthreads();
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      if (flag[t]) {
-        int before = s_count[t];
-        for (int w = 0; w < warp; ++w) before += s_warp[t * 32 + w];
-        const int slot = before + __popc(m[t] & ((1u << lane) - 1u));
-        if (slot < ecap) edges[(size_t)t * ecap + slot] = fine[t];
-      }
-    }
-    __syncthreads();
-    if (threadIdx.x < 4) {
-      int tot = 0;
-      for (int w = 0; w < nw; ++w) tot += s_warp[threadIdx.x * 32 + w];
-      s_count[threadIdx.x] += tot;
-    }
-    __syncthreads();
+#define CH_THREADS 256
+
+// flags of sample n for the four zero-crossing kinds (harvest.cpp:1179-1255):
+// bit 0: negative-going of f, 1: of -f, 2: of d = f[n+1]-f[n] (peaks), 3: of -d (dips)
+__device__ __forceinline__ unsigned ch_flags(double a, double b, double c, int n, int y_length) {
+  unsigned m = 0;
+  if (n < y_length - 1) {
+    if (0.0 < a && b <= 0.0) m |= 1u;
+    if (a < 0.0 && b >= 0.0) m |= 2u;
   }
+  if (n < y_length - 2) {
+    const double d0 = b - a, d1 = c - b;
+    if (0.0 < d0 && d1 <= 0.0) m |= 4u;
+    if (d0 < 0.0 && d1 >= 0.0) m |= 8u;
+  }
+  return m;
 }
 
-__global__ void __launch_bounds__(512) channel_kernel(ChanParams p) {
+// One CTA per (overlap-save block, channel): band-pass by the convolution theorem
+// (harvest.cpp:1277-1299) and order-preserving extraction of the fine zero-crossing edges of the
+// block's V output samples straight from shared memory.
+__global__ void __launch_bounds__(CH_THREADS) channel_kernel(ChanParams p) {
   extern __shared__ double2 smem_raw[];
-  __shared__ int s_count[4];
-  __shared__ int s_warp[4 * 32];
+  __shared__ int s_wsum[4][CH_THREADS / 32];
   cplx *S = smem_raw;
   double *W = reinterpret_cast<double *>(S);
   const int NC = p.NB / 2;
-  const int c = blockIdx.x;
+  const int b = blockIdx.x, c = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int h = p.half_len[c];
   const cplx *H = p.Hc + (size_t)c * (NC + 1);
-  double *edges = p.edges + (size_t)c * 4 * p.ecap;
-  if (threadIdx.x < 4) s_count[threadIdx.x] = 0;
-  __syncthreads();
-  for (int b = 0; b < p.n_blocks; ++b) {
-    const cplx *Y = p.Yb + (size_t)b * (NC + 1);
-    // convolution theorem, harvest.cpp:1277-1291
-    wb_irfft<-1>(S, NC, p.log2nc, p.tw, [&](int k) {
-      const cplx yv = Y[k], hv = H[k];
-      return make_double2(yv.x * hv.x - yv.y * hv.y, yv.x * hv.y + yv.y * hv.x);
-    });
-    // filtered[n] = seg[n + 1 + h - s_b], s_b = b V + 1 - h_max   (delay compensation :1297-1299)
-    const int n0 = b * p.V;
-    const int off = h + p.h_max - n0;  // n + off = n + 1 + h - s_b
-    const int n_end = min(n0 + p.V, p.y_length);
-    emit_edges([&](int n) { return W[wb_didx(n + off)]; }, n0, n_end, p.y_length, edges, p.ecap, s_count, s_warp);
+  const cplx *Y = p.Yb + (size_t)b * (NC + 1);
+  wb_irfft<-1>(S, NC, p.log2nc, p.tw, [&](int k) {
+    const cplx yv = Y[k], hv = H[k];
+    return make_double2(yv.x * hv.x - yv.y * hv.y, yv.x * hv.y + yv.y * hv.x);
+  });
+  // filtered[n] = seg[n + 1 + h - s_b], s_b = b V + 1 - h_max   (delay compensation :1297-1299)
+  const int n0 = b * p.V;
+  const int off = h + p.h_max - n0;
+  const int n_end = min(n0 + p.V, p.y_length);
+  // each thread owns a contiguous run of samples (odd length: conflict-free shared-memory reads)
+  int chunk = (p.V + CH_THREADS - 1) / CH_THREADS;
+  chunk |= 1;
+  const int my_begin = n0 + tid * chunk, my_end = min(n_end, my_begin + chunk);
+  int cnt[4] = {0, 0, 0, 0};
+  for (int n = my_begin; n < my_end; ++n) {
+    const unsigned m = ch_flags(W[wb_didx(n + off)], W[wb_didx(n + 1 + off)], W[wb_didx(n + 2 + off)], n, p.y_length);
+    cnt[0] += m & 1u; cnt[1] += (m >> 1) & 1u; cnt[2] += (m >> 2) & 1u; cnt[3] += (m >> 3) & 1u;
   }
-  if (threadIdx.x < 4) p.ecount[c * 4 + threadIdx.x] = min(s_count[threadIdx.x], p.ecap);
+  int pre[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    int incl = cnt[t];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_wsum[t][warp] = incl;
+    pre[t] = incl - cnt[t];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    int total = 0;
+    for (int w = 0; w < CH_THREADS / 32; ++w) {
+      const int v = s_wsum[t][w];
+      if (w < warp) pre[t] += v;
+      total += v;
+    }
+    if (tid == 0) p.seg_count[((size_t)c * 4 + t) * p.n_blocks + b] = min(total, p.bcap);
+  }
+  double *dst = p.seg_edges + ((size_t)c * 4 * p.n_blocks + b) * p.bcap;
+  const size_t tstride = (size_t)p.n_blocks * p.bcap;
+  for (int n = my_begin; n < my_end; ++n) {
+    const double a = W[wb_didx(n + off)], bb = W[wb_didx(n + 1 + off)], cc = W[wb_didx(n + 2 + off)];
+    const unsigned m = ch_flags(a, bb, cc, n, p.y_length);
+    if (m & 3u) {
+      const double fine = (n + 1) - a / (bb - a);
+      if (m & 1u) { if (pre[0] < p.bcap) dst[pre[0]] = fine; ++pre[0]; }
+      if (m & 2u) { if (pre[1] < p.bcap) dst[tstride + pre[1]] = fine; ++pre[1]; }
+    }
+    if (m & 12u) {
+      const double d0 = bb - a, d1 = cc - bb;
+      const double fine = (n + 1) - d0 / (d1 - d0);
+      if (m & 4u) { if (pre[2] < p.bcap) dst[2 * tstride + pre[2]] = fine; ++pre[2]; }
+      if (m & 8u) { if (pre[3] < p.bcap) dst[3 * tstride + pre[3]] = fine; ++pre[3]; }
+    }
+  }
+}
+
+// gathers the per-block edge runs of one (channel, kind) into one ordered list
+__global__ void edge_compact_kernel(const double *__restrict__ seg_edges, const int *__restrict__ seg_count,
+                                    int n_blocks, int bcap, double *__restrict__ edges, int *__restrict__ ecount,
+                                    int ecap) {
+  __shared__ int s_off[64];
+  const int ct = blockIdx.x;  // channel * 4 + kind
+  const int *cnt = seg_count + (size_t)ct * n_blocks;
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int b = 0; b < n_blocks; ++b) { s_off[b] = run; run += cnt[b]; }
+    s_off[n_blocks] = run;
+    ecount[ct] = min(run, ecap);
+  }
+  __syncthreads();
+  for (int b = 0; b < n_blocks; ++b) {
+    const int o = s_off[b], n = s_off[b + 1] - o;
+    const double *src = seg_edges + ((size_t)ct * n_blocks + b) * bcap;
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+      if (o + i < ecap) edges[(size_t)ct * ecap + o + i] = src[i];
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -427,12 +461,24 @@ __global__ void __launch_bounds__(RF_WARPS * 32) refine_kernel(RefineParams p) {
     const int fft_size = 1 << log2fft;
     const double base_time0 = (-hw + 0) / fs;
     const int basic_index = wb_round((current_position + base_time0) * fs + 0.001);
-    // main window (harvest.cpp:762-774)
+    // main window (harvest.cpp:762-774): 0.42 + 0.5 cos(t) + 0.08 cos(2t), t = 2 pi tmp / T.
+    // The angle advances by exactly 2 pi / len per sample, so each lane evaluates one sincos at
+    // its first sample (with the reference's expression) and then rotates by 32 samples per step;
+    // cos(2t) = 2 cos(t)^2 - 1.  <= 19 rotations -> a few 1e-16 of drift.
     const double two_pi = 2.0 * WB_PI;
-    for (int i = lane; i < len; i += 32) {
-      const double tmp = ((basic_index + i) - 1.0) / fs - current_position;
+    {
+      double sd, cd;
+      sincos(two_pi * 32.0 / len, &sd, &cd);
+      const double tmp = ((basic_index + lane) - 1.0) / fs - current_position;
       const double tmp2 = two_pi * tmp / window_length_in_time;
-      mw[i + 1] = 0.42 + 0.5 * cos(tmp2) + 0.08 * cos(2 * tmp2);
+      double sn, cs;
+      sincos(tmp2, &sn, &cs);
+      for (int i = lane; i < len; i += 32) {
+        mw[i + 1] = 0.42 + 0.5 * cs + 0.08 * (2.0 * cs * cs - 1.0);
+        const double c2 = cs * cd - sn * sd;
+        sn = sn * cd + cs * sd;
+        cs = c2;
+      }
     }
     __syncwarp();
     const int nh = wb_min_i(static_cast<int>(fs / 2.0 / current_f0), 6);
@@ -467,20 +513,30 @@ __global__ void __launch_bounds__(RF_WARPS * 32) refine_kernel(RefineParams p) {
       mr[hh] = wb_warp_sum(mr[hh]); mi[hh] = wb_warp_sum(mi[hh]);
       dr[hh] = wb_warp_sum(dr[hh]); di[hh] = wb_warp_sum(di[hh]);
     }
-    if (lane == 0) {
-      // spectra are conjugated by the reference (harvest.cpp:829-841): main = (mr, -mi), diff = (dr, -di)
-      double numerator = 0.0, denominator = 0.0, score = 0.0;
-      for (int hh = 0; hh < nh; ++hh) {
+    // fixF0 (harvest.cpp:844-878): lane hh evaluates harmonic hh (divisions, sqrt in parallel),
+    // lane 0 accumulates in the reference's order.
+    // spectra are conjugated by the reference (harvest.cpp:829-841): main = (mr, -mi), diff = (dr, -di)
+    double my_inst = 0.0, my_amp = 0.0;
+#pragma unroll
+    for (int hh = 0; hh < 6; ++hh) {
+      if (lane == hh && hh < nh) {
         const double m_re = mr[hh], m_im = -mi[hh], d_re = dr[hh], d_im = -di[hh];
         const double power = m_re * m_re + m_im * m_im;
         const double num_i = m_re * d_im - m_im * d_re;
-        const double inst = (power == 0.0) ? 0.0
-                            : static_cast<double>(idx[hh]) * fs / fft_size + num_i / power * fs / 2.0 / WB_PI;
-        const double amp = sqrt(power);
-        numerator += amp * inst;
-        denominator += amp * (hh + 1.0);
-        score += fabs((inst / (hh + 1.0) - current_f0) / current_f0);
+        my_inst = (power == 0.0) ? 0.0
+                  : static_cast<double>(idx[hh]) * fs / fft_size + num_i / power * fs / 2.0 / WB_PI;
+        my_amp = sqrt(power);
       }
+    }
+    double numerator = 0.0, denominator = 0.0, score = 0.0;
+    for (int hh = 0; hh < nh; ++hh) {
+      const double inst = __shfl_sync(0xffffffffu, my_inst, hh);
+      const double amp = __shfl_sync(0xffffffffu, my_amp, hh);
+      numerator += amp * inst;
+      denominator += amp * (hh + 1.0);
+      score += fabs((inst / (hh + 1.0) - current_f0) / current_f0);
+    }
+    if (lane == 0) {
       double refined = numerator / (denominator + WB_SAFEGUARD);
       double sc = 1.0 / (score / nh + WB_SAFEGUARD);
       if (refined < p.f0_floor || refined > p.f0_ceil || sc < 2.5) { refined = 0.0; sc = 0.0; }
@@ -645,16 +701,23 @@ int wb_harvest_run_basic(WbHarvestPlan *pl, WbWorkspace *ws, const double *d_x, 
 
   // ---- H5: channels
   const int ecap = y_length / 2 + 4;
+  const int bcap = pl->V / 2 + 2;
+  if (n_blocks > 63) return WB_ERR_UNSUPPORTED;  // TODO(long streams): tile the block axis
   double *d_edges = (double *)ws->get("hv_edges", sizeof(double) * (size_t)nch * 4 * ecap);
   int *d_ecount = (int *)ws->get("hv_ecount", sizeof(int) * nch * 4);
-  if (!d_edges || !d_ecount) return WB_ERR_CUDA;
+  double *d_seg = (double *)ws->get("hv_seg_edges", sizeof(double) * (size_t)nch * 4 * n_blocks * bcap);
+  int *d_segc = (int *)ws->get("hv_seg_count", sizeof(int) * (size_t)nch * 4 * n_blocks);
+  if (!d_edges || !d_ecount || !d_seg || !d_segc) return WB_ERR_CUDA;
   {
     ChanParams p;
     p.Yb = d_Yb; p.Hc = (const cplx *)ws->get("hv_Hc", 0); p.half_len = (const int *)ws->get("hv_hl", 0);
     p.n_blocks = n_blocks; p.NB = NB; p.log2nc = log2nc; p.V = pl->V; p.h_max = pl->h_max; p.y_length = y_length;
-    p.tw = tw; p.edges = d_edges; p.ecount = d_ecount; p.ecap = ecap;
+    p.tw = tw; p.seg_edges = d_seg; p.seg_count = d_segc; p.bcap = bcap;
     WB_CUDA_CHECK(cudaFuncSetAttribute(channel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
-    WB_LAUNCH("channel_kernel", channel_kernel<<<nch, 512, smem_fft, stream>>>(p));
+    dim3 grid(n_blocks, nch);
+    WB_LAUNCH("channel_kernel", channel_kernel<<<grid, CH_THREADS, smem_fft, stream>>>(p));
+    WB_CUDA_CHECK(cudaGetLastError());
+    WB_LAUNCH("edge_compact_kernel", edge_compact_kernel<<<nch * 4, 256, 0, stream>>>(d_seg, d_segc, n_blocks, bcap, d_edges, d_ecount, ecap));
     WB_CUDA_CHECK(cudaGetLastError());
   }
 

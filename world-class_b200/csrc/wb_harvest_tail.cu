@@ -131,8 +131,50 @@ __device__ __forceinline__ double tl_search_score(double f0, const double *cands
   return score;
 }
 
-__device__ __forceinline__ double tl_block_sum(double v, double *red) {
-  return wb_block_sum(v, red);
+// searchF0Base (harvest.cpp:254-272): one warp per frame; the first candidate with the highest
+// positive score wins (the reference's scan uses a strict >).
+__global__ void search_base_kernel(const double *__restrict__ cand, const double *__restrict__ score,
+                                   const int *__restrict__ nc, int L, int MC, double *__restrict__ base) {
+  const int frame = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (frame >= L) return;
+  const int nc7 = *nc * 7;
+  const double *c = cand + (size_t)frame * MC, *sc = score + (size_t)frame * MC;
+  double best_score = 0.0;
+  int best_idx = -1;
+  for (int j = lane; j < nc7; j += 32) {
+    const double v = sc[j];
+    if (v > best_score) { best_score = v; best_idx = j; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double s2 = __shfl_xor_sync(0xffffffffu, best_score, o);
+    const int i2 = __shfl_xor_sync(0xffffffffu, best_idx, o);
+    if (i2 >= 0 && (best_idx < 0 || s2 > best_score || (s2 == best_score && i2 < best_idx))) { best_score = s2; best_idx = i2; }
+  }
+  if (lane == 0) base[frame] = best_idx >= 0 ? c[best_idx] : 0.0;
+}
+
+// exclusive prefix sum of v[0..n) into out[0..n] (out[n] = total); all threads; n may exceed blockDim
+__device__ void tl_exclusive_scan(const int *v, int n, int *out, int *s_scan) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int chunk = (n + nt - 1) / nt;
+  const int b = min(n, tid * chunk), e = min(n, (tid + 1) * chunk);
+  int cnt = 0;
+  for (int i = b; i < e; ++i) cnt += v[i];
+  __syncthreads();
+  s_scan[tid] = cnt;
+  __syncthreads();
+  for (int o = 1; o < nt; o <<= 1) {
+    const int t = (tid >= o) ? s_scan[tid - o] : 0;
+    __syncthreads();
+    s_scan[tid] += t;
+    __syncthreads();
+  }
+  int run = s_scan[tid] - cnt;
+  for (int i = b; i < e; ++i) { const int x = v[i]; out[i] = run; run += x; }
+  if (tid == nt - 1) out[n] = s_scan[nt - 1];
+  __syncthreads();
 }
 
 __global__ void __launch_bounds__(TL_THREADS) harvest_tail_kernel(TailParams p) {
@@ -143,15 +185,7 @@ __global__ void __launch_bounds__(TL_THREADS) harvest_tail_kernel(TailParams p) 
   const int L = p.L, MC = p.MC;
   const int nc7 = *p.nc * 7;
 
-  // ---- searchF0Base + fixStep1
-  for (int i = tid; i < L; i += nt) {
-    const double *c = p.cand + (size_t)i * MC, *sc = p.score + (size_t)i * MC;
-    double best = 0.0, best_score = 0.0;
-    for (int j = 0; j < nc7; ++j)
-      if (sc[j] > best_score) { best = c[j]; best_score = sc[j]; }
-    p.base[i] = best;
-  }
-  __syncthreads();
+  // ---- fixStep1 (searchF0Base ran in search_base_kernel)
   for (int i = tid; i < L; i += nt) {
     double v = 0.0;  // entries the reference leaves unwritten read as 0 (zero-filled heap)
     if (i >= 2 && p.base[i] != 0.0) {
@@ -197,12 +231,8 @@ __global__ void __launch_bounds__(TL_THREADS) harvest_tail_kernel(TailParams p) 
     p.sec_st[s] = st; p.sec_ed[s] = ed; p.sec_lo[s] = lo; p.sec_len[s] = hi - lo + 1;
   }
   __syncthreads();
-  if (tid == 0) {
-    long long off = 0;
-    for (int s = 0; s < nsec; ++s) { p.sec_off[s] = (int)off; off += p.sec_len[s]; }
-    p.sec_off[nsec] = (int)off;
-    s_i[0] = (off > p.secbuf_cap) ? 1 : 0;
-  }
+  tl_exclusive_scan(p.sec_len, nsec, p.sec_off, s_scan);
+  if (tid == 0) s_i[0] = ((long long)p.sec_off[nsec] > p.secbuf_cap) ? 1 : 0;
   __syncthreads();
   if (s_i[0]) {
     if (tid == 0) atomicExch(p.error_flag, WB_ERR_UNSUPPORTED);
@@ -429,6 +459,7 @@ int wb_harvest_tail(WbWorkspace *ws, const double *d_cand, const double *d_score
   p.fw = (double *)ws->get("tl_fw", sizeof(double) * p.fw_cap);
   p.error_flag = ws->error_flag();
   if (!p.secbuf || !p.pad || !p.fw || !p.error_flag) return WB_ERR_CUDA;
+  WB_LAUNCH("search_base_kernel", search_base_kernel<<<(L * 32 + 255) / 256, 256, 0, stream>>>(d_cand, d_score, d_nc, L, MC, p.base));
   WB_LAUNCH("harvest_tail_kernel", harvest_tail_kernel<<<1, TL_THREADS, 0, stream>>>(p));
   WB_CUDA_CHECK(cudaGetLastError());
   return WB_OK;

@@ -47,3 +47,8 @@ int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int
 int wb_synthesis_run(WbWorkspace *ws, int fs, int fft_size, double frame_period_ms, const double *d_f0,
                      int f0_length, const double *d_sp, const double *d_ap, int out_length, double *d_out,
                      double f0_upper_bound, WbRngState *d_rng, cudaStream_t stream);
+int wb_synthesis_timebase(WbWorkspace *ws, int fs, int fft_size, double frame_period_ms, const double *d_f0,
+                          int f0_length, int out_length, cudaStream_t stream);
+int wb_synthesis_render(WbWorkspace *ws, int fs, int fft_size, double frame_period_ms, int f0_length,
+                        const double *d_sp, const double *d_ap, int out_length, double *d_out,
+                        double f0_upper_bound, WbRngState *d_rng, cudaStream_t stream);

@@ -48,8 +48,19 @@ int do_init() {
     memcpy(g_pow[0].col[c], e, sizeof(e));
   }
   for (int b = 1; b < WB_RNG_NPOW; ++b) mat_square(g_pow[b - 1], g_pow[b]);
-  WB_CUDA_CHECK(cudaMalloc(&g_d_pow, sizeof(Mat128) * WB_RNG_NPOW));
-  WB_CUDA_CHECK(cudaMemcpy(g_d_pow, g_pow.data(), sizeof(Mat128) * WB_RNG_NPOW, cudaMemcpyHostToDevice));
+  // 4-bit window tables (see wb_rng.cuh)
+  std::vector<uint32_t> tab((size_t)WB_RNG_NPOW * WB_RNG_TAB_ENTRIES * 4);
+  for (int b = 0; b < WB_RNG_NPOW; ++b)
+    for (int n = 0; n < 32; ++n)
+      for (int v = 0; v < 16; ++v) {
+        uint32_t acc[4] = {0, 0, 0, 0};
+        for (int bit = 0; bit < 4; ++bit)
+          if (v >> bit & 1)
+            for (int k = 0; k < 4; ++k) acc[k] ^= g_pow[b].col[n * 4 + bit][k];
+        memcpy(&tab[(((size_t)b * 32 + n) * 16 + v) * 4], acc, sizeof(acc));
+      }
+  WB_CUDA_CHECK(cudaMalloc(&g_d_pow, tab.size() * sizeof(uint32_t)));
+  WB_CUDA_CHECK(cudaMemcpy(g_d_pow, tab.data(), tab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
   WB_CUDA_CHECK(cudaMalloc(&g_d_state, sizeof(WbRngState)));
   // seed of the reference (world_matlabfunctions.cpp:244-247)
   const WbRngState s0 = {{123456789u, 362436069u, 521288629u, 88675123u}};
@@ -57,7 +68,7 @@ int do_init() {
   return WB_OK;
 }
 
-#define WB_RNG_CHUNK 32
+#define WB_RNG_CHUNK 64
 
 __global__ void rng_fill_kernel(const WbRngState *__restrict__ state, const uint4 *__restrict__ pow_tables,
                                 const unsigned long long *__restrict__ d_count,
@@ -74,10 +85,11 @@ __global__ void rng_fill_kernel(const WbRngState *__restrict__ state, const uint
 
 __global__ void rng_advance_kernel(WbRngState *state, const uint4 *__restrict__ pow_tables,
                                    const unsigned long long *__restrict__ d_count) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
+  if (blockIdx.x == 0 && threadIdx.x < 32) {
     uint32_t s[4] = {state->s[0], state->s[1], state->s[2], state->s[3]};
-    wb_rng_jump(pow_tables, s, *d_count);
-    state->s[0] = s[0]; state->s[1] = s[1]; state->s[2] = s[2]; state->s[3] = s[3];
+    wb_rng_jump_warp(pow_tables, s, *d_count);
+    __syncwarp();
+    if (threadIdx.x == 0) { state->s[0] = s[0]; state->s[1] = s[1]; state->s[2] = s[2]; state->s[3] = s[3]; }
   }
 }
 

@@ -29,28 +29,55 @@ __host__ __device__ __forceinline__ double wb_randn_next(uint32_t (&s)[4]) {
   return tmp / 268435456.0 - 6.0;
 }
 
-// cols: 128 columns of 4 words (uint4), column b = image of basis state bit b.
-__device__ __forceinline__ void wb_rng_apply(const uint4 *__restrict__ cols, uint32_t (&s)[4]) {
+// One jump matrix is stored as a 4-bit window table: tab[n][v], n = 0..31 (nibble of the state),
+// v = 0..15, holds the XOR of the matrix columns selected by v in nibble n.  A matrix-vector
+// product is then 32 independent 16-byte loads (fully unrolled, no data-dependent loop).
+#define WB_RNG_TAB_ENTRIES (32 * 16)
+__device__ __forceinline__ void wb_rng_apply(const uint4 *__restrict__ tab, uint32_t (&s)[4]) {
   uint32_t o0 = 0, o1 = 0, o2 = 0, o3 = 0;
 #pragma unroll
   for (int w = 0; w < 4; ++w) {
-    uint32_t bits = s[w];
-    while (bits) {
-      const int b = __ffs(bits) - 1;
-      bits &= bits - 1;
-      const uint4 c = __ldg(&cols[w * 32 + b]);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const uint32_t nib = (s[w] >> (4 * k)) & 15u;
+      const uint4 c = __ldg(&tab[(w * 8 + k) * 16 + nib]);
       o0 ^= c.x; o1 ^= c.y; o2 ^= c.z; o3 ^= c.w;
     }
   }
   s[0] = o0; s[1] = o1; s[2] = o2; s[3] = o3;
 }
 
-// s <- M^n s.  pow_tables: WB_RNG_NPOW matrices of 128 uint4 columns.
+// s <- M^n s.  pow_tables: WB_RNG_NPOW window tables.
 __device__ __forceinline__ void wb_rng_jump(const uint4 *__restrict__ pow_tables, uint32_t (&s)[4],
                                             unsigned long long n) {
   int b = 0;
   while (n) {
-    if (n & 1ull) wb_rng_apply(pow_tables + b * 128, s);
+    if (n & 1ull) wb_rng_apply(pow_tables + (size_t)b * WB_RNG_TAB_ENTRIES, s);
+    n >>= 1;
+    ++b;
+  }
+}
+
+// Warp-cooperative version: every lane passes the same state; lane l looks up nibble l and the
+// partial results are XOR-reduced.  All 32 lanes must call.
+__device__ __forceinline__ void wb_rng_jump_warp(const uint4 *__restrict__ pow_tables, uint32_t (&s)[4],
+                                                 unsigned long long n) {
+  const int lane = threadIdx.x & 31;
+  int b = 0;
+  while (n) {
+    if (n & 1ull) {
+      const uint32_t word = (lane >> 3) == 0 ? s[0] : ((lane >> 3) == 1 ? s[1] : ((lane >> 3) == 2 ? s[2] : s[3]));
+      const uint32_t nib = (word >> (4 * (lane & 7))) & 15u;
+      uint4 c = __ldg(&pow_tables[(size_t)b * WB_RNG_TAB_ENTRIES + lane * 16 + nib]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        c.x ^= __shfl_xor_sync(0xffffffffu, c.x, o);
+        c.y ^= __shfl_xor_sync(0xffffffffu, c.y, o);
+        c.z ^= __shfl_xor_sync(0xffffffffu, c.z, o);
+        c.w ^= __shfl_xor_sync(0xffffffffu, c.w, o);
+      }
+      s[0] = c.x; s[1] = c.y; s[2] = c.z; s[3] = c.w;
+    }
     n >>= 1;
     ++b;
   }

@@ -99,6 +99,7 @@ __device__ __forceinline__ IncFn ps_incfn(double a, int e) {
   return f;
 }
 
+// Writes total_phase[i]; the fmod / wrap detection is done by the (fully parallel) pulse kernels.
 __global__ void __launch_bounds__(PS_THREADS) phase_scan_kernel(const double *__restrict__ incr, int n,
                                                                 double *__restrict__ wrap_phase) {
   __shared__ IncFn warp_fn[32];
@@ -106,10 +107,9 @@ __global__ void __launch_bounds__(PS_THREADS) phase_scan_kernel(const double *__
   __shared__ double s_sum;   // current running sum (exact double)
   __shared__ int s_pos;      // next element to process
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const double two_pi = 2.0 * WB_PI;
   if (tid == 0) {
     const double s0 = incr[0];  // total_phase[0] = interpolated_f0[0] * const_val
-    wrap_phase[0] = fmod(s0, two_pi);
+    wrap_phase[0] = s0;
     s_sum = s0;
     s_pos = 1;
   }
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(PS_THREADS) phase_scan_kernel(const double *__
       // degenerate running sum (zero/negative/subnormal/non-finite): genuine sequential add
       if (tid == 0) {
         const double s = sum + incr[pos];
-        wrap_phase[pos] = fmod(s, two_pi);
+        wrap_phase[pos] = s;
         s_sum = s;
         s_pos = pos + 1;
       }
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(PS_THREADS) phase_scan_kernel(const double *__
       if (i < n && my_bad == 0x7fffffff) {
         S += (S & 1ull) ? fn[q].co : fn[q].ce;
         if (S >= LIMIT) my_bad = i;
-        else wrap_phase[i] = fmod((double)S * ulp, two_pi);
+        else wrap_phase[i] = (double)S * ulp;
       }
     }
     if (my_bad != 0x7fffffff) atomicMin(&s_first_bad, my_bad);
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(PS_THREADS) phase_scan_kernel(const double *__
         }
         const double before = (double)Sb * ulp;
         const double s = before + incr[first_bad];
-        wrap_phase[first_bad] = fmod(s, two_pi);
+        wrap_phase[first_bad] = s;
         s_sum = s;
         s_pos = first_bad + 1;
       }
@@ -225,21 +225,22 @@ __global__ void __launch_bounds__(PS_THREADS) phase_scan_kernel(const double *__
 
 // ---- K3: pulse detection + ordered compaction (synthesis.cpp:266-281) -------------------------
 #define PD_THREADS 256
-__global__ void pulse_count_kernel(const double *__restrict__ wrap, int y_length,
+__global__ void pulse_count_kernel(const double *__restrict__ total, int y_length,
                                    unsigned long long *__restrict__ block_counts) {
   __shared__ int s_cnt;
   if (threadIdx.x == 0) s_cnt = 0;
   __syncthreads();
   const int ii = blockIdx.x * PD_THREADS + threadIdx.x;
+  const double two_pi = 2.0 * WB_PI;
   bool flag = false;
-  if (ii < y_length - 1) flag = fabs(wrap[ii + 1] - wrap[ii]) > WB_PI;
+  if (ii < y_length - 1) flag = fabs(fmod(total[ii + 1], two_pi) - fmod(total[ii], two_pi)) > WB_PI;
   const unsigned m = __ballot_sync(0xffffffffu, flag);
   if ((threadIdx.x & 31) == 0 && m) atomicAdd(&s_cnt, __popc(m));
   __syncthreads();
   if (threadIdx.x == 0) block_counts[blockIdx.x] = (unsigned long long)s_cnt;
 }
 
-__global__ void pulse_write_kernel(const double *__restrict__ wrap, int y_length, int fs,
+__global__ void pulse_write_kernel(const double *__restrict__ total, int y_length, int fs,
                                    const unsigned long long *__restrict__ block_offsets,
                                    int *__restrict__ pulse_index, double *__restrict__ pulse_shift, int max_pulses) {
   __shared__ int warp_cnt[PD_THREADS / 32];
@@ -248,7 +249,7 @@ __global__ void pulse_write_kernel(const double *__restrict__ wrap, int y_length
   bool flag = false;
   double w0 = 0.0, w1 = 0.0;
   if (ii < y_length - 1) {
-    w0 = wrap[ii]; w1 = wrap[ii + 1];
+    w0 = fmod(total[ii], 2.0 * WB_PI); w1 = fmod(total[ii + 1], 2.0 * WB_PI);
     flag = fabs(w1 - w0) > WB_PI;
   }
   const unsigned m = __ballot_sync(0xffffffffu, flag);
@@ -488,25 +489,21 @@ static void make_dc_remover(int fft_size, std::vector<double> &r) {
   }
 }
 
-// f0_upper_bound: an upper bound of max(f0) known to the host (e.g. Harvest's f0_ceil); <= 0 if
-// unknown, in which case the pulse count is read back (one stream synchronisation).
-int wb_synthesis_run(WbWorkspace *ws, int fs, int fft_size, double frame_period_ms, const double *d_f0,
-                     int f0_length, const double *d_sp, const double *d_ap, int out_length, double *d_out,
-                     double f0_upper_bound, WbRngState *d_rng, cudaStream_t stream) {
+// ---- host side -------------------------------------------------------------------------------
+// Part 1 (depends on f0 only): time base, exact phase scan, pulse list.  May run on a side
+// stream while CheapTrick / D4C are still busy.
+int wb_synthesis_timebase(WbWorkspace *ws, int fs, int fft_size, double frame_period_ms, const double *d_f0,
+                          int f0_length, int out_length, cudaStream_t stream) {
   if (out_length <= 0) return WB_OK;
   if (f0_length < 2) return WB_ERR_ARG;
-  int log2n = 0;
-  while ((1 << log2n) < fft_size) ++log2n;
-  if ((1 << log2n) != fft_size || fft_size < 128 || fft_size > 8192) return WB_ERR_UNSUPPORTED;
   const double frame_period = frame_period_ms / 1000.;      // synthesis.cpp:31
   const double lowest_f0 = fs / fft_size + 1.0;             // synthesis.cpp:97 (integer division)
   // Every pulse needs a 2 pi phase advance and one sample adds at most 2 pi max(f0, 500) / fs,
   // so pulses <= out_length * max(f0_max, 500) / fs + 1.  The index/shift lists are sized for
   // f0 <= fs / 4; the response buffer for the tighter bound (or the exact count).
   const int max_pulses = out_length / 4 + 16;
-
   double *d_incr = (double *)ws->get("syn_incr", sizeof(double) * out_length);
-  double *d_wrap = (double *)ws->get("syn_wrap", sizeof(double) * out_length);
+  double *d_total = (double *)ws->get("syn_wrap", sizeof(double) * out_length);
   unsigned char *d_vuv = (unsigned char *)ws->get("syn_vuv", out_length);
   const int n_blocks = (out_length + PD_THREADS - 1) / PD_THREADS;
   unsigned long long *d_bc = (unsigned long long *)ws->get("syn_bcount", sizeof(unsigned long long) * (n_blocks + 1));
@@ -515,11 +512,39 @@ int wb_synthesis_run(WbWorkspace *ws, int fs, int fft_size, double frame_period_
   double *d_pshift = (double *)ws->get("syn_pshift", sizeof(double) * max_pulses);
   int *d_np = (int *)ws->get("syn_np", sizeof(int) * 4);
   unsigned long long *d_ncount = (unsigned long long *)ws->get("syn_ncount", sizeof(unsigned long long));
+  if (!d_incr || !d_total || !d_vuv || !d_bc || !d_bo || !d_pidx || !d_pshift || !d_np || !d_ncount) return WB_ERR_CUDA;
+  WB_LAUNCH("timebase_kernel", timebase_kernel<<<(out_length + 255) / 256, 256, 0, stream>>>(
+      d_f0, f0_length, fs, frame_period, lowest_f0, out_length, d_incr, d_vuv));
+  WB_LAUNCH("phase_scan_kernel", phase_scan_kernel<<<1, PS_THREADS, 0, stream>>>(d_incr, out_length, d_total));
+  WB_LAUNCH("pulse_count_kernel", pulse_count_kernel<<<n_blocks, PD_THREADS, 0, stream>>>(d_total, out_length, d_bc));
+  int rc = wb_exclusive_scan_u64(d_bc, d_bo, n_blocks, stream);
+  if (rc) return rc;
+  WB_LAUNCH("pulse_write_kernel", pulse_write_kernel<<<n_blocks, PD_THREADS, 0, stream>>>(d_total, out_length, fs, d_bo, d_pidx, d_pshift, max_pulses));
+  WB_LAUNCH("pulse_finalize_kernel", pulse_finalize_kernel<<<1, 1, 0, stream>>>(d_bo, n_blocks, d_pidx, max_pulses, d_np, d_ncount, ws->error_flag()));
+  WB_CUDA_CHECK(cudaGetLastError());
+  return WB_OK;
+}
+
+// Part 2: noise, impulse responses, overlap-add.  Must follow wb_synthesis_timebase on `ws`.
+// f0_upper_bound: an upper bound of max(f0) known to the host (e.g. Harvest's f0_ceil); <= 0 if
+// unknown, in which case the pulse count is read back (one stream synchronisation).
+int wb_synthesis_render(WbWorkspace *ws, int fs, int fft_size, double frame_period_ms, int f0_length,
+                        const double *d_sp, const double *d_ap, int out_length, double *d_out,
+                        double f0_upper_bound, WbRngState *d_rng, cudaStream_t stream) {
+  if (out_length <= 0) return WB_OK;
+  int log2n = 0;
+  while ((1 << log2n) < fft_size) ++log2n;
+  if ((1 << log2n) != fft_size || fft_size < 128 || fft_size > 8192) return WB_ERR_UNSUPPORTED;
+  const double frame_period = frame_period_ms / 1000.;
+  const int max_pulses = out_length / 4 + 16;
+  unsigned char *d_vuv = (unsigned char *)ws->get("syn_vuv", 0);
+  int *d_pidx = (int *)ws->get("syn_pidx", 0);
+  double *d_pshift = (double *)ws->get("syn_pshift", 0);
+  int *d_np = (int *)ws->get("syn_np", 0);
+  unsigned long long *d_ncount = (unsigned long long *)ws->get("syn_ncount", 0);
   double *d_noise = (double *)ws->get("noise", sizeof(double) * out_length);
   double *d_dcr = (double *)ws->get("syn_dcr", sizeof(double) * fft_size);
-  if (!d_incr || !d_wrap || !d_vuv || !d_bc || !d_bo || !d_pidx || !d_pshift || !d_np || !d_ncount || !d_noise ||
-      !d_dcr)
-    return WB_ERR_CUDA;
+  if (!d_vuv || !d_pidx || !d_pshift || !d_np || !d_ncount || !d_noise || !d_dcr) return WB_ERR_CUDA;
   const cplx *tw_n = wb_twiddle_table(fft_size);
   const cplx *tw_2n = wb_twiddle_table(2 * fft_size);
   if (!tw_n || !tw_2n) return WB_ERR_CUDA;
@@ -531,16 +556,7 @@ int wb_synthesis_run(WbWorkspace *ws, int fs, int fft_size, double frame_period_
     for (int i = 0; i < fft_size; ++i) h[i] = r[i];
     WB_CUDA_CHECK(cudaMemcpyAsync(d_dcr, h, sizeof(double) * fft_size, cudaMemcpyHostToDevice, stream));
   }
-
-  WB_LAUNCH("timebase_kernel", timebase_kernel<<<(out_length + 255) / 256, 256, 0, stream>>>(d_f0, f0_length, fs, frame_period, lowest_f0,
-                                                                out_length, d_incr, d_vuv));
-  WB_LAUNCH("phase_scan_kernel", phase_scan_kernel<<<1, PS_THREADS, 0, stream>>>(d_incr, out_length, d_wrap));
-  WB_LAUNCH("pulse_count_kernel", pulse_count_kernel<<<n_blocks, PD_THREADS, 0, stream>>>(d_wrap, out_length, d_bc));
-  int rc = wb_exclusive_scan_u64(d_bc, d_bo, n_blocks, stream);
-  if (rc) return rc;
-  WB_LAUNCH("pulse_write_kernel", pulse_write_kernel<<<n_blocks, PD_THREADS, 0, stream>>>(d_wrap, out_length, fs, d_bo, d_pidx, d_pshift, max_pulses));
-  WB_LAUNCH("pulse_finalize_kernel", pulse_finalize_kernel<<<1, 1, 0, stream>>>(d_bo, n_blocks, d_pidx, max_pulses, d_np, d_ncount, ws->error_flag()));
-  WB_CUDA_CHECK(cudaGetLastError());
+  int rc;
   if ((rc = wb_rng_fill(d_rng, d_ncount, (unsigned long long)out_length, d_noise, stream))) return rc;
 
   int resp_pulses;
@@ -573,4 +589,13 @@ int wb_synthesis_run(WbWorkspace *ws, int fs, int fft_size, double frame_period_
   WB_LAUNCH("ola_kernel", ola_kernel<<<(out_length + 255) / 256, 256, 0, stream>>>(d_resp, d_pidx, d_np, resp_pulses, fft_size, out_length, d_out));
   WB_CUDA_CHECK(cudaGetLastError());
   return wb_rng_advance(d_rng, d_ncount, stream);
+}
+
+int wb_synthesis_run(WbWorkspace *ws, int fs, int fft_size, double frame_period_ms, const double *d_f0,
+                     int f0_length, const double *d_sp, const double *d_ap, int out_length, double *d_out,
+                     double f0_upper_bound, WbRngState *d_rng, cudaStream_t stream) {
+  int rc = wb_synthesis_timebase(ws, fs, fft_size, frame_period_ms, d_f0, f0_length, out_length, stream);
+  if (rc) return rc;
+  return wb_synthesis_render(ws, fs, fft_size, frame_period_ms, f0_length, d_sp, d_ap, out_length, d_out,
+                             f0_upper_bound, d_rng, stream);
 }
