@@ -79,7 +79,7 @@ int wb_randn_fill(double *out, int n);                /* HOST out; next n values
 /* ---- stand-alone FFT with the reference wrapper's semantics -------------------------
  * include/world_fft.hpp:33-41 + src/world_fft.cpp:31-77: forward = e^{+i}, backward = e^{-i},
  * unnormalised; complex numbers are interleaved (re, im) doubles; HOST pointers;
- * n = power of two in [16, 16384]; `batch` independent transforms back to back. */
+ * n = power of two in [128, 16384] (c2c: up to 8192); `batch` independent transforms back to back. */
 int wb_fft_r2c(const double *in, int n, int batch, double *out);   /* fft_plan_dft_r2c_1d + fft_execute */
 int wb_fft_c2r(const double *in, int n, int batch, double *out);   /* fft_plan_dft_c2r_1d + fft_execute */
 int wb_fft_c2c(const double *in, int n, int batch, int sign, double *out); /* sign: 1 = FFT_FORWARD, 2 = FFT_BACKWARD */

@@ -44,9 +44,10 @@ struct CtParams {
   int *error_flag;
 };
 
+template <int LOG2N>
 __global__ void __launch_bounds__(256) ct_frame_kernel(CtParams p) {
   extern __shared__ double2 smem_raw[];
-  const int N = p.fft_size, NC = N / 2, bins = NC + 1;
+  constexpr int N = 1 << LOG2N, NC = N / 2, bins = NC + 1;
   cplx *S = smem_raw;                                         // FFT slots
   double *A = reinterpret_cast<double *>(S + wb_fft_slots(NC));  // N + 2 doubles
   double *B = A + (N + 2);                                    // seg_capacity doubles
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(256) ct_frame_kernel(CtParams p) {
   __syncthreads();
 
   // ---- power spectrum (cheaptrick.cpp:198-218)
-  wb_rfft<1>(S, NC, p.log2nc, p.twiddle, [&](int k, cplx X) { A[k] = X.x * X.x + X.y * X.y; });
+  wb_rfft_t<1, LOG2N - 1>(S, p.twiddle, [&](int k, cplx X) { A[k] = X.x * X.x + X.y * X.y; });
   wb_dc_correction(A, f0, fs, N);
 
   // ---- linear smoothing with width 2 f0 / 3 (cheaptrick.cpp:124-125)
@@ -109,7 +110,7 @@ __global__ void __launch_bounds__(256) ct_frame_kernel(CtParams p) {
 
   // ---- liftering in the cepstral domain (cheaptrick.cpp:238-269)
   const double q1 = p.q1;
-  wb_rfft<1>(S, NC, p.log2nc, p.twiddle, [&](int k, cplx X) {
+  wb_rfft_t<1, LOG2N - 1>(S, p.twiddle, [&](int k, cplx X) {
     double sl = 1.0, cl = (1.0 - 2.0 * q1) + 2.0 * q1;
     if (k > 0) {
       const double quefrency = static_cast<double>(k) / fs;
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(256) ct_frame_kernel(CtParams p) {
     }
     A[k] = X.x * sl * cl / N;
   });
-  wb_irfft<-1>(S, NC, p.log2nc, p.twiddle, [&](int k) { return make_double2(A[k], 0.0); });
+  wb_irfft_t<-1, LOG2N - 1>(S, p.twiddle, [&](int k) { return make_double2(A[k], 0.0); });
 
   double *out = p.sp + (size_t)frame * bins;
   for (int i = tid; i < bins; i += nt) out[i] = exp(W[wb_didx(i)]);
@@ -162,9 +163,12 @@ int wb_cheaptrick_run(WbWorkspace *ws, int fs, int fft_size, double q1, double f
   p.seg_capacity = fft_size / 2 + fft_size / 4 + 8;
   p.error_flag = ws->error_flag();
   const size_t smem = wb_cheaptrick_smem_bytes(fft_size, p.seg_capacity);
-  WB_CUDA_CHECK(cudaFuncSetAttribute(ct_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int threads = wb_max_i(64, wb_min_i(256, fft_size / 8));
-  WB_LAUNCH("ct_frame_kernel", ct_frame_kernel<<<f0_length, threads, smem, stream>>>(p));
+  rc = WB_DISPATCH_LOG2(log2n, 8, 13, {
+    if (cudaFuncSetAttribute(ct_frame_kernel<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WB_ERR_CUDA;
+    WB_LAUNCH("ct_frame_kernel", ct_frame_kernel<L2><<<f0_length, threads, smem, stream>>>(p));
+  });
+  if (rc) return rc;
   WB_CUDA_CHECK(cudaGetLastError());
   return wb_rng_advance(d_rng, d_offsets + f0_length, stream);
 }

@@ -91,9 +91,10 @@ struct LtParams {
   double *ap0;
 };
 
+template <int LOG2N>
 __global__ void __launch_bounds__(256) lt_frame_kernel(LtParams p) {
   extern __shared__ double2 smem_raw[];
-  const int N = p.fft_size, NC = N / 2;
+  constexpr int N = 1 << LOG2N, NC = N / 2;
   cplx *S = smem_raw;
   double *win = reinterpret_cast<double *>(S + wb_fft_slots(NC));  // N doubles
   double *red = win + N;                                          // 128
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(256) lt_frame_kernel(LtParams p) {
   double a = 0.0, b = 0.0;
   const int b0 = p.boundary0, b1 = p.boundary1, b2 = p.boundary2;
   // wb_rfft's emit runs once per k on some thread: accumulate per thread, reduce afterwards
-  wb_rfft<1>(S, NC, p.log2nc, p.twiddle, [&](int k, cplx X) {
+  wb_rfft_t<1, LOG2N - 1>(S, p.twiddle, [&](int k, cplx X) {
     if (k > b0 && k <= b2) {
       const double pw = X.x * X.x + X.y * X.y;
       b += pw;
@@ -199,9 +200,10 @@ struct BodyParams {
   int *error_flag;
 };
 
+template <int LOG2N>
 __global__ void __launch_bounds__(512) d4c_body_kernel(BodyParams p) {
   extern __shared__ double2 smem_raw[];
-  const int N = p.fft_size_d4c, NC = N / 2, bins = NC + 1;
+  constexpr int N = 1 << LOG2N, NC = N / 2, bins = NC + 1;
   const int binsp = (bins + 1) & ~1;  // keep 16-byte alignment
   cplx *S = smem_raw;                                            // slots for an N-point complex FFT
   double *SC = reinterpret_cast<double *>(S + wb_fft_slots(N));   // static centroid / group delay
@@ -223,7 +225,7 @@ __global__ void __launch_bounds__(512) d4c_body_kernel(BodyParams p) {
   const int fs = p.fs;
   const double pos = p.tpos[frame];
   const double *noise = p.noise + p.noise_off[frame];
-  const int log2n = p.log2n;
+  constexpr int log2n = LOG2N;
 
   // ---- static centroid: two windows at pos -/+ 0.25/f0 (d4c.cpp:339-405)
   // The reference transforms w[n] and (n+1) w[n] separately; both are real, so one complex
@@ -242,7 +244,7 @@ __global__ void __launch_bounds__(512) d4c_body_kernel(BodyParams p) {
       S[wb_sidx(j)] = z;
     }
     __syncthreads();
-    wb_cfft_dif<1>(S, N, log2n, p.tw_2n, 2 * N);
+    wb_cfft_dif_t<1, LOG2N>(S, p.tw_2n);
     for (int k = tid; k <= NC; k += nt) {
       const cplx zk = S[wb_sidx(wb_brev(k, log2n))];
       const cplx zc = S[wb_sidx(wb_brev((N - k) & (N - 1), log2n))];
@@ -262,7 +264,7 @@ __global__ void __launch_bounds__(512) d4c_body_kernel(BodyParams p) {
     for (int j = wlen + tid; j < N; j += nt) W[wb_didx(j)] = 0.0;
     __syncthreads();
     // `win` (= SP..SG) is dead from here on
-    wb_rfft<1>(S, NC, log2n - 1, p.tw_n, [&](int k, cplx X) { SP[k] = X.x * X.x + X.y * X.y; });
+    wb_rfft_t<1, LOG2N - 1>(S, p.tw_n, [&](int k, cplx X) { SP[k] = X.x * X.x + X.y * X.y; });
     wb_dc_correction(SP, f0, fs, N);
     if (!wb_linear_smoothing(SP, SP, f0, fs, N, seg, p.seg_capacity, red)) {
       if (tid == 0) atomicExch(p.error_flag, WB_ERR_UNSUPPORTED);
@@ -288,7 +290,7 @@ __global__ void __launch_bounds__(512) d4c_body_kernel(BodyParams p) {
       W[wb_didx(j)] = (j < wl) ? SC[center - hwl + j] * __ldg(&p.nuttall[j]) : 0.0;
     __syncthreads();
     double tot = 0.0;
-    wb_rfft<1>(S, NC, log2n - 1, p.tw_n, [&](int k, cplx X) {
+    wb_rfft_t<1, LOG2N - 1>(S, p.tw_n, [&](int k, cplx X) {
       const double pw = X.x * X.x + X.y * X.y;
       SG[k] = pw;
       tot += pw;
@@ -411,8 +413,11 @@ int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int
     p.boundary2 = static_cast<int>(ceil(7900.0 * N_lt / fs));
     p.twiddle = tw_lt; p.noise = d_noise; p.noise_off = d_offsets; p.ap0 = d_ap0;
     const size_t smem = sizeof(cplx) * wb_fft_slots(N_lt / 2) + sizeof(double) * (N_lt + 128);
-    WB_CUDA_CHECK(cudaFuncSetAttribute(lt_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    WB_LAUNCH("lt_frame_kernel", lt_frame_kernel<<<f0_length, 256, smem, stream>>>(p));
+    rc = WB_DISPATCH_LOG2(l_lt, 9, 14, {
+      if (cudaFuncSetAttribute(lt_frame_kernel<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WB_ERR_CUDA;
+      WB_LAUNCH("lt_frame_kernel", lt_frame_kernel<L2><<<f0_length, 256, smem, stream>>>(p));
+    });
+    if (rc) return rc;
     WB_CUDA_CHECK(cudaGetLastError());
   }
   if ((rc = wb_rng_advance(d_rng, d_offsets + f0_length, stream))) return rc;
@@ -433,8 +438,11 @@ int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int
     const int binsp = ((N / 2 + 1) + 1) & ~1;
     const size_t smem = sizeof(cplx) * wb_fft_slots(N) + sizeof(double) * (3 * binsp + p.seg_capacity + 1088) +
                         sizeof(int) * 256 + sizeof(unsigned long long) * 4 + sizeof(double) * (D4C_MAX_AP + 2);
-    WB_CUDA_CHECK(cudaFuncSetAttribute(d4c_body_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    WB_LAUNCH("d4c_body_kernel", d4c_body_kernel<<<f0_length, 512, smem, stream>>>(p));
+    rc = WB_DISPATCH_LOG2(l, 9, 13, {
+      if (cudaFuncSetAttribute(d4c_body_kernel<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WB_ERR_CUDA;
+      WB_LAUNCH("d4c_body_kernel", d4c_body_kernel<L2><<<f0_length, 512, smem, stream>>>(p));
+    });
+    if (rc) return rc;
     WB_CUDA_CHECK(cudaGetLastError());
   }
   return wb_rng_advance(d_rng, d_offsets + f0_length, stream);

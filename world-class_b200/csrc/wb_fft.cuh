@@ -6,14 +6,18 @@
 //   backward (c2r, c2c FFT_BACKWARD): x[n] = sum_k X[k] e^{-2 pi i n k / N}   (SIGN = -1)
 //   everything unnormalised (c2r(r2c(x)) = N x).
 //
-// Layout.  A complex FFT of NC points lives in NC (+ padding) double2 slots of shared
-// memory.  Slot padding sidx(i) = i + (i >> 3) makes every pass bank-conflict free for
-// 16-byte accesses.  Passes are radix-8 (plus one radix-4/2 clean-up) butterflies held
-// in registers; the decimation-in-frequency (DIF) transform reads natural order and
-// leaves BIT-REVERSED order, the decimation-in-time (DIT) transform reads bit-reversed
-// order and leaves natural order, so forward -> pointwise -> inverse chains need no
-// reordering pass.  Twiddles come from a per-size table T[k] = e^{+2 pi i k / NT},
-// NT = 2 NC, kept in global memory (L1-resident, read through __ldg).
+// Layout.  A complex FFT of N points lives in N (+ padding) double2 slots of shared memory.
+// Slot padding sidx(i) = i + (i >> 3) makes every pass bank-conflict free for 16-byte
+// accesses.  Passes are radix-8 (plus one radix-4/2 clean-up) butterflies held in registers;
+// the decimation-in-frequency (DIF) transform reads natural order and leaves BIT-REVERSED
+// order, the decimation-in-time (DIT) transform reads bit-reversed order and leaves natural
+// order, so forward -> pointwise -> inverse chains need no reordering pass.  Twiddles come
+// from a table T[k] = e^{+2 pi i k / (2N)} kept in global memory (L1-resident, __ldg).
+//
+// Everything is templated on log2(N): sub-block sizes, slot offsets (the padded offset of
+// element base + q*m is sidx(base) + q*m + (q*m >> 3), a compile-time immediate) and twiddle
+// strides fold to constants and every pass is fully unrolled.  Kernels are instantiated per FFT
+// size and dispatched on the host.
 #pragma once
 #include "wb_common.cuh"
 
@@ -77,184 +81,177 @@ __device__ __forceinline__ void wb_dft4(cplx (&a)[4]) {
   a[1] = wb_cadd(b2, b3); a[3] = wb_csub(b2, b3);
 }
 
-// ---- one DIF pass over sub-blocks of size M (radix R), in place ---------------------
-// s: padded slots, N: transform size, T: table with NT entries, tstep = NT / M.
+// padded offset of element (base + q * m) relative to sidx(base); valid because base mod 8 < m
+// whenever m < 8 (see header comment)
+#define WB_OFF(q, m) ((q) * (m) + (((q) * (m)) >> 3))
+
+// twiddles w^1..w^7 of one radix-8 butterfly from three table loads
 template <int SIGN>
-__device__ __forceinline__ void wb_pass_dif8(cplx *s, int N, int M, const cplx *__restrict__ T, int NT) {
-  const int m8 = M >> 3, tstep = NT / M;
-  for (int u = threadIdx.x; u < (N >> 3); u += blockDim.x) {
+__device__ __forceinline__ void wb_twiddles8(const cplx *__restrict__ T, int t1, cplx (&w)[8]) {
+  w[1] = wb_tw<SIGN>(T, t1);
+  w[2] = wb_tw<SIGN>(T, 2 * t1);
+  w[4] = wb_tw<SIGN>(T, 4 * t1);
+  w[3] = wb_cmul(w[1], w[2]);
+  w[5] = wb_cmul(w[1], w[4]);
+  w[6] = wb_cmul(w[2], w[4]);
+  w[7] = wb_cmul(w[3], w[4]);
+}
+
+// ---- one DIF pass over sub-blocks of size M (radix 8), in place; table has 2N entries -------
+template <int SIGN, int N, int M>
+__device__ __forceinline__ void wb_pass_dif8(cplx *s, const cplx *__restrict__ T) {
+  constexpr int m8 = M / 8, tstep = 2 * N / M;
+  for (int u = threadIdx.x; u < N / 8; u += blockDim.x) {
     const int j = u & (m8 - 1);
     const int base = ((u - j) << 3) + j;  // (u / m8) * M + j
+    cplx *sp = s + wb_sidx(base);
     cplx a[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) a[q] = s[wb_sidx(base + q * m8)];
+    for (int q = 0; q < 8; ++q) a[q] = sp[WB_OFF(q, m8)];
     wb_dft8<SIGN>(a);
     if (m8 > 1) {
-      const cplx w1 = wb_tw<SIGN>(T, j * tstep);
-      const cplx w2 = wb_tw<SIGN>(T, 2 * j * tstep);
-      const cplx w4 = wb_tw<SIGN>(T, 4 * j * tstep);
-      const cplx w3 = wb_cmul(w1, w2), w5 = wb_cmul(w1, w4), w6 = wb_cmul(w2, w4);
-      const cplx w7 = wb_cmul(w3, w4);
-      a[1] = wb_cmul(a[1], w1); a[2] = wb_cmul(a[2], w2); a[3] = wb_cmul(a[3], w3);
-      a[4] = wb_cmul(a[4], w4); a[5] = wb_cmul(a[5], w5); a[6] = wb_cmul(a[6], w6);
-      a[7] = wb_cmul(a[7], w7);
+      cplx w[8];
+      wb_twiddles8<SIGN>(T, j * tstep, w);
+#pragma unroll
+      for (int q = 1; q < 8; ++q) a[q] = wb_cmul(a[q], w[q]);
     }
     // slot q' <- A[brev3(q')]
-    s[wb_sidx(base + 0 * m8)] = a[0]; s[wb_sidx(base + 1 * m8)] = a[4];
-    s[wb_sidx(base + 2 * m8)] = a[2]; s[wb_sidx(base + 3 * m8)] = a[6];
-    s[wb_sidx(base + 4 * m8)] = a[1]; s[wb_sidx(base + 5 * m8)] = a[5];
-    s[wb_sidx(base + 6 * m8)] = a[3]; s[wb_sidx(base + 7 * m8)] = a[7];
+    sp[WB_OFF(0, m8)] = a[0]; sp[WB_OFF(1, m8)] = a[4]; sp[WB_OFF(2, m8)] = a[2]; sp[WB_OFF(3, m8)] = a[6];
+    sp[WB_OFF(4, m8)] = a[1]; sp[WB_OFF(5, m8)] = a[5]; sp[WB_OFF(6, m8)] = a[3]; sp[WB_OFF(7, m8)] = a[7];
   }
 }
 
-template <int SIGN>
-__device__ __forceinline__ void wb_pass_dif4(cplx *s, int N, int M, const cplx *__restrict__ T, int NT) {
-  const int m4 = M >> 2, tstep = NT / M;
-  for (int u = threadIdx.x; u < (N >> 2); u += blockDim.x) {
-    const int j = u & (m4 - 1);
-    const int base = ((u - j) << 2) + j;
+// final radix-4 / radix-2 pass (sub-block size 4 or 2: no twiddles)
+template <int SIGN, int N>
+__device__ __forceinline__ void wb_pass_dif4_last(cplx *s) {
+  for (int u = threadIdx.x; u < N / 4; u += blockDim.x) {
+    cplx *sp = s + wb_sidx(4 * u);
     cplx a[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) a[q] = s[wb_sidx(base + q * m4)];
+    for (int q = 0; q < 4; ++q) a[q] = sp[q];
     wb_dft4<SIGN>(a);
-    if (m4 > 1) {
-      const cplx w1 = wb_tw<SIGN>(T, j * tstep);
-      const cplx w2 = wb_tw<SIGN>(T, 2 * j * tstep);
-      const cplx w3 = wb_cmul(w1, w2);
-      a[1] = wb_cmul(a[1], w1); a[2] = wb_cmul(a[2], w2); a[3] = wb_cmul(a[3], w3);
-    }
-    s[wb_sidx(base)] = a[0]; s[wb_sidx(base + m4)] = a[2];
-    s[wb_sidx(base + 2 * m4)] = a[1]; s[wb_sidx(base + 3 * m4)] = a[3];
+    sp[0] = a[0]; sp[1] = a[2]; sp[2] = a[1]; sp[3] = a[3];
   }
 }
-
-template <int SIGN>
-__device__ __forceinline__ void wb_pass_dif2(cplx *s, int N, int M, const cplx *__restrict__ T, int NT) {
-  const int m2 = M >> 1, tstep = NT / M;
-  for (int u = threadIdx.x; u < (N >> 1); u += blockDim.x) {
-    const int j = u & (m2 - 1);
-    const int base = ((u - j) << 1) + j;
-    cplx a0 = s[wb_sidx(base)], a1 = s[wb_sidx(base + m2)];
-    cplx d = wb_csub(a0, a1);
-    if (m2 > 1) d = wb_cmul(d, wb_tw<SIGN>(T, j * tstep));
-    s[wb_sidx(base)] = wb_cadd(a0, a1);
-    s[wb_sidx(base + m2)] = d;
+template <int SIGN, int N>
+__device__ __forceinline__ void wb_pass_dif2_last(cplx *s) {
+  for (int u = threadIdx.x; u < N / 2; u += blockDim.x) {
+    cplx *sp = s + wb_sidx(2 * u);
+    const cplx a0 = sp[0], a1 = sp[1];
+    sp[0] = wb_cadd(a0, a1);
+    sp[1] = wb_csub(a0, a1);
   }
 }
 
 // ---- DIT passes (transpose of the above) --------------------------------------------
-template <int SIGN>
-__device__ __forceinline__ void wb_pass_dit8(cplx *s, int N, int M, const cplx *__restrict__ T, int NT) {
-  const int m8 = M >> 3, tstep = NT / M;
-  for (int u = threadIdx.x; u < (N >> 3); u += blockDim.x) {
+template <int SIGN, int N, int M>
+__device__ __forceinline__ void wb_pass_dit8(cplx *s, const cplx *__restrict__ T) {
+  constexpr int m8 = M / 8, tstep = 2 * N / M;
+  for (int u = threadIdx.x; u < N / 8; u += blockDim.x) {
     const int j = u & (m8 - 1);
     const int base = ((u - j) << 3) + j;
+    cplx *sp = s + wb_sidx(base);
     cplx a[8];
     // a[r] = slot brev3(r)
-    a[0] = s[wb_sidx(base + 0 * m8)]; a[4] = s[wb_sidx(base + 1 * m8)];
-    a[2] = s[wb_sidx(base + 2 * m8)]; a[6] = s[wb_sidx(base + 3 * m8)];
-    a[1] = s[wb_sidx(base + 4 * m8)]; a[5] = s[wb_sidx(base + 5 * m8)];
-    a[3] = s[wb_sidx(base + 6 * m8)]; a[7] = s[wb_sidx(base + 7 * m8)];
+    a[0] = sp[WB_OFF(0, m8)]; a[4] = sp[WB_OFF(1, m8)]; a[2] = sp[WB_OFF(2, m8)]; a[6] = sp[WB_OFF(3, m8)];
+    a[1] = sp[WB_OFF(4, m8)]; a[5] = sp[WB_OFF(5, m8)]; a[3] = sp[WB_OFF(6, m8)]; a[7] = sp[WB_OFF(7, m8)];
     if (m8 > 1) {
-      const cplx w1 = wb_tw<SIGN>(T, j * tstep);
-      const cplx w2 = wb_tw<SIGN>(T, 2 * j * tstep);
-      const cplx w4 = wb_tw<SIGN>(T, 4 * j * tstep);
-      const cplx w3 = wb_cmul(w1, w2), w5 = wb_cmul(w1, w4), w6 = wb_cmul(w2, w4);
-      const cplx w7 = wb_cmul(w3, w4);
-      a[1] = wb_cmul(a[1], w1); a[2] = wb_cmul(a[2], w2); a[3] = wb_cmul(a[3], w3);
-      a[4] = wb_cmul(a[4], w4); a[5] = wb_cmul(a[5], w5); a[6] = wb_cmul(a[6], w6);
-      a[7] = wb_cmul(a[7], w7);
+      cplx w[8];
+      wb_twiddles8<SIGN>(T, j * tstep, w);
+#pragma unroll
+      for (int q = 1; q < 8; ++q) a[q] = wb_cmul(a[q], w[q]);
     }
     wb_dft8<SIGN>(a);
 #pragma unroll
-    for (int p = 0; p < 8; ++p) s[wb_sidx(base + p * m8)] = a[p];
+    for (int p = 0; p < 8; ++p) sp[WB_OFF(p, m8)] = a[p];
   }
 }
-
-template <int SIGN>
-__device__ __forceinline__ void wb_pass_dit4(cplx *s, int N, int M, const cplx *__restrict__ T, int NT) {
-  const int m4 = M >> 2, tstep = NT / M;
-  for (int u = threadIdx.x; u < (N >> 2); u += blockDim.x) {
-    const int j = u & (m4 - 1);
-    const int base = ((u - j) << 2) + j;
+template <int SIGN, int N>
+__device__ __forceinline__ void wb_pass_dit4_first(cplx *s) {
+  for (int u = threadIdx.x; u < N / 4; u += blockDim.x) {
+    cplx *sp = s + wb_sidx(4 * u);
     cplx a[4];
-    a[0] = s[wb_sidx(base)]; a[2] = s[wb_sidx(base + m4)];
-    a[1] = s[wb_sidx(base + 2 * m4)]; a[3] = s[wb_sidx(base + 3 * m4)];
-    if (m4 > 1) {
-      const cplx w1 = wb_tw<SIGN>(T, j * tstep);
-      const cplx w2 = wb_tw<SIGN>(T, 2 * j * tstep);
-      const cplx w3 = wb_cmul(w1, w2);
-      a[1] = wb_cmul(a[1], w1); a[2] = wb_cmul(a[2], w2); a[3] = wb_cmul(a[3], w3);
-    }
+    a[0] = sp[0]; a[2] = sp[1]; a[1] = sp[2]; a[3] = sp[3];
     wb_dft4<SIGN>(a);
 #pragma unroll
-    for (int p = 0; p < 4; ++p) s[wb_sidx(base + p * m4)] = a[p];
+    for (int p = 0; p < 4; ++p) sp[p] = a[p];
+  }
+}
+template <int SIGN, int N>
+__device__ __forceinline__ void wb_pass_dit2_first(cplx *s) {
+  for (int u = threadIdx.x; u < N / 2; u += blockDim.x) {
+    cplx *sp = s + wb_sidx(2 * u);
+    const cplx a0 = sp[0], a1 = sp[1];
+    sp[0] = wb_cadd(a0, a1);
+    sp[1] = wb_csub(a0, a1);
   }
 }
 
-template <int SIGN>
-__device__ __forceinline__ void wb_pass_dit2(cplx *s, int N, int M, const cplx *__restrict__ T, int NT) {
-  const int m2 = M >> 1, tstep = NT / M;
-  for (int u = threadIdx.x; u < (N >> 1); u += blockDim.x) {
-    const int j = u & (m2 - 1);
-    const int base = ((u - j) << 1) + j;
-    cplx a0 = s[wb_sidx(base)], a1 = s[wb_sidx(base + m2)];
-    if (m2 > 1) a1 = wb_cmul(a1, wb_tw<SIGN>(T, j * tstep));
-    s[wb_sidx(base)] = wb_cadd(a0, a1);
-    s[wb_sidx(base + m2)] = wb_csub(a0, a1);
+template <int SIGN, int N, int M>
+struct WbDifPasses {
+  static __device__ __forceinline__ void run(cplx *s, const cplx *__restrict__ T) {
+    if constexpr (M >= 8) {
+      wb_pass_dif8<SIGN, N, M>(s, T);
+      __syncthreads();
+      WbDifPasses<SIGN, N, M / 8>::run(s, T);
+    } else if constexpr (M == 4) {
+      wb_pass_dif4_last<SIGN, N>(s);
+      __syncthreads();
+    } else if constexpr (M == 2) {
+      wb_pass_dif2_last<SIGN, N>(s);
+      __syncthreads();
+    }
   }
-}
+};
 
-// ---- complex transforms -------------------------------------------------------------
+template <int SIGN, int N, int M>  // M = sub-block size produced by the passes done so far
+struct WbDitPasses {
+  static __device__ __forceinline__ void run(cplx *s, const cplx *__restrict__ T) {
+    if constexpr (M < N) {
+      wb_pass_dit8<SIGN, N, M * 8>(s, T);
+      __syncthreads();
+      WbDitPasses<SIGN, N, M * 8>::run(s, T);
+    }
+  }
+};
+
+// ---- complex transforms: N = 2^LOG2N points, table T with 2N entries -------------------------
 // natural order in, bit-reversed order out.  Ends with __syncthreads().
 // Caller must __syncthreads() after filling `s`.
-template <int SIGN>
-__device__ inline void wb_cfft_dif(cplx *s, int N, int log2n, const cplx *__restrict__ T, int NT) {
-  const int n8 = log2n / 3, rem = log2n - 3 * n8;
-  int M = N;
-  for (int p = 0; p < n8; ++p) {
-    wb_pass_dif8<SIGN>(s, N, M, T, NT);
-    __syncthreads();
-    M >>= 3;
-  }
-  if (rem == 2) { wb_pass_dif4<SIGN>(s, N, 4, T, NT); __syncthreads(); }
-  else if (rem == 1) { wb_pass_dif2<SIGN>(s, N, 2, T, NT); __syncthreads(); }
+template <int SIGN, int LOG2N>
+__device__ __forceinline__ void wb_cfft_dif_t(cplx *s, const cplx *__restrict__ T) {
+  WbDifPasses<SIGN, (1 << LOG2N), (1 << LOG2N)>::run(s, T);
 }
 
 // bit-reversed order in, natural order out.  Ends with __syncthreads().
-template <int SIGN>
-__device__ inline void wb_cfft_dit(cplx *s, int N, int log2n, const cplx *__restrict__ T, int NT) {
-  const int n8 = log2n / 3, rem = log2n - 3 * n8;
-  int M = 1 << rem;
-  if (rem == 2) { wb_pass_dit4<SIGN>(s, N, 4, T, NT); __syncthreads(); }
-  else if (rem == 1) { wb_pass_dit2<SIGN>(s, N, 2, T, NT); __syncthreads(); }
-  for (int p = 0; p < n8; ++p) {
-    M <<= 3;
-    wb_pass_dit8<SIGN>(s, N, M, T, NT);
-    __syncthreads();
-  }
+template <int SIGN, int LOG2N>
+__device__ __forceinline__ void wb_cfft_dit_t(cplx *s, const cplx *__restrict__ T) {
+  constexpr int N = 1 << LOG2N, rem = LOG2N % 3;
+  if constexpr (rem == 2) { wb_pass_dit4_first<SIGN, N>(s); __syncthreads(); }
+  if constexpr (rem == 1) { wb_pass_dit2_first<SIGN, N>(s); __syncthreads(); }
+  WbDitPasses<SIGN, N, (1 << rem)>::run(s, T);
 }
 
 __device__ __forceinline__ int wb_brev(int k, int bits) { return (int)(__brev((unsigned)k) >> (32 - bits)); }
 
 // ---- real transforms ------------------------------------------------------------------
-// r2c of a real sequence of length N = 2 NC that was packed as z[n] = x[2n] + i x[2n+1]
-// into slots wb_sidx(n) (i.e. real sample j at double index wb_didx(j)).
-// After the complex DIF transform, `emit(k, X)` is called exactly once for every
-// k = 0..NC (X[k] of the length-N real transform, forward sign).  T has NT = N entries.
+// r2c of a real sequence of length 2 NC (NC = 2^LOG2NC) that was packed as
+// z[n] = x[2n] + i x[2n+1] into slots wb_sidx(n) (real sample j at double index wb_didx(j)).
+// After the complex DIF transform, `emit(k, X)` is called exactly once for every k = 0..NC
+// (X[k] of the real transform, forward sign).  T has 2 NC entries.
 // The slots are left untouched by the post-processing (emit must not write to s).
-template <int SIGN, typename Emit>
-__device__ inline void wb_rfft(cplx *s, int NC, int log2nc, const cplx *__restrict__ T, Emit emit) {
-  const int N = 2 * NC;
-  wb_cfft_dif<SIGN>(s, NC, log2nc, T, N);
+template <int SIGN, int LOG2NC, typename Emit>
+__device__ __forceinline__ void wb_rfft_t(cplx *s, const cplx *__restrict__ T, Emit emit) {
+  constexpr int NC = 1 << LOG2NC;
+  wb_cfft_dif_t<SIGN, LOG2NC>(s, T);
   for (int k = threadIdx.x; k <= (NC >> 1); k += blockDim.x) {
     if (k == 0) {
       const cplx z = s[0];
       emit(0, make_double2(z.x + z.y, 0.0));
       emit(NC, make_double2(z.x - z.y, 0.0));
     } else {
-      const cplx zk = s[wb_sidx(wb_brev(k, log2nc))];
-      const cplx zc = s[wb_sidx(wb_brev(NC - k, log2nc))];
+      const cplx zk = s[wb_sidx(wb_brev(k, LOG2NC))];
+      const cplx zc = s[wb_sidx(wb_brev(NC - k, LOG2NC))];
       // E = (Z[k] + conj Z[NC-k]) / 2 ; O = (Z[k] - conj Z[NC-k]) / (2i)
       const cplx E = make_double2(0.5 * (zk.x + zc.x), 0.5 * (zk.y - zc.y));
       const cplx O = make_double2(0.5 * (zk.y + zc.y), -0.5 * (zk.x - zc.x));
@@ -269,9 +266,9 @@ __device__ inline void wb_rfft(cplx *s, int NC, int log2nc, const cplx *__restri
 // c2r (SIGN = -1 for the reference's backward transform): `get(k)` returns X[k] for
 // k = 0..NC (Hermitian half; imaginary parts of X[0], X[NC] are ignored like Ooura's
 // rdft).  On return real output sample j is at double index wb_didx(j) of `s`.
-template <int SIGN, typename Get>
-__device__ inline void wb_irfft(cplx *s, int NC, int log2nc, const cplx *__restrict__ T, Get get) {
-  const int N = 2 * NC;
+template <int SIGN, int LOG2NC, typename Get>
+__device__ __forceinline__ void wb_irfft_t(cplx *s, const cplx *__restrict__ T, Get get) {
+  constexpr int NC = 1 << LOG2NC;
   for (int k = threadIdx.x; k <= (NC >> 1); k += blockDim.x) {
     if (k == 0) {
       const double x0 = get(0).x, xn = get(NC).x;
@@ -281,10 +278,28 @@ __device__ inline void wb_irfft(cplx *s, int NC, int log2nc, const cplx *__restr
       const cplx A = make_double2(xk.x + xc.x, xk.y - xc.y);               // X[k] + conj X[NC-k]
       const cplx B = wb_cmul(make_double2(xk.x - xc.x, xk.y + xc.y), wb_tw<SIGN>(T, k));
       // Z[k] = A + iB ; Z[NC-k] = conj(A) + i conj(B)
-      s[wb_sidx(wb_brev(k, log2nc))] = make_double2(A.x - B.y, A.y + B.x);
-      if (k != NC - k) s[wb_sidx(wb_brev(NC - k, log2nc))] = make_double2(A.x + B.y, B.x - A.y);
+      s[wb_sidx(wb_brev(k, LOG2NC))] = make_double2(A.x - B.y, A.y + B.x);
+      if (k != NC - k) s[wb_sidx(wb_brev(NC - k, LOG2NC))] = make_double2(A.x + B.y, B.x - A.y);
     }
   }
   __syncthreads();
-  wb_cfft_dit<SIGN>(s, NC, log2nc, T, N);
+  wb_cfft_dit_t<SIGN, LOG2NC>(s, T);
 }
+
+// ---- host-side dispatch helper: call F.template operator()<LOG2N>() for a runtime log2n ------
+#define WB_DISPATCH_LOG2(LOG2, LO, HI, ...)                              \
+  [&]() -> int {                                                        \
+    switch (LOG2) {                                                     \
+      case 6: if (6 >= LO && 6 <= HI) { constexpr int L2 = (6 >= LO && 6 <= HI) ? 6 : LO; __VA_ARGS__; return WB_OK; } break;   \
+      case 7: if (7 >= LO && 7 <= HI) { constexpr int L2 = (7 >= LO && 7 <= HI) ? 7 : LO; __VA_ARGS__; return WB_OK; } break;   \
+      case 8: if (8 >= LO && 8 <= HI) { constexpr int L2 = (8 >= LO && 8 <= HI) ? 8 : LO; __VA_ARGS__; return WB_OK; } break;   \
+      case 9: if (9 >= LO && 9 <= HI) { constexpr int L2 = (9 >= LO && 9 <= HI) ? 9 : LO; __VA_ARGS__; return WB_OK; } break;   \
+      case 10: if (10 >= LO && 10 <= HI) { constexpr int L2 = (10 >= LO && 10 <= HI) ? 10 : LO; __VA_ARGS__; return WB_OK; } break; \
+      case 11: if (11 >= LO && 11 <= HI) { constexpr int L2 = (11 >= LO && 11 <= HI) ? 11 : LO; __VA_ARGS__; return WB_OK; } break; \
+      case 12: if (12 >= LO && 12 <= HI) { constexpr int L2 = (12 >= LO && 12 <= HI) ? 12 : LO; __VA_ARGS__; return WB_OK; } break; \
+      case 13: if (13 >= LO && 13 <= HI) { constexpr int L2 = (13 >= LO && 13 <= HI) ? 13 : LO; __VA_ARGS__; return WB_OK; } break; \
+      case 14: if (14 >= LO && 14 <= HI) { constexpr int L2 = (14 >= LO && 14 <= HI) ? 14 : LO; __VA_ARGS__; return WB_OK; } break; \
+      default: break;                                                   \
+    }                                                                   \
+    return WB_ERR_UNSUPPORTED;                                          \
+  }()

@@ -7,41 +7,41 @@
 
 namespace {
 
-__global__ void r2c_kernel(const double *__restrict__ in, int n, int log2nc, const cplx *__restrict__ T,
-                           cplx *__restrict__ out) {
+template <int LOG2N>
+__global__ void r2c_kernel(const double *__restrict__ in, const cplx *__restrict__ T, cplx *__restrict__ out) {
   extern __shared__ double2 smem_raw[];
   cplx *S = smem_raw;
   double *W = reinterpret_cast<double *>(S);
-  const int NC = n / 2;
+  constexpr int n = 1 << LOG2N, NC = n / 2;
   const double *src = in + (size_t)blockIdx.x * n;
   cplx *dst = out + (size_t)blockIdx.x * (NC + 1);
   for (int j = threadIdx.x; j < n; j += blockDim.x) W[wb_didx(j)] = src[j];
   __syncthreads();
-  wb_rfft<1>(S, NC, log2nc, T, [&](int k, cplx X) { dst[k] = X; });
+  wb_rfft_t<1, LOG2N - 1>(S, T, [&](int k, cplx X) { dst[k] = X; });
 }
 
-__global__ void c2r_kernel(const cplx *__restrict__ in, int n, int log2nc, const cplx *__restrict__ T,
-                           double *__restrict__ out) {
+template <int LOG2N>
+__global__ void c2r_kernel(const cplx *__restrict__ in, const cplx *__restrict__ T, double *__restrict__ out) {
   extern __shared__ double2 smem_raw[];
   cplx *S = smem_raw;
   double *W = reinterpret_cast<double *>(S);
-  const int NC = n / 2;
+  constexpr int n = 1 << LOG2N, NC = n / 2;
   const cplx *src = in + (size_t)blockIdx.x * (NC + 1);
   double *dst = out + (size_t)blockIdx.x * n;
-  wb_irfft<-1>(S, NC, log2nc, T, [&](int k) { return src[k]; });
+  wb_irfft_t<-1, LOG2N - 1>(S, T, [&](int k) { return src[k]; });
   for (int j = threadIdx.x; j < n; j += blockDim.x) dst[j] = W[wb_didx(j)];
 }
 
-template <int SIGN>
-__global__ void c2c_kernel(const cplx *__restrict__ in, int n, int log2n, const cplx *__restrict__ T,
-                           cplx *__restrict__ out) {
+template <int SIGN, int LOG2N>
+__global__ void c2c_kernel(const cplx *__restrict__ in, const cplx *__restrict__ T, cplx *__restrict__ out) {
   extern __shared__ double2 smem_raw[];
   cplx *S = smem_raw;
+  constexpr int n = 1 << LOG2N, log2n = LOG2N;
   const cplx *src = in + (size_t)blockIdx.x * n;
   cplx *dst = out + (size_t)blockIdx.x * n;
   for (int j = threadIdx.x; j < n; j += blockDim.x) S[wb_sidx(j)] = src[j];
   __syncthreads();
-  wb_cfft_dif<SIGN>(S, n, log2n, T, 2 * n);
+  wb_cfft_dif_t<SIGN, LOG2N>(S, T);
   for (int k = threadIdx.x; k < n; k += blockDim.x) dst[k] = S[wb_sidx(wb_brev(k, log2n))];
 }
 
@@ -58,32 +58,43 @@ int ilog2(int n) {
 //       2 = c2c forward, 3 = c2c backward (in/out: batch*n complex)
 int wb_fft_batch_dev(int kind, const void *d_in, int n, int batch, void *d_out, cudaStream_t stream) {
   const int l = ilog2(n);
-  if (l < 4 || n > 16384 || batch < 0) return WB_ERR_UNSUPPORTED;
+  if (l < 7 || n > 16384 || batch < 0) return WB_ERR_UNSUPPORTED;
   if (batch == 0) return WB_OK;
   const int threads = 256;
+  int rc;
   if (kind == 0 || kind == 1) {
     const cplx *T = wb_twiddle_table(n);
     if (!T) return WB_ERR_CUDA;
     const size_t smem = sizeof(cplx) * wb_fft_slots(n / 2);
     if (kind == 0) {
-      WB_CUDA_CHECK(cudaFuncSetAttribute(r2c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      WB_LAUNCH("r2c_kernel", r2c_kernel<<<batch, threads, smem, stream>>>((const double *)d_in, n, l - 1, T, (cplx *)d_out));
+      rc = WB_DISPATCH_LOG2(l, 7, 14, {
+        if (cudaFuncSetAttribute(r2c_kernel<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WB_ERR_CUDA;
+        WB_LAUNCH("r2c_kernel", r2c_kernel<L2><<<batch, threads, smem, stream>>>((const double *)d_in, T, (cplx *)d_out));
+      });
     } else {
-      WB_CUDA_CHECK(cudaFuncSetAttribute(c2r_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      WB_LAUNCH("c2r_kernel", c2r_kernel<<<batch, threads, smem, stream>>>((const cplx *)d_in, n, l - 1, T, (double *)d_out));
+      rc = WB_DISPATCH_LOG2(l, 7, 14, {
+        if (cudaFuncSetAttribute(c2r_kernel<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WB_ERR_CUDA;
+        WB_LAUNCH("c2r_kernel", c2r_kernel<L2><<<batch, threads, smem, stream>>>((const cplx *)d_in, T, (double *)d_out));
+      });
     }
   } else {
+    if (n > 8192) return WB_ERR_UNSUPPORTED;
     const cplx *T = wb_twiddle_table(2 * n);
     if (!T) return WB_ERR_CUDA;
     const size_t smem = sizeof(cplx) * wb_fft_slots(n);
     if (kind == 2) {
-      WB_CUDA_CHECK(cudaFuncSetAttribute(c2c_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      WB_LAUNCH("c2c_kernel", c2c_kernel<1><<<batch, threads, smem, stream>>>((const cplx *)d_in, n, l, T, (cplx *)d_out));
+      rc = WB_DISPATCH_LOG2(l, 7, 13, {
+        if (cudaFuncSetAttribute(c2c_kernel<1, L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WB_ERR_CUDA;
+        WB_LAUNCH("c2c_kernel", c2c_kernel<1, L2><<<batch, threads, smem, stream>>>((const cplx *)d_in, T, (cplx *)d_out));
+      });
     } else {
-      WB_CUDA_CHECK(cudaFuncSetAttribute(c2c_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      WB_LAUNCH("c2c_kernel", c2c_kernel<-1><<<batch, threads, smem, stream>>>((const cplx *)d_in, n, l, T, (cplx *)d_out));
+      rc = WB_DISPATCH_LOG2(l, 7, 13, {
+        if (cudaFuncSetAttribute(c2c_kernel<-1, L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WB_ERR_CUDA;
+        WB_LAUNCH("c2c_kernel", c2c_kernel<-1, L2><<<batch, threads, smem, stream>>>((const cplx *)d_in, T, (cplx *)d_out));
+      });
     }
   }
+  if (rc) return rc;
   WB_CUDA_CHECK(cudaGetLastError());
   return WB_OK;
 }

@@ -154,13 +154,13 @@ __global__ void dc_subtract_kernel(double *__restrict__ y, int n, const double *
 // ---------------------------------------------------------------------------------------------
 // H3/H4: overlap-save block spectra and per-channel filter spectra
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512) yspec_kernel(const double *__restrict__ y, int y_length, int NB, int log2nc,
-                                                    int V, int h_max, const cplx *__restrict__ tw,
-                                                    cplx *__restrict__ Yb) {
+template <int LOG2NB>
+__global__ void __launch_bounds__(512) yspec_kernel(const double *__restrict__ y, int y_length, int V, int h_max,
+                                                    const cplx *__restrict__ tw, cplx *__restrict__ Yb) {
   extern __shared__ double2 smem_raw[];
   cplx *S = smem_raw;
   double *W = reinterpret_cast<double *>(S);
-  const int NC = NB / 2;
+  constexpr int NB = 1 << LOG2NB, NC = NB / 2;
   const int b = blockIdx.x;
   const long long s_b = (long long)b * V + 1 - h_max;
   for (int i = threadIdx.x; i < NB; i += blockDim.x) {
@@ -169,17 +169,18 @@ __global__ void __launch_bounds__(512) yspec_kernel(const double *__restrict__ y
   }
   __syncthreads();
   cplx *dst = Yb + (size_t)b * (NC + 1);
-  wb_rfft<1>(S, NC, log2nc, tw, [&](int k, cplx X) { dst[k] = X; });
+  wb_rfft_t<1, LOG2NB - 1>(S, tw, [&](int k, cplx X) { dst[k] = X; });
 }
 
 // getFilteredSignal (harvest.cpp:1264-1274): Nuttall(2h+1) x cos(2 pi bf i / fs), then r2c
+template <int LOG2NB>
 __global__ void __launch_bounds__(512) filter_spec_kernel(const double *__restrict__ boundary_f0, const int *__restrict__ half_len,
-                                                          double actual_fs, int NB, int log2nc,
-                                                          const cplx *__restrict__ tw, cplx *__restrict__ Hc) {
+                                                          double actual_fs, const cplx *__restrict__ tw,
+                                                          cplx *__restrict__ Hc) {
   extern __shared__ double2 smem_raw[];
   cplx *S = smem_raw;
   double *W = reinterpret_cast<double *>(S);
-  const int NC = NB / 2;
+  constexpr int NB = 1 << LOG2NB, NC = NB / 2;
   const int c = blockIdx.x;
   const double bf = boundary_f0[c];
   const int h = half_len[c];
@@ -196,7 +197,7 @@ __global__ void __launch_bounds__(512) filter_spec_kernel(const double *__restri
   }
   __syncthreads();
   cplx *dst = Hc + (size_t)c * (NC + 1);
-  wb_rfft<1>(S, NC, log2nc, tw, [&](int k, cplx X) { dst[k] = X; });
+  wb_rfft_t<1, LOG2NB - 1>(S, tw, [&](int k, cplx X) { dst[k] = X; });
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -232,18 +233,19 @@ __device__ __forceinline__ unsigned ch_flags(double a, double b, double c, int n
 // One CTA per (overlap-save block, channel): band-pass by the convolution theorem
 // (harvest.cpp:1277-1299) and order-preserving extraction of the fine zero-crossing edges of the
 // block's V output samples straight from shared memory.
+template <int LOG2NB>
 __global__ void __launch_bounds__(CH_THREADS) channel_kernel(ChanParams p) {
   extern __shared__ double2 smem_raw[];
   __shared__ int s_wsum[4][CH_THREADS / 32];
   cplx *S = smem_raw;
   double *W = reinterpret_cast<double *>(S);
-  const int NC = p.NB / 2;
+  constexpr int NC = (1 << LOG2NB) / 2;
   const int b = blockIdx.x, c = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int h = p.half_len[c];
   const cplx *H = p.Hc + (size_t)c * (NC + 1);
   const cplx *Y = p.Yb + (size_t)b * (NC + 1);
-  wb_irfft<-1>(S, NC, p.log2nc, p.tw, [&](int k) {
+  wb_irfft_t<-1, LOG2NB - 1>(S, p.tw, [&](int k) {
     const cplx yv = Y[k], hv = H[k];
     return make_double2(yv.x * hv.x - yv.y * hv.y, yv.x * hv.y + yv.y * hv.x);
   });
@@ -441,46 +443,41 @@ struct RefineParams {
 };
 
 #define RF_WARPS 8
+#define RF_GROUP 8   // lanes per candidate (4 candidates per warp)
+
+// Blackman main window at angle cosine c (harvest.cpp:770-774), cos(2t) = 2 cos(t)^2 - 1
+__device__ __forceinline__ double rf_window(double c) { return 0.42 + 0.5 * c + 0.08 * (2.0 * c * c - 1.0); }
+
+// Eight lanes per candidate.  The window angle advances by exactly 2 pi / len per sample, so a
+// lane evaluates one sincos at its first sample (with the reference's expression) and rotates
+// by RF_GROUP samples per step (<= 76 rotations, ~1e-15 drift); the neighbours needed by the
+// differentiated window (harvest.cpp:794-803) come from one more rotation by +-1 sample.
+// Nothing is staged in shared memory.
 __global__ void __launch_bounds__(RF_WARPS * 32) refine_kernel(RefineParams p) {
-  extern __shared__ double rf_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double *mw = rf_smem + (size_t)warp * (p.max_wlen + 2);  // main window, index shifted by +1 (mw[0] = mw[len+1] = pad)
+  const int sub = lane & (RF_GROUP - 1), grp = lane / RF_GROUP;
   const int n_work = *p.work_count;
-  const int total_warps = gridDim.x * RF_WARPS;
+  const int groups_per_warp = 32 / RF_GROUP;
+  const int total_groups = gridDim.x * RF_WARPS * groups_per_warp;
   const double fs = p.actual_fs;
-  for (int wi = blockIdx.x * RF_WARPS + warp; wi < n_work; wi += total_warps) {
-    const int item = p.work[wi];
+  const double two_pi = 2.0 * WB_PI;
+  // all lanes of a warp iterate together (the shuffles below use the full mask)
+  const int first = (blockIdx.x * RF_WARPS + warp) * groups_per_warp;
+  for (int base = first; base < n_work; base += total_groups) {
+    const int wi = base + grp;
+    const bool active = wi < n_work;
+    const int item = active ? p.work[wi] : 0;
     const int frame = item >> 7, slot = item & 127;
     const size_t at = (size_t)frame * p.max_candidates + slot;
-    const double current_f0 = p.cand[at];
+    const double current_f0 = active ? p.cand[at] : 100.0;
     const double current_position = frame * p.frame_period / 1000.0;
     const int hw = static_cast<int>(1.5 * fs / current_f0 + 1.0);
-    const int len = 2 * hw + 1;
+    const int len = active ? 2 * hw + 1 : 0;
     const double window_length_in_time = (2.0 * hw + 1.0) / fs;
-    const int log2fft = 2 + (31 - __clz(len));  // 2 + int(log2(len)), len odd
+    const int log2fft = 2 + (31 - __clz(2 * hw + 1));  // 2 + int(log2(len)), len odd
     const int fft_size = 1 << log2fft;
     const double base_time0 = (-hw + 0) / fs;
     const int basic_index = wb_round((current_position + base_time0) * fs + 0.001);
-    // main window (harvest.cpp:762-774): 0.42 + 0.5 cos(t) + 0.08 cos(2t), t = 2 pi tmp / T.
-    // The angle advances by exactly 2 pi / len per sample, so each lane evaluates one sincos at
-    // its first sample (with the reference's expression) and then rotates by 32 samples per step;
-    // cos(2t) = 2 cos(t)^2 - 1.  <= 19 rotations -> a few 1e-16 of drift.
-    const double two_pi = 2.0 * WB_PI;
-    {
-      double sd, cd;
-      sincos(two_pi * 32.0 / len, &sd, &cd);
-      const double tmp = ((basic_index + lane) - 1.0) / fs - current_position;
-      const double tmp2 = two_pi * tmp / window_length_in_time;
-      double sn, cs;
-      sincos(tmp2, &sn, &cs);
-      for (int i = lane; i < len; i += 32) {
-        mw[i + 1] = 0.42 + 0.5 * cs + 0.08 * (2.0 * cs * cs - 1.0);
-        const double c2 = cs * cd - sn * sd;
-        sn = sn * cd + cs * sd;
-        cs = c2;
-      }
-    }
-    __syncwarp();
     const int nh = wb_min_i(static_cast<int>(fs / 2.0 / current_f0), 6);
     int idx[6];
 #pragma unroll
@@ -490,15 +487,26 @@ __global__ void __launch_bounds__(RF_WARPS * 32) refine_kernel(RefineParams p) {
     for (int hh = 0; hh < 6; ++hh) { mr[hh] = mi[hh] = dr[hh] = di[hh] = 0.0; }
     const cplx *T = p.tw[log2fft];
     const int mask = fft_size - 1;
-    for (int i = lane; i < len; i += 32) {
+    // rotation constants
+    double s1, c1, sg, cg;
+    sincos(two_pi / (2 * hw + 1), &s1, &c1);
+    sincos(two_pi * RF_GROUP / (2 * hw + 1), &sg, &cg);
+    double sn, cs;
+    {
+      const double tmp = ((basic_index + sub) - 1.0) / fs - current_position;
+      sincos(two_pi * tmp / window_length_in_time, &sn, &cs);
+    }
+    for (int i = sub; i < len; i += RF_GROUP) {
       const int safe = wb_max_i(0, wb_min_i(p.y_length - 1, basic_index + i - 1));
       const double yv = p.y[safe];
-      // diff window (harvest.cpp:794-803)
+      const double w_here = rf_window(cs);
+      const double w_next = rf_window(cs * c1 - sn * s1);  // angle + delta
+      const double w_prev = rf_window(cs * c1 + sn * s1);  // angle - delta
       double dwin;
-      if (i == 0) dwin = -mw[2] / 2.0;
-      else if (i == len - 1) dwin = mw[len - 1] / 2.0;
-      else dwin = -(mw[i + 2] - mw[i]) / 2.0;
-      const double vm = mw[i + 1] * yv, vd = dwin * yv;
+      if (i == 0) dwin = -w_next / 2.0;
+      else if (i == len - 1) dwin = w_prev / 2.0;
+      else dwin = -(w_next - w_prev) / 2.0;
+      const double vm = w_here * yv, vd = dwin * yv;
 #pragma unroll
       for (int hh = 0; hh < 6; ++hh) {
         if (hh < nh) {
@@ -507,19 +515,28 @@ __global__ void __launch_bounds__(RF_WARPS * 32) refine_kernel(RefineParams p) {
           dr[hh] = fma(vd, w.x, dr[hh]); di[hh] = fma(vd, w.y, di[hh]);
         }
       }
+      const double c2 = cs * cg - sn * sg;
+      sn = sn * cg + cs * sg;
+      cs = c2;
     }
+    // reduce over the 8 lanes of the group
 #pragma unroll
     for (int hh = 0; hh < 6; ++hh) {
-      mr[hh] = wb_warp_sum(mr[hh]); mi[hh] = wb_warp_sum(mi[hh]);
-      dr[hh] = wb_warp_sum(dr[hh]); di[hh] = wb_warp_sum(di[hh]);
+#pragma unroll
+      for (int o = RF_GROUP / 2; o > 0; o >>= 1) {
+        mr[hh] += __shfl_xor_sync(0xffffffffu, mr[hh], o);
+        mi[hh] += __shfl_xor_sync(0xffffffffu, mi[hh], o);
+        dr[hh] += __shfl_xor_sync(0xffffffffu, dr[hh], o);
+        di[hh] += __shfl_xor_sync(0xffffffffu, di[hh], o);
+      }
     }
-    // fixF0 (harvest.cpp:844-878): lane hh evaluates harmonic hh (divisions, sqrt in parallel),
-    // lane 0 accumulates in the reference's order.
+    // fixF0 (harvest.cpp:844-878): sub-lane hh evaluates harmonic hh (divisions, sqrt in parallel),
+    // then every lane accumulates in the reference's order.
     // spectra are conjugated by the reference (harvest.cpp:829-841): main = (mr, -mi), diff = (dr, -di)
     double my_inst = 0.0, my_amp = 0.0;
 #pragma unroll
     for (int hh = 0; hh < 6; ++hh) {
-      if (lane == hh && hh < nh) {
+      if (sub == hh && hh < nh) {
         const double m_re = mr[hh], m_im = -mi[hh], d_re = dr[hh], d_im = -di[hh];
         const double power = m_re * m_re + m_im * m_im;
         const double num_i = m_re * d_im - m_im * d_re;
@@ -529,21 +546,23 @@ __global__ void __launch_bounds__(RF_WARPS * 32) refine_kernel(RefineParams p) {
       }
     }
     double numerator = 0.0, denominator = 0.0, score = 0.0;
-    for (int hh = 0; hh < nh; ++hh) {
-      const double inst = __shfl_sync(0xffffffffu, my_inst, hh);
-      const double amp = __shfl_sync(0xffffffffu, my_amp, hh);
-      numerator += amp * inst;
-      denominator += amp * (hh + 1.0);
-      score += fabs((inst / (hh + 1.0) - current_f0) / current_f0);
+#pragma unroll
+    for (int hh = 0; hh < 6; ++hh) {
+      const double inst = __shfl_sync(0xffffffffu, my_inst, hh, RF_GROUP);
+      const double amp = __shfl_sync(0xffffffffu, my_amp, hh, RF_GROUP);
+      if (hh < nh) {
+        numerator += amp * inst;
+        denominator += amp * (hh + 1.0);
+        score += fabs((inst / (hh + 1.0) - current_f0) / current_f0);
+      }
     }
-    if (lane == 0) {
+    if (sub == 0 && active) {
       double refined = numerator / (denominator + WB_SAFEGUARD);
       double sc = 1.0 / (score / nh + WB_SAFEGUARD);
       if (refined < p.f0_floor || refined > p.f0_ceil || sc < 2.5) { refined = 0.0; sc = 0.0; }
       p.cand[at] = refined;
       p.score[at] = sc;
     }
-    __syncwarp();
   }
 }
 
@@ -639,8 +658,11 @@ static int harvest_prepare_filters(WbHarvestPlan *pl, WbWorkspace *ws, cudaStrea
   const cplx *tw = wb_twiddle_table(pl->NB);
   if (!tw) return WB_ERR_CUDA;
   const size_t smem = sizeof(cplx) * wb_fft_slots(NC);
-  WB_CUDA_CHECK(cudaFuncSetAttribute(filter_spec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  WB_LAUNCH("filter_spec_kernel", filter_spec_kernel<<<pl->nch, 512, smem, stream>>>(d_bf, d_hl, pl->actual_fs, pl->NB, ilog2_exact(NC), tw, d_Hc));
+  int rc = WB_DISPATCH_LOG2(ilog2_exact(pl->NB), 13, 14, {
+    if (cudaFuncSetAttribute(filter_spec_kernel<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WB_ERR_CUDA;
+    WB_LAUNCH("filter_spec_kernel", filter_spec_kernel<L2><<<pl->nch, 512, smem, stream>>>(d_bf, d_hl, pl->actual_fs, tw, d_Hc));
+  });
+  if (rc) return rc;
   WB_CUDA_CHECK(cudaGetLastError());
   WB_CUDA_CHECK(cudaStreamSynchronize(stream));  // host vectors are pageable; make the plan self-contained
   pl->filters_ready = true;
@@ -695,8 +717,11 @@ int wb_harvest_run_basic(WbHarvestPlan *pl, WbWorkspace *ws, const double *d_x, 
   if (!d_Yb) return WB_ERR_CUDA;
   const cplx *tw = wb_twiddle_table(NB);
   const size_t smem_fft = sizeof(cplx) * wb_fft_slots(NC);
-  WB_CUDA_CHECK(cudaFuncSetAttribute(yspec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
-  WB_LAUNCH("yspec_kernel", yspec_kernel<<<n_blocks, 512, smem_fft, stream>>>(d_y, y_length, NB, log2nc, pl->V, pl->h_max, tw, d_Yb));
+  rc = WB_DISPATCH_LOG2(log2nc + 1, 13, 14, {
+    if (cudaFuncSetAttribute(yspec_kernel<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft) != cudaSuccess) return WB_ERR_CUDA;
+    WB_LAUNCH("yspec_kernel", yspec_kernel<L2><<<n_blocks, 512, smem_fft, stream>>>(d_y, y_length, pl->V, pl->h_max, tw, d_Yb));
+  });
+  if (rc) return rc;
   WB_CUDA_CHECK(cudaGetLastError());
 
   // ---- H5: channels
@@ -713,9 +738,12 @@ int wb_harvest_run_basic(WbHarvestPlan *pl, WbWorkspace *ws, const double *d_x, 
     p.Yb = d_Yb; p.Hc = (const cplx *)ws->get("hv_Hc", 0); p.half_len = (const int *)ws->get("hv_hl", 0);
     p.n_blocks = n_blocks; p.NB = NB; p.log2nc = log2nc; p.V = pl->V; p.h_max = pl->h_max; p.y_length = y_length;
     p.tw = tw; p.seg_edges = d_seg; p.seg_count = d_segc; p.bcap = bcap;
-    WB_CUDA_CHECK(cudaFuncSetAttribute(channel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
     dim3 grid(n_blocks, nch);
-    WB_LAUNCH("channel_kernel", channel_kernel<<<grid, CH_THREADS, smem_fft, stream>>>(p));
+    rc = WB_DISPATCH_LOG2(log2nc + 1, 13, 14, {
+      if (cudaFuncSetAttribute(channel_kernel<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft) != cudaSuccess) return WB_ERR_CUDA;
+      WB_LAUNCH("channel_kernel", channel_kernel<L2><<<grid, CH_THREADS, smem_fft, stream>>>(p));
+    });
+    if (rc) return rc;
     WB_CUDA_CHECK(cudaGetLastError());
     WB_LAUNCH("edge_compact_kernel", edge_compact_kernel<<<nch * 4, 256, 0, stream>>>(d_seg, d_segc, n_blocks, bcap, d_edges, d_ecount, ecap));
     WB_CUDA_CHECK(cudaGetLastError());
@@ -764,9 +792,7 @@ int wb_harvest_run_basic(WbHarvestPlan *pl, WbWorkspace *ws, const double *d_x, 
       p.tw[l] = wb_twiddle_table(1 << l);
       if (!p.tw[l]) return WB_ERR_CUDA;
     }
-    const size_t smem = sizeof(double) * RF_WARPS * (p.max_wlen + 2);
-    WB_CUDA_CHECK(cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    WB_LAUNCH("refine_kernel", refine_kernel<<<148 * 4, RF_WARPS * 32, smem, stream>>>(p));
+    WB_LAUNCH("refine_kernel", refine_kernel<<<148 * 8, RF_WARPS * 32, 0, stream>>>(p));
     WB_CUDA_CHECK(cudaGetLastError());
   }
   WB_LAUNCH("remove_kernel", remove_kernel<<<(unsigned)((n_cs + 255) / 256), 256, 0, stream>>>(d_candA, d_scoreA, d_nc, Lb, MC, d_candB, d_scoreB));

@@ -299,19 +299,20 @@ struct RespParams {
 // MinimumPhaseAnalysis::compute (world_common.cpp:192-233).  On entry the packed real view W of
 // S holds log_spectrum[0..NC] (this function mirrors it); on exit MP[k], k = 0..NC, holds the
 // minimum phase spectrum.  S needs wb_fft_slots(N) slots.
-__device__ inline void minimum_phase(cplx *S, cplx *MP, int N, int log2n, const cplx *tw_n, const cplx *tw_2n) {
-  const int NC = N / 2;
+template <int LOG2N>
+__device__ __forceinline__ void minimum_phase(cplx *S, cplx *MP, const cplx *tw_n, const cplx *tw_2n) {
+  constexpr int N = 1 << LOG2N, NC = N / 2, log2n = LOG2N;
   double *W = reinterpret_cast<double *>(S);
   for (int i = NC + 1 + threadIdx.x; i < N; i += blockDim.x) W[wb_didx(i)] = W[wb_didx(N - i)];
   __syncthreads();
   // "inverse_fft" is a forward r2c in the reference; sign flips / doubling at :203-209
-  wb_rfft<1>(S, NC, log2n - 1, tw_n, [&](int k, cplx X) {
+  wb_rfft_t<1, LOG2N - 1>(S, tw_n, [&](int k, cplx X) {
     if (k == 0 || k == NC) MP[k] = make_double2(X.x, X.y * -1.0);
     else MP[k] = make_double2(X.x * 2.0, X.y * -2.0);
   });
   for (int i = threadIdx.x; i < N; i += blockDim.x) S[wb_sidx(i)] = (i <= NC) ? MP[i] : make_double2(0.0, 0.0);
   __syncthreads();
-  wb_cfft_dif<1>(S, N, log2n, tw_2n, 2 * N);  // c2c FFT_FORWARD
+  wb_cfft_dif_t<1, LOG2N>(S, tw_2n);  // c2c FFT_FORWARD
   for (int k = threadIdx.x; k <= NC; k += blockDim.x) {
     const cplx v = S[wb_sidx(wb_brev(k, log2n))];
     const double tmp = exp(v.x / N);
@@ -322,9 +323,10 @@ __device__ inline void minimum_phase(cplx *S, cplx *MP, int N, int log2n, const 
   __syncthreads();
 }
 
+template <int LOG2N>
 __global__ void __launch_bounds__(256) response_kernel(RespParams p) {
   extern __shared__ double2 smem_raw[];
-  const int N = p.fft_size, NC = N / 2, bins = NC + 1;
+  constexpr int N = 1 << LOG2N, NC = N / 2, bins = NC + 1;
   const int binsp = (bins + 1) & ~1;
   cplx *S = smem_raw;                         // wb_fft_slots(N)
   cplx *MP = S + wb_fft_slots(N);             // bins
@@ -336,7 +338,6 @@ __global__ void __launch_bounds__(256) response_kernel(RespParams p) {
   double *W = reinterpret_cast<double *>(S);
   const int tid = threadIdx.x, nt = blockDim.x;
   const int P = *p.n_pulses;
-  const int log2n = p.log2n;
   if (P > p.max_resp_pulses) {  // f0 exceeded the caller's bound: refuse rather than overrun
     if (tid == 0 && blockIdx.x == 0) atomicExch(p.error_flag, WB_ERR_ARG);
     return;
@@ -384,9 +385,9 @@ __global__ void __launch_bounds__(256) response_kernel(RespParams p) {
     if (periodic_on) {
       for (int k = tid; k < bins; k += nt) W[wb_didx(k)] = log(SE[k] * (1.0 - AR[k]) + WB_SAFEGUARD) / 2.0;
       __syncthreads();
-      minimum_phase(S, MP, N, log2n, p.tw_n, p.tw_2n);
+      minimum_phase<LOG2N>(S, MP, p.tw_n, p.tw_2n);
       const double coefficient = 2.0 * WB_PI * frac_shift * p.fs / N;
-      wb_irfft<-1>(S, NC, log2n - 1, p.tw_n, [&](int k) {
+      wb_irfft_t<-1, LOG2N - 1>(S, p.tw_n, [&](int k) {
         const cplx v = MP[k];
         const double re2 = cos(coefficient * k);
         const double im2 = sqrt(1.0 - re2 * re2);  // Q8: always >= 0
@@ -414,15 +415,15 @@ __global__ void __launch_bounds__(256) response_kernel(RespParams p) {
       const double average = wb_block_sum(part, red) / noise_size;
       for (int i = tid; i < N; i += nt) W[wb_didx(i)] = (i < noise_size) ? nz[i] - average : 0.0;
       __syncthreads();
-      wb_rfft<1>(S, NC, log2n - 1, p.tw_n, [&](int k, cplx X) { NS[k] = X; });
+      wb_rfft_t<1, LOG2N - 1>(S, p.tw_n, [&](int k, cplx X) { NS[k] = X; });
       if (current_vuv != 0.0) {
         for (int k = tid; k < bins; k += nt) W[wb_didx(k)] = log(SE[k] * AR[k]) / 2.0;
       } else {
         for (int k = tid; k < bins; k += nt) W[wb_didx(k)] = log(SE[k]) / 2.0;
       }
       __syncthreads();
-      minimum_phase(S, MP, N, log2n, p.tw_n, p.tw_2n);
-      wb_irfft<-1>(S, NC, log2n - 1, p.tw_n, [&](int k) {
+      minimum_phase<LOG2N>(S, MP, p.tw_n, p.tw_2n);
+      wb_irfft_t<-1, LOG2N - 1>(S, p.tw_n, [&](int k) {
         const cplx a = MP[k], b = NS[k];
         return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
       });
@@ -580,11 +581,14 @@ int wb_synthesis_render(WbWorkspace *ws, int fs, int fft_size, double frame_peri
   p.n_pulses = d_np; p.noise = d_noise; p.dc_remover = d_dcr; p.tw_n = tw_n; p.tw_2n = tw_2n; p.response = d_resp;
   const int binsp = ((fft_size / 2 + 1) + 1) & ~1;
   const size_t smem = sizeof(cplx) * (wb_fft_slots(fft_size) + 2 * binsp) + sizeof(double) * (2 * binsp + fft_size + 128);
-  WB_CUDA_CHECK(cudaFuncSetAttribute(response_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   p.max_resp_pulses = resp_pulses;
   p.error_flag = ws->error_flag();
   const int grid = wb_min_i(resp_pulses, 148 * 8);
-  WB_LAUNCH("response_kernel", response_kernel<<<grid, 256, smem, stream>>>(p));
+  rc = WB_DISPATCH_LOG2(log2n, 8, 13, {
+    if (cudaFuncSetAttribute(response_kernel<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WB_ERR_CUDA;
+    WB_LAUNCH("response_kernel", response_kernel<L2><<<grid, 256, smem, stream>>>(p));
+  });
+  if (rc) return rc;
   WB_CUDA_CHECK(cudaGetLastError());
   WB_LAUNCH("ola_kernel", ola_kernel<<<(out_length + 255) / 256, 256, 0, stream>>>(d_resp, d_pidx, d_np, resp_pulses, fft_size, out_length, d_out));
   WB_CUDA_CHECK(cudaGetLastError());
