@@ -1,6 +1,6 @@
 """Aggregates an ncu source-page CSV (SASS level) by CUDA source line using nvdisasm -g line info.
 
-usage: python profiles/hotlines.py <report.ncu-rep> <kernel regex> <cubin> [top_n]
+usage: python profiles/hotlines.py <report.ncu-rep> <kernel regex> <cubin> [top_n] [cubin symbol regex]
 The SASS instruction order of the ncu page and of nvdisasm agree, so instruction k of the kernel
 is mapped to the `//## File "...", line N` annotation that precedes it in the nvdisasm listing.
 """
@@ -14,6 +14,7 @@ from collections import defaultdict
 def main():
     rep, kregex, cubin = sys.argv[1], sys.argv[2], sys.argv[3]
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 25
+    cregex = sys.argv[5] if len(sys.argv) > 5 else kregex  # symbol regex inside the cubin
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kregex],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(src.splitlines()))
@@ -31,7 +32,7 @@ def main():
     lines = dis.splitlines()
     start = None
     for i, l in enumerate(lines):
-        if l.startswith(".text.") and re.search(kregex, l):
+        if l.startswith(".text.") and re.search(cregex, l):
             start = i
             break
     if start is None:

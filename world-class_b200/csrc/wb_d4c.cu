@@ -24,12 +24,12 @@ __device__ __forceinline__ int d4c_half_window(double ratio, int fs, double f0) 
   return wb_round(ratio * fs / f0 / 2.0);  // d4c.cpp:250
 }
 
-// d4c.cpp:246-303.  at(j) -> reference to destination sample j.  `win` >= 2*hw+1 doubles.
-// All threads must call; ends with __syncthreads().  Returns the window length.
-template <typename At>
+// d4c.cpp:246-303.  at(j) -> reference to destination sample j; win(j) -> reference to scratch for
+// window sample j.  All threads must call; ends with __syncthreads().  Returns the window length.
+template <typename At, typename Win>
 __device__ inline int d4c_windowed_waveform(const double *__restrict__ x, int x_length, int fs, double f0,
                                             double position_s, int window_type, double ratio,
-                                            const double *__restrict__ noise, double *win, double *red, At at) {
+                                            const double *__restrict__ noise, Win win, double *red, At at) {
   const int hw = d4c_half_window(ratio, fs, f0);
   const int wlen = 2 * hw + 1;
   const int origin = wb_round(position_s * fs + 0.001);
@@ -41,7 +41,7 @@ __device__ inline int d4c_windowed_waveform(const double *__restrict__ x, int x_
     double w;
     if (window_type == D4C_HANNING) w = 0.5 * cos(c2 * position) + 0.5;
     else w = 0.42 + 0.5 * cos(c2 * position) + 0.08 * cos(c2 * position * 2);
-    win[j] = w;
+    win(j) = w;
     const int idx = wb_min_i(x_length - 1, wb_max_i(0, origin + j - hw));
     const double v = x[idx] * w + noise[j] * WB_SAFEGUARD;
     at(j) = v;
@@ -50,7 +50,7 @@ __device__ inline int d4c_windowed_waveform(const double *__restrict__ x, int x_
   }
   wb_block_sum2(s1, s2, red);
   const double coef = s1 / s2;
-  for (int j = threadIdx.x; j < wlen; j += blockDim.x) at(j) -= win[j] * coef;
+  for (int j = threadIdx.x; j < wlen; j += blockDim.x) at(j) -= win(j) * coef;
   __syncthreads();
   return wlen;
 }
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(256) lt_frame_kernel(LtParams p) {
   }
   const double cf0 = f0 > p.lowest_f0 ? f0 : p.lowest_f0;
   const int wlen = d4c_windowed_waveform(p.x, p.x_length, p.fs, cf0, p.tpos[frame], D4C_BLACKMAN, 3.0,
-                                         p.noise + p.noise_off[frame], win, red,
+                                         p.noise + p.noise_off[frame], [&](int j) -> double & { return win[j]; }, red,
                                          [&](int j) -> double & { return W[wb_didx(j)]; });
   for (int j = wlen + threadIdx.x; j < N; j += blockDim.x) W[wb_didx(j)] = 0.0;
   __syncthreads();
@@ -131,8 +131,11 @@ __global__ void __launch_bounds__(256) lt_frame_kernel(LtParams p) {
 // smallest values to all threads.  Values must be non-negative.
 __device__ inline double d4c_sum_smallest(const double *v, int n, int m, int *hist, unsigned long long *ctl,
                                           double *red) {
+  // MSB-first radix select on the (non-negative) double bit patterns, 8 bits per pass.  As soon
+  // as the bucket that contains the m-th smallest value holds a single element the remaining
+  // passes are skipped: the element is fetched directly.
   unsigned long long prefix = 0ull, mask = 0ull;
-  if (threadIdx.x == 0) ctl[1] = (unsigned long long)m;  // remaining rank (1-based)
+  if (threadIdx.x == 0) { ctl[1] = (unsigned long long)m; ctl[3] = 0ull; }
   for (int pass = 0; pass < 8; ++pass) {
     const int shift = 56 - 8 * pass;
     for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
@@ -158,20 +161,34 @@ __device__ inline double d4c_sum_smallest(const double *v, int n, int m, int *hi
       if (remaining > excl && remaining <= incl) {
         int r = remaining - excl;
         int d = lane * 8;
+        int hcount = 0;
         for (int q = 0; q < 8; ++q) {
           const int h = hist[lane * 8 + q];
-          if (r <= h) { d = lane * 8 + q; break; }
+          if (r <= h) { d = lane * 8 + q; hcount = h; break; }
           r -= h;
         }
         ctl[0] = (unsigned long long)d;
         ctl[2] = (unsigned long long)r;
+        ctl[3] = (hcount == 1) ? 1ull : 0ull;
       }
     }
     __syncthreads();
     prefix |= ctl[0] << shift;
     mask |= 255ull << shift;
+    const bool unique = ctl[3] != 0ull;
     __syncthreads();
     if (threadIdx.x == 0) ctl[1] = ctl[2];
+    if (unique) {
+      // exactly one element carries this prefix: it is the m-th smallest
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned long long key = (unsigned long long)__double_as_longlong(v[i]);
+        if ((key & mask) == prefix) ctl[0] = key;
+      }
+      __syncthreads();
+      prefix = ctl[0];
+      __syncthreads();
+      break;
+    }
   }
   // prefix is now the bit pattern of the m-th smallest value
   const double t = __longlong_as_double((long long)prefix);
@@ -200,22 +217,29 @@ struct BodyParams {
   int *error_flag;
 };
 
+#define D4C_BODY_THREADS 256
+
+// Shared memory (N = 4096: 110 KB -> two CTAs per SM):
+//   S   : slots of an N-point complex FFT; doubles as the linear-smoothing scratch (`seg`) and,
+//         in its upper half, as window scratch while only a packed real transform lives in it
+//   SC  : static centroid -> static group delay
+//   SP  : smoothed power  -> second smoothing output -> band power spectrum
 template <int LOG2N>
-__global__ void __launch_bounds__(512) d4c_body_kernel(BodyParams p) {
+__global__ void __launch_bounds__(D4C_BODY_THREADS, 2) d4c_body_kernel(BodyParams p) {
   extern __shared__ double2 smem_raw[];
   constexpr int N = 1 << LOG2N, NC = N / 2, bins = NC + 1;
-  const int binsp = (bins + 1) & ~1;  // keep 16-byte alignment
-  cplx *S = smem_raw;                                            // slots for an N-point complex FFT
-  double *SC = reinterpret_cast<double *>(S + wb_fft_slots(N));   // static centroid / group delay
-  double *SP = SC + binsp;                                        // smoothed power | window scratch (with SG)
-  double *SG = SP + binsp;                                        // smoothed group delay | band power
-  double *seg = SG + binsp;                                       // seg_capacity
-  double *red = seg + p.seg_capacity;                             // 1024 + 64
-  int *hist = reinterpret_cast<int *>(red + 1088);                // 256 ints
+  constexpr int binsp = (bins + 1) & ~1;  // keep 16-byte alignment
+  cplx *S = smem_raw;
+  double *SC = reinterpret_cast<double *>(S + wb_fft_slots(N));
+  double *SP = SC + binsp;
+  double *red = SP + binsp;                                       // 320
+  int *hist = reinterpret_cast<int *>(red + 320);                 // 256 ints
   unsigned long long *ctl = reinterpret_cast<unsigned long long *>(hist + 256);  // 4
   double *coarse = reinterpret_cast<double *>(ctl + 4);           // D4C_MAX_AP + 2
   double *W = reinterpret_cast<double *>(S);
-  double *win = SP;  // SP..SG: >= N doubles of scratch while neither is live
+  double *seg = W;                                                // 2 * slots(N) doubles available
+  const int seg_capacity = 2 * wb_fft_slots(N);
+  double *win_hi = reinterpret_cast<double *>(S + wb_fft_slots(NC) + 8);  // >= N doubles above the packed real data
 
   const int frame = blockIdx.x;
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -229,10 +253,12 @@ __global__ void __launch_bounds__(512) d4c_body_kernel(BodyParams p) {
 
   // ---- static centroid: two windows at pos -/+ 0.25/f0 (d4c.cpp:339-405)
   // The reference transforms w[n] and (n+1) w[n] separately; both are real, so one complex
-  // transform of z[n] = w[n] + i (n+1) w[n] yields both spectra.
+  // transform of z[n] = w[n] + i (n+1) w[n] yields both spectra.  While the window is being
+  // built the imaginary parts of the slots hold the window samples.
   for (int c = 0; c < 2; ++c) {
     const double cpos = (c == 0) ? pos - 0.25 / f0 : pos + 0.25 / f0;
-    const int wlen = d4c_windowed_waveform(p.x, p.x_length, fs, f0, cpos, D4C_BLACKMAN, 4.0, noise, win, red,
+    const int wlen = d4c_windowed_waveform(p.x, p.x_length, fs, f0, cpos, D4C_BLACKMAN, 4.0, noise,
+                                           [&](int j) -> double & { return S[wb_sidx(j)].y; }, red,
                                            [&](int j) -> double & { return S[wb_sidx(j)].x; });
     noise += wlen;
     double pw = 0.0;
@@ -259,14 +285,14 @@ __global__ void __launch_bounds__(512) d4c_body_kernel(BodyParams p) {
 
   // ---- smoothed power spectrum (d4c.cpp:411-434)
   {
-    const int wlen = d4c_windowed_waveform(p.x, p.x_length, fs, f0, pos, D4C_HANNING, 4.0, noise, win, red,
+    const int wlen = d4c_windowed_waveform(p.x, p.x_length, fs, f0, pos, D4C_HANNING, 4.0, noise,
+                                           [&](int j) -> double & { return win_hi[j]; }, red,
                                            [&](int j) -> double & { return W[wb_didx(j)]; });
     for (int j = wlen + tid; j < N; j += nt) W[wb_didx(j)] = 0.0;
     __syncthreads();
-    // `win` (= SP..SG) is dead from here on
     wb_rfft_t<1, LOG2N - 1>(S, p.tw_n, [&](int k, cplx X) { SP[k] = X.x * X.x + X.y * X.y; });
     wb_dc_correction(SP, f0, fs, N);
-    if (!wb_linear_smoothing(SP, SP, f0, fs, N, seg, p.seg_capacity, red)) {
+    if (!wb_linear_smoothing(SP, SP, f0, fs, N, seg, seg_capacity, red)) {
       if (tid == 0) atomicExch(p.error_flag, WB_ERR_UNSUPPORTED);
       return;
     }
@@ -275,9 +301,9 @@ __global__ void __launch_bounds__(512) d4c_body_kernel(BodyParams p) {
   // ---- static group delay (d4c.cpp:440-460)
   for (int k = tid; k < bins; k += nt) SC[k] = SC[k] / SP[k];
   __syncthreads();
-  wb_linear_smoothing(SC, SC, f0 / 2.0, fs, N, seg, p.seg_capacity, red);
-  wb_linear_smoothing(SC, SG, f0, fs, N, seg, p.seg_capacity, red);
-  for (int k = tid; k < bins; k += nt) SC[k] -= SG[k];
+  wb_linear_smoothing(SC, SC, f0 / 2.0, fs, N, seg, seg_capacity, red);
+  wb_linear_smoothing(SC, SP, f0, fs, N, seg, seg_capacity, red);
+  for (int k = tid; k < bins; k += nt) SC[k] -= SP[k];
   __syncthreads();
 
   // ---- coarse aperiodicity per 3 kHz band (d4c.cpp:466-503)
@@ -292,11 +318,11 @@ __global__ void __launch_bounds__(512) d4c_body_kernel(BodyParams p) {
     double tot = 0.0;
     wb_rfft_t<1, LOG2N - 1>(S, p.tw_n, [&](int k, cplx X) {
       const double pw = X.x * X.x + X.y * X.y;
-      SG[k] = pw;
+      SP[k] = pw;
       tot += pw;
     });
     const double total = wb_block_sum(tot, red);
-    const double low = d4c_sum_smallest(SG, bins, m_small, hist, ctl, red);
+    const double low = d4c_sum_smallest(SP, bins, m_small, hist, ctl, red);
     if (tid == 0) {
       double ca = 10 * log10(low / total);
       const double rev = (f0 - 100) / 50.0;  // d4c.cpp:325-327
@@ -320,8 +346,7 @@ __global__ void __launch_bounds__(512) d4c_body_kernel(BodyParams p) {
     // histc (world_matlabfunctions.cpp:136-156): first knot strictly above xi, clamped to [1, nk-1]
     int k = 1;
     while (k < nk - 1) {
-      const double knot = (k == nk - 1) ? fs / 2.0 : k * WB_FREQ_INTERVAL;
-      if (xi < knot) break;
+      if (xi < k * WB_FREQ_INTERVAL) break;
       ++k;
     }
     const double x0 = (k - 1) * WB_FREQ_INTERVAL;
@@ -433,14 +458,14 @@ int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int
     p.n_ap = n_ap; p.window_length = window_length; p.nuttall = d_nuttall;
     p.tw_n = tw_n; p.tw_2n = tw_2n; p.noise = d_noise; p.noise_off = d_offsets;
     p.out_fft_size = out_fft_size; p.ap = d_ap;
-    p.seg_capacity = N / 2 + N / 4 + 8;
+    p.seg_capacity = 0;  // the smoothing scratch aliases the FFT slots
     p.error_flag = ws->error_flag();
     const int binsp = ((N / 2 + 1) + 1) & ~1;
-    const size_t smem = sizeof(cplx) * wb_fft_slots(N) + sizeof(double) * (3 * binsp + p.seg_capacity + 1088) +
+    const size_t smem = sizeof(cplx) * wb_fft_slots(N) + sizeof(double) * (2 * binsp + 320) +
                         sizeof(int) * 256 + sizeof(unsigned long long) * 4 + sizeof(double) * (D4C_MAX_AP + 2);
     rc = WB_DISPATCH_LOG2(l, 9, 13, {
       if (cudaFuncSetAttribute(d4c_body_kernel<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WB_ERR_CUDA;
-      WB_LAUNCH("d4c_body_kernel", d4c_body_kernel<L2><<<f0_length, 512, smem, stream>>>(p));
+      WB_LAUNCH("d4c_body_kernel", d4c_body_kernel<L2><<<f0_length, D4C_BODY_THREADS, smem, stream>>>(p));
     });
     if (rc) return rc;
     WB_CUDA_CHECK(cudaGetLastError());

@@ -56,7 +56,7 @@ bool decimate_coefficients(int r, DecimCoef *c) {
 }
 
 #define DEC_NFACT 9
-#define DEC_CHUNK 128
+#define DEC_CHUNK 32
 #define DEC_WARM 400
 
 // tmp1 of decimate() (world_matlabfunctions.cpp:189-193) over new_x of
@@ -71,39 +71,70 @@ __device__ __forceinline__ double dec_tmp1(const double *__restrict__ x, int x_l
   return 2 * dec_new_x(x, x_length, lag, len1 - 1) - dec_new_x(x, x_length, lag, len1 - 2 - (i - (DEC_NFACT + len1)));
 }
 
+// Both IIR passes work on tiles: a block stages DEC_TILE + DEC_WARM input samples in shared memory
+// with coalesced loads, every thread then runs the recurrence over its DEC_CHUNK outputs (plus
+// warm-up) out of shared memory, and the results leave through shared memory again.  The
+// per-thread stride of DEC_CHUNK doubles is padded to DEC_CHUNK + 1 to stay bank-conflict free.
+#define DEC_THREADS 128
+#define DEC_TILE (DEC_THREADS * DEC_CHUNK)
+__device__ __forceinline__ int dec_pad(int r) { return r + (r / DEC_CHUNK); }
+
 // forward pass: out[i] = FilterForDecimate(tmp1)[i], i in [0, len2)
-__global__ void dec_forward_kernel(const double *__restrict__ x, int x_length, int lag, int len1, int len2,
-                                   DecimCoef c, double *__restrict__ out) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int begin = t * DEC_CHUNK;
-  if (begin >= len2) return;
-  const int end = min(len2, begin + DEC_CHUNK);
-  int i = max(0, begin - DEC_WARM);
-  double w0 = 0.0, w1 = 0.0, w2 = 0.0;
-  for (; i < end; ++i) {
-    const double xi = dec_tmp1(x, x_length, lag, len1, i);
-    const double wt = xi + c.a[0] * w0 + c.a[1] * w1 + c.a[2] * w2;
-    if (i >= begin) out[i] = c.b[0] * wt + c.b[1] * w0 + c.b[1] * w1 + c.b[0] * w2;
-    w2 = w1; w1 = w0; w0 = wt;
+__global__ void __launch_bounds__(DEC_THREADS) dec_forward_kernel(const double *__restrict__ x, int x_length, int lag,
+                                                                  int len1, int len2, DecimCoef c,
+                                                                  double *__restrict__ out) {
+  extern __shared__ double dec_smem[];
+  double *s_in = dec_smem;                                     // dec_pad(DEC_TILE + DEC_WARM) + 1
+  double *s_out = dec_smem + dec_pad(DEC_TILE + DEC_WARM) + 1;  // dec_pad(DEC_TILE) + 1
+  const int tile_begin = blockIdx.x * DEC_TILE;
+  const int in_begin = tile_begin - DEC_WARM;
+  for (int r = threadIdx.x; r < DEC_TILE + DEC_WARM; r += DEC_THREADS) {
+    const int i = in_begin + r;
+    s_in[dec_pad(r)] = (i >= 0 && i < len2) ? dec_tmp1(x, x_length, lag, len1, i) : 0.0;
+  }
+  __syncthreads();
+  const int begin = tile_begin + threadIdx.x * DEC_CHUNK;
+  if (begin < len2) {
+    const int end = min(len2, begin + DEC_CHUNK);
+    double w0 = 0.0, w1 = 0.0, w2 = 0.0;
+    for (int i = max(0, begin - DEC_WARM); i < end; ++i) {
+      const double xi = s_in[dec_pad(i - in_begin)];
+      const double wt = xi + c.a[0] * w0 + c.a[1] * w1 + c.a[2] * w2;
+      if (i >= begin) s_out[dec_pad(i - tile_begin)] = c.b[0] * wt + c.b[1] * w0 + c.b[1] * w1 + c.b[0] * w2;
+      w2 = w1; w1 = w0; w0 = wt;
+    }
+  }
+  __syncthreads();
+  for (int r = threadIdx.x; r < DEC_TILE; r += DEC_THREADS) {
+    const int i = tile_begin + r;
+    if (i < len2) out[i] = s_out[dec_pad(r)];
   }
 }
 
 // backward pass over `fwd` (the reference reverses, filters, reverses) fused with the pick of
 // every r-th sample (world_matlabfunctions.cpp:201-207) and the lag removal + zero padding of
 // harvest.cpp:231-232,242.  y[m], m in [0, y_length).
-__global__ void dec_backward_kernel(const double *__restrict__ fwd, int len1, int len2, int r, int lag,
-                                    DecimCoef c, int y_length, double *__restrict__ y) {
+__global__ void __launch_bounds__(DEC_THREADS) dec_backward_kernel(const double *__restrict__ fwd, int len1, int len2,
+                                                                   int r, int lag, DecimCoef c, int y_length,
+                                                                   double *__restrict__ y) {
+  extern __shared__ double dec_smem[];
+  double *s_in = dec_smem;
   // reversed index u = len2 - 1 - i runs forward in filter time
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int begin = t * DEC_CHUNK;
+  const int tile_begin = blockIdx.x * DEC_TILE;
+  const int in_begin = tile_begin - DEC_WARM;
+  for (int q = threadIdx.x; q < DEC_TILE + DEC_WARM; q += DEC_THREADS) {
+    const int u = in_begin + q;
+    s_in[dec_pad(q)] = (u >= 0 && u < len2) ? fwd[len2 - 1 - u] : 0.0;
+  }
+  __syncthreads();
+  const int begin = tile_begin + threadIdx.x * DEC_CHUNK;
   if (begin >= len2) return;
   const int end = min(len2, begin + DEC_CHUNK);
   const int nout = len1 / r + 1;
   const int nbeg = r - r * nout + len1;
-  int u = max(0, begin - DEC_WARM);
   double w0 = 0.0, w1 = 0.0, w2 = 0.0;
-  for (; u < end; ++u) {
-    const double xi = fwd[len2 - 1 - u];
+  for (int u = max(0, begin - DEC_WARM); u < end; ++u) {
+    const double xi = s_in[dec_pad(u - in_begin)];
     const double wt = xi + c.a[0] * w0 + c.a[1] * w1 + c.a[2] * w2;
     if (u >= begin) {
       const double v = c.b[0] * wt + c.b[1] * w0 + c.b[1] * w1 + c.b[0] * w2;
@@ -304,10 +335,11 @@ __global__ void __launch_bounds__(CH_THREADS) channel_kernel(ChanParams p) {
   }
 }
 
-// gathers the per-block edge runs of one (channel, kind) into one ordered list
+// gathers the per-block edge runs of one (channel, kind) into one ordered list and derives the
+// interval locations / values of zeroCrossingEngine (harvest.cpp:1208-1211)
 __global__ void edge_compact_kernel(const double *__restrict__ seg_edges, const int *__restrict__ seg_count,
                                     int n_blocks, int bcap, double *__restrict__ edges, int *__restrict__ ecount,
-                                    int ecap) {
+                                    int ecap, double fs, double *__restrict__ locs, double *__restrict__ vals) {
   __shared__ int s_off[64];
   const int ct = blockIdx.x;  // channel * 4 + kind
   const int *cnt = seg_count + (size_t)ct * n_blocks;
@@ -324,6 +356,14 @@ __global__ void edge_compact_kernel(const double *__restrict__ seg_edges, const 
     for (int i = threadIdx.x; i < n; i += blockDim.x)
       if (o + i < ecap) edges[(size_t)ct * ecap + o + i] = src[i];
   }
+  __syncthreads();
+  const int total = min(s_off[n_blocks], ecap);
+  const double *e = edges + (size_t)ct * ecap;
+  for (int k = threadIdx.x; k + 1 < total; k += blockDim.x) {
+    const double e0 = e[k], e1 = e[k + 1];
+    vals[(size_t)ct * ecap + k] = fs / (e1 - e0);
+    locs[(size_t)ct * ecap + k] = (e0 + e1) / 2.0 / fs;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -331,14 +371,12 @@ __global__ void edge_compact_kernel(const double *__restrict__ seg_edges, const 
 // 1 ms frame grid + gating.  One thread per (channel, frame).
 // ---------------------------------------------------------------------------------------------
 struct RawParams {
-  const double *edges; const int *ecount; int ecap;
+  const double *locs; const double *vals; const int *ecount; int ecap;
   const double *boundary_f0; int nch; int f0_length; double actual_fs;
   double f0_floor; double f0_ceil; int frame_period;
   double *raw;  // [nch][f0_length]
 };
 
-__device__ __forceinline__ double hv_loc(const double *e, int k, double fs) { return (e[k] + e[k + 1]) / 2.0 / fs; }
-__device__ __forceinline__ double hv_val(const double *e, int k, double fs) { return fs / (e[k + 1] - e[k]); }
 
 __global__ void raw_candidate_kernel(RawParams p) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -358,19 +396,20 @@ __global__ void raw_candidate_kernel(RawParams p) {
   double v[4];
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
-    const double *e = p.edges + ((size_t)c * 4 + t) * p.ecap;
+    const double *loc = p.locs + ((size_t)c * 4 + t) * p.ecap;
+    const double *val = p.vals + ((size_t)c * 4 + t) * p.ecap;
     const int ni = cnt[t] - 1;
     // histc: first k with loc[k] > t_i, clamped to [1, ni - 1]
     int lo = 0, hi = ni;
     while (lo < hi) {
       const int mid = (lo + hi) >> 1;
-      if (hv_loc(e, mid, p.actual_fs) > t_i) hi = mid; else lo = mid + 1;
+      if (loc[mid] > t_i) hi = mid; else lo = mid + 1;
     }
     int k = lo;
     if (k < 1) k = 1;
     if (k > ni - 1) k = ni - 1;
-    const double x0 = hv_loc(e, k - 1, p.actual_fs), x1 = hv_loc(e, k, p.actual_fs);
-    const double y0 = hv_val(e, k - 1, p.actual_fs), y1 = hv_val(e, k, p.actual_fs);
+    const double x0 = loc[k - 1], x1 = loc[k];
+    const double y0 = val[k - 1], y1 = val[k];
     const double s = (t_i - x0) / (x1 - x0);
     v[t] = y0 + s * (y1 - y0);
   }
@@ -586,14 +625,15 @@ __global__ void remove_kernel(const double *__restrict__ cand_in, const double *
       // tmp_f0_candidates_ rows 0 and f0_length-1 are never filled (zero)
       const bool zero_row = (nb == 0 || nb == f0_length - 1);
       const double *row = cand_in + (size_t)nb * max_candidates;
-      double best_error = 1.0;
-      for (int k = 0; k < nc7; ++k) {
-        const double v = zero_row ? 0.0 : row[k];
-        const double tmp = fabs(reference_f0 - v) / reference_f0;
-        if (tmp > best_error) continue;
-        best_error = tmp;
+      // min_k fl(|ref - v_k| / ref) = fl(min_k |ref - v_k| / ref): rounded division by a positive
+      // constant is monotone, so one division reproduces selectBestF0's running minimum bit for bit
+      double dmin = fabs(reference_f0 - (zero_row ? 0.0 : row[0]));
+      for (int k = 1; k < nc7; ++k) {
+        const double d = fabs(reference_f0 - (zero_row ? 0.0 : row[k]));
+        dmin = d < dmin ? d : dmin;
       }
-      err[side] = best_error;
+      const double e = dmin / reference_f0;
+      err[side] = e > 1.0 ? 1.0 : e;
     }
     const double min_error = err[0] < err[1] ? err[0] : err[1];
     if (min_error > 0.05) { c = 0; s = 0; }
@@ -607,6 +647,8 @@ int ilog2_exact(int n) {
   while ((1 << l) < n) ++l;
   return ((1 << l) == n) ? l : -1;
 }
+
+int dec_pad_host(int r) { return r + (r / DEC_CHUNK); }
 
 }  // namespace
 
@@ -697,10 +739,14 @@ int wb_harvest_run_basic(WbHarvestPlan *pl, WbWorkspace *ws, const double *d_x, 
     if (!d_fwd) return WB_ERR_CUDA;
     DecimCoef dc;
     memcpy(&dc, pl->decim_coef, sizeof(dc));
-    const int n_thr = (len2 + DEC_CHUNK - 1) / DEC_CHUNK;
+    const int n_tiles = (len2 + DEC_TILE - 1) / DEC_TILE;
+    const size_t dec_smem_f = sizeof(double) * (dec_pad_host(DEC_TILE + DEC_WARM) + 1 + dec_pad_host(DEC_TILE) + 1);
+    const size_t dec_smem_b = sizeof(double) * (dec_pad_host(DEC_TILE + DEC_WARM) + 1);
+    WB_CUDA_CHECK(cudaFuncSetAttribute(dec_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_smem_f));
+    WB_CUDA_CHECK(cudaFuncSetAttribute(dec_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_smem_b));
     WB_CUDA_CHECK(cudaMemsetAsync(d_y, 0, sizeof(double) * y_length, stream));            // new_y is zero-initialised
-    WB_LAUNCH("dec_forward_kernel", dec_forward_kernel<<<(n_thr + 127) / 128, 128, 0, stream>>>(d_x, x_length, lag, len1, len2, dc, d_fwd));
-    WB_LAUNCH("dec_backward_kernel", dec_backward_kernel<<<(n_thr + 127) / 128, 128, 0, stream>>>(d_fwd, len1, len2, r, lag, dc, y_length, d_y));
+    WB_LAUNCH("dec_forward_kernel", dec_forward_kernel<<<n_tiles, DEC_THREADS, dec_smem_f, stream>>>(d_x, x_length, lag, len1, len2, dc, d_fwd));
+    WB_LAUNCH("dec_backward_kernel", dec_backward_kernel<<<n_tiles, DEC_THREADS, dec_smem_b, stream>>>(d_fwd, len1, len2, r, lag, dc, y_length, d_y));
   }
   unsigned long long *d_absmax = (unsigned long long *)ws->get("hv_absmax", 16);
   double *d_mean = (double *)ws->get("hv_mean", 16);
@@ -730,6 +776,9 @@ int wb_harvest_run_basic(WbHarvestPlan *pl, WbWorkspace *ws, const double *d_x, 
   if (n_blocks > 63) return WB_ERR_UNSUPPORTED;  // TODO(long streams): tile the block axis
   double *d_edges = (double *)ws->get("hv_edges", sizeof(double) * (size_t)nch * 4 * ecap);
   int *d_ecount = (int *)ws->get("hv_ecount", sizeof(int) * nch * 4);
+  double *d_locs = (double *)ws->get("hv_locs", sizeof(double) * (size_t)nch * 4 * ecap);
+  double *d_vals = (double *)ws->get("hv_vals", sizeof(double) * (size_t)nch * 4 * ecap);
+  if (!d_locs || !d_vals) return WB_ERR_CUDA;
   double *d_seg = (double *)ws->get("hv_seg_edges", sizeof(double) * (size_t)nch * 4 * n_blocks * bcap);
   int *d_segc = (int *)ws->get("hv_seg_count", sizeof(int) * (size_t)nch * 4 * n_blocks);
   if (!d_edges || !d_ecount || !d_seg || !d_segc) return WB_ERR_CUDA;
@@ -745,7 +794,7 @@ int wb_harvest_run_basic(WbHarvestPlan *pl, WbWorkspace *ws, const double *d_x, 
     });
     if (rc) return rc;
     WB_CUDA_CHECK(cudaGetLastError());
-    WB_LAUNCH("edge_compact_kernel", edge_compact_kernel<<<nch * 4, 256, 0, stream>>>(d_seg, d_segc, n_blocks, bcap, d_edges, d_ecount, ecap));
+    WB_LAUNCH("edge_compact_kernel", edge_compact_kernel<<<nch * 4, 256, 0, stream>>>(d_seg, d_segc, n_blocks, bcap, d_edges, d_ecount, ecap, afs, d_locs, d_vals));
     WB_CUDA_CHECK(cudaGetLastError());
   }
 
@@ -754,7 +803,7 @@ int wb_harvest_run_basic(WbHarvestPlan *pl, WbWorkspace *ws, const double *d_x, 
   if (!d_raw) return WB_ERR_CUDA;
   {
     RawParams p;
-    p.edges = d_edges; p.ecount = d_ecount; p.ecap = ecap; p.boundary_f0 = (const double *)ws->get("hv_bf", 0);
+    p.locs = d_locs; p.vals = d_vals; p.ecount = d_ecount; p.ecap = ecap; p.boundary_f0 = (const double *)ws->get("hv_bf", 0);
     p.nch = nch; p.f0_length = Lb; p.actual_fs = afs; p.f0_floor = pl->opt.f0_floor; p.f0_ceil = pl->opt.f0_ceil;
     p.frame_period = frame_period; p.raw = d_raw;
     dim3 grid((Lb + 255) / 256, nch);

@@ -20,7 +20,7 @@
 
 namespace {
 
-#define TL_THREADS 1024
+#define TL_THREADS 512
 #define TL_MARGIN 104
 #define TL_LAG 300
 #define TL_CHUNK 64
@@ -97,7 +97,33 @@ __device__ __forceinline__ double tl_select_best(double reference_f0, const doub
   return best_idx >= 0 ? cands[best_idx] : 0.0;
 }
 
-// extendF0 (harvest.cpp:371-404) by one warp on sparse section s
+// selectBestF0 on a candidate row already held in registers (lane l: entries l and l + 32)
+__device__ __forceinline__ double tl_select_best_reg(double reference_f0, double c0, double c1, int n, double allowed) {
+  const int lane = threadIdx.x & 31;
+  double best_err = allowed, best_val = 0.0;
+  int best_idx = -1;
+  if (lane < n) {
+    const double tmp = fabs(reference_f0 - c0) / reference_f0;
+    if (!(tmp > best_err)) { best_err = tmp; best_idx = lane; best_val = c0; }
+  }
+  if (lane + 32 < n) {
+    const double tmp = fabs(reference_f0 - c1) / reference_f0;
+    if (!(tmp > best_err)) { best_err = tmp; best_idx = lane + 32; best_val = c1; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double e2 = __shfl_xor_sync(0xffffffffu, best_err, o);
+    const int i2 = __shfl_xor_sync(0xffffffffu, best_idx, o);
+    const double v2 = __shfl_xor_sync(0xffffffffu, best_val, o);
+    if (i2 >= 0 && (best_idx < 0 || e2 < best_err || (e2 == best_err && i2 > best_idx))) { best_err = e2; best_idx = i2; best_val = v2; }
+  }
+  return best_idx >= 0 ? best_val : 0.0;
+}
+
+// extendF0 (harvest.cpp:371-404) by one warp on sparse section s.  The candidate rows of the next
+// TL_PF frames are fetched together (they do not depend on the running F0), so the serial chain
+// of selectBestF0 calls runs from registers instead of paying one L2 round trip per frame.
+#define TL_PF 8
 __device__ int tl_extend_f0(const TailParams &p, int s, int origin, int last_point, int shift, int nc7) {
   const int lane = threadIdx.x & 31;
   double *f = p.secbuf + p.sec_off[s] - p.sec_lo[s];  // f[i] valid for lo <= i <= hi
@@ -106,18 +132,55 @@ __device__ int tl_extend_f0(const TailParams &p, int s, int origin, int last_poi
   int shifted_origin = origin;
   const int distance = abs(last_point - origin);
   int count = 0;
-  for (int i = 0; i <= distance; ++i) {
-    const int pos = origin + shift * i + shift;
-    const double v = tl_select_best(tmp_f0, p.cand + (size_t)pos * p.MC, nc7, 0.18);
-    if (lane == 0) f[pos] = v;
-    if (v == 0.0) {
-      count++;
-    } else {
-      tmp_f0 = v;
-      count = 0;
-      shifted_origin = pos;
+  bool stop = false;
+  const int n = nc7;
+  if (n > 64) {
+    // wide candidate tables (rare): plain version, one row per step from global memory
+    for (int i = 0; i <= distance; ++i) {
+      const int pos = origin + shift * i + shift;
+      const double v = tl_select_best(tmp_f0, p.cand + (size_t)pos * p.MC, nc7, 0.18);
+      if (lane == 0) f[pos] = v;
+      if (v == 0.0) {
+        count++;
+      } else {
+        tmp_f0 = v;
+        count = 0;
+        shifted_origin = pos;
+      }
+      if (count == threshold) break;
     }
-    if (count == threshold) break;
+    __syncwarp();
+    return shifted_origin;
+  }
+  for (int i0 = 0; i0 <= distance && !stop; i0 += TL_PF) {
+    double c0[TL_PF], c1[TL_PF];
+#pragma unroll
+    for (int k = 0; k < TL_PF; ++k) {
+      const int i = i0 + k;
+      c0[k] = 0.0; c1[k] = 0.0;
+      if (i <= distance) {
+        const double *row = p.cand + (size_t)(origin + shift * i + shift) * p.MC;
+        if (lane < n) c0[k] = row[lane];
+        if (lane + 32 < n) c1[k] = row[lane + 32];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < TL_PF; ++k) {
+      const int i = i0 + k;
+      if (i <= distance && !stop) {
+        const int pos = origin + shift * i + shift;
+        const double v = tl_select_best_reg(tmp_f0, c0[k], c1[k], n, 0.18);
+        if (lane == 0) f[pos] = v;
+        if (v == 0.0) {
+          count++;
+        } else {
+          tmp_f0 = v;
+          count = 0;
+          shifted_origin = pos;
+        }
+        if (count == threshold) stop = true;
+      }
+    }
   }
   __syncwarp();
   return shifted_origin;
