@@ -132,6 +132,20 @@ int wb_synthesis_compute_dev(wb_synthesis_t *h, const double *d_f0, int f0_lengt
                              const double *d_spectrogram, const double *d_aperiodicity,
                              int out_length, double *d_out, double f0_upper_bound, void *stream);
 
+/* ---- codec (include/codec.hpp:23-88; src/codec.cpp:211-325) ------------------------------
+ * Same argument meaning as the reference's free functions; rows are separately allocated. */
+int wb_code_aperiodicity(const double *const *aperiodicity, int f0_length, int fs, int fft_size,
+                         double **coded_aperiodicity);                       /* src/codec.cpp:216-235 */
+int wb_decode_aperiodicity(const double *const *coded_aperiodicity, int f0_length, int fs, int fft_size,
+                           double **aperiodicity);                           /* src/codec.cpp:237-265 */
+int wb_code_spectral_envelope(const double *const *spectrogram, int f0_length, int fs, int fft_size,
+                              int number_of_dimensions, double **coded_spectral_envelope); /* :267-296 */
+int wb_decode_spectral_envelope(const double *const *coded_spectral_envelope, int f0_length, int fs,
+                                int fft_size, int number_of_dimensions, double **spectrogram); /* :298-325 */
+/* contiguous DEVICE arrays; kind: 0 code ap, 1 decode ap, 2 code sp, 3 decode sp; asynchronous */
+int wb_codec_dev(int kind, const double *d_in, int f0_length, int fs, int fft_size, int number_of_dimensions,
+                 double *d_out, void *stream);
+
 /* ---- whole chain, device resident -----------------------------------------------------
  * The call sequence of test/test.cpp:288-384 (Harvest -> CheapTrick -> D4C -> Synthesis) with
  * every intermediate kept in HBM.  NULL option pointers = defaults; NULL output pointers in

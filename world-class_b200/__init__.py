@@ -91,6 +91,11 @@ def _declare(L):
         "wb_cheaptrick_compute": (ci, [vp, vp, ci, vp, vp, ci, vp]),
         "wb_cheaptrick_compute_dev": (ci, [vp, vp, ci, vp, vp, ci, vp, vp]),
         "wb_get_number_of_aperiodicities": (ci, [ci]),
+        "wb_code_aperiodicity": (ci, [vp, ci, ci, ci, vp]),
+        "wb_decode_aperiodicity": (ci, [vp, ci, ci, ci, vp]),
+        "wb_code_spectral_envelope": (ci, [vp, ci, ci, ci, ci, vp]),
+        "wb_decode_spectral_envelope": (ci, [vp, ci, ci, ci, ci, vp]),
+        "wb_codec_dev": (ci, [ci, vp, ci, ci, ci, ci, vp, vp]),
         "wb_pipeline_create": (ci, [ci, ctypes.POINTER(HarvestOption), ctypes.POINTER(CheapTrickOption),
                                     ctypes.POINTER(D4COption), ctypes.POINTER(vp)]),
         "wb_pipeline_destroy": (None, [vp]),
@@ -406,3 +411,36 @@ def profile_results():
         _check(lib().wb_profile_query(name.encode(), ctypes.byref(ms), ctypes.byref(cnt)), "wb_profile_query")
         res[name] = (ms.value, cnt.value)
     return res
+
+
+# ---- codec (include/codec.hpp:23-88) ---------------------------------------------------------
+def GetNumberOfAperiodicities(fs):
+    return lib().wb_get_number_of_aperiodicities(int(fs))
+
+
+def _codec(fn, name, src, out_cols, *args):
+    src = _f64(src)
+    out = np.empty((src.shape[0], out_cols), dtype=np.float64)
+    ri, ro = _row_pointers(src), _row_pointers(out)
+    _check(fn(ri.ctypes.data, src.shape[0], *args, ro.ctypes.data), name)
+    return out
+
+
+def CodeAperiodicity(aperiodicity, fs, fft_size):
+    return _codec(lib().wb_code_aperiodicity, "wb_code_aperiodicity", aperiodicity, GetNumberOfAperiodicities(fs),
+                  int(fs), int(fft_size))
+
+
+def DecodeAperiodicity(coded_aperiodicity, fs, fft_size):
+    return _codec(lib().wb_decode_aperiodicity, "wb_decode_aperiodicity", coded_aperiodicity, int(fft_size) // 2 + 1,
+                  int(fs), int(fft_size))
+
+
+def CodeSpectralEnvelope(spectrogram, fs, fft_size, number_of_dimensions):
+    return _codec(lib().wb_code_spectral_envelope, "wb_code_spectral_envelope", spectrogram, int(number_of_dimensions),
+                  int(fs), int(fft_size), int(number_of_dimensions))
+
+
+def DecodeSpectralEnvelope(coded_spectral_envelope, fs, fft_size, number_of_dimensions):
+    return _codec(lib().wb_decode_spectral_envelope, "wb_decode_spectral_envelope", coded_spectral_envelope,
+                  int(fft_size) // 2 + 1, int(fs), int(fft_size), int(number_of_dimensions))

@@ -552,6 +552,72 @@ int wb_pipeline_run(wb_pipeline_t *p, const double *x, int x_length, double *tpo
   return p->ws.read_error_flag(st);
 }
 
+// ---- codec (include/codec.hpp:23-88) --------------------------------------------------------
+static WbWorkspace *codec_ws() {
+  static WbWorkspace ws;  // codec functions are free functions in the reference: one shared workspace
+  return &ws;
+}
+
+static int codec_rows(int kind, const double *const *in, int in_cols, int f0_length, int fs, int fft_size, int nd,
+                      double **out, int out_cols) {
+  int rc = ctx_init();
+  if (rc) return rc;
+  if (!in || !out || f0_length < 0 || fs <= 0 || fft_size < 2) return WB_ERR_ARG;
+  if (f0_length == 0) return WB_OK;
+  if (in_cols <= 0 || out_cols <= 0) return WB_ERR_UNSUPPORTED;
+  WbWorkspace *ws = codec_ws();
+  cudaStream_t st = g_stream;
+  double *d_in = (double *)ws->get("codec_in", sizeof(double) * (size_t)f0_length * in_cols);
+  double *d_out = (double *)ws->get("codec_out", sizeof(double) * (size_t)f0_length * out_cols);
+  if (!d_in || !d_out) return WB_ERR_CUDA;
+  if ((rc = rows_to_device(ws, "rows_stage_in", in, f0_length, in_cols, d_in, st))) return rc;
+  switch (kind) {
+    case 0: rc = wb_code_aperiodicity_dev(d_in, f0_length, fs, fft_size, d_out, st); break;
+    case 1: rc = wb_decode_aperiodicity_dev(d_in, f0_length, fs, fft_size, d_out, st); break;
+    case 2: rc = wb_code_spectral_envelope_dev(ws, d_in, f0_length, fs, fft_size, nd, d_out, st); break;
+    default: rc = wb_decode_spectral_envelope_dev(ws, d_in, f0_length, fs, fft_size, nd, d_out, st); break;
+  }
+  if (rc) return rc;
+  return rows_to_host(ws, d_out, f0_length, out_cols, out, st);
+}
+
+int wb_code_aperiodicity(const double *const *aperiodicity, int f0_length, int fs, int fft_size,
+                         double **coded_aperiodicity) {
+  return codec_rows(0, aperiodicity, fft_size / 2 + 1, f0_length, fs, fft_size, 0, coded_aperiodicity,
+                    wb_number_of_aperiodicities(fs));
+}
+int wb_decode_aperiodicity(const double *const *coded_aperiodicity, int f0_length, int fs, int fft_size,
+                           double **aperiodicity) {
+  return codec_rows(1, coded_aperiodicity, wb_number_of_aperiodicities(fs), f0_length, fs, fft_size, 0, aperiodicity,
+                    fft_size / 2 + 1);
+}
+int wb_code_spectral_envelope(const double *const *spectrogram, int f0_length, int fs, int fft_size,
+                              int number_of_dimensions, double **coded_spectral_envelope) {
+  return codec_rows(2, spectrogram, fft_size / 2 + 1, f0_length, fs, fft_size, number_of_dimensions,
+                    coded_spectral_envelope, number_of_dimensions);
+}
+int wb_decode_spectral_envelope(const double *const *coded_spectral_envelope, int f0_length, int fs, int fft_size,
+                                int number_of_dimensions, double **spectrogram) {
+  return codec_rows(3, coded_spectral_envelope, number_of_dimensions, f0_length, fs, fft_size, number_of_dimensions,
+                    spectrogram, fft_size / 2 + 1);
+}
+
+// contiguous device-pointer variants; asynchronous on `stream`
+int wb_codec_dev(int kind, const double *d_in, int f0_length, int fs, int fft_size, int number_of_dimensions,
+                 double *d_out, void *stream) {
+  int rc = ctx_init();
+  if (rc) return rc;
+  if (!d_in || !d_out || f0_length < 0) return WB_ERR_ARG;
+  cudaStream_t st = pick_stream(stream);
+  switch (kind) {
+    case 0: return wb_code_aperiodicity_dev(d_in, f0_length, fs, fft_size, d_out, st);
+    case 1: return wb_decode_aperiodicity_dev(d_in, f0_length, fs, fft_size, d_out, st);
+    case 2: return wb_code_spectral_envelope_dev(codec_ws(), d_in, f0_length, fs, fft_size, number_of_dimensions, d_out, st);
+    case 3: return wb_decode_spectral_envelope_dev(codec_ws(), d_in, f0_length, fs, fft_size, number_of_dimensions, d_out, st);
+    default: return WB_ERR_ARG;
+  }
+}
+
 /* test / bench hook: copies n_bytes of a named internal device buffer of the last run */
 int wb_pipeline_debug_read(wb_pipeline_t *p, const char *name, void *out, unsigned long long n_bytes) {
   if (!p || !name || !out) return WB_ERR_ARG;

@@ -52,3 +52,13 @@ int wb_synthesis_timebase(WbWorkspace *ws, int fs, int fft_size, double frame_pe
 int wb_synthesis_render(WbWorkspace *ws, int fs, int fft_size, double frame_period_ms, int f0_length,
                         const double *d_sp, const double *d_ap, int out_length, double *d_out,
                         double f0_upper_bound, WbRngState *d_rng, cudaStream_t stream);
+
+// codec (wb_codec.cu)
+int wb_code_aperiodicity_dev(const double *d_ap, int f0_length, int fs, int fft_size, double *d_coded,
+                             cudaStream_t stream);
+int wb_decode_aperiodicity_dev(const double *d_coded, int f0_length, int fs, int fft_size, double *d_ap,
+                               cudaStream_t stream);
+int wb_code_spectral_envelope_dev(WbWorkspace *ws, const double *d_sp, int f0_length, int fs, int fft_size, int nd,
+                                  double *d_coded, cudaStream_t stream);
+int wb_decode_spectral_envelope_dev(WbWorkspace *ws, const double *d_coded, int f0_length, int fs, int fft_size,
+                                    int nd, double *d_sp, cudaStream_t stream);
