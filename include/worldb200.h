@@ -153,6 +153,9 @@ int wb_codec_dev(int kind, const double *d_in, int f0_length, int fs, int fft_si
 int wb_pipeline_create(int fs, const WbHarvestOption *hopt, const WbCheapTrickOption *copt,
                        const WbD4COption *dopt, wb_pipeline_t **out);
 void wb_pipeline_destroy(wb_pipeline_t *p);
+/* fresh != 0: every run restarts its own randn() stream at the reference's seed (one utterance ==
+ * one reference process); such pipelines may run concurrently on different streams (batches). */
+int wb_pipeline_set_fresh_rng(wb_pipeline_t *p, int fresh);
 int wb_pipeline_fft_size(const wb_pipeline_t *p);
 int wb_pipeline_f0_length(const wb_pipeline_t *p, int x_length);      /* src/harvest.cpp:173-181 */
 int wb_pipeline_out_length(const wb_pipeline_t *p, int x_length);     /* test/test.cpp:362-363 */

@@ -99,6 +99,7 @@ def _declare(L):
         "wb_pipeline_create": (ci, [ci, ctypes.POINTER(HarvestOption), ctypes.POINTER(CheapTrickOption),
                                     ctypes.POINTER(D4COption), ctypes.POINTER(vp)]),
         "wb_pipeline_destroy": (None, [vp]),
+        "wb_pipeline_set_fresh_rng": (ci, [vp, ci]),
         "wb_pipeline_fft_size": (ci, [vp]),
         "wb_pipeline_f0_length": (ci, [vp, ci]),
         "wb_pipeline_out_length": (ci, [vp, ci]),
@@ -348,6 +349,10 @@ class Pipeline:
             _lib.wb_pipeline_destroy(self._h)
             self._h = None
 
+    def set_fresh_rng(self, fresh=True):
+        """Batch mode: every run starts its own randn() stream at the reference's seed."""
+        _check(lib().wb_pipeline_set_fresh_rng(self._h, 1 if fresh else 0), "wb_pipeline_set_fresh_rng")
+
     def f0_length(self, x_length):
         return lib().wb_pipeline_f0_length(self._h, int(x_length))
 
@@ -444,3 +449,43 @@ def CodeSpectralEnvelope(spectrogram, fs, fft_size, number_of_dimensions):
 def DecodeSpectralEnvelope(coded_spectral_envelope, fs, fft_size, number_of_dimensions):
     return _codec(lib().wb_decode_spectral_envelope, "wb_decode_spectral_envelope", coded_spectral_envelope,
                   int(fft_size) // 2 + 1, int(fs), int(fft_size), int(number_of_dimensions))
+
+
+class BatchPipeline:
+    """Independent utterances (BASELINE configs[2]) on `n_streams` concurrent pipelines of one GPU.
+
+    Each utterance is processed exactly like one reference process (fresh randn() stream).  Inputs and
+    outputs are torch CUDA tensors; utterance i runs on stream i % n_streams, so the small,
+    latency-bound kernels of one utterance overlap with the wide kernels of the others."""
+
+    def __init__(self, fs, n_streams=8, harvest_option=None, cheaptrick_option=None, d4c_option=None):
+        import torch
+        self._torch = torch
+        self.pipes = [Pipeline(fs, harvest_option, cheaptrick_option, d4c_option) for _ in range(n_streams)]
+        for p in self.pipes:
+            p.set_fresh_rng(True)
+        self.streams = [torch.cuda.Stream() for _ in range(n_streams)]
+        self.fft_size = self.pipes[0].fft_size
+
+    def run(self, xs):
+        """xs: list of 1-D float64 CUDA tensors -> list of dict(f0, sp, ap, y) of CUDA tensors."""
+        torch = self._torch
+        outs = []
+        cur = torch.cuda.current_stream()
+        for i, x in enumerate(xs):
+            pl, st = self.pipes[i % len(self.pipes)], self.streams[i % len(self.streams)]
+            n = x.numel()
+            L, ny, bins = pl.f0_length(n), pl.out_length(n), self.fft_size // 2 + 1
+            o = {"tpos": torch.empty(L, dtype=torch.float64, device=x.device),
+                 "f0": torch.empty(L, dtype=torch.float64, device=x.device),
+                 "sp": torch.empty((L, bins), dtype=torch.float64, device=x.device),
+                 "ap": torch.empty((L, bins), dtype=torch.float64, device=x.device),
+                 "y": torch.empty(ny, dtype=torch.float64, device=x.device)}
+            st.wait_stream(cur)
+            pl.run_dev(x.data_ptr(), n, d_y=o["y"].data_ptr(), y_length=ny, stream=st.cuda_stream,
+                       d_tpos=o["tpos"].data_ptr(), d_f0=o["f0"].data_ptr(), d_sp=o["sp"].data_ptr(),
+                       d_ap=o["ap"].data_ptr())
+            outs.append(o)
+        for st in self.streams:
+            cur.wait_stream(st)
+        return outs

@@ -88,10 +88,15 @@ struct wb_pipeline {
   WbWorkspace ws;
   cudaStream_t side = nullptr;       // Synthesis time base overlaps CheapTrick / D4C here
   cudaEvent_t ev_f0 = nullptr, ev_tb = nullptr;
+  bool private_rng = false;          // batch mode: every run starts from the reference's seed
+  WbRngState *d_rng_private = nullptr;
+  WbRngState *d_rng_seed = nullptr;
   ~wb_pipeline() {
     if (ev_f0) cudaEventDestroy(ev_f0);
     if (ev_tb) cudaEventDestroy(ev_tb);
     if (side) cudaStreamDestroy(side);
+    if (d_rng_private) cudaFree(d_rng_private);
+    if (d_rng_seed) cudaFree(d_rng_seed);
   }
 };
 
@@ -465,6 +470,22 @@ int wb_pipeline_create(int fs, const WbHarvestOption *hopt, const WbCheapTrickOp
 }
 
 void wb_pipeline_destroy(wb_pipeline_t *p) { delete p; }
+
+/* Batch mode: with fresh != 0 every run of this pipeline draws from its own randn() stream that
+ * restarts at the reference's seed, i.e. each utterance is processed like one reference process.
+ * Pipelines in this mode are independent of each other and may run concurrently on different
+ * streams.  Default (0): the process-global stream, like consecutive calls in one reference process. */
+int wb_pipeline_set_fresh_rng(wb_pipeline_t *p, int fresh) {
+  if (!p) return WB_ERR_ARG;
+  if (fresh && !p->d_rng_private) {
+    const WbRngState s0 = {{123456789u, 362436069u, 521288629u, 88675123u}};
+    WB_CUDA_CHECK(cudaMalloc(&p->d_rng_private, sizeof(WbRngState)));
+    WB_CUDA_CHECK(cudaMalloc(&p->d_rng_seed, sizeof(WbRngState)));
+    WB_CUDA_CHECK(cudaMemcpy(p->d_rng_seed, &s0, sizeof(s0), cudaMemcpyHostToDevice));
+  }
+  p->private_rng = fresh != 0;
+  return WB_OK;
+}
 int wb_pipeline_fft_size(const wb_pipeline_t *p) { return p ? p->ct.fft_size : 0; }
 int wb_pipeline_f0_length(const wb_pipeline_t *p, int x_length) {
   return p ? wb_harvest_get_samples(p->fs, x_length, p->plan.opt.frame_period) : 0;
@@ -502,6 +523,10 @@ int wb_pipeline_run_dev(wb_pipeline_t *p, const double *d_x, int x_length, doubl
     if ((rc = wb_harvest_pick(d_basic, Lb, fp, f0_length, d_tpos, d_f0, st))) return rc;
   }
   WbRngState *rng = wb_rng_global_state();
+  if (p->private_rng) {
+    rng = p->d_rng_private;
+    WB_CUDA_CHECK(cudaMemcpyAsync(rng, p->d_rng_seed, sizeof(WbRngState), cudaMemcpyDeviceToDevice, st));
+  }
   // The pulse list depends on f0 only: compute it on the side stream, concurrently with CheapTrick / D4C
   if (y_length > 0) {
     WB_CUDA_CHECK(cudaEventRecord(p->ev_f0, st));
