@@ -5,7 +5,10 @@
 #include <math.h>
 #include <string.h>
 #include <mutex>
+#include <algorithm>
 #include <new>
+#include <thread>
+#include <vector>
 
 #include "wb_internal.h"
 #include "wb_harvest.h"
@@ -35,15 +38,48 @@ int ctx_init() {
 
 inline cudaStream_t pick_stream(void *stream) { return stream ? (cudaStream_t)stream : g_stream; }
 
+// ---- host <-> device transfers of row-pointer matrices -------------------------------------------
+// The reference API hands matrices over as separately allocated rows (test/test.cpp:146-149).  Rows are
+// staged through pinned memory in a few chunks: the DMA of chunk k+1 overlaps the (multi-threaded)
+// host memcpy of chunk k.
+const int kRowChunks = 4;
+const int kCopyThreads = 8;
+
+template <typename F>
+void parallel_rows(int r0, int r1, F f) {
+  const int n = r1 - r0;
+  const int nthreads = std::max(1, std::min(kCopyThreads, n / 64));
+  if (nthreads == 1) { for (int i = r0; i < r1; ++i) f(i); return; }
+  std::vector<std::thread> pool;
+  pool.reserve(nthreads);
+  for (int t = 0; t < nthreads; ++t) {
+    const int b = r0 + (int)((long long)n * t / nthreads), e = r0 + (int)((long long)n * (t + 1) / nthreads);
+    pool.emplace_back([=]() { for (int i = b; i < e; ++i) f(i); });
+  }
+  for (auto &th : pool) th.join();
+}
+
 // copy a contiguous [rows][cols] device matrix into separately allocated host rows
 int rows_to_host(WbWorkspace *ws, const double *d_src, int rows, int cols, double **dst, cudaStream_t st) {
   const size_t bytes = sizeof(double) * (size_t)rows * cols;
   double *stage = (double *)ws->get_pinned("rows_stage", bytes);
   if (!stage) return WB_ERR_CUDA;
-  WB_CUDA_CHECK(cudaMemcpyAsync(stage, d_src, bytes, cudaMemcpyDeviceToHost, st));
-  WB_CUDA_CHECK(cudaStreamSynchronize(st));
-  for (int i = 0; i < rows; ++i) memcpy(dst[i], stage + (size_t)i * cols, sizeof(double) * cols);
-  return WB_OK;
+  cudaEvent_t ev[kRowChunks];
+  int bounds[kRowChunks + 1];
+  for (int c = 0; c <= kRowChunks; ++c) bounds[c] = (int)((long long)rows * c / kRowChunks);
+  for (int c = 0; c < kRowChunks; ++c) {
+    WB_CUDA_CHECK(cudaEventCreateWithFlags(&ev[c], cudaEventDisableTiming));
+    const size_t off = (size_t)bounds[c] * cols, cnt = (size_t)(bounds[c + 1] - bounds[c]) * cols;
+    if (cnt) WB_CUDA_CHECK(cudaMemcpyAsync(stage + off, d_src + off, sizeof(double) * cnt, cudaMemcpyDeviceToHost, st));
+    WB_CUDA_CHECK(cudaEventRecord(ev[c], st));
+  }
+  int rc = WB_OK;
+  for (int c = 0; c < kRowChunks; ++c) {
+    if (cudaEventSynchronize(ev[c]) != cudaSuccess) rc = WB_ERR_CUDA;
+    if (!rc) parallel_rows(bounds[c], bounds[c + 1], [=](int i) { memcpy(dst[i], stage + (size_t)i * cols, sizeof(double) * cols); });
+    cudaEventDestroy(ev[c]);
+  }
+  return rc;
 }
 
 // gather separately allocated host rows into a contiguous device matrix
@@ -52,8 +88,12 @@ int rows_to_device(WbWorkspace *ws, const char *name, const double *const *src, 
   const size_t bytes = sizeof(double) * (size_t)rows * cols;
   double *stage = (double *)ws->get_pinned(name, bytes);
   if (!stage) return WB_ERR_CUDA;
-  for (int i = 0; i < rows; ++i) memcpy(stage + (size_t)i * cols, src[i], sizeof(double) * cols);
-  WB_CUDA_CHECK(cudaMemcpyAsync(d_dst, stage, bytes, cudaMemcpyHostToDevice, st));
+  for (int c = 0; c < kRowChunks; ++c) {
+    const int r0 = (int)((long long)rows * c / kRowChunks), r1 = (int)((long long)rows * (c + 1) / kRowChunks);
+    parallel_rows(r0, r1, [=](int i) { memcpy(stage + (size_t)i * cols, src[i], sizeof(double) * cols); });
+    const size_t off = (size_t)r0 * cols, cnt = (size_t)(r1 - r0) * cols;
+    if (cnt) WB_CUDA_CHECK(cudaMemcpyAsync(d_dst + off, stage + off, sizeof(double) * cnt, cudaMemcpyHostToDevice, st));
+  }
   return WB_OK;
 }
 

@@ -35,18 +35,26 @@ __device__ inline int d4c_windowed_waveform(const double *__restrict__ x, int x_
   const int origin = wb_round(position_s * fs + 0.001);
   const double c1 = 2.0 / ratio / fs;
   const double c2 = WB_PI * f0;
+  // The window angle c2 * c1 * (j - hw) is linear in j: one sincos at the thread's first sample (the
+  // reference's expression), then a rotation by blockDim samples per step (<= 32 steps, ~1e-15 drift);
+  // cos(2t) = 2 cos(t)^2 - 1 for the Blackman term (d4c.cpp:266-283).
+  double sd, cd, sn, cs;
+  sincos(c2 * c1 * blockDim.x, &sd, &cd);
+  sincos(c2 * (c1 * ((int)threadIdx.x - hw)), &sn, &cs);
   double s1 = 0.0, s2 = 0.0;
   for (int j = threadIdx.x; j < wlen; j += blockDim.x) {
-    const double position = c1 * (j - hw);
     double w;
-    if (window_type == D4C_HANNING) w = 0.5 * cos(c2 * position) + 0.5;
-    else w = 0.42 + 0.5 * cos(c2 * position) + 0.08 * cos(c2 * position * 2);
+    if (window_type == D4C_HANNING) w = 0.5 * cs + 0.5;
+    else w = 0.42 + 0.5 * cs + 0.08 * (2.0 * cs * cs - 1.0);
     win(j) = w;
     const int idx = wb_min_i(x_length - 1, wb_max_i(0, origin + j - hw));
     const double v = x[idx] * w + noise[j] * WB_SAFEGUARD;
     at(j) = v;
     s1 += v;
     s2 += w;
+    const double c_next = cs * cd - sn * sd;
+    sn = sn * cd + cs * sd;
+    cs = c_next;
   }
   wb_block_sum2(s1, s2, red);
   const double coef = s1 / s2;
@@ -126,79 +134,113 @@ __global__ void __launch_bounds__(256) lt_frame_kernel(LtParams p) {
   if (threadIdx.x == 0) p.ap0[frame] = a / b;
 }
 
-// ---- order statistic: sum of the m smallest of v[0..n) (d4c.cpp:494-499) ---------------------
-// hist: 256 ints, ctl: 4 unsigned long long, red: reduction scratch.  Returns the sum of the m
-// smallest values to all threads.  Values must be non-negative.
-__device__ inline double d4c_sum_smallest(const double *v, int n, int m, int *hist, unsigned long long *ctl,
-                                          double *red) {
-  // MSB-first radix select on the (non-negative) double bit patterns, 8 bits per pass.  As soon
-  // as the bucket that contains the m-th smallest value holds a single element the remaining
-  // passes are skipped: the element is fetched directly.
-  unsigned long long prefix = 0ull, mask = 0ull;
-  if (threadIdx.x == 0) { ctl[1] = (unsigned long long)m; ctl[3] = 0ull; }
+// ---- order statistic: sum of the m smallest of v[0..n) (d4c.cpp:494-499) ----------------------
+// The reference sorts the band power spectrum and takes a cumulative sum; only
+// S[bins - boundary - 2] / S[bins - 1] is used, i.e. (sum of the m smallest) / total.  MSB-first radix
+// select on the (non-negative) double bit patterns, 8 bits per pass; as soon as the bucket holding
+// the m-th smallest value contains a single element the remaining passes are skipped.
+// Two order statistics at once (the two bands of one paired transform): same algorithm as
+// d4c_sum_smallest, histograms / control words doubled, warps 0 and 1 resolve one array each.
+// get(i, w) -> value i of array w.  hist: 512 ints, ctl: 8 words.
+template <typename Get>
+__device__ inline void d4c_sum_smallest2(Get get, int n, int m, bool has_second, int *hist, unsigned long long *ctl,
+                                         double *red, double &low_a, double &low_b) {
+  unsigned long long prefix[2] = {0ull, 0ull}, mask[2] = {0ull, 0ull};
+  bool done[2] = {false, !has_second};
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (tid == 0) { ctl[1] = (unsigned long long)m; ctl[5] = (unsigned long long)m; ctl[3] = 0ull; ctl[7] = 0ull; }
   for (int pass = 0; pass < 8; ++pass) {
+    if (done[0] && done[1]) break;
     const int shift = 56 - 8 * pass;
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    for (int i = tid; i < 512; i += nt) hist[i] = 0;
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const unsigned long long key = (unsigned long long)__double_as_longlong(v[i]);
-      if ((key & mask) == prefix) atomicAdd(&hist[(int)((key >> shift) & 255ull)], 1);
-    }
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      const int lane = threadIdx.x;
-      int c = 0;
+    for (int i = tid; i < n; i += nt) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) c += hist[lane * 8 + q];
-      int incl = c;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-      }
-      const int excl = incl - c;
-      const int remaining = (int)ctl[1];
-      if (remaining > excl && remaining <= incl) {
-        int r = remaining - excl;
-        int d = lane * 8;
-        int hcount = 0;
-        for (int q = 0; q < 8; ++q) {
-          const int h = hist[lane * 8 + q];
-          if (r <= h) { d = lane * 8 + q; hcount = h; break; }
-          r -= h;
+      for (int w = 0; w < 2; ++w) {
+        if (!done[w]) {
+          const unsigned long long key = (unsigned long long)__double_as_longlong(get(i, w));
+          if ((key & mask[w]) == prefix[w]) atomicAdd(&hist[w * 256 + (int)((key >> shift) & 255ull)], 1);
         }
-        ctl[0] = (unsigned long long)d;
-        ctl[2] = (unsigned long long)r;
-        ctl[3] = (hcount == 1) ? 1ull : 0ull;
       }
     }
     __syncthreads();
-    prefix |= ctl[0] << shift;
-    mask |= 255ull << shift;
-    const bool unique = ctl[3] != 0ull;
+    if (tid < 64) {
+      const int w = tid >> 5, lane = tid & 31;
+      if (!done[w]) {  // uniform per warp
+        const int *h = hist + w * 256;
+        unsigned long long *c4 = ctl + w * 4;
+        int c = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) c += h[lane * 8 + q];
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        const int excl = incl - c;
+        const int remaining = (int)c4[1];
+        if (remaining > excl && remaining <= incl) {
+          int r = remaining - excl;
+          int d = lane * 8;
+          int hcount = 0;
+          for (int q = 0; q < 8; ++q) {
+            const int hv = h[lane * 8 + q];
+            if (r <= hv) { d = lane * 8 + q; hcount = hv; break; }
+            r -= hv;
+          }
+          c4[0] = (unsigned long long)d;
+          c4[2] = (unsigned long long)r;
+          c4[3] = (hcount == 1) ? 1ull : 0ull;
+        }
+      }
+    }
     __syncthreads();
-    if (threadIdx.x == 0) ctl[1] = ctl[2];
-    if (unique) {
-      // exactly one element carries this prefix: it is the m-th smallest
-      for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const unsigned long long key = (unsigned long long)__double_as_longlong(v[i]);
-        if ((key & mask) == prefix) ctl[0] = key;
+    bool unique[2] = {false, false};
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      if (!done[w]) {
+        prefix[w] |= ctl[w * 4 + 0] << shift;
+        mask[w] |= 255ull << shift;
+        unique[w] = ctl[w * 4 + 3] != 0ull;
+        if (pass == 7) done[w] = true;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) { ctl[1] = ctl[2]; ctl[5] = ctl[6]; }
+    if ((unique[0] && !done[0]) || (unique[1] && !done[1])) {
+      // exactly one element carries this prefix: fetch it and skip the remaining passes
+      for (int i = tid; i < n; i += nt) {
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          if (unique[w] && !done[w]) {
+            const unsigned long long key = (unsigned long long)__double_as_longlong(get(i, w));
+            if ((key & mask[w]) == prefix[w]) ctl[w * 4 + 0] = key;
+          }
+        }
       }
       __syncthreads();
-      prefix = ctl[0];
+#pragma unroll
+      for (int w = 0; w < 2; ++w)
+        if (unique[w] && !done[w]) { prefix[w] = ctl[w * 4 + 0]; done[w] = true; }
       __syncthreads();
-      break;
     }
   }
-  // prefix is now the bit pattern of the m-th smallest value
-  const double t = __longlong_as_double((long long)prefix);
-  double s = 0.0, cnt = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const double x = v[i];
-    if (x < t) { s += x; cnt += 1.0; }
+  const double ta = __longlong_as_double((long long)prefix[0]);
+  const double tb = __longlong_as_double((long long)prefix[1]);
+  double sa = 0.0, ca = 0.0, sb = 0.0, cb = 0.0;
+  for (int i = tid; i < n; i += nt) {
+    const double va = get(i, 0);
+    if (va < ta) { sa += va; ca += 1.0; }
+    if (has_second) {
+      const double vb = get(i, 1);
+      if (vb < tb) { sb += vb; cb += 1.0; }
+    }
   }
-  wb_block_sum2(s, cnt, red);
-  return s + (m - cnt) * t;
+  wb_block_sum2(sa, ca, red);
+  wb_block_sum2(sb, cb, red);
+  low_a = sa + (m - ca) * ta;
+  low_b = sb + (m - cb) * tb;
 }
 
 // ---- body (d4c.cpp:308-503 + :155-168) -------------------------------------------------------
@@ -233,9 +275,9 @@ __global__ void __launch_bounds__(D4C_BODY_THREADS, 2) d4c_body_kernel(BodyParam
   double *SC = reinterpret_cast<double *>(S + wb_fft_slots(N));
   double *SP = SC + binsp;
   double *red = SP + binsp;                                       // 320
-  int *hist = reinterpret_cast<int *>(red + 320);                 // 256 ints
-  unsigned long long *ctl = reinterpret_cast<unsigned long long *>(hist + 256);  // 4
-  double *coarse = reinterpret_cast<double *>(ctl + 4);           // D4C_MAX_AP + 2
+  int *hist = reinterpret_cast<int *>(red + 320);                 // 2 x 256 ints
+  unsigned long long *ctl = reinterpret_cast<unsigned long long *>(hist + 512);  // 2 x 4
+  double *coarse = reinterpret_cast<double *>(ctl + 8);           // D4C_MAX_AP + 2
   double *W = reinterpret_cast<double *>(S);
   double *seg = W;                                                // 2 * slots(N) doubles available
   const int seg_capacity = 2 * wb_fft_slots(N);
@@ -310,24 +352,51 @@ __global__ void __launch_bounds__(D4C_BODY_THREADS, 2) d4c_body_kernel(BodyParam
   const int wl = p.window_length, hwl = wl / 2;
   const int boundary = wb_round(N * 8.0 / wl);
   const int m_small = bins - boundary - 1;  // cumulative-sum index bins - boundary - 2
-  for (int b = 0; b < p.n_ap; ++b) {
-    const int center = static_cast<int>(WB_FREQ_INTERVAL * (b + 1) * N / fs);
-    for (int j = tid; j < N; j += nt)
-      W[wb_didx(j)] = (j < wl) ? SC[center - hwl + j] * __ldg(&p.nuttall[j]) : 0.0;
+  // Bands are transformed in pairs: band b in the real part, band b+1 in the imaginary part of ONE
+  // complex N-point transform (both are real, so the spectra separate exactly); the two power
+  // spectra are left interleaved in the FFT slots and both order statistics are resolved together.
+  for (int b = 0; b < p.n_ap; b += 2) {
+    const bool has2 = (b + 1 < p.n_ap);
+    const int center_a = static_cast<int>(WB_FREQ_INTERVAL * (b + 1) * N / fs);
+    const int center_b = static_cast<int>(WB_FREQ_INTERVAL * (b + 2) * N / fs);
+    for (int j = tid; j < N; j += nt) {
+      cplx z = make_double2(0.0, 0.0);
+      if (j < wl) {
+        const double nw = __ldg(&p.nuttall[j]);
+        z.x = SC[center_a - hwl + j] * nw;
+        if (has2) z.y = SC[center_b - hwl + j] * nw;
+      }
+      S[wb_sidx(j)] = z;
+    }
     __syncthreads();
-    double tot = 0.0;
-    wb_rfft_t<1, LOG2N - 1>(S, p.tw_n, [&](int k, cplx X) {
-      const double pw = X.x * X.x + X.y * X.y;
-      SP[k] = pw;
-      tot += pw;
-    });
-    const double total = wb_block_sum(tot, red);
-    const double low = d4c_sum_smallest(SP, bins, m_small, hist, ctl, red);
+    wb_cfft_dif_t<1, LOG2N>(S, p.tw_2n);
+    double tot_a = 0.0, tot_b = 0.0;
+    for (int k = tid; k <= NC; k += nt) {
+      const int slot = wb_sidx(wb_brev(k, log2n));
+      const cplx zk = S[slot];
+      const cplx zc = S[wb_sidx(wb_brev((N - k) & (N - 1), log2n))];
+      const double ar = 0.5 * (zk.x + zc.x), ai = 0.5 * (zk.y - zc.y);   // spectrum of band b
+      const double br = 0.5 * (zk.y + zc.y), bi = -0.5 * (zk.x - zc.x);  // spectrum of band b+1
+      const double pa = ar * ar + ai * ai, pb = br * br + bi * bi;
+      // slots of indices > NC are only read (by the thread that owns N - k), never written: in-place is safe
+      S[slot] = make_double2(pa, pb);
+      tot_a += pa;
+      tot_b += pb;
+    }
+    wb_block_sum2(tot_a, tot_b, red);
+    double low_a, low_b;
+    d4c_sum_smallest2([&](int i, int w) { const cplx v = S[wb_sidx(wb_brev(i, log2n))]; return w == 0 ? v.x : v.y; },
+                      bins, m_small, has2, hist, ctl, red, low_a, low_b);
     if (tid == 0) {
-      double ca = 10 * log10(low / total);
       const double rev = (f0 - 100) / 50.0;  // d4c.cpp:325-327
+      double ca = 10 * log10(low_a / tot_a);
       ca = ca + rev;
       coarse[b + 1] = ca < 0.0 ? ca : 0.0;
+      if (has2) {
+        double cb = 10 * log10(low_b / tot_b);
+        cb = cb + rev;
+        coarse[b + 2] = cb < 0.0 ? cb : 0.0;
+      }
     }
     __syncthreads();
   }
@@ -462,7 +531,7 @@ int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int
     p.error_flag = ws->error_flag();
     const int binsp = ((N / 2 + 1) + 1) & ~1;
     const size_t smem = sizeof(cplx) * wb_fft_slots(N) + sizeof(double) * (2 * binsp + 320) +
-                        sizeof(int) * 256 + sizeof(unsigned long long) * 4 + sizeof(double) * (D4C_MAX_AP + 2);
+                        sizeof(int) * 512 + sizeof(unsigned long long) * 8 + sizeof(double) * (D4C_MAX_AP + 2);
     rc = WB_DISPATCH_LOG2(l, 9, 13, {
       if (cudaFuncSetAttribute(d4c_body_kernel<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WB_ERR_CUDA;
       WB_LAUNCH("d4c_body_kernel", d4c_body_kernel<L2><<<f0_length, D4C_BODY_THREADS, smem, stream>>>(p));

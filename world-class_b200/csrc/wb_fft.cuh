@@ -7,8 +7,8 @@
 //   everything unnormalised (c2r(r2c(x)) = N x).
 //
 // Layout.  A complex FFT of N points lives in N (+ padding) double2 slots of shared memory.
-// Slot padding sidx(i) = i + (i >> 3) makes every pass bank-conflict free for 16-byte
-// accesses.  Passes are radix-8 (plus one radix-4/2 clean-up) butterflies held in registers;
+// Slot padding sidx(i) = i + (i >> 3) + (i >> 6) + (i >> 9) makes every pass and the
+// bit-reversed reads of the real-transform split step bank-conflict free for 16-byte accesses.  Passes are radix-8 (plus one radix-4/2 clean-up) butterflies held in registers;
 // the decimation-in-frequency (DIF) transform reads natural order and leaves BIT-REVERSED
 // order, the decimation-in-time (DIT) transform reads bit-reversed order and leaves natural
 // order, so forward -> pointwise -> inverse chains need no reordering pass.  Twiddles come
@@ -21,9 +21,12 @@
 #pragma once
 #include "wb_common.cuh"
 
-__device__ __forceinline__ int wb_sidx(int i) { return i + (i >> 3); }
+// Three-level padding: +1 slot per 8, per 64 and per 512 elements.  The first level keeps the
+// small-stride butterfly passes conflict free, the other two spread the bit-reversed access
+// pattern of the real-transform split step (lanes hit slots N/32 apart) over all banks.
+__device__ __forceinline__ int wb_sidx(int i) { return i + (i >> 3) + (i >> 6) + (i >> 9); }
 // number of double2 slots needed for an NC-point complex FFT
-__host__ __device__ __forceinline__ int wb_fft_slots(int nc) { return nc + (nc >> 3) + 1; }
+__host__ __device__ __forceinline__ int wb_fft_slots(int nc) { return nc + (nc >> 3) + (nc >> 6) + (nc >> 9) + 1; }
 // position (in doubles) of real sample j when a real sequence is packed as z[n] = x[2n] + i x[2n+1]
 __device__ __forceinline__ int wb_didx(int j) { return 2 * wb_sidx(j >> 1) + (j & 1); }
 
@@ -81,9 +84,10 @@ __device__ __forceinline__ void wb_dft4(cplx (&a)[4]) {
   a[1] = wb_cadd(b2, b3); a[3] = wb_csub(b2, b3);
 }
 
-// padded offset of element (base + q * m) relative to sidx(base); valid because base mod 8 < m
-// whenever m < 8 (see header comment)
-#define WB_OFF(q, m) ((q) * (m) + (((q) * (m)) >> 3))
+// padded offset of element (base + q * m) relative to sidx(base): the three shift terms separate
+// because base = M * block + j with j < m = M / 8, so (base mod 2^s) + (q m mod 2^s) never carries
+// for s = 3, 6, 9 (for M <= 2^s the whole sub-block lies inside one 2^s-aligned group).
+#define WB_OFF(q, m) ((q) * (m) + (((q) * (m)) >> 3) + (((q) * (m)) >> 6) + (((q) * (m)) >> 9))
 
 // twiddles w^1..w^7 of one radix-8 butterfly from three table loads
 template <int SIGN>
