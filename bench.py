@@ -157,6 +157,7 @@ def main():
     copt = wb.CheapTrickOption(f0_floor=71.0)                             # test/test.cpp:130
     dopt = wb.D4COption(threshold=0.85)                                   # test/test.cpp:181
     pl = wb.Pipeline(FS, hopt, copt, dopt)
+    pl.set_graph(True)   # the ~45 launches of one step are replayed as one CUDA graph
     n = len(x_host)
     L, ny, fft_size = pl.f0_length(n), pl.out_length(n), pl.fft_size
     bins = fft_size // 2 + 1

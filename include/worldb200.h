@@ -156,6 +156,9 @@ void wb_pipeline_destroy(wb_pipeline_t *p);
 /* fresh != 0: every run restarts its own randn() stream at the reference's seed (one utterance ==
  * one reference process); such pipelines may run concurrently on different streams (batches). */
 int wb_pipeline_set_fresh_rng(wb_pipeline_t *p, int fresh);
+/* use_graph != 0: repeated wb_pipeline_run_dev calls with identical arguments replay a captured CUDA
+ * graph (one launch for the whole chain).  The internal buffers are used unless all outputs are given. */
+int wb_pipeline_set_graph(wb_pipeline_t *p, int use_graph);
 int wb_pipeline_fft_size(const wb_pipeline_t *p);
 int wb_pipeline_f0_length(const wb_pipeline_t *p, int x_length);      /* src/harvest.cpp:173-181 */
 int wb_pipeline_out_length(const wb_pipeline_t *p, int x_length);     /* test/test.cpp:362-363 */

@@ -100,6 +100,7 @@ def _declare(L):
                                     ctypes.POINTER(D4COption), ctypes.POINTER(vp)]),
         "wb_pipeline_destroy": (None, [vp]),
         "wb_pipeline_set_fresh_rng": (ci, [vp, ci]),
+        "wb_pipeline_set_graph": (ci, [vp, ci]),
         "wb_pipeline_fft_size": (ci, [vp]),
         "wb_pipeline_f0_length": (ci, [vp, ci]),
         "wb_pipeline_out_length": (ci, [vp, ci]),
@@ -352,6 +353,10 @@ class Pipeline:
     def set_fresh_rng(self, fresh=True):
         """Batch mode: every run starts its own randn() stream at the reference's seed."""
         _check(lib().wb_pipeline_set_fresh_rng(self._h, 1 if fresh else 0), "wb_pipeline_set_fresh_rng")
+
+    def set_graph(self, use_graph=True):
+        """Replay a captured CUDA graph for repeated run_dev calls with identical arguments."""
+        _check(lib().wb_pipeline_set_graph(self._h, 1 if use_graph else 0), "wb_pipeline_set_graph")
 
     def f0_length(self, x_length):
         return lib().wb_pipeline_f0_length(self._h, int(x_length))

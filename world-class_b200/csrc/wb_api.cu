@@ -128,6 +128,13 @@ struct wb_pipeline {
   WbWorkspace ws;
   cudaStream_t side = nullptr;       // Synthesis time base overlaps CheapTrick / D4C here
   cudaEvent_t ev_f0 = nullptr, ev_tb = nullptr;
+  // CUDA graph of one whole run (captured after a warm run with the same arguments)
+  bool use_graph = false;
+  cudaGraphExec_t graph_exec = nullptr;
+  unsigned long long graph_kernels = 0;
+  const void *graph_key[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int graph_len[2] = {0, 0};
+  int warm_len[2] = {0, 0};
   bool private_rng = false;          // batch mode: every run starts from the reference's seed
   WbRngState *d_rng_private = nullptr;
   WbRngState *d_rng_seed = nullptr;
@@ -137,6 +144,7 @@ struct wb_pipeline {
     if (side) cudaStreamDestroy(side);
     if (d_rng_private) cudaFree(d_rng_private);
     if (d_rng_seed) cudaFree(d_rng_seed);
+    if (graph_exec) cudaGraphExecDestroy(graph_exec);
   }
 };
 
@@ -536,10 +544,63 @@ int wb_pipeline_out_length(const wb_pipeline_t *p, int x_length) {  // test/test
   return static_cast<int>((f0_length - 1) * p->plan.opt.frame_period / 1000.0 * p->fs) + 1;
 }
 
+static int pipeline_enqueue(wb_pipeline_t *p, const double *d_x, int x_length, double *d_tpos, double *d_f0,
+                            double *d_sp, double *d_ap, double *d_y, int y_length, cudaStream_t st);
+
+/* use_graph != 0: after one ordinary run with a given set of arguments, the next run with the same
+ * arguments is captured into a CUDA graph and later runs replay it (one launch instead of ~45). */
+int wb_pipeline_set_graph(wb_pipeline_t *p, int use_graph) {
+  if (!p) return WB_ERR_ARG;
+  p->use_graph = use_graph != 0;
+  return WB_OK;
+}
+
 int wb_pipeline_run_dev(wb_pipeline_t *p, const double *d_x, int x_length, double *d_tpos, double *d_f0,
                         double *d_sp, double *d_ap, double *d_y, int y_length, void *stream) {
   if (!p || !d_x || x_length <= 0 || y_length < 0) return WB_ERR_ARG;
   cudaStream_t st = pick_stream(stream);
+  if (!p->use_graph || wb_prof_is_enabled())
+    return pipeline_enqueue(p, d_x, x_length, d_tpos, d_f0, d_sp, d_ap, d_y, y_length, st);
+  const void *key[8] = {d_x, d_tpos, d_f0, d_sp, d_ap, d_y, (const void *)st, nullptr};
+  const bool same = p->graph_exec && memcmp(key, p->graph_key, sizeof(key)) == 0 && p->graph_len[0] == x_length &&
+                    p->graph_len[1] == y_length;
+  if (same) {
+    WB_CUDA_CHECK(cudaGraphLaunch(p->graph_exec, st));
+    wb_launch_counter_add(p->graph_kernels);
+    return WB_OK;
+  }
+  if (p->warm_len[0] != x_length || p->warm_len[1] != y_length) {
+    // first run with these sizes: ordinary enqueue (allocations, plan-time tables, lazy initialisation)
+    int rc = pipeline_enqueue(p, d_x, x_length, d_tpos, d_f0, d_sp, d_ap, d_y, y_length, st);
+    if (!rc) { p->warm_len[0] = x_length; p->warm_len[1] = y_length; }
+    return rc;
+  }
+  if (p->graph_exec) { cudaGraphExecDestroy(p->graph_exec); p->graph_exec = nullptr; }
+  const unsigned long long k0 = wb_launch_counter();
+  WB_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  int rc = pipeline_enqueue(p, d_x, x_length, d_tpos, d_f0, d_sp, d_ap, d_y, y_length, st);
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamEndCapture(st, &graph);
+  if (rc || e != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    if (rc) return rc;
+    // capture not possible: fall back to ordinary launches from now on
+    p->use_graph = false;
+    return pipeline_enqueue(p, d_x, x_length, d_tpos, d_f0, d_sp, d_ap, d_y, y_length, st);
+  }
+  p->graph_kernels = wb_launch_counter() - k0;
+  e = cudaGraphInstantiate(&p->graph_exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) { p->graph_exec = nullptr; p->use_graph = false; cudaGetLastError(); return pipeline_enqueue(p, d_x, x_length, d_tpos, d_f0, d_sp, d_ap, d_y, y_length, st); }
+  memcpy(p->graph_key, key, sizeof(key));
+  p->graph_len[0] = x_length; p->graph_len[1] = y_length;
+  WB_CUDA_CHECK(cudaGraphLaunch(p->graph_exec, st));
+  return WB_OK;
+}
+
+static int pipeline_enqueue(wb_pipeline_t *p, const double *d_x, int x_length, double *d_tpos, double *d_f0,
+                            double *d_sp, double *d_ap, double *d_y, int y_length, cudaStream_t st) {
   const int fs = p->fs;
   const double fp = p->plan.opt.frame_period;
   const int f0_length = wb_pipeline_f0_length(p, x_length);

@@ -133,6 +133,8 @@ struct WbLaunchScope {
     __VA_ARGS__;                           \
   } while (0)
 unsigned long long wb_launch_counter();
+void wb_launch_counter_add(unsigned long long n);  // kernels replayed through a CUDA graph
+int wb_prof_is_enabled();
 void wb_prof_set_enabled(int on);
 // synchronises the device, folds all pending event pairs into per-name totals
 int wb_prof_collect();

@@ -79,6 +79,38 @@ __device__ __forceinline__ double dec_tmp1(const double *__restrict__ x, int x_l
 #define DEC_TILE (DEC_THREADS * DEC_CHUNK)
 __device__ __forceinline__ int dec_pad(int r) { return r + (r / DEC_CHUNK); }
 
+// Look-ahead form of the warm-up of w[t] = x[t] + a0 w[t-1] + a1 w[t-2] + a2 w[t-3]: four samples
+// per step of the dependency chain (only the state matters during warm-up, so the different
+// rounding is irrelevant; the DEC_CHUNK output samples use the reference's own operation order).
+struct DecLook {
+  double h1, h2, h3;         // impulse response h_0 = 1, h_1.., of the recursive part
+  double m2[3], m3[3], m4[3];  // first rows of M^2, M^3, M^4 (M = companion matrix)
+};
+__device__ __forceinline__ DecLook dec_look_init(const DecimCoef &c) {
+  DecLook L;
+  const double a0 = c.a[0], a1 = c.a[1], a2 = c.a[2];
+  // rows r_k = first row of M^k: r_1 = (a0, a1, a2); r_{k+1} = r_k M
+  double r[3] = {a0, a1, a2};
+  L.h1 = a0;
+  double r2[3] = {r[0] * a0 + r[1], r[0] * a1 + r[2], r[0] * a2};
+  L.h2 = r2[0];
+  double r3[3] = {r2[0] * a0 + r2[1], r2[0] * a1 + r2[2], r2[0] * a2};
+  L.h3 = r3[0];
+  double r4[3] = {r3[0] * a0 + r3[1], r3[0] * a1 + r3[2], r3[0] * a2};
+  for (int k = 0; k < 3; ++k) { L.m2[k] = r2[k]; L.m3[k] = r3[k]; L.m4[k] = r4[k]; }
+  return L;
+}
+__device__ __forceinline__ void dec_look_step(const DecLook &L, double x1, double x2, double x3, double x4,
+                                              double &w0, double &w1, double &w2) {
+  const double f2 = fma(L.h1, x1, x2);
+  const double f3 = fma(L.h2, x1, fma(L.h1, x2, x3));
+  const double f4 = fma(L.h3, x1, fma(L.h2, x2, fma(L.h1, x3, x4)));
+  const double n2 = fma(L.m2[0], w0, fma(L.m2[1], w1, fma(L.m2[2], w2, f2)));
+  const double n1 = fma(L.m3[0], w0, fma(L.m3[1], w1, fma(L.m3[2], w2, f3)));
+  const double n0 = fma(L.m4[0], w0, fma(L.m4[1], w1, fma(L.m4[2], w2, f4)));
+  w0 = n0; w1 = n1; w2 = n2;
+}
+
 // forward pass: out[i] = FilterForDecimate(tmp1)[i], i in [0, len2)
 __global__ void __launch_bounds__(DEC_THREADS) dec_forward_kernel(const double *__restrict__ x, int x_length, int lag,
                                                                   int len1, int len2, DecimCoef c,
@@ -97,7 +129,12 @@ __global__ void __launch_bounds__(DEC_THREADS) dec_forward_kernel(const double *
   if (begin < len2) {
     const int end = min(len2, begin + DEC_CHUNK);
     double w0 = 0.0, w1 = 0.0, w2 = 0.0;
-    for (int i = max(0, begin - DEC_WARM); i < end; ++i) {
+    const DecLook look = dec_look_init(c);
+    int i = max(0, begin - DEC_WARM);
+    for (; i + 4 <= begin; i += 4)
+      dec_look_step(look, s_in[dec_pad(i - in_begin)], s_in[dec_pad(i + 1 - in_begin)], s_in[dec_pad(i + 2 - in_begin)],
+                    s_in[dec_pad(i + 3 - in_begin)], w0, w1, w2);
+    for (; i < end; ++i) {
       const double xi = s_in[dec_pad(i - in_begin)];
       const double wt = xi + c.a[0] * w0 + c.a[1] * w1 + c.a[2] * w2;
       if (i >= begin) s_out[dec_pad(i - tile_begin)] = c.b[0] * wt + c.b[1] * w0 + c.b[1] * w1 + c.b[0] * w2;
@@ -133,7 +170,12 @@ __global__ void __launch_bounds__(DEC_THREADS) dec_backward_kernel(const double 
   const int nout = len1 / r + 1;
   const int nbeg = r - r * nout + len1;
   double w0 = 0.0, w1 = 0.0, w2 = 0.0;
-  for (int u = max(0, begin - DEC_WARM); u < end; ++u) {
+  const DecLook look = dec_look_init(c);
+  int u = max(0, begin - DEC_WARM);
+  for (; u + 4 <= begin; u += 4)
+    dec_look_step(look, s_in[dec_pad(u - in_begin)], s_in[dec_pad(u + 1 - in_begin)], s_in[dec_pad(u + 2 - in_begin)],
+                  s_in[dec_pad(u + 3 - in_begin)], w0, w1, w2);
+  for (; u < end; ++u) {
     const double xi = s_in[dec_pad(u - in_begin)];
     const double wt = xi + c.a[0] * w0 + c.a[1] * w1 + c.a[2] * w2;
     if (u >= begin) {

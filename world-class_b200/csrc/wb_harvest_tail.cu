@@ -23,7 +23,7 @@ namespace {
 #define TL_THREADS 512
 #define TL_MARGIN 104
 #define TL_LAG 300
-#define TL_CHUNK 64
+#define TL_CHUNK 31   // odd: the per-thread stride stays bank-conflict free in shared memory
 
 struct TailParams {
   const double *cand; const double *score; const int *nc; int L; int MC;
@@ -38,6 +38,9 @@ struct TailParams {
   int *order;          // maxsec
   double *pad;         // L + 2*TL_LAG
   double *fw; long long fw_cap;
+  double *gA, *gB;     // global fallbacks of the two contour buffers (L + 2*TL_LAG each)
+  int smem_doubles;    // dynamic shared memory available to the kernel
+  long long *clocks;   // [16] phase time stamps (clock64 of thread 0), for profiling the serial tail
   int *error_flag;
 };
 
@@ -97,7 +100,31 @@ __device__ __forceinline__ double tl_select_best(double reference_f0, const doub
   return best_idx >= 0 ? cands[best_idx] : 0.0;
 }
 
-// selectBestF0 on a candidate row already held in registers (lane l: entries l and l + 32)
+// selectBestF0 on a candidate row held in registers (lane l: entries l and l + 32), resolved with
+// warp reductions instead of a shuffle tree: fl(d / ref) is monotone in d, so the candidate with the
+// smallest |ref - c| (the LAST one among equal distances) is the reference's choice, and one
+// division at the end reproduces its `tmp > best_error` test against allowed_range.
+__device__ __forceinline__ double tl_select_best_fast(double reference_f0, double c0, double c1, int n, double allowed) {
+  const int lane = threadIdx.x & 31;
+  const double inf = __longlong_as_double(0x7ff0000000000000LL);
+  const double d0 = (lane < n) ? fabs(reference_f0 - c0) : inf;
+  const double d1 = (lane + 32 < n) ? fabs(reference_f0 - c1) : inf;
+  double dl = d0, vl = c0;
+  int il = lane;
+  if (lane + 32 < n && d1 <= d0) { dl = d1; vl = c1; il = lane + 32; }
+  const unsigned long long key = (unsigned long long)__double_as_longlong(dl);  // dl >= 0 or +inf (NaN sorts last)
+  const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+  const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+  const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+  const int mi = __reduce_max_sync(0xffffffffu, (hi == mh && lo == ml) ? il : -1);
+  if (mi < 0) return 0.0;
+  const double v = __shfl_sync(0xffffffffu, vl, mi & 31);
+  const double dmin = __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
+  const double err = dmin / reference_f0;
+  return (err > allowed) ? 0.0 : v;
+}
+
+// (shuffle-tree version, kept for reference / wide tables)
 __device__ __forceinline__ double tl_select_best_reg(double reference_f0, double c0, double c1, int n, double allowed) {
   const int lane = threadIdx.x & 31;
   double best_err = allowed, best_val = 0.0;
@@ -152,8 +179,9 @@ __device__ int tl_extend_f0(const TailParams &p, int s, int origin, int last_poi
     __syncwarp();
     return shifted_origin;
   }
-  for (int i0 = 0; i0 <= distance && !stop; i0 += TL_PF) {
-    double c0[TL_PF], c1[TL_PF];
+  // software pipeline: the rows of batch k+1 are in flight while batch k is resolved
+  double n0[TL_PF], n1[TL_PF];
+  auto load_batch = [&](int i0, double (&c0)[TL_PF], double (&c1)[TL_PF]) {
 #pragma unroll
     for (int k = 0; k < TL_PF; ++k) {
       const int i = i0 + k;
@@ -164,12 +192,19 @@ __device__ int tl_extend_f0(const TailParams &p, int s, int origin, int last_poi
         if (lane + 32 < n) c1[k] = row[lane + 32];
       }
     }
+  };
+  load_batch(0, n0, n1);
+  for (int i0 = 0; i0 <= distance && !stop; i0 += TL_PF) {
+    double c0[TL_PF], c1[TL_PF];
+#pragma unroll
+    for (int k = 0; k < TL_PF; ++k) { c0[k] = n0[k]; c1[k] = n1[k]; }
+    if (i0 + TL_PF <= distance) load_batch(i0 + TL_PF, n0, n1);
 #pragma unroll
     for (int k = 0; k < TL_PF; ++k) {
       const int i = i0 + k;
       if (i <= distance && !stop) {
         const int pos = origin + shift * i + shift;
-        const double v = tl_select_best_reg(tmp_f0, c0[k], c1[k], n, 0.18);
+        const double v = tl_select_best_fast(tmp_f0, c0[k], c1[k], n, 0.18);
         if (lane == 0) f[pos] = v;
         if (v == 0.0) {
           count++;
@@ -241,41 +276,60 @@ __device__ void tl_exclusive_scan(const int *v, int n, int *out, int *s_scan) {
 }
 
 __global__ void __launch_bounds__(TL_THREADS) harvest_tail_kernel(TailParams p) {
+  extern __shared__ double tl_smem[];   // p.smem_doubles doubles: contour buffers A | B (later: forward-filter scratch)
   __shared__ int s_scan[TL_THREADS];
   __shared__ double s_red[64];
   __shared__ int s_i[8];
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
   const int L = p.L, MC = p.MC;
   const int nc7 = *p.nc * 7;
+  const int Lp_cap = L + 2 * TL_LAG;
+  // Two contour buffers A and B (padded length each) live in shared memory when they fit (10 s of
+  // audio at 1 ms: 2 x 85 KB), otherwise in global scratch.  During smoothing only A (the padded
+  // contour) is live and everything above it is forward-filter scratch.
+  const bool two_ok = p.smem_doubles >= 2 * Lp_cap;
+  double *cA = two_ok ? tl_smem : p.gA;
+  double *cB = two_ok ? tl_smem + Lp_cap : p.gB;
+  double *fw_smem = tl_smem + Lp_cap;
+  const long long fw_smem_cap = two_ok ? (long long)p.smem_doubles - Lp_cap : 0;
+  int clk_i = 0;
+#define TL_STAMP() do { if (tid == 0) p.clocks[clk_i] = clock64(); ++clk_i; } while (0)
+  TL_STAMP();  // 0: start
 
   // ---- fixStep1 (searchF0Base ran in search_base_kernel)
+  for (int i = tid; i < L; i += nt) cA[i] = p.base[i];
+  __syncthreads();
   for (int i = tid; i < L; i += nt) {
     double v = 0.0;  // entries the reference leaves unwritten read as 0 (zero-filled heap)
-    if (i >= 2 && p.base[i] != 0.0) {
-      const double reference_f0 = p.base[i - 1] * 2 - p.base[i - 2];
-      v = (fabs((p.base[i] - reference_f0) / reference_f0) > 0.008 &&
-           fabs((p.base[i] - p.base[i - 1])) / p.base[i - 1] > 0.008) ? 0.0 : p.base[i];
+    const double b0v = cA[i];
+    if (i >= 2 && b0v != 0.0) {
+      const double b1v = cA[i - 1], b2v = cA[i - 2];
+      const double reference_f0 = b1v * 2 - b2v;
+      v = (fabs((b0v - reference_f0) / reference_f0) > 0.008 && fabs((b0v - b1v)) / b1v > 0.008) ? 0.0 : b0v;
     }
+    cB[i] = v;
     p.s1[i] = v;
-    p.s2[i] = v;
   }
   __syncthreads();
 
-  // ---- fixStep2: drop voiced sections shorter than 6
+  TL_STAMP();  // 1: after fixStep1
+  // ---- fixStep2: drop voiced sections shorter than 6 (in place: the boundary list is extracted first)
   {
-    const int nb = tl_boundaries(p.s1, L, p.blist, s_scan);
+    const int nb = tl_boundaries(cB, L, p.blist, s_scan);
     for (int k = tid; k < nb / 2; k += nt) {
       const int st = p.blist[2 * k], ed = p.blist[2 * k + 1];
       if (ed - st >= 6) continue;
-      for (int j = st; j <= ed; ++j) p.s2[j] = 0.0;
+      for (int j = st; j <= ed; ++j) cB[j] = 0.0;
     }
     __syncthreads();
+    for (int i = tid; i < L; i += nt) p.s2[i] = cB[i];
   }
 
+  TL_STAMP();  // 2: after fixStep2
   // ---- fixStep3
   int nsec;
   {
-    const int nb = tl_boundaries(p.s2, L, p.blist, s_scan);
+    const int nb = tl_boundaries(cB, L, p.blist, s_scan);
     nsec = nb / 2;
     if (nsec > p.maxsec) {
       if (tid == 0) atomicExch(p.error_flag, WB_ERR_UNSUPPORTED);
@@ -307,10 +361,11 @@ __global__ void __launch_bounds__(TL_THREADS) harvest_tail_kernel(TailParams p) 
     const int st = p.sec_st[s], ed = p.sec_ed[s], lo = p.sec_lo[s], len = p.sec_len[s], off = p.sec_off[s];
     for (int j = tid; j < len; j += nt) {
       const int i = lo + j;
-      p.secbuf[off + j] = (i >= st && i <= ed) ? p.s2[i] : 0.0;
+      p.secbuf[off + j] = (i >= st && i <= ed) ? cB[i] : 0.0;
     }
   }
   __syncthreads();
+  TL_STAMP();  // 3: sections materialised
   // extend (forward first, then backward) + per-section sums for extendSub
   for (int s = warp; s < nsec; s += nwarps) {
     const int ed0 = p.sec_ed[s], st0 = p.sec_st[s];
@@ -323,6 +378,7 @@ __global__ void __launch_bounds__(TL_THREADS) harvest_tail_kernel(TailParams p) 
     if (lane == 0) { p.sec_st[s] = st1; p.sec_ed[s] = ed1; p.sec_sum[s] = acc; }
   }
   __syncthreads();
+  TL_STAMP();  // 4: after extend
   // extendSub (harvest.cpp:443-455); mean_f0 is carried across sections
   if (tid == 0) {
     const double threshold2 = 2200.0;
@@ -350,10 +406,11 @@ __global__ void __launch_bounds__(TL_THREADS) harvest_tail_kernel(TailParams p) 
   }
   __syncthreads();
   const int nkeep = s_i[1];
+  TL_STAMP();  // 5: after extendSub + sort
   // mergeF0 (harvest.cpp:502-536)
   {
     const int s0 = p.kslot[0];
-    for (int i = tid; i < L; i += nt) p.s3[i] = tl_getsec(p, s0, i);
+    for (int i = tid; i < L; i += nt) cA[i] = tl_getsec(p, s0, i);
     __syncthreads();
     for (int it = 1; it < nkeep; ++it) {
       const int o = p.order[it];
@@ -362,52 +419,57 @@ __global__ void __launch_bounds__(TL_THREADS) harvest_tail_kernel(TailParams p) 
       const int st1 = p.kb[0], ed1 = p.kb[1];
       int new_b0 = st1, new_b1 = ed1;
       if (index1 - ed1 > 0) {
-        for (int i = index1 + tid; i <= index2; i += nt) p.s3[i] = tl_getsec(p, so, i);
+        for (int i = index1 + tid; i <= index2; i += nt) cA[i] = tl_getsec(p, so, i);
         new_b0 = index1; new_b1 = index2;
       } else if (!(st1 <= index1 && ed1 >= index2)) {
         // mergeF0Sub
         double sc1 = 0.0, sc2 = 0.0;
         for (int i = index1 + tid; i <= ed1; i += nt) {
           const double *c = p.cand + (size_t)i * MC, *sc = p.score + (size_t)i * MC;
-          sc1 += tl_search_score(p.s3[i], c, sc, nc7);
+          sc1 += tl_search_score(cA[i], c, sc, nc7);
           sc2 += tl_search_score(tl_getsec(p, so, i), c, sc, nc7);
         }
         wb_block_sum2(sc1, sc2, s_red);
         __syncthreads();
-        if (sc1 > sc2) { for (int i = ed1 + tid; i <= index2; i += nt) p.s3[i] = tl_getsec(p, so, i); }
-        else { for (int i = index1 + tid; i <= index2; i += nt) p.s3[i] = tl_getsec(p, so, i); }
+        if (sc1 > sc2) { for (int i = ed1 + tid; i <= index2; i += nt) cA[i] = tl_getsec(p, so, i); }
+        else { for (int i = index1 + tid; i <= index2; i += nt) cA[i] = tl_getsec(p, so, i); }
         new_b1 = index2;
       }
       __syncthreads();
       if (tid == 0) { p.kb[0] = new_b0; p.kb[1] = new_b1; }
       __syncthreads();
     }
+    for (int i = tid; i < L; i += nt) p.s3[i] = cA[i];
   }
 
+  TL_STAMP();  // 6: after merge
   // ---- fixStep4: bridge unvoiced gaps shorter than 9
-  for (int i = tid; i < L; i += nt) p.s4[i] = p.s3[i];
+  for (int i = tid; i < L; i += nt) cB[i] = cA[i];
   __syncthreads();
   {
-    const int nb = tl_boundaries(p.s3, L, p.blist, s_scan);
+    const int nb = tl_boundaries(cA, L, p.blist, s_scan);
     for (int g = tid; g < nb / 2 - 1; g += nt) {
       const int ed = p.blist[2 * g + 1], st_next = p.blist[2 * (g + 1)];
       const int distance = st_next - ed - 1;
       if (distance >= 9) continue;
-      const double tmp0 = p.s3[ed] + 1;
-      const double tmp1 = p.s3[st_next] - 1;
+      const double tmp0 = cA[ed] + 1;
+      const double tmp1 = cA[st_next] - 1;
       const double coefficient = (tmp1 - tmp0) / (distance + 1.0);
       int count = 1;
-      for (int j = ed + 1; j <= st_next - 1; ++j) p.s4[j] = tmp0 + coefficient * count++;
+      for (int j = ed + 1; j <= st_next - 1; ++j) cB[j] = tmp0 + coefficient * count++;
     }
     __syncthreads();
+    for (int i = tid; i < L; i += nt) p.s4[i] = cB[i];
   }
 
+  TL_STAMP();  // 7: after fixStep4
   // ---- smoothF0Contour
   const int Lp = L + 2 * TL_LAG;
-  for (int i = tid; i < Lp; i += nt) p.pad[i] = (i >= TL_LAG && i < TL_LAG + L) ? p.s4[i - TL_LAG] : 0.0;
+  double *pad = cA;
+  for (int i = tid; i < Lp; i += nt) pad[i] = (i >= TL_LAG && i < TL_LAG + L) ? cB[i - TL_LAG] : 0.0;
   for (int i = tid; i < L; i += nt) p.out[i] = 0.0;
   __syncthreads();
-  const int nbs = tl_boundaries(p.pad, Lp, p.blist, s_scan);
+  const int nbs = tl_boundaries(pad, Lp, p.blist, s_scan);
   const int nsm = nbs / 2;
   if (nsm > p.maxsec) {
     if (tid == 0) atomicExch(p.error_flag, WB_ERR_UNSUPPORTED);
@@ -428,6 +490,7 @@ __global__ void __launch_bounds__(TL_THREADS) harvest_tail_kernel(TailParams p) 
     p.sec_lo[nsm] = items;
     s_i[2] = items;
     s_i[3] = (off > p.fw_cap) ? 1 : 0;
+    s_i[5] = (off <= fw_smem_cap) ? 1 : 0;  // forward outputs fit in shared memory
   }
   __syncthreads();
   if (s_i[3]) {
@@ -436,7 +499,11 @@ __global__ void __launch_bounds__(TL_THREADS) harvest_tail_kernel(TailParams p) 
   }
   const double b0 = 0.0078202080334971724, b1 = 0.015640416066994345;
   const double a0 = 1.7347257688092754, a1 = -0.76600660094326412;
+  // impulse response of 1 / (1 - a0 z^-1 - a1 z^-2) for the look-ahead form of the warm-up
+  const double h1 = a0, h2 = a0 * a0 + a1, h3 = a0 * h2 + a1 * h1, h4 = a0 * h3 + a1 * h2;
   const int n_items = s_i[2];
+  const bool fw_in_smem = s_i[5] != 0;
+  TL_STAMP();  // 8: smoothing set-up
   // forward pass (harvest.cpp:649-654)
   for (int item = tid; item < n_items; item += nt) {
     int lo = 0, hi = nsm - 1;
@@ -445,17 +512,31 @@ __global__ void __launch_bounds__(TL_THREADS) harvest_tail_kernel(TailParams p) 
     const int st = p.sec_st[s], ed = p.sec_ed[s], flen = p.sec_len[s];
     const int c = item - p.sec_lo[s];
     const int begin = st + c * TL_CHUNK, end = min(st + flen, begin + TL_CHUNK);
-    double *fw = p.fw + p.sec_off[s] - st;
-    const double x_st = p.pad[st], x_ed = p.pad[ed];
+    double *fw = (fw_in_smem ? fw_smem : p.fw) + p.sec_off[s] - st;
+    const double x_st = pad[st], x_ed = pad[ed];
     double w0 = 0.0, w1 = 0.0;
-    for (int i = max(0, begin - TL_LAG); i < end; ++i) {
-      const double xi = (i < st) ? x_st : (i > ed ? x_ed : p.pad[i]);
+    int i = max(0, begin - TL_LAG);
+    // warm-up (only the state matters): four samples per step of the dependency chain
+    for (; i + 4 <= begin; i += 4) {
+      const double x1 = (i < st) ? x_st : (i > ed ? x_ed : pad[i]);
+      const double x2 = (i + 1 < st) ? x_st : (i + 1 > ed ? x_ed : pad[i + 1]);
+      const double x3 = (i + 2 < st) ? x_st : (i + 2 > ed ? x_ed : pad[i + 2]);
+      const double x4 = (i + 3 < st) ? x_st : (i + 3 > ed ? x_ed : pad[i + 3]);
+      const double f3 = fma(h2, x1, fma(h1, x2, x3));
+      const double f4 = fma(h3, x1, fma(h2, x2, fma(h1, x3, x4)));
+      const double n1 = fma(h3, w0, fma(a1 * h2, w1, f3));
+      const double n0 = fma(h4, w0, fma(a1 * h3, w1, f4));
+      w0 = n0; w1 = n1;
+    }
+    for (; i < end; ++i) {
+      const double xi = (i < st) ? x_st : (i > ed ? x_ed : pad[i]);
       const double wt = xi + a0 * w0 + a1 * w1;
       if (i >= begin) fw[i] = b0 * wt + b1 * w0 + b0 * w1;
       w1 = w0; w0 = wt;
     }
   }
   __syncthreads();
+  TL_STAMP();  // 9: after forward pass
   // backward pass (harvest.cpp:656-662): outputs on [st, ed]
   if (tid == 0) {
     int items = 0;
@@ -475,15 +556,27 @@ __global__ void __launch_bounds__(TL_THREADS) harvest_tail_kernel(TailParams p) 
     const int st = p.sec_st[s], ed = p.sec_ed[s], flen = p.sec_len[s];
     const int c = item - p.kb[s];
     const int begin = st + c * TL_CHUNK, end = min(ed + 1, begin + TL_CHUNK);  // outputs [begin, end)
-    const double *fw = p.fw + p.sec_off[s] - st;
+    const double *fw = (fw_in_smem ? fw_smem : p.fw) + p.sec_off[s] - st;
     const int top = min(st + flen - 1, end - 1 + TL_LAG);
     double w0 = 0.0, w1 = 0.0;
-    for (int j = top; j >= begin; --j) {
+    int j = top;
+    for (; j - 4 >= end - 1; j -= 4) {  // warm-up above the output range, four samples per chain step
+      const double x1 = fw[j], x2 = fw[j - 1], x3 = fw[j - 2], x4 = fw[j - 3];
+      const double f3 = fma(h2, x1, fma(h1, x2, x3));
+      const double f4 = fma(h3, x1, fma(h2, x2, fma(h1, x3, x4)));
+      const double n1 = fma(h3, w0, fma(a1 * h2, w1, f3));
+      const double n0 = fma(h4, w0, fma(a1 * h3, w1, f4));
+      w0 = n0; w1 = n1;
+    }
+    for (; j >= begin; --j) {
       const double wt = fw[j] + a0 * w0 + a1 * w1;
       if (j < end) p.out[j - TL_LAG] = b0 * wt + b1 * w0 + b0 * w1;
       w1 = w0; w0 = wt;
     }
   }
+  __syncthreads();
+  TL_STAMP();  // 10: end
+#undef TL_STAMP
 }
 
 // compute(): pick basic_f0 at the frame_period grid (harvest.cpp:199-204)
@@ -521,9 +614,18 @@ int wb_harvest_tail(WbWorkspace *ws, const double *d_cand, const double *d_score
   p.fw_cap = (long long)L + 2 * TL_LAG + (long long)TL_LAG * p.maxsec;
   p.fw = (double *)ws->get("tl_fw", sizeof(double) * p.fw_cap);
   p.error_flag = ws->error_flag();
-  if (!p.secbuf || !p.pad || !p.fw || !p.error_flag) return WB_ERR_CUDA;
+  p.clocks = (long long *)ws->get("tl_clocks", sizeof(long long) * 16);
+  p.gA = (double *)ws->get("tl_ga", sizeof(double) * (L + 2 * TL_LAG));
+  p.gB = (double *)ws->get("tl_gb", sizeof(double) * (L + 2 * TL_LAG));
+  if (!p.gA || !p.gB) return WB_ERR_CUDA;
+  if (!p.secbuf || !p.pad || !p.fw || !p.error_flag || !p.clocks) return WB_ERR_CUDA;
   WB_LAUNCH("search_base_kernel", search_base_kernel<<<(L * 32 + 255) / 256, 256, 0, stream>>>(d_cand, d_score, d_nc, L, MC, p.base));
-  WB_LAUNCH("harvest_tail_kernel", harvest_tail_kernel<<<1, TL_THREADS, 0, stream>>>(p));
+  // shared memory: the two contour buffers (+ forward-filter scratch) when they fit (10 s at 1 ms: 2 x 85 KB)
+  const int want = 2 * (L + 2 * TL_LAG) + 16 * TL_LAG;
+  p.smem_doubles = want < 25600 ? want : (2 * (L + 2 * TL_LAG) <= 25600 ? 25600 : 0);
+  const size_t tl_smem_bytes = sizeof(double) * (size_t)p.smem_doubles;
+  WB_CUDA_CHECK(cudaFuncSetAttribute(harvest_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl_smem_bytes));
+  WB_LAUNCH("harvest_tail_kernel", harvest_tail_kernel<<<1, TL_THREADS, tl_smem_bytes, stream>>>(p));
   WB_CUDA_CHECK(cudaGetLastError());
   return WB_OK;
 }

@@ -70,15 +70,27 @@ int do_init() {
 
 #define WB_RNG_CHUNK 64
 
-__global__ void rng_fill_kernel(const WbRngState *__restrict__ state, const uint4 *__restrict__ pow_tables,
-                                const unsigned long long *__restrict__ d_count,
-                                unsigned long long max_count, double *__restrict__ out) {
+// Two-level jump: warp 0 jumps cooperatively to the block's first stream position (one table
+// load per lane and matrix), every thread then only jumps by tid * WB_RNG_CHUNK, which touches
+// the same seven small tables in every block (L1-resident).
+__global__ void __launch_bounds__(128) rng_fill_kernel(const WbRngState *__restrict__ state,
+                                                       const uint4 *__restrict__ pow_tables,
+                                                       const unsigned long long *__restrict__ d_count,
+                                                       unsigned long long max_count, double *__restrict__ out) {
+  __shared__ uint32_t s_base[4];
   const unsigned long long count = d_count ? min(*d_count, max_count) : max_count;
-  const unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const unsigned long long begin = g * WB_RNG_CHUNK;
+  const unsigned long long block_begin = (unsigned long long)blockIdx.x * blockDim.x * WB_RNG_CHUNK;
+  if (block_begin >= count) return;
+  if (threadIdx.x < 32) {
+    uint32_t b[4] = {state->s[0], state->s[1], state->s[2], state->s[3]};
+    wb_rng_jump_warp(pow_tables, b, block_begin);
+    if (threadIdx.x == 0) { s_base[0] = b[0]; s_base[1] = b[1]; s_base[2] = b[2]; s_base[3] = b[3]; }
+  }
+  __syncthreads();
+  const unsigned long long begin = block_begin + (unsigned long long)threadIdx.x * WB_RNG_CHUNK;
   if (begin >= count) return;
-  uint32_t s[4] = {state->s[0], state->s[1], state->s[2], state->s[3]};
-  wb_rng_jump(pow_tables, s, begin);
+  uint32_t s[4] = {s_base[0], s_base[1], s_base[2], s_base[3]};
+  wb_rng_jump(pow_tables, s, (unsigned long long)threadIdx.x * WB_RNG_CHUNK);
   const unsigned long long end = min(count, begin + WB_RNG_CHUNK);
   for (unsigned long long i = begin; i < end; ++i) out[i] = wb_randn_next(s);
 }

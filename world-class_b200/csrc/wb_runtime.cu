@@ -159,6 +159,8 @@ WbLaunchScope::~WbLaunchScope() {
 }
 
 unsigned long long wb_launch_counter() { return g_launches.load(); }
+void wb_launch_counter_add(unsigned long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int wb_prof_is_enabled() { return g_prof_on.load(std::memory_order_relaxed); }
 void wb_prof_set_enabled(int on) { g_prof_on.store(on ? 1 : 0); }
 
 int wb_prof_collect() {
