@@ -15,8 +15,11 @@ def main():
     rep, kregex, cubin = sys.argv[1], sys.argv[2], sys.argv[3]
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 25
     cregex = sys.argv[5] if len(sys.argv) > 5 else kregex  # symbol regex inside the cubin
-    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kregex],
-                         capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):   # a `--page source --csv` export made on the GPU box (profiles/capture.sh)
+        src = open(rep).read()
+    else:
+        src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kregex],
+                             capture_output=True, text=True).stdout
     rows = list(csv.reader(src.splitlines()))
     # may contain several launches: keep the first kernel block
     hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")

@@ -1,7 +1,7 @@
 """Turns an ncu report into the committed evidence: a per-kernel CSV/markdown table and
 profiles/ncu_traffic.json (DRAM bytes per launch, read by bench.py for `roofline.traffic`).
 
-usage: python profiles/summarize.py <report.ncu-rep> <tag>
+usage: python profiles/summarize.py <report.ncu-rep | raw-page.csv> <tag>
 """
 import csv
 import json
@@ -25,12 +25,19 @@ METRICS = [
     ("launch__block_size", "block"),
     ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram_pct"),
     ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem_bank_conflicts"),
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smem_wavefronts"),
+    ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "lsu_pipe_pct"),
+    ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1_wavefront_pct"),
+    ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm_throughput_pct"),
 ]
 
 
 def main():
     rep, tag = sys.argv[1], sys.argv[2]
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):   # a `--page raw --csv` export made on the GPU box (profiles/capture.sh)
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}

@@ -33,8 +33,9 @@ def test_harvest_stages(wb, signals, fs, seconds):
     _cmp("raw", hv.debug_read("hv_raw", (nch, Lb)), ref["raw"])
     nc = hv.debug_read("hv_nc", (4,), dtype=np.int32)
     assert nc[0] == ref["nc"]
-    _cmp("cand1", hv.debug_read("hv_candA", (Lb, mc)), ref["cand1"])
-    _cmp("score1", hv.debug_read("hv_scoreA", (Lb, mc)), ref["score1"], tol=1e-6)
+    cand_score = hv.debug_read("hv_candA", (2, Lb, mc))   # refined candidates | scores
+    _cmp("cand1", cand_score[0], ref["cand1"])
+    _cmp("score1", cand_score[1], ref["score1"], tol=1e-6)
     _cmp("cand2", hv.debug_read("hv_candB", (Lb, mc)), ref["cand2"])
     cont = hv.debug_read("tl_contours", (5, Lb))
     for k, name in enumerate(["base", "step1", "step2", "step3", "step4"]):

@@ -59,6 +59,14 @@ def test_narrow_f0_range(wb, signals):
     _compare(_chain(wb, x, fs, h_floor=90.0, h_ceil=300.0), ref, "narrow range")
 
 
+def test_loud_input_takes_the_truncating_dc_path(wb, signals):
+    """|y| >= 1 after decimation: harvest.cpp:238-241 subtracts an int-truncated running sum."""
+    fs = 16000
+    x = 4.0 * signals.synth_speech(fs, 0.7, seed=24) + 0.8
+    ref, _ = refbin.run_reference(x, fs, stages="hcds")
+    _compare(_chain(wb, x, fs), ref, "loud input")
+
+
 def test_ragged_lengths(wb, signals):
     """Lengths that are not multiples of the decimation ratio / frame hop."""
     fs = 48000

@@ -152,6 +152,16 @@ def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
+def _out_array(arr, shape):
+    """A caller-owned output array (checked) or a fresh one."""
+    if arr is None:
+        return np.empty(shape, dtype=np.float64)
+    if not (isinstance(arr, np.ndarray) and arr.dtype == np.float64 and arr.flags["C_CONTIGUOUS"] and
+            arr.shape == tuple(shape)):
+        raise ValueError("output array must be C-contiguous float64 of shape %r" % (tuple(shape),))
+    return arr
+
+
 def _row_pointers(mat):
     """A C `double **` (array of row pointers) into a C-contiguous 2-D float64 array."""
     assert mat.flags["C_CONTIGUOUS"] and mat.dtype == np.float64 and mat.ndim == 2
@@ -232,12 +242,13 @@ class Harvest:
         fp = self.option.frame_period if frame_period is None else frame_period
         return lib().wb_harvest_get_samples(int(fs), int(x_length), float(fp))
 
-    def compute(self, x):
-        """-> (temporal_positions, f0)"""
+    def compute(self, x, temporal_positions=None, f0=None):
+        """-> (temporal_positions, f0).  Like the reference (test/test.cpp:102-104) the caller may own the
+        output arrays: pass float64 arrays of getSamples() entries to have them filled in place."""
         x = _f64(x)
         n = self.getSamples(self.fs, len(x))
-        tpos = np.empty(n, dtype=np.float64)
-        f0 = np.empty(n, dtype=np.float64)
+        tpos = _out_array(temporal_positions, (n,))
+        f0 = _out_array(f0, (n,))
         _check(lib().wb_harvest_compute(self._h, x.ctypes.data, len(x), tpos.ctypes.data, f0.ctypes.data),
                "wb_harvest_compute")
         return tpos, f0
@@ -270,10 +281,11 @@ class CheapTrick:
     def getF0FloorForCheapTrick(fs, fft_size):
         return lib().wb_cheaptrick_get_f0_floor(int(fs), int(fft_size))
 
-    def compute(self, x, temporal_positions, f0):
-        """-> spectrogram [f0_length][fft_size/2+1] (host arrays in, host array out)."""
+    def compute(self, x, temporal_positions, f0, spectrogram=None):
+        """-> spectrogram [f0_length][fft_size/2+1] (host arrays in, host array out; `spectrogram` may be a
+        caller-owned output array, test/test.cpp:146-149)."""
         x, tpos, f0 = _f64(x), _f64(temporal_positions), _f64(f0)
-        sp = np.empty((len(f0), self.fft_size // 2 + 1), dtype=np.float64)
+        sp = _out_array(spectrogram, (len(f0), self.fft_size // 2 + 1))
         rows = _row_pointers(sp)
         _check(lib().wb_cheaptrick_compute(self._h, x.ctypes.data, len(x), tpos.ctypes.data, f0.ctypes.data,
                                            len(f0), rows.ctypes.data), "wb_cheaptrick_compute")
@@ -293,10 +305,11 @@ class D4C:
             _lib.wb_d4c_destroy(self._h)
             self._h = None
 
-    def compute(self, x, temporal_positions, f0, fft_size):
-        """-> aperiodicity [f0_length][fft_size/2+1]"""
+    def compute(self, x, temporal_positions, f0, fft_size, aperiodicity=None):
+        """-> aperiodicity [f0_length][fft_size/2+1] (`aperiodicity` may be a caller-owned output array,
+        test/test.cpp:170-173)."""
         x, tpos, f0 = _f64(x), _f64(temporal_positions), _f64(f0)
-        ap = np.empty((len(f0), int(fft_size) // 2 + 1), dtype=np.float64)
+        ap = _out_array(aperiodicity, (len(f0), int(fft_size) // 2 + 1))
         rows = _row_pointers(ap)
         _check(lib().wb_d4c_compute(self._h, x.ctypes.data, len(x), tpos.ctypes.data, f0.ctypes.data,
                                     len(f0), int(fft_size), rows.ctypes.data), "wb_d4c_compute")
@@ -316,12 +329,12 @@ class Synthesis:
             _lib.wb_synthesis_destroy(self._h)
             self._h = None
 
-    def compute(self, f0, spectrogram, aperiodicity, out_length):
-        """-> waveform of out_length samples"""
+    def compute(self, f0, spectrogram, aperiodicity, out_length, out=None):
+        """-> waveform of out_length samples (`out` may be a caller-owned output array)"""
         f0 = _f64(f0)
         sp, ap = _f64(spectrogram), _f64(aperiodicity)
         assert sp.shape == ap.shape == (len(f0), self.fft_size // 2 + 1)
-        out = np.empty(int(out_length), dtype=np.float64)
+        out = _out_array(out, (int(out_length),))
         rs, ra = _row_pointers(sp), _row_pointers(ap)
         _check(lib().wb_synthesis_compute(self._h, f0.ctypes.data, len(f0), rs.ctypes.data, ra.ctypes.data,
                                           len(out), out.ctypes.data), "wb_synthesis_compute")

@@ -6,6 +6,8 @@
 #include <string.h>
 #include <mutex>
 #include <algorithm>
+#include <chrono>
+#include <stdlib.h>
 #include <new>
 #include <thread>
 #include <vector>
@@ -37,6 +39,34 @@ int ctx_init() {
 }
 
 inline cudaStream_t pick_stream(void *stream) { return stream ? (cudaStream_t)stream : g_stream; }
+
+// stand-alone stage calls draw from the process-global randn stream and move it on (reference semantics)
+inline WbRngCursor global_cursor() {
+  WbRngCursor c;
+  c.state = wb_rng_global_state();
+  return c;
+}
+
+// ---- optional host-side phase trace (WB_TRACE=1): wall-clock milestones of the host-pointer entry points
+struct HostTrace {
+  bool on;
+  const char *what;
+  std::chrono::steady_clock::time_point t0, last;
+  explicit HostTrace(const char *w) : what(w) {
+    static const bool enabled = getenv("WB_TRACE") != nullptr;
+    on = enabled;
+    if (on) t0 = last = std::chrono::steady_clock::now();
+  }
+  void mark(const char *phase, cudaStream_t sync_stream = nullptr) {
+    if (!on) return;
+    if (sync_stream) cudaStreamSynchronize(sync_stream);
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[wb_trace] %-22s %-18s +%8.3f ms (total %8.3f)\n", what, phase,
+            std::chrono::duration<double, std::milli>(now - last).count(),
+            std::chrono::duration<double, std::milli>(now - t0).count());
+    last = now;
+  }
+};
 
 // ---- host <-> device transfers of row-pointer matrices -------------------------------------------
 // The reference API hands matrices over as separately allocated rows (test/test.cpp:146-149).  Rows are
@@ -126,8 +156,10 @@ struct wb_pipeline {
   double ct_f0_floor_internal;
   WbD4COption d4c;
   WbWorkspace ws;
-  cudaStream_t side = nullptr;       // Synthesis time base overlaps CheapTrick / D4C here
-  cudaEvent_t ev_f0 = nullptr, ev_tb = nullptr;
+  // After Harvest the chain forks: CheapTrick stays on the caller's stream, D4C runs on `d4c_stream`
+  // and the Synthesis time base / pulse list / noise on `side`; they join before the impulse responses.
+  cudaStream_t side = nullptr, d4c_stream = nullptr;
+  cudaEvent_t ev_f0 = nullptr, ev_tb = nullptr, ev_ct_count = nullptr, ev_body_count = nullptr, ev_d4c = nullptr;
   // CUDA graph of one whole run (captured after a warm run with the same arguments)
   bool use_graph = false;
   cudaGraphExec_t graph_exec = nullptr;
@@ -141,7 +173,11 @@ struct wb_pipeline {
   ~wb_pipeline() {
     if (ev_f0) cudaEventDestroy(ev_f0);
     if (ev_tb) cudaEventDestroy(ev_tb);
+    if (ev_ct_count) cudaEventDestroy(ev_ct_count);
+    if (ev_body_count) cudaEventDestroy(ev_body_count);
+    if (ev_d4c) cudaEventDestroy(ev_d4c);
     if (side) cudaStreamDestroy(side);
+    if (d4c_stream) cudaStreamDestroy(d4c_stream);
     if (d_rng_private) cudaFree(d_rng_private);
     if (d_rng_seed) cudaFree(d_rng_seed);
     if (graph_exec) cudaGraphExecDestroy(graph_exec);
@@ -159,6 +195,14 @@ struct wb_synthesis {
   int fft_size;
   double frame_period_ms;
   WbWorkspace ws;
+  // host-pointer compute(): the pulse list (f0 only) is built on `side` while sp / ap are still uploading
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_f0 = nullptr, ev_tb = nullptr;
+  ~wb_synthesis() {
+    if (ev_f0) cudaEventDestroy(ev_f0);
+    if (ev_tb) cudaEventDestroy(ev_tb);
+    if (side) cudaStreamDestroy(side);
+  }
 };
 
 extern "C" {
@@ -229,8 +273,8 @@ int wb_randn_fill(double *out, int n) {
   WB_CUDA_CHECK(cudaMalloc(&d_n, sizeof(unsigned long long)));
   const unsigned long long nn = (unsigned long long)n;
   WB_CUDA_CHECK(cudaMemcpyAsync(d_n, &nn, sizeof(nn), cudaMemcpyHostToDevice, g_stream));
-  rc = wb_rng_fill(wb_rng_global_state(), nullptr, nn, d, g_stream);
-  if (!rc) rc = wb_rng_advance(wb_rng_global_state(), d_n, g_stream);
+  rc = wb_rng_fill(wb_rng_global_state(), nullptr, nullptr, nn, d, g_stream);
+  if (!rc) rc = wb_rng_advance(wb_rng_global_state(), d_n, nullptr, g_stream);
   if (!rc) {
     cudaError_t e = cudaMemcpyAsync(out, d, sizeof(double) * n, cudaMemcpyDeviceToHost, g_stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(g_stream);
@@ -304,7 +348,7 @@ int wb_cheaptrick_compute_dev(wb_cheaptrick_t *h, const double *d_x, int x_lengt
                               const double *d_f0, int f0_length, double *d_sp, void *stream) {
   if (!h || !d_x || !d_tpos || !d_f0 || !d_sp || x_length <= 0 || f0_length < 0) return WB_ERR_ARG;
   return wb_cheaptrick_run(&h->ws, h->fs, h->opt.fft_size, h->opt.q1, h->f0_floor_internal, d_x, x_length,
-                           d_tpos, d_f0, f0_length, d_sp, wb_rng_global_state(), pick_stream(stream));
+                           d_tpos, d_f0, f0_length, d_sp, global_cursor(), pick_stream(stream));
 }
 
 int wb_cheaptrick_compute(wb_cheaptrick_t *h, const double *x, int x_length, const double *tpos,
@@ -320,8 +364,11 @@ int wb_cheaptrick_compute(wb_cheaptrick_t *h, const double *x, int x_length, con
   if ((rc = vec_to_device(&h->ws, "h_f0", f0, f0_length, &d_f, st))) return rc;
   double *d_sp = (double *)h->ws.get("h_sp", sizeof(double) * (size_t)f0_length * bins);
   if (!d_sp) return WB_ERR_CUDA;
+  HostTrace tr("cheaptrick_compute");
   if ((rc = wb_cheaptrick_compute_dev(h, d_x, x_length, d_t, d_f, f0_length, d_sp, st))) return rc;
+  tr.mark("kernels", st);
   if ((rc = rows_to_host(&h->ws, d_sp, f0_length, bins, spectrogram, st))) return rc;
+  tr.mark("rows_to_host");
   return h->ws.read_error_flag(st);
 }
 
@@ -347,7 +394,7 @@ int wb_d4c_compute_dev(wb_d4c_t *h, const double *d_x, int x_length, const doubl
                        int f0_length, int fft_size, double *d_ap, void *stream) {
   if (!h || !d_x || !d_tpos || !d_f0 || !d_ap || x_length <= 0 || f0_length < 0 || fft_size < 2) return WB_ERR_ARG;
   return wb_d4c_run(&h->ws, h->fs, h->opt.threshold, d_x, x_length, d_tpos, d_f0, f0_length, fft_size, d_ap,
-                    wb_rng_global_state(), pick_stream(stream));
+                    global_cursor(), pick_stream(stream));
 }
 
 int wb_d4c_compute(wb_d4c_t *h, const double *x, int x_length, const double *tpos, const double *f0,
@@ -363,8 +410,11 @@ int wb_d4c_compute(wb_d4c_t *h, const double *x, int x_length, const double *tpo
   if ((rc = vec_to_device(&h->ws, "h_f0", f0, f0_length, &d_f, st))) return rc;
   double *d_ap = (double *)h->ws.get("h_ap", sizeof(double) * (size_t)f0_length * bins);
   if (!d_ap) return WB_ERR_CUDA;
+  HostTrace tr("d4c_compute");
   if ((rc = wb_d4c_compute_dev(h, d_x, x_length, d_t, d_f, f0_length, fft_size, d_ap, st))) return rc;
+  tr.mark("kernels", st);
   if ((rc = rows_to_host(&h->ws, d_ap, f0_length, bins, aperiodicity, st))) return rc;
+  tr.mark("rows_to_host");
   return h->ws.read_error_flag(st);
 }
 
@@ -376,6 +426,12 @@ int wb_synthesis_create(int fs, int fft_size, double frame_period_ms, wb_synthes
   wb_synthesis *h = new (std::nothrow) wb_synthesis();
   if (!h) return WB_ERR_ARG;
   h->fs = fs; h->fft_size = fft_size; h->frame_period_ms = frame_period_ms;
+  if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_f0, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_tb, cudaEventDisableTiming) != cudaSuccess) {
+    delete h;
+    return WB_ERR_CUDA;
+  }
   *out = h;
   return WB_OK;
 }
@@ -387,7 +443,7 @@ int wb_synthesis_compute_dev(wb_synthesis_t *h, const double *d_f0, int f0_lengt
                              void *stream) {
   if (!h || !d_f0 || !d_sp || !d_ap || !d_out || f0_length < 2 || out_length < 0) return WB_ERR_ARG;
   return wb_synthesis_run(&h->ws, h->fs, h->fft_size, h->frame_period_ms, d_f0, f0_length, d_sp, d_ap,
-                          out_length, d_out, f0_upper_bound, wb_rng_global_state(), pick_stream(stream));
+                          out_length, d_out, f0_upper_bound, global_cursor(), pick_stream(stream));
 }
 
 int wb_synthesis_compute(wb_synthesis_t *h, const double *f0, int f0_length, const double *const *spectrogram,
@@ -405,11 +461,24 @@ int wb_synthesis_compute(wb_synthesis_t *h, const double *f0, int f0_length, con
   double *d_ap = (double *)h->ws.get("h_ap", sizeof(double) * (size_t)f0_length * bins);
   double *d_out = (double *)h->ws.get("h_out", sizeof(double) * (size_t)out_length);
   if (!d_sp || !d_ap || !d_out) return WB_ERR_CUDA;
+  HostTrace tr("synthesis_compute");
+  // pulse list + excitation noise on the side stream (needs f0 only), overlapping the row uploads below
+  WbRngCursor cur = global_cursor();
+  WB_CUDA_CHECK(cudaEventRecord(h->ev_f0, st));
+  WB_CUDA_CHECK(cudaStreamWaitEvent(h->side, h->ev_f0, 0));
+  if ((rc = wb_synthesis_timebase(&h->ws, h->fs, h->fft_size, h->frame_period_ms, d_f, f0_length, out_length, h->side, &cur)))
+    return rc;
+  WB_CUDA_CHECK(cudaEventRecord(h->ev_tb, h->side));
   if ((rc = rows_to_device(&h->ws, "rows_stage_sp", spectrogram, f0_length, bins, d_sp, st))) return rc;
   if ((rc = rows_to_device(&h->ws, "rows_stage_ap", aperiodicity, f0_length, bins, d_ap, st))) return rc;
-  if ((rc = wb_synthesis_compute_dev(h, d_f, f0_length, d_sp, d_ap, out_length, d_out, max_f0 + 1.0, st))) return rc;
+  tr.mark("rows staged");
+  WB_CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_tb, 0));
+  if ((rc = wb_synthesis_render(&h->ws, h->fs, h->fft_size, h->frame_period_ms, f0_length, d_sp, d_ap, out_length, d_out,
+                                max_f0 + 1.0, cur, st, true)))
+    return rc;
   WB_CUDA_CHECK(cudaMemcpyAsync(out, d_out, sizeof(double) * out_length, cudaMemcpyDeviceToHost, st));
   WB_CUDA_CHECK(cudaStreamSynchronize(st));
+  tr.mark("done");
   return h->ws.read_error_flag(st);
 }
 
@@ -468,7 +537,10 @@ int wb_harvest_compute(wb_harvest_t *h, const double *x, int x_length, double *t
   double *d_t = (double *)h->ws.get("h_tpos", sizeof(double) * f0_length);
   double *d_f = (double *)h->ws.get("h_f0", sizeof(double) * f0_length);
   if (!d_t || !d_f) return WB_ERR_CUDA;
+  HostTrace tr("harvest_compute");
   if ((rc = wb_harvest_compute_dev(h, d_x, x_length, d_t, d_f, st))) return rc;
+  tr.mark("enqueued");
+  tr.mark("kernels", st);
   WB_CUDA_CHECK(cudaMemcpyAsync(tpos, d_t, sizeof(double) * f0_length, cudaMemcpyDeviceToHost, st));
   WB_CUDA_CHECK(cudaMemcpyAsync(f0, d_f, sizeof(double) * f0_length, cudaMemcpyDeviceToHost, st));
   WB_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -507,8 +579,15 @@ int wb_pipeline_create(int fs, const WbHarvestOption *hopt, const WbCheapTrickOp
   p->ct_f0_floor_internal = wb_cheaptrick_get_f0_floor(fs, p->ct.fft_size);
   wb_d4c_option_default(&p->d4c);
   if (dopt) p->d4c = *dopt;
+  // D4C is the longest branch after the fork: give its stream the highest priority
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
   if (cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&p->d4c_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
       cudaEventCreateWithFlags(&p->ev_f0, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&p->ev_ct_count, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&p->ev_body_count, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&p->ev_d4c, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&p->ev_tb, cudaEventDisableTiming) != cudaSuccess) {
     delete p;
     return WB_ERR_CUDA;
@@ -628,27 +707,52 @@ static int pipeline_enqueue(wb_pipeline_t *p, const double *d_x, int x_length, d
     rng = p->d_rng_private;
     WB_CUDA_CHECK(cudaMemcpyAsync(rng, p->d_rng_seed, sizeof(WbRngState), cudaMemcpyDeviceToDevice, st));
   }
-  // The pulse list depends on f0 only: compute it on the side stream, concurrently with CheapTrick / D4C
-  if (y_length > 0) {
-    WB_CUDA_CHECK(cudaEventRecord(p->ev_f0, st));
-    WB_CUDA_CHECK(cudaStreamWaitEvent(p->side, p->ev_f0, 0));
-    if ((rc = wb_synthesis_timebase(&p->ws, fs, p->ct.fft_size, fp, d_f0, f0_length, y_length, p->side))) return rc;
-    WB_CUDA_CHECK(cudaEventRecord(p->ev_tb, p->side));
+  // Fork.  Everything below depends on f0 only until the impulse responses need sp, ap and the pulses.
+  // The randn() stream is consumed in the reference's serial order CheapTrick -> Love Train -> D4C body
+  // -> Synthesis; each stage counts its draws up front, so the stages run concurrently and chain their
+  // stream positions through rng_pos[] (WbRngCursor): [0] after CheapTrick, [1] after D4C.
+  // (Per-kernel event timing needs one stream: profiling runs the branches back to back.)
+  const bool fork = !wb_prof_is_enabled();
+  cudaStream_t s_d4c = fork ? p->d4c_stream : st, s_side = fork ? p->side : st;
+  unsigned long long *rng_pos = (unsigned long long *)p->ws.get("pl_rng_pos", sizeof(unsigned long long) * 4);
+  if (!rng_pos) return WB_ERR_CUDA;
+  WB_CUDA_CHECK(cudaEventRecord(p->ev_f0, st));
+  if (fork) {
+    WB_CUDA_CHECK(cudaStreamWaitEvent(s_d4c, p->ev_f0, 0));
+    if (y_length > 0) WB_CUDA_CHECK(cudaStreamWaitEvent(s_side, p->ev_f0, 0));
   }
+  // CheapTrick (caller's stream)
+  WbRngCursor c_ct;
+  c_ct.state = rng; c_ct.skip_out = rng_pos + 0; c_ct.advance = false; c_ct.record_skip_out = p->ev_ct_count;
   if ((rc = wb_cheaptrick_run(&p->ws, fs, p->ct.fft_size, p->ct.q1, p->ct_f0_floor_internal, d_x, x_length, d_tpos,
-                              d_f0, f0_length, d_sp, rng, st)))
+                              d_f0, f0_length, d_sp, c_ct, st)))
     return rc;
+  // D4C
+  WbRngCursor c_d4c;
+  c_d4c.state = rng; c_d4c.skip_in = rng_pos + 0; c_d4c.skip_out = rng_pos + 1; c_d4c.advance = false;
+  c_d4c.wait_skip_in = p->ev_ct_count; c_d4c.record_skip_out = p->ev_body_count;
   if ((rc = wb_d4c_run(&p->ws, fs, p->d4c.threshold, d_x, x_length, d_tpos, d_f0, f0_length, p->ct.fft_size, d_ap,
-                       rng, st)))
+                       c_d4c, s_d4c)))
     return rc;
+  WB_CUDA_CHECK(cudaEventRecord(p->ev_d4c, s_d4c));
   if (y_length > 0) {
     if (!d_y) return WB_ERR_CUDA;
-    // Harvest's contour is bounded by f0_ceil up to the smoothing overshoot
+    // Synthesis, part 1 (pulse list) on the side stream
+    WbRngCursor c_syn;
+    c_syn.state = rng; c_syn.skip_in = rng_pos + 1; c_syn.wait_skip_in = p->ev_body_count;
+    c_syn.advance = true;  // moves the state past the whole chain
+    if ((rc = wb_synthesis_timebase(&p->ws, fs, p->ct.fft_size, fp, d_f0, f0_length, y_length, s_side, &c_syn))) return rc;
+    WB_CUDA_CHECK(cudaEventRecord(p->ev_tb, s_side));
+    // join, then part 2.  Harvest's contour is bounded by f0_ceil up to the smoothing overshoot.
     const double f0_bound = p->plan.opt.f0_ceil * 1.25;
     WB_CUDA_CHECK(cudaStreamWaitEvent(st, p->ev_tb, 0));
+    WB_CUDA_CHECK(cudaStreamWaitEvent(st, p->ev_d4c, 0));
     if ((rc = wb_synthesis_render(&p->ws, fs, p->ct.fft_size, fp, f0_length, d_sp, d_ap, y_length, d_y, f0_bound,
-                                  rng, st)))
+                                  c_syn, st, true)))
       return rc;
+  } else {
+    WB_CUDA_CHECK(cudaStreamWaitEvent(st, p->ev_d4c, 0));
+    if ((rc = wb_rng_advance(rng, rng_pos + 1, nullptr, st))) return rc;
   }
   return WB_OK;
 }

@@ -15,14 +15,18 @@ __device__ __forceinline__ double ct_current_f0(double f0, double f0_floor) {
   return (f0 <= f0_floor) ? WB_DEFAULT_F0 : f0;  // cheaptrick.cpp:76
 }
 
-// randn() calls made by frame i: window samples + one per bin (cheaptrick.cpp:153, :227)
-__global__ void ct_count_kernel(const double *__restrict__ f0, int f0_length, int fs, int fft_size,
-                                double f0_floor, unsigned long long *__restrict__ counts) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= f0_length) return;
-  const double cf0 = ct_current_f0(f0[i], f0_floor);
-  const int hw = wb_round(1.5 * fs / cf0);
-  counts[i] = (unsigned long long)(2 * hw + 1) + (unsigned long long)(fft_size / 2 + 1);
+// randn() calls made by frame i: window samples + one per bin (cheaptrick.cpp:153, :227); their exclusive
+// prefix sums are the frames' positions in the stream
+__global__ void __launch_bounds__(1024) ct_count_scan_kernel(const double *__restrict__ f0, int f0_length, int fs,
+                                                             int fft_size, double f0_floor,
+                                                             unsigned long long *__restrict__ offsets,
+                                                             const unsigned long long *__restrict__ skip_in,
+                                                             unsigned long long *__restrict__ skip_out) {
+  wb_block_count_scan([&](int i) {
+    const double cf0 = ct_current_f0(f0[i], f0_floor);
+    const int hw = wb_round(1.5 * fs / cf0);
+    return (unsigned long long)(2 * hw + 1) + (unsigned long long)(fft_size / 2 + 1);
+  }, f0_length, offsets, skip_in, skip_out);
 }
 
 struct CtParams {
@@ -135,7 +139,7 @@ size_t wb_cheaptrick_smem_bytes(int fft_size, int seg_capacity) {
 // Consumes the global randn stream exactly like the reference's serial loop.
 int wb_cheaptrick_run(WbWorkspace *ws, int fs, int fft_size, double q1, double f0_floor_internal,
                       const double *d_x, int x_length, const double *d_tpos, const double *d_f0,
-                      int f0_length, double *d_sp, WbRngState *d_rng, cudaStream_t stream) {
+                      int f0_length, double *d_sp, const WbRngCursor &rng, cudaStream_t stream) {
   if (f0_length <= 0) return WB_OK;
   int log2n = 0;
   while ((1 << log2n) < fft_size) ++log2n;
@@ -144,16 +148,18 @@ int wb_cheaptrick_run(WbWorkspace *ws, int fs, int fft_size, double q1, double f
   const cplx *tw = wb_twiddle_table(fft_size);
   if (!tw) return WB_ERR_CUDA;
 
-  unsigned long long *d_counts = (unsigned long long *)ws->get("ct_counts", sizeof(unsigned long long) * (f0_length + 1));
   unsigned long long *d_offsets = (unsigned long long *)ws->get("ct_offsets", sizeof(unsigned long long) * (f0_length + 1));
   const unsigned long long max_noise = (unsigned long long)f0_length * (unsigned long long)(fft_size + bins);
-  double *d_noise = (double *)ws->get("noise", sizeof(double) * max_noise);
-  if (!d_counts || !d_offsets || !d_noise) return WB_ERR_CUDA;
+  double *d_noise = (double *)ws->get("noise_ct", sizeof(double) * max_noise);
+  if (!d_offsets || !d_noise) return WB_ERR_CUDA;
 
-  WB_LAUNCH("ct_count_kernel", ct_count_kernel<<<(f0_length + 255) / 256, 256, 0, stream>>>(d_f0, f0_length, fs, fft_size, f0_floor_internal, d_counts));
-  int rc = wb_exclusive_scan_u64(d_counts, d_offsets, f0_length, stream);  // d_offsets[f0_length] = total
-  if (rc) return rc;
-  rc = wb_rng_fill(d_rng, d_offsets + f0_length, max_noise, d_noise, stream);
+  if (rng.wait_skip_in) WB_CUDA_CHECK(cudaStreamWaitEvent(stream, rng.wait_skip_in, 0));
+  WB_LAUNCH("ct_count_scan_kernel", ct_count_scan_kernel<<<1, 1024, 0, stream>>>(d_f0, f0_length, fs, fft_size, f0_floor_internal,
+                                                                              d_offsets, rng.skip_in, rng.skip_out));  // d_offsets[f0_length] = total
+  WB_CUDA_CHECK(cudaGetLastError());
+  int rc;
+  if (rng.record_skip_out) WB_CUDA_CHECK(cudaEventRecord(rng.record_skip_out, stream));
+  rc = wb_rng_fill(rng.state, rng.skip_in, d_offsets + f0_length, max_noise, d_noise, stream);
   if (rc) return rc;
 
   CtParams p;
@@ -170,5 +176,5 @@ int wb_cheaptrick_run(WbWorkspace *ws, int fs, int fft_size, double q1, double f
   });
   if (rc) return rc;
   WB_CUDA_CHECK(cudaGetLastError());
-  return wb_rng_advance(d_rng, d_offsets + f0_length, stream);
+  return rng.advance ? wb_rng_advance(rng.state, d_offsets + f0_length, rng.skip_in, stream) : WB_OK;
 }

@@ -116,6 +116,46 @@ __device__ inline void wb_block_inclusive_scan(double *a, int n, double *red) {
   __syncthreads();
 }
 
+// Single-CTA exclusive prefix sum over the per-item counts count(i), i in [0, n): offsets[i], offsets[n] = total;
+// optionally publishes *skip_out = *skip_in + total (randn stream bookkeeping, see WbRngCursor).
+// count(i) is evaluated twice (it is a cheap closed form everywhere).  blockDim.x multiple of 32, <= 1024.
+template <typename F>
+__device__ __forceinline__ void wb_block_count_scan(F count, int n, unsigned long long *__restrict__ offsets,
+                                                    const unsigned long long *__restrict__ skip_in,
+                                                    unsigned long long *__restrict__ skip_out) {
+  __shared__ unsigned long long s_warp_total[32];
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  const int chunk = (n + nt - 1) / nt;
+  const int b = min(n, tid * chunk), e = min(n, b + chunk);
+  unsigned long long s = 0;
+  for (int i = b; i < e; ++i) s += count(i);
+  unsigned long long incl = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_warp_total[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned long long w = (lane < nw) ? s_warp_total[lane] : 0ull;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long t = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += t;
+    }
+    s_warp_total[lane] = w;  // inclusive over warps
+  }
+  __syncthreads();
+  unsigned long long run = incl - s + (warp > 0 ? s_warp_total[warp - 1] : 0ull);
+  for (int i = b; i < e; ++i) { offsets[i] = run; run += count(i); }
+  if (tid == 0) {
+    const unsigned long long total = s_warp_total[nw - 1];
+    offsets[n] = total;
+    if (skip_out) *skip_out = (skip_in ? *skip_in : 0ull) + total;
+  }
+}
+
 // ---- launch accounting / per-kernel timing (wb_runtime.cu) ---------------------------------
 // Every kernel launch of the library goes through WB_LAUNCH: it counts launches (bench.py's
 // gpu_launches) and, when profiling is enabled, brackets the launch with CUDA events on the

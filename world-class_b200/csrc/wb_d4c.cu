@@ -63,29 +63,34 @@ __device__ inline int d4c_windowed_waveform(const double *__restrict__ x, int x_
   return wlen;
 }
 
-// ---- randn() call counts ------------------------------------------------------------------
-__global__ void lt_count_kernel(const double *__restrict__ f0, int n, int fs, double lowest_f0,
-                                unsigned long long *__restrict__ counts) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  unsigned long long c = 0;
-  if (f0[i] != 0.0) {
-    const double cf0 = f0[i] > lowest_f0 ? f0[i] : lowest_f0;
-    c = 2ull * d4c_half_window(3.0, fs, cf0) + 1ull;
-  }
-  counts[i] = c;
+// ---- randn() call counts and the frames' positions in the stream -------------------------------
+__global__ void __launch_bounds__(1024) lt_count_scan_kernel(const double *__restrict__ f0, int n, int fs,
+                                                             double lowest_f0, unsigned long long *__restrict__ offsets,
+                                                             const unsigned long long *__restrict__ skip_in,
+                                                             unsigned long long *__restrict__ skip_out) {
+  wb_block_count_scan([&](int i) {
+    unsigned long long c = 0;
+    if (f0[i] != 0.0) {
+      const double cf0 = f0[i] > lowest_f0 ? f0[i] : lowest_f0;
+      c = 2ull * d4c_half_window(3.0, fs, cf0) + 1ull;
+    }
+    return c;
+  }, n, offsets, skip_in, skip_out);
 }
 
-__global__ void body_count_kernel(const double *__restrict__ f0, const double *__restrict__ ap0, int n, int fs,
-                                  double threshold, unsigned long long *__restrict__ counts) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  unsigned long long c = 0;
-  if (!(f0[i] == 0 || ap0[i] <= threshold)) {
-    const double cf0 = f0[i] > WB_FLOOR_F0_D4C ? f0[i] : WB_FLOOR_F0_D4C;
-    c = 3ull * (2ull * d4c_half_window(4.0, fs, cf0) + 1ull);
-  }
-  counts[i] = c;
+__global__ void __launch_bounds__(1024) body_count_scan_kernel(const double *__restrict__ f0, const double *__restrict__ ap0,
+                                                               int n, int fs, double threshold,
+                                                               unsigned long long *__restrict__ offsets,
+                                                               const unsigned long long *__restrict__ skip_in,
+                                                               unsigned long long *__restrict__ skip_out) {
+  wb_block_count_scan([&](int i) {
+    unsigned long long c = 0;
+    if (!(f0[i] == 0 || ap0[i] <= threshold)) {
+      const double cf0 = f0[i] > WB_FLOOR_F0_D4C ? f0[i] : WB_FLOOR_F0_D4C;
+      c = 3ull * (2ull * d4c_half_window(4.0, fs, cf0) + 1ull);
+    }
+    return c;
+  }, n, offsets, skip_in, skip_out);
 }
 
 // ---- Love Train (d4c.cpp:181-240) ---------------------------------------------------------
@@ -286,7 +291,13 @@ __global__ void __launch_bounds__(D4C_BODY_THREADS, 2) d4c_body_kernel(BodyParam
   const int frame = blockIdx.x;
   const int tid = threadIdx.x, nt = blockDim.x;
   const double f0_in = p.f0[frame];
-  if (f0_in == 0 || p.ap0[frame] <= p.threshold) return;  // row already initialised (d4c.cpp:146)
+  if (f0_in == 0 || p.ap0[frame] <= p.threshold) {
+    // not analysed: the row keeps its initial value 1 - kMySafeGuardMinimum (d4c.cpp:127-132, :146)
+    const int out_bins = p.out_fft_size / 2 + 1;
+    double *out = p.ap + (size_t)frame * out_bins;
+    for (int i = tid; i < out_bins; i += nt) out[i] = 1.0 - WB_SAFEGUARD;
+    return;
+  }
   const double f0 = f0_in > WB_FLOOR_F0_D4C ? f0_in : WB_FLOOR_F0_D4C;
   const int fs = p.fs;
   const double pos = p.tpos[frame];
@@ -426,10 +437,6 @@ __global__ void __launch_bounds__(D4C_BODY_THREADS, 2) d4c_body_kernel(BodyParam
   }
 }
 
-__global__ void fill_kernel(double *__restrict__ p, size_t n, double v) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
-}
-
 int ilog2_exact(int n) {
   int l = 0;
   while ((1 << l) < n) ++l;
@@ -450,7 +457,7 @@ int wb_number_of_aperiodicities(int fs) {  // d4c.cpp:65-67, codec.cpp:211-214
 }
 
 int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int x_length, const double *d_tpos,
-               const double *d_f0, int f0_length, int out_fft_size, double *d_ap, WbRngState *d_rng,
+               const double *d_f0, int f0_length, int out_fft_size, double *d_ap, const WbRngCursor &rng,
                cudaStream_t stream) {
   if (f0_length <= 0) return WB_OK;
   const int N = wb_d4c_fft_size(fs), N_lt = wb_d4c_lt_fft_size(fs);
@@ -460,18 +467,16 @@ int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int
   if (n_ap < 0 || n_ap > D4C_MAX_AP) return WB_ERR_UNSUPPORTED;
   const int out_bins = out_fft_size / 2 + 1;
 
-  // rows start as 1 - kMySafeGuardMinimum (d4c.cpp:127-132)
-  const size_t n_out = (size_t)f0_length * out_bins;
-  WB_LAUNCH("fill_kernel", fill_kernel<<<(unsigned)((n_out + 1023) / 1024 < 4096 ? (n_out + 1023) / 1024 : 4096), 256, 0, stream>>>(
-      d_ap, n_out, 1.0 - WB_SAFEGUARD));
-
-  unsigned long long *d_counts = (unsigned long long *)ws->get("d4c_counts", sizeof(unsigned long long) * (f0_length + 1));
+  (void)out_bins;
   unsigned long long *d_offsets = (unsigned long long *)ws->get("d4c_offsets", sizeof(unsigned long long) * (f0_length + 1));
   double *d_ap0 = (double *)ws->get("d4c_ap0", sizeof(double) * f0_length);
   const unsigned long long max_noise_lt = (unsigned long long)f0_length * N_lt;
   const unsigned long long max_noise_body = (unsigned long long)f0_length * 3ull * N;
-  double *d_noise = (double *)ws->get("noise", sizeof(double) * (max_noise_body > max_noise_lt ? max_noise_body : max_noise_lt));
-  if (!d_counts || !d_offsets || !d_ap0 || !d_noise) return WB_ERR_CUDA;
+  double *d_noise = (double *)ws->get("noise_d4c", sizeof(double) * (max_noise_body > max_noise_lt ? max_noise_body : max_noise_lt));
+  // stream position after the Love Train draws (= skip_in + Love Train count)
+  unsigned long long *d_skip_mid = (unsigned long long *)ws->get("d4c_skip_mid", sizeof(unsigned long long));
+  unsigned long long *d_skip_end = rng.skip_out ? rng.skip_out : (unsigned long long *)ws->get("d4c_skip_end", sizeof(unsigned long long));
+  if (!d_offsets || !d_ap0 || !d_noise || !d_skip_mid || !d_skip_end) return WB_ERR_CUDA;
   const cplx *tw_lt = wb_twiddle_table(N_lt);
   const cplx *tw_n = wb_twiddle_table(N);
   const cplx *tw_2n = wb_twiddle_table(2 * N);
@@ -492,12 +497,12 @@ int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int
     WB_CUDA_CHECK(cudaMemcpyAsync(d_nuttall, h, sizeof(double) * window_length, cudaMemcpyHostToDevice, stream));
   }
 
-  const int cb = (f0_length + 255) / 256;
   // ---- Love Train
-  WB_LAUNCH("lt_count_kernel", lt_count_kernel<<<cb, 256, 0, stream>>>(d_f0, f0_length, fs, 40.0, d_counts));
-  int rc = wb_exclusive_scan_u64(d_counts, d_offsets, f0_length, stream);
-  if (rc) return rc;
-  if ((rc = wb_rng_fill(d_rng, d_offsets + f0_length, max_noise_lt, d_noise, stream))) return rc;
+  if (rng.wait_skip_in) WB_CUDA_CHECK(cudaStreamWaitEvent(stream, rng.wait_skip_in, 0));
+  WB_LAUNCH("lt_count_scan_kernel", lt_count_scan_kernel<<<1, 1024, 0, stream>>>(d_f0, f0_length, fs, 40.0, d_offsets, rng.skip_in, d_skip_mid));
+  WB_CUDA_CHECK(cudaGetLastError());
+  int rc;
+  if ((rc = wb_rng_fill(rng.state, rng.skip_in, d_offsets + f0_length, max_noise_lt, d_noise, stream))) return rc;
   {
     LtParams p;
     p.x = d_x; p.x_length = x_length; p.tpos = d_tpos; p.f0 = d_f0; p.f0_length = f0_length;
@@ -514,12 +519,12 @@ int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int
     if (rc) return rc;
     WB_CUDA_CHECK(cudaGetLastError());
   }
-  if ((rc = wb_rng_advance(d_rng, d_offsets + f0_length, stream))) return rc;
-
   // ---- body
-  WB_LAUNCH("body_count_kernel", body_count_kernel<<<cb, 256, 0, stream>>>(d_f0, d_ap0, f0_length, fs, threshold, d_counts));
-  if ((rc = wb_exclusive_scan_u64(d_counts, d_offsets, f0_length, stream))) return rc;
-  if ((rc = wb_rng_fill(d_rng, d_offsets + f0_length, max_noise_body, d_noise, stream))) return rc;
+  WB_LAUNCH("body_count_scan_kernel", body_count_scan_kernel<<<1, 1024, 0, stream>>>(d_f0, d_ap0, f0_length, fs, threshold, d_offsets,
+                                                                                  d_skip_mid, d_skip_end));
+  WB_CUDA_CHECK(cudaGetLastError());
+  if (rng.record_skip_out) WB_CUDA_CHECK(cudaEventRecord(rng.record_skip_out, stream));
+  if ((rc = wb_rng_fill(rng.state, d_skip_mid, d_offsets + f0_length, max_noise_body, d_noise, stream))) return rc;
   {
     BodyParams p;
     p.x = d_x; p.x_length = x_length; p.tpos = d_tpos; p.f0 = d_f0; p.ap0 = d_ap0; p.f0_length = f0_length;
@@ -539,5 +544,5 @@ int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int
     if (rc) return rc;
     WB_CUDA_CHECK(cudaGetLastError());
   }
-  return wb_rng_advance(d_rng, d_offsets + f0_length, stream);
+  return rng.advance ? wb_rng_advance(rng.state, d_skip_end, nullptr, stream) : WB_OK;
 }

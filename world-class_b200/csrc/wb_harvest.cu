@@ -153,7 +153,8 @@ __global__ void __launch_bounds__(DEC_THREADS) dec_forward_kernel(const double *
 // harvest.cpp:231-232,242.  y[m], m in [0, y_length).
 __global__ void __launch_bounds__(DEC_THREADS) dec_backward_kernel(const double *__restrict__ fwd, int len1, int len2,
                                                                    int r, int lag, DecimCoef c, int y_length,
-                                                                   double *__restrict__ y) {
+                                                                   double *__restrict__ y,
+                                                                   unsigned long long *__restrict__ absmax_bits) {
   extern __shared__ double dec_smem[];
   double *s_in = dec_smem;
   // reversed index u = len2 - 1 - i runs forward in filter time
@@ -165,7 +166,8 @@ __global__ void __launch_bounds__(DEC_THREADS) dec_backward_kernel(const double 
   }
   __syncthreads();
   const int begin = tile_begin + threadIdx.x * DEC_CHUNK;
-  if (begin >= len2) return;
+  double amax = 0.0;  // max |y| over the samples this thread writes (feeds the DC "correction" below)
+  if (begin < len2) {
   const int end = min(len2, begin + DEC_CHUNK);
   const int nout = len1 / r + 1;
   const int nbeg = r - r * nout + len1;
@@ -186,42 +188,46 @@ __global__ void __launch_bounds__(DEC_THREADS) dec_backward_kernel(const double 
       if (i >= nbeg && i < len1 + DEC_NFACT && (i - nbeg) % r == 0) {
         const int cnt = (i - nbeg) / r;
         const int m = cnt - lag / r;
-        if (m >= 0 && m < y_length) y[m] = v;
+        if (m >= 0 && m < y_length) { y[m] = v; amax = fmax(amax, fabs(v)); }
       }
     }
     w2 = w1; w1 = w0; w0 = wt;
   }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  if ((threadIdx.x & 31) == 0 && amax > 0.0) atomicMax(absmax_bits, (unsigned long long)__double_as_longlong(amax));
 }
 
-__global__ void copy_kernel(const double *__restrict__ x, int n, double *__restrict__ y) {
+__global__ void copy_kernel(const double *__restrict__ x, int n, double *__restrict__ y,
+                            unsigned long long *__restrict__ absmax_bits) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) y[i] = x[i];
+  double v = 0.0;
+  if (i < n) { v = x[i]; y[i] = v; v = fabs(v); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0 && v > 0.0) atomicMax(absmax_bits, (unsigned long long)__double_as_longlong(v));
 }
 
 // harvest.cpp:238-241: `accumulate(y_, y_ + y_length_, 0)` has an int accumulator, i.e. the
 // running sum is truncated towards zero after every addition.  If every |y| < 1 the result is
-// exactly 0 (the normal case); otherwise replay the truncating recurrence sequentially.
-__global__ void dc_absmax_kernel(const double *__restrict__ y, int n, unsigned long long *__restrict__ absmax_bits) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  double v = (i < n) ? fabs(y[i]) : 0.0;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-  if ((threadIdx.x & 31) == 0) atomicMax(absmax_bits, (unsigned long long)__double_as_longlong(v));
-}
-__global__ void dc_mean_kernel(const double *__restrict__ y, int n, const unsigned long long *__restrict__ absmax_bits,
-                               double *__restrict__ mean_out) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// exactly 0 and y is left alone (the normal case, decided from the max |y| gathered by the
+// producer); otherwise the truncating recurrence is replayed sequentially.  One CTA.
+__global__ void __launch_bounds__(1024) dc_fix_kernel(double *__restrict__ y, int n,
+                                                      const unsigned long long *__restrict__ absmax_bits) {
+  __shared__ double s_mean;
   const double amax = __longlong_as_double((long long)*absmax_bits);
-  if (amax < 1.0) { *mean_out = 0.0; return; }
-  int acc = 0;
-  for (int i = 0; i < n; ++i) acc = (int)(acc + y[i]);
-  double mean_y = acc;
-  mean_y /= n;
-  *mean_out = mean_y;
-}
-__global__ void dc_subtract_kernel(double *__restrict__ y, int n, const double *__restrict__ mean) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) y[i] -= *mean;
+  if (amax < 1.0) return;
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int i = 0; i < n; ++i) acc = (int)(acc + y[i]);
+    double mean_y = acc;
+    mean_y /= n;
+    s_mean = mean_y;
+  }
+  __syncthreads();
+  const double mean = s_mean;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) y[i] -= mean;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -377,137 +383,166 @@ __global__ void __launch_bounds__(CH_THREADS) channel_kernel(ChanParams p) {
   }
 }
 
-// gathers the per-block edge runs of one (channel, kind) into one ordered list and derives the
-// interval locations / values of zeroCrossingEngine (harvest.cpp:1208-1211)
-__global__ void edge_compact_kernel(const double *__restrict__ seg_edges, const int *__restrict__ seg_count,
-                                    int n_blocks, int bcap, double *__restrict__ edges, int *__restrict__ ecount,
-                                    int ecap, double fs, double *__restrict__ locs, double *__restrict__ vals) {
-  __shared__ int s_off[64];
-  const int ct = blockIdx.x;  // channel * 4 + kind
-  const int *cnt = seg_count + (size_t)ct * n_blocks;
-  if (threadIdx.x == 0) {
-    int run = 0;
-    for (int b = 0; b < n_blocks; ++b) { s_off[b] = run; run += cnt[b]; }
-    s_off[n_blocks] = run;
-    ecount[ct] = min(run, ecap);
-  }
-  __syncthreads();
-  for (int b = 0; b < n_blocks; ++b) {
-    const int o = s_off[b], n = s_off[b + 1] - o;
-    const double *src = seg_edges + ((size_t)ct * n_blocks + b) * bcap;
-    for (int i = threadIdx.x; i < n; i += blockDim.x)
-      if (o + i < ecap) edges[(size_t)ct * ecap + o + i] = src[i];
-  }
-  __syncthreads();
-  const int total = min(s_off[n_blocks], ecap);
-  const double *e = edges + (size_t)ct * ecap;
-  for (int k = threadIdx.x; k + 1 < total; k += blockDim.x) {
-    const double e0 = e[k], e1 = e[k + 1];
-    vals[(size_t)ct * ecap + k] = fs / (e1 - e0);
-    locs[(size_t)ct * ecap + k] = (e0 + e1) / 2.0 / fs;
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
-// getF0CandidateContour (harvest.cpp:1098-1143): interp1 of the four interval sequences to the
-// 1 ms frame grid + gating.  One thread per (channel, frame).
+// zeroCrossingEngine's interval sequences (harvest.cpp:1208-1211) and getF0CandidateContour's four
+// interp1 calls (harvest.cpp:1098-1143, world_matlabfunctions.cpp:136-182), evaluated in the INVERSE
+// direction: instead of every frame searching the interval list (a chain of dependent loads), every
+// interval writes the frames it covers.  One CTA per (channel, kind).
 // ---------------------------------------------------------------------------------------------
-struct RawParams {
-  const double *locs; const double *vals; const int *ecount; int ecap;
-  const double *boundary_f0; int nch; int f0_length; double actual_fs;
-  double f0_floor; double f0_ceil; int frame_period;
-  double *raw;  // [nch][f0_length]
+struct IntervalParams {
+  const double *seg_edges; const int *seg_count; int n_blocks; int bcap;
+  double *edges; int *ecount; int ecap; double fs;
+  double *locs; double *vals;
+  int f0_length; int frame_period;
+  const double *t_tab;  // [f0_length] frame times
+  double *contour;  // [nch * 4][f0_length]: interpolated interval frequency per frame
 };
 
+// smallest frame i in [0, L] with t_i >= x; t_tab[i] = i * frame_period / 1000.0 (the reference's own
+// expression, tabulated so that the frame loop has no division for it)
+__device__ __forceinline__ int iv_first_frame(double x, double frames_per_second, const double *__restrict__ t_tab, int L) {
+  int g = static_cast<int>(ceil(x * frames_per_second));
+  g = wb_max_i(0, wb_min_i(L, g));
+  while (g > 0 && t_tab[g - 1] >= x) --g;
+  while (g < L && t_tab[g] < x) ++g;
+  return g;
+}
 
-__global__ void raw_candidate_kernel(RawParams p) {
+__global__ void frame_time_kernel(int n, int frame_period, double *__restrict__ t_tab) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int c = blockIdx.y;
-  if (i >= p.f0_length) return;
-  const int *cnt = p.ecount + c * 4;
-  double *out = p.raw + (size_t)c * p.f0_length;
-  // number of intervals = edges - 1 (0 if fewer than 2 edges); all four must exceed 2
-  bool ok = true;
-#pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    const int ni = cnt[t] < 2 ? 0 : cnt[t] - 1;
-    if (ni - 2 <= 0) ok = false;
+  if (i < n) t_tab[i] = i * frame_period / 1000.0;
+}
+
+#define IV_THREADS 1024
+#define IV_PER_ITER ((IV_THREADS / 32) * 31)
+__global__ void __launch_bounds__(IV_THREADS) interval_kernel(IntervalParams p) {
+  __shared__ int s_off[64];
+  const int ct = blockIdx.x;  // channel * 4 + kind
+  const int *cnt = p.seg_count + (size_t)ct * p.n_blocks;
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int b = 0; b < p.n_blocks; ++b) { s_off[b] = run; run += cnt[b]; }
+    s_off[p.n_blocks] = run;
+    p.ecount[ct] = min(run, p.ecap);
   }
-  if (!ok) { out[i] = 0.0; return; }
-  const double t_i = i * p.frame_period / 1000.0;
-  double v[4];
-#pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    const double *loc = p.locs + ((size_t)c * 4 + t) * p.ecap;
-    const double *val = p.vals + ((size_t)c * 4 + t) * p.ecap;
-    const int ni = cnt[t] - 1;
-    // histc: first k with loc[k] > t_i, clamped to [1, ni - 1]
-    int lo = 0, hi = ni;
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (loc[mid] > t_i) hi = mid; else lo = mid + 1;
+  __syncthreads();
+  double *e = p.edges + (size_t)ct * p.ecap;
+  for (int b = 0; b < p.n_blocks; ++b) {
+    const int o = s_off[b], n = s_off[b + 1] - o;
+    const double *src = p.seg_edges + ((size_t)ct * p.n_blocks + b) * p.bcap;
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+      if (o + i < p.ecap) e[o + i] = src[i];
+  }
+  __syncthreads();
+  const int total = min(s_off[p.n_blocks], p.ecap);
+  const int ni = total < 2 ? 0 : total - 1;  // number of intervals
+  double *loc = p.locs + (size_t)ct * p.ecap, *val = p.vals + (size_t)ct * p.ecap;
+  double *out = p.contour + (size_t)ct * p.f0_length;
+  const double fs = p.fs;
+  const int L = p.f0_length;
+  const double *t_tab = p.t_tab;
+  const double frames_per_second = 1000.0 / p.frame_period;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // Lanes 1..31 of a warp own 31 consecutive intervals; lane 0 recomputes the interval before them, so
+  // every owner gets its left knot (and the first frame at or after it) with one shuffle.
+  for (int k0 = 0; k0 < ni; k0 += IV_PER_ITER) {
+    const int k = k0 + warp * 31 + lane - 1;
+    double x1 = 0.0, y1 = 0.0;
+    int f1 = L;
+    if (k >= 0 && k < ni) {
+      const double e0 = e[k], e1 = e[k + 1];
+      y1 = fs / (e1 - e0);
+      x1 = (e0 + e1) / 2.0 / fs;
+      if (lane > 0) { val[k] = y1; loc[k] = x1; }
+      if (k < ni - 1) f1 = iv_first_frame(x1, frames_per_second, t_tab, L);
     }
-    int k = lo;
-    if (k < 1) k = 1;
-    if (k > ni - 1) k = ni - 1;
-    const double x0 = loc[k - 1], x1 = loc[k];
-    const double y0 = val[k - 1], y1 = val[k];
-    const double s = (t_i - x0) / (x1 - x0);
-    v[t] = y0 + s * (y1 - y0);
+    const double x0 = __shfl_up_sync(0xffffffffu, x1, 1);
+    const double y0 = __shfl_up_sync(0xffffffffu, y1, 1);
+    const int f0 = __shfl_up_sync(0xffffffffu, f1, 1);
+    // interp1's histc puts frame t between knots k - 1 and k when loc[k-1] <= t < loc[k]; the index is
+    // clamped to [1, ni - 1], i.e. the first and last knot pairs extrapolate (needs ni > 2, checked by
+    // the consumer exactly like harvest.cpp:1113-1117)
+    if (lane > 0 && k >= 1 && k < ni && ni > 2) {
+      const int i_lo = (k > 1) ? f0 : 0;
+      const double dx = x1 - x0, dy = y1 - y0;
+      for (int i = i_lo; i < f1; ++i) {
+        const double s = (t_tab[i] - x0) / dx;
+        out[i] = y0 + s * dy;
+      }
+    }
   }
-  const double bf = p.boundary_f0[c];
-  const double upper = bf * 1.1, lower = bf * 0.9;
-  double f = (v[0] + v[1] + v[2] + v[3]) / 4.0;
-  if (f > upper || f < lower || f > p.f0_ceil || f < p.f0_floor) f = 0.0;
-  out[i] = f;
 }
 
 // ---------------------------------------------------------------------------------------------
-// detectOfficialF0Candidates (harvest.cpp:1005-1083): one thread per frame
+// getF0CandidateContour's gating (harvest.cpp:1126-1142) + detectOfficialF0Candidates
+// (harvest.cpp:1005-1083).  One CTA per 32 frames: the warps sweep the channels (coalesced reads of
+// the four contours), the gated raw candidates of the tile go to shared memory, then one thread
+// per frame runs the reference's run-length scan over the channels and appends the frame's
+// candidates to the refinement work list.
 // ---------------------------------------------------------------------------------------------
-__global__ void detect_kernel(const double *__restrict__ raw, int nch, int f0_length, int own_cap,
-                              double *__restrict__ own /*[f0_length][own_cap]*/, int *__restrict__ nc_max) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= f0_length) return;
-  double *dst = own + (size_t)i * own_cap;
+struct CandParams {
+  const double *contour; const int *ecount; const double *boundary_f0;
+  int nch; int f0_length; double f0_floor; double f0_ceil;
+  double *raw;       // [nch][f0_length]
+  double *own;       // [f0_length][own_cap]
+  int own_cap;
+  int *nc_max;       // [0] = max candidates per frame, [1] = work count
+  int *work;         // frame * 32 + j of every own candidate
+};
+
+#define CD_FRAMES 32
+#define CD_PITCH 33
+#define CD_THREADS 1024
+__global__ void __launch_bounds__(CD_THREADS) candidate_kernel(CandParams p) {
+  extern __shared__ double cd_tile[];  // [nch][CD_PITCH]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int L = p.f0_length;
+  const int f = blockIdx.x * CD_FRAMES + lane;
+  for (int c = warp; c < p.nch; c += CD_THREADS / 32) {
+    const int *cnt = p.ecount + c * 4;
+    bool ok = true;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int ni = cnt[t] < 2 ? 0 : cnt[t] - 1;
+      if (ni - 2 <= 0) ok = false;
+    }
+    double v = 0.0;
+    if (ok && f < L) {
+      const double *src = p.contour + (size_t)c * 4 * L + f;
+      const double v0 = src[0], v1 = src[L], v2 = src[2 * (size_t)L], v3 = src[3 * (size_t)L];
+      const double bf = p.boundary_f0[c];
+      const double upper = bf * 1.1, lower = bf * 0.9;
+      v = (v0 + v1 + v2 + v3) / 4.0;
+      if (v > upper || v < lower || v > p.f0_ceil || v < p.f0_floor) v = 0.0;
+    }
+    if (f < L) p.raw[(size_t)c * L + f] = v;
+    cd_tile[c * CD_PITCH + lane] = v;
+  }
+  __syncthreads();
+  if (warp != 0 || f >= L) return;
+  double *dst = p.own + (size_t)f * p.own_cap;
+  const int nch = p.nch;
   int count = 0;
   int prev = 0, st = 0;
   double acc = 0.0;
   for (int j = 1; j < nch; ++j) {
     // vuv[0] = vuv[nch-1] = 0
-    const double r = raw[(size_t)j * f0_length + i];
+    const double r = cd_tile[j * CD_PITCH + lane];
     const int cur = (j == nch - 1) ? 0 : (r > 0 ? 1 : 0);
     if (cur - prev == 1) { st = j; acc = 0.0; }
     if (cur == 1) acc += r;
     if (cur - prev == -1) {
       const int ed = j;
-      if (ed - st >= 10 && count < own_cap) dst[count++] = acc / (ed - st);
+      if (ed - st >= 10 && count < p.own_cap) dst[count++] = acc / (ed - st);
     }
     prev = cur;
   }
-  for (int k = count; k < own_cap; ++k) dst[k] = 0.0;
-  if (count > 0) atomicMax(nc_max, count);
-}
-
-// overlapF0Candidates (harvest.cpp:987-1000) + work list of the non-zero candidates
-__global__ void overlap_kernel(const double *__restrict__ own, int own_cap, const int *__restrict__ nc_ptr,
-                               int f0_length, int max_candidates, double *__restrict__ cand /*[f0_length][max_candidates]*/,
-                               double *__restrict__ score, int *__restrict__ work, int *__restrict__ work_count) {
-  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= (long long)f0_length * max_candidates) return;
-  const int k = (int)(g / max_candidates), slot = (int)(g % max_candidates);
-  const int nc = *nc_ptr;
-  double v = 0.0;
-  if (nc > 0 && slot < nc * 7) {
-    const int o = slot / nc, j = slot % nc;
-    int src = k;
-    if (o >= 1 && o <= 3) src = k - o;         // copies from earlier frames
-    else if (o >= 4) src = k + (o - 3);        // copies from later frames
-    if (src >= 0 && src < f0_length) v = own[(size_t)src * own_cap + j];
+  for (int k = count; k < p.own_cap; ++k) dst[k] = 0.0;
+  if (count > 0) {
+    atomicMax(p.nc_max, count);
+    const int at = atomicAdd(p.nc_max + 1, count);
+    for (int j = 0; j < count; ++j) p.work[at + j] = f * 32 + j;
   }
-  cand[g] = v;
-  score[g] = 0.0;
-  if (v > 0.0) work[atomicAdd(work_count, 1)] = k * 128 + slot;  // max_candidates <= 128 checked on the host
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -516,9 +551,10 @@ __global__ void overlap_kernel(const double *__restrict__ own, int own_cap, cons
 struct RefineParams {
   const double *y; int y_length; double actual_fs;
   double f0_floor, f0_ceil; int frame_period;
-  const int *work; const int *work_count;
+  const int *work; const int *nc_and_count;   // own candidates (frame * 32 + j); [0] = nc, [1] = their number
+  const double *own; int own_cap; int f0_length;
   int max_candidates;
-  double *cand; double *score;
+  double *cand; double *score;                // zero-initialised [f0_length][max_candidates] tables
   const cplx *tw[16];   // twiddle tables by log2(fft_size)
   int max_wlen;         // shared window buffer length per warp
 };
@@ -537,7 +573,11 @@ __device__ __forceinline__ double rf_window(double c) { return 0.42 + 0.5 * c + 
 __global__ void __launch_bounds__(RF_WARPS * 32) refine_kernel(RefineParams p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane & (RF_GROUP - 1), grp = lane / RF_GROUP;
-  const int n_work = *p.work_count;
+  // overlapF0Candidates (harvest.cpp:987-1000): own candidate j of frame src also becomes candidate
+  // j + nc * o of frame src + o (o = 1..3) and of frame src - (o - 3) (o = 4..6); every copy is refined at
+  // its own frame position.  Work item w = 7 * (own candidate) + o.
+  const int nc = p.nc_and_count[0];
+  const int n_work = p.nc_and_count[1] * 7;
   const int groups_per_warp = 32 / RF_GROUP;
   const int total_groups = gridDim.x * RF_WARPS * groups_per_warp;
   const double fs = p.actual_fs;
@@ -546,11 +586,15 @@ __global__ void __launch_bounds__(RF_WARPS * 32) refine_kernel(RefineParams p) {
   const int first = (blockIdx.x * RF_WARPS + warp) * groups_per_warp;
   for (int base = first; base < n_work; base += total_groups) {
     const int wi = base + grp;
-    const bool active = wi < n_work;
-    const int item = active ? p.work[wi] : 0;
-    const int frame = item >> 7, slot = item & 127;
+    bool active = wi < n_work;
+    const int item = active ? p.work[wi / 7] : 0;
+    const int o = wi % 7;
+    const int src = item >> 5, own_j = item & 31;
+    const int frame = (o <= 3) ? src + o : src - (o - 3);
+    const int slot = o * nc + own_j;
+    active = active && frame >= 0 && frame < p.f0_length;
     const size_t at = (size_t)frame * p.max_candidates + slot;
-    const double current_f0 = active ? p.cand[at] : 100.0;
+    const double current_f0 = active ? p.own[(size_t)src * p.own_cap + own_j] : 100.0;
     const double current_position = frame * p.frame_period / 1000.0;
     const int hw = static_cast<int>(1.5 * fs / current_f0 + 1.0);
     const int len = active ? 2 * hw + 1 : 0;
@@ -572,21 +616,22 @@ __global__ void __launch_bounds__(RF_WARPS * 32) refine_kernel(RefineParams p) {
     double s1, c1, sg, cg;
     sincos(two_pi / (2 * hw + 1), &s1, &c1);
     sincos(two_pi * RF_GROUP / (2 * hw + 1), &sg, &cg);
+    // Interior samples of the differentiated window (harvest.cpp:794-803) in closed form: with
+    // w(a) = 0.42 + 0.5 cos a + 0.08 cos 2a,  -(w(a + d) - w(a - d)) / 2 = sin a (0.5 sin d + 0.16 sin 2d cos a)
+    const double dw_a = 0.5 * s1, dw_b = 0.16 * (2.0 * s1 * c1);
     double sn, cs;
     {
       const double tmp = ((basic_index + sub) - 1.0) / fs - current_position;
       sincos(two_pi * tmp / window_length_in_time, &sn, &cs);
     }
+#pragma unroll 2
     for (int i = sub; i < len; i += RF_GROUP) {
       const int safe = wb_max_i(0, wb_min_i(p.y_length - 1, basic_index + i - 1));
       const double yv = p.y[safe];
-      const double w_here = rf_window(cs);
-      const double w_next = rf_window(cs * c1 - sn * s1);  // angle + delta
-      const double w_prev = rf_window(cs * c1 + sn * s1);  // angle - delta
-      double dwin;
-      if (i == 0) dwin = -w_next / 2.0;
-      else if (i == len - 1) dwin = w_prev / 2.0;
-      else dwin = -(w_next - w_prev) / 2.0;
+      const double w_here = fma(cs, fma(0.16, cs, 0.5), 0.34);  // = rf_window(cs)
+      double dwin = sn * fma(dw_b, cs, dw_a);
+      if (i == 0) dwin = -rf_window(cs * c1 - sn * s1) / 2.0;            // -w[1] / 2
+      else if (i == len - 1) dwin = rf_window(cs * c1 + sn * s1) / 2.0;  // w[len - 2] / 2
       const double vm = w_here * yv, vd = dwin * yv;
 #pragma unroll
       for (int hh = 0; hh < 6; ++hh) {
@@ -596,45 +641,70 @@ __global__ void __launch_bounds__(RF_WARPS * 32) refine_kernel(RefineParams p) {
           dr[hh] = fma(vd, w.x, dr[hh]); di[hh] = fma(vd, w.y, di[hh]);
         }
       }
-      const double c2 = cs * cg - sn * sg;
-      sn = sn * cg + cs * sg;
+      const double c2 = fma(cs, cg, -(sn * sg));
+      sn = fma(sn, cg, cs * sg);
       cs = c2;
     }
-    // reduce over the 8 lanes of the group
+    // Reduce-scatter over the 8 lanes of the group: three exchange steps (lane ^ 4, ^ 2, ^ 1), each lane
+    // keeping half of the harmonic slots it still holds, leave lane `sub` with the complete sums of
+    // harmonic `sub` (slots 6 and 7 are empty) -- 28 exchanges instead of 72 for a full butterfly.
+    double my_mr, my_mi, my_dr, my_di;
+    {
+      const bool up4 = (sub & 4) != 0, up2 = (sub & 2) != 0, up1 = (sub & 1) != 0;
+      double a4[4][4];
 #pragma unroll
-    for (int hh = 0; hh < 6; ++hh) {
+      for (int q = 0; q < 4; ++q) {
+        const double lo[4] = {mr[q], mi[q], dr[q], di[q]};
+        const bool has_hi = q < 2;          // harmonic slots 6 and 7 do not exist
+        const int qh = has_hi ? q + 4 : 0;
+        const double hi[4] = {has_hi ? mr[qh] : 0.0, has_hi ? mi[qh] : 0.0, has_hi ? dr[qh] : 0.0, has_hi ? di[qh] : 0.0};
 #pragma unroll
-      for (int o = RF_GROUP / 2; o > 0; o >>= 1) {
-        mr[hh] += __shfl_xor_sync(0xffffffffu, mr[hh], o);
-        mi[hh] += __shfl_xor_sync(0xffffffffu, mi[hh], o);
-        dr[hh] += __shfl_xor_sync(0xffffffffu, dr[hh], o);
-        di[hh] += __shfl_xor_sync(0xffffffffu, di[hh], o);
+        for (int c = 0; c < 4; ++c) {
+          const double send = up4 ? lo[c] : hi[c];
+          a4[q][c] = (up4 ? hi[c] : lo[c]) + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
       }
+      double a2[2][4];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const double send = up2 ? a4[q][c] : a4[q + 2][c];
+          a2[q][c] = (up2 ? a4[q + 2][c] : a4[q][c]) + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+      }
+      double a1[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const double send = up1 ? a2[0][c] : a2[1][c];
+        a1[c] = (up1 ? a2[1][c] : a2[0][c]) + __shfl_xor_sync(0xffffffffu, send, 1);
+      }
+      my_mr = a1[0]; my_mi = a1[1]; my_dr = a1[2]; my_di = a1[3];
     }
-    // fixF0 (harvest.cpp:844-878): sub-lane hh evaluates harmonic hh (divisions, sqrt in parallel),
-    // then every lane accumulates in the reference's order.
+    // fixF0 (harvest.cpp:844-878): lane `sub` evaluates harmonic `sub` (divisions, sqrt in parallel, no
+    // divergence), then every lane accumulates in the reference's order.
     // spectra are conjugated by the reference (harvest.cpp:829-841): main = (mr, -mi), diff = (dr, -di)
-    double my_inst = 0.0, my_amp = 0.0;
-#pragma unroll
-    for (int hh = 0; hh < 6; ++hh) {
-      if (sub == hh && hh < nh) {
-        const double m_re = mr[hh], m_im = -mi[hh], d_re = dr[hh], d_im = -di[hh];
-        const double power = m_re * m_re + m_im * m_im;
-        const double num_i = m_re * d_im - m_im * d_re;
-        my_inst = (power == 0.0) ? 0.0
-                  : static_cast<double>(idx[hh]) * fs / fft_size + num_i / power * fs / 2.0 / WB_PI;
-        my_amp = sqrt(power);
-      }
+    double my_inst = 0.0, my_amp = 0.0, my_dev = 0.0;
+    {
+      const double m_re = my_mr, m_im = -my_mi, d_re = my_dr, d_im = -my_di;
+      const int my_idx = wb_round(current_f0 * fft_size / fs * (sub + 1));
+      const double power = m_re * m_re + m_im * m_im;
+      const double num_i = m_re * d_im - m_im * d_re;
+      my_inst = (power == 0.0) ? 0.0
+                : static_cast<double>(my_idx) * fs / fft_size + num_i / power * fs / 2.0 / WB_PI;
+      my_amp = sqrt(power);
+      my_dev = fabs((my_inst / (sub + 1.0) - current_f0) / current_f0);
     }
     double numerator = 0.0, denominator = 0.0, score = 0.0;
 #pragma unroll
     for (int hh = 0; hh < 6; ++hh) {
       const double inst = __shfl_sync(0xffffffffu, my_inst, hh, RF_GROUP);
       const double amp = __shfl_sync(0xffffffffu, my_amp, hh, RF_GROUP);
+      const double dev = __shfl_sync(0xffffffffu, my_dev, hh, RF_GROUP);
       if (hh < nh) {
         numerator += amp * inst;
         denominator += amp * (hh + 1.0);
-        score += fabs((inst / (hh + 1.0) - current_f0) / current_f0);
+        score += dev;
       }
     }
     if (sub == 0 && active) {
@@ -769,9 +839,11 @@ int wb_harvest_run_basic(WbHarvestPlan *pl, WbWorkspace *ws, const double *d_x, 
 
   // ---- H1/H2: decimated, DC-"corrected" waveform
   double *d_y = (double *)ws->get("hv_y", sizeof(double) * (y_length + 8));
-  if (!d_y) return WB_ERR_CUDA;
+  unsigned long long *d_absmax = (unsigned long long *)ws->get("hv_absmax", 16);
+  if (!d_y || !d_absmax) return WB_ERR_CUDA;
+  WB_CUDA_CHECK(cudaMemsetAsync(d_absmax, 0, 8, stream));
   if (r == 1) {
-    WB_LAUNCH("copy_kernel", copy_kernel<<<(x_length + 255) / 256, 256, 0, stream>>>(d_x, x_length, d_y));  // y_length = x_length + 1: last is zero
+    WB_LAUNCH("copy_kernel", copy_kernel<<<(x_length + 255) / 256, 256, 0, stream>>>(d_x, x_length, d_y, d_absmax));  // y_length = x_length + 1: last is zero
     WB_CUDA_CHECK(cudaMemsetAsync(d_y + x_length, 0, sizeof(double) * (y_length - x_length), stream));
   } else {
     const int lag = static_cast<int>(ceil(140.0 / r) * r);                               // harvest.cpp:222
@@ -788,15 +860,9 @@ int wb_harvest_run_basic(WbHarvestPlan *pl, WbWorkspace *ws, const double *d_x, 
     WB_CUDA_CHECK(cudaFuncSetAttribute(dec_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_smem_b));
     WB_CUDA_CHECK(cudaMemsetAsync(d_y, 0, sizeof(double) * y_length, stream));            // new_y is zero-initialised
     WB_LAUNCH("dec_forward_kernel", dec_forward_kernel<<<n_tiles, DEC_THREADS, dec_smem_f, stream>>>(d_x, x_length, lag, len1, len2, dc, d_fwd));
-    WB_LAUNCH("dec_backward_kernel", dec_backward_kernel<<<n_tiles, DEC_THREADS, dec_smem_b, stream>>>(d_fwd, len1, len2, r, lag, dc, y_length, d_y));
+    WB_LAUNCH("dec_backward_kernel", dec_backward_kernel<<<n_tiles, DEC_THREADS, dec_smem_b, stream>>>(d_fwd, len1, len2, r, lag, dc, y_length, d_y, d_absmax));
   }
-  unsigned long long *d_absmax = (unsigned long long *)ws->get("hv_absmax", 16);
-  double *d_mean = (double *)ws->get("hv_mean", 16);
-  if (!d_absmax || !d_mean) return WB_ERR_CUDA;
-  WB_CUDA_CHECK(cudaMemsetAsync(d_absmax, 0, 8, stream));
-  WB_LAUNCH("dc_absmax_kernel", dc_absmax_kernel<<<(y_length + 255) / 256, 256, 0, stream>>>(d_y, y_length, d_absmax));
-  WB_LAUNCH("dc_mean_kernel", dc_mean_kernel<<<1, 32, 0, stream>>>(d_y, y_length, d_absmax, d_mean));
-  WB_LAUNCH("dc_subtract_kernel", dc_subtract_kernel<<<(y_length + 255) / 256, 256, 0, stream>>>(d_y, y_length, d_mean));
+  WB_LAUNCH("dc_fix_kernel", dc_fix_kernel<<<1, 1024, 0, stream>>>(d_y, y_length, d_absmax));
   WB_CUDA_CHECK(cudaGetLastError());
 
   // ---- H3: overlap-save block spectra
@@ -836,42 +902,59 @@ int wb_harvest_run_basic(WbHarvestPlan *pl, WbWorkspace *ws, const double *d_x, 
     });
     if (rc) return rc;
     WB_CUDA_CHECK(cudaGetLastError());
-    WB_LAUNCH("edge_compact_kernel", edge_compact_kernel<<<nch * 4, 256, 0, stream>>>(d_seg, d_segc, n_blocks, bcap, d_edges, d_ecount, ecap, afs, d_locs, d_vals));
     WB_CUDA_CHECK(cudaGetLastError());
   }
 
-  // ---- raw candidates on the frame grid
-  double *d_raw = (double *)ws->get("hv_raw", sizeof(double) * (size_t)nch * Lb);
-  if (!d_raw) return WB_ERR_CUDA;
+  // ---- interval sequences -> the four interpolated contours on the frame grid
+  double *d_contour = (double *)ws->get("hv_contour", sizeof(double) * (size_t)nch * 4 * Lb);
+  if (!d_contour) return WB_ERR_CUDA;
   {
-    RawParams p;
-    p.locs = d_locs; p.vals = d_vals; p.ecount = d_ecount; p.ecap = ecap; p.boundary_f0 = (const double *)ws->get("hv_bf", 0);
-    p.nch = nch; p.f0_length = Lb; p.actual_fs = afs; p.f0_floor = pl->opt.f0_floor; p.f0_ceil = pl->opt.f0_ceil;
-    p.frame_period = frame_period; p.raw = d_raw;
-    dim3 grid((Lb + 255) / 256, nch);
-    WB_LAUNCH("raw_candidate_kernel", raw_candidate_kernel<<<grid, 256, 0, stream>>>(p));
+    IntervalParams p;
+    p.seg_edges = d_seg; p.seg_count = d_segc; p.n_blocks = n_blocks; p.bcap = bcap;
+    p.edges = d_edges; p.ecount = d_ecount; p.ecap = ecap; p.fs = afs; p.locs = d_locs; p.vals = d_vals;
+    p.f0_length = Lb; p.frame_period = frame_period; p.contour = d_contour;
+    // frame times: a function of (Lb, frame_period) only, tabulated once per plan and length
+    double *d_ttab = (double *)ws->get("hv_ttab", sizeof(double) * Lb);
+    if (!d_ttab) return WB_ERR_CUDA;
+    if (pl->ttab_len != Lb || pl->ttab_period != frame_period || pl->ttab_ptr != (const void *)d_ttab) {
+      WB_LAUNCH("frame_time_kernel", frame_time_kernel<<<(Lb + 255) / 256, 256, 0, stream>>>(Lb, frame_period, d_ttab));
+      pl->ttab_len = Lb; pl->ttab_period = frame_period; pl->ttab_ptr = d_ttab;
+    }
+    p.t_tab = d_ttab;
+    WB_LAUNCH("interval_kernel", interval_kernel<<<nch * 4, IV_THREADS, 0, stream>>>(p));
     WB_CUDA_CHECK(cudaGetLastError());
   }
 
-  // ---- official candidates, overlap, refine, prune
+  // ---- raw candidates, official candidates, refinement work list
+  double *d_raw = (double *)ws->get("hv_raw", sizeof(double) * (size_t)nch * Lb);
   double *d_own = (double *)ws->get("hv_own", sizeof(double) * (size_t)Lb * own_cap);
   int *d_nc = (int *)ws->get("hv_nc", 16);
-  int *d_work = (int *)ws->get("hv_work", sizeof(int) * (size_t)Lb * MC);
-  double *d_candA = (double *)ws->get("hv_candA", sizeof(double) * (size_t)Lb * MC);
-  double *d_scoreA = (double *)ws->get("hv_scoreA", sizeof(double) * (size_t)Lb * MC);
+  int *d_work = (int *)ws->get("hv_work", sizeof(int) * (size_t)Lb * own_cap);
+  double *d_candA = (double *)ws->get("hv_candA", sizeof(double) * (size_t)Lb * MC * 2);   // cand | score, one memset
   double *d_candB = (double *)ws->get("hv_candB", sizeof(double) * (size_t)Lb * MC);
   double *d_scoreB = (double *)ws->get("hv_scoreB", sizeof(double) * (size_t)Lb * MC);
-  if (!d_own || !d_nc || !d_work || !d_candA || !d_scoreA || !d_candB || !d_scoreB) return WB_ERR_CUDA;
-  WB_CUDA_CHECK(cudaMemsetAsync(d_nc, 0, 16, stream));  // [0] = nc, [1] = work count
-  WB_LAUNCH("detect_kernel", detect_kernel<<<(Lb + 127) / 128, 128, 0, stream>>>(d_raw, nch, Lb, own_cap, d_own, d_nc));
+  if (!d_raw || !d_own || !d_nc || !d_work || !d_candA || !d_candB || !d_scoreB) return WB_ERR_CUDA;
+  double *d_scoreA = d_candA + (size_t)Lb * MC;
+  if (own_cap > 32) return WB_ERR_UNSUPPORTED;
+  WB_CUDA_CHECK(cudaMemsetAsync(d_nc, 0, 16, stream));  // [0] = nc, [1] = number of own candidates
+  WB_CUDA_CHECK(cudaMemsetAsync(d_candA, 0, sizeof(double) * (size_t)Lb * MC * 2, stream));
+  {
+    CandParams p;
+    p.contour = d_contour; p.ecount = d_ecount; p.boundary_f0 = (const double *)ws->get("hv_bf", 0);
+    p.nch = nch; p.f0_length = Lb; p.f0_floor = pl->opt.f0_floor; p.f0_ceil = pl->opt.f0_ceil;
+    p.raw = d_raw; p.own = d_own; p.own_cap = own_cap; p.nc_max = d_nc; p.work = d_work;
+    const size_t smem = sizeof(double) * (size_t)nch * CD_PITCH;
+    if (smem > 200 * 1024) return WB_ERR_UNSUPPORTED;
+    WB_CUDA_CHECK(cudaFuncSetAttribute(candidate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WB_LAUNCH("candidate_kernel", candidate_kernel<<<(Lb + CD_FRAMES - 1) / CD_FRAMES, CD_THREADS, smem, stream>>>(p));
+    WB_CUDA_CHECK(cudaGetLastError());
+  }
   const long long n_cs = (long long)Lb * MC;
-  WB_LAUNCH("overlap_kernel", overlap_kernel<<<(unsigned)((n_cs + 255) / 256), 256, 0, stream>>>(d_own, own_cap, d_nc, Lb, MC, d_candA, d_scoreA,
-                                                                    d_work, d_nc + 1));
-  WB_CUDA_CHECK(cudaGetLastError());
   {
     RefineParams p;
     p.y = d_y; p.y_length = y_length; p.actual_fs = afs; p.f0_floor = pl->opt.f0_floor; p.f0_ceil = pl->opt.f0_ceil;
-    p.frame_period = frame_period; p.work = d_work; p.work_count = d_nc + 1; p.max_candidates = MC;
+    p.frame_period = frame_period; p.work = d_work; p.nc_and_count = d_nc; p.max_candidates = MC;
+    p.own = d_own; p.own_cap = own_cap; p.f0_length = Lb;
     p.cand = d_candA; p.score = d_scoreA;
     // candidates are in [f0_floor, f0_ceil] of the raw stage: half window <= 1.5 fs / (0.9 floor) + 1
     const int max_hw = static_cast<int>(1.5 * afs / (pl->opt.f0_floor * 0.9) + 1.0) + 1;

@@ -21,6 +21,9 @@ struct WbHarvestPlan {
   int NB, V;                        // overlap-save block size and hop
   double decim_coef[5];             // a[3], b[2]
   bool filters_ready;
+  // frame-time table of the interval stage (valid for this length / period / buffer)
+  int ttab_len = 0, ttab_period = 0;
+  const void *ttab_ptr = nullptr;
 };
 
 int wb_harvest_plan_init(WbHarvestPlan *pl, int fs, const WbHarvestOptionInternal &opt);

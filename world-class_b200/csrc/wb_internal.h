@@ -24,13 +24,15 @@ class WbWorkspace {
 // e^{+2 pi i k / n}, k = 0..n-1, on the device; cached per n (power of two).
 const cplx *wb_twiddle_table(int n);
 
-// offsets[0..n] <- exclusive prefix sums of counts[0..n) (offsets[n] = total)
+// offsets[0..n] <- exclusive prefix sums of counts[0..n) (offsets[n] = total); optionally publishes
+// *d_skip_out = *d_skip_in + total (randn stream bookkeeping, see WbRngCursor)
 int wb_exclusive_scan_u64(const unsigned long long *d_counts, unsigned long long *d_offsets, int n,
-                          cudaStream_t stream);
+                          cudaStream_t stream, const unsigned long long *d_skip_in = nullptr,
+                          unsigned long long *d_skip_out = nullptr);
 
 int wb_cheaptrick_run(WbWorkspace *ws, int fs, int fft_size, double q1, double f0_floor_internal,
                       const double *d_x, int x_length, const double *d_tpos, const double *d_f0,
-                      int f0_length, double *d_sp, WbRngState *d_rng, cudaStream_t stream);
+                      int f0_length, double *d_sp, const WbRngCursor &rng, cudaStream_t stream);
 
 // stand-alone batched transforms (wb_fftapi.cu); kind 0 r2c, 1 c2r, 2 c2c fwd, 3 c2c bwd
 int wb_fft_batch_dev(int kind, const void *d_in, int n, int batch, void *d_out, cudaStream_t stream);
@@ -40,18 +42,20 @@ int wb_d4c_fft_size(int fs);
 int wb_d4c_lt_fft_size(int fs);
 int wb_number_of_aperiodicities(int fs);
 int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int x_length, const double *d_tpos,
-               const double *d_f0, int f0_length, int out_fft_size, double *d_ap, WbRngState *d_rng,
+               const double *d_f0, int f0_length, int out_fft_size, double *d_ap, const WbRngCursor &rng,
                cudaStream_t stream);
 
 // Synthesis (wb_synthesis.cu)
 int wb_synthesis_run(WbWorkspace *ws, int fs, int fft_size, double frame_period_ms, const double *d_f0,
                      int f0_length, const double *d_sp, const double *d_ap, int out_length, double *d_out,
-                     double f0_upper_bound, WbRngState *d_rng, cudaStream_t stream);
+                     double f0_upper_bound, const WbRngCursor &rng, cudaStream_t stream);
 int wb_synthesis_timebase(WbWorkspace *ws, int fs, int fft_size, double frame_period_ms, const double *d_f0,
-                          int f0_length, int out_length, cudaStream_t stream);
+                          int f0_length, int out_length, cudaStream_t stream,
+                          const WbRngCursor *noise_cursor = nullptr);
 int wb_synthesis_render(WbWorkspace *ws, int fs, int fft_size, double frame_period_ms, int f0_length,
                         const double *d_sp, const double *d_ap, int out_length, double *d_out,
-                        double f0_upper_bound, WbRngState *d_rng, cudaStream_t stream);
+                        double f0_upper_bound, const WbRngCursor &rng, cudaStream_t stream,
+                        bool noise_ready = false);
 
 // codec (wb_codec.cu)
 int wb_code_aperiodicity_dev(const double *d_ap, int f0_length, int fs, int fft_size, double *d_coded,

@@ -68,38 +68,64 @@ int do_init() {
   return WB_OK;
 }
 
-#define WB_RNG_CHUNK 64
-
-// Two-level jump: warp 0 jumps cooperatively to the block's first stream position (one table
-// load per lane and matrix), every thread then only jumps by tid * WB_RNG_CHUNK, which touches
-// the same seven small tables in every block (L1-resident).
-__global__ void __launch_bounds__(128) rng_fill_kernel(const WbRngState *__restrict__ state,
-                                                       const uint4 *__restrict__ pow_tables,
-                                                       const unsigned long long *__restrict__ d_count,
-                                                       unsigned long long max_count, double *__restrict__ out) {
-  __shared__ uint32_t s_base[4];
+// Fill kernel.  A thread produces WB_RNG_CHUNK consecutive values, a warp 32 chunks, a CTA one tile
+// of RNG_TILE values per iteration (persistent CTAs stride over the tiles).  Jump-ahead in three
+// levels: every warp jumps cooperatively (one table load per lane and matrix) to its first stream
+// position; a lane then only needs M^(lane * chunk), i.e. five more window tables, which are kept
+// in SHARED memory -- per-thread gathers from the global tables cost ~32 L1 wavefronts per load
+// and used to dominate this kernel.
+#define WB_RNG_CHUNK 32
+#define WB_RNG_LOG2_CHUNK 5
+#define RNG_THREADS 256
+#define RNG_TILE (RNG_THREADS * WB_RNG_CHUNK)
+#define RNG_LANE_TABLES 5
+__global__ void __launch_bounds__(RNG_THREADS) rng_fill_kernel(const WbRngState *__restrict__ state,
+                                                               const uint4 *__restrict__ pow_tables,
+                                                               const unsigned long long *__restrict__ d_skip,
+                                                               const unsigned long long *__restrict__ d_count,
+                                                               unsigned long long max_count, double *__restrict__ out) {
+  __shared__ uint4 s_tab[RNG_LANE_TABLES * WB_RNG_TAB_ENTRIES];  // M^(chunk * 2^j), j = 0..4
   const unsigned long long count = d_count ? min(*d_count, max_count) : max_count;
-  const unsigned long long block_begin = (unsigned long long)blockIdx.x * blockDim.x * WB_RNG_CHUNK;
-  if (block_begin >= count) return;
-  if (threadIdx.x < 32) {
-    uint32_t b[4] = {state->s[0], state->s[1], state->s[2], state->s[3]};
-    wb_rng_jump_warp(pow_tables, b, block_begin);
-    if (threadIdx.x == 0) { s_base[0] = b[0]; s_base[1] = b[1]; s_base[2] = b[2]; s_base[3] = b[3]; }
-  }
+  const unsigned long long n_tiles = (count + RNG_TILE - 1) / RNG_TILE;
+  if ((unsigned long long)blockIdx.x >= n_tiles) return;
+  for (int i = threadIdx.x; i < RNG_LANE_TABLES * WB_RNG_TAB_ENTRIES; i += RNG_THREADS)
+    s_tab[i] = pow_tables[(size_t)WB_RNG_LOG2_CHUNK * WB_RNG_TAB_ENTRIES + i];
   __syncthreads();
-  const unsigned long long begin = block_begin + (unsigned long long)threadIdx.x * WB_RNG_CHUNK;
-  if (begin >= count) return;
-  uint32_t s[4] = {s_base[0], s_base[1], s_base[2], s_base[3]};
-  wb_rng_jump(pow_tables, s, (unsigned long long)threadIdx.x * WB_RNG_CHUNK);
-  const unsigned long long end = min(count, begin + WB_RNG_CHUNK);
-  for (unsigned long long i = begin; i < end; ++i) out[i] = wb_randn_next(s);
+  const unsigned long long skip = d_skip ? *d_skip : 0ull;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t s0 = state->s[0], s1 = state->s[1], s2 = state->s[2], s3 = state->s[3];
+  for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const unsigned long long warp_begin = tile * RNG_TILE + (unsigned long long)warp * 32 * WB_RNG_CHUNK;
+    if (warp_begin >= count) continue;   // uniform per warp
+    uint32_t s[4] = {s0, s1, s2, s3};
+    wb_rng_jump_warp(pow_tables, s, skip + warp_begin);
+#pragma unroll
+    for (int j = 0; j < RNG_LANE_TABLES; ++j)
+      if (lane >> j & 1) wb_rng_apply_shared(s_tab + j * WB_RNG_TAB_ENTRIES, s);
+    const unsigned long long begin = warp_begin + (unsigned long long)lane * WB_RNG_CHUNK;
+    if (begin >= count) continue;
+    double *dst = out + begin;
+    if (begin + WB_RNG_CHUNK <= count) {
+      // out is 16-byte aligned at even offsets: cudaMalloc'ed base, begin is a multiple of the chunk
+#pragma unroll 4
+      for (int i = 0; i < WB_RNG_CHUNK; i += 2) {
+        const double a = wb_randn_next(s);
+        const double b = wb_randn_next(s);
+        *reinterpret_cast<double2 *>(dst + i) = make_double2(a, b);
+      }
+    } else {
+      const int n = (int)(count - begin);
+      for (int i = 0; i < n; ++i) dst[i] = wb_randn_next(s);
+    }
+  }
 }
 
 __global__ void rng_advance_kernel(WbRngState *state, const uint4 *__restrict__ pow_tables,
-                                   const unsigned long long *__restrict__ d_count) {
+                                   const unsigned long long *__restrict__ d_count,
+                                   const unsigned long long *__restrict__ d_count2) {
   if (blockIdx.x == 0 && threadIdx.x < 32) {
     uint32_t s[4] = {state->s[0], state->s[1], state->s[2], state->s[3]};
-    wb_rng_jump_warp(pow_tables, s, *d_count);
+    wb_rng_jump_warp(pow_tables, s, (d_count ? *d_count : 0ull) + (d_count2 ? *d_count2 : 0ull));
     __syncwarp();
     if (threadIdx.x == 0) { state->s[0] = s[0]; state->s[1] = s[1]; state->s[2] = s[2]; state->s[3] = s[3]; }
   }
@@ -120,19 +146,21 @@ void wb_rng_host_jump(uint32_t s[4], unsigned long long n) {
     if (n & 1ull) mat_apply(g_pow[b], s);
 }
 
-int wb_rng_fill(const WbRngState *d_state, const unsigned long long *d_count_or_null,
-                unsigned long long max_count, double *d_out, cudaStream_t stream) {
+int wb_rng_fill(const WbRngState *d_state, const unsigned long long *d_skip_or_null,
+                const unsigned long long *d_count_or_null, unsigned long long max_count, double *d_out,
+                cudaStream_t stream) {
   if (max_count == 0) return WB_OK;
-  const unsigned long long threads = (max_count + WB_RNG_CHUNK - 1) / WB_RNG_CHUNK;
-  const int block = 128;
-  const unsigned long long grid = (threads + block - 1) / block;
-  WB_LAUNCH("rng_fill_kernel", rng_fill_kernel<<<(unsigned)grid, block, 0, stream>>>(d_state, g_d_pow, d_count_or_null, max_count, d_out));
+  const unsigned long long tiles = (max_count + RNG_TILE - 1) / RNG_TILE;
+  const unsigned long long cap = 148ull * 5ull;  // persistent: 5 CTAs (40 KB of tables each) per SM
+  const unsigned long long grid = tiles < cap ? tiles : cap;
+  WB_LAUNCH("rng_fill_kernel", rng_fill_kernel<<<(unsigned)grid, RNG_THREADS, 0, stream>>>(d_state, g_d_pow, d_skip_or_null, d_count_or_null, max_count, d_out));
   WB_CUDA_CHECK(cudaGetLastError());
   return WB_OK;
 }
 
-int wb_rng_advance(WbRngState *d_state, const unsigned long long *d_count, cudaStream_t stream) {
-  WB_LAUNCH("rng_advance_kernel", rng_advance_kernel<<<1, 32, 0, stream>>>(d_state, g_d_pow, d_count));
+int wb_rng_advance(WbRngState *d_state, const unsigned long long *d_count, const unsigned long long *d_count2_or_null,
+                   cudaStream_t stream) {
+  WB_LAUNCH("rng_advance_kernel", rng_advance_kernel<<<1, 32, 0, stream>>>(d_state, g_d_pow, d_count, d_count2_or_null));
   WB_CUDA_CHECK(cudaGetLastError());
   return WB_OK;
 }

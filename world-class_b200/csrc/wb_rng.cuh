@@ -47,6 +47,21 @@ __device__ __forceinline__ void wb_rng_apply(const uint4 *__restrict__ tab, uint
   s[0] = o0; s[1] = o1; s[2] = o2; s[3] = o3;
 }
 
+// same with the window table in shared memory
+__device__ __forceinline__ void wb_rng_apply_shared(const uint4 *tab, uint32_t (&s)[4]) {
+  uint32_t o0 = 0, o1 = 0, o2 = 0, o3 = 0;
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const uint32_t nib = (s[w] >> (4 * k)) & 15u;
+      const uint4 c = tab[(w * 8 + k) * 16 + nib];
+      o0 ^= c.x; o1 ^= c.y; o2 ^= c.z; o3 ^= c.w;
+    }
+  }
+  s[0] = o0; s[1] = o1; s[2] = o2; s[3] = o3;
+}
+
 // s <- M^n s.  pow_tables: WB_RNG_NPOW window tables.
 __device__ __forceinline__ void wb_rng_jump(const uint4 *__restrict__ pow_tables, uint32_t (&s)[4],
                                             unsigned long long n) {
@@ -89,8 +104,25 @@ int wb_rng_init();                         // builds tables, uploads, seeds the 
 const uint4 *wb_rng_tables();              // device pointer to the power tables
 WbRngState *wb_rng_global_state();         // device pointer to the global state
 void wb_rng_host_jump(uint32_t s[4], unsigned long long n);
-// out[i] = value of the (i+1)-th randn() call after state *d_state; does not advance it.
-int wb_rng_fill(const WbRngState *d_state, const unsigned long long *d_count_or_null,
-                unsigned long long max_count, double *d_out, cudaStream_t stream);
-// *d_state <- M^(*d_count) *d_state
-int wb_rng_advance(WbRngState *d_state, const unsigned long long *d_count, cudaStream_t stream);
+// out[i] = value of the (*d_skip + i + 1)-th randn() call after state *d_state (d_skip null = 0); does not
+// advance the state.
+int wb_rng_fill(const WbRngState *d_state, const unsigned long long *d_skip_or_null,
+                const unsigned long long *d_count_or_null, unsigned long long max_count, double *d_out,
+                cudaStream_t stream);
+// *d_state <- M^(*d_count + *d_count2) *d_state (either pointer may be null = 0)
+int wb_rng_advance(WbRngState *d_state, const unsigned long long *d_count, const unsigned long long *d_count2_or_null,
+                   cudaStream_t stream);
+
+// Where a stage's randn() draws sit in the stream and how it hands the position on.  The stage draws from
+// *state advanced by *skip_in calls; once it has counted its own calls it writes skip_in + count to
+// *skip_out.  Stand-alone stage calls set `advance` (the state itself is moved past the draws at the end);
+// the whole-chain pipeline runs stages concurrently on several streams, chains them through the skip
+// counters (ordered by the two events) and advances the state once at the end.
+struct WbRngCursor {
+  WbRngState *state = nullptr;
+  const unsigned long long *skip_in = nullptr;   // device; null = 0
+  unsigned long long *skip_out = nullptr;        // device; null = not needed
+  bool advance = true;
+  cudaEvent_t wait_skip_in = nullptr;            // waited for before *skip_in is first read
+  cudaEvent_t record_skip_out = nullptr;         // recorded after *skip_out is written
+};

@@ -67,25 +67,10 @@ std::map<int, cplx *> g_tw;
 
 #define SCAN_THREADS 1024
 __global__ void __launch_bounds__(SCAN_THREADS) scan_u64_kernel(const unsigned long long *__restrict__ counts,
-                                                                unsigned long long *__restrict__ offsets, int n) {
-  __shared__ unsigned long long part[SCAN_THREADS];
-  const int tid = threadIdx.x;
-  const int chunk = (n + SCAN_THREADS - 1) / SCAN_THREADS;
-  const int b = tid * chunk, e = min(n, b + chunk);
-  unsigned long long s = 0;
-  for (int i = b; i < e; ++i) s += counts[i];
-  part[tid] = s;
-  __syncthreads();
-  // Hillis-Steele inclusive scan over the partials
-  for (int o = 1; o < SCAN_THREADS; o <<= 1) {
-    unsigned long long t = (tid >= o) ? part[tid - o] : 0ull;
-    __syncthreads();
-    part[tid] += t;
-    __syncthreads();
-  }
-  unsigned long long run = (tid > 0) ? part[tid - 1] : 0ull;
-  for (int i = b; i < e; ++i) { offsets[i] = run; run += counts[i]; }
-  if (tid == SCAN_THREADS - 1) offsets[n] = part[SCAN_THREADS - 1];
+                                                                unsigned long long *__restrict__ offsets, int n,
+                                                                const unsigned long long *__restrict__ skip_in,
+                                                                unsigned long long *__restrict__ skip_out) {
+  wb_block_count_scan([&](int i) { return counts[i]; }, n, offsets, skip_in, skip_out);
 }
 }  // namespace
 
@@ -117,8 +102,8 @@ const cplx *wb_twiddle_table(int n) {
 }
 
 int wb_exclusive_scan_u64(const unsigned long long *d_counts, unsigned long long *d_offsets, int n,
-                          cudaStream_t stream) {
-  WB_LAUNCH("scan_u64_kernel", scan_u64_kernel<<<1, SCAN_THREADS, 0, stream>>>(d_counts, d_offsets, n));
+                          cudaStream_t stream, const unsigned long long *d_skip_in, unsigned long long *d_skip_out) {
+  WB_LAUNCH("scan_u64_kernel", scan_u64_kernel<<<1, SCAN_THREADS, 0, stream>>>(d_counts, d_offsets, n, d_skip_in, d_skip_out));
   WB_CUDA_CHECK(cudaGetLastError());
   return WB_OK;
 }

@@ -494,7 +494,7 @@ static void make_dc_remover(int fft_size, std::vector<double> &r) {
 // Part 1 (depends on f0 only): time base, exact phase scan, pulse list.  May run on a side
 // stream while CheapTrick / D4C are still busy.
 int wb_synthesis_timebase(WbWorkspace *ws, int fs, int fft_size, double frame_period_ms, const double *d_f0,
-                          int f0_length, int out_length, cudaStream_t stream) {
+                          int f0_length, int out_length, cudaStream_t stream, const WbRngCursor *noise_cursor) {
   if (out_length <= 0) return WB_OK;
   if (f0_length < 2) return WB_ERR_ARG;
   const double frame_period = frame_period_ms / 1000.;      // synthesis.cpp:31
@@ -523,6 +523,13 @@ int wb_synthesis_timebase(WbWorkspace *ws, int fs, int fft_size, double frame_pe
   WB_LAUNCH("pulse_write_kernel", pulse_write_kernel<<<n_blocks, PD_THREADS, 0, stream>>>(d_total, out_length, fs, d_bo, d_pidx, d_pshift, max_pulses));
   WB_LAUNCH("pulse_finalize_kernel", pulse_finalize_kernel<<<1, 1, 0, stream>>>(d_bo, n_blocks, d_pidx, max_pulses, d_np, d_ncount, ws->error_flag()));
   WB_CUDA_CHECK(cudaGetLastError());
+  if (noise_cursor) {
+    // the aperiodic excitation only needs the pulse span: draw it here, off the critical path
+    double *d_noise = (double *)ws->get("noise_syn", sizeof(double) * out_length);
+    if (!d_noise) return WB_ERR_CUDA;
+    if (noise_cursor->wait_skip_in) WB_CUDA_CHECK(cudaStreamWaitEvent(stream, noise_cursor->wait_skip_in, 0));
+    return wb_rng_fill(noise_cursor->state, noise_cursor->skip_in, d_ncount, (unsigned long long)out_length, d_noise, stream);
+  }
   return WB_OK;
 }
 
@@ -531,7 +538,7 @@ int wb_synthesis_timebase(WbWorkspace *ws, int fs, int fft_size, double frame_pe
 // unknown, in which case the pulse count is read back (one stream synchronisation).
 int wb_synthesis_render(WbWorkspace *ws, int fs, int fft_size, double frame_period_ms, int f0_length,
                         const double *d_sp, const double *d_ap, int out_length, double *d_out,
-                        double f0_upper_bound, WbRngState *d_rng, cudaStream_t stream) {
+                        double f0_upper_bound, const WbRngCursor &rng, cudaStream_t stream, bool noise_ready) {
   if (out_length <= 0) return WB_OK;
   int log2n = 0;
   while ((1 << log2n) < fft_size) ++log2n;
@@ -543,7 +550,7 @@ int wb_synthesis_render(WbWorkspace *ws, int fs, int fft_size, double frame_peri
   double *d_pshift = (double *)ws->get("syn_pshift", 0);
   int *d_np = (int *)ws->get("syn_np", 0);
   unsigned long long *d_ncount = (unsigned long long *)ws->get("syn_ncount", 0);
-  double *d_noise = (double *)ws->get("noise", sizeof(double) * out_length);
+  double *d_noise = (double *)ws->get("noise_syn", sizeof(double) * out_length);
   double *d_dcr = (double *)ws->get("syn_dcr", sizeof(double) * fft_size);
   if (!d_vuv || !d_pidx || !d_pshift || !d_np || !d_ncount || !d_noise || !d_dcr) return WB_ERR_CUDA;
   const cplx *tw_n = wb_twiddle_table(fft_size);
@@ -558,7 +565,10 @@ int wb_synthesis_render(WbWorkspace *ws, int fs, int fft_size, double frame_peri
     WB_CUDA_CHECK(cudaMemcpyAsync(d_dcr, h, sizeof(double) * fft_size, cudaMemcpyHostToDevice, stream));
   }
   int rc;
-  if ((rc = wb_rng_fill(d_rng, d_ncount, (unsigned long long)out_length, d_noise, stream))) return rc;
+  if (!noise_ready) {
+    if (rng.wait_skip_in) WB_CUDA_CHECK(cudaStreamWaitEvent(stream, rng.wait_skip_in, 0));
+    if ((rc = wb_rng_fill(rng.state, rng.skip_in, d_ncount, (unsigned long long)out_length, d_noise, stream))) return rc;
+  }
 
   int resp_pulses;
   if (f0_upper_bound > 0.0) {
@@ -592,14 +602,15 @@ int wb_synthesis_render(WbWorkspace *ws, int fs, int fft_size, double frame_peri
   WB_CUDA_CHECK(cudaGetLastError());
   WB_LAUNCH("ola_kernel", ola_kernel<<<(out_length + 255) / 256, 256, 0, stream>>>(d_resp, d_pidx, d_np, resp_pulses, fft_size, out_length, d_out));
   WB_CUDA_CHECK(cudaGetLastError());
-  return wb_rng_advance(d_rng, d_ncount, stream);
+  // (skip_out is not published: Synthesis is the last consumer of the stream in the chain)
+  return rng.advance ? wb_rng_advance(rng.state, d_ncount, rng.skip_in, stream) : WB_OK;
 }
 
 int wb_synthesis_run(WbWorkspace *ws, int fs, int fft_size, double frame_period_ms, const double *d_f0,
                      int f0_length, const double *d_sp, const double *d_ap, int out_length, double *d_out,
-                     double f0_upper_bound, WbRngState *d_rng, cudaStream_t stream) {
-  int rc = wb_synthesis_timebase(ws, fs, fft_size, frame_period_ms, d_f0, f0_length, out_length, stream);
+                     double f0_upper_bound, const WbRngCursor &rng, cudaStream_t stream) {
+  int rc = wb_synthesis_timebase(ws, fs, fft_size, frame_period_ms, d_f0, f0_length, out_length, stream, nullptr);
   if (rc) return rc;
   return wb_synthesis_render(ws, fs, fft_size, frame_period_ms, f0_length, d_sp, d_ap, out_length, d_out,
-                             f0_upper_bound, d_rng, stream);
+                             f0_upper_bound, rng, stream, false);
 }
