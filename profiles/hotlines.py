@@ -1,6 +1,8 @@
 """Aggregates an ncu source-page CSV (SASS level) by CUDA source line using nvdisasm -g line info.
 
-usage: python profiles/hotlines.py <report.ncu-rep> <kernel regex> <cubin> [top_n] [cubin symbol regex]
+usage: python profiles/hotlines.py <report.ncu-rep | source-page.csv> <kernel regex> <cubin> [top_n] [cubin symbol regex] [outer]
+With `outer` as the sixth argument samples are attributed to the outermost source line of the inline chain
+(the statement of the kernel body), i.e. to the phase of the kernel instead of the helper it inlines.
 The SASS instruction order of the ncu page and of nvdisasm agree, so instruction k of the kernel
 is mapped to the `//## File "...", line N` annotation that precedes it in the nvdisasm listing.
 """
@@ -15,6 +17,7 @@ def main():
     rep, kregex, cubin = sys.argv[1], sys.argv[2], sys.argv[3]
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 25
     cregex = sys.argv[5] if len(sys.argv) > 5 else kregex  # symbol regex inside the cubin
+    outer = len(sys.argv) > 6 and sys.argv[6] == "outer"
     if rep.endswith(".csv"):   # a `--page source --csv` export made on the GPU box (profiles/capture.sh)
         src = open(rep).read()
     else:
@@ -30,7 +33,7 @@ def main():
             break
         body.append(r)
     col = {h: i for i, h in enumerate(hdr)}
-    dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout
+    dis = subprocess.run(["nvdisasm", "-gi" if outer else "-g", "-c", cubin], capture_output=True, text=True).stdout
     # find the function section matching the kernel
     lines = dis.splitlines()
     start = None
@@ -48,7 +51,12 @@ def main():
                 break
         m = re.search(r'//## File "([^"]+)", line (\d+)', l)
         if m:
-            cur = (m.group(1).split("/")[-1], int(m.group(2)))
+            if outer:
+                allm = re.findall(r'"([^"]+)", line (\d+)', l)
+                m_file, m_line = allm[-1]
+                cur = (m_file.split("/")[-1], int(m_line))
+            else:
+                cur = (m.group(1).split("/")[-1], int(m.group(2)))
             continue
         if re.match(r"\s+/\*[0-9a-f]{4,}\*/", l):
             mapping.append(cur)

@@ -6,7 +6,10 @@
 #include <string.h>
 #include <mutex>
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
 #include <stdlib.h>
 #include <new>
 #include <thread>
@@ -72,21 +75,106 @@ struct HostTrace {
 // The reference API hands matrices over as separately allocated rows (test/test.cpp:146-149).  Rows are
 // staged through pinned memory in a few chunks: the DMA of chunk k+1 overlaps the (multi-threaded)
 // host memcpy of chunk k.
-const int kRowChunks = 4;
-const int kCopyThreads = 8;
+const int kRowChunks = 8;
+
+// Persistent helper threads for the row copies (spawning threads per chunk cost more than the copies).
+// Workers spin briefly between jobs -- the chunks of one matrix follow each other within microseconds --
+// and then sleep on a condition variable.  The calling thread takes a slice too.
+class CopyPool {
+ public:
+  static CopyPool &get() {
+    static CopyPool pool;
+    return pool;
+  }
+  // f(begin, end) over contiguous slices of [r0, r1); returns when every slice is done
+  void parallel_for(int r0, int r1, const std::function<void(int, int)> &f) {
+    const int n = r1 - r0;
+    const int parts = std::max(1, std::min((int)workers_.size() + 1, n / 32));
+    if (parts == 1) { f(r0, r1); return; }
+    std::lock_guard<std::mutex> serial(call_mutex_);   // one job at a time (entry points of different handles may race)
+    Job job;
+    {
+      std::lock_guard<std::mutex> lock(m_);
+      job.f = &f; job.r0 = r0; job.n = n; job.parts = parts; job.gen = ++generation_value_;
+      job_ = job;
+      pending_.store(parts, std::memory_order_relaxed);
+      ticket_.store((job.gen << 32) | 0ull, std::memory_order_release);
+      generation_.store(job.gen, std::memory_order_release);
+    }
+    cv_.notify_all();
+    run_parts(job);
+    while (pending_.load(std::memory_order_acquire) > 0) std::this_thread::yield();
+  }
+
+ private:
+  struct Job {
+    const std::function<void(int, int)> *f = nullptr;
+    int r0 = 0, n = 0, parts = 0;
+    unsigned long long gen = 0;
+  };
+  CopyPool() {
+    unsigned hc = std::thread::hardware_concurrency();
+    const int n = (int)std::max(1u, std::min(hc > 1 ? hc - 1 : 1u, 11u));
+    for (int i = 0; i < n; ++i) workers_.emplace_back([this]() { worker(); });
+  }
+  ~CopyPool() {
+    {
+      std::lock_guard<std::mutex> lock(m_);
+      stop_ = true;
+      generation_.store(++generation_value_, std::memory_order_release);
+    }
+    cv_.notify_all();
+    for (auto &t : workers_) t.join();
+  }
+  // Parts are handed out through one (generation, next part) word with compare-and-swap, against a
+  // private snapshot of the job: a worker still looping on an old job can neither take nor skip a part of
+  // the next one.
+  void run_parts(const Job &job) {
+    for (;;) {
+      unsigned long long cur = ticket_.load(std::memory_order_acquire);
+      if ((cur >> 32) != job.gen) return;
+      const int part = (int)(cur & 0xffffffffull);
+      if (part >= job.parts) return;
+      if (!ticket_.compare_exchange_weak(cur, cur + 1, std::memory_order_acq_rel)) continue;
+      const int b = job.r0 + (int)((long long)job.n * part / job.parts);
+      const int e = job.r0 + (int)((long long)job.n * (part + 1) / job.parts);
+      (*job.f)(b, e);
+      pending_.fetch_sub(1, std::memory_order_acq_rel);
+    }
+  }
+  void worker() {
+    unsigned long long seen = 0;
+    for (;;) {
+      // spin for a while, then sleep
+      bool got = false;
+      const auto t0 = std::chrono::steady_clock::now();
+      while (std::chrono::steady_clock::now() - t0 < std::chrono::microseconds(300)) {
+        if (generation_.load(std::memory_order_acquire) != seen) { got = true; break; }
+      }
+      Job job;
+      {
+        std::unique_lock<std::mutex> lock(m_);
+        if (!got) cv_.wait(lock, [&]() { return generation_.load(std::memory_order_acquire) != seen; });
+        seen = generation_.load(std::memory_order_acquire);
+        if (stop_) return;
+        job = job_;
+      }
+      run_parts(job);
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex m_, call_mutex_;
+  std::condition_variable cv_;
+  std::atomic<unsigned long long> generation_{0}, ticket_{0};
+  unsigned long long generation_value_ = 0;
+  std::atomic<int> pending_{0};
+  Job job_;
+  bool stop_ = false;
+};
 
 template <typename F>
 void parallel_rows(int r0, int r1, F f) {
-  const int n = r1 - r0;
-  const int nthreads = std::max(1, std::min(kCopyThreads, n / 64));
-  if (nthreads == 1) { for (int i = r0; i < r1; ++i) f(i); return; }
-  std::vector<std::thread> pool;
-  pool.reserve(nthreads);
-  for (int t = 0; t < nthreads; ++t) {
-    const int b = r0 + (int)((long long)n * t / nthreads), e = r0 + (int)((long long)n * (t + 1) / nthreads);
-    pool.emplace_back([=]() { for (int i = b; i < e; ++i) f(i); });
-  }
-  for (auto &th : pool) th.join();
+  CopyPool::get().parallel_for(r0, r1, [&](int b, int e) { for (int i = b; i < e; ++i) f(i); });
 }
 
 // copy a contiguous [rows][cols] device matrix into separately allocated host rows

@@ -19,6 +19,7 @@ namespace {
 #define D4C_HANNING 1
 #define D4C_BLACKMAN 2
 #define D4C_MAX_AP 8
+#define D4C_BODY_THREADS 256
 
 __device__ __forceinline__ int d4c_half_window(double ratio, int fs, double f0) {
   return wb_round(ratio * fs / f0 / 2.0);  // d4c.cpp:250
@@ -141,111 +142,203 @@ __global__ void __launch_bounds__(256) lt_frame_kernel(LtParams p) {
 
 // ---- order statistic: sum of the m smallest of v[0..n) (d4c.cpp:494-499) ----------------------
 // The reference sorts the band power spectrum and takes a cumulative sum; only
-// S[bins - boundary - 2] / S[bins - 1] is used, i.e. (sum of the m smallest) / total.  MSB-first radix
-// select on the (non-negative) double bit patterns, 8 bits per pass; as soon as the bucket holding
-// the m-th smallest value contains a single element the remaining passes are skipped.
-// Two order statistics at once (the two bands of one paired transform): same algorithm as
-// d4c_sum_smallest, histograms / control words doubled, warps 0 and 1 resolve one array each.
-// get(i, w) -> value i of array w.  hist: 512 ints, ctl: 8 words.
-template <typename Get>
-__device__ inline void d4c_sum_smallest2(Get get, int n, int m, bool has_second, int *hist, unsigned long long *ctl,
-                                         double *red, double &low_a, double &low_b) {
-  unsigned long long prefix[2] = {0ull, 0ull}, mask[2] = {0ull, 0ull};
-  bool done[2] = {false, !has_second};
-  const int tid = threadIdx.x, nt = blockDim.x;
-  if (tid == 0) { ctl[1] = (unsigned long long)m; ctl[5] = (unsigned long long)m; ctl[3] = 0ull; ctl[7] = 0ull; }
-  for (int pass = 0; pass < 8; ++pass) {
-    if (done[0] && done[1]) break;
-    const int shift = 56 - 8 * pass;
-    for (int i = tid; i < 512; i += nt) hist[i] = 0;
+// S[bins - boundary - 2] / S[bins - 1] is used, i.e. (sum of the m smallest) / total.  Radix select
+// on the (non-negative) double bit patterns, two arrays at once (the two bands of one paired
+// transform):
+//  * the caller hands over the AND and the OR of its keys (gathered while the keys were produced);
+//    the leading bits on which they agree are common to all keys, so the first digit starts at the
+//    first bit that actually varies;
+//  * digits are BITS wide (2^BITS counters per array): one histogram pass usually isolates a bucket
+//    with a handful of keys around the m-th smallest;
+//  * as soon as that bucket holds <= SEL_LIST keys, ONE more pass sums everything below the bucket
+//    and collects the bucket's keys, and a single warp ranks them.
+// get(i, w) -> value i of array w.  hist: 2 << BITS ints; ctl: SEL_CTL_WORDS + 2 * SEL_LIST words.
+#define SEL_LIST 32
+#define SEL_CTL_WORDS 20
+template <int BITS, typename Get>
+__device__ inline void d4c_sum_smallest2(Get get, int n, int m, bool has_second, unsigned long long and_a,
+                                         unsigned long long or_a, unsigned long long and_b, unsigned long long or_b,
+                                         int *hist, unsigned long long *ctl, double *red, double &low_a, double &low_b) {
+  constexpr int BINS = 1 << BITS;
+  constexpr int PER = BINS / D4C_BODY_THREADS;  // bins per thread in the scan
+  static_assert(PER >= 1, "histogram smaller than the block");
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  int *s_wtot = reinterpret_cast<int *>(ctl + 12);  // 2 x 8 warp totals of the bucket scan (8 words)
+  unsigned long long *list = ctl + SEL_CTL_WORDS;    // 2 x SEL_LIST keys
+  // ---- common leading bits of each array
+  {
+    const unsigned full = 0xffffffffu;
+    const unsigned aah = __reduce_and_sync(full, (unsigned)(and_a >> 32)), aal = __reduce_and_sync(full, (unsigned)and_a);
+    const unsigned oah = __reduce_or_sync(full, (unsigned)(or_a >> 32)), oal = __reduce_or_sync(full, (unsigned)or_a);
+    const unsigned abh = __reduce_and_sync(full, (unsigned)(and_b >> 32)), abl = __reduce_and_sync(full, (unsigned)and_b);
+    const unsigned obh = __reduce_or_sync(full, (unsigned)(or_b >> 32)), obl = __reduce_or_sync(full, (unsigned)or_b);
+    if (tid == 0) {
+      ctl[8] = ~0ull; ctl[9] = 0ull; ctl[10] = ~0ull; ctl[11] = 0ull;
+      ctl[1] = (unsigned long long)m; ctl[5] = (unsigned long long)m;   // remaining rank (1-based)
+    }
+    __syncthreads();
+    if (lane == 0) {
+      atomicAnd(&ctl[8], ((unsigned long long)aah << 32) | aal);
+      atomicOr(&ctl[9], ((unsigned long long)oah << 32) | oal);
+      atomicAnd(&ctl[10], ((unsigned long long)abh << 32) | abl);
+      atomicOr(&ctl[11], ((unsigned long long)obh << 32) | obl);
+    }
+    __syncthreads();
+  }
+  unsigned long long prefix[2], mask[2];
+  int shift[2], width[2];
+  bool done[2];       // threshold fully determined (= prefix)
+  bool listed[2];     // bucket small enough: resolve from the collected list
+#pragma unroll
+  for (int w = 0; w < 2; ++w) {
+    const unsigned long long all_and = ctl[8 + 2 * w], all_or = ctl[9 + 2 * w];
+    const unsigned long long diff = all_and ^ all_or;
+    listed[w] = false;
+    if (diff == 0ull || (w == 1 && !has_second)) {  // every key identical: that key is the threshold
+      prefix[w] = all_and; mask[w] = ~0ull; shift[w] = 0; width[w] = 0; done[w] = true;
+    } else {
+      const int top = 64 - __clzll((long long)diff);  // bits [0, top) vary
+      mask[w] = (top >= 64) ? 0ull : ~((1ull << top) - 1ull);
+      prefix[w] = all_and & mask[w];
+      shift[w] = top > BITS ? top - BITS : 0;
+      width[w] = top - shift[w];
+      done[w] = false;
+    }
+  }
+  for (int pass = 0; pass < 64; ++pass) {
+    if ((done[0] || listed[0]) && (done[1] || listed[1])) break;
+    {
+      int4 *h4 = reinterpret_cast<int4 *>(hist);
+      for (int i = tid; i < 2 * BINS / 4; i += nt) h4[i] = make_int4(0, 0, 0, 0);
+    }
     __syncthreads();
     for (int i = tid; i < n; i += nt) {
 #pragma unroll
       for (int w = 0; w < 2; ++w) {
-        if (!done[w]) {
+        if (!(done[w] || listed[w])) {
           const unsigned long long key = (unsigned long long)__double_as_longlong(get(i, w));
-          if ((key & mask[w]) == prefix[w]) atomicAdd(&hist[w * 256 + (int)((key >> shift) & 255ull)], 1);
+          if ((key & mask[w]) == prefix[w])
+            atomicAdd(&hist[w * BINS + (int)((key >> shift[w]) & ((1ull << width[w]) - 1ull))], 1);
         }
       }
     }
     __syncthreads();
-    if (tid < 64) {
-      const int w = tid >> 5, lane = tid & 31;
-      if (!done[w]) {  // uniform per warp
-        const int *h = hist + w * 256;
-        unsigned long long *c4 = ctl + w * 4;
-        int c = 0;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) c += h[lane * 8 + q];
-        int incl = c;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int t = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += t;
-        }
-        const int excl = incl - c;
-        const int remaining = (int)c4[1];
-        if (remaining > excl && remaining <= incl) {
-          int r = remaining - excl;
-          int d = lane * 8;
-          int hcount = 0;
-          for (int q = 0; q < 8; ++q) {
-            const int hv = h[lane * 8 + q];
-            if (r <= hv) { d = lane * 8 + q; hcount = hv; break; }
-            r -= hv;
-          }
-          c4[0] = (unsigned long long)d;
-          c4[2] = (unsigned long long)r;
-          c4[3] = (hcount == 1) ? 1ull : 0ull;
-        }
-      }
-    }
-    __syncthreads();
-    bool unique[2] = {false, false};
+    // bucket holding the remaining rank: block-wide scan of the counters, both arrays at once
+    int c[2] = {0, 0}, incl[2];
 #pragma unroll
     for (int w = 0; w < 2; ++w) {
-      if (!done[w]) {
-        prefix[w] |= ctl[w * 4 + 0] << shift;
-        mask[w] |= 255ull << shift;
-        unique[w] = ctl[w * 4 + 3] != 0ull;
-        if (pass == 7) done[w] = true;
+#pragma unroll
+      for (int q = 0; q < PER; ++q) c[w] += hist[w * BINS + tid * PER + q];
+      incl[w] = c[w];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl[w], o);
+        if (lane >= o) incl[w] += t;
+      }
+      if (lane == 31) s_wtot[w * 8 + warp] = incl[w];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      if (done[w] || listed[w]) continue;
+      int before = 0;
+      for (int q = 0; q < warp; ++q) before += s_wtot[w * 8 + q];
+      const int excl = before + incl[w] - c[w];
+      unsigned long long *c4 = ctl + w * 4;
+      const int remaining = (int)c4[1];
+      if (remaining > excl && remaining <= excl + c[w]) {
+        int r = remaining - excl;
+        int d = tid * PER, hcount = 0;
+        for (int q = 0; q < PER; ++q) {
+          const int hv = hist[w * BINS + tid * PER + q];
+          if (r <= hv) { d = tid * PER + q; hcount = hv; break; }
+          r -= hv;
+        }
+        c4[0] = (unsigned long long)d;
+        c4[2] = (unsigned long long)r;
+        c4[3] = (unsigned long long)hcount;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      if (!(done[w] || listed[w])) {
+        prefix[w] |= ctl[w * 4 + 0] << shift[w];
+        mask[w] |= ((1ull << width[w]) - 1ull) << shift[w];
+        if (shift[w] == 0) done[w] = true;
+        else if (ctl[w * 4 + 3] <= (unsigned long long)SEL_LIST) listed[w] = true;
+        const int ns = shift[w] > BITS ? shift[w] - BITS : 0;
+        width[w] = shift[w] - ns;
+        shift[w] = ns;
       }
     }
     __syncthreads();
     if (tid == 0) { ctl[1] = ctl[2]; ctl[5] = ctl[6]; }
-    if ((unique[0] && !done[0]) || (unique[1] && !done[1])) {
-      // exactly one element carries this prefix: fetch it and skip the remaining passes
-      for (int i = tid; i < n; i += nt) {
-#pragma unroll
-        for (int w = 0; w < 2; ++w) {
-          if (unique[w] && !done[w]) {
-            const unsigned long long key = (unsigned long long)__double_as_longlong(get(i, w));
-            if ((key & mask[w]) == prefix[w]) ctl[w * 4 + 0] = key;
-          }
-        }
-      }
-      __syncthreads();
-#pragma unroll
-      for (int w = 0; w < 2; ++w)
-        if (unique[w] && !done[w]) { prefix[w] = ctl[w * 4 + 0]; done[w] = true; }
-      __syncthreads();
-    }
   }
-  const double ta = __longlong_as_double((long long)prefix[0]);
-  const double tb = __longlong_as_double((long long)prefix[1]);
+  // ---- one pass: sum / count of everything below the bucket, collect the bucket's keys
+  if (tid == 0) { s_wtot[0] = 0; s_wtot[1] = 0; }
+  __syncthreads();
   double sa = 0.0, ca = 0.0, sb = 0.0, cb = 0.0;
   for (int i = tid; i < n; i += nt) {
-    const double va = get(i, 0);
-    if (va < ta) { sa += va; ca += 1.0; }
-    if (has_second) {
-      const double vb = get(i, 1);
-      if (vb < tb) { sb += vb; cb += 1.0; }
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      if (w == 1 && !has_second) continue;
+      const double v = get(i, w);
+      const unsigned long long key = (unsigned long long)__double_as_longlong(v);
+      const unsigned long long top = key & mask[w];
+      if (top < prefix[w]) {
+        if (w == 0) { sa += v; ca += 1.0; } else { sb += v; cb += 1.0; }
+      } else if (listed[w] && top == prefix[w]) {
+        const int at = atomicAdd(&s_wtot[w], 1);
+        if (at < SEL_LIST) list[w * SEL_LIST + at] = key;
+      }
     }
   }
-  wb_block_sum2(sa, ca, red);
+  __syncthreads();
+  // ---- rank the collected keys: warp w resolves array w (remaining rank r, 1-based, inside the bucket)
+  if ((warp == 0 && listed[0]) || (warp == 1 && listed[1])) {
+    const int w = warp;
+    const int cnt = min(s_wtot[w], SEL_LIST);
+    const int r = (int)ctl[w * 4 + 1];
+    const unsigned long long mine = lane < cnt ? list[w * SEL_LIST + lane] : ~0ull;
+    int rank = 0;
+    for (int j = 0; j < cnt; ++j) {
+      const unsigned long long other = __shfl_sync(0xffffffffu, mine, j);
+      rank += (other < mine || (other == mine && j < lane)) ? 1 : 0;
+    }
+    const unsigned hit = __ballot_sync(0xffffffffu, lane < cnt && rank == r - 1);
+    const int src = hit ? (__ffs(hit) - 1) : 0;
+    const unsigned long long thr = __shfl_sync(0xffffffffu, mine, src);
+    // bucket keys strictly below the threshold join the "below" totals; they are summed in rank order
+    // (the collection order above depends on the atomics and must not leak into the rounding)
+    __syncwarp();
+    if (lane < cnt) list[w * SEL_LIST + rank] = mine;
+    __syncwarp();
+    const unsigned long long sorted = lane < cnt ? list[w * SEL_LIST + lane] : ~0ull;
+    double ls = 0.0, lc = 0.0;
+    if (lane < cnt && sorted < thr) { ls = __longlong_as_double((long long)sorted); lc = 1.0; }
+    ls = wb_warp_sum(ls);
+    lc = wb_warp_sum(lc);
+    if (lane == 0) {
+      ctl[w * 4 + 0] = thr;
+      ctl[w * 4 + 2] = (unsigned long long)__double_as_longlong(ls);
+      ctl[w * 4 + 3] = (unsigned long long)__double_as_longlong(lc);
+    }
+  }
+  wb_block_sum2(sa, ca, red);   // (contains the barriers that publish ctl)
   wb_block_sum2(sb, cb, red);
-  low_a = sa + (m - ca) * ta;
-  low_b = sb + (m - cb) * tb;
+  double t[2];
+#pragma unroll
+  for (int w = 0; w < 2; ++w) {
+    t[w] = __longlong_as_double((long long)prefix[w]);
+    if (listed[w]) {
+      t[w] = __longlong_as_double((long long)ctl[w * 4 + 0]);
+      const double ls = __longlong_as_double((long long)ctl[w * 4 + 2]), lc = __longlong_as_double((long long)ctl[w * 4 + 3]);
+      if (w == 0) { sa += ls; ca += lc; } else { sb += ls; cb += lc; }
+    }
+  }
+  low_a = sa + (m - ca) * t[0];
+  low_b = sb + (m - cb) * t[1];
 }
 
 // ---- body (d4c.cpp:308-503 + :155-168) -------------------------------------------------------
@@ -264,7 +357,6 @@ struct BodyParams {
   int *error_flag;
 };
 
-#define D4C_BODY_THREADS 256
 
 // Shared memory (N = 4096: 110 KB -> two CTAs per SM):
 //   S   : slots of an N-point complex FFT; doubles as the linear-smoothing scratch (`seg`) and,
@@ -280,9 +372,8 @@ __global__ void __launch_bounds__(D4C_BODY_THREADS, 2) d4c_body_kernel(BodyParam
   double *SC = reinterpret_cast<double *>(S + wb_fft_slots(N));
   double *SP = SC + binsp;
   double *red = SP + binsp;                                       // 320
-  int *hist = reinterpret_cast<int *>(red + 320);                 // 2 x 256 ints
-  unsigned long long *ctl = reinterpret_cast<unsigned long long *>(hist + 512);  // 2 x 4
-  double *coarse = reinterpret_cast<double *>(ctl + 8);           // D4C_MAX_AP + 2
+  unsigned long long *ctl = reinterpret_cast<unsigned long long *>(red + 320);   // select: control words + 2 x SEL_LIST keys
+  double *coarse = reinterpret_cast<double *>(ctl + SEL_CTL_WORDS + 2 * SEL_LIST);  // D4C_MAX_AP + 2
   double *W = reinterpret_cast<double *>(S);
   double *seg = W;                                                // 2 * slots(N) doubles available
   const int seg_capacity = 2 * wb_fft_slots(N);
@@ -310,6 +401,51 @@ __global__ void __launch_bounds__(D4C_BODY_THREADS, 2) d4c_body_kernel(BodyParam
   // built the imaginary parts of the slots hold the window samples.
   for (int c = 0; c < 2; ++c) {
     const double cpos = (c == 0) ? pos - 0.25 / f0 : pos + 0.25 / f0;
+    if constexpr (N == 16 * D4C_BODY_THREADS) {
+      // One radix-16 butterfly per thread in the first FFT pass: thread t owns samples t + 256 q, exactly the
+      // stride of the window loop, so the windowed, mean-free, unit-power waveform (d4c.cpp:246-303, :372-380)
+      // is built in registers and handed to the transform without touching shared memory.
+      const int hw = d4c_half_window(4.0, fs, f0);
+      const int wlen = 2 * hw + 1;
+      const int origin = wb_round(cpos * fs + 0.001);
+      const double c1 = 2.0 / 4.0 / fs;
+      const double c2 = WB_PI * f0;
+      double sd, cd, sn, cs;
+      sincos(c2 * c1 * D4C_BODY_THREADS, &sd, &cd);
+      sincos(c2 * (c1 * (tid - hw)), &sn, &cs);
+      double v[16], w[16];
+      double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const int j = tid + q * D4C_BODY_THREADS;
+        v[q] = 0.0; w[q] = 0.0;
+        if (j < wlen) {
+          const double wq = 0.42 + 0.5 * cs + 0.08 * (2.0 * cs * cs - 1.0);
+          const int idx = wb_min_i(p.x_length - 1, wb_max_i(0, origin + j - hw));
+          const double vq = p.x[idx] * wq + noise[j] * WB_SAFEGUARD;
+          v[q] = vq; w[q] = wq;
+          s1 += vq;
+          s2 += wq;
+          const double c_next = cs * cd - sn * sd;
+          sn = sn * cd + cs * sd;
+          cs = c_next;
+        }
+      }
+      wb_block_sum2(s1, s2, red);
+      const double coef = s1 / s2;
+      double pw = 0.0;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        if (tid + q * D4C_BODY_THREADS < wlen) { v[q] -= w[q] * coef; pw += v[q] * v[q]; }
+      }
+      const double power = sqrt(wb_block_sum(pw, red));
+      noise += wlen;
+      wb_cfft_dif_in_t<1, LOG2N>(S, p.tw_2n, [&](int j, int q) {
+        cplx z = make_double2(0.0, 0.0);
+        if (j < wlen) { z.x = v[q] / power; z.y = z.x * (j + 1.0); }
+        return z;
+      });
+    } else {
     const int wlen = d4c_windowed_waveform(p.x, p.x_length, fs, f0, cpos, D4C_BLACKMAN, 4.0, noise,
                                            [&](int j) -> double & { return S[wb_sidx(j)].y; }, red,
                                            [&](int j) -> double & { return S[wb_sidx(j)].x; });
@@ -323,7 +459,8 @@ __global__ void __launch_bounds__(D4C_BODY_THREADS, 2) d4c_body_kernel(BodyParam
       S[wb_sidx(j)] = z;
     }
     __syncthreads();
-    wb_cfft_dif_t<1, LOG2N>(S, p.tw_2n);
+    wb_cfft_dif_t<1, LOG2N, 16>(S, p.tw_2n);
+    }
     for (int k = tid; k <= NC; k += nt) {
       const cplx zk = S[wb_sidx(wb_brev(k, log2n))];
       const cplx zc = S[wb_sidx(wb_brev((N - k) & (N - 1), log2n))];
@@ -343,7 +480,7 @@ __global__ void __launch_bounds__(D4C_BODY_THREADS, 2) d4c_body_kernel(BodyParam
                                            [&](int j) -> double & { return W[wb_didx(j)]; });
     for (int j = wlen + tid; j < N; j += nt) W[wb_didx(j)] = 0.0;
     __syncthreads();
-    wb_rfft_t<1, LOG2N - 1>(S, p.tw_n, [&](int k, cplx X) { SP[k] = X.x * X.x + X.y * X.y; });
+    wb_rfft_t<1, LOG2N - 1, 16>(S, p.tw_n, [&](int k, cplx X) { SP[k] = X.x * X.x + X.y * X.y; });
     wb_dc_correction(SP, f0, fs, N);
     if (!wb_linear_smoothing(SP, SP, f0, fs, N, seg, seg_capacity, red)) {
       if (tid == 0) atomicExch(p.error_flag, WB_ERR_UNSUPPORTED);
@@ -370,18 +507,18 @@ __global__ void __launch_bounds__(D4C_BODY_THREADS, 2) d4c_body_kernel(BodyParam
     const bool has2 = (b + 1 < p.n_ap);
     const int center_a = static_cast<int>(WB_FREQ_INTERVAL * (b + 1) * N / fs);
     const int center_b = static_cast<int>(WB_FREQ_INTERVAL * (b + 2) * N / fs);
-    for (int j = tid; j < N; j += nt) {
+    // the windowed band slices feed the first FFT pass directly (the rest of the N points is zero padding)
+    wb_cfft_dif_in_t<1, LOG2N>(S, p.tw_2n, [&](int j, int) {
       cplx z = make_double2(0.0, 0.0);
       if (j < wl) {
         const double nw = __ldg(&p.nuttall[j]);
         z.x = SC[center_a - hwl + j] * nw;
         if (has2) z.y = SC[center_b - hwl + j] * nw;
       }
-      S[wb_sidx(j)] = z;
-    }
-    __syncthreads();
-    wb_cfft_dif_t<1, LOG2N>(S, p.tw_2n);
+      return z;
+    });
     double tot_a = 0.0, tot_b = 0.0;
+    unsigned long long and_a = ~0ull, or_a = 0ull, and_b = ~0ull, or_b = 0ull;  // bit patterns of the power values
     for (int k = tid; k <= NC; k += nt) {
       const int slot = wb_sidx(wb_brev(k, log2n));
       const cplx zk = S[slot];
@@ -393,11 +530,14 @@ __global__ void __launch_bounds__(D4C_BODY_THREADS, 2) d4c_body_kernel(BodyParam
       S[slot] = make_double2(pa, pb);
       tot_a += pa;
       tot_b += pb;
+      const unsigned long long ka = (unsigned long long)__double_as_longlong(pa), kb = (unsigned long long)__double_as_longlong(pb);
+      and_a &= ka; or_a |= ka; and_b &= kb; or_b |= kb;
     }
     wb_block_sum2(tot_a, tot_b, red);
     double low_a, low_b;
-    d4c_sum_smallest2([&](int i, int w) { const cplx v = S[wb_sidx(wb_brev(i, log2n))]; return w == 0 ? v.x : v.y; },
-                      bins, m_small, has2, hist, ctl, red, low_a, low_b);
+    // (SP is free from here on: it holds the 2 x 2^(LOG2N-1) counters of the select)
+    d4c_sum_smallest2<LOG2N - 1>([&](int i, int w) { const cplx v = S[wb_sidx(wb_brev(i, log2n))]; return w == 0 ? v.x : v.y; },
+                                 bins, m_small, has2, and_a, or_a, and_b, or_b, reinterpret_cast<int *>(SP), ctl, red, low_a, low_b);
     if (tid == 0) {
       const double rev = (f0 - 100) / 50.0;  // d4c.cpp:325-327
       double ca = 10 * log10(low_a / tot_a);
@@ -536,7 +676,7 @@ int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int
     p.error_flag = ws->error_flag();
     const int binsp = ((N / 2 + 1) + 1) & ~1;
     const size_t smem = sizeof(cplx) * wb_fft_slots(N) + sizeof(double) * (2 * binsp + 320) +
-                        sizeof(int) * 512 + sizeof(unsigned long long) * 8 + sizeof(double) * (D4C_MAX_AP + 2);
+                        sizeof(unsigned long long) * (SEL_CTL_WORDS + 2 * SEL_LIST) + sizeof(double) * (D4C_MAX_AP + 2);
     rc = WB_DISPATCH_LOG2(l, 9, 13, {
       if (cudaFuncSetAttribute(d4c_body_kernel<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WB_ERR_CUDA;
       WB_LAUNCH("d4c_body_kernel", d4c_body_kernel<L2><<<f0_length, D4C_BODY_THREADS, smem, stream>>>(p));

@@ -20,6 +20,7 @@
 // size and dispatched on the host.
 #pragma once
 #include "wb_common.cuh"
+#include <type_traits>
 
 // Three-level padding: +1 slot per 8, per 64 and per 512 elements.  The first level keeps the
 // small-stride butterfly passes conflict free, the other two spread the bit-reversed access
@@ -84,6 +85,45 @@ __device__ __forceinline__ void wb_dft4(cplx (&a)[4]) {
   a[1] = wb_cadd(b2, b3); a[3] = wb_csub(b2, b3);
 }
 
+// a[p] <- sum_n a[n] W16^{np},  W16 = e^{SIGN 2 pi i / 16}: 4 x 4 decomposition (n = q + 4 t, p = r + 4 s):
+// radix-4 over t, twiddle W16^{qr}, radix-4 over q.
+template <int SIGN>
+__device__ __forceinline__ cplx wb_mul_w16(cplx v, double wr, double wi_abs) {  // v * (wr, SIGN * wi_abs)
+  const double wi = SIGN > 0 ? wi_abs : -wi_abs;
+  return make_double2(fma(v.x, wr, -(v.y * wi)), fma(v.x, wi, v.y * wr));
+}
+template <int SIGN>
+__device__ __forceinline__ void wb_dft16(cplx (&a)[16]) {
+  const double r = 0.70710678118654752440, c1 = 0.92387953251128675613, s1 = 0.38268343236508977173;
+  cplx b[4][4];  // b[q][r]
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    cplx t[4] = {a[q], a[q + 4], a[q + 8], a[q + 12]};
+    wb_dft4<SIGN>(t);
+    b[q][0] = t[0]; b[q][1] = t[1]; b[q][2] = t[2]; b[q][3] = t[3];
+  }
+  // W16^{qr}
+  b[1][1] = wb_mul_w16<SIGN>(b[1][1], c1, s1);                                   // W^1
+  b[1][2] = SIGN > 0 ? make_double2((b[1][2].x - b[1][2].y) * r, (b[1][2].x + b[1][2].y) * r)
+                     : make_double2((b[1][2].x + b[1][2].y) * r, (b[1][2].y - b[1][2].x) * r);  // W^2
+  b[1][3] = wb_mul_w16<SIGN>(b[1][3], s1, c1);                                   // W^3
+  b[2][1] = SIGN > 0 ? make_double2((b[2][1].x - b[2][1].y) * r, (b[2][1].x + b[2][1].y) * r)
+                     : make_double2((b[2][1].x + b[2][1].y) * r, (b[2][1].y - b[2][1].x) * r);  // W^2
+  b[2][2] = wb_mul_i<SIGN>(b[2][2]);                                             // W^4
+  b[2][3] = SIGN > 0 ? make_double2((-b[2][3].x - b[2][3].y) * r, (b[2][3].x - b[2][3].y) * r)
+                     : make_double2((b[2][3].y - b[2][3].x) * r, (-b[2][3].x - b[2][3].y) * r);  // W^6
+  b[3][1] = wb_mul_w16<SIGN>(b[3][1], s1, c1);                                   // W^3
+  b[3][2] = SIGN > 0 ? make_double2((-b[3][2].x - b[3][2].y) * r, (b[3][2].x - b[3][2].y) * r)
+                     : make_double2((b[3][2].y - b[3][2].x) * r, (-b[3][2].x - b[3][2].y) * r);  // W^6
+  b[3][3] = wb_mul_w16<SIGN>(b[3][3], -c1, -s1);                                 // W^9 = -W^1
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr) {
+    cplx t[4] = {b[0][rr], b[1][rr], b[2][rr], b[3][rr]};
+    wb_dft4<SIGN>(t);
+    a[rr] = t[0]; a[rr + 4] = t[1]; a[rr + 8] = t[2]; a[rr + 12] = t[3];
+  }
+}
+
 // padded offset of element (base + q * m) relative to sidx(base): the three shift terms separate
 // because base = M * block + j with j < m = M / 8, so (base mod 2^s) + (q m mod 2^s) never carries
 // for s = 3, 6, 9 (for M <= 2^s the whole sub-block lies inside one 2^s-aligned group).
@@ -122,6 +162,80 @@ __device__ __forceinline__ void wb_pass_dif8(cplx *s, const cplx *__restrict__ T
     // slot q' <- A[brev3(q')]
     sp[WB_OFF(0, m8)] = a[0]; sp[WB_OFF(1, m8)] = a[4]; sp[WB_OFF(2, m8)] = a[2]; sp[WB_OFF(3, m8)] = a[6];
     sp[WB_OFF(4, m8)] = a[1]; sp[WB_OFF(5, m8)] = a[5]; sp[WB_OFF(6, m8)] = a[3]; sp[WB_OFF(7, m8)] = a[7];
+  }
+}
+
+// a[p] *= w^p, p = 1..15, with w^1, w^2, w^4, w^8 from the table and the rest by products
+template <int SIGN>
+__device__ __forceinline__ void wb_apply_twiddles16(const cplx *__restrict__ T, int t1, cplx (&a)[16]) {
+  const cplx w1 = wb_tw<SIGN>(T, t1), w2 = wb_tw<SIGN>(T, 2 * t1), w4 = wb_tw<SIGN>(T, 4 * t1), w8 = wb_tw<SIGN>(T, 8 * t1);
+  a[1] = wb_cmul(a[1], w1);
+  a[2] = wb_cmul(a[2], w2);
+  const cplx w3 = wb_cmul(w1, w2);
+  a[3] = wb_cmul(a[3], w3);
+  a[4] = wb_cmul(a[4], w4);
+  const cplx w5 = wb_cmul(w1, w4);
+  a[5] = wb_cmul(a[5], w5);
+  const cplx w6 = wb_cmul(w2, w4);
+  a[6] = wb_cmul(a[6], w6);
+  const cplx w7 = wb_cmul(w3, w4);
+  a[7] = wb_cmul(a[7], w7);
+  a[8] = wb_cmul(a[8], w8);
+  a[9] = wb_cmul(a[9], wb_cmul(w1, w8));
+  a[10] = wb_cmul(a[10], wb_cmul(w2, w8));
+  a[11] = wb_cmul(a[11], wb_cmul(w3, w8));
+  a[12] = wb_cmul(a[12], wb_cmul(w4, w8));
+  a[13] = wb_cmul(a[13], wb_cmul(w5, w8));
+  a[14] = wb_cmul(a[14], wb_cmul(w6, w8));
+  a[15] = wb_cmul(a[15], wb_cmul(w7, w8));
+}
+
+__device__ __forceinline__ constexpr int wb_brev4c(int q) { return ((q & 1) << 3) | ((q & 2) << 1) | ((q & 4) >> 1) | ((q & 8) >> 3); }
+
+// ---- radix-16 DIF pass over sub-blocks of size M, in place.  `in(i, q)` supplies element i of the input
+// (q = 0..15 is its position inside the butterfly, a compile-time constant after unrolling, so the functor
+// may index per-thread register arrays with it): the default reads the slots, a caller-provided functor
+// fuses the producer of the data into the first pass (no store + reload of the input, and zero padding
+// costs nothing).
+struct WbFromSlots {};
+template <int SIGN, int N, int M, typename In>
+__device__ __forceinline__ void wb_pass_dif16(cplx *s, const cplx *__restrict__ T, In in) {
+  constexpr int m = M / 16, tstep = 2 * N / M;
+  for (int u = threadIdx.x; u < N / 16; u += blockDim.x) {
+    const int j = u & (m - 1);
+    const int base = ((u - j) << 4) + j;  // (u / m) * M + j
+    cplx *sp = s + wb_sidx(base);
+    cplx a[16];
+    if constexpr (std::is_same<In, WbFromSlots>::value) {
+#pragma unroll
+      for (int q = 0; q < 16; ++q) a[q] = sp[WB_OFF(q, m)];
+    } else {
+#pragma unroll
+      for (int q = 0; q < 16; ++q) a[q] = in(base + q * m, q);
+    }
+    wb_dft16<SIGN>(a);
+    if (m > 1) wb_apply_twiddles16<SIGN>(T, j * tstep, a);
+    // slot q' <- A[brev4(q')]
+#pragma unroll
+    for (int q = 0; q < 16; ++q) sp[WB_OFF(q, m)] = a[wb_brev4c(q)];
+  }
+}
+
+// ---- radix-16 DIT pass (transpose of the above)
+template <int SIGN, int N, int M>
+__device__ __forceinline__ void wb_pass_dit16(cplx *s, const cplx *__restrict__ T) {
+  constexpr int m = M / 16, tstep = 2 * N / M;
+  for (int u = threadIdx.x; u < N / 16; u += blockDim.x) {
+    const int j = u & (m - 1);
+    const int base = ((u - j) << 4) + j;
+    cplx *sp = s + wb_sidx(base);
+    cplx a[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) a[wb_brev4c(q)] = sp[WB_OFF(q, m)];
+    if (m > 1) wb_apply_twiddles16<SIGN>(T, j * tstep, a);
+    wb_dft16<SIGN>(a);
+#pragma unroll
+    for (int p = 0; p < 16; ++p) sp[WB_OFF(p, m)] = a[p];
   }
 }
 
@@ -191,30 +305,53 @@ __device__ __forceinline__ void wb_pass_dit2_first(cplx *s) {
   }
 }
 
-template <int SIGN, int N, int M>
+// Pass plans (template parameter R):
+//   R = 16: radix 16 while the sub-block size allows it, then ONE twiddle-free clean-up pass of radix
+//           8 / 4 / 2 (4096 = 16.16.16, 2048 = 16.16.8, 1024 = 16.16.4, ...): three passes over shared
+//           memory where radix 8 needs four, at ~100-128 registers per thread (two 256-thread CTAs per SM).
+//   R = 8:  radix 8 plus a radix-4 / 2 clean-up pass, ~60-75 registers: for kernels whose shared-memory
+//           footprint allows three or more CTAs per SM, where occupancy is worth more than the saved pass.
+#ifndef WB_FFT_DEFAULT_RADIX
+#define WB_FFT_DEFAULT_RADIX 8
+#endif
+template <int SIGN, int N, int M, int R>
 struct WbDifPasses {
-  static __device__ __forceinline__ void run(cplx *s, const cplx *__restrict__ T) {
-    if constexpr (M >= 8) {
-      wb_pass_dif8<SIGN, N, M>(s, T);
+  template <typename In>
+  static __device__ __forceinline__ void run(cplx *s, const cplx *__restrict__ T, In in) {
+    if constexpr (R == 16 && M >= 16) {
+      wb_pass_dif16<SIGN, N, M>(s, T, in);
       __syncthreads();
-      WbDifPasses<SIGN, N, M / 8>::run(s, T);
-    } else if constexpr (M == 4) {
-      wb_pass_dif4_last<SIGN, N>(s);
-      __syncthreads();
-    } else if constexpr (M == 2) {
-      wb_pass_dif2_last<SIGN, N>(s);
-      __syncthreads();
+      WbDifPasses<SIGN, N, M / 16, R>::run(s, T, WbFromSlots());
+    } else {
+      static_assert(std::is_same<In, WbFromSlots>::value, "fused input needs the radix-16 plan and N >= 16");
+      if constexpr (M >= 8) {
+        wb_pass_dif8<SIGN, N, M>(s, T);
+        __syncthreads();
+        WbDifPasses<SIGN, N, M / 8, R>::run(s, T, WbFromSlots());
+      } else if constexpr (M == 4) {
+        wb_pass_dif4_last<SIGN, N>(s);
+        __syncthreads();
+      } else if constexpr (M == 2) {
+        wb_pass_dif2_last<SIGN, N>(s);
+        __syncthreads();
+      }
     }
   }
 };
 
-template <int SIGN, int N, int M>  // M = sub-block size produced by the passes done so far
+template <int SIGN, int N, int M, int R>  // M = sub-block size produced by the passes done so far
 struct WbDitPasses {
   static __device__ __forceinline__ void run(cplx *s, const cplx *__restrict__ T) {
     if constexpr (M < N) {
-      wb_pass_dit8<SIGN, N, M * 8>(s, T);
-      __syncthreads();
-      WbDitPasses<SIGN, N, M * 8>::run(s, T);
+      if constexpr (R == 16) {
+        wb_pass_dit16<SIGN, N, M * 16>(s, T);
+        __syncthreads();
+        WbDitPasses<SIGN, N, M * 16, R>::run(s, T);
+      } else {
+        wb_pass_dit8<SIGN, N, M * 8>(s, T);
+        __syncthreads();
+        WbDitPasses<SIGN, N, M * 8, R>::run(s, T);
+      }
     }
   }
 };
@@ -222,18 +359,34 @@ struct WbDitPasses {
 // ---- complex transforms: N = 2^LOG2N points, table T with 2N entries -------------------------
 // natural order in, bit-reversed order out.  Ends with __syncthreads().
 // Caller must __syncthreads() after filling `s`.
-template <int SIGN, int LOG2N>
+template <int SIGN, int LOG2N, int R = WB_FFT_DEFAULT_RADIX>
 __device__ __forceinline__ void wb_cfft_dif_t(cplx *s, const cplx *__restrict__ T) {
-  WbDifPasses<SIGN, (1 << LOG2N), (1 << LOG2N)>::run(s, T);
+  WbDifPasses<SIGN, (1 << LOG2N), (1 << LOG2N), R>::run(s, T, WbFromSlots());
+}
+
+// Radix-16 plan with element i of the input coming from in(i, q) instead of the slots (LOG2N >= 4).  The slots
+// are only written: the caller must make sure nobody still reads them (a __syncthreads() after their last use).
+template <int SIGN, int LOG2N, typename In>
+__device__ __forceinline__ void wb_cfft_dif_in_t(cplx *s, const cplx *__restrict__ T, In in) {
+  WbDifPasses<SIGN, (1 << LOG2N), (1 << LOG2N), 16>::run(s, T, in);
 }
 
 // bit-reversed order in, natural order out.  Ends with __syncthreads().
-template <int SIGN, int LOG2N>
+template <int SIGN, int LOG2N, int R = WB_FFT_DEFAULT_RADIX>
 __device__ __forceinline__ void wb_cfft_dit_t(cplx *s, const cplx *__restrict__ T) {
-  constexpr int N = 1 << LOG2N, rem = LOG2N % 3;
-  if constexpr (rem == 2) { wb_pass_dit4_first<SIGN, N>(s); __syncthreads(); }
-  if constexpr (rem == 1) { wb_pass_dit2_first<SIGN, N>(s); __syncthreads(); }
-  WbDitPasses<SIGN, N, (1 << rem)>::run(s, T);
+  constexpr int N = 1 << LOG2N;
+  if constexpr (R == 16) {
+    constexpr int rem = LOG2N % 4;
+    if constexpr (rem == 3) { wb_pass_dit8<SIGN, N, 8>(s, T); __syncthreads(); }
+    if constexpr (rem == 2) { wb_pass_dit4_first<SIGN, N>(s); __syncthreads(); }
+    if constexpr (rem == 1) { wb_pass_dit2_first<SIGN, N>(s); __syncthreads(); }
+    WbDitPasses<SIGN, N, (1 << rem), R>::run(s, T);
+  } else {
+    constexpr int rem = LOG2N % 3;
+    if constexpr (rem == 2) { wb_pass_dit4_first<SIGN, N>(s); __syncthreads(); }
+    if constexpr (rem == 1) { wb_pass_dit2_first<SIGN, N>(s); __syncthreads(); }
+    WbDitPasses<SIGN, N, (1 << rem), R>::run(s, T);
+  }
 }
 
 __device__ __forceinline__ int wb_brev(int k, int bits) { return (int)(__brev((unsigned)k) >> (32 - bits)); }
@@ -244,10 +397,10 @@ __device__ __forceinline__ int wb_brev(int k, int bits) { return (int)(__brev((u
 // After the complex DIF transform, `emit(k, X)` is called exactly once for every k = 0..NC
 // (X[k] of the real transform, forward sign).  T has 2 NC entries.
 // The slots are left untouched by the post-processing (emit must not write to s).
-template <int SIGN, int LOG2NC, typename Emit>
+template <int SIGN, int LOG2NC, int R = WB_FFT_DEFAULT_RADIX, typename Emit>
 __device__ __forceinline__ void wb_rfft_t(cplx *s, const cplx *__restrict__ T, Emit emit) {
   constexpr int NC = 1 << LOG2NC;
-  wb_cfft_dif_t<SIGN, LOG2NC>(s, T);
+  wb_cfft_dif_t<SIGN, LOG2NC, R>(s, T);
   for (int k = threadIdx.x; k <= (NC >> 1); k += blockDim.x) {
     if (k == 0) {
       const cplx z = s[0];
@@ -270,7 +423,7 @@ __device__ __forceinline__ void wb_rfft_t(cplx *s, const cplx *__restrict__ T, E
 // c2r (SIGN = -1 for the reference's backward transform): `get(k)` returns X[k] for
 // k = 0..NC (Hermitian half; imaginary parts of X[0], X[NC] are ignored like Ooura's
 // rdft).  On return real output sample j is at double index wb_didx(j) of `s`.
-template <int SIGN, int LOG2NC, typename Get>
+template <int SIGN, int LOG2NC, int R = WB_FFT_DEFAULT_RADIX, typename Get>
 __device__ __forceinline__ void wb_irfft_t(cplx *s, const cplx *__restrict__ T, Get get) {
   constexpr int NC = 1 << LOG2NC;
   for (int k = threadIdx.x; k <= (NC >> 1); k += blockDim.x) {
@@ -287,7 +440,7 @@ __device__ __forceinline__ void wb_irfft_t(cplx *s, const cplx *__restrict__ T, 
     }
   }
   __syncthreads();
-  wb_cfft_dit_t<SIGN, LOG2NC>(s, T);
+  wb_cfft_dit_t<SIGN, LOG2NC, R>(s, T);
 }
 
 // ---- host-side dispatch helper: call F.template operator()<LOG2N>() for a runtime log2n ------

@@ -413,11 +413,12 @@ __global__ void frame_time_kernel(int n, int frame_period, double *__restrict__ 
   if (i < n) t_tab[i] = i * frame_period / 1000.0;
 }
 
-#define IV_THREADS 1024
+#define IV_THREADS 512
 #define IV_PER_ITER ((IV_THREADS / 32) * 31)
 __global__ void __launch_bounds__(IV_THREADS) interval_kernel(IntervalParams p) {
   __shared__ int s_off[64];
-  const int ct = blockIdx.x;  // channel * 4 + kind
+  // channel * 4 + kind; the high channels have the most zero crossings: schedule them first
+  const int ct = gridDim.x - 1 - blockIdx.x;
   const int *cnt = p.seg_count + (size_t)ct * p.n_blocks;
   if (threadIdx.x == 0) {
     int run = 0;
@@ -492,7 +493,7 @@ struct CandParams {
 
 #define CD_FRAMES 32
 #define CD_PITCH 33
-#define CD_THREADS 1024
+#define CD_THREADS 512
 __global__ void __launch_bounds__(CD_THREADS) candidate_kernel(CandParams p) {
   extern __shared__ double cd_tile[];  // [nch][CD_PITCH]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
