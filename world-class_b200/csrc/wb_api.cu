@@ -215,6 +215,60 @@ int rows_to_device(WbWorkspace *ws, const char *name, const double *const *src, 
   return WB_OK;
 }
 
+// Streams / events for a row-chunked compute + download (WbRowChunks): frame ranges alternate between the
+// library stream and `alt`, finished ranges are downloaded on `copy` and scattered to the caller's rows.
+struct RowPipeline {
+  cudaStream_t alt = nullptr, copy = nullptr;
+  cudaEvent_t ev[kRowChunks] = {nullptr}, done[kRowChunks] = {nullptr}, ready = nullptr;
+  bool ok = false;
+  int init() {
+    if (ok) return WB_OK;
+    if (cudaStreamCreateWithFlags(&alt, cudaStreamNonBlocking) != cudaSuccess) return WB_ERR_CUDA;
+    if (cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking) != cudaSuccess) return WB_ERR_CUDA;
+    if (cudaEventCreateWithFlags(&ready, cudaEventDisableTiming) != cudaSuccess) return WB_ERR_CUDA;
+    for (int c = 0; c < kRowChunks; ++c) {
+      if (cudaEventCreateWithFlags(&ev[c], cudaEventDisableTiming) != cudaSuccess) return WB_ERR_CUDA;
+      if (cudaEventCreateWithFlags(&done[c], cudaEventDisableTiming) != cudaSuccess) return WB_ERR_CUDA;
+    }
+    ok = true;
+    return WB_OK;
+  }
+  ~RowPipeline() {
+    for (int c = 0; c < kRowChunks; ++c) {
+      if (ev[c]) cudaEventDestroy(ev[c]);
+      if (done[c]) cudaEventDestroy(done[c]);
+    }
+    if (ready) cudaEventDestroy(ready);
+    if (alt) cudaStreamDestroy(alt);
+    if (copy) cudaStreamDestroy(copy);
+  }
+  void describe(int rows, WbRowChunks *ch) const {
+    ch->n = kRowChunks;
+    for (int c = 0; c <= kRowChunks; ++c) ch->bounds[c] = (int)((long long)rows * c / kRowChunks);
+    for (int c = 0; c < kRowChunks; ++c) ch->ev[c] = ev[c];
+    ch->alt = alt;
+    ch->ev_ready = ready;
+  }
+  // download range c as soon as ev[c] fires, scatter it to the caller's rows while the next ranges compute
+  int download(WbWorkspace *ws, const WbRowChunks &ch, const double *d_src, int cols, double **dst) {
+    const int rows = ch.bounds[ch.n];
+    double *stage = (double *)ws->get_pinned("rows_stage", sizeof(double) * (size_t)rows * cols);
+    if (!stage) return WB_ERR_CUDA;
+    for (int c = 0; c < ch.n; ++c) {
+      const size_t off = (size_t)ch.bounds[c] * cols, cnt = (size_t)(ch.bounds[c + 1] - ch.bounds[c]) * cols;
+      WB_CUDA_CHECK(cudaStreamWaitEvent(copy, ch.ev[c], 0));
+      if (cnt) WB_CUDA_CHECK(cudaMemcpyAsync(stage + off, d_src + off, sizeof(double) * cnt, cudaMemcpyDeviceToHost, copy));
+      WB_CUDA_CHECK(cudaEventRecord(done[c], copy));
+    }
+    int rc = WB_OK;
+    for (int c = 0; c < ch.n; ++c) {
+      if (cudaEventSynchronize(done[c]) != cudaSuccess) rc = WB_ERR_CUDA;
+      if (!rc) parallel_rows(ch.bounds[c], ch.bounds[c + 1], [=](int i) { memcpy(dst[i], stage + (size_t)i * cols, sizeof(double) * cols); });
+    }
+    return rc;
+  }
+};
+
 int vec_to_device(WbWorkspace *ws, const char *name, const double *src, size_t n, double **d_out, cudaStream_t st) {
   double *d = (double *)ws->get(name, sizeof(double) * n);
   if (!d) return WB_ERR_CUDA;
@@ -230,6 +284,7 @@ struct wb_cheaptrick {
   WbCheapTrickOption opt;   // fft_size resolved
   double f0_floor_internal; // cheaptrick.cpp:34 / :44
   WbWorkspace ws;
+  RowPipeline rows;
 };
 
 struct wb_harvest {
@@ -276,6 +331,7 @@ struct wb_d4c {
   int fs;
   WbD4COption opt;
   WbWorkspace ws;
+  RowPipeline rows;
 };
 
 struct wb_synthesis {
@@ -453,9 +509,14 @@ int wb_cheaptrick_compute(wb_cheaptrick_t *h, const double *x, int x_length, con
   double *d_sp = (double *)h->ws.get("h_sp", sizeof(double) * (size_t)f0_length * bins);
   if (!d_sp) return WB_ERR_CUDA;
   HostTrace tr("cheaptrick_compute");
-  if ((rc = wb_cheaptrick_compute_dev(h, d_x, x_length, d_t, d_f, f0_length, d_sp, st))) return rc;
-  tr.mark("kernels", st);
-  if ((rc = rows_to_host(&h->ws, d_sp, f0_length, bins, spectrogram, st))) return rc;
+  if ((rc = h->rows.init())) return rc;
+  WbRowChunks ch;
+  h->rows.describe(f0_length, &ch);
+  if ((rc = wb_cheaptrick_run(&h->ws, h->fs, h->opt.fft_size, h->opt.q1, h->f0_floor_internal, d_x, x_length, d_t, d_f,
+                              f0_length, d_sp, global_cursor(), st, &ch)))
+    return rc;
+  tr.mark("enqueued");
+  if ((rc = h->rows.download(&h->ws, ch, d_sp, bins, spectrogram))) return rc;
   tr.mark("rows_to_host");
   return h->ws.read_error_flag(st);
 }
@@ -499,9 +560,14 @@ int wb_d4c_compute(wb_d4c_t *h, const double *x, int x_length, const double *tpo
   double *d_ap = (double *)h->ws.get("h_ap", sizeof(double) * (size_t)f0_length * bins);
   if (!d_ap) return WB_ERR_CUDA;
   HostTrace tr("d4c_compute");
-  if ((rc = wb_d4c_compute_dev(h, d_x, x_length, d_t, d_f, f0_length, fft_size, d_ap, st))) return rc;
-  tr.mark("kernels", st);
-  if ((rc = rows_to_host(&h->ws, d_ap, f0_length, bins, aperiodicity, st))) return rc;
+  if ((rc = h->rows.init())) return rc;
+  WbRowChunks ch;
+  h->rows.describe(f0_length, &ch);
+  if ((rc = wb_d4c_run(&h->ws, h->fs, h->opt.threshold, d_x, x_length, d_t, d_f, f0_length, fft_size, d_ap,
+                       global_cursor(), st, &ch)))
+    return rc;
+  tr.mark("enqueued");
+  if ((rc = h->rows.download(&h->ws, ch, d_ap, bins, aperiodicity))) return rc;
   tr.mark("rows_to_host");
   return h->ws.read_error_flag(st);
 }

@@ -46,6 +46,7 @@ struct CtParams {
   double *sp;                       // [f0_length][fft_size/2+1]
   int seg_capacity;
   int *error_flag;
+  int frame_begin;                  // this launch covers frames frame_begin + blockIdx.x
 };
 
 template <int LOG2N>
@@ -58,7 +59,7 @@ __global__ void __launch_bounds__(256) ct_frame_kernel(CtParams p) {
   double *red = B + p.seg_capacity;                           // 1024 + 64
   double *W = reinterpret_cast<double *>(S);                  // packed real waveform view
 
-  const int frame = blockIdx.x;
+  const int frame = p.frame_begin + blockIdx.x;
   const int tid = threadIdx.x, nt = blockDim.x;
   const double f0 = ct_current_f0(p.f0[frame], p.f0_floor);
   const int fs = p.fs;
@@ -139,7 +140,8 @@ size_t wb_cheaptrick_smem_bytes(int fft_size, int seg_capacity) {
 // Consumes the global randn stream exactly like the reference's serial loop.
 int wb_cheaptrick_run(WbWorkspace *ws, int fs, int fft_size, double q1, double f0_floor_internal,
                       const double *d_x, int x_length, const double *d_tpos, const double *d_f0,
-                      int f0_length, double *d_sp, const WbRngCursor &rng, cudaStream_t stream) {
+                      int f0_length, double *d_sp, const WbRngCursor &rng, cudaStream_t stream,
+                      const WbRowChunks *chunks) {
   if (f0_length <= 0) return WB_OK;
   int log2n = 0;
   while ((1 << log2n) < fft_size) ++log2n;
@@ -170,11 +172,35 @@ int wb_cheaptrick_run(WbWorkspace *ws, int fs, int fft_size, double q1, double f
   p.error_flag = ws->error_flag();
   const size_t smem = wb_cheaptrick_smem_bytes(fft_size, p.seg_capacity);
   const int threads = wb_max_i(64, wb_min_i(256, fft_size / 8));
-  rc = WB_DISPATCH_LOG2(log2n, 8, 13, {
-    if (cudaFuncSetAttribute(ct_frame_kernel<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WB_ERR_CUDA;
-    WB_LAUNCH("ct_frame_kernel", ct_frame_kernel<L2><<<f0_length, threads, smem, stream>>>(p));
-  });
-  if (rc) return rc;
+  p.frame_begin = 0;
+  if (!chunks || chunks->n <= 1) {
+    rc = WB_DISPATCH_LOG2(log2n, 8, 13, {
+      if (cudaFuncSetAttribute(ct_frame_kernel<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WB_ERR_CUDA;
+      WB_LAUNCH("ct_frame_kernel", ct_frame_kernel<L2><<<f0_length, threads, smem, stream>>>(p));
+    });
+    if (rc) return rc;
+    if (chunks && chunks->n == 1) WB_CUDA_CHECK(cudaEventRecord(chunks->ev[0], stream));
+  } else {
+    // row ranges on alternating streams (see WbRowChunks); everything before this point is on `stream`
+    WB_CUDA_CHECK(cudaEventRecord(chunks->ev_ready, stream));
+    WB_CUDA_CHECK(cudaStreamWaitEvent(chunks->alt, chunks->ev_ready, 0));
+    for (int c = 0; c < chunks->n; ++c) {
+      cudaStream_t cs = (c & 1) ? chunks->alt : stream;
+      const int count = chunks->bounds[c + 1] - chunks->bounds[c];
+      p.frame_begin = chunks->bounds[c];
+      if (count > 0) {
+        rc = WB_DISPATCH_LOG2(log2n, 8, 13, {
+          if (cudaFuncSetAttribute(ct_frame_kernel<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WB_ERR_CUDA;
+          WbLaunchScope scope("ct_frame_kernel", cs);
+          ct_frame_kernel<L2><<<count, threads, smem, cs>>>(p);
+        });
+        if (rc) return rc;
+      }
+      WB_CUDA_CHECK(cudaEventRecord(chunks->ev[c], cs));
+    }
+    // the caller's stream continues (randn bookkeeping, later calls) after every range
+    for (int c = 1; c < chunks->n; c += 2) WB_CUDA_CHECK(cudaStreamWaitEvent(stream, chunks->ev[c], 0));
+  }
   WB_CUDA_CHECK(cudaGetLastError());
   return rng.advance ? wb_rng_advance(rng.state, d_offsets + f0_length, rng.skip_in, stream) : WB_OK;
 }

@@ -355,6 +355,7 @@ struct BodyParams {
   double *ap;                          // [f0_length][out_fft_size/2+1]
   int seg_capacity;
   int *error_flag;
+  int frame_begin;                     // this launch covers frames frame_begin + blockIdx.x
 };
 
 
@@ -379,7 +380,7 @@ __global__ void __launch_bounds__(D4C_BODY_THREADS, 2) d4c_body_kernel(BodyParam
   const int seg_capacity = 2 * wb_fft_slots(N);
   double *win_hi = reinterpret_cast<double *>(S + wb_fft_slots(NC) + 8);  // >= N doubles above the packed real data
 
-  const int frame = blockIdx.x;
+  const int frame = p.frame_begin + blockIdx.x;
   const int tid = threadIdx.x, nt = blockDim.x;
   const double f0_in = p.f0[frame];
   if (f0_in == 0 || p.ap0[frame] <= p.threshold) {
@@ -598,7 +599,7 @@ int wb_number_of_aperiodicities(int fs) {  // d4c.cpp:65-67, codec.cpp:211-214
 
 int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int x_length, const double *d_tpos,
                const double *d_f0, int f0_length, int out_fft_size, double *d_ap, const WbRngCursor &rng,
-               cudaStream_t stream) {
+               cudaStream_t stream, const WbRowChunks *chunks) {
   if (f0_length <= 0) return WB_OK;
   const int N = wb_d4c_fft_size(fs), N_lt = wb_d4c_lt_fft_size(fs);
   const int l = ilog2_exact(N), l_lt = ilog2_exact(N_lt);
@@ -677,11 +678,34 @@ int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int
     const int binsp = ((N / 2 + 1) + 1) & ~1;
     const size_t smem = sizeof(cplx) * wb_fft_slots(N) + sizeof(double) * (2 * binsp + 320) +
                         sizeof(unsigned long long) * (SEL_CTL_WORDS + 2 * SEL_LIST) + sizeof(double) * (D4C_MAX_AP + 2);
-    rc = WB_DISPATCH_LOG2(l, 9, 13, {
-      if (cudaFuncSetAttribute(d4c_body_kernel<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WB_ERR_CUDA;
-      WB_LAUNCH("d4c_body_kernel", d4c_body_kernel<L2><<<f0_length, D4C_BODY_THREADS, smem, stream>>>(p));
-    });
-    if (rc) return rc;
+    p.frame_begin = 0;
+    if (!chunks || chunks->n <= 1) {
+      rc = WB_DISPATCH_LOG2(l, 9, 13, {
+        if (cudaFuncSetAttribute(d4c_body_kernel<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WB_ERR_CUDA;
+        WB_LAUNCH("d4c_body_kernel", d4c_body_kernel<L2><<<f0_length, D4C_BODY_THREADS, smem, stream>>>(p));
+      });
+      if (rc) return rc;
+      if (chunks && chunks->n == 1) WB_CUDA_CHECK(cudaEventRecord(chunks->ev[0], stream));
+    } else {
+      // row ranges on alternating streams (see WbRowChunks); everything before this point is on `stream`
+      WB_CUDA_CHECK(cudaEventRecord(chunks->ev_ready, stream));
+      WB_CUDA_CHECK(cudaStreamWaitEvent(chunks->alt, chunks->ev_ready, 0));
+      for (int c = 0; c < chunks->n; ++c) {
+        cudaStream_t cs = (c & 1) ? chunks->alt : stream;
+        const int count = chunks->bounds[c + 1] - chunks->bounds[c];
+        p.frame_begin = chunks->bounds[c];
+        if (count > 0) {
+          rc = WB_DISPATCH_LOG2(l, 9, 13, {
+            if (cudaFuncSetAttribute(d4c_body_kernel<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WB_ERR_CUDA;
+            WbLaunchScope scope("d4c_body_kernel", cs);
+            d4c_body_kernel<L2><<<count, D4C_BODY_THREADS, smem, cs>>>(p);
+          });
+          if (rc) return rc;
+        }
+        WB_CUDA_CHECK(cudaEventRecord(chunks->ev[c], cs));
+      }
+      for (int c = 1; c < chunks->n; c += 2) WB_CUDA_CHECK(cudaStreamWaitEvent(stream, chunks->ev[c], 0));
+    }
     WB_CUDA_CHECK(cudaGetLastError());
   }
   return rng.advance ? wb_rng_advance(rng.state, d_skip_end, nullptr, stream) : WB_OK;

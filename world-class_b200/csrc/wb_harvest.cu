@@ -65,17 +65,22 @@ __device__ __forceinline__ double dec_new_x(const double *__restrict__ x, int x_
   const int k = j - lag;
   return x[k < 0 ? 0 : (k >= x_length ? x_length - 1 : k)];
 }
+// branch-free: the two source samples are selected with predicates so that the staging loops below can
+// keep many loads in flight (interior samples read the same address twice)
 __device__ __forceinline__ double dec_tmp1(const double *__restrict__ x, int x_length, int lag, int len1, int i) {
-  if (i < DEC_NFACT) return 2 * dec_new_x(x, x_length, lag, 0) - dec_new_x(x, x_length, lag, DEC_NFACT - i);
-  if (i < DEC_NFACT + len1) return dec_new_x(x, x_length, lag, i - DEC_NFACT);
-  return 2 * dec_new_x(x, x_length, lag, len1 - 1) - dec_new_x(x, x_length, lag, len1 - 2 - (i - (DEC_NFACT + len1)));
+  const bool head = i < DEC_NFACT, tail = i >= DEC_NFACT + len1;
+  const int ja = head ? 0 : (tail ? len1 - 1 : i - DEC_NFACT);
+  const int jb = head ? DEC_NFACT - i : (tail ? len1 - 2 - (i - (DEC_NFACT + len1)) : ja);
+  const double a = dec_new_x(x, x_length, lag, ja), b = dec_new_x(x, x_length, lag, jb);
+  return (head || tail) ? 2 * a - b : a;
 }
 
 // Both IIR passes work on tiles: a block stages DEC_TILE + DEC_WARM input samples in shared memory
 // with coalesced loads, every thread then runs the recurrence over its DEC_CHUNK outputs (plus
 // warm-up) out of shared memory, and the results leave through shared memory again.  The
 // per-thread stride of DEC_CHUNK doubles is padded to DEC_CHUNK + 1 to stay bank-conflict free.
-#define DEC_THREADS 128
+#define DEC_THREADS 128       /* threads that run the recurrence */
+#define DEC_BLOCK 512         /* threads that stage the tiles (load latency, not arithmetic, dominates) */
 #define DEC_TILE (DEC_THREADS * DEC_CHUNK)
 __device__ __forceinline__ int dec_pad(int r) { return r + (r / DEC_CHUNK); }
 
@@ -112,7 +117,7 @@ __device__ __forceinline__ void dec_look_step(const DecLook &L, double x1, doubl
 }
 
 // forward pass: out[i] = FilterForDecimate(tmp1)[i], i in [0, len2)
-__global__ void __launch_bounds__(DEC_THREADS) dec_forward_kernel(const double *__restrict__ x, int x_length, int lag,
+__global__ void __launch_bounds__(DEC_BLOCK) dec_forward_kernel(const double *__restrict__ x, int x_length, int lag,
                                                                   int len1, int len2, DecimCoef c,
                                                                   double *__restrict__ out) {
   extern __shared__ double dec_smem[];
@@ -120,13 +125,16 @@ __global__ void __launch_bounds__(DEC_THREADS) dec_forward_kernel(const double *
   double *s_out = dec_smem + dec_pad(DEC_TILE + DEC_WARM) + 1;  // dec_pad(DEC_TILE) + 1
   const int tile_begin = blockIdx.x * DEC_TILE;
   const int in_begin = tile_begin - DEC_WARM;
-  for (int r = threadIdx.x; r < DEC_TILE + DEC_WARM; r += DEC_THREADS) {
+#pragma unroll 3
+  for (int r = threadIdx.x; r < DEC_TILE + DEC_WARM; r += DEC_BLOCK) {
     const int i = in_begin + r;
-    s_in[dec_pad(r)] = (i >= 0 && i < len2) ? dec_tmp1(x, x_length, lag, len1, i) : 0.0;
+    const int ic = min(max(i, 0), len2 - 1);
+    const double v = dec_tmp1(x, x_length, lag, len1, ic);
+    s_in[dec_pad(r)] = (i >= 0 && i < len2) ? v : 0.0;
   }
   __syncthreads();
   const int begin = tile_begin + threadIdx.x * DEC_CHUNK;
-  if (begin < len2) {
+  if (threadIdx.x < DEC_THREADS && begin < len2) {
     const int end = min(len2, begin + DEC_CHUNK);
     double w0 = 0.0, w1 = 0.0, w2 = 0.0;
     const DecLook look = dec_look_init(c);
@@ -142,7 +150,8 @@ __global__ void __launch_bounds__(DEC_THREADS) dec_forward_kernel(const double *
     }
   }
   __syncthreads();
-  for (int r = threadIdx.x; r < DEC_TILE; r += DEC_THREADS) {
+#pragma unroll 4
+  for (int r = threadIdx.x; r < DEC_TILE; r += DEC_BLOCK) {
     const int i = tile_begin + r;
     if (i < len2) out[i] = s_out[dec_pad(r)];
   }
@@ -151,7 +160,7 @@ __global__ void __launch_bounds__(DEC_THREADS) dec_forward_kernel(const double *
 // backward pass over `fwd` (the reference reverses, filters, reverses) fused with the pick of
 // every r-th sample (world_matlabfunctions.cpp:201-207) and the lag removal + zero padding of
 // harvest.cpp:231-232,242.  y[m], m in [0, y_length).
-__global__ void __launch_bounds__(DEC_THREADS) dec_backward_kernel(const double *__restrict__ fwd, int len1, int len2,
+__global__ void __launch_bounds__(DEC_BLOCK) dec_backward_kernel(const double *__restrict__ fwd, int len1, int len2,
                                                                    int r, int lag, DecimCoef c, int y_length,
                                                                    double *__restrict__ y,
                                                                    unsigned long long *__restrict__ absmax_bits) {
@@ -160,14 +169,16 @@ __global__ void __launch_bounds__(DEC_THREADS) dec_backward_kernel(const double 
   // reversed index u = len2 - 1 - i runs forward in filter time
   const int tile_begin = blockIdx.x * DEC_TILE;
   const int in_begin = tile_begin - DEC_WARM;
-  for (int q = threadIdx.x; q < DEC_TILE + DEC_WARM; q += DEC_THREADS) {
+#pragma unroll 3
+  for (int q = threadIdx.x; q < DEC_TILE + DEC_WARM; q += DEC_BLOCK) {
     const int u = in_begin + q;
-    s_in[dec_pad(q)] = (u >= 0 && u < len2) ? fwd[len2 - 1 - u] : 0.0;
+    const double v = fwd[len2 - 1 - min(max(u, 0), len2 - 1)];
+    s_in[dec_pad(q)] = (u >= 0 && u < len2) ? v : 0.0;
   }
   __syncthreads();
   const int begin = tile_begin + threadIdx.x * DEC_CHUNK;
   double amax = 0.0;  // max |y| over the samples this thread writes (feeds the DC "correction" below)
-  if (begin < len2) {
+  if (threadIdx.x < DEC_THREADS && begin < len2) {
   const int end = min(len2, begin + DEC_CHUNK);
   const int nout = len1 / r + 1;
   const int nbeg = r - r * nout + len1;
@@ -313,7 +324,7 @@ __device__ __forceinline__ unsigned ch_flags(double a, double b, double c, int n
 // (harvest.cpp:1277-1299) and order-preserving extraction of the fine zero-crossing edges of the
 // block's V output samples straight from shared memory.
 template <int LOG2NB>
-__global__ void __launch_bounds__(CH_THREADS) channel_kernel(ChanParams p) {
+__global__ void __launch_bounds__(CH_THREADS, 3) channel_kernel(ChanParams p) {
   extern __shared__ double2 smem_raw[];
   __shared__ int s_wsum[4][CH_THREADS / 32];
   cplx *S = smem_raw;
@@ -324,7 +335,7 @@ __global__ void __launch_bounds__(CH_THREADS) channel_kernel(ChanParams p) {
   const int h = p.half_len[c];
   const cplx *H = p.Hc + (size_t)c * (NC + 1);
   const cplx *Y = p.Yb + (size_t)b * (NC + 1);
-  wb_irfft_t<-1, LOG2NB - 1>(S, p.tw, [&](int k) {
+  wb_irfft_t<-1, LOG2NB - 1, 16>(S, p.tw, [&](int k) {
     const cplx yv = Y[k], hv = H[k];
     return make_double2(yv.x * hv.x - yv.y * hv.y, yv.x * hv.y + yv.y * hv.x);
   });
@@ -391,12 +402,17 @@ __global__ void __launch_bounds__(CH_THREADS) channel_kernel(ChanParams p) {
 // ---------------------------------------------------------------------------------------------
 struct IntervalParams {
   const double *seg_edges; const int *seg_count; int n_blocks; int bcap;
-  double *edges; int *ecount; int ecap; double fs;
-  double *locs; double *vals;
+  int *ecount; int ecap; double fs;
   int f0_length; int frame_period;
   const double *t_tab;  // [f0_length] frame times
-  double *contour;  // [nch * 4][f0_length]: interpolated interval frequency per frame
+  double *contour;  // interpolated interval frequency per (channel, kind, frame), see iv_contour_index
 };
+
+// Layout of the four interpolated contours: tile-major, [frame / 32][channel][kind][frame % 32], so that the
+// candidate kernel (one CTA per 32 frames) streams one contiguous block.
+__device__ __forceinline__ size_t iv_contour_index(int ct, int n_ct, int frame) {
+  return ((size_t)(frame >> 5) * n_ct + ct) * 32 + (frame & 31);
+}
 
 // smallest frame i in [0, L] with t_i >= x; t_tab[i] = i * frame_period / 1000.0 (the reference's own
 // expression, tabulated so that the frame loop has no division for it)
@@ -416,29 +432,41 @@ __global__ void frame_time_kernel(int n, int frame_period, double *__restrict__ 
 #define IV_THREADS 512
 #define IV_PER_ITER ((IV_THREADS / 32) * 31)
 __global__ void __launch_bounds__(IV_THREADS) interval_kernel(IntervalParams p) {
-  __shared__ int s_off[64];
+  __shared__ int s_off[65];
   // channel * 4 + kind; the high channels have the most zero crossings: schedule them first
   const int ct = gridDim.x - 1 - blockIdx.x;
   const int *cnt = p.seg_count + (size_t)ct * p.n_blocks;
-  if (threadIdx.x == 0) {
-    int run = 0;
-    for (int b = 0; b < p.n_blocks; ++b) { s_off[b] = run; run += cnt[b]; }
-    s_off[p.n_blocks] = run;
-    p.ecount[ct] = min(run, p.ecap);
+  if (threadIdx.x < 32) {
+    // exclusive offsets of the per-block edge runs (n_blocks <= 63): the ordered edge list of this
+    // (channel, kind) is their concatenation
+    const int lane = threadIdx.x;
+    const int c0 = lane < p.n_blocks ? cnt[lane] : 0, c1 = lane + 32 < p.n_blocks ? cnt[lane + 32] : 0;
+    int i0 = c0, i1 = c1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t0 = __shfl_up_sync(0xffffffffu, i0, o), t1 = __shfl_up_sync(0xffffffffu, i1, o);
+      if (lane >= o) { i0 += t0; i1 += t1; }
+    }
+    const int tot0 = __shfl_sync(0xffffffffu, i0, 31);
+    s_off[lane] = i0 - c0;
+    s_off[lane + 32] = tot0 + i1 - c1;
+    if (lane == 31) { s_off[64] = tot0 + i1; p.ecount[ct] = min(tot0 + i1, p.ecap); }
   }
   __syncthreads();
-  double *e = p.edges + (size_t)ct * p.ecap;
-  for (int b = 0; b < p.n_blocks; ++b) {
-    const int o = s_off[b], n = s_off[b + 1] - o;
-    const double *src = p.seg_edges + ((size_t)ct * p.n_blocks + b) * p.bcap;
-    for (int i = threadIdx.x; i < n; i += blockDim.x)
-      if (o + i < p.ecap) e[o + i] = src[i];
-  }
-  __syncthreads();
-  const int total = min(s_off[p.n_blocks], p.ecap);
+  const int total = min(s_off[64], p.ecap);
   const int ni = total < 2 ? 0 : total - 1;  // number of intervals
-  double *loc = p.locs + (size_t)ct * p.ecap, *val = p.vals + (size_t)ct * p.ecap;
-  double *out = p.contour + (size_t)ct * p.f0_length;
+  const double *seg = p.seg_edges + (size_t)ct * p.n_blocks * p.bcap;
+  // edge k of the concatenated list: last block b with s_off[b] <= k (blocks beyond n_blocks hold the total)
+  auto edge = [&](int k) -> double {
+    int lo = 0, hi = 63;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (s_off[mid] <= k) lo = mid; else hi = mid - 1;
+    }
+    return seg[(size_t)lo * p.bcap + (k - s_off[lo])];
+  };
+  double *out = p.contour;
+  const int n_ct = gridDim.x;
   const double fs = p.fs;
   const int L = p.f0_length;
   const double *t_tab = p.t_tab;
@@ -451,10 +479,10 @@ __global__ void __launch_bounds__(IV_THREADS) interval_kernel(IntervalParams p) 
     double x1 = 0.0, y1 = 0.0;
     int f1 = L;
     if (k >= 0 && k < ni) {
-      const double e0 = e[k], e1 = e[k + 1];
+      // zeroCrossingEngine (harvest.cpp:1208-1211): interval value and location
+      const double e0 = edge(k), e1 = edge(k + 1);
       y1 = fs / (e1 - e0);
       x1 = (e0 + e1) / 2.0 / fs;
-      if (lane > 0) { val[k] = y1; loc[k] = x1; }
       if (k < ni - 1) f1 = iv_first_frame(x1, frames_per_second, t_tab, L);
     }
     const double x0 = __shfl_up_sync(0xffffffffu, x1, 1);
@@ -468,7 +496,7 @@ __global__ void __launch_bounds__(IV_THREADS) interval_kernel(IntervalParams p) 
       const double dx = x1 - x0, dy = y1 - y0;
       for (int i = i_lo; i < f1; ++i) {
         const double s = (t_tab[i] - x0) / dx;
-        out[i] = y0 + s * dy;
+        out[iv_contour_index(ct, n_ct, i)] = y0 + s * dy;
       }
     }
   }
@@ -499,6 +527,7 @@ __global__ void __launch_bounds__(CD_THREADS) candidate_kernel(CandParams p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int L = p.f0_length;
   const int f = blockIdx.x * CD_FRAMES + lane;
+#pragma unroll 4
   for (int c = warp; c < p.nch; c += CD_THREADS / 32) {
     const int *cnt = p.ecount + c * 4;
     bool ok = true;
@@ -509,8 +538,8 @@ __global__ void __launch_bounds__(CD_THREADS) candidate_kernel(CandParams p) {
     }
     double v = 0.0;
     if (ok && f < L) {
-      const double *src = p.contour + (size_t)c * 4 * L + f;
-      const double v0 = src[0], v1 = src[L], v2 = src[2 * (size_t)L], v3 = src[3 * (size_t)L];
+      const double *src = p.contour + iv_contour_index(c * 4, p.nch * 4, f);
+      const double v0 = src[0], v1 = src[32], v2 = src[64], v3 = src[96];
       const double bf = p.boundary_f0[c];
       const double upper = bf * 1.1, lower = bf * 0.9;
       v = (v0 + v1 + v2 + v3) / 4.0;
@@ -860,8 +889,8 @@ int wb_harvest_run_basic(WbHarvestPlan *pl, WbWorkspace *ws, const double *d_x, 
     WB_CUDA_CHECK(cudaFuncSetAttribute(dec_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_smem_f));
     WB_CUDA_CHECK(cudaFuncSetAttribute(dec_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_smem_b));
     WB_CUDA_CHECK(cudaMemsetAsync(d_y, 0, sizeof(double) * y_length, stream));            // new_y is zero-initialised
-    WB_LAUNCH("dec_forward_kernel", dec_forward_kernel<<<n_tiles, DEC_THREADS, dec_smem_f, stream>>>(d_x, x_length, lag, len1, len2, dc, d_fwd));
-    WB_LAUNCH("dec_backward_kernel", dec_backward_kernel<<<n_tiles, DEC_THREADS, dec_smem_b, stream>>>(d_fwd, len1, len2, r, lag, dc, y_length, d_y, d_absmax));
+    WB_LAUNCH("dec_forward_kernel", dec_forward_kernel<<<n_tiles, DEC_BLOCK, dec_smem_f, stream>>>(d_x, x_length, lag, len1, len2, dc, d_fwd));
+    WB_LAUNCH("dec_backward_kernel", dec_backward_kernel<<<n_tiles, DEC_BLOCK, dec_smem_b, stream>>>(d_fwd, len1, len2, r, lag, dc, y_length, d_y, d_absmax));
   }
   WB_LAUNCH("dc_fix_kernel", dc_fix_kernel<<<1, 1024, 0, stream>>>(d_y, y_length, d_absmax));
   WB_CUDA_CHECK(cudaGetLastError());
@@ -883,14 +912,10 @@ int wb_harvest_run_basic(WbHarvestPlan *pl, WbWorkspace *ws, const double *d_x, 
   const int ecap = y_length / 2 + 4;
   const int bcap = pl->V / 2 + 2;
   if (n_blocks > 63) return WB_ERR_UNSUPPORTED;  // TODO(long streams): tile the block axis
-  double *d_edges = (double *)ws->get("hv_edges", sizeof(double) * (size_t)nch * 4 * ecap);
   int *d_ecount = (int *)ws->get("hv_ecount", sizeof(int) * nch * 4);
-  double *d_locs = (double *)ws->get("hv_locs", sizeof(double) * (size_t)nch * 4 * ecap);
-  double *d_vals = (double *)ws->get("hv_vals", sizeof(double) * (size_t)nch * 4 * ecap);
-  if (!d_locs || !d_vals) return WB_ERR_CUDA;
   double *d_seg = (double *)ws->get("hv_seg_edges", sizeof(double) * (size_t)nch * 4 * n_blocks * bcap);
   int *d_segc = (int *)ws->get("hv_seg_count", sizeof(int) * (size_t)nch * 4 * n_blocks);
-  if (!d_edges || !d_ecount || !d_seg || !d_segc) return WB_ERR_CUDA;
+  if (!d_ecount || !d_seg || !d_segc) return WB_ERR_CUDA;
   {
     ChanParams p;
     p.Yb = d_Yb; p.Hc = (const cplx *)ws->get("hv_Hc", 0); p.half_len = (const int *)ws->get("hv_hl", 0);
@@ -907,12 +932,12 @@ int wb_harvest_run_basic(WbHarvestPlan *pl, WbWorkspace *ws, const double *d_x, 
   }
 
   // ---- interval sequences -> the four interpolated contours on the frame grid
-  double *d_contour = (double *)ws->get("hv_contour", sizeof(double) * (size_t)nch * 4 * Lb);
+  double *d_contour = (double *)ws->get("hv_contour", sizeof(double) * (size_t)nch * 4 * ((Lb + 31) / 32) * 32);
   if (!d_contour) return WB_ERR_CUDA;
   {
     IntervalParams p;
     p.seg_edges = d_seg; p.seg_count = d_segc; p.n_blocks = n_blocks; p.bcap = bcap;
-    p.edges = d_edges; p.ecount = d_ecount; p.ecap = ecap; p.fs = afs; p.locs = d_locs; p.vals = d_vals;
+    p.ecount = d_ecount; p.ecap = ecap; p.fs = afs;
     p.f0_length = Lb; p.frame_period = frame_period; p.contour = d_contour;
     // frame times: a function of (Lb, frame_period) only, tabulated once per plan and length
     double *d_ttab = (double *)ws->get("hv_ttab", sizeof(double) * Lb);

@@ -366,11 +366,24 @@ __global__ void __launch_bounds__(TL_THREADS) harvest_tail_kernel(TailParams p) 
   }
   __syncthreads();
   TL_STAMP();  // 3: sections materialised
-  // extend (forward first, then backward) + per-section sums for extendSub
+  // extend: the forward and the backward extension of a section are independent serial chains (they write
+  // disjoint frames of the section and start from its own two ends), so they run on different warps;
+  // then the per-section sums for extendSub
+  for (int item = warp; item < 2 * nsec; item += nwarps) {
+    const int s = item >> 1;
+    if ((item & 1) == 0) {
+      const int ed0 = p.sec_ed[s];
+      const int ed1 = tl_extend_f0(p, s, ed0, min(L - 2, ed0 + 100), 1, nc7);
+      if (lane == 0) p.kb[2 * s + 1] = ed1;
+    } else {
+      const int st0 = p.sec_st[s];
+      const int st1 = tl_extend_f0(p, s, st0, max(1, st0 - 100), -1, nc7);
+      if (lane == 0) p.kb[2 * s] = st1;
+    }
+  }
+  __syncthreads();
   for (int s = warp; s < nsec; s += nwarps) {
-    const int ed0 = p.sec_ed[s], st0 = p.sec_st[s];
-    const int ed1 = tl_extend_f0(p, s, ed0, min(L - 2, ed0 + 100), 1, nc7);
-    const int st1 = tl_extend_f0(p, s, st0, max(1, st0 - 100), -1, nc7);
+    const int st1 = p.kb[2 * s], ed1 = p.kb[2 * s + 1];
     const double *f = p.secbuf + p.sec_off[s] - p.sec_lo[s];
     double acc = 0.0;
     for (int j = st1 + lane; j < ed1; j += 32) acc += f[j];

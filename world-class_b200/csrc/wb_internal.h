@@ -30,9 +30,22 @@ int wb_exclusive_scan_u64(const unsigned long long *d_counts, unsigned long long
                           cudaStream_t stream, const unsigned long long *d_skip_in = nullptr,
                           unsigned long long *d_skip_out = nullptr);
 
+// Host-pointer entry points overlap the device -> host transfer of finished output rows with the frames
+// still being computed: the frame kernel is launched in `n` row ranges [bounds[c], bounds[c+1]) that
+// alternate between the caller's stream and `alt` (they are independent, so they overlap each other),
+// and ev[c] is recorded when range c is complete.  Null = one launch.
+struct WbRowChunks {
+  int n = 0;
+  int bounds[17] = {0};
+  cudaEvent_t ev[16] = {nullptr};
+  cudaStream_t alt = nullptr;
+  cudaEvent_t ev_ready = nullptr;   // recorded on the caller's stream when the frame kernel's inputs are ready
+};
+
 int wb_cheaptrick_run(WbWorkspace *ws, int fs, int fft_size, double q1, double f0_floor_internal,
                       const double *d_x, int x_length, const double *d_tpos, const double *d_f0,
-                      int f0_length, double *d_sp, const WbRngCursor &rng, cudaStream_t stream);
+                      int f0_length, double *d_sp, const WbRngCursor &rng, cudaStream_t stream,
+                      const WbRowChunks *chunks = nullptr);
 
 // stand-alone batched transforms (wb_fftapi.cu); kind 0 r2c, 1 c2r, 2 c2c fwd, 3 c2c bwd
 int wb_fft_batch_dev(int kind, const void *d_in, int n, int batch, void *d_out, cudaStream_t stream);
@@ -43,7 +56,7 @@ int wb_d4c_lt_fft_size(int fs);
 int wb_number_of_aperiodicities(int fs);
 int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int x_length, const double *d_tpos,
                const double *d_f0, int f0_length, int out_fft_size, double *d_ap, const WbRngCursor &rng,
-               cudaStream_t stream);
+               cudaStream_t stream, const WbRowChunks *chunks = nullptr);
 
 // Synthesis (wb_synthesis.cu)
 int wb_synthesis_run(WbWorkspace *ws, int fs, int fft_size, double frame_period_ms, const double *d_f0,

@@ -324,17 +324,15 @@ __device__ __forceinline__ void minimum_phase(cplx *S, cplx *MP, const cplx *tw_
 }
 
 template <int LOG2N>
-__global__ void __launch_bounds__(256) response_kernel(RespParams p) {
+__global__ void __launch_bounds__(256, 3) response_kernel(RespParams p) {
   extern __shared__ double2 smem_raw[];
   constexpr int N = 1 << LOG2N, NC = N / 2, bins = NC + 1;
   const int binsp = (bins + 1) & ~1;
   cplx *S = smem_raw;                         // wb_fft_slots(N)
-  cplx *MP = S + wb_fft_slots(N);             // bins
-  cplx *NS = MP + binsp;                      // bins: noise spectrum
-  double *SE = reinterpret_cast<double *>(NS + binsp);  // spectral envelope
+  cplx *MP = S + wb_fft_slots(N);             // bins: minimum-phase spectrum (x noise spectrum for the aperiodic part)
+  double *SE = reinterpret_cast<double *>(MP + binsp);  // spectral envelope
   double *AR = SE + binsp;                    // aperiodic ratio
-  double *PR = AR + binsp;                    // periodic response (N)
-  double *red = PR + N;                       // 128
+  double *red = AR + binsp;                   // 128
   double *W = reinterpret_cast<double *>(S);
   const int tid = threadIdx.x, nt = blockDim.x;
   const int P = *p.n_pulses;
@@ -397,25 +395,22 @@ __global__ void __launch_bounds__(256) response_kernel(RespParams p) {
       double part = 0.0;
       for (int i = tid; i < NC; i += nt) part += W[wb_didx(i)];
       const double dc = wb_block_sum(part, red);
+      // (parked in the pulse's global row; the same thread finishes element i below)
       for (int i = tid; i < NC; i += nt) {
         const double rm = -dc * p.dc_remover[i];
-        PR[i] = rm;
-        PR[i + NC] = W[wb_didx(i)] + rm;
+        resp[i] = rm;
+        resp[i + NC] = W[wb_didx(i)] + rm;
       }
     } else {
-      for (int i = tid; i < N; i += nt) PR[i] = 0.0;
+      for (int i = tid; i < N; i += nt) resp[i] = 0.0;
     }
     __syncthreads();
 
     // ---- aperiodic response (synthesis.cpp:479-530)
     {
+      // minimum phase of the aperiodic envelope first, then the noise spectrum is multiplied into it bin by
+      // bin as the transform emits it (no separate noise-spectrum buffer)
       const double *nz = p.noise + (idx - p.pulse_index[0]);
-      double part = 0.0;
-      for (int i = tid; i < noise_size; i += nt) part += nz[i];
-      const double average = wb_block_sum(part, red) / noise_size;
-      for (int i = tid; i < N; i += nt) W[wb_didx(i)] = (i < noise_size) ? nz[i] - average : 0.0;
-      __syncthreads();
-      wb_rfft_t<1, LOG2N - 1>(S, p.tw_n, [&](int k, cplx X) { NS[k] = X; });
       if (current_vuv != 0.0) {
         for (int k = tid; k < bins; k += nt) W[wb_didx(k)] = log(SE[k] * AR[k]) / 2.0;
       } else {
@@ -423,16 +418,22 @@ __global__ void __launch_bounds__(256) response_kernel(RespParams p) {
       }
       __syncthreads();
       minimum_phase<LOG2N>(S, MP, p.tw_n, p.tw_2n);
-      wb_irfft_t<-1, LOG2N - 1>(S, p.tw_n, [&](int k) {
-        const cplx a = MP[k], b = NS[k];
-        return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+      double part = 0.0;
+      for (int i = tid; i < noise_size; i += nt) part += nz[i];
+      const double average = wb_block_sum(part, red) / noise_size;
+      for (int i = tid; i < N; i += nt) W[wb_didx(i)] = (i < noise_size) ? nz[i] - average : 0.0;
+      __syncthreads();
+      wb_rfft_t<1, LOG2N - 1>(S, p.tw_n, [&](int k, cplx X) {
+        const cplx a = MP[k];
+        MP[k] = make_double2(a.x * X.x - a.y * X.y, a.x * X.y + a.y * X.x);
       });
+      wb_irfft_t<-1, LOG2N - 1>(S, p.tw_n, [&](int k) { return MP[k]; });
     }
     // ---- combine (synthesis.cpp:339-343) with the aperiodic fftshift folded in
     const double sqrt_noise_size = sqrt((double)noise_size);
     for (int i = tid; i < N; i += nt) {
       const double aper = W[wb_didx(i < NC ? i + NC : i - NC)];
-      resp[i] = (PR[i] * sqrt_noise_size + aper) / N;
+      resp[i] = (resp[i] * sqrt_noise_size + aper) / N;
     }
     __syncthreads();
   }
@@ -590,10 +591,10 @@ int wb_synthesis_render(WbWorkspace *ws, int fs, int fft_size, double frame_peri
   p.frame_period = frame_period; p.pulse_index = d_pidx; p.pulse_shift = d_pshift; p.vuv = d_vuv;
   p.n_pulses = d_np; p.noise = d_noise; p.dc_remover = d_dcr; p.tw_n = tw_n; p.tw_2n = tw_2n; p.response = d_resp;
   const int binsp = ((fft_size / 2 + 1) + 1) & ~1;
-  const size_t smem = sizeof(cplx) * (wb_fft_slots(fft_size) + 2 * binsp) + sizeof(double) * (2 * binsp + fft_size + 128);
+  const size_t smem = sizeof(cplx) * (wb_fft_slots(fft_size) + binsp) + sizeof(double) * (2 * binsp + 128);
   p.max_resp_pulses = resp_pulses;
   p.error_flag = ws->error_flag();
-  const int grid = wb_min_i(resp_pulses, 148 * 8);
+  const int grid = wb_min_i(resp_pulses, 148 * 9);
   rc = WB_DISPATCH_LOG2(log2n, 8, 13, {
     if (cudaFuncSetAttribute(response_kernel<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WB_ERR_CUDA;
     WB_LAUNCH("response_kernel", response_kernel<L2><<<grid, 256, smem, stream>>>(p));
