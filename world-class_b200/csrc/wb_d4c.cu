@@ -12,6 +12,7 @@
 #include "wb_smooth.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 #include <vector>
 
 namespace {
@@ -356,6 +357,7 @@ struct BodyParams {
   int seg_capacity;
   int *error_flag;
   int frame_begin;                     // this launch covers frames frame_begin + blockIdx.x
+  int debug_skip;                      // profiling only (WB_D4C_SKIP, profiles/d4c_phases.py): phases to leave out
 };
 
 
@@ -400,7 +402,15 @@ __global__ void __launch_bounds__(D4C_BODY_THREADS, 2) d4c_body_kernel(BodyParam
   // The reference transforms w[n] and (n+1) w[n] separately; both are real, so one complex
   // transform of z[n] = w[n] + i (n+1) w[n] yields both spectra.  While the window is being
   // built the imaginary parts of the slots hold the window samples.
-  for (int c = 0; c < 2; ++c) {
+  // (the window angle of sample j is the same in both windows: its rotation constants are set up once)
+  double rot_sd = 0.0, rot_cd = 1.0, rot_sn = 0.0, rot_cs = 1.0;
+  if constexpr (N == 16 * D4C_BODY_THREADS) {
+    const double c1 = 2.0 / 4.0 / fs;
+    const double c2 = WB_PI * f0;
+    sincos(c2 * c1 * D4C_BODY_THREADS, &rot_sd, &rot_cd);
+    sincos(c2 * (c1 * (tid - d4c_half_window(4.0, fs, f0))), &rot_sn, &rot_cs);
+  }
+  for (int c = 0; c < ((p.debug_skip & 8) ? 0 : 2); ++c) {
     const double cpos = (c == 0) ? pos - 0.25 / f0 : pos + 0.25 / f0;
     if constexpr (N == 16 * D4C_BODY_THREADS) {
       // One radix-16 butterfly per thread in the first FFT pass: thread t owns samples t + 256 q, exactly the
@@ -409,11 +419,8 @@ __global__ void __launch_bounds__(D4C_BODY_THREADS, 2) d4c_body_kernel(BodyParam
       const int hw = d4c_half_window(4.0, fs, f0);
       const int wlen = 2 * hw + 1;
       const int origin = wb_round(cpos * fs + 0.001);
-      const double c1 = 2.0 / 4.0 / fs;
-      const double c2 = WB_PI * f0;
-      double sd, cd, sn, cs;
-      sincos(c2 * c1 * D4C_BODY_THREADS, &sd, &cd);
-      sincos(c2 * (c1 * (tid - hw)), &sn, &cs);
+      const double sd = rot_sd, cd = rot_cd;
+      double sn = rot_sn, cs = rot_cs;
       double v[16], w[16];
       double s1 = 0.0, s2 = 0.0;
 #pragma unroll
@@ -439,11 +446,13 @@ __global__ void __launch_bounds__(D4C_BODY_THREADS, 2) d4c_body_kernel(BodyParam
       for (int q = 0; q < 16; ++q) {
         if (tid + q * D4C_BODY_THREADS < wlen) { v[q] -= w[q] * coef; pw += v[q] * v[q]; }
       }
-      const double power = sqrt(wb_block_sum(pw, red));
+      // unit power (d4c.cpp:372-380): one reciprocal per window instead of a division per sample (the
+      // quotients differ from the reference's by at most one ulp)
+      const double inv_power = 1.0 / sqrt(wb_block_sum(pw, red));
       noise += wlen;
       wb_cfft_dif_in_t<1, LOG2N>(S, p.tw_2n, [&](int j, int q) {
         cplx z = make_double2(0.0, 0.0);
-        if (j < wlen) { z.x = v[q] / power; z.y = z.x * (j + 1.0); }
+        if (j < wlen) { z.x = v[q] * inv_power; z.y = z.x * (j + 1.0); }
         return z;
       });
     } else {
@@ -492,8 +501,10 @@ __global__ void __launch_bounds__(D4C_BODY_THREADS, 2) d4c_body_kernel(BodyParam
   // ---- static group delay (d4c.cpp:440-460)
   for (int k = tid; k < bins; k += nt) SC[k] = SC[k] / SP[k];
   __syncthreads();
-  wb_linear_smoothing(SC, SC, f0 / 2.0, fs, N, seg, seg_capacity, red);
-  wb_linear_smoothing(SC, SP, f0, fs, N, seg, seg_capacity, red);
+  if (!(p.debug_skip & 2)) {
+    wb_linear_smoothing(SC, SC, f0 / 2.0, fs, N, seg, seg_capacity, red);
+    wb_linear_smoothing(SC, SP, f0, fs, N, seg, seg_capacity, red);
+  }
   for (int k = tid; k < bins; k += nt) SC[k] -= SP[k];
   __syncthreads();
 
@@ -504,7 +515,7 @@ __global__ void __launch_bounds__(D4C_BODY_THREADS, 2) d4c_body_kernel(BodyParam
   // Bands are transformed in pairs: band b in the real part, band b+1 in the imaginary part of ONE
   // complex N-point transform (both are real, so the spectra separate exactly); the two power
   // spectra are left interleaved in the FFT slots and both order statistics are resolved together.
-  for (int b = 0; b < p.n_ap; b += 2) {
+  for (int b = 0; b < ((p.debug_skip & 4) ? 0 : p.n_ap); b += 2) {
     const bool has2 = (b + 1 < p.n_ap);
     const int center_a = static_cast<int>(WB_FREQ_INTERVAL * (b + 1) * N / fs);
     const int center_b = static_cast<int>(WB_FREQ_INTERVAL * (b + 2) * N / fs);
@@ -535,7 +546,8 @@ __global__ void __launch_bounds__(D4C_BODY_THREADS, 2) d4c_body_kernel(BodyParam
       and_a &= ka; or_a |= ka; and_b &= kb; or_b |= kb;
     }
     wb_block_sum2(tot_a, tot_b, red);
-    double low_a, low_b;
+    double low_a = 0.5 * tot_a, low_b = 0.5 * tot_b;
+    if (!(p.debug_skip & 1))
     // (SP is free from here on: it holds the 2 x 2^(LOG2N-1) counters of the select)
     d4c_sum_smallest2<LOG2N - 1>([&](int i, int w) { const cplx v = S[wb_sidx(wb_brev(i, log2n))]; return w == 0 ? v.x : v.y; },
                                  bins, m_small, has2, and_a, or_a, and_b, or_b, reinterpret_cast<int *>(SP), ctl, red, low_a, low_b);
@@ -675,6 +687,7 @@ int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int
     p.out_fft_size = out_fft_size; p.ap = d_ap;
     p.seg_capacity = 0;  // the smoothing scratch aliases the FFT slots
     p.error_flag = ws->error_flag();
+    p.debug_skip = getenv("WB_D4C_SKIP") ? atoi(getenv("WB_D4C_SKIP")) : 0;
     const int binsp = ((N / 2 + 1) + 1) & ~1;
     const size_t smem = sizeof(cplx) * wb_fft_slots(N) + sizeof(double) * (2 * binsp + 320) +
                         sizeof(unsigned long long) * (SEL_CTL_WORDS + 2 * SEL_LIST) + sizeof(double) * (D4C_MAX_AP + 2);
