@@ -302,7 +302,8 @@ struct wb_pipeline {
   // After Harvest the chain forks: CheapTrick stays on the caller's stream, D4C runs on `d4c_stream`
   // and the Synthesis time base / pulse list / noise on `side`; they join before the impulse responses.
   cudaStream_t side = nullptr, d4c_stream = nullptr;
-  cudaEvent_t ev_f0 = nullptr, ev_tb = nullptr, ev_ct_count = nullptr, ev_body_count = nullptr, ev_d4c = nullptr;
+  cudaEvent_t ev_f0 = nullptr, ev_tb = nullptr, ev_ct_count = nullptr, ev_body_count = nullptr, ev_d4c = nullptr,
+              ev_start = nullptr;
   // CUDA graph of one whole run (captured after a warm run with the same arguments)
   bool use_graph = false;
   cudaGraphExec_t graph_exec = nullptr;
@@ -319,6 +320,7 @@ struct wb_pipeline {
     if (ev_ct_count) cudaEventDestroy(ev_ct_count);
     if (ev_body_count) cudaEventDestroy(ev_body_count);
     if (ev_d4c) cudaEventDestroy(ev_d4c);
+    if (ev_start) cudaEventDestroy(ev_start);
     if (side) cudaStreamDestroy(side);
     if (d4c_stream) cudaStreamDestroy(d4c_stream);
     if (d_rng_private) cudaFree(d_rng_private);
@@ -742,6 +744,7 @@ int wb_pipeline_create(int fs, const WbHarvestOption *hopt, const WbCheapTrickOp
       cudaEventCreateWithFlags(&p->ev_ct_count, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&p->ev_body_count, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&p->ev_d4c, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&p->ev_start, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&p->ev_tb, cudaEventDisableTiming) != cudaSuccess) {
     delete p;
     return WB_ERR_CUDA;
@@ -845,6 +848,12 @@ static int pipeline_enqueue(wb_pipeline_t *p, const double *d_x, int x_length, d
   if (!d_y && y_length > 0) d_y = (double *)p->ws.get("pl_y", sizeof(double) * (size_t)y_length);
   if (!d_tpos || !d_f0 || !d_sp || !d_ap) return WB_ERR_CUDA;
   int rc, Lb = 0;
+  // (side stream, joined with the pulse list further down: warm L2 with the randn jump tables while Harvest runs)
+  if (y_length > 0 && !wb_prof_is_enabled()) {
+    WB_CUDA_CHECK(cudaEventRecord(p->ev_start, st));
+    WB_CUDA_CHECK(cudaStreamWaitEvent(p->side, p->ev_start, 0));
+    if ((rc = wb_rng_prefetch_tables(p->side))) return rc;
+  }
   // Harvest (always analysed on the 1 ms grid, harvest.cpp:185-204)
   if (fp == 1.0) {
     if ((rc = wb_harvest_run_basic(&p->plan, &p->ws, d_x, x_length, 1, d_f0, &Lb, st))) return rc;

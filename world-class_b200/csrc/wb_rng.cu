@@ -131,7 +131,27 @@ __global__ void rng_advance_kernel(WbRngState *state, const uint4 *__restrict__ 
   }
 }
 
+// Pulls the jump tables into L2 (they are read in chains of dependent loads by every fill): issued on a
+// side stream at the start of a whole-chain run, long before the first fill needs them.
+__global__ void rng_prefetch_kernel(const uint4 *__restrict__ pow_tables, int n, unsigned *__restrict__ sink) {
+  unsigned acc = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint4 v = __ldg(&pow_tables[i]);
+    acc ^= v.x ^ v.y ^ v.z ^ v.w;
+  }
+  if (acc == 0x9e3779b9u) *sink = acc;  // keeps the loads alive; practically never taken
+}
+
 }  // namespace
+
+int wb_rng_prefetch_tables(cudaStream_t stream) {
+  static unsigned *d_sink = nullptr;
+  if (!d_sink && cudaMalloc(&d_sink, sizeof(unsigned)) != cudaSuccess) return WB_ERR_CUDA;
+  const int n = WB_RNG_NPOW * WB_RNG_TAB_ENTRIES;
+  WB_LAUNCH("rng_prefetch_kernel", rng_prefetch_kernel<<<24, 256, 0, stream>>>(g_d_pow, n, d_sink));
+  WB_CUDA_CHECK(cudaGetLastError());
+  return WB_OK;
+}
 
 int wb_rng_init() {
   std::call_once(g_once, []() { g_init_status = do_init(); });

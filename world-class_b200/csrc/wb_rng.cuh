@@ -113,6 +113,9 @@ int wb_rng_fill(const WbRngState *d_state, const unsigned long long *d_skip_or_n
 int wb_rng_advance(WbRngState *d_state, const unsigned long long *d_count, const unsigned long long *d_count2_or_null,
                    cudaStream_t stream);
 
+// warms L2 with the jump tables (asynchronous, see rng_prefetch_kernel)
+int wb_rng_prefetch_tables(cudaStream_t stream);
+
 // Where a stage's randn() draws sit in the stream and how it hands the position on.  The stage draws from
 // *state advanced by *skip_in calls; once it has counted its own calls it writes skip_in + count to
 // *skip_out.  Stand-alone stage calls set `advance` (the state itself is moved past the draws at the end);
