@@ -80,11 +80,18 @@ __global__ void __launch_bounds__(1024) lt_count_scan_kernel(const double *__res
   }, n, offsets, skip_in, skip_out);
 }
 
+// The stream position of the body draws is (position before D4C) + (Love Train draws): the two are
+// added here, so the Love Train count itself does not have to wait for the stage before D4C.
 __global__ void __launch_bounds__(1024) body_count_scan_kernel(const double *__restrict__ f0, const double *__restrict__ ap0,
                                                                int n, int fs, double threshold,
                                                                unsigned long long *__restrict__ offsets,
-                                                               const unsigned long long *__restrict__ skip_in,
+                                                               const unsigned long long *__restrict__ skip_before,
+                                                               const unsigned long long *__restrict__ lt_total,
+                                                               unsigned long long *__restrict__ skip_mid,
                                                                unsigned long long *__restrict__ skip_out) {
+  if (threadIdx.x == 0) *skip_mid = (skip_before ? *skip_before : 0ull) + *lt_total;
+  __syncthreads();
+  const unsigned long long *skip_in = skip_mid;
   wb_block_count_scan([&](int i) {
     unsigned long long c = 0;
     if (!(f0[i] == 0 || ap0[i] <= threshold)) {
@@ -637,9 +644,13 @@ int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int
 
   // Nuttall window of the band analysis (d4c.cpp:69-72, world_common.cpp:118-126), host libm like the reference
   const int window_length = static_cast<int>(WB_FREQ_INTERVAL * N / fs) * 2 + 1;
+  // (cached per workspace: the upload below is skipped -- and absent from a captured graph -- once the
+  // table of this length sits in this buffer)
   double *d_nuttall = (double *)ws->get("d4c_nuttall", sizeof(double) * window_length);
-  if (!d_nuttall) return WB_ERR_CUDA;
-  {
+  int *nuttall_tag = (int *)ws->get_pinned("d4c_nuttall_tag", sizeof(int) * 4);
+  if (!d_nuttall || !nuttall_tag) return WB_ERR_CUDA;
+  const long long tag_ptr = (long long)(size_t)d_nuttall;
+  if (nuttall_tag[0] != window_length || nuttall_tag[1] != (int)(tag_ptr & 0x7fffffff) || nuttall_tag[2] != (int)(tag_ptr >> 31)) {
     double *h = (double *)ws->get_pinned("d4c_nuttall_h", sizeof(double) * window_length);
     if (!h) return WB_ERR_CUDA;
     for (int i = 0; i < window_length; ++i) {
@@ -648,12 +659,15 @@ int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int
              0.012604 * cos(6.0 * WB_PI * tmp);
     }
     WB_CUDA_CHECK(cudaMemcpyAsync(d_nuttall, h, sizeof(double) * window_length, cudaMemcpyHostToDevice, stream));
+    nuttall_tag[0] = window_length; nuttall_tag[1] = (int)(tag_ptr & 0x7fffffff); nuttall_tag[2] = (int)(tag_ptr >> 31);
   }
 
-  // ---- Love Train
-  if (rng.wait_skip_in) WB_CUDA_CHECK(cudaStreamWaitEvent(stream, rng.wait_skip_in, 0));
-  WB_LAUNCH("lt_count_scan_kernel", lt_count_scan_kernel<<<1, 1024, 0, stream>>>(d_f0, f0_length, fs, 40.0, d_offsets, rng.skip_in, d_skip_mid));
+  // ---- Love Train (its frame offsets do not depend on the stream position: only the draw itself waits)
+  unsigned long long *d_lt_total = (unsigned long long *)ws->get("d4c_lt_total", sizeof(unsigned long long));
+  if (!d_lt_total) return WB_ERR_CUDA;
+  WB_LAUNCH("lt_count_scan_kernel", lt_count_scan_kernel<<<1, 1024, 0, stream>>>(d_f0, f0_length, fs, 40.0, d_offsets, nullptr, d_lt_total));
   WB_CUDA_CHECK(cudaGetLastError());
+  if (rng.wait_skip_in) WB_CUDA_CHECK(cudaStreamWaitEvent(stream, rng.wait_skip_in, 0));
   int rc;
   if ((rc = wb_rng_fill(rng.state, rng.skip_in, d_offsets + f0_length, max_noise_lt, d_noise, stream))) return rc;
   {
@@ -674,7 +688,7 @@ int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int
   }
   // ---- body
   WB_LAUNCH("body_count_scan_kernel", body_count_scan_kernel<<<1, 1024, 0, stream>>>(d_f0, d_ap0, f0_length, fs, threshold, d_offsets,
-                                                                                  d_skip_mid, d_skip_end));
+                                                                                  rng.skip_in, d_lt_total, d_skip_mid, d_skip_end));
   WB_CUDA_CHECK(cudaGetLastError());
   if (rng.record_skip_out) WB_CUDA_CHECK(cudaEventRecord(rng.record_skip_out, stream));
   if ((rc = wb_rng_fill(rng.state, d_skip_mid, d_offsets + f0_length, max_noise_body, d_noise, stream))) return rc;

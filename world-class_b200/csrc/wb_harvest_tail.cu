@@ -48,8 +48,11 @@ __device__ __forceinline__ int tl_vuv(const double *f0, int n, int i) {
   return (i <= 0 || i >= n - 1) ? 0 : (f0[i] > 0 ? 1 : 0);
 }
 
-// getBoundaryList (harvest.cpp:296-314).  All threads; returns the number of boundaries.
-__device__ int tl_boundaries(const double *f0, int n, int *blist, int *s_scan) {
+// getBoundaryList (harvest.cpp:296-314).  All threads; returns the number of boundaries.  The list goes to
+// the shared-memory buffer when it fits (the usual case: a few dozen voiced sections), else to global
+// scratch; *blist_out tells which.
+__device__ int tl_boundaries(const double *f0, int n, int *blist_shared, int shared_cap, int *blist_global,
+                             int **blist_out, int *s_scan) {
   const int tid = threadIdx.x, nt = blockDim.x;
   const int chunk = (n + nt - 1) / nt;
   const int b = max(1, tid * chunk), e = min(n, (tid + 1) * chunk);
@@ -66,6 +69,8 @@ __device__ int tl_boundaries(const double *f0, int n, int *blist, int *s_scan) {
   }
   int k = s_scan[tid] - cnt;
   const int total = s_scan[nt - 1];
+  int *blist = (total <= shared_cap) ? blist_shared : blist_global;
+  *blist_out = blist;
   for (int i = b; i < e; ++i) {
     if (tl_vuv(f0, n, i) - tl_vuv(f0, n, i - 1) != 0) { blist[k] = i - k % 2; ++k; }
   }
@@ -275,9 +280,27 @@ __device__ void tl_exclusive_scan(const int *v, int n, int *out, int *s_scan) {
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(TL_THREADS) harvest_tail_kernel(TailParams p) {
+#define TL_SMAX 192   // sections whose bookkeeping fits in shared memory
+__global__ void __launch_bounds__(TL_THREADS) harvest_tail_kernel(TailParams p_in) {
   extern __shared__ double tl_smem[];   // p.smem_doubles doubles: contour buffers A | B (later: forward-filter scratch)
   __shared__ int s_scan[TL_THREADS];
+  // Section bookkeeping (boundaries, ranges, offsets, ...) is read in chains of dependent loads by a few
+  // threads: it lives in shared memory whenever the number of sections allows (else in global scratch).
+  __shared__ int s_blist[2 * TL_SMAX + 2];
+  __shared__ int s_secint[9 * (TL_SMAX + 2)];
+  __shared__ double s_secsum[TL_SMAX + 2];
+  TailParams p = p_in;
+  auto use_shared_sections = [&](bool yes) {
+    if (yes) {
+      const int m = TL_SMAX + 2;
+      p.sec_st = s_secint; p.sec_ed = s_secint + m; p.sec_lo = s_secint + 2 * m; p.sec_len = s_secint + 3 * m;
+      p.sec_off = s_secint + 4 * m; p.kb = s_secint + 5 * m; p.kslot = s_secint + 7 * m; p.order = s_secint + 8 * m;
+      p.sec_sum = s_secsum;
+    } else {
+      p.sec_st = p_in.sec_st; p.sec_ed = p_in.sec_ed; p.sec_lo = p_in.sec_lo; p.sec_len = p_in.sec_len;
+      p.sec_off = p_in.sec_off; p.kb = p_in.kb; p.kslot = p_in.kslot; p.order = p_in.order; p.sec_sum = p_in.sec_sum;
+    }
+  };
   __shared__ double s_red[64];
   __shared__ int s_i[8];
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
@@ -315,7 +338,7 @@ __global__ void __launch_bounds__(TL_THREADS) harvest_tail_kernel(TailParams p) 
   TL_STAMP();  // 1: after fixStep1
   // ---- fixStep2: drop voiced sections shorter than 6 (in place: the boundary list is extracted first)
   {
-    const int nb = tl_boundaries(cB, L, p.blist, s_scan);
+    const int nb = tl_boundaries(cB, L, s_blist, 2 * TL_SMAX, p_in.blist, &p.blist, s_scan);
     for (int k = tid; k < nb / 2; k += nt) {
       const int st = p.blist[2 * k], ed = p.blist[2 * k + 1];
       if (ed - st >= 6) continue;
@@ -329,8 +352,9 @@ __global__ void __launch_bounds__(TL_THREADS) harvest_tail_kernel(TailParams p) 
   // ---- fixStep3
   int nsec;
   {
-    const int nb = tl_boundaries(cB, L, p.blist, s_scan);
+    const int nb = tl_boundaries(cB, L, s_blist, 2 * TL_SMAX, p_in.blist, &p.blist, s_scan);
     nsec = nb / 2;
+    use_shared_sections(nsec <= TL_SMAX);
     if (nsec > p.maxsec) {
       if (tid == 0) atomicExch(p.error_flag, WB_ERR_UNSUPPORTED);
       nsec = 0;
@@ -460,7 +484,7 @@ __global__ void __launch_bounds__(TL_THREADS) harvest_tail_kernel(TailParams p) 
   for (int i = tid; i < L; i += nt) cB[i] = cA[i];
   __syncthreads();
   {
-    const int nb = tl_boundaries(cA, L, p.blist, s_scan);
+    const int nb = tl_boundaries(cA, L, s_blist, 2 * TL_SMAX, p_in.blist, &p.blist, s_scan);
     for (int g = tid; g < nb / 2 - 1; g += nt) {
       const int ed = p.blist[2 * g + 1], st_next = p.blist[2 * (g + 1)];
       const int distance = st_next - ed - 1;
@@ -482,8 +506,9 @@ __global__ void __launch_bounds__(TL_THREADS) harvest_tail_kernel(TailParams p) 
   for (int i = tid; i < Lp; i += nt) pad[i] = (i >= TL_LAG && i < TL_LAG + L) ? cB[i - TL_LAG] : 0.0;
   for (int i = tid; i < L; i += nt) p.out[i] = 0.0;
   __syncthreads();
-  const int nbs = tl_boundaries(pad, Lp, p.blist, s_scan);
+  const int nbs = tl_boundaries(pad, Lp, s_blist, 2 * TL_SMAX, p_in.blist, &p.blist, s_scan);
   const int nsm = nbs / 2;
+  use_shared_sections(nsm <= TL_SMAX);
   if (nsm > p.maxsec) {
     if (tid == 0) atomicExch(p.error_flag, WB_ERR_UNSUPPORTED);
     return;

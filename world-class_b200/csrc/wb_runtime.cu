@@ -40,6 +40,7 @@ void *WbWorkspace::get_pinned(const std::string &name, size_t bytes) {
     fprintf(stderr, "worldb200: cudaMallocHost(%zu) failed for %s\n", grow, name.c_str());
     return nullptr;
   }
+  memset(p, 0, grow);  // (cache tags kept in pinned buffers rely on a zero start)
   pinned_[name] = Buf{p, grow};
   return p;
 }

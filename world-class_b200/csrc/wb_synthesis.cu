@@ -558,12 +558,19 @@ int wb_synthesis_render(WbWorkspace *ws, int fs, int fft_size, double frame_peri
   const cplx *tw_2n = wb_twiddle_table(2 * fft_size);
   if (!tw_n || !tw_2n) return WB_ERR_CUDA;
   {
-    double *h = (double *)ws->get_pinned("syn_dcr_h", sizeof(double) * fft_size);
-    if (!h) return WB_ERR_CUDA;
-    std::vector<double> r;
-    make_dc_remover(fft_size, r);
-    for (int i = 0; i < fft_size; ++i) h[i] = r[i];
-    WB_CUDA_CHECK(cudaMemcpyAsync(d_dcr, h, sizeof(double) * fft_size, cudaMemcpyHostToDevice, stream));
+    // cached per workspace (see the Nuttall table in wb_d4c.cu)
+    int *tag = (int *)ws->get_pinned("syn_dcr_tag", sizeof(int) * 4);
+    if (!tag) return WB_ERR_CUDA;
+    const long long tag_ptr = (long long)(size_t)d_dcr;
+    if (tag[0] != fft_size || tag[1] != (int)(tag_ptr & 0x7fffffff) || tag[2] != (int)(tag_ptr >> 31)) {
+      double *h = (double *)ws->get_pinned("syn_dcr_h", sizeof(double) * fft_size);
+      if (!h) return WB_ERR_CUDA;
+      std::vector<double> r;
+      make_dc_remover(fft_size, r);
+      for (int i = 0; i < fft_size; ++i) h[i] = r[i];
+      WB_CUDA_CHECK(cudaMemcpyAsync(d_dcr, h, sizeof(double) * fft_size, cudaMemcpyHostToDevice, stream));
+      tag[0] = fft_size; tag[1] = (int)(tag_ptr & 0x7fffffff); tag[2] = (int)(tag_ptr >> 31);
+    }
   }
   int rc;
   if (!noise_ready) {
