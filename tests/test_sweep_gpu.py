@@ -67,6 +67,14 @@ def test_loud_input_takes_the_truncating_dc_path(wb, signals):
     _compare(_chain(wb, x, fs), ref, "loud input")
 
 
+def test_long_utterance(wb, signals):
+    """70 s in one piece: 88 overlap-save blocks in Harvest, contour buffers beyond shared memory."""
+    fs = 16000
+    x = signals.synth_speech(fs, 70.0, seed=25)
+    ref, _ = refbin.run_reference(x, fs, stages="hcds")
+    _compare(_chain(wb, x, fs), ref, "70 s utterance")
+
+
 def test_ragged_lengths(wb, signals):
     """Lengths that are not multiples of the decimation ratio / frame hop."""
     fs = 48000

@@ -430,35 +430,38 @@ __global__ void frame_time_kernel(int n, int frame_period, double *__restrict__ 
 }
 
 #define IV_THREADS 512
+#define IV_MAX_BLOCKS 128   /* overlap-save blocks per utterance: ~117 s of audio at the 8 kHz analysis rate */
 #define IV_PER_ITER ((IV_THREADS / 32) * 31)
 __global__ void __launch_bounds__(IV_THREADS) interval_kernel(IntervalParams p) {
-  __shared__ int s_off[65];
+  __shared__ int s_off[IV_MAX_BLOCKS + 1];
   // channel * 4 + kind; the high channels have the most zero crossings: schedule them first
   const int ct = gridDim.x - 1 - blockIdx.x;
   const int *cnt = p.seg_count + (size_t)ct * p.n_blocks;
   if (threadIdx.x < 32) {
-    // exclusive offsets of the per-block edge runs (n_blocks <= 63): the ordered edge list of this
-    // (channel, kind) is their concatenation
+    // exclusive offsets of the per-block edge runs (n_blocks <= IV_MAX_BLOCKS): the ordered edge list of
+    // this (channel, kind) is their concatenation.  Lane l owns blocks 4 l .. 4 l + 3.
     const int lane = threadIdx.x;
-    const int c0 = lane < p.n_blocks ? cnt[lane] : 0, c1 = lane + 32 < p.n_blocks ? cnt[lane + 32] : 0;
-    int i0 = c0, i1 = c1;
+    int c[4], sum = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { c[q] = (4 * lane + q < p.n_blocks) ? cnt[4 * lane + q] : 0; sum += c[q]; }
+    int incl = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const int t0 = __shfl_up_sync(0xffffffffu, i0, o), t1 = __shfl_up_sync(0xffffffffu, i1, o);
-      if (lane >= o) { i0 += t0; i1 += t1; }
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
     }
-    const int tot0 = __shfl_sync(0xffffffffu, i0, 31);
-    s_off[lane] = i0 - c0;
-    s_off[lane + 32] = tot0 + i1 - c1;
-    if (lane == 31) { s_off[64] = tot0 + i1; p.ecount[ct] = min(tot0 + i1, p.ecap); }
+    int run = incl - sum;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { s_off[4 * lane + q] = run; run += c[q]; }
+    if (lane == 31) { s_off[IV_MAX_BLOCKS] = run; p.ecount[ct] = min(run, p.ecap); }
   }
   __syncthreads();
-  const int total = min(s_off[64], p.ecap);
+  const int total = min(s_off[IV_MAX_BLOCKS], p.ecap);
   const int ni = total < 2 ? 0 : total - 1;  // number of intervals
   const double *seg = p.seg_edges + (size_t)ct * p.n_blocks * p.bcap;
   // edge k of the concatenated list: last block b with s_off[b] <= k (blocks beyond n_blocks hold the total)
   auto edge = [&](int k) -> double {
-    int lo = 0, hi = 63;
+    int lo = 0, hi = IV_MAX_BLOCKS - 1;
     while (lo < hi) {
       const int mid = (lo + hi + 1) >> 1;
       if (s_off[mid] <= k) lo = mid; else hi = mid - 1;
@@ -911,7 +914,7 @@ int wb_harvest_run_basic(WbHarvestPlan *pl, WbWorkspace *ws, const double *d_x, 
   // ---- H5: channels
   const int ecap = y_length / 2 + 4;
   const int bcap = pl->V / 2 + 2;
-  if (n_blocks > 63) return WB_ERR_UNSUPPORTED;  // TODO(long streams): tile the block axis
+  if (n_blocks > IV_MAX_BLOCKS) return WB_ERR_UNSUPPORTED;  // ~117 s; longer streams are processed in segments (parallel.py)
   int *d_ecount = (int *)ws->get("hv_ecount", sizeof(int) * nch * 4);
   double *d_seg = (double *)ws->get("hv_seg_edges", sizeof(double) * (size_t)nch * 4 * n_blocks * bcap);
   int *d_segc = (int *)ws->get("hv_seg_count", sizeof(int) * (size_t)nch * 4 * n_blocks);

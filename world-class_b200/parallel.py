@@ -21,7 +21,7 @@ def shard_indices(n_items, rank, world):
     return list(range(rank, n_items, world))
 
 
-def plan_segments(n_samples, fs, segment_seconds=60.0, halo_seconds=1.0):
+def plan_segments(n_samples, fs, segment_seconds=30.0, halo_seconds=1.0):
     """Cuts [0, n_samples) into segment cores of `segment_seconds`; returns a list of dicts
     core=(a, b) and padded=(a - halo, b + halo) clipped to the stream, sample indices."""
     seg = max(1, int(round(segment_seconds * fs)))
@@ -45,7 +45,7 @@ def extract_core(y_padded, seg):
     return core
 
 
-def process_stream(x, fs, process_segment, segment_seconds=60.0, halo_seconds=1.0, group=None):
+def process_stream(x, fs, process_segment, segment_seconds=30.0, halo_seconds=1.0, group=None):
     """Shards a long stream over the ranks of `group` and returns the stitched output on every rank.
 
     process_segment(x_padded) -> y_padded must map a padded segment to its re-synthesis (same
