@@ -10,7 +10,7 @@ for _ in range(3):
     pl.run_dev(d_x.data_ptr(), len(x))
 wb.device_synchronize()
 c=pl.debug_read("tl_clocks",(16,),dtype=np.int64)
-d=np.diff(c[:11])
-print("phase cycles:", d.tolist(), "total", c[10]-c[0])
-names=["fixStep1","fixStep2(+bound)","bound+meta","getMultiChannel","extend","extendSub+sort","merge","fixStep4(+bound)","smooth setup","fwd IIR","bwd IIR"]
+d=np.diff(c[:9])
+print("phase cycles:", d.tolist(), "total", c[8]-c[0])
+names=["fixStep1","fixStep2(+bound)","bound+meta+sections","extend","extendSub+sort","merge","fixStep4(+bound)","smooth setup"]
 for n,v in zip(names,d): print("%-18s %8d cyc  %6.1f us" % (n, v, v/1.9e3))

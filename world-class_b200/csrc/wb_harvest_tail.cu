@@ -18,6 +18,8 @@
 // reference's rows hold there.
 #include "wb_harvest.h"
 
+#include <algorithm>
+
 namespace {
 
 #define TL_THREADS 512
@@ -42,6 +44,7 @@ struct TailParams {
   int smem_doubles;    // dynamic shared memory available to the kernel
   long long *clocks;   // [16] phase time stamps (clock64 of thread 0), for profiling the serial tail
   int *error_flag;
+  int *smooth_hdr;     // [4] section count / forward items / backward items of the smoothing passes
 };
 
 __device__ __forceinline__ int tl_vuv(const double *f0, int n, int i) {
@@ -125,6 +128,11 @@ __device__ __forceinline__ double tl_select_best_fast(double reference_f0, doubl
   if (mi < 0) return 0.0;
   const double v = __shfl_sync(0xffffffffu, vl, mi & 31);
   const double dmin = __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
+  // `fl(dmin / ref) > allowed`: the quotient (the long pole of this serial chain) is only formed when the
+  // decision is within rounding distance of the threshold
+  const double bound = allowed * reference_f0;
+  if (dmin < bound * (1.0 - 1e-12)) return v;
+  if (dmin > bound * (1.0 + 1e-12)) return 0.0;
   const double err = dmin / reference_f0;
   return (err > allowed) ? 0.0 : v;
 }
@@ -313,8 +321,8 @@ __global__ void __launch_bounds__(TL_THREADS) harvest_tail_kernel(TailParams p_i
   const bool two_ok = p.smem_doubles >= 2 * Lp_cap;
   double *cA = two_ok ? tl_smem : p.gA;
   double *cB = two_ok ? tl_smem + Lp_cap : p.gB;
-  double *fw_smem = tl_smem + Lp_cap;
-  const long long fw_smem_cap = two_ok ? (long long)p.smem_doubles - Lp_cap : 0;
+  // (the smoothing kernels that follow read this header: no work unless the set-up at the end fills it in)
+  if (tid == 0) { p_in.smooth_hdr[0] = 0; p_in.smooth_hdr[1] = 0; p_in.smooth_hdr[2] = 0; }
   int clk_i = 0;
 #define TL_STAMP() do { if (tid == 0) p.clocks[clk_i] = clock64(); ++clk_i; } while (0)
   TL_STAMP();  // 0: start
@@ -500,121 +508,179 @@ __global__ void __launch_bounds__(TL_THREADS) harvest_tail_kernel(TailParams p_i
   }
 
   TL_STAMP();  // 7: after fixStep4
-  // ---- smoothF0Contour
+  // ---- smoothF0Contour (harvest.cpp:670-703), set-up only: the padded contour and the section table go to
+  // global memory; the two zero-phase filter passes run as their own kernels over the whole GPU (this CTA
+  // would spend ~40 us of single-SM instruction issue on them)
   const int Lp = L + 2 * TL_LAG;
   double *pad = cA;
-  for (int i = tid; i < Lp; i += nt) pad[i] = (i >= TL_LAG && i < TL_LAG + L) ? cB[i - TL_LAG] : 0.0;
+  for (int i = tid; i < Lp; i += nt) {
+    const double v = (i >= TL_LAG && i < TL_LAG + L) ? cB[i - TL_LAG] : 0.0;
+    pad[i] = v;
+    p_in.pad[i] = v;
+  }
   for (int i = tid; i < L; i += nt) p.out[i] = 0.0;
   __syncthreads();
   const int nbs = tl_boundaries(pad, Lp, s_blist, 2 * TL_SMAX, p_in.blist, &p.blist, s_scan);
   const int nsm = nbs / 2;
-  use_shared_sections(nsm <= TL_SMAX);
   if (nsm > p.maxsec) {
     if (tid == 0) atomicExch(p.error_flag, WB_ERR_UNSUPPORTED);
     return;
   }
-  // per section: forward outputs on [st, min(ed + LAG, Lp - 1)], stored at fw[fwoff + (i - st)]
+  // per section: forward outputs on [st, min(ed + LAG, Lp - 1)], stored at fw[fwoff + (i - st)];
+  // work items = TL_CHUNK outputs each.  Table layout (global): st | ed | flen | fw offset | first fwd item |
+  // first bwd item, each maxsec + 2 ints.
   if (tid == 0) {
     long long off = 0;
-    int items = 0;
+    int items = 0, items_b = 0;
     for (int s = 0; s < nsm; ++s) {
       const int st = p.blist[2 * s], ed = p.blist[2 * s + 1];
       const int flen = min(ed + TL_LAG, Lp - 1) - st + 1;
-      p.sec_st[s] = st; p.sec_ed[s] = ed; p.sec_len[s] = flen; p.sec_off[s] = (int)off;
-      p.sec_lo[s] = items;  // first forward work item of this section
+      p_in.sec_st[s] = st; p_in.sec_ed[s] = ed; p_in.sec_len[s] = flen; p_in.sec_off[s] = (int)off;
+      p_in.sec_lo[s] = items;   // first forward work item of this section
+      p_in.kb[s] = items_b;     // first backward work item
       off += flen;
       items += (flen + TL_CHUNK - 1) / TL_CHUNK;
+      items_b += (ed - st + 1 + TL_CHUNK - 1) / TL_CHUNK;
     }
-    p.sec_lo[nsm] = items;
-    s_i[2] = items;
-    s_i[3] = (off > p.fw_cap) ? 1 : 0;
-    s_i[5] = (off <= fw_smem_cap) ? 1 : 0;  // forward outputs fit in shared memory
+    p_in.sec_lo[nsm] = items;
+    p_in.kb[nsm] = items_b;
+    if (off > p.fw_cap) {
+      atomicExch(p.error_flag, WB_ERR_UNSUPPORTED);
+    } else {
+      p_in.smooth_hdr[0] = nsm; p_in.smooth_hdr[1] = items; p_in.smooth_hdr[2] = items_b;
+    }
   }
-  __syncthreads();
-  if (s_i[3]) {
-    if (tid == 0) atomicExch(p.error_flag, WB_ERR_UNSUPPORTED);
-    return;
-  }
-  const double b0 = 0.0078202080334971724, b1 = 0.015640416066994345;
-  const double a0 = 1.7347257688092754, a1 = -0.76600660094326412;
-  // impulse response of 1 / (1 - a0 z^-1 - a1 z^-2) for the look-ahead form of the warm-up
-  const double h1 = a0, h2 = a0 * a0 + a1, h3 = a0 * h2 + a1 * h1, h4 = a0 * h3 + a1 * h2;
-  const int n_items = s_i[2];
-  const bool fw_in_smem = s_i[5] != 0;
   TL_STAMP();  // 8: smoothing set-up
-  // forward pass (harvest.cpp:649-654)
-  for (int item = tid; item < n_items; item += nt) {
-    int lo = 0, hi = nsm - 1;
-    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (p.sec_lo[mid] <= item) lo = mid; else hi = mid - 1; }
-    const int s = lo;
-    const int st = p.sec_st[s], ed = p.sec_ed[s], flen = p.sec_len[s];
-    const int c = item - p.sec_lo[s];
-    const int begin = st + c * TL_CHUNK, end = min(st + flen, begin + TL_CHUNK);
-    double *fw = (fw_in_smem ? fw_smem : p.fw) + p.sec_off[s] - st;
-    const double x_st = pad[st], x_ed = pad[ed];
-    double w0 = 0.0, w1 = 0.0;
-    int i = max(0, begin - TL_LAG);
-    // warm-up (only the state matters): four samples per step of the dependency chain
-    for (; i + 4 <= begin; i += 4) {
-      const double x1 = (i < st) ? x_st : (i > ed ? x_ed : pad[i]);
-      const double x2 = (i + 1 < st) ? x_st : (i + 1 > ed ? x_ed : pad[i + 1]);
-      const double x3 = (i + 2 < st) ? x_st : (i + 2 > ed ? x_ed : pad[i + 2]);
-      const double x4 = (i + 3 < st) ? x_st : (i + 3 > ed ? x_ed : pad[i + 3]);
-      const double f3 = fma(h2, x1, fma(h1, x2, x3));
-      const double f4 = fma(h3, x1, fma(h2, x2, fma(h1, x3, x4)));
-      const double n1 = fma(h3, w0, fma(a1 * h2, w1, f3));
-      const double n0 = fma(h4, w0, fma(a1 * h3, w1, f4));
-      w0 = n0; w1 = n1;
-    }
-    for (; i < end; ++i) {
-      const double xi = (i < st) ? x_st : (i > ed ? x_ed : pad[i]);
-      const double wt = xi + a0 * w0 + a1 * w1;
-      if (i >= begin) fw[i] = b0 * wt + b1 * w0 + b0 * w1;
-      w1 = w0; w0 = wt;
-    }
-  }
-  __syncthreads();
-  TL_STAMP();  // 9: after forward pass
-  // backward pass (harvest.cpp:656-662): outputs on [st, ed]
-  if (tid == 0) {
-    int items = 0;
-    for (int s = 0; s < nsm; ++s) {
-      p.kb[s] = items;
-      items += (p.sec_ed[s] - p.sec_st[s] + 1 + TL_CHUNK - 1) / TL_CHUNK;
-    }
-    p.kb[nsm] = items;
-    s_i[4] = items;
-  }
-  __syncthreads();
-  const int n_items_b = s_i[4];
-  for (int item = tid; item < n_items_b; item += nt) {
-    int lo = 0, hi = nsm - 1;
-    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (p.kb[mid] <= item) lo = mid; else hi = mid - 1; }
-    const int s = lo;
-    const int st = p.sec_st[s], ed = p.sec_ed[s], flen = p.sec_len[s];
-    const int c = item - p.kb[s];
-    const int begin = st + c * TL_CHUNK, end = min(ed + 1, begin + TL_CHUNK);  // outputs [begin, end)
-    const double *fw = (fw_in_smem ? fw_smem : p.fw) + p.sec_off[s] - st;
-    const int top = min(st + flen - 1, end - 1 + TL_LAG);
-    double w0 = 0.0, w1 = 0.0;
-    int j = top;
-    for (; j - 4 >= end - 1; j -= 4) {  // warm-up above the output range, four samples per chain step
-      const double x1 = fw[j], x2 = fw[j - 1], x3 = fw[j - 2], x4 = fw[j - 3];
-      const double f3 = fma(h2, x1, fma(h1, x2, x3));
-      const double f4 = fma(h3, x1, fma(h2, x2, fma(h1, x3, x4)));
-      const double n1 = fma(h3, w0, fma(a1 * h2, w1, f3));
-      const double n0 = fma(h4, w0, fma(a1 * h3, w1, f4));
-      w0 = n0; w1 = n1;
-    }
-    for (; j >= begin; --j) {
-      const double wt = fw[j] + a0 * w0 + a1 * w1;
-      if (j < end) p.out[j - TL_LAG] = b0 * wt + b1 * w0 + b0 * w1;
-      w1 = w0; w0 = wt;
-    }
-  }
-  __syncthreads();
-  TL_STAMP();  // 10: end
 #undef TL_STAMP
+}
+
+// Butterworth coefficients of filteringF0 (harvest.cpp:639-647) and the impulse response of
+// 1 / (1 - a0 z^-1 - a1 z^-2) for the look-ahead form of the warm-up
+#define TL_B0 0.0078202080334971724
+#define TL_B1 0.015640416066994345
+#define TL_A0 1.7347257688092754
+#define TL_A1 (-0.76600660094326412)
+
+struct SmoothParams {
+  const int *hdr;          // nsm, forward items, backward items
+  const int *sec_st, *sec_ed, *sec_len, *sec_off, *first_fwd, *first_bwd;
+  const double *pad;       // padded contour, L + 2 * TL_LAG
+  double *fw;              // forward-pass outputs per section
+  double *out;             // smoothed contour, L
+};
+
+#define SM_THREADS 128
+#define SM_WARPS (SM_THREADS / 32)
+#define SM_TABLE 128   // sections whose item table is staged in shared memory
+// One WARP per work item (TL_CHUNK outputs of one section plus TL_LAG samples of warm-up): the lanes
+// fetch the item's input span with coalesced loads into shared memory, lane 0 then runs the serial
+// recurrence out of shared memory (a global load per step would cost more than the arithmetic), and the
+// warp stores the outputs.
+
+// section of work item `item`: last s with first[s] <= item
+__device__ __forceinline__ int sm_find_section(const int *first, int nsm, int item) {
+  int lo = 0, hi = nsm - 1;
+  while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (first[mid] <= item) lo = mid; else hi = mid - 1; }
+  return lo;
+}
+
+// forward pass (harvest.cpp:649-654); the warm-up before a section start sees the held first value, samples
+// after the section end the held last value (the reference's own edge padding)
+__global__ void __launch_bounds__(SM_THREADS) smooth_forward_kernel(SmoothParams p) {
+  __shared__ double s_x[SM_WARPS][TL_LAG + TL_CHUNK + 1];
+  __shared__ int s_first[SM_TABLE];
+  const int nsm = p.hdr[0], n_items = p.hdr[1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if ((int)blockIdx.x * SM_WARPS >= n_items) return;
+  const bool staged = nsm <= SM_TABLE;
+  if (staged) for (int k = threadIdx.x; k < nsm; k += SM_THREADS) s_first[k] = p.first_fwd[k];
+  __syncthreads();
+  const int *first = staged ? s_first : p.first_fwd;
+  const double b0 = TL_B0, b1 = TL_B1, a0 = TL_A0, a1 = TL_A1;
+  const double h1 = a0, h2 = a0 * a0 + a1, h3 = a0 * h2 + a1 * h1, h4 = a0 * h3 + a1 * h2;
+  const double *pad = p.pad;
+  double *x = s_x[warp];
+  for (int item = blockIdx.x * SM_WARPS + warp; item < n_items; item += gridDim.x * SM_WARPS) {
+    const int s = sm_find_section(first, nsm, item);
+    const int st = p.sec_st[s], ed = p.sec_ed[s], flen = p.sec_len[s];
+    const int c = item - first[s];
+    const int begin = st + c * TL_CHUNK, end = min(st + flen, begin + TL_CHUNK);
+    double *fw = p.fw + p.sec_off[s] - st;
+    const int i0 = max(0, begin - TL_LAG);
+    const double x_st = pad[st], x_ed = pad[ed];
+    __syncwarp();
+    for (int k = lane; k < end - i0; k += 32) {
+      const int i = i0 + k;
+      x[k] = (i < st) ? x_st : (i > ed ? x_ed : pad[i]);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      double w0 = 0.0, w1 = 0.0;
+      int i = i0;
+      // warm-up (only the state matters): four samples per step of the dependency chain
+      for (; i + 4 <= begin; i += 4) {
+        const double x1 = x[i - i0], x2 = x[i + 1 - i0], x3 = x[i + 2 - i0], x4 = x[i + 3 - i0];
+        const double f3 = fma(h2, x1, fma(h1, x2, x3));
+        const double f4 = fma(h3, x1, fma(h2, x2, fma(h1, x3, x4)));
+        const double n1 = fma(h3, w0, fma(a1 * h2, w1, f3));
+        const double n0 = fma(h4, w0, fma(a1 * h3, w1, f4));
+        w0 = n0; w1 = n1;
+      }
+      for (; i < end; ++i) {
+        const double wt = x[i - i0] + a0 * w0 + a1 * w1;
+        if (i >= begin) x[i - i0] = b0 * wt + b1 * w0 + b0 * w1;   // (the input sample is not needed again)
+        w1 = w0; w0 = wt;
+      }
+    }
+    __syncwarp();
+    for (int i = begin + lane; i < end; i += 32) fw[i] = x[i - i0];
+  }
+}
+
+// backward pass (harvest.cpp:656-662): outputs on [st, ed]
+__global__ void __launch_bounds__(SM_THREADS) smooth_backward_kernel(SmoothParams p) {
+  __shared__ double s_x[SM_WARPS][TL_LAG + TL_CHUNK + 1];
+  __shared__ int s_first[SM_TABLE];
+  const int nsm = p.hdr[0], n_items = p.hdr[2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if ((int)blockIdx.x * SM_WARPS >= n_items) return;
+  const bool staged = nsm <= SM_TABLE;
+  if (staged) for (int k = threadIdx.x; k < nsm; k += SM_THREADS) s_first[k] = p.first_bwd[k];
+  __syncthreads();
+  const int *first = staged ? s_first : p.first_bwd;
+  const double b0 = TL_B0, b1 = TL_B1, a0 = TL_A0, a1 = TL_A1;
+  const double h1 = a0, h2 = a0 * a0 + a1, h3 = a0 * h2 + a1 * h1, h4 = a0 * h3 + a1 * h2;
+  double *x = s_x[warp];
+  for (int item = blockIdx.x * SM_WARPS + warp; item < n_items; item += gridDim.x * SM_WARPS) {
+    const int s = sm_find_section(first, nsm, item);
+    const int st = p.sec_st[s], ed = p.sec_ed[s], flen = p.sec_len[s];
+    const int c = item - first[s];
+    const int begin = st + c * TL_CHUNK, end = min(ed + 1, begin + TL_CHUNK);  // outputs [begin, end)
+    const double *fw = p.fw + p.sec_off[s] - st;
+    const int top = min(st + flen - 1, end - 1 + TL_LAG);
+    __syncwarp();
+    for (int k = lane; k <= top - begin; k += 32) x[k] = fw[begin + k];
+    __syncwarp();
+    if (lane == 0) {
+      double w0 = 0.0, w1 = 0.0;
+      int j = top;
+      for (; j - 4 >= end - 1; j -= 4) {  // warm-up above the output range, four samples per chain step
+        const double x1 = x[j - begin], x2 = x[j - 1 - begin], x3 = x[j - 2 - begin], x4 = x[j - 3 - begin];
+        const double f3 = fma(h2, x1, fma(h1, x2, x3));
+        const double f4 = fma(h3, x1, fma(h2, x2, fma(h1, x3, x4)));
+        const double n1 = fma(h3, w0, fma(a1 * h2, w1, f3));
+        const double n0 = fma(h4, w0, fma(a1 * h3, w1, f4));
+        w0 = n0; w1 = n1;
+      }
+      for (; j >= begin; --j) {
+        const double wt = x[j - begin] + a0 * w0 + a1 * w1;
+        if (j < end) x[j - begin] = b0 * wt + b1 * w0 + b0 * w1;
+        w1 = w0; w0 = wt;
+      }
+    }
+    __syncwarp();
+    for (int j = begin + lane; j < end; j += 32) p.out[j - TL_LAG] = x[j - begin];
+  }
 }
 
 // compute(): pick basic_f0 at the frame_period grid (harvest.cpp:199-204)
@@ -653,18 +719,31 @@ int wb_harvest_tail(WbWorkspace *ws, const double *d_cand, const double *d_score
   p.fw = (double *)ws->get("tl_fw", sizeof(double) * p.fw_cap);
   p.error_flag = ws->error_flag();
   p.clocks = (long long *)ws->get("tl_clocks", sizeof(long long) * 16);
+  p.smooth_hdr = (int *)ws->get("tl_smooth_hdr", sizeof(int) * 4);
   p.gA = (double *)ws->get("tl_ga", sizeof(double) * (L + 2 * TL_LAG));
   p.gB = (double *)ws->get("tl_gb", sizeof(double) * (L + 2 * TL_LAG));
   if (!p.gA || !p.gB) return WB_ERR_CUDA;
-  if (!p.secbuf || !p.pad || !p.fw || !p.error_flag || !p.clocks) return WB_ERR_CUDA;
+  if (!p.secbuf || !p.pad || !p.fw || !p.error_flag || !p.clocks || !p.smooth_hdr) return WB_ERR_CUDA;
   WB_LAUNCH("search_base_kernel", search_base_kernel<<<(L * 32 + 255) / 256, 256, 0, stream>>>(d_cand, d_score, d_nc, L, MC, p.base));
   // shared memory: the two contour buffers (+ forward-filter scratch) when they fit (10 s at 1 ms: 2 x 85 KB)
-  const int want = 2 * (L + 2 * TL_LAG) + 16 * TL_LAG;
-  p.smem_doubles = want < 25600 ? want : (2 * (L + 2 * TL_LAG) <= 25600 ? 25600 : 0);
+  const int want = 2 * (L + 2 * TL_LAG);
+  p.smem_doubles = want <= 25600 ? want : 0;
   const size_t tl_smem_bytes = sizeof(double) * (size_t)p.smem_doubles;
   WB_CUDA_CHECK(cudaFuncSetAttribute(harvest_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl_smem_bytes));
   WB_LAUNCH("harvest_tail_kernel", harvest_tail_kernel<<<1, TL_THREADS, tl_smem_bytes, stream>>>(p));
   WB_CUDA_CHECK(cudaGetLastError());
+  {
+    SmoothParams q;
+    q.hdr = p.smooth_hdr; q.sec_st = p.sec_st; q.sec_ed = p.sec_ed; q.sec_len = p.sec_len; q.sec_off = p.sec_off;
+    q.first_fwd = p.sec_lo; q.first_bwd = p.kb; q.pad = p.pad; q.fw = p.fw; q.out = p.out;
+    // work items (TL_CHUNK outputs each) are bounded by the padded length plus one partial chunk and one
+    // lag of forward outputs per section; the kernels stride over the actual count
+    const long long max_items = ((long long)L + 2 * TL_LAG + (long long)TL_LAG * p.maxsec) / TL_CHUNK + p.maxsec + 1;
+    const int grid = (int)std::min<long long>((max_items + SM_WARPS - 1) / SM_WARPS, 148 * 8);
+    WB_LAUNCH("smooth_forward_kernel", smooth_forward_kernel<<<grid, SM_THREADS, 0, stream>>>(q));
+    WB_LAUNCH("smooth_backward_kernel", smooth_backward_kernel<<<grid, SM_THREADS, 0, stream>>>(q));
+    WB_CUDA_CHECK(cudaGetLastError());
+  }
   return WB_OK;
 }
 
