@@ -128,6 +128,9 @@ def main():
     if args.impl == "reference":
         return run_reference_arm(args)
 
+    # one JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION prints to stdout) out of it
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
@@ -317,7 +320,7 @@ def main():
     # ---- extra (not the headline): BASELINE configs[2]-style batch, independent 22.05 kHz / 5 s utterances on
     # concurrent streams of this GPU (each utterance == one reference process)
     batch_extra = None
-    if rank == 0:
+    if rank == 0 and world == 1:
         try:
             n_utt, bfs, bsec = 32, 22050, 5.0
             bxs = [torch.from_numpy(signals.synth_speech(bfs, bsec, seed=1000 + i)).cuda() for i in range(n_utt)]
@@ -343,7 +346,7 @@ def main():
 
     # ---- CPU baseline: the reference's OpenMP build on this host, bounded sample
     cpu_baseline = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:   # (N = 1 only, as the contract says)
         res = cpu_reference_run(x_host, repeat=3, omp=True)
         if res is not None:
             ms = float(np.median(res["ms"]))

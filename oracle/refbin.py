@@ -46,7 +46,11 @@ def run_reference(x, fs, stages="hcds", f0=None, frame_period=5.0, harvest_f0_fl
             cmd += ["--f0-in", f0in]
         if taskset is not None:
             cmd = ["taskset", "-c", str(taskset)] + cmd
-        r = subprocess.run(cmd, capture_output=True, text=True)
+        env = dict(os.environ)
+        if omp:
+            # the OpenMP baseline uses every host thread (torchrun pins OMP_NUM_THREADS=1 for its workers)
+            env.pop("OMP_NUM_THREADS", None)
+        r = subprocess.run(cmd, capture_output=True, text=True, env=env)
         if r.returncode != 0:
             raise RuntimeError("refrun failed (%d): %s" % (r.returncode, r.stderr[-2000:]))
         timings = [json.loads(line) for line in r.stdout.splitlines() if line.startswith("{")]
