@@ -31,7 +31,8 @@ __device__ __forceinline__ int d4c_half_window(double ratio, int fs, double f0) 
 template <typename At, typename Win>
 __device__ inline int d4c_windowed_waveform(const double *__restrict__ x, int x_length, int fs, double f0,
                                             double position_s, int window_type, double ratio,
-                                            const double *__restrict__ noise, Win win, double *red, At at) {
+                                            const double *__restrict__ noise, Win win, double *red, At at,
+                                            const double *rot = nullptr) {
   const int hw = d4c_half_window(ratio, fs, f0);
   const int wlen = 2 * hw + 1;
   const int origin = wb_round(position_s * fs + 0.001);
@@ -40,9 +41,14 @@ __device__ inline int d4c_windowed_waveform(const double *__restrict__ x, int x_
   // The window angle c2 * c1 * (j - hw) is linear in j: one sincos at the thread's first sample (the
   // reference's expression), then a rotation by blockDim samples per step (<= 32 steps, ~1e-15 drift);
   // cos(2t) = 2 cos(t)^2 - 1 for the Blackman term (d4c.cpp:266-283).
+  // (`rot`: the four rotation constants, if the caller already has them for this f0 and ratio)
   double sd, cd, sn, cs;
-  sincos(c2 * c1 * blockDim.x, &sd, &cd);
-  sincos(c2 * (c1 * ((int)threadIdx.x - hw)), &sn, &cs);
+  if (rot) {
+    sd = rot[0]; cd = rot[1]; sn = rot[2]; cs = rot[3];
+  } else {
+    sincos(c2 * c1 * blockDim.x, &sd, &cd);
+    sincos(c2 * (c1 * ((int)threadIdx.x - hw)), &sn, &cs);
+  }
   double s1 = 0.0, s2 = 0.0;
   for (int j = threadIdx.x; j < wlen; j += blockDim.x) {
     double w;
@@ -492,9 +498,11 @@ __global__ void __launch_bounds__(D4C_BODY_THREADS, 2) d4c_body_kernel(BodyParam
 
   // ---- smoothed power spectrum (d4c.cpp:411-434)
   {
+    const double rot[4] = {rot_sd, rot_cd, rot_sn, rot_cs};
     const int wlen = d4c_windowed_waveform(p.x, p.x_length, fs, f0, pos, D4C_HANNING, 4.0, noise,
                                            [&](int j) -> double & { return win_hi[j]; }, red,
-                                           [&](int j) -> double & { return W[wb_didx(j)]; });
+                                           [&](int j) -> double & { return W[wb_didx(j)]; },
+                                           (N == 16 * D4C_BODY_THREADS) ? rot : nullptr);
     for (int j = wlen + tid; j < N; j += nt) W[wb_didx(j)] = 0.0;
     __syncthreads();
     wb_rfft_t<1, LOG2N - 1, 16>(S, p.tw_n, [&](int k, cplx X) { SP[k] = X.x * X.x + X.y * X.y; });

@@ -496,9 +496,11 @@ __global__ void __launch_bounds__(IV_THREADS) interval_kernel(IntervalParams p) 
     // the consumer exactly like harvest.cpp:1113-1117)
     if (lane > 0 && k >= 1 && k < ni && ni > 2) {
       const int i_lo = (k > 1) ? f0 : 0;
-      const double dx = x1 - x0, dy = y1 - y0;
+      // interp1 divides by the knot distance for every frame (world_matlabfunctions.cpp:168-176); it is a loop
+      // invariant here, so its reciprocal is formed once (the quotient can differ in the last bit)
+      const double inv_dx = 1.0 / (x1 - x0), dy = y1 - y0;
       for (int i = i_lo; i < f1; ++i) {
-        const double s = (t_tab[i] - x0) / dx;
+        const double s = (t_tab[i] - x0) * inv_dx;
         out[iv_contour_index(ct, n_ct, i)] = y0 + s * dy;
       }
     }

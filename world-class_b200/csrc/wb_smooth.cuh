@@ -39,30 +39,39 @@ __device__ inline bool wb_linear_smoothing(const double *in, double *out, double
   const int boundary = static_cast<int>(width * fft_size / fs) + 1;
   const int len = nc + boundary * 2 + 1;
   if (len > seg_capacity) return false;
+  // fft_size is a power of two: multiplying by its reciprocal is exact, i.e. bit-identical to the division
+  const double inv_fft = 1.0 / fft_size;
   // mirroring_spectrum[i] * fs / fft_size  (world_common.cpp:32-47)
   for (int i = threadIdx.x; i < len; i += blockDim.x) {
     double v;
     if (i < boundary) v = in[boundary - i];
     else if (i < nc + boundary) v = in[i - boundary];
     else v = in[nc - (i - (nc + boundary))];
-    seg[i] = v * fs / fft_size;
+    seg[i] = v * fs * inv_fft;
   }
   __syncthreads();
   wb_block_inclusive_scan(seg, len, red);  // mirroring_segment
   const double origin = -(boundary - 0.5) * fs / fft_size;
-  const double interval = static_cast<double>(fs) / fft_size;
+  // interp1Q (world_matlabfunctions.cpp:220-241) divides by the knot interval fs / fft_size and the result by
+  // the width; both are loop invariants here, so their reciprocals are formed once.  The quotients can
+  // differ from the reference's in the last bit; the interpolant is continuous across the knot index, so
+  // even a flipped truncation only moves the result by an ulp.
+  const double inv_interval = static_cast<double>(fft_size) / fs;
+  const double inv_width = 1.0 / width;
   for (int i = threadIdx.x; i <= nc; i += blockDim.x) {
-    double fa = static_cast<double>(i) / fft_size * fs - width / 2.0;
-    int base = static_cast<int>((fa - origin) / interval);
-    double frac = (fa - origin) / interval - base;
+    double fa = static_cast<double>(i) * inv_fft * fs - width / 2.0;
+    double q = (fa - origin) * inv_interval;
+    int base = static_cast<int>(q);
+    double frac = q - base;
     double dy = (base >= len - 1) ? 0.0 : seg[base + 1] - seg[base];
     const double low = seg[base] + dy * frac;
     fa += width;
-    base = static_cast<int>((fa - origin) / interval);
-    frac = (fa - origin) / interval - base;
+    q = (fa - origin) * inv_interval;
+    base = static_cast<int>(q);
+    frac = q - base;
     dy = (base >= len - 1) ? 0.0 : seg[base + 1] - seg[base];
     const double high = seg[base] + dy * frac;
-    out[i] = (high - low) / width;
+    out[i] = (high - low) * inv_width;
   }
   __syncthreads();
   return true;
