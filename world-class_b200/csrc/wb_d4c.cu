@@ -168,16 +168,16 @@ __global__ void __launch_bounds__(256) lt_frame_kernel(LtParams p) {
 //    and collects the bucket's keys, and a single warp ranks them.
 // get(i, w) -> value i of array w.  hist: 2 << BITS ints; ctl: SEL_CTL_WORDS + 2 * SEL_LIST words.
 #define SEL_LIST 32
-#define SEL_CTL_WORDS 20
+#define SEL_CTL_WORDS (12 + D4C_BODY_THREADS / 32)
 template <int BITS, typename Get>
 __device__ inline void d4c_sum_smallest2(Get get, int n, int m, bool has_second, unsigned long long and_a,
                                          unsigned long long or_a, unsigned long long and_b, unsigned long long or_b,
                                          int *hist, unsigned long long *ctl, double *red, double &low_a, double &low_b) {
   constexpr int BINS = 1 << BITS;
-  constexpr int PER = BINS / D4C_BODY_THREADS;  // bins per thread in the scan
-  static_assert(PER >= 1, "histogram smaller than the block");
+  constexpr int PER = BINS >= D4C_BODY_THREADS ? BINS / D4C_BODY_THREADS : 1;  // bins per thread in the scan
+  constexpr int NW = D4C_BODY_THREADS / 32;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
-  int *s_wtot = reinterpret_cast<int *>(ctl + 12);  // 2 x 8 warp totals of the bucket scan (8 words)
+  int *s_wtot = reinterpret_cast<int *>(ctl + 12);  // 2 x NW warp totals of the bucket scan (NW words)
   unsigned long long *list = ctl + SEL_CTL_WORDS;    // 2 x SEL_LIST keys
   // ---- common leading bits of each array
   {
@@ -242,28 +242,28 @@ __device__ inline void d4c_sum_smallest2(Get get, int n, int m, bool has_second,
 #pragma unroll
     for (int w = 0; w < 2; ++w) {
 #pragma unroll
-      for (int q = 0; q < PER; ++q) c[w] += hist[w * BINS + tid * PER + q];
+      for (int q = 0; q < PER; ++q) c[w] += (tid * PER + q < BINS) ? hist[w * BINS + tid * PER + q] : 0;
       incl[w] = c[w];
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const int t = __shfl_up_sync(0xffffffffu, incl[w], o);
         if (lane >= o) incl[w] += t;
       }
-      if (lane == 31) s_wtot[w * 8 + warp] = incl[w];
+      if (lane == 31) s_wtot[w * NW + warp] = incl[w];
     }
     __syncthreads();
 #pragma unroll
     for (int w = 0; w < 2; ++w) {
       if (done[w] || listed[w]) continue;
       int before = 0;
-      for (int q = 0; q < warp; ++q) before += s_wtot[w * 8 + q];
+      for (int q = 0; q < warp; ++q) before += s_wtot[w * NW + q];
       const int excl = before + incl[w] - c[w];
       unsigned long long *c4 = ctl + w * 4;
       const int remaining = (int)c4[1];
       if (remaining > excl && remaining <= excl + c[w]) {
         int r = remaining - excl;
         int d = tid * PER, hcount = 0;
-        for (int q = 0; q < PER; ++q) {
+        for (int q = 0; q < PER && tid * PER + q < BINS; ++q) {
           const int hv = hist[w * BINS + tid * PER + q];
           if (r <= hv) { d = tid * PER + q; hcount = hv; break; }
           r -= hv;

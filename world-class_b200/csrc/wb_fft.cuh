@@ -141,17 +141,28 @@ __device__ __forceinline__ void wb_twiddles8(const cplx *__restrict__ T, int t1,
   w[7] = wb_cmul(w[3], w[4]);
 }
 
+// `in(i, q)` of a DIF pass supplies element i of the input (q = its position inside the butterfly, a
+// compile-time constant after unrolling, so the functor may index per-thread register arrays with it): the
+// default reads the slots, a caller-provided functor fuses the producer of the data into the first pass
+// (no store + reload of the input, and zero padding costs nothing).
+struct WbFromSlots {};
+
 // ---- one DIF pass over sub-blocks of size M (radix 8), in place; table has 2N entries -------
-template <int SIGN, int N, int M>
-__device__ __forceinline__ void wb_pass_dif8(cplx *s, const cplx *__restrict__ T) {
+template <int SIGN, int N, int M, typename In = WbFromSlots>
+__device__ __forceinline__ void wb_pass_dif8(cplx *s, const cplx *__restrict__ T, In in = In()) {
   constexpr int m8 = M / 8, tstep = 2 * N / M;
   for (int u = threadIdx.x; u < N / 8; u += blockDim.x) {
     const int j = u & (m8 - 1);
     const int base = ((u - j) << 3) + j;  // (u / m8) * M + j
     cplx *sp = s + wb_sidx(base);
     cplx a[8];
+    if constexpr (std::is_same<In, WbFromSlots>::value) {
 #pragma unroll
-    for (int q = 0; q < 8; ++q) a[q] = sp[WB_OFF(q, m8)];
+      for (int q = 0; q < 8; ++q) a[q] = sp[WB_OFF(q, m8)];
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) a[q] = in(base + q * m8, q);
+    }
     wb_dft8<SIGN>(a);
     if (m8 > 1) {
       cplx w[8];
@@ -192,12 +203,7 @@ __device__ __forceinline__ void wb_apply_twiddles16(const cplx *__restrict__ T, 
 
 __device__ __forceinline__ constexpr int wb_brev4c(int q) { return ((q & 1) << 3) | ((q & 2) << 1) | ((q & 4) >> 1) | ((q & 8) >> 3); }
 
-// ---- radix-16 DIF pass over sub-blocks of size M, in place.  `in(i, q)` supplies element i of the input
-// (q = 0..15 is its position inside the butterfly, a compile-time constant after unrolling, so the functor
-// may index per-thread register arrays with it): the default reads the slots, a caller-provided functor
-// fuses the producer of the data into the first pass (no store + reload of the input, and zero padding
-// costs nothing).
-struct WbFromSlots {};
+// ---- radix-16 DIF pass over sub-blocks of size M, in place (input functor: see WbFromSlots)
 template <int SIGN, int N, int M, typename In>
 __device__ __forceinline__ void wb_pass_dif16(cplx *s, const cplx *__restrict__ T, In in) {
   constexpr int m = M / 16, tstep = 2 * N / M;
@@ -323,9 +329,9 @@ struct WbDifPasses {
       __syncthreads();
       WbDifPasses<SIGN, N, M / 16, R>::run(s, T, WbFromSlots());
     } else {
-      static_assert(std::is_same<In, WbFromSlots>::value, "fused input needs the radix-16 plan and N >= 16");
+      static_assert(M >= 8 || std::is_same<In, WbFromSlots>::value, "fused input needs N >= 8");
       if constexpr (M >= 8) {
-        wb_pass_dif8<SIGN, N, M>(s, T);
+        wb_pass_dif8<SIGN, N, M>(s, T, in);
         __syncthreads();
         WbDifPasses<SIGN, N, M / 8, R>::run(s, T, WbFromSlots());
       } else if constexpr (M == 4) {
@@ -366,9 +372,9 @@ __device__ __forceinline__ void wb_cfft_dif_t(cplx *s, const cplx *__restrict__ 
 
 // Radix-16 plan with element i of the input coming from in(i, q) instead of the slots (LOG2N >= 4).  The slots
 // are only written: the caller must make sure nobody still reads them (a __syncthreads() after their last use).
-template <int SIGN, int LOG2N, typename In>
+template <int SIGN, int LOG2N, int R = 16, typename In>
 __device__ __forceinline__ void wb_cfft_dif_in_t(cplx *s, const cplx *__restrict__ T, In in) {
-  WbDifPasses<SIGN, (1 << LOG2N), (1 << LOG2N), 16>::run(s, T, in);
+  WbDifPasses<SIGN, (1 << LOG2N), (1 << LOG2N), R>::run(s, T, in);
 }
 
 // bit-reversed order in, natural order out.  Ends with __syncthreads().

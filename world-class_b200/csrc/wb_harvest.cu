@@ -762,8 +762,13 @@ __global__ void remove_kernel(const double *__restrict__ cand_in, const double *
   if (g >= (long long)f0_length * max_candidates) return;
   const int i = (int)(g / max_candidates), j = (int)(g % max_candidates);
   const int nc7 = *nc_ptr * 7;
+  if (j >= nc7) {  // beyond the populated slots: nothing was ever stored there
+    cand_out[g] = 0.0;
+    score_out[g] = 0.0;
+    return;
+  }
   double c = cand_in[g], s = score_in[g];
-  if (i >= 1 && i < f0_length - 1 && j < nc7 && c != 0) {
+  if (i >= 1 && i < f0_length - 1 && c != 0) {
     const double reference_f0 = c;
     double err[2];
 #pragma unroll
@@ -832,6 +837,12 @@ int wb_harvest_plan_init(WbHarvestPlan *pl, int fs, const WbHarvestOptionInterna
   pl->V = pl->NB - 2 - 2 * h_max;
   if (r > 1 && !decimate_coefficients(r, (DecimCoef *)pl->decim_coef)) return WB_ERR_UNSUPPORTED;
   pl->filters_ready = false;
+  if (!pl->aux_stream) {
+    if (cudaStreamCreateWithFlags(&pl->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&pl->aux_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&pl->aux_join, cudaEventDisableTiming) != cudaSuccess)
+      return WB_ERR_CUDA;
+  }
   return WB_OK;
 }
 
@@ -871,6 +882,20 @@ int wb_harvest_run_basic(WbHarvestPlan *pl, WbWorkspace *ws, const double *d_x, 
   const int Lb = static_cast<int>(1000.0 * x_length / fs / frame_period) + 1;            // harvest.cpp:173-176
   *f0_length_out = Lb;
   const int nch = pl->nch, MC = pl->max_candidates, own_cap = MC / 7;
+
+  // ---- clears of the candidate tables: nothing before the candidate stage touches them, so they run on
+  // the auxiliary stream beside the chain
+  {
+    int *d_nc0 = (int *)ws->get("hv_nc", 16);
+    double *d_candA0 = (double *)ws->get("hv_candA", sizeof(double) * (size_t)Lb * MC * 2);
+    if (!d_nc0 || !d_candA0) return WB_ERR_CUDA;
+    cudaStream_t aux = wb_prof_is_enabled() ? stream : pl->aux_stream;
+    WB_CUDA_CHECK(cudaEventRecord(pl->aux_fork, stream));
+    WB_CUDA_CHECK(cudaStreamWaitEvent(aux, pl->aux_fork, 0));
+    WB_CUDA_CHECK(cudaMemsetAsync(d_nc0, 0, 16, aux));  // [0] = nc, [1] = number of own candidates
+    WB_CUDA_CHECK(cudaMemsetAsync(d_candA0, 0, sizeof(double) * (size_t)Lb * MC * 2, aux));
+    WB_CUDA_CHECK(cudaEventRecord(pl->aux_join, aux));
+  }
 
   // ---- H1/H2: decimated, DC-"corrected" waveform
   double *d_y = (double *)ws->get("hv_y", sizeof(double) * (y_length + 8));
@@ -967,8 +992,7 @@ int wb_harvest_run_basic(WbHarvestPlan *pl, WbWorkspace *ws, const double *d_x, 
   if (!d_raw || !d_own || !d_nc || !d_work || !d_candA || !d_candB || !d_scoreB) return WB_ERR_CUDA;
   double *d_scoreA = d_candA + (size_t)Lb * MC;
   if (own_cap > 32) return WB_ERR_UNSUPPORTED;
-  WB_CUDA_CHECK(cudaMemsetAsync(d_nc, 0, 16, stream));  // [0] = nc, [1] = number of own candidates
-  WB_CUDA_CHECK(cudaMemsetAsync(d_candA, 0, sizeof(double) * (size_t)Lb * MC * 2, stream));
+  WB_CUDA_CHECK(cudaStreamWaitEvent(stream, pl->aux_join, 0));   // the table clears issued at the top
   {
     CandParams p;
     p.contour = d_contour; p.ecount = d_ecount; p.boundary_f0 = (const double *)ws->get("hv_bf", 0);

@@ -24,6 +24,17 @@ struct WbHarvestPlan {
   // frame-time table of the interval stage (valid for this length / period / buffer)
   int ttab_len = 0, ttab_period = 0;
   const void *ttab_ptr = nullptr;
+  // auxiliary stream: table clears that nothing before the candidate stage depends on run beside the chain
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
+  WbHarvestPlan() = default;
+  WbHarvestPlan(const WbHarvestPlan &) = delete;
+  WbHarvestPlan &operator=(const WbHarvestPlan &) = delete;
+  ~WbHarvestPlan() {
+    if (aux_fork) cudaEventDestroy(aux_fork);
+    if (aux_join) cudaEventDestroy(aux_join);
+    if (aux_stream) cudaStreamDestroy(aux_stream);
+  }
 };
 
 int wb_harvest_plan_init(WbHarvestPlan *pl, int fs, const WbHarvestOptionInternal &opt);
