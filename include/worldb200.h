@@ -146,6 +146,16 @@ int wb_decode_spectral_envelope(const double *const *coded_spectral_envelope, in
 int wb_codec_dev(int kind, const double *d_in, int f0_length, int fs, int fft_size, int number_of_dimensions,
                  double *d_out, void *stream);
 
+/* ---- parameter modification between analysis and synthesis (test/test.cpp:201-243) --------------
+ * F0 scaling (f0[i] *= f0_shift; pass NaN to leave F0 alone) and spectral stretching by `ratio` (each row:
+ * log, interp1 from the axis ratio*i/fft_size*fs to i/fft_size*fs, exp; for ratio < 1 the bins from
+ * int(fft_size/2*ratio) on repeat the bin before them; pass ratio <= 0 to leave the spectrogram alone).
+ * In place, like the reference demo.  *_dev: contiguous DEVICE arrays, asynchronous on `stream`. */
+int wb_parameter_modification(double *f0, int f0_length, double **spectrogram, int fs, int fft_size,
+                              double f0_shift, double ratio);
+int wb_parameter_modification_dev(double *d_f0, int f0_length, double *d_spectrogram, int fs, int fft_size,
+                                  double f0_shift, double ratio, void *stream);
+
 /* ---- whole chain, device resident -----------------------------------------------------
  * The call sequence of test/test.cpp:288-384 (Harvest -> CheapTrick -> D4C -> Synthesis) with
  * every intermediate kept in HBM.  NULL option pointers = defaults; NULL output pointers in
@@ -159,6 +169,9 @@ int wb_pipeline_set_fresh_rng(wb_pipeline_t *p, int fresh);
 /* use_graph != 0: repeated wb_pipeline_run_dev calls with identical arguments replay a captured CUDA
  * graph (one launch for the whole chain).  The internal buffers are used unless all outputs are given. */
 int wb_pipeline_set_graph(wb_pipeline_t *p, int use_graph);
+/* apply the parameter modification above between analysis and synthesis (the demo's call order,
+ * test/test.cpp:318-332): the returned f0 / spectrogram are the modified ones.  NaN / <= 0 switch a part off. */
+int wb_pipeline_set_modification(wb_pipeline_t *p, double f0_shift, double ratio);
 int wb_pipeline_fft_size(const wb_pipeline_t *p);
 int wb_pipeline_f0_length(const wb_pipeline_t *p, int x_length);      /* src/harvest.cpp:173-181 */
 int wb_pipeline_out_length(const wb_pipeline_t *p, int x_length);     /* test/test.cpp:362-363 */

@@ -14,6 +14,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 REFRUN = os.path.join(HERE, "_ref", "refrun")
 REFRUN_OMP = os.path.join(HERE, "_ref", "refrun_omp")
+REFMOD = os.path.join(HERE, "_ref", "refmod")
 
 
 def available(omp=False):
@@ -66,3 +67,24 @@ def run_reference(x, fs, stages="hcds", f0=None, frame_period=5.0, harvest_f0_fl
                     out[name] = np.fromfile(p, dtype=np.float64).reshape(shape)
             out["fft_size"] = info["fft_size"]
         return out, timings
+
+
+def run_modification(f0, sp, fs, fft_size, shift=None, ratio=None):
+    """The reference demo's ParameterModification (test/test.cpp:201-243) through oracle/_ref/refmod.
+    shift / ratio = None leaves the argument off the demo's command line.  Returns (f0, sp)."""
+    if not os.path.exists(REFMOD):
+        raise FileNotFoundError("%s missing: run `make -C oracle` where /root/reference exists" % REFMOD)
+    f0 = np.ascontiguousarray(f0, dtype=np.float64)
+    sp = np.ascontiguousarray(sp, dtype=np.float64)
+    L, bins = sp.shape
+    assert bins == fft_size // 2 + 1 and len(f0) == L
+    with tempfile.TemporaryDirectory(prefix="wbmod_") as d:
+        pf, ps, po = os.path.join(d, "f0.f64"), os.path.join(d, "sp.f64"), os.path.join(d, "o")
+        f0.tofile(pf)
+        sp.tofile(ps)
+        cmd = [REFMOD, pf, ps, str(int(fs)), str(int(fft_size)), str(L),
+               "-" if shift is None else repr(float(shift)), "-" if ratio is None else repr(float(ratio)), po]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("refmod failed (%d): %s" % (r.returncode, r.stderr[-2000:]))
+        return np.fromfile(po + ".f0", dtype=np.float64), np.fromfile(po + ".sp", dtype=np.float64).reshape(L, bins)

@@ -438,3 +438,27 @@ def decode_spectral_envelope(coded, fs, fft_size, nd):
         ms[0], ms[M + 1] = ms[1], ms[M]
         out[f] = np.exp(interp1(mel_axis, ms, fa) / M)
     return out
+
+
+# ---- the demo's parameter modification (test/test.cpp:201-243) -------------------------------------
+def parameter_modification(f0, sp, fs, fft_size, shift=None, ratio=None):
+    """F0 scaling (:205-209) and spectral stretching (:211-236): every row is log'ed, interp1'ed from the
+    axis ratio * i / fft_size * fs to the axis i / fft_size * fs (linear extrapolation beyond the last knot),
+    exp'ed, and for ratio < 1 the bins from int(fft_size / 2 * ratio) on repeat the bin before them."""
+    f0 = np.array(f0, dtype=float, copy=True)
+    sp = np.array(sp, dtype=float, copy=True)
+    if shift is not None:
+        f0 = f0 * shift
+    if ratio is None:
+        return f0, sp
+    bins = fft_size // 2 + 1
+    idx = np.arange(bins)
+    axis1 = ratio * idx / fft_size * fs
+    axis2 = idx.astype(float) / fft_size * fs
+    cut = int(fft_size / 2.0 * ratio)
+    for i in range(sp.shape[0]):
+        row = np.exp(interp1(axis1, np.log(sp[i]), axis2))
+        if ratio < 1.0:
+            row[cut:] = row[cut - 1]
+        sp[i] = row
+    return f0, sp

@@ -32,6 +32,16 @@ def main():
     ref, _ = refbin.run_reference(x, fs, stages="hcds")
     np.savez_compressed(os.path.join(HERE, "cfg2_48k_1s.npz"), x=x, fs=fs, tpos=ref["tpos"], f0=ref["f0"],
                         sp_every8=ref["sp"][::8], ap_every8=ref["ap"][::8], y=ref["y"], fft_size=ref["fft_size"])
+    # the demo's ParameterModification (test/test.cpp:201-243) through oracle/_ref/refmod on 12 frames of the
+    # 16 kHz case: F0 scaling alone, stretching up, stretching down
+    g = np.load(os.path.join(HERE, "cfg1_16k_1s.npz"))
+    sel = slice(60, 72)
+    mod = {"f0_in": g["f0"][sel], "sp_in": g["sp"][sel], "fs": 16000, "fft_size": int(g["fft_size"])}
+    for tag, (shift, ratio) in {"a": (1.5, None), "b": (0.8, 1.3), "c": (1.25, 0.7)}.items():
+        f0m, spm = refbin.run_modification(mod["f0_in"], mod["sp_in"], 16000, int(g["fft_size"]), shift, ratio)
+        mod["f0_" + tag], mod["sp_" + tag] = f0m, spm
+        mod["args_" + tag] = np.array([shift, np.nan if ratio is None else ratio])
+    np.savez_compressed(os.path.join(HERE, "mod_16k.npz"), **mod)
     # first values of the randn() stream (a tiny C program would do the same: the generator is public
     # in world_matlabfunctions.cpp:243-264); obtained here from Synthesis' noise is not possible, so
     # the stream is pinned through the waveform parity instead.

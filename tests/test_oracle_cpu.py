@@ -79,3 +79,14 @@ def test_golden_48k_voicing_matches_second_fixture():
     g = np.load(os.path.join(ROOT, "tests", "golden", "cfg2_48k_1s.npz"))
     assert int(g["fft_size"]) == 2048 and g["sp_every8"].shape[1] == 1025
     assert (g["f0"] > 0).sum() > 100
+
+
+def test_parameter_modification_restatement_matches_reference():
+    """oracle/world_np.parameter_modification vs the reference demo's own function (golden from oracle/_ref/refmod)."""
+    m = np.load(os.path.join(ROOT, "tests", "golden", "mod_16k.npz"))
+    for tag in "abc":
+        shift, ratio = m["args_" + tag]
+        f0, sp = world_np.parameter_modification(m["f0_in"], m["sp_in"], int(m["fs"]), int(m["fft_size"]), shift,
+                                                 None if np.isnan(ratio) else float(ratio))
+        assert np.array_equal(f0, m["f0_" + tag]), tag
+        assert _rel(sp, m["sp_" + tag]) < 1e-14, tag

@@ -101,6 +101,9 @@ def _declare(L):
         "wb_pipeline_destroy": (None, [vp]),
         "wb_pipeline_set_fresh_rng": (ci, [vp, ci]),
         "wb_pipeline_set_graph": (ci, [vp, ci]),
+        "wb_pipeline_set_modification": (ci, [vp, cd, cd]),
+        "wb_parameter_modification": (ci, [vp, ci, vp, ci, ci, cd, cd]),
+        "wb_parameter_modification_dev": (ci, [vp, ci, vp, ci, ci, cd, cd, vp]),
         "wb_pipeline_fft_size": (ci, [vp]),
         "wb_pipeline_f0_length": (ci, [vp, ci]),
         "wb_pipeline_out_length": (ci, [vp, ci]),
@@ -346,6 +349,19 @@ def synthesis_length(f0_length, frame_period, fs):
     return int((f0_length - 1) * frame_period / 1000.0 * fs) + 1
 
 
+# ---- parameter modification (test/test.cpp:201-243) -------------------------------------------
+def ParameterModification(f0, spectrogram, fs, fft_size, f0_shift=None, ratio=None):
+    """In place on host arrays, like the reference demo: f0 *= f0_shift, spectrogram stretched by `ratio`
+    (None = leave alone).  Returns (f0, spectrogram)."""
+    f0 = _out_array(f0, (len(f0),))
+    sp = _out_array(spectrogram, (len(f0), int(fft_size) // 2 + 1))
+    rows = _row_pointers(sp)
+    _check(lib().wb_parameter_modification(f0.ctypes.data, len(f0), rows.ctypes.data, int(fs), int(fft_size),
+                                           float("nan") if f0_shift is None else float(f0_shift),
+                                           0.0 if ratio is None else float(ratio)), "wb_parameter_modification")
+    return f0, sp
+
+
 # ---- whole chain, device resident (test/test.cpp:288-384) ------------------------------------
 class Pipeline:
     """Harvest -> CheapTrick -> D4C -> Synthesis with every intermediate kept in HBM."""
@@ -370,6 +386,13 @@ class Pipeline:
     def set_graph(self, use_graph=True):
         """Replay a captured CUDA graph for repeated run_dev calls with identical arguments."""
         _check(lib().wb_pipeline_set_graph(self._h, 1 if use_graph else 0), "wb_pipeline_set_graph")
+
+    def set_modification(self, f0_shift=None, ratio=None):
+        """Apply the demo's ParameterModification (test/test.cpp:201-243) between analysis and synthesis:
+        F0 scaling by `f0_shift`, spectral stretching by `ratio` (None = off).  The returned f0 / sp are the
+        modified ones."""
+        _check(lib().wb_pipeline_set_modification(self._h, float("nan") if f0_shift is None else float(f0_shift),
+                                                  0.0 if ratio is None else float(ratio)), "wb_pipeline_set_modification")
 
     def f0_length(self, x_length):
         return lib().wb_pipeline_f0_length(self._h, int(x_length))

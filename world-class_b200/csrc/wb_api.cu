@@ -311,6 +311,7 @@ struct wb_pipeline {
   const void *graph_key[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int graph_len[2] = {0, 0};
   int warm_len[2] = {0, 0};
+  double mod_f0_shift = NAN, mod_ratio = 0.0;   // parameter modification between analysis and synthesis (off)
   bool private_rng = false;          // batch mode: every run starts from the reference's seed
   WbRngState *d_rng_private = nullptr;
   WbRngState *d_rng_seed = nullptr;
@@ -785,6 +786,15 @@ static int pipeline_enqueue(wb_pipeline_t *p, const double *d_x, int x_length, d
 
 /* use_graph != 0: after one ordinary run with a given set of arguments, the next run with the same
  * arguments is captured into a CUDA graph and later runs replay it (one launch instead of ~45). */
+int wb_pipeline_set_modification(wb_pipeline_t *p, double f0_shift, double ratio) {
+  if (!p) return WB_ERR_ARG;
+  if (f0_shift == f0_shift && !(f0_shift > 0.0)) return WB_ERR_ARG;
+  p->mod_f0_shift = f0_shift;
+  p->mod_ratio = ratio > 0.0 ? ratio : 0.0;
+  if (p->graph_exec) { cudaGraphExecDestroy(p->graph_exec); p->graph_exec = nullptr; }   // the captured chain changes
+  return WB_OK;
+}
+
 int wb_pipeline_set_graph(wb_pipeline_t *p, int use_graph) {
   if (!p) return WB_ERR_ARG;
   p->use_graph = use_graph != 0;
@@ -865,6 +875,16 @@ static int pipeline_enqueue(wb_pipeline_t *p, const double *d_x, int x_length, d
     if ((rc = wb_harvest_run_basic(&p->plan, &p->ws, d_x, x_length, 1, d_basic, &Lb, st))) return rc;
     if ((rc = wb_harvest_pick(d_basic, Lb, fp, f0_length, d_tpos, d_f0, st))) return rc;
   }
+  // parameter modification (test/test.cpp:318-332 applies it between analysis and synthesis): the analysis
+  // stages keep the estimated f0, Synthesis gets the scaled one
+  const bool mod_f0 = p->mod_f0_shift == p->mod_f0_shift;
+  const double *d_f0_syn = d_f0;
+  if (mod_f0) {
+    double *d_mod = (double *)p->ws.get("pl_f0_mod", sizeof(double) * f0_length);
+    if (!d_mod) return WB_ERR_CUDA;
+    if ((rc = wb_parameter_modification_run(d_f0, d_mod, f0_length, nullptr, fs, p->ct.fft_size, p->mod_f0_shift, 0.0, st))) return rc;
+    d_f0_syn = d_mod;
+  }
   WbRngState *rng = wb_rng_global_state();
   if (p->private_rng) {
     rng = p->d_rng_private;
@@ -890,6 +910,9 @@ static int pipeline_enqueue(wb_pipeline_t *p, const double *d_x, int x_length, d
   if ((rc = wb_cheaptrick_run(&p->ws, fs, p->ct.fft_size, p->ct.q1, p->ct_f0_floor_internal, d_x, x_length, d_tpos,
                               d_f0, f0_length, d_sp, c_ct, st)))
     return rc;
+  if (p->mod_ratio > 0.0 &&
+      (rc = wb_parameter_modification_run(nullptr, nullptr, f0_length, d_sp, fs, p->ct.fft_size, NAN, p->mod_ratio, st)))
+    return rc;
   // D4C
   WbRngCursor c_d4c;
   c_d4c.state = rng; c_d4c.skip_in = rng_pos + 0; c_d4c.skip_out = rng_pos + 1; c_d4c.advance = false;
@@ -904,10 +927,10 @@ static int pipeline_enqueue(wb_pipeline_t *p, const double *d_x, int x_length, d
     WbRngCursor c_syn;
     c_syn.state = rng; c_syn.skip_in = rng_pos + 1; c_syn.wait_skip_in = p->ev_body_count;
     c_syn.advance = true;  // moves the state past the whole chain
-    if ((rc = wb_synthesis_timebase(&p->ws, fs, p->ct.fft_size, fp, d_f0, f0_length, y_length, s_side, &c_syn))) return rc;
+    if ((rc = wb_synthesis_timebase(&p->ws, fs, p->ct.fft_size, fp, d_f0_syn, f0_length, y_length, s_side, &c_syn))) return rc;
     WB_CUDA_CHECK(cudaEventRecord(p->ev_tb, s_side));
     // join, then part 2.  Harvest's contour is bounded by f0_ceil up to the smoothing overshoot.
-    const double f0_bound = p->plan.opt.f0_ceil * 1.25;
+    const double f0_bound = p->plan.opt.f0_ceil * 1.25 * (mod_f0 && p->mod_f0_shift > 1.0 ? p->mod_f0_shift : 1.0);
     WB_CUDA_CHECK(cudaStreamWaitEvent(st, p->ev_tb, 0));
     WB_CUDA_CHECK(cudaStreamWaitEvent(st, p->ev_d4c, 0));
     if ((rc = wb_synthesis_render(&p->ws, fs, p->ct.fft_size, fp, f0_length, d_sp, d_ap, y_length, d_y, f0_bound,
@@ -917,6 +940,9 @@ static int pipeline_enqueue(wb_pipeline_t *p, const double *d_x, int x_length, d
     WB_CUDA_CHECK(cudaStreamWaitEvent(st, p->ev_d4c, 0));
     if ((rc = wb_rng_advance(rng, rng_pos + 1, nullptr, st))) return rc;
   }
+  // the caller sees the modified f0, like the demo's world_parameters after ParameterModification (D4C, the
+  // last reader of the estimated contour, has been joined above)
+  if (mod_f0) WB_CUDA_CHECK(cudaMemcpyAsync(d_f0, d_f0_syn, sizeof(double) * f0_length, cudaMemcpyDeviceToDevice, st));
   return WB_OK;
 }
 
@@ -943,6 +969,42 @@ int wb_pipeline_run(wb_pipeline_t *p, const double *x, int x_length, double *tpo
   if (y_length > 0) WB_CUDA_CHECK(cudaMemcpyAsync(y, d_y, sizeof(double) * (size_t)y_length, cudaMemcpyDeviceToHost, st));
   WB_CUDA_CHECK(cudaStreamSynchronize(st));
   return p->ws.read_error_flag(st);
+}
+
+// ---- parameter modification (test/test.cpp:201-243) ------------------------------------------
+int wb_parameter_modification_dev(double *d_f0, int f0_length, double *d_spectrogram, int fs, int fft_size,
+                                  double f0_shift, double ratio, void *stream) {
+  int rc = ctx_init();
+  if (rc) return rc;
+  if (f0_length < 0 || fs <= 0 || fft_size < 4) return WB_ERR_ARG;
+  return wb_parameter_modification_run(d_f0, d_f0, f0_length, d_spectrogram, fs, fft_size, f0_shift, ratio,
+                                       pick_stream(stream));
+}
+
+int wb_parameter_modification(double *f0, int f0_length, double **spectrogram, int fs, int fft_size,
+                              double f0_shift, double ratio) {
+  int rc = ctx_init();
+  if (rc) return rc;
+  if (f0_length < 0 || fs <= 0 || fft_size < 4) return WB_ERR_ARG;
+  if (f0_length == 0) return WB_OK;
+  static WbWorkspace ws;   // a free function in the reference's demo: one shared workspace
+  cudaStream_t st = g_stream;
+  const int bins = fft_size / 2 + 1;
+  const bool do_f0 = f0 && f0_shift == f0_shift, do_sp = spectrogram && ratio > 0.0;
+  double *d_f0 = nullptr, *d_sp = nullptr;
+  if (do_f0 && (rc = vec_to_device(&ws, "mod_f0", f0, f0_length, &d_f0, st))) return rc;
+  if (do_sp) {
+    d_sp = (double *)ws.get("mod_sp", sizeof(double) * (size_t)f0_length * bins);
+    if (!d_sp) return WB_ERR_CUDA;
+    if ((rc = rows_to_device(&ws, "rows_stage_in", spectrogram, f0_length, bins, d_sp, st))) return rc;
+  }
+  if ((rc = wb_parameter_modification_run(d_f0, d_f0, f0_length, d_sp, fs, fft_size, do_f0 ? f0_shift : NAN,
+                                          do_sp ? ratio : 0.0, st)))
+    return rc;
+  if (do_f0) WB_CUDA_CHECK(cudaMemcpyAsync(f0, d_f0, sizeof(double) * f0_length, cudaMemcpyDeviceToHost, st));
+  if (do_sp && (rc = rows_to_host(&ws, d_sp, f0_length, bins, spectrogram, st))) return rc;
+  WB_CUDA_CHECK(cudaStreamSynchronize(st));
+  return WB_OK;
 }
 
 // ---- codec (include/codec.hpp:23-88) --------------------------------------------------------

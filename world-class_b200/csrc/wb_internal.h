@@ -79,3 +79,7 @@ int wb_code_spectral_envelope_dev(WbWorkspace *ws, const double *d_sp, int f0_le
                                   double *d_coded, cudaStream_t stream);
 int wb_decode_spectral_envelope_dev(WbWorkspace *ws, const double *d_coded, int f0_length, int fs, int fft_size,
                                     int nd, double *d_sp, cudaStream_t stream);
+
+// parameter modification (wb_modify.cu): test/test.cpp:201-243
+int wb_parameter_modification_run(const double *d_f0_in, double *d_f0_out, int f0_length, double *d_sp, int fs,
+                                  int fft_size, double f0_shift, double ratio, cudaStream_t stream);
