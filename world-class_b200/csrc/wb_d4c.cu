@@ -157,29 +157,53 @@ __global__ void __launch_bounds__(256) lt_frame_kernel(LtParams p) {
 // ---- order statistic: sum of the m smallest of v[0..n) (d4c.cpp:494-499) ----------------------
 // The reference sorts the band power spectrum and takes a cumulative sum; only
 // S[bins - boundary - 2] / S[bins - 1] is used, i.e. (sum of the m smallest) / total.  Radix select
-// on the (non-negative) double bit patterns, two arrays at once (the two bands of one paired
-// transform):
-//  * the caller hands over the AND and the OR of its keys (gathered while the keys were produced);
-//    the leading bits on which they agree are common to all keys, so the first digit starts at the
-//    first bit that actually varies;
-//  * digits are BITS wide (2^BITS counters per array): one histogram pass usually isolates a bucket
-//    with a handful of keys around the m-th smallest;
-//  * as soon as that bucket holds <= SEL_LIST keys, ONE more pass sums everything below the bucket
-//    and collects the bucket's keys, and a single warp ranks them.
-// get(i, w) -> value i of array w.  hist: 2 << BITS ints; ctl: SEL_CTL_WORDS + 2 * SEL_LIST words.
+// on the bit patterns of the (non-negative) values, two arrays at once (the two bands of one paired
+// transform).
+//  * Keys are the bit patterns minus SEL_BIAS (the pattern of 2^-255, saturating at 0): every value in
+//    [2^-255, 2^257) then has its three top key bits clear, and the bits just below them -- nine exponent
+//    bits and the leading mantissa bits -- form a first digit that does not straddle the exponent
+//    boundary at 2.0 the way the raw patterns of a power spectrum (1e-10 .. 1e7) do.
+//  * The PRODUCER of the values counts that first digit (PRE_BITS wide, packed 16-bit counters) while it
+//    computes them; if all keys are in range the select starts from the finished histogram and needs no
+//    counting pass over the data.  Otherwise, and for further digits, counting passes with BITS-wide
+//    digits start at the first key bit that actually varies (AND / OR of the keys, also gathered by
+//    the producer).
+//  * As soon as the bucket holding the m-th smallest key has <= SEL_LIST keys, ONE pass sums everything
+//    below the bucket and collects the bucket's keys, and a single warp ranks them.
+// get(i, w) -> value i of array w.  hist: 2 << BITS ints (= 2 << PRE_BITS shorts); ctl: SEL_CTL_WORDS +
+// 2 * SEL_LIST words.
 #define SEL_LIST 32
 #define SEL_CTL_WORDS (12 + D4C_BODY_THREADS / 32)
-template <int BITS, typename Get>
+#define SEL_BIAS 0x3000000000000000ull
+#define SEL_PRE_TOP 61   // the pre-counted digit ends below key bit 61
+__device__ __forceinline__ unsigned long long sel_key(double v) {
+  const unsigned long long k = (unsigned long long)__double_as_longlong(v);
+  return k > SEL_BIAS ? k - SEL_BIAS : 0ull;
+}
+__device__ __forceinline__ double sel_val(unsigned long long key) { return __longlong_as_double((long long)(key + SEL_BIAS)); }
+// producer side: count key `k` of array w (0 / 1) in the packed histogram
+template <int PRE_BITS>
+__device__ __forceinline__ void sel_precount(unsigned *hist16, int w, unsigned long long k) {
+  const int bin = (int)((k >> (SEL_PRE_TOP - PRE_BITS)) & ((1ull << PRE_BITS) - 1ull));
+  const int at = (w << PRE_BITS) + bin;
+  atomicAdd(&hist16[at >> 1], 1u << (16 * (at & 1)));
+}
+
+template <int BITS, int PRE_BITS, typename Get>
 __device__ inline void d4c_sum_smallest2(Get get, int n, int m, bool has_second, unsigned long long and_a,
                                          unsigned long long or_a, unsigned long long and_b, unsigned long long or_b,
-                                         int *hist, unsigned long long *ctl, double *red, double &low_a, double &low_b) {
+                                         bool precounted, int *hist, unsigned long long *ctl, double *red,
+                                         double &low_a, double &low_b) {
   constexpr int BINS = 1 << BITS;
   constexpr int PER = BINS >= D4C_BODY_THREADS ? BINS / D4C_BODY_THREADS : 1;  // bins per thread in the scan
+  constexpr int PRE_BINS = 1 << PRE_BITS;
+  constexpr int PRE_PER = PRE_BINS >= D4C_BODY_THREADS ? PRE_BINS / D4C_BODY_THREADS : 1;
+  constexpr int PRE_SHIFT = SEL_PRE_TOP - PRE_BITS;
   constexpr int NW = D4C_BODY_THREADS / 32;
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
   int *s_wtot = reinterpret_cast<int *>(ctl + 12);  // 2 x NW warp totals of the bucket scan (NW words)
   unsigned long long *list = ctl + SEL_CTL_WORDS;    // 2 x SEL_LIST keys
-  // ---- common leading bits of each array
+  // ---- AND / OR of the keys of each array
   {
     const unsigned full = 0xffffffffu;
     const unsigned aah = __reduce_and_sync(full, (unsigned)(and_a >> 32)), aal = __reduce_and_sync(full, (unsigned)and_a);
@@ -203,13 +227,18 @@ __device__ inline void d4c_sum_smallest2(Get get, int n, int m, bool has_second,
   int shift[2], width[2];
   bool done[2];       // threshold fully determined (= prefix)
   bool listed[2];     // bucket small enough: resolve from the collected list
+  bool counted[2];    // the first digit of this array is already in the packed histogram
 #pragma unroll
   for (int w = 0; w < 2; ++w) {
     const unsigned long long all_and = ctl[8 + 2 * w], all_or = ctl[9 + 2 * w];
     const unsigned long long diff = all_and ^ all_or;
     listed[w] = false;
+    counted[w] = false;
     if (diff == 0ull || (w == 1 && !has_second)) {  // every key identical: that key is the threshold
       prefix[w] = all_and; mask[w] = ~0ull; shift[w] = 0; width[w] = 0; done[w] = true;
+    } else if (precounted && (all_or >> SEL_PRE_TOP) == 0ull) {
+      prefix[w] = 0ull; mask[w] = ~((1ull << SEL_PRE_TOP) - 1ull);   // bits 61.. are zero in every key
+      shift[w] = PRE_SHIFT; width[w] = PRE_BITS; done[w] = false; counted[w] = true;
     } else {
       const int top = 64 - __clzll((long long)diff);  // bits [0, top) vary
       mask[w] = (top >= 64) ? 0ull : ~((1ull << top) - 1ull);
@@ -219,30 +248,13 @@ __device__ inline void d4c_sum_smallest2(Get get, int n, int m, bool has_second,
       done[w] = false;
     }
   }
-  for (int pass = 0; pass < 64; ++pass) {
-    if ((done[0] || listed[0]) && (done[1] || listed[1])) break;
-    {
-      int4 *h4 = reinterpret_cast<int4 *>(hist);
-      for (int i = tid; i < 2 * BINS / 4; i += nt) h4[i] = make_int4(0, 0, 0, 0);
-    }
-    __syncthreads();
-    for (int i = tid; i < n; i += nt) {
-#pragma unroll
-      for (int w = 0; w < 2; ++w) {
-        if (!(done[w] || listed[w])) {
-          const unsigned long long key = (unsigned long long)__double_as_longlong(get(i, w));
-          if ((key & mask[w]) == prefix[w])
-            atomicAdd(&hist[w * BINS + (int)((key >> shift[w]) & ((1ull << width[w]) - 1ull))], 1);
-        }
-      }
-    }
-    __syncthreads();
-    // bucket holding the remaining rank: block-wide scan of the counters, both arrays at once
+  // ---- bucket holding the remaining rank: block-wide scan of the counters.  count(w, bin) reads a counter.
+  auto find_bucket = [&](auto count, int per, int nbins, bool act0, bool act1) {
     int c[2] = {0, 0}, incl[2];
 #pragma unroll
     for (int w = 0; w < 2; ++w) {
-#pragma unroll
-      for (int q = 0; q < PER; ++q) c[w] += (tid * PER + q < BINS) ? hist[w * BINS + tid * PER + q] : 0;
+      if (w == 0 ? act0 : act1)
+        for (int q = 0; q < per; ++q) c[w] += (tid * per + q < nbins) ? count(w, tid * per + q) : 0;
       incl[w] = c[w];
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -254,7 +266,7 @@ __device__ inline void d4c_sum_smallest2(Get get, int n, int m, bool has_second,
     __syncthreads();
 #pragma unroll
     for (int w = 0; w < 2; ++w) {
-      if (done[w] || listed[w]) continue;
+      if (!(w == 0 ? act0 : act1)) continue;
       int before = 0;
       for (int q = 0; q < warp; ++q) before += s_wtot[w * NW + q];
       const int excl = before + incl[w] - c[w];
@@ -262,10 +274,10 @@ __device__ inline void d4c_sum_smallest2(Get get, int n, int m, bool has_second,
       const int remaining = (int)c4[1];
       if (remaining > excl && remaining <= excl + c[w]) {
         int r = remaining - excl;
-        int d = tid * PER, hcount = 0;
-        for (int q = 0; q < PER && tid * PER + q < BINS; ++q) {
-          const int hv = hist[w * BINS + tid * PER + q];
-          if (r <= hv) { d = tid * PER + q; hcount = hv; break; }
+        int d = tid * per, hcount = 0;
+        for (int q = 0; q < per && tid * per + q < nbins; ++q) {
+          const int hv = count(w, tid * per + q);
+          if (r <= hv) { d = tid * per + q; hcount = hv; break; }
           r -= hv;
         }
         c4[0] = (unsigned long long)d;
@@ -276,7 +288,7 @@ __device__ inline void d4c_sum_smallest2(Get get, int n, int m, bool has_second,
     __syncthreads();
 #pragma unroll
     for (int w = 0; w < 2; ++w) {
-      if (!(done[w] || listed[w])) {
+      if (w == 0 ? act0 : act1) {
         prefix[w] |= ctl[w * 4 + 0] << shift[w];
         mask[w] |= ((1ull << width[w]) - 1ull) << shift[w];
         if (shift[w] == 0) done[w] = true;
@@ -288,6 +300,33 @@ __device__ inline void d4c_sum_smallest2(Get get, int n, int m, bool has_second,
     }
     __syncthreads();
     if (tid == 0) { ctl[1] = ctl[2]; ctl[5] = ctl[6]; }
+  };
+  if (counted[0] || counted[1]) {
+    const unsigned *h16 = reinterpret_cast<const unsigned *>(hist);
+    find_bucket([&](int w, int bin) { const int at = (w << PRE_BITS) + bin; return (int)((h16[at >> 1] >> (16 * (at & 1))) & 0xffffu); },
+                PRE_PER, PRE_BINS, counted[0], counted[1]);
+  }
+  for (int pass = 0; pass < 64; ++pass) {
+    const bool act0 = !(done[0] || listed[0]), act1 = !(done[1] || listed[1]);
+    if (!act0 && !act1) break;
+    {
+      int4 *h4 = reinterpret_cast<int4 *>(hist);
+      for (int i = tid; i < 2 * BINS / 4; i += nt)
+        if ((i < BINS / 4) ? act0 : act1) h4[i] = make_int4(0, 0, 0, 0);
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) {
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        if (w == 0 ? act0 : act1) {
+          const unsigned long long key = sel_key(get(i, w));
+          if ((key & mask[w]) == prefix[w])
+            atomicAdd(&hist[w * BINS + (int)((key >> shift[w]) & ((1ull << width[w]) - 1ull))], 1);
+        }
+      }
+    }
+    __syncthreads();
+    find_bucket([&](int w, int bin) { return hist[w * BINS + bin]; }, PER, BINS, act0, act1);
   }
   // ---- one pass: sum / count of everything below the bucket, collect the bucket's keys
   if (tid == 0) { s_wtot[0] = 0; s_wtot[1] = 0; }
@@ -298,7 +337,7 @@ __device__ inline void d4c_sum_smallest2(Get get, int n, int m, bool has_second,
     for (int w = 0; w < 2; ++w) {
       if (w == 1 && !has_second) continue;
       const double v = get(i, w);
-      const unsigned long long key = (unsigned long long)__double_as_longlong(v);
+      const unsigned long long key = sel_key(v);
       const unsigned long long top = key & mask[w];
       if (top < prefix[w]) {
         if (w == 0) { sa += v; ca += 1.0; } else { sb += v; cb += 1.0; }
@@ -330,7 +369,7 @@ __device__ inline void d4c_sum_smallest2(Get get, int n, int m, bool has_second,
     __syncwarp();
     const unsigned long long sorted = lane < cnt ? list[w * SEL_LIST + lane] : ~0ull;
     double ls = 0.0, lc = 0.0;
-    if (lane < cnt && sorted < thr) { ls = __longlong_as_double((long long)sorted); lc = 1.0; }
+    if (lane < cnt && sorted < thr) { ls = sel_val(sorted); lc = 1.0; }
     ls = wb_warp_sum(ls);
     lc = wb_warp_sum(lc);
     if (lane == 0) {
@@ -344,9 +383,9 @@ __device__ inline void d4c_sum_smallest2(Get get, int n, int m, bool has_second,
   double t[2];
 #pragma unroll
   for (int w = 0; w < 2; ++w) {
-    t[w] = __longlong_as_double((long long)prefix[w]);
+    t[w] = sel_val(prefix[w]);
     if (listed[w]) {
-      t[w] = __longlong_as_double((long long)ctl[w * 4 + 0]);
+      t[w] = sel_val(ctl[w * 4 + 0]);
       const double ls = __longlong_as_double((long long)ctl[w * 4 + 2]), lc = __longlong_as_double((long long)ctl[w * 4 + 3]);
       if (w == 0) { sa += ls; ca += lc; } else { sb += ls; cb += lc; }
     }
@@ -534,6 +573,12 @@ __global__ void __launch_bounds__(D4C_BODY_THREADS, 2) d4c_body_kernel(BodyParam
     const bool has2 = (b + 1 < p.n_ap);
     const int center_a = static_cast<int>(WB_FREQ_INTERVAL * (b + 1) * N / fs);
     const int center_b = static_cast<int>(WB_FREQ_INTERVAL * (b + 2) * N / fs);
+    // counters of the select's first digit (SP is free by now: 2 x 2^LOG2N packed 16-bit counters); the
+    // barriers inside the transform order the clear before the counting
+    {
+      int4 *h4 = reinterpret_cast<int4 *>(SP);
+      for (int i = tid; i < N / 4; i += nt) h4[i] = make_int4(0, 0, 0, 0);
+    }
     // the windowed band slices feed the first FFT pass directly (the rest of the N points is zero padding)
     wb_cfft_dif_in_t<1, LOG2N>(S, p.tw_2n, [&](int j, int) {
       cplx z = make_double2(0.0, 0.0);
@@ -545,7 +590,8 @@ __global__ void __launch_bounds__(D4C_BODY_THREADS, 2) d4c_body_kernel(BodyParam
       return z;
     });
     double tot_a = 0.0, tot_b = 0.0;
-    unsigned long long and_a = ~0ull, or_a = 0ull, and_b = ~0ull, or_b = 0ull;  // bit patterns of the power values
+    unsigned long long and_a = ~0ull, or_a = 0ull, and_b = ~0ull, or_b = 0ull;  // select keys of the power values
+    unsigned *hist16 = reinterpret_cast<unsigned *>(SP);   // (SP is free from here on: counters of the select)
     for (int k = tid; k <= NC; k += nt) {
       const int slot = wb_sidx(wb_brev(k, log2n));
       const cplx zk = S[slot];
@@ -557,15 +603,18 @@ __global__ void __launch_bounds__(D4C_BODY_THREADS, 2) d4c_body_kernel(BodyParam
       S[slot] = make_double2(pa, pb);
       tot_a += pa;
       tot_b += pb;
-      const unsigned long long ka = (unsigned long long)__double_as_longlong(pa), kb = (unsigned long long)__double_as_longlong(pb);
+      // first digit of the order-statistic select, counted while the values are at hand
+      const unsigned long long ka = sel_key(pa), kb = sel_key(pb);
       and_a &= ka; or_a |= ka; and_b &= kb; or_b |= kb;
+      sel_precount<LOG2N>(hist16, 0, ka);
+      if (has2) sel_precount<LOG2N>(hist16, 1, kb);
     }
     wb_block_sum2(tot_a, tot_b, red);
     double low_a = 0.5 * tot_a, low_b = 0.5 * tot_b;
     if (!(p.debug_skip & 1))
-    // (SP is free from here on: it holds the 2 x 2^(LOG2N-1) counters of the select)
-    d4c_sum_smallest2<LOG2N - 1>([&](int i, int w) { const cplx v = S[wb_sidx(wb_brev(i, log2n))]; return w == 0 ? v.x : v.y; },
-                                 bins, m_small, has2, and_a, or_a, and_b, or_b, reinterpret_cast<int *>(SP), ctl, red, low_a, low_b);
+    d4c_sum_smallest2<LOG2N - 1, LOG2N>([&](int i, int w) { const cplx v = S[wb_sidx(wb_brev(i, log2n))]; return w == 0 ? v.x : v.y; },
+                                        bins, m_small, has2, and_a, or_a, and_b, or_b, true, reinterpret_cast<int *>(SP), ctl, red,
+                                        low_a, low_b);
     if (tid == 0) {
       const double rev = (f0 - 100) / 50.0;  // d4c.cpp:325-327
       double ca = 10 * log10(low_a / tot_a);
