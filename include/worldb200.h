@@ -182,8 +182,45 @@ int wb_pipeline_run(wb_pipeline_t *p, const double *x, int x_length, double *tem
                     double *f0_or_null, double *spectrogram_or_null, double *aperiodicity_or_null,
                     double *y, int y_length);
 
+/* wav in -> wav out, the demo's whole flow (test/test.cpp:288-384 between wavread, tools/audioio.cpp:228-253,
+ * and wavwrite, :121-184): HOST 16-bit PCM in both directions; the two sample-format conversions run on the
+ * device, so 2 bytes per sample cross PCIe instead of 8. */
+int wb_pipeline_run_pcm16(wb_pipeline_t *p, const short *pcm_in, int x_length, short *pcm_out, int y_length);
+/* like wb_pipeline_run with HOST outputs narrowed to fp32 on the device (contiguous matrices; NULL = not
+ * wanted).  The arithmetic is fp64 throughout; only the delivered arrays are rounded (to nearest). */
+int wb_pipeline_run_f32(wb_pipeline_t *p, const double *x, int x_length, float *f0_or_null, float *spectrogram_or_null,
+                        float *aperiodicity_or_null, float *y, int y_length);
+
 /* test / bench hook: copies n_bytes of a named internal device buffer of the last run to `out` */
 int wb_pipeline_debug_read(wb_pipeline_t *p, const char *name, void *out, unsigned long long n_bytes);
+
+/* ---- data formats either side of the path (N2, N3) --------------------------------
+ * Sample formats of the reference's wav reader / writer as DEVICE conversions, asynchronous on `stream`:
+ * x = pcm / 32768 (tools/audioio.cpp:232-249 at 16 bit), pcm = clamp(trunc(x * 32767)) (:176-180). */
+int wb_pcm16_to_f64_dev(const short *d_pcm, int n, double *d_x, void *stream);
+int wb_f64_to_pcm16_dev(const double *d_x, int n, short *d_pcm, void *stream);
+int wb_f64_to_f32_dev(const double *d_in, unsigned long long n, float *d_out, void *stream);
+/* The reference's parameter files (tools/parameterio.hpp:24-117, tools/parameterio.cpp:60-244), byte-compatible
+ * both ways; same argument meaning, but failures are status codes instead of a printf.  HOST code. */
+int wb_write_f0(const char *filename, int f0_length, double frame_period, const double *temporal_positions,
+                const double *f0, int text_flag);                                   /* parameterio.cpp:60-90 */
+int wb_read_f0(const char *filename, double *temporal_positions, double *f0);       /* :92-119 */
+double wb_get_header_information(const char *filename, const char *parameter);      /* :121-147 */
+int wb_write_spectral_envelope(const char *filename, int fs, int f0_length, double frame_period, int fft_size,
+                               int number_of_dimensions, const double *const *spectrogram);   /* :149-177 */
+int wb_read_spectral_envelope(const char *filename, double **spectrogram);          /* :179-199 */
+int wb_write_aperiodicity(const char *filename, int fs, int f0_length, double frame_period, int fft_size,
+                          int number_of_dimensions, const double *const *aperiodicity);       /* :201-223 */
+int wb_read_aperiodicity(const char *filename, double **aperiodicity);              /* :225-244 */
+/* the same containers from / to one contiguous matrix (kind 0 = "SPEC", 1 = "AP  "; row_stride in doubles) */
+int wb_write_parameter_matrix(int kind, const char *filename, int fs, int f0_length, double frame_period,
+                              int fft_size, int number_of_dimensions, const double *matrix, long long row_stride);
+int wb_read_parameter_matrix(int kind, const char *filename, double *matrix, long long row_stride);
+/* The reference's RIFF reader / writer (tools/audioio.hpp, tools/audioio.cpp): mono PCM only */
+int wb_wavwrite(const double *x, int x_length, int fs, int nbit, const char *filename);  /* audioio.cpp:121-184 */
+int wb_get_audio_length(const char *filename);        /* :186-226; 0 = cannot open, -1 = header not accepted */
+int wb_wavread(const char *filename, int *fs, int *nbit, double *x);                      /* :228-253 */
+int wb_wavread_pcm16(const char *filename, int *fs, short *pcm);  /* the raw 16-bit samples (for *_pcm16) */
 
 /* ---- measurement hooks (bench.py) ------------------------------------------------------ */
 unsigned long long wb_launch_count(void);  /* kernels launched by this library so far */

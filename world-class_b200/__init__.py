@@ -110,6 +110,24 @@ def _declare(L):
         "wb_pipeline_run_dev": (ci, [vp, vp, ci, vp, vp, vp, vp, vp, ci, vp]),
         "wb_pipeline_run": (ci, [vp, vp, ci, vp, vp, vp, vp, vp, ci]),
         "wb_pipeline_debug_read": (ci, [vp, ctypes.c_char_p, vp, ctypes.c_ulonglong]),
+        "wb_pipeline_run_pcm16": (ci, [vp, vp, ci, vp, ci]),
+        "wb_pipeline_run_f32": (ci, [vp, vp, ci, vp, vp, vp, vp, ci]),
+        "wb_pcm16_to_f64_dev": (ci, [vp, ci, vp, vp]),
+        "wb_f64_to_pcm16_dev": (ci, [vp, ci, vp, vp]),
+        "wb_f64_to_f32_dev": (ci, [vp, ctypes.c_ulonglong, vp, vp]),
+        "wb_write_f0": (ci, [ctypes.c_char_p, ci, cd, vp, vp, ci]),
+        "wb_read_f0": (ci, [ctypes.c_char_p, vp, vp]),
+        "wb_get_header_information": (cd, [ctypes.c_char_p, ctypes.c_char_p]),
+        "wb_write_spectral_envelope": (ci, [ctypes.c_char_p, ci, ci, cd, ci, ci, vp]),
+        "wb_read_spectral_envelope": (ci, [ctypes.c_char_p, vp]),
+        "wb_write_aperiodicity": (ci, [ctypes.c_char_p, ci, ci, cd, ci, ci, vp]),
+        "wb_read_aperiodicity": (ci, [ctypes.c_char_p, vp]),
+        "wb_write_parameter_matrix": (ci, [ci, ctypes.c_char_p, ci, ci, cd, ci, ci, vp, ctypes.c_longlong]),
+        "wb_read_parameter_matrix": (ci, [ci, ctypes.c_char_p, vp, ctypes.c_longlong]),
+        "wb_wavwrite": (ci, [vp, ci, ci, ci, ctypes.c_char_p]),
+        "wb_get_audio_length": (ci, [ctypes.c_char_p]),
+        "wb_wavread": (ci, [ctypes.c_char_p, ctypes.POINTER(ci), ctypes.POINTER(ci), vp]),
+        "wb_wavread_pcm16": (ci, [ctypes.c_char_p, ctypes.POINTER(ci), vp]),
         "wb_launch_count": (ctypes.c_ulonglong, []),
         "wb_stream": (vp, []),
         "wb_profile_enable": (None, [ci]),
@@ -413,6 +431,30 @@ class Pipeline:
                                      ptr(out.get("sp")), ptr(out.get("ap")), y.ctypes.data, ny), "wb_pipeline_run")
         return out
 
+    def run_pcm16(self, pcm):
+        """wav in -> wav out: host int16 samples in, re-synthesised host int16 samples out (the sample-format
+        conversions of the reference's wavread / wavwrite run on the device)."""
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        ny = self.out_length(len(pcm))
+        out = np.empty(ny, dtype=np.int16)
+        _check(lib().wb_pipeline_run_pcm16(self._h, pcm.ctypes.data, len(pcm), out.ctypes.data, ny), "wb_pipeline_run_pcm16")
+        return out
+
+    def run_f32(self, x, want_params=True, want_y=True):
+        """host x -> dict(f0, sp, ap, y) as float32 host arrays (narrowed on the device; arithmetic stays fp64)"""
+        x = _f64(x)
+        L, bins = self.f0_length(len(x)), self.fft_size // 2 + 1
+        ny = self.out_length(len(x)) if want_y else 0
+        out = {}
+        if want_params:
+            out.update(f0=np.empty(L, np.float32), sp=np.empty((L, bins), np.float32), ap=np.empty((L, bins), np.float32))
+        if want_y:
+            out["y"] = np.empty(ny, np.float32)
+        ptr = lambda a: a.ctypes.data if a is not None else None
+        _check(lib().wb_pipeline_run_f32(self._h, x.ctypes.data, len(x), ptr(out.get("f0")), ptr(out.get("sp")),
+                                         ptr(out.get("ap")), ptr(out.get("y")), ny), "wb_pipeline_run_f32")
+        return out
+
     def debug_read(self, name, shape, dtype=np.float64):
         out = np.empty(shape, dtype=dtype)
         _check(lib().wb_pipeline_debug_read(self._h, name.encode(), out.ctypes.data, out.nbytes), "wb_pipeline_debug_read")
@@ -490,6 +532,89 @@ def CodeSpectralEnvelope(spectrogram, fs, fft_size, number_of_dimensions):
 def DecodeSpectralEnvelope(coded_spectral_envelope, fs, fft_size, number_of_dimensions):
     return _codec(lib().wb_decode_spectral_envelope, "wb_decode_spectral_envelope", coded_spectral_envelope,
                   int(fft_size) // 2 + 1, int(fs), int(fft_size), int(number_of_dimensions))
+
+
+# ---- the reference's file formats (tools/parameterio.hpp, tools/audioio.hpp) ----------------------------
+def WriteF0(filename, f0_length, frame_period, temporal_positions, f0, text_flag=0):
+    tpos, f0 = _f64(temporal_positions), _f64(f0)
+    _check(lib().wb_write_f0(os.fsencode(filename), int(f0_length), float(frame_period), tpos.ctypes.data,
+                             f0.ctypes.data, int(text_flag)), "wb_write_f0")
+
+
+def GetHeaderInformation(filename, parameter):
+    return lib().wb_get_header_information(os.fsencode(filename), parameter.encode())
+
+
+def ReadF0(filename):
+    """-> (temporal_positions, f0)"""
+    n = int(GetHeaderInformation(filename, "NOF "))
+    tpos, f0 = np.empty(n), np.empty(n)
+    _check(lib().wb_read_f0(os.fsencode(filename), tpos.ctypes.data, f0.ctypes.data), "wb_read_f0")
+    return tpos, f0
+
+
+def _write_matrix(fn, name, filename, fs, f0_length, frame_period, fft_size, number_of_dimensions, mat):
+    mat = _f64(mat)
+    rows = _row_pointers(mat)
+    _check(fn(os.fsencode(filename), int(fs), int(f0_length), float(frame_period), int(fft_size),
+              int(number_of_dimensions), rows.ctypes.data), name)
+
+
+def _read_matrix(fn, name, filename):
+    n, fft, nod = (int(GetHeaderInformation(filename, k)) for k in ("NOF ", "FFT ", "NOD "))
+    mat = np.empty((n, nod if nod else fft // 2 + 1))
+    rows = _row_pointers(mat)
+    _check(fn(os.fsencode(filename), rows.ctypes.data), name)
+    return mat
+
+
+def WriteSpectralEnvelope(filename, fs, f0_length, frame_period, fft_size, number_of_dimensions, spectrogram):
+    _write_matrix(lib().wb_write_spectral_envelope, "wb_write_spectral_envelope", filename, fs, f0_length, frame_period,
+                  fft_size, number_of_dimensions, spectrogram)
+
+
+def ReadSpectralEnvelope(filename):
+    return _read_matrix(lib().wb_read_spectral_envelope, "wb_read_spectral_envelope", filename)
+
+
+def WriteAperiodicity(filename, fs, f0_length, frame_period, fft_size, number_of_dimensions, aperiodicity):
+    _write_matrix(lib().wb_write_aperiodicity, "wb_write_aperiodicity", filename, fs, f0_length, frame_period,
+                  fft_size, number_of_dimensions, aperiodicity)
+
+
+def ReadAperiodicity(filename):
+    return _read_matrix(lib().wb_read_aperiodicity, "wb_read_aperiodicity", filename)
+
+
+def wavwrite(x, fs, nbit, filename):
+    x = _f64(x)
+    _check(lib().wb_wavwrite(x.ctypes.data, len(x), int(fs), int(nbit), os.fsencode(filename)), "wb_wavwrite")
+
+
+def GetAudioLength(filename):
+    return lib().wb_get_audio_length(os.fsencode(filename))
+
+
+def wavread(filename):
+    """-> (x, fs, nbit)"""
+    n = GetAudioLength(filename)
+    if n <= 0:
+        raise WorldB200Error("wavread: cannot read %r (GetAudioLength = %d)" % (filename, n))
+    x = np.empty(n)
+    fs, nbit = ctypes.c_int(), ctypes.c_int()
+    _check(lib().wb_wavread(os.fsencode(filename), ctypes.byref(fs), ctypes.byref(nbit), x.ctypes.data), "wb_wavread")
+    return x, fs.value, nbit.value
+
+
+def wavread_pcm16(filename):
+    """-> (int16 samples, fs)"""
+    n = GetAudioLength(filename)
+    if n <= 0:
+        raise WorldB200Error("wavread_pcm16: cannot read %r (GetAudioLength = %d)" % (filename, n))
+    pcm = np.empty(n, dtype=np.int16)
+    fs = ctypes.c_int()
+    _check(lib().wb_wavread_pcm16(os.fsencode(filename), ctypes.byref(fs), pcm.ctypes.data), "wb_wavread_pcm16")
+    return pcm, fs.value
 
 
 class BatchPipeline:

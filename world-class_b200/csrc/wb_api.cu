@@ -971,6 +971,87 @@ int wb_pipeline_run(wb_pipeline_t *p, const double *x, int x_length, double *tpo
   return p->ws.read_error_flag(st);
 }
 
+// wav in -> wav out (test/test.cpp:288-384 with tools/audioio.cpp either side): 16-bit PCM crosses PCIe, the
+// sample-format conversions of wavread / wavwrite run on the device (wb_io.cu)
+int wb_pipeline_run_pcm16(wb_pipeline_t *p, const short *pcm_in, int x_length, short *pcm_out, int y_length) {
+  if (!p || !pcm_in || x_length <= 0 || y_length < 0 || (y_length > 0 && !pcm_out)) return WB_ERR_ARG;
+  cudaStream_t st = g_stream;
+  short *d_pcm_in = (short *)p->ws.get("pl_pcm_in", sizeof(short) * (size_t)x_length);
+  short *d_pcm_out = (short *)p->ws.get("pl_pcm_out", sizeof(short) * (size_t)(y_length > 0 ? y_length : 1));
+  double *d_x = (double *)p->ws.get("h_x", sizeof(double) * (size_t)x_length);
+  double *d_y = (double *)p->ws.get("pl_y", sizeof(double) * (size_t)(y_length > 0 ? y_length : 1));
+  if (!d_pcm_in || !d_pcm_out || !d_x || !d_y) return WB_ERR_CUDA;
+  int rc;
+  WB_CUDA_CHECK(cudaMemcpyAsync(d_pcm_in, pcm_in, sizeof(short) * (size_t)x_length, cudaMemcpyHostToDevice, st));
+  if ((rc = wb_pcm16_to_f64_run(d_pcm_in, x_length, d_x, st))) return rc;
+  if ((rc = wb_pipeline_run_dev(p, d_x, x_length, nullptr, nullptr, nullptr, nullptr, d_y, y_length, st))) return rc;
+  if (y_length > 0) {
+    if ((rc = wb_f64_to_pcm16_run(d_y, y_length, d_pcm_out, st))) return rc;
+    WB_CUDA_CHECK(cudaMemcpyAsync(pcm_out, d_pcm_out, sizeof(short) * (size_t)y_length, cudaMemcpyDeviceToHost, st));
+  }
+  WB_CUDA_CHECK(cudaStreamSynchronize(st));
+  return p->ws.read_error_flag(st);
+}
+
+// analysis (+ optional re-synthesis) with the outputs narrowed to fp32 on the device: half the bytes back to
+// the host, contiguous [f0_length][fft_size/2+1] matrices.  Arithmetic stays fp64.
+int wb_pipeline_run_f32(wb_pipeline_t *p, const double *x, int x_length, float *f0, float *sp, float *ap, float *y,
+                        int y_length) {
+  if (!p || !x || x_length <= 0 || y_length < 0 || (y_length > 0 && !y)) return WB_ERR_ARG;
+  cudaStream_t st = g_stream;
+  const int f0_length = wb_pipeline_f0_length(p, x_length);
+  const size_t bins = p->ct.fft_size / 2 + 1, cells = (size_t)f0_length * bins;
+  double *d_x;
+  int rc;
+  if ((rc = vec_to_device(&p->ws, "h_x", x, x_length, &d_x, st))) return rc;
+  double *d_f = (double *)p->ws.get("pl_f0", sizeof(double) * f0_length);
+  double *d_sp = (double *)p->ws.get("pl_sp", sizeof(double) * cells);
+  double *d_ap = (double *)p->ws.get("pl_ap", sizeof(double) * cells);
+  double *d_y = (double *)p->ws.get("pl_y", sizeof(double) * (size_t)(y_length > 0 ? y_length : 1));
+  float *d_n = (float *)p->ws.get("pl_f32", sizeof(float) * (2 * cells + (size_t)f0_length + (size_t)y_length + 4));
+  if (!d_f || !d_sp || !d_ap || !d_y || !d_n) return WB_ERR_CUDA;
+  if ((rc = wb_pipeline_run_dev(p, d_x, x_length, nullptr, d_f, d_sp, d_ap, d_y, y_length, st))) return rc;
+  float *n_sp = d_n, *n_ap = d_n + cells, *n_f0 = d_n + 2 * cells, *n_y = n_f0 + f0_length;
+  if (sp) {
+    if ((rc = wb_f64_to_f32_run(d_sp, cells, n_sp, st))) return rc;
+    WB_CUDA_CHECK(cudaMemcpyAsync(sp, n_sp, sizeof(float) * cells, cudaMemcpyDeviceToHost, st));
+  }
+  if (ap) {
+    if ((rc = wb_f64_to_f32_run(d_ap, cells, n_ap, st))) return rc;
+    WB_CUDA_CHECK(cudaMemcpyAsync(ap, n_ap, sizeof(float) * cells, cudaMemcpyDeviceToHost, st));
+  }
+  if (f0) {
+    if ((rc = wb_f64_to_f32_run(d_f, f0_length, n_f0, st))) return rc;
+    WB_CUDA_CHECK(cudaMemcpyAsync(f0, n_f0, sizeof(float) * f0_length, cudaMemcpyDeviceToHost, st));
+  }
+  if (y_length > 0) {
+    if ((rc = wb_f64_to_f32_run(d_y, y_length, n_y, st))) return rc;
+    WB_CUDA_CHECK(cudaMemcpyAsync(y, n_y, sizeof(float) * (size_t)y_length, cudaMemcpyDeviceToHost, st));
+  }
+  WB_CUDA_CHECK(cudaStreamSynchronize(st));
+  return p->ws.read_error_flag(st);
+}
+
+/* device-pointer conversions (asynchronous on `stream`) */
+int wb_pcm16_to_f64_dev(const short *d_pcm, int n, double *d_x, void *stream) {
+  int rc = ctx_init();
+  if (rc) return rc;
+  if (n < 0 || (n > 0 && (!d_pcm || !d_x))) return WB_ERR_ARG;
+  return wb_pcm16_to_f64_run(d_pcm, n, d_x, pick_stream(stream));
+}
+int wb_f64_to_pcm16_dev(const double *d_x, int n, short *d_pcm, void *stream) {
+  int rc = ctx_init();
+  if (rc) return rc;
+  if (n < 0 || (n > 0 && (!d_pcm || !d_x))) return WB_ERR_ARG;
+  return wb_f64_to_pcm16_run(d_x, n, d_pcm, pick_stream(stream));
+}
+int wb_f64_to_f32_dev(const double *d_in, unsigned long long n, float *d_out, void *stream) {
+  int rc = ctx_init();
+  if (rc) return rc;
+  if (n > 0 && (!d_in || !d_out)) return WB_ERR_ARG;
+  return wb_f64_to_f32_run(d_in, (size_t)n, d_out, pick_stream(stream));
+}
+
 // ---- parameter modification (test/test.cpp:201-243) ------------------------------------------
 int wb_parameter_modification_dev(double *d_f0, int f0_length, double *d_spectrogram, int fs, int fft_size,
                                   double f0_shift, double ratio, void *stream) {

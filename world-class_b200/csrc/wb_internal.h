@@ -83,3 +83,8 @@ int wb_decode_spectral_envelope_dev(WbWorkspace *ws, const double *d_coded, int 
 // parameter modification (wb_modify.cu): test/test.cpp:201-243
 int wb_parameter_modification_run(const double *d_f0_in, double *d_f0_out, int f0_length, double *d_sp, int fs,
                                   int fft_size, double f0_shift, double ratio, cudaStream_t stream);
+
+// sample-format conversions (wb_io.cu): tools/audioio.cpp:176-180 (wavwrite), :232-249 (wavread, 16 bit); fp32 narrowing
+int wb_pcm16_to_f64_run(const short *d_in, int n, double *d_out, cudaStream_t stream);
+int wb_f64_to_pcm16_run(const double *d_in, int n, short *d_out, cudaStream_t stream);
+int wb_f64_to_f32_run(const double *d_in, size_t n, float *d_out, cudaStream_t stream);
