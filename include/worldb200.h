@@ -191,6 +191,29 @@ int wb_pipeline_run_pcm16(wb_pipeline_t *p, const short *pcm_in, int x_length, s
 int wb_pipeline_run_f32(wb_pipeline_t *p, const double *x, int x_length, float *f0_or_null, float *spectrogram_or_null,
                         float *aperiodicity_or_null, float *y, int y_length);
 
+/* ---- one long stream sharded over ranks (BASELINE configs[3]: frames shard, one exchange step) -----------
+ * CheapTrick (src/cheaptrick.cpp:48-95), D4C (src/d4c.cpp:113-173) and Synthesis (src/synthesis.cpp:77-177) of a
+ * RANGE of a stream whose whole f0 contour is known (gathered from the ranks' Harvest runs).  A frame's
+ * position in the process-global randn() stream (src/world_matlabfunctions.cpp:243-264) and the sequential
+ * phase sum that places the pulses (src/synthesis.cpp:257-264) are recomputed for the whole stream on every
+ * rank -- they are cheap functions of f0 -- so the rows / samples of a range are bit-identical to those of an
+ * unsharded run.  Device pointers; asynchronous on `stream`; d_f0_all / d_ap0_all hold f0_length entries;
+ * *_rows address the first row of the range ([rows][fft_size/2+1], contiguous).  Per rank, in this order:
+ *   begin; envelope (writes d_ap0_all[frame_begin, frame_end)); [all-gather d_ap0_all]; aperiodicity; synthesis.
+ * The sp / ap rows given to synthesis must cover every frame a pulse reaching into the sample range
+ * interpolates between: frames floor((sample_begin - fft_size) / fs / frame_period) .. ceil((sample_end +
+ * fft_size) / fs / frame_period), clipped to the stream. */
+int wb_pipeline_stream_begin_dev(wb_pipeline_t *p, const double *d_f0_all, int f0_length, int out_length, void *stream);
+int wb_pipeline_stream_envelope_dev(wb_pipeline_t *p, const double *d_x, int x_length, const double *d_f0_all,
+                                    int f0_length, int frame_begin, int frame_end, double *d_sp_rows,
+                                    double *d_ap0_all, void *stream);
+int wb_pipeline_stream_aperiodicity_dev(wb_pipeline_t *p, const double *d_x, int x_length, const double *d_f0_all,
+                                        const double *d_ap0_all, int f0_length, int frame_begin, int frame_end,
+                                        double *d_ap_rows, void *stream);
+int wb_pipeline_stream_synthesis_dev(wb_pipeline_t *p, int f0_length, const double *d_sp_rows, const double *d_ap_rows,
+                                     int row_begin, int n_rows, int out_length, int sample_begin, int sample_end,
+                                     double *d_out, void *stream);
+
 /* test / bench hook: copies n_bytes of a named internal device buffer of the last run to `out` */
 int wb_pipeline_debug_read(wb_pipeline_t *p, const char *name, void *out, unsigned long long n_bytes);
 

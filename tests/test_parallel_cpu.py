@@ -81,3 +81,70 @@ def test_single_process_fallback_matches():
     x = np.random.default_rng(0).standard_normal(5000)
     y = parallel.process_stream(x, 1000, _fake_vocoder, segment_seconds=0.7, halo_seconds=0.01)
     assert np.allclose(y, _fake_vocoder(x), atol=1e-15)
+
+
+# ---- exact stream sharding: planning and the exchange step (no GPU) ----------------------------------------
+@pytest.mark.parametrize("n,fs,world,seg", [(480000, 48000, 2, 4), (60 * 48000 + 1234, 48000, 3, 30), (22050 * 7 + 5, 22050, 2, 3),
+                                            (16000, 16000, 1, 30), (3600 * 48000, 48000, 8, 30), (16000 * 3, 16000, 8, 1)])
+def test_stream_plan_covers_the_stream_and_keeps_the_analysis_grid(n, fs, world, seg):
+    import worldb200  # noqa: F401
+    from worldb200 import parallel as P
+    fft = 2048 if fs == 48000 else 1024
+    pl = P.StreamPlan(n, fs, world, 5.0, fft, segment_seconds=seg, halo_seconds=2)
+    assert pl.f0_length == int(1000.0 * n / fs / 5.0) + 1 and pl.out_length == int((pl.f0_length - 1) * 5.0 / 1000.0 * fs) + 1
+    # frames and samples are partitioned in rank order
+    assert pl.frames[0][0] == 0 and pl.frames[-1][1] == pl.f0_length and pl.samples[0][0] == 0 and pl.samples[-1][1] == pl.out_length
+    for k in range(world - 1):
+        assert pl.frames[k][1] == pl.frames[k + 1][0] and pl.samples[k][1] == pl.samples[k + 1][0]
+    r = P.decimation_ratio(fs)
+    for k in range(world):
+        fb, fe = pl.frames[k]
+        covered = fb
+        for s in pl.segments[k]:
+            pa, pb = s["padded"]
+            cfb, cfe = s["frames"]
+            assert cfb == covered and cfe > cfb
+            covered = cfe
+            assert pa % fs == 0 and pa % r == 0 and (pb - n) % r == 0 and 0 <= pa < pb <= n      # grid + decimation phase
+            assert s["frame_offset"] * 5.0 / 1000.0 == pa / fs                                   # same frame times
+            local_len = int(1000.0 * (pb - pa) / fs / 5.0) + 1                                   # Harvest::getSamples of the segment
+            assert 0 <= cfb - s["frame_offset"] and cfe - s["frame_offset"] <= local_len
+            # the core keeps >= 1 s of context on both sides unless it touches the stream's end
+            assert pa == 0 or (cfb / 200.0 - pa / fs) >= 1.0
+            assert pb >= n - r or (pb / fs - cfe / 200.0) >= 1.0
+        assert covered == fe
+        ra, rb = pl.rows[k]
+        sa, sb = pl.samples[k]
+        assert ra <= fb and rb >= fe
+        # every pulse reaching into [sa, sb) sits at a sample in (sa - fft, sb + fft): its two frames are rows
+        assert ra == 0 or ra <= int((sa - fft) / fs * 200.0)
+        assert rb == pl.f0_length or rb >= int(np.ceil((sb + fft) / fs * 200.0)) + 1
+
+
+def _gather_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import worldb200  # noqa: F401
+    from worldb200 import parallel as P
+    ranges = [(0, 5), (5, 6), (6, 13)][:world] if world == 3 else [(0, 7), (7, 13)]
+    b, e = ranges[rank]
+    full = torch.arange(13, dtype=torch.float64) * 1.5 + 0.25
+    got = P.gather_ranges(full[b:e].clone(), ranges, 13)
+    q.put((rank, bool(torch.equal(got, full))))
+    dist.destroy_process_group()
+
+
+def test_gather_ranges_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]

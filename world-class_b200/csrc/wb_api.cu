@@ -971,6 +971,97 @@ int wb_pipeline_run(wb_pipeline_t *p, const double *x, int x_length, double *tpo
   return p->ws.read_error_flag(st);
 }
 
+// ---- one long stream sharded over ranks (BASELINE configs[3]) ----------------------
+// The frames of a stream are independent given the whole stream's f0, EXCEPT for their position in the
+// process-global randn() stream (a prefix sum over all earlier frames and stages) and, in Synthesis, the
+// sequential phase sum that places the pulses.  Both are cheap functions of f0 (and of the Love Train
+// decisions), so every rank recomputes them for the whole stream and does the heavy per-frame / per-pulse work
+// for its own range only; the results equal an unsharded run bit for bit.  Call order per rank:
+//   begin -> envelope (CheapTrick + Love Train rows) -> [all-gather ap0] -> aperiodicity (D4C body rows)
+//   -> synthesis (sample range).  The collectives themselves are the caller's (torch.distributed / NCCL).
+namespace {
+__global__ void frame_times_kernel(double *__restrict__ tpos, int n, double frame_period) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) tpos[i] = i * frame_period / 1000.0;   // harvest.cpp:196-199
+}
+}  // namespace
+
+int wb_pipeline_stream_begin_dev(wb_pipeline_t *p, const double *d_f0_all, int f0_length, int out_length, void *stream_) {
+  if (!p || !d_f0_all || f0_length < 2 || out_length < 0) return WB_ERR_ARG;
+  cudaStream_t stream = pick_stream(stream_);
+  const double fp = p->plan.opt.frame_period;
+  double *d_tpos = (double *)p->ws.get("st_tpos", sizeof(double) * f0_length);
+  unsigned long long *rng_pos = (unsigned long long *)p->ws.get("pl_rng_pos", sizeof(unsigned long long) * 4);
+  if (!d_tpos || !rng_pos) return WB_ERR_CUDA;
+  WB_LAUNCH("frame_times_kernel", frame_times_kernel<<<(f0_length + 255) / 256, 256, 0, stream>>>(d_tpos, f0_length, fp));
+  WB_CUDA_CHECK(cudaGetLastError());
+  if (p->private_rng)
+    WB_CUDA_CHECK(cudaMemcpyAsync(p->d_rng_private, p->d_rng_seed, sizeof(WbRngState), cudaMemcpyDeviceToDevice, stream));
+  // the time base / exact phase scan / pulse list of the whole stream depend on f0 only: side stream
+  if (out_length > 0) {
+    WB_CUDA_CHECK(cudaEventRecord(p->ev_f0, stream));
+    WB_CUDA_CHECK(cudaStreamWaitEvent(p->side, p->ev_f0, 0));
+    int rc = wb_synthesis_timebase(&p->ws, p->fs, p->ct.fft_size, fp, d_f0_all, f0_length, out_length, p->side, nullptr);
+    if (rc) return rc;
+    WB_CUDA_CHECK(cudaEventRecord(p->ev_tb, p->side));
+  }
+  return WB_OK;
+}
+
+int wb_pipeline_stream_envelope_dev(wb_pipeline_t *p, const double *d_x, int x_length, const double *d_f0_all,
+                                    int f0_length, int frame_begin, int frame_end, double *d_sp_rows,
+                                    double *d_ap0_all, void *stream_) {
+  if (!p || !d_x || !d_f0_all || !d_sp_rows || !d_ap0_all || x_length <= 0) return WB_ERR_ARG;
+  cudaStream_t stream = pick_stream(stream_);
+  double *d_tpos = (double *)p->ws.get("st_tpos", 0);
+  unsigned long long *rng_pos = (unsigned long long *)p->ws.get("pl_rng_pos", 0);
+  if (!d_tpos || !rng_pos) return WB_ERR_ARG;   // begin has not been called
+  WbRngState *rng = p->private_rng ? p->d_rng_private : wb_rng_global_state();
+  const WbFrameRange range = {frame_begin, frame_end};
+  WbRngCursor c_ct;
+  c_ct.state = rng; c_ct.skip_out = rng_pos + 0; c_ct.advance = false;
+  int rc;
+  if ((rc = wb_cheaptrick_run(&p->ws, p->fs, p->ct.fft_size, p->ct.q1, p->ct_f0_floor_internal, d_x, x_length, d_tpos,
+                              d_f0_all, f0_length, d_sp_rows, c_ct, stream, nullptr, &range)))
+    return rc;
+  WbRngCursor c_lt;
+  c_lt.state = rng; c_lt.skip_in = rng_pos + 0; c_lt.advance = false;
+  return wb_d4c_run(&p->ws, p->fs, p->d4c.threshold, d_x, x_length, d_tpos, d_f0_all, f0_length, p->ct.fft_size, nullptr,
+                    c_lt, stream, nullptr, &range, 1, d_ap0_all);
+}
+
+int wb_pipeline_stream_aperiodicity_dev(wb_pipeline_t *p, const double *d_x, int x_length, const double *d_f0_all,
+                                        const double *d_ap0_all, int f0_length, int frame_begin, int frame_end,
+                                        double *d_ap_rows, void *stream_) {
+  if (!p || !d_x || !d_f0_all || !d_ap_rows || !d_ap0_all || x_length <= 0) return WB_ERR_ARG;
+  cudaStream_t stream = pick_stream(stream_);
+  double *d_tpos = (double *)p->ws.get("st_tpos", 0);
+  unsigned long long *rng_pos = (unsigned long long *)p->ws.get("pl_rng_pos", 0);
+  if (!d_tpos || !rng_pos) return WB_ERR_ARG;
+  WbRngState *rng = p->private_rng ? p->d_rng_private : wb_rng_global_state();
+  const WbFrameRange range = {frame_begin, frame_end};
+  WbRngCursor c;
+  c.state = rng; c.skip_in = rng_pos + 0; c.skip_out = rng_pos + 1; c.advance = false;
+  return wb_d4c_run(&p->ws, p->fs, p->d4c.threshold, d_x, x_length, d_tpos, d_f0_all, f0_length, p->ct.fft_size, d_ap_rows,
+                    c, stream, nullptr, &range, 2, const_cast<double *>(d_ap0_all));
+}
+
+int wb_pipeline_stream_synthesis_dev(wb_pipeline_t *p, int f0_length, const double *d_sp_rows, const double *d_ap_rows,
+                                     int row_begin, int n_rows, int out_length, int sample_begin, int sample_end,
+                                     double *d_out, void *stream_) {
+  if (!p || !d_sp_rows || !d_ap_rows || !d_out || out_length <= 0) return WB_ERR_ARG;
+  cudaStream_t stream = pick_stream(stream_);
+  unsigned long long *rng_pos = (unsigned long long *)p->ws.get("pl_rng_pos", 0);
+  if (!rng_pos || !p->ws.get("syn_pidx", 0)) return WB_ERR_ARG;   // begin (with out_length > 0) has not been called
+  WbRngState *rng = p->private_rng ? p->d_rng_private : wb_rng_global_state();
+  WB_CUDA_CHECK(cudaStreamWaitEvent(stream, p->ev_tb, 0));
+  WbRngCursor c;
+  c.state = rng; c.skip_in = rng_pos + 1; c.advance = true;   // moves the state past the whole stream's draws
+  return wb_synthesis_render_range(&p->ws, p->fs, p->ct.fft_size, p->plan.opt.frame_period, f0_length, d_sp_rows, d_ap_rows,
+                                   row_begin, n_rows, out_length, sample_begin, sample_end, d_out,
+                                   p->plan.opt.f0_ceil * 1.25, c, stream);
+}
+
 // wav in -> wav out (test/test.cpp:288-384 with tools/audioio.cpp either side): 16-bit PCM crosses PCIe, the
 // sample-format conversions of wavread / wavwrite run on the device (wb_io.cu)
 int wb_pipeline_run_pcm16(wb_pipeline_t *p, const short *pcm_in, int x_length, short *pcm_out, int y_length) {

@@ -141,8 +141,9 @@ size_t wb_cheaptrick_smem_bytes(int fft_size, int seg_capacity) {
 int wb_cheaptrick_run(WbWorkspace *ws, int fs, int fft_size, double q1, double f0_floor_internal,
                       const double *d_x, int x_length, const double *d_tpos, const double *d_f0,
                       int f0_length, double *d_sp, const WbRngCursor &rng, cudaStream_t stream,
-                      const WbRowChunks *chunks) {
+                      const WbRowChunks *chunks, const WbFrameRange *range) {
   if (f0_length <= 0) return WB_OK;
+  if (range && (range->begin < 0 || range->end > f0_length || range->begin > range->end || chunks)) return WB_ERR_ARG;
   int log2n = 0;
   while ((1 << log2n) < fft_size) ++log2n;
   if ((1 << log2n) != fft_size || fft_size < 128 || fft_size > 16384) return WB_ERR_UNSUPPORTED;
@@ -151,7 +152,8 @@ int wb_cheaptrick_run(WbWorkspace *ws, int fs, int fft_size, double q1, double f
   if (!tw) return WB_ERR_CUDA;
 
   unsigned long long *d_offsets = (unsigned long long *)ws->get("ct_offsets", sizeof(unsigned long long) * (f0_length + 1));
-  const unsigned long long max_noise = (unsigned long long)f0_length * (unsigned long long)(fft_size + bins);
+  const int n_rows = range ? range->end - range->begin : f0_length;
+  const unsigned long long max_noise = (unsigned long long)(n_rows > 0 ? n_rows : 1) * (unsigned long long)(fft_size + bins);
   double *d_noise = (double *)ws->get("noise_ct", sizeof(double) * max_noise);
   if (!d_offsets || !d_noise) return WB_ERR_CUDA;
 
@@ -161,22 +163,36 @@ int wb_cheaptrick_run(WbWorkspace *ws, int fs, int fft_size, double q1, double f
   WB_CUDA_CHECK(cudaGetLastError());
   int rc;
   if (rng.record_skip_out) WB_CUDA_CHECK(cudaEventRecord(rng.record_skip_out, stream));
-  rc = wb_rng_fill(rng.state, rng.skip_in, d_offsets + f0_length, max_noise, d_noise, stream);
-  if (rc) return rc;
+  const unsigned long long *d_noise_off = d_offsets;
+  if (range) {
+    // draw only the rows' share of the stream; the frames index it relative to the first row
+    unsigned long long *d_rel = (unsigned long long *)ws->get("ct_offsets_rel", sizeof(unsigned long long) * (f0_length + 1));
+    unsigned long long *d_pos = (unsigned long long *)ws->get("ct_range_pos", sizeof(unsigned long long) * 2);
+    if (!d_rel || !d_pos) return WB_ERR_CUDA;
+    if ((rc = wb_range_offsets(d_offsets, *range, d_rel, rng.skip_in, d_pos, d_pos + 1, stream))) return rc;
+    if (n_rows > 0 && (rc = wb_rng_fill(rng.state, d_pos, d_pos + 1, max_noise, d_noise, stream))) return rc;
+    d_noise_off = d_rel;
+  } else {
+    rc = wb_rng_fill(rng.state, rng.skip_in, d_offsets + f0_length, max_noise, d_noise, stream);
+    if (rc) return rc;
+  }
 
   CtParams p;
   p.x = d_x; p.x_length = x_length; p.tpos = d_tpos; p.f0 = d_f0; p.f0_length = f0_length;
   p.fs = fs; p.fft_size = fft_size; p.log2nc = log2n - 1; p.q1 = q1; p.f0_floor = f0_floor_internal;
-  p.twiddle = tw; p.noise = d_noise; p.noise_off = d_offsets; p.sp = d_sp;
+  p.twiddle = tw; p.noise = d_noise; p.noise_off = d_noise_off;
+  p.sp = range ? d_sp - (size_t)range->begin * bins : d_sp;   // (rows are addressed by absolute frame)
   p.seg_capacity = fft_size / 2 + fft_size / 4 + 8;
   p.error_flag = ws->error_flag();
   const size_t smem = wb_cheaptrick_smem_bytes(fft_size, p.seg_capacity);
   const int threads = wb_max_i(64, wb_min_i(256, fft_size / 8));
-  p.frame_begin = 0;
-  if (!chunks || chunks->n <= 1) {
+  p.frame_begin = range ? range->begin : 0;
+  if (n_rows <= 0) {
+    // (an empty range still takes part in the stream bookkeeping below)
+  } else if (!chunks || chunks->n <= 1) {
     rc = WB_DISPATCH_LOG2(log2n, 8, 13, {
       if (cudaFuncSetAttribute(ct_frame_kernel<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WB_ERR_CUDA;
-      WB_LAUNCH("ct_frame_kernel", ct_frame_kernel<L2><<<f0_length, threads, smem, stream>>>(p));
+      WB_LAUNCH("ct_frame_kernel", ct_frame_kernel<L2><<<n_rows, threads, smem, stream>>>(p));
     });
     if (rc) return rc;
     if (chunks && chunks->n == 1) WB_CUDA_CHECK(cudaEventRecord(chunks->ev[0], stream));

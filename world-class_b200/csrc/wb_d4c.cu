@@ -117,6 +117,7 @@ struct LtParams {
   const cplx *twiddle;
   const double *noise; const unsigned long long *noise_off;
   double *ap0;
+  int frame_begin;   // this launch covers frames frame_begin + blockIdx.x
 };
 
 template <int LOG2N>
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(256) lt_frame_kernel(LtParams p) {
   double *win = reinterpret_cast<double *>(S + wb_fft_slots(NC));  // N doubles
   double *red = win + N;                                          // 128
   double *W = reinterpret_cast<double *>(S);
-  const int frame = blockIdx.x;
+  const int frame = p.frame_begin + blockIdx.x;
   const double f0 = p.f0[frame];
   if (f0 == 0.0) {
     if (threadIdx.x == 0) p.ap0[frame] = 0.0;
@@ -675,8 +676,12 @@ int wb_number_of_aperiodicities(int fs) {  // d4c.cpp:65-67, codec.cpp:211-214
 
 int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int x_length, const double *d_tpos,
                const double *d_f0, int f0_length, int out_fft_size, double *d_ap, const WbRngCursor &rng,
-               cudaStream_t stream, const WbRowChunks *chunks) {
+               cudaStream_t stream, const WbRowChunks *chunks, const WbFrameRange *range, int phase, double *d_ap0_ext) {
   if (f0_length <= 0) return WB_OK;
+  if (range && (range->begin < 0 || range->end > f0_length || range->begin > range->end || chunks)) return WB_ERR_ARG;
+  if (phase < 0 || phase > 2 || (phase != 0 && !d_ap0_ext)) return WB_ERR_ARG;
+  const int row0 = range ? range->begin : 0;
+  const int n_rows = range ? range->end - range->begin : f0_length;
   const int N = wb_d4c_fft_size(fs), N_lt = wb_d4c_lt_fft_size(fs);
   const int l = ilog2_exact(N), l_lt = ilog2_exact(N_lt);
   if (l < 7 || N > 8192 || l_lt < 7 || N_lt > 16384) return WB_ERR_UNSUPPORTED;
@@ -686,9 +691,16 @@ int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int
 
   (void)out_bins;
   unsigned long long *d_offsets = (unsigned long long *)ws->get("d4c_offsets", sizeof(unsigned long long) * (f0_length + 1));
-  double *d_ap0 = (double *)ws->get("d4c_ap0", sizeof(double) * f0_length);
-  const unsigned long long max_noise_lt = (unsigned long long)f0_length * N_lt;
-  const unsigned long long max_noise_body = (unsigned long long)f0_length * 3ull * N;
+  double *d_ap0 = d_ap0_ext ? d_ap0_ext : (double *)ws->get("d4c_ap0", sizeof(double) * f0_length);
+  const unsigned long long max_noise_lt = (unsigned long long)(n_rows > 0 ? n_rows : 1) * N_lt;
+  const unsigned long long max_noise_body = (unsigned long long)(n_rows > 0 ? n_rows : 1) * 3ull * N;
+  // sharded streams: the rows' share of the stream, indexed relative to the first row (see WbFrameRange)
+  unsigned long long *d_rel = nullptr, *d_pos = nullptr;
+  if (range) {
+    d_rel = (unsigned long long *)ws->get("d4c_offsets_rel", sizeof(unsigned long long) * (f0_length + 1));
+    d_pos = (unsigned long long *)ws->get("d4c_range_pos", sizeof(unsigned long long) * 2);
+    if (!d_rel || !d_pos) return WB_ERR_CUDA;
+  }
   double *d_noise = (double *)ws->get("noise_d4c", sizeof(double) * (max_noise_body > max_noise_lt ? max_noise_body : max_noise_lt));
   // stream position after the Love Train draws (= skip_in + Love Train count)
   unsigned long long *d_skip_mid = (unsigned long long *)ws->get("d4c_skip_mid", sizeof(unsigned long long));
@@ -726,47 +738,58 @@ int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int
   WB_CUDA_CHECK(cudaGetLastError());
   if (rng.wait_skip_in) WB_CUDA_CHECK(cudaStreamWaitEvent(stream, rng.wait_skip_in, 0));
   int rc;
-  if ((rc = wb_rng_fill(rng.state, rng.skip_in, d_offsets + f0_length, max_noise_lt, d_noise, stream))) return rc;
-  {
+  if (phase != 2) {
+  if (range) {
+    if ((rc = wb_range_offsets(d_offsets, *range, d_rel, rng.skip_in, d_pos, d_pos + 1, stream))) return rc;
+    if (n_rows > 0 && (rc = wb_rng_fill(rng.state, d_pos, d_pos + 1, max_noise_lt, d_noise, stream))) return rc;
+  } else if ((rc = wb_rng_fill(rng.state, rng.skip_in, d_offsets + f0_length, max_noise_lt, d_noise, stream))) return rc;
+  if (n_rows > 0) {
     LtParams p;
     p.x = d_x; p.x_length = x_length; p.tpos = d_tpos; p.f0 = d_f0; p.f0_length = f0_length;
     p.fs = fs; p.fft_size = N_lt; p.log2nc = l_lt - 1; p.lowest_f0 = 40.0;
     p.boundary0 = static_cast<int>(ceil(100.0 * N_lt / fs));
     p.boundary1 = static_cast<int>(ceil(4000.0 * N_lt / fs));
     p.boundary2 = static_cast<int>(ceil(7900.0 * N_lt / fs));
-    p.twiddle = tw_lt; p.noise = d_noise; p.noise_off = d_offsets; p.ap0 = d_ap0;
+    p.twiddle = tw_lt; p.noise = d_noise; p.noise_off = range ? d_rel : d_offsets; p.ap0 = d_ap0;
+    p.frame_begin = row0;
     const size_t smem = sizeof(cplx) * wb_fft_slots(N_lt / 2) + sizeof(double) * (N_lt + 128);
     rc = WB_DISPATCH_LOG2(l_lt, 9, 14, {
       if (cudaFuncSetAttribute(lt_frame_kernel<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WB_ERR_CUDA;
-      WB_LAUNCH("lt_frame_kernel", lt_frame_kernel<L2><<<f0_length, 256, smem, stream>>>(p));
+      WB_LAUNCH("lt_frame_kernel", lt_frame_kernel<L2><<<n_rows, 256, smem, stream>>>(p));
     });
     if (rc) return rc;
     WB_CUDA_CHECK(cudaGetLastError());
   }
+  }
+  if (phase == 1) return WB_OK;   // (the stream bookkeeping is done by the body phase)
   // ---- body
   WB_LAUNCH("body_count_scan_kernel", body_count_scan_kernel<<<1, 1024, 0, stream>>>(d_f0, d_ap0, f0_length, fs, threshold, d_offsets,
                                                                                   rng.skip_in, d_lt_total, d_skip_mid, d_skip_end));
   WB_CUDA_CHECK(cudaGetLastError());
   if (rng.record_skip_out) WB_CUDA_CHECK(cudaEventRecord(rng.record_skip_out, stream));
-  if ((rc = wb_rng_fill(rng.state, d_skip_mid, d_offsets + f0_length, max_noise_body, d_noise, stream))) return rc;
-  {
+  if (range) {
+    if ((rc = wb_range_offsets(d_offsets, *range, d_rel, d_skip_mid, d_pos, d_pos + 1, stream))) return rc;
+    if (n_rows > 0 && (rc = wb_rng_fill(rng.state, d_pos, d_pos + 1, max_noise_body, d_noise, stream))) return rc;
+  } else if ((rc = wb_rng_fill(rng.state, d_skip_mid, d_offsets + f0_length, max_noise_body, d_noise, stream))) return rc;
+  if (n_rows > 0) {
     BodyParams p;
     p.x = d_x; p.x_length = x_length; p.tpos = d_tpos; p.f0 = d_f0; p.ap0 = d_ap0; p.f0_length = f0_length;
     p.fs = fs; p.fft_size_d4c = N; p.log2n = l; p.threshold = threshold;
     p.n_ap = n_ap; p.window_length = window_length; p.nuttall = d_nuttall;
-    p.tw_n = tw_n; p.tw_2n = tw_2n; p.noise = d_noise; p.noise_off = d_offsets;
-    p.out_fft_size = out_fft_size; p.ap = d_ap;
+    p.tw_n = tw_n; p.tw_2n = tw_2n; p.noise = d_noise; p.noise_off = range ? d_rel : d_offsets;
+    p.out_fft_size = out_fft_size;
+    p.ap = range ? d_ap - (size_t)row0 * (out_fft_size / 2 + 1) : d_ap;   // (rows are addressed by absolute frame)
     p.seg_capacity = 0;  // the smoothing scratch aliases the FFT slots
     p.error_flag = ws->error_flag();
     p.debug_skip = getenv("WB_D4C_SKIP") ? atoi(getenv("WB_D4C_SKIP")) : 0;
     const int binsp = ((N / 2 + 1) + 1) & ~1;
     const size_t smem = sizeof(cplx) * wb_fft_slots(N) + sizeof(double) * (2 * binsp + 320) +
                         sizeof(unsigned long long) * (SEL_CTL_WORDS + 2 * SEL_LIST) + sizeof(double) * (D4C_MAX_AP + 2);
-    p.frame_begin = 0;
+    p.frame_begin = row0;
     if (!chunks || chunks->n <= 1) {
       rc = WB_DISPATCH_LOG2(l, 9, 13, {
         if (cudaFuncSetAttribute(d4c_body_kernel<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WB_ERR_CUDA;
-        WB_LAUNCH("d4c_body_kernel", d4c_body_kernel<L2><<<f0_length, D4C_BODY_THREADS, smem, stream>>>(p));
+        WB_LAUNCH("d4c_body_kernel", d4c_body_kernel<L2><<<n_rows, D4C_BODY_THREADS, smem, stream>>>(p));
       });
       if (rc) return rc;
       if (chunks && chunks->n == 1) WB_CUDA_CHECK(cudaEventRecord(chunks->ev[0], stream));

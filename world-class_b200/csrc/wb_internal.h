@@ -42,10 +42,21 @@ struct WbRowChunks {
   cudaEvent_t ev_ready = nullptr;   // recorded on the caller's stream when the frame kernel's inputs are ready
 };
 
+// A contiguous range of the frames of one long stream (frames shard across ranks).
+// The per-frame stages take the WHOLE stream's f0 (the randn() position of a frame is a prefix sum over all
+// earlier frames) but compute, draw noise for and write only rows [begin, end); the output pointer then
+// addresses row `begin`.  The cursor bookkeeping (skip_out, advance) is that of the whole stream.
+struct WbFrameRange { int begin; int end; };
+// rel[i] = offsets[i] - offsets[begin] for i in [begin, end]; *skip_range = *skip_in + offsets[begin];
+// *count_range = offsets[end] - offsets[begin]
+int wb_range_offsets(const unsigned long long *d_offsets, WbFrameRange range, unsigned long long *d_rel,
+                     const unsigned long long *d_skip_in, unsigned long long *d_skip_range,
+                     unsigned long long *d_count_range, cudaStream_t stream);
+
 int wb_cheaptrick_run(WbWorkspace *ws, int fs, int fft_size, double q1, double f0_floor_internal,
                       const double *d_x, int x_length, const double *d_tpos, const double *d_f0,
                       int f0_length, double *d_sp, const WbRngCursor &rng, cudaStream_t stream,
-                      const WbRowChunks *chunks = nullptr);
+                      const WbRowChunks *chunks = nullptr, const WbFrameRange *range = nullptr);
 
 // stand-alone batched transforms (wb_fftapi.cu); kind 0 r2c, 1 c2r, 2 c2c fwd, 3 c2c bwd
 int wb_fft_batch_dev(int kind, const void *d_in, int n, int batch, void *d_out, cudaStream_t stream);
@@ -54,11 +65,22 @@ int wb_fft_batch_dev(int kind, const void *d_in, int n, int batch, void *d_out, 
 int wb_d4c_fft_size(int fs);
 int wb_d4c_lt_fft_size(int fs);
 int wb_number_of_aperiodicities(int fs);
+// phase: 0 = Love Train + body (d_ap0_ext may be null: internal buffer); sharded streams run 1 = Love Train only
+// (writes d_ap0_ext[begin, end)) and, once every rank's decisions are gathered, 2 = body only (reads all of
+// d_ap0_ext).  With a range, d_ap addresses row `begin`.
 int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int x_length, const double *d_tpos,
                const double *d_f0, int f0_length, int out_fft_size, double *d_ap, const WbRngCursor &rng,
-               cudaStream_t stream, const WbRowChunks *chunks = nullptr);
+               cudaStream_t stream, const WbRowChunks *chunks = nullptr, const WbFrameRange *range = nullptr,
+               int phase = 0, double *d_ap0_ext = nullptr);
 
 // Synthesis (wb_synthesis.cu)
+// Samples [sample_begin, sample_end) of the whole stream's waveform.  Must follow wb_synthesis_timebase (whole
+// stream, without noise) on `ws`.  d_sp / d_ap hold rows [row_begin, row_begin + n_rows) and must cover every
+// frame a pulse touching the sample range interpolates between; d_out addresses sample `sample_begin`.
+int wb_synthesis_render_range(WbWorkspace *ws, int fs, int fft_size, double frame_period_ms, int f0_length,
+                              const double *d_sp, const double *d_ap, int row_begin, int n_rows, int out_length,
+                              int sample_begin, int sample_end, double *d_out, double f0_upper_bound,
+                              const WbRngCursor &rng, cudaStream_t stream);
 int wb_synthesis_run(WbWorkspace *ws, int fs, int fft_size, double frame_period_ms, const double *d_f0,
                      int f0_length, const double *d_sp, const double *d_ap, int out_length, double *d_out,
                      double f0_upper_bound, const WbRngCursor &rng, cudaStream_t stream);

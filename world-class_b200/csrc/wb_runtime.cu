@@ -144,6 +144,30 @@ WbLaunchScope::~WbLaunchScope() {
   }
 }
 
+namespace {
+__global__ void range_offsets_kernel(const unsigned long long *__restrict__ offsets, int begin, int end,
+                                     unsigned long long *__restrict__ rel, const unsigned long long *__restrict__ skip_in,
+                                     unsigned long long *__restrict__ skip_range, unsigned long long *__restrict__ count_range) {
+  const unsigned long long base = offsets[begin];
+  const int i = begin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= end) rel[i] = offsets[i] - base;
+  if (i == begin) {
+    *skip_range = (skip_in ? *skip_in : 0ull) + base;
+    *count_range = offsets[end] - base;
+  }
+}
+}  // namespace
+
+int wb_range_offsets(const unsigned long long *d_offsets, WbFrameRange range, unsigned long long *d_rel,
+                     const unsigned long long *d_skip_in, unsigned long long *d_skip_range,
+                     unsigned long long *d_count_range, cudaStream_t stream) {
+  const int n = range.end - range.begin + 1;
+  WB_LAUNCH("range_offsets_kernel", range_offsets_kernel<<<(n + 255) / 256, 256, 0, stream>>>(
+      d_offsets, range.begin, range.end, d_rel, d_skip_in, d_skip_range, d_count_range));
+  WB_CUDA_CHECK(cudaGetLastError());
+  return WB_OK;
+}
+
 unsigned long long wb_launch_counter() { return g_launches.load(); }
 void wb_launch_counter_add(unsigned long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int wb_prof_is_enabled() { return g_prof_on.load(std::memory_order_relaxed); }

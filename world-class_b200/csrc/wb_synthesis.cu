@@ -294,7 +294,41 @@ struct RespParams {
   double *response;              // [max_resp_pulses][fft_size]
   int max_resp_pulses;
   int *error_flag;
+  // sharded streams (wb_synthesis_render_range): pulses [range[0], range[1]) only, noise[0] is the draw of
+  // sample index range[2], sp / ap address frame `row_begin`; null = every pulse
+  const int *range;
+  int row_begin;
 };
+
+// pulses whose response overlaps samples [sample_begin, sample_end), and the share of the noise stream
+// they read: range = {first pulse, one past the last, sample index of the first pulse}; *noise_skip /
+// *noise_count position the randn() fill
+__global__ void pulse_range_kernel(const int *__restrict__ pulse_index, const int *__restrict__ n_pulses, int fft_size,
+                                   int sample_begin, int sample_end, const unsigned long long *__restrict__ skip_in,
+                                   int *__restrict__ range, unsigned long long *__restrict__ noise_skip,
+                                   unsigned long long *__restrict__ noise_count) {
+  const int P = *n_pulses, half = fft_size / 2;
+  // a pulse at idx covers samples (idx - half, idx - half + fft_size]: wanted are idx > sample_begin + half - 1 - fft_size
+  // and idx <= sample_end - 1 + half - 1 (see ola_kernel)
+  auto first_above = [&](int v) {   // first pulse with idx > v
+    int lo = 0, hi = P;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (pulse_index[mid] > v) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+  };
+  const int p_lo = first_above(sample_begin + half - 1 - fft_size);
+  const int p_hi = first_above(sample_end - 1 + half - 1);
+  range[0] = p_lo;
+  range[1] = p_hi;
+  if (P == 0 || p_lo >= p_hi) { range[2] = 0; *noise_skip = skip_in ? *skip_in : 0ull; *noise_count = 0ull; return; }
+  const int idx_lo = pulse_index[p_lo];
+  const int idx_end = pulse_index[p_hi < P ? p_hi : P - 1];   // the last pulse of the stream draws nothing (Q11)
+  range[2] = idx_lo;
+  *noise_skip = (skip_in ? *skip_in : 0ull) + (unsigned long long)(idx_lo - pulse_index[0]);
+  *noise_count = (unsigned long long)(idx_end - idx_lo);
+}
 
 // MinimumPhaseAnalysis::compute (world_common.cpp:192-233).  On entry the packed real view W of
 // S holds log_spectrum[0..NC] (this function mirrors it); on exit MP[k], k = 0..NC, holds the
@@ -336,13 +370,14 @@ __global__ void __launch_bounds__(256, 3) response_kernel(RespParams p) {
   double *W = reinterpret_cast<double *>(S);
   const int tid = threadIdx.x, nt = blockDim.x;
   const int P = *p.n_pulses;
-  if (P > p.max_resp_pulses) {  // f0 exceeded the caller's bound: refuse rather than overrun
+  const int p_lo = p.range ? p.range[0] : 0, p_hi = p.range ? p.range[1] : P;
+  if (p_hi - p_lo > p.max_resp_pulses) {  // f0 exceeded the caller's bound: refuse rather than overrun
     if (tid == 0 && blockIdx.x == 0) atomicExch(p.error_flag, WB_ERR_ARG);
     return;
   }
 
-  for (int pulse = blockIdx.x; pulse < P; pulse += gridDim.x) {
-    double *resp = p.response + (size_t)pulse * N;
+  for (int pulse = p_lo + blockIdx.x; pulse < p_hi; pulse += gridDim.x) {
+    double *resp = p.response + (size_t)(pulse - p_lo) * N;
     const int idx = p.pulse_index[pulse];
     const int idx_next = p.pulse_index[wb_min_i(P - 1, pulse + 1)];
     const int noise_size = idx_next - idx;
@@ -359,8 +394,8 @@ __global__ void __launch_bounds__(256, 3) response_kernel(RespParams p) {
     const int fl = wb_min_i(p.f0_length - 1, (int)floor(tf));
     const int cl = wb_min_i(p.f0_length - 1, (int)ceil(tf));
     const double interp = tf - fl;
-    const double *sp_f = p.sp + (size_t)fl * bins, *sp_c = p.sp + (size_t)cl * bins;
-    const double *ap_f = p.ap + (size_t)fl * bins, *ap_c = p.ap + (size_t)cl * bins;
+    const double *sp_f = p.sp + (size_t)(fl - p.row_begin) * bins, *sp_c = p.sp + (size_t)(cl - p.row_begin) * bins;
+    const double *ap_f = p.ap + (size_t)(fl - p.row_begin) * bins, *ap_c = p.ap + (size_t)(cl - p.row_begin) * bins;
     for (int k = tid; k < bins; k += nt) {
       double se, ar;
       const double af = fmax(0.001, fmin(0.999999999999, ap_f[k]));
@@ -410,7 +445,7 @@ __global__ void __launch_bounds__(256, 3) response_kernel(RespParams p) {
     {
       // minimum phase of the aperiodic envelope first, then the noise spectrum is multiplied into it bin by
       // bin as the transform emits it (no separate noise-spectrum buffer)
-      const double *nz = p.noise + (idx - p.pulse_index[0]);
+      const double *nz = p.noise + (idx - (p.range ? p.range[2] : p.pulse_index[0]));
       if (current_vuv != 0.0) {
         for (int k = tid; k < bins; k += nt) W[wb_didx(k)] = log(SE[k] * AR[k]) / 2.0;
       } else {
@@ -442,13 +477,17 @@ __global__ void __launch_bounds__(256, 3) response_kernel(RespParams p) {
 // ---- K6: deterministic overlap-add (synthesis.cpp:118-139) -------------------------------------
 // out[n] = sum over pulses (in pulse order, like the serial reference) of
 // response[p][n - (idx_p - N/2 + 1)].
+// Sharded streams: samples [sample_begin, sample_end) only, out[0] is sample_begin and response[0] belongs to
+// pulse range[0] (null = the whole waveform).
 __global__ void ola_kernel(const double *__restrict__ response, const int *__restrict__ pulse_index,
                            const int *__restrict__ n_pulses, int max_resp_pulses, int fft_size, int out_length,
-                           double *__restrict__ out) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= out_length) return;
+                           double *__restrict__ out, int sample_begin, int sample_end, const int *__restrict__ range) {
+  const int n = sample_begin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= sample_end) return;
+  out += -sample_begin;
   const int P = *n_pulses;
-  if (P > max_resp_pulses) { out[n] = 0.0; return; }
+  const int p_first = range ? range[0] : 0;
+  if ((range ? range[1] - range[0] : P) > max_resp_pulses) { out[n] = 0.0; return; }
   const int half = fft_size / 2;
   // pulses with 0 <= n - (idx - half + 1) < fft_size  <=>  n - half - ... :
   // idx in [n + half + 1 - fft_size, n + half - 1 + 1 - 0] -> idx >= n - half + 1 ... derive:
@@ -469,7 +508,7 @@ __global__ void ola_kernel(const double *__restrict__ response, const int *__res
     // the reference skips pulses with index + fft_size < 0 or index + 1 >= out_length entirely
     if (index + fft_size < 0 || index + 1 >= out_length) continue;
     const int j = n - index - 1;
-    acc += response[(size_t)q * fft_size + j];
+    acc += response[(size_t)(q - p_first) * fft_size + j];
   }
   out[n] = acc;
 }
@@ -601,6 +640,7 @@ int wb_synthesis_render(WbWorkspace *ws, int fs, int fft_size, double frame_peri
   const size_t smem = sizeof(cplx) * (wb_fft_slots(fft_size) + binsp) + sizeof(double) * (2 * binsp + 128);
   p.max_resp_pulses = resp_pulses;
   p.error_flag = ws->error_flag();
+  p.range = nullptr; p.row_begin = 0;
   const int grid = wb_min_i(resp_pulses, 148 * 9);
   rc = WB_DISPATCH_LOG2(log2n, 8, 13, {
     if (cudaFuncSetAttribute(response_kernel<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WB_ERR_CUDA;
@@ -608,9 +648,97 @@ int wb_synthesis_render(WbWorkspace *ws, int fs, int fft_size, double frame_peri
   });
   if (rc) return rc;
   WB_CUDA_CHECK(cudaGetLastError());
-  WB_LAUNCH("ola_kernel", ola_kernel<<<(out_length + 255) / 256, 256, 0, stream>>>(d_resp, d_pidx, d_np, resp_pulses, fft_size, out_length, d_out));
+  WB_LAUNCH("ola_kernel", ola_kernel<<<(out_length + 255) / 256, 256, 0, stream>>>(d_resp, d_pidx, d_np, resp_pulses, fft_size, out_length, d_out,
+                                                                                  0, out_length, nullptr));
   WB_CUDA_CHECK(cudaGetLastError());
   // (skip_out is not published: Synthesis is the last consumer of the stream in the chain)
+  return rng.advance ? wb_rng_advance(rng.state, d_ncount, rng.skip_in, stream) : WB_OK;
+}
+
+static int upload_dc_remover(WbWorkspace *ws, int fft_size, double **out, cudaStream_t stream) {
+  double *d_dcr = (double *)ws->get("syn_dcr", sizeof(double) * fft_size);
+  int *tag = (int *)ws->get_pinned("syn_dcr_tag", sizeof(int) * 4);
+  if (!d_dcr || !tag) return WB_ERR_CUDA;
+  const long long tag_ptr = (long long)(size_t)d_dcr;
+  if (tag[0] != fft_size || tag[1] != (int)(tag_ptr & 0x7fffffff) || tag[2] != (int)(tag_ptr >> 31)) {
+    double *h = (double *)ws->get_pinned("syn_dcr_h", sizeof(double) * fft_size);
+    if (!h) return WB_ERR_CUDA;
+    std::vector<double> r;
+    make_dc_remover(fft_size, r);
+    for (int i = 0; i < fft_size; ++i) h[i] = r[i];
+    WB_CUDA_CHECK(cudaMemcpyAsync(d_dcr, h, sizeof(double) * fft_size, cudaMemcpyHostToDevice, stream));
+    tag[0] = fft_size; tag[1] = (int)(tag_ptr & 0x7fffffff); tag[2] = (int)(tag_ptr >> 31);
+  }
+  *out = d_dcr;
+  return WB_OK;
+}
+
+// One rank's share of a long stream: the time base and the pulse list of the WHOLE
+// stream are on `ws` (every rank computes them from the gathered f0: they are cheap and sequential); this
+// renders the pulses that reach into [sample_begin, sample_end) with their whole-stream noise positions and
+// overlap-adds them in the reference's order, so the samples equal those of an unsharded run bit for bit.
+int wb_synthesis_render_range(WbWorkspace *ws, int fs, int fft_size, double frame_period_ms, int f0_length,
+                              const double *d_sp, const double *d_ap, int row_begin, int n_rows, int out_length,
+                              int sample_begin, int sample_end, double *d_out, double f0_upper_bound,
+                              const WbRngCursor &rng, cudaStream_t stream) {
+  if (out_length <= 0) return WB_OK;
+  if (sample_begin < 0 || sample_end > out_length || sample_begin > sample_end || row_begin < 0 || n_rows < 0 ||
+      row_begin + n_rows > f0_length || !(f0_upper_bound > 0.0))
+    return WB_ERR_ARG;
+  int log2n = 0;
+  while ((1 << log2n) < fft_size) ++log2n;
+  if ((1 << log2n) != fft_size || fft_size < 128 || fft_size > 8192) return WB_ERR_UNSUPPORTED;
+  const double frame_period = frame_period_ms / 1000.;
+  const int n_samples = sample_end - sample_begin;
+  unsigned char *d_vuv = (unsigned char *)ws->get("syn_vuv", 0);
+  int *d_pidx = (int *)ws->get("syn_pidx", 0);
+  double *d_pshift = (double *)ws->get("syn_pshift", 0);
+  int *d_np = (int *)ws->get("syn_np", 0);
+  unsigned long long *d_ncount = (unsigned long long *)ws->get("syn_ncount", 0);
+  // The pulses of the range sit in a window of n_samples + fft_size samples, and the noise of the last one
+  // runs up to the next pulse: a voiced sample has f0 > lowest_f0 / 2 (interpolation towards an unvoiced
+  // frame, synthesis.cpp:225-243), so pulses are less than 2 fs / lowest_f0 < 2 fft_size samples apart.
+  const int span = n_samples + 3 * fft_size + 8;
+  double *d_noise = (double *)ws->get("noise_syn_range", sizeof(double) * (size_t)span);
+  int *d_range = (int *)ws->get("syn_range", sizeof(int) * 4);
+  unsigned long long *d_npos = (unsigned long long *)ws->get("syn_range_pos", sizeof(unsigned long long) * 2);
+  double *d_dcr = nullptr;
+  int rc = upload_dc_remover(ws, fft_size, &d_dcr, stream);
+  if (rc) return rc;
+  if (!d_vuv || !d_pidx || !d_pshift || !d_np || !d_ncount || !d_noise || !d_range || !d_npos) return WB_ERR_CUDA;
+  const cplx *tw_n = wb_twiddle_table(fft_size);
+  const cplx *tw_2n = wb_twiddle_table(2 * fft_size);
+  if (!tw_n || !tw_2n) return WB_ERR_CUDA;
+  if (rng.wait_skip_in) WB_CUDA_CHECK(cudaStreamWaitEvent(stream, rng.wait_skip_in, 0));
+  WB_LAUNCH("pulse_range_kernel", pulse_range_kernel<<<1, 1, 0, stream>>>(d_pidx, d_np, fft_size, sample_begin, sample_end, rng.skip_in,
+                                                                     d_range, d_npos, d_npos + 1));
+  WB_CUDA_CHECK(cudaGetLastError());
+  if (n_samples > 0) {
+    if ((rc = wb_rng_fill(rng.state, d_npos, d_npos + 1, (unsigned long long)span, d_noise, stream))) return rc;
+    const double fmax = f0_upper_bound > WB_DEFAULT_F0 ? f0_upper_bound : WB_DEFAULT_F0;
+    const int resp_pulses = (int)((double)span * fmax / fs + 4.0);
+    double *d_resp = (double *)ws->get("syn_resp", sizeof(double) * (size_t)resp_pulses * fft_size);
+    if (!d_resp) return WB_ERR_CUDA;
+    RespParams p;
+    p.sp = d_sp; p.ap = d_ap; p.f0_length = f0_length; p.fs = fs; p.fft_size = fft_size; p.log2n = log2n;
+    p.frame_period = frame_period; p.pulse_index = d_pidx; p.pulse_shift = d_pshift; p.vuv = d_vuv;
+    p.n_pulses = d_np; p.noise = d_noise; p.dc_remover = d_dcr; p.tw_n = tw_n; p.tw_2n = tw_2n; p.response = d_resp;
+    const int binsp = ((fft_size / 2 + 1) + 1) & ~1;
+    const size_t smem = sizeof(cplx) * (wb_fft_slots(fft_size) + binsp) + sizeof(double) * (2 * binsp + 128);
+    p.max_resp_pulses = resp_pulses;
+    p.error_flag = ws->error_flag();
+    p.range = d_range; p.row_begin = row_begin;
+    const int grid = wb_min_i(resp_pulses, 148 * 9);
+    rc = WB_DISPATCH_LOG2(log2n, 8, 13, {
+      if (cudaFuncSetAttribute(response_kernel<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WB_ERR_CUDA;
+      WB_LAUNCH("response_kernel", response_kernel<L2><<<grid, 256, smem, stream>>>(p));
+    });
+    if (rc) return rc;
+    WB_CUDA_CHECK(cudaGetLastError());
+    WB_LAUNCH("ola_kernel", ola_kernel<<<(n_samples + 255) / 256, 256, 0, stream>>>(d_resp, d_pidx, d_np, resp_pulses, fft_size, out_length, d_out,
+                                                                                   sample_begin, sample_end, d_range));
+    WB_CUDA_CHECK(cudaGetLastError());
+  }
   return rng.advance ? wb_rng_advance(rng.state, d_ncount, rng.skip_in, stream) : WB_OK;
 }
 

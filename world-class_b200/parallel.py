@@ -100,3 +100,247 @@ def process_batch(items, process_item, group=None):
     rank = dist.get_rank(group) if distributed else 0
     world = dist.get_world_size(group) if distributed else 1
     return {i: process_item(items[i]) for i in shard_indices(len(items), rank, world)}
+
+
+# ---- exact sharding of one long stream (BASELINE configs[3]) -----------------------
+#
+# process_stream() above treats segments as independent utterances (fresh randn() stream each): simple, but
+# the stitched result is not what ONE reference process would produce for the whole stream.  The functions
+# below shard the same work so that it IS: every rank
+#   1. runs Harvest on its share of the stream (sub-segments with a halo, aligned so that the decimation phase
+#      and the 1 ms analysis grid coincide with those of the whole stream) and ONE all-gather assembles the
+#      whole f0 contour;
+#   2. recomputes the cheap sequential parts for the whole stream (randn() positions = prefix sums of the
+#      per-frame draw counts, the phase sum that places the pulses) and computes CheapTrick / Love Train for
+#      its own frame rows only;
+#   3. a second small all-gather exchanges the Love Train decisions (they decide how many randn() draws the
+#      D4C body of every EARLIER frame consumed), then D4C and Synthesis run on the rank's rows / samples with
+#      whole-stream randn positions -- bit-identical to an unsharded run given the same f0;
+#   4. one all-gather stitches the waveform.
+# The collectives are torch.distributed's (NCCL on GPUs, gloo in the CPU tests); the compute is the C-ABI's
+# wb_pipeline_stream_* entry points.
+
+
+def decimation_ratio(fs, target_fs=8000.0):
+    """Harvest's decimation ratio (src/harvest.cpp:81-82)."""
+    r = int(fs / target_fs + 0.5)          # matlab_round of a positive number
+    return max(1, min(12, r))
+
+
+class StreamPlan:
+    """Pure planning (no GPU): who owns which frames / samples of a stream of n_samples at fs, and which
+    padded Harvest segments reproduce the whole-stream analysis grid.
+
+    Rank boundaries and segment cuts fall on whole seconds, so that with 1000 / frame_period integer every
+    segment's local frame j is the stream's frame j + offset at exactly the same time, and the padded end of
+    a segment is congruent to n_samples modulo the decimation ratio, which gives the segment the
+    whole-stream decimation phase (decimate() starts at x_length % r - 1, world_matlabfunctions.cpp:201-206)."""
+
+    def __init__(self, n_samples, fs, world, frame_period=5.0, fft_size=2048, segment_seconds=30, halo_seconds=2,
+                 target_fs=8000.0):
+        fps = 1000.0 / frame_period
+        if abs(fps - round(fps)) > 1e-9:
+            raise ValueError("exact stream sharding needs 1000 / frame_period to be an integer")
+        self.n, self.fs, self.world, self.fp, self.fft_size = int(n_samples), int(fs), int(world), float(frame_period), int(fft_size)
+        self.fps = int(round(fps))
+        self.r = decimation_ratio(fs, target_fs)
+        if self.fs % self.r:
+            raise ValueError("exact stream sharding needs fs to be a multiple of the decimation ratio")
+        self.f0_length = int(1000.0 * self.n / self.fs / self.fp) + 1                    # harvest.cpp:173-176
+        self.out_length = int((self.f0_length - 1) * self.fp / 1000.0 * self.fs) + 1     # test/test.cpp:362-363
+        seconds = -(-self.n // self.fs)                                                   # ceil
+        seg, halo = max(1, int(segment_seconds)), max(1, int(halo_seconds))
+        # rank r owns seconds [cut[r], cut[r + 1])
+        self.cut = [(seconds * k) // self.world for k in range(self.world + 1)]
+        self.segments = []      # per rank: list of dict(core frames, padded samples, frame offset)
+        self.frames = []        # per rank: (frame_begin, frame_end) of the rows it owns
+        for k in range(self.world):
+            s0, s1 = self.cut[k], self.cut[k + 1]
+            fb = min(self.f0_length, s0 * self.fps)
+            fe = self.f0_length if k == self.world - 1 else min(self.f0_length, s1 * self.fps)
+            self.frames.append((fb, fe))
+            segs = []
+            a = s0
+            while a < s1:
+                b = min(s1, a + seg)
+                pa = max(0, a - halo) * self.fs
+                pb = min(self.n, (b + halo) * self.fs)
+                pb -= (pb - self.n) % self.r                  # whole-stream decimation phase
+                cfb = a * self.fps
+                cfe = self.f0_length if (k == self.world - 1 and b == s1) else min(self.f0_length, b * self.fps)
+                if cfe > cfb:
+                    segs.append({"padded": (pa, pb), "frames": (cfb, cfe), "frame_offset": (pa // self.fs) * self.fps})
+                a = b
+            self.segments.append(segs)
+        # samples: any partition works; cut where the rank's first frame starts
+        cuts = [0] + [min(self.out_length, int(self.frames[k][0] * self.fp / 1000.0 * self.fs)) for k in range(1, self.world)] + [self.out_length]
+        self.samples = [(cuts[k], cuts[k + 1]) for k in range(self.world)]
+        # rows (frames) a rank needs for its samples: every frame a pulse reaching into them interpolates between
+        self.rows = []
+        for k in range(self.world):
+            sa, sb = self.samples[k]
+            fb, fe = self.frames[k]
+            lo = int(max(0, sa - self.fft_size) / self.fs * self.fps) - 1
+            hi = int((sb + self.fft_size) / self.fs * self.fps) + 3
+            self.rows.append((max(0, min(fb, lo)), min(self.f0_length, max(fe, hi))))
+
+
+def gather_ranges(local, ranges, total, group=None, device=None):
+    """Assembles a 1-D float64 array of `total` entries from per-rank contiguous pieces (`local` is this
+    rank's piece, ranges[k] = (begin, end) of rank k) with ONE all-gather.  torch tensors in / out."""
+    import torch
+    import torch.distributed as dist
+    world = len(ranges)
+    if world == 1 or not (dist.is_available() and dist.is_initialized()):
+        assert len(local) == total
+        return local
+    rank = dist.get_rank(group)
+    width = max(e - b for b, e in ranges)
+    mine = torch.zeros(width, dtype=local.dtype, device=local.device)
+    mine[:len(local)] = local
+    gathered = torch.empty((world, width), dtype=local.dtype, device=local.device)
+    if dist.get_backend(group) == "nccl":
+        dist.all_gather_into_tensor(gathered.view(-1), mine, group=group)
+    else:
+        dist.all_gather([gathered[k] for k in range(world)], mine, group=group)
+    out = torch.empty(total, dtype=local.dtype, device=local.device)
+    for k, (b, e) in enumerate(ranges):
+        out[b:e] = gathered[k, :e - b]
+    assert ranges[rank][1] - ranges[rank][0] == len(local)
+    return out
+
+
+class StreamWorker:
+    """One rank's share of an exactly sharded stream on its GPU (torch CUDA tensors, C-ABI calls)."""
+
+    def __init__(self, plan, rank, harvest_option=None, cheaptrick_option=None, d4c_option=None):
+        import torch
+        import worldb200 as wb
+        self.wb, self.torch, self.plan, self.rank = wb, torch, plan, rank
+        self.harvest_option = harvest_option if harvest_option is not None else wb.HarvestOption()
+        assert abs(self.harvest_option.frame_period - plan.fp) < 1e-12
+        self.pipe = wb.Pipeline(plan.fs, self.harvest_option, cheaptrick_option, d4c_option)
+        self.pipe.set_fresh_rng(True)                       # the stream is one reference process
+        assert self.pipe.fft_size == plan.fft_size, "plan was made for another FFT size"
+        self.harvest = wb.Harvest(plan.fs, self.harvest_option)
+        self.bins = plan.fft_size // 2 + 1
+
+    def harvest_local(self, d_x):
+        """f0 of the frames this rank owns (whole-stream frame grid)."""
+        torch, L = self.torch, self.wb.lib()
+        fb, fe = self.plan.frames[self.rank]
+        out = torch.zeros(fe - fb, dtype=torch.float64, device=d_x.device)
+        for seg in self.plan.segments[self.rank]:
+            pa, pb = seg["padded"]
+            n = pb - pa
+            n_local = self.harvest.getSamples(self.plan.fs, n)
+            d_t = torch.empty(n_local, dtype=torch.float64, device=d_x.device)
+            d_f = torch.empty(n_local, dtype=torch.float64, device=d_x.device)
+            self.wb._check(L.wb_harvest_compute_dev(self.harvest._h, d_x.data_ptr() + 8 * pa, n, d_t.data_ptr(), d_f.data_ptr(), None),
+                           "wb_harvest_compute_dev")
+            self.wb.device_synchronize()
+            cfb, cfe = seg["frames"]
+            off = seg["frame_offset"]
+            out[cfb - fb:cfe - fb] = d_f[cfb - off:cfe - off]
+        return out
+
+    def begin(self, d_f0_all):
+        self.d_f0_all = d_f0_all
+        self.wb._check(self.wb.lib().wb_pipeline_stream_begin_dev(self.pipe._h, d_f0_all.data_ptr(), self.plan.f0_length,
+                                                                  self.plan.out_length, None), "wb_pipeline_stream_begin_dev")
+
+    def envelope(self, d_x, d_ap0_all):
+        """CheapTrick + Love Train for the rows this rank needs; writes its entries of d_ap0_all."""
+        torch = self.torch
+        ra, rb = self.plan.rows[self.rank]
+        self.d_sp = torch.empty((rb - ra, self.bins), dtype=torch.float64, device=d_x.device)
+        self.wb._check(self.wb.lib().wb_pipeline_stream_envelope_dev(self.pipe._h, d_x.data_ptr(), self.plan.n, self.d_f0_all.data_ptr(),
+                                                                     self.plan.f0_length, ra, rb, self.d_sp.data_ptr(),
+                                                                     d_ap0_all.data_ptr(), None), "wb_pipeline_stream_envelope_dev")
+        self.wb.device_synchronize()
+
+    def aperiodicity(self, d_x, d_ap0_all):
+        torch = self.torch
+        ra, rb = self.plan.rows[self.rank]
+        self.d_ap = torch.empty((rb - ra, self.bins), dtype=torch.float64, device=d_x.device)
+        self.wb._check(self.wb.lib().wb_pipeline_stream_aperiodicity_dev(self.pipe._h, d_x.data_ptr(), self.plan.n, self.d_f0_all.data_ptr(),
+                                                                         d_ap0_all.data_ptr(), self.plan.f0_length, ra, rb,
+                                                                         self.d_ap.data_ptr(), None), "wb_pipeline_stream_aperiodicity_dev")
+        self.wb.device_synchronize()
+
+    def synthesis(self):
+        torch = self.torch
+        ra, rb = self.plan.rows[self.rank]
+        sa, sb = self.plan.samples[self.rank]
+        d_y = torch.zeros(max(1, sb - sa), dtype=torch.float64, device=self.d_sp.device)
+        self.wb._check(self.wb.lib().wb_pipeline_stream_synthesis_dev(self.pipe._h, self.plan.f0_length, self.d_sp.data_ptr(),
+                                                                      self.d_ap.data_ptr(), ra, rb - ra, self.plan.out_length, sa, sb,
+                                                                      d_y.data_ptr(), None), "wb_pipeline_stream_synthesis_dev")
+        self.wb.device_synchronize()
+        return d_y[:sb - sa]
+
+    def owned_rows(self, d_rows):
+        """the rows of d_sp / d_ap this rank owns (without the halo rows it computed for its pulses)"""
+        ra, _ = self.plan.rows[self.rank]
+        fb, fe = self.plan.frames[self.rank]
+        return d_rows[fb - ra:fe - ra]
+
+
+def process_stream_exact(d_x, fs, harvest_option=None, cheaptrick_option=None, d4c_option=None, segment_seconds=30,
+                         halo_seconds=2, group=None, d_f0_all=None):
+    """Analysis + re-synthesis of one long stream (a float64 CUDA tensor every rank holds) sharded over the
+    ranks of `group`.  Returns dict(f0 [whole], y [whole], sp, ap [this rank's rows], frames, worker).
+    Pass d_f0_all to skip Harvest (e.g. a contour computed elsewhere)."""
+    import torch
+    import torch.distributed as dist
+    import worldb200 as wb
+    distributed = dist.is_available() and dist.is_initialized()
+    rank = dist.get_rank(group) if distributed else 0
+    world = dist.get_world_size(group) if distributed else 1
+    hopt = harvest_option if harvest_option is not None else wb.HarvestOption()
+    copt = cheaptrick_option if cheaptrick_option is not None else wb.CheapTrickOption()
+    fft_size = copt.fft_size if copt.fft_size else wb.CheapTrick.getFFTSizeForCheapTrick(fs, copt.f0_floor)
+    plan = StreamPlan(d_x.numel(), fs, world, hopt.frame_period, fft_size, segment_seconds, halo_seconds, hopt.target_fs)
+    w = StreamWorker(plan, rank, hopt, cheaptrick_option, d4c_option)
+    if d_f0_all is None:
+        d_f0_all = gather_ranges(w.harvest_local(d_x), plan.frames, plan.f0_length, group)      # exchange 1
+    w.begin(d_f0_all)
+    d_ap0 = torch.zeros(plan.f0_length, dtype=torch.float64, device=d_x.device)
+    w.envelope(d_x, d_ap0)
+    fb, fe = plan.frames[rank]
+    d_ap0 = gather_ranges(d_ap0[fb:fe].clone(), plan.frames, plan.f0_length, group)              # exchange 2
+    w.aperiodicity(d_x, d_ap0)
+    d_y = gather_ranges(w.synthesis(), plan.samples, plan.out_length, group)                    # exchange 3 (stitch)
+    return {"f0": d_f0_all, "y": d_y, "sp": w.owned_rows(w.d_sp), "ap": w.owned_rows(w.d_ap), "frames": (fb, fe),
+            "worker": w, "plan": plan}
+
+
+def simulate_stream_ranks(d_x, fs, world, harvest_option=None, cheaptrick_option=None, d4c_option=None, segment_seconds=30,
+                          halo_seconds=2, d_f0_all=None):
+    """The same computation as process_stream_exact() with `world` VIRTUAL ranks run one after the other in
+    this process (one worker object each, as separate processes would have); the exchanges become plain
+    concatenations.  Used by the single-GPU tests."""
+    import torch
+    import worldb200 as wb
+    hopt = harvest_option if harvest_option is not None else wb.HarvestOption()
+    copt = cheaptrick_option if cheaptrick_option is not None else wb.CheapTrickOption()
+    fft_size = copt.fft_size if copt.fft_size else wb.CheapTrick.getFFTSizeForCheapTrick(fs, copt.f0_floor)
+    plan = StreamPlan(d_x.numel(), fs, world, hopt.frame_period, fft_size, segment_seconds, halo_seconds, hopt.target_fs)
+    workers = [StreamWorker(plan, k, hopt, cheaptrick_option, d4c_option) for k in range(world)]
+    if d_f0_all is None:
+        d_f0_all = torch.cat([w.harvest_local(d_x) for w in workers])
+    assert d_f0_all.numel() == plan.f0_length
+    d_ap0 = torch.zeros(plan.f0_length, dtype=torch.float64, device=d_x.device)
+    pieces = []
+    for w in workers:
+        w.begin(d_f0_all)
+        mine = torch.zeros_like(d_ap0)
+        w.envelope(d_x, mine)
+        fb, fe = plan.frames[w.rank]
+        pieces.append(mine[fb:fe])
+    d_ap0 = torch.cat(pieces)
+    for w in workers:
+        w.aperiodicity(d_x, d_ap0)
+    d_y = torch.cat([w.synthesis() for w in workers])
+    return {"f0": d_f0_all, "y": d_y, "sp": torch.cat([w.owned_rows(w.d_sp) for w in workers]),
+            "ap": torch.cat([w.owned_rows(w.d_ap) for w in workers]), "ap0": d_ap0, "plan": plan}
