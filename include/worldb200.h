@@ -199,7 +199,8 @@ int wb_pipeline_run_f32(wb_pipeline_t *p, const double *x, int x_length, float *
  * rank -- they are cheap functions of f0 -- so the rows / samples of a range are bit-identical to those of an
  * unsharded run.  Device pointers; asynchronous on `stream`; d_f0_all / d_ap0_all hold f0_length entries;
  * *_rows address the first row of the range ([rows][fft_size/2+1], contiguous).  Per rank, in this order:
- *   begin; envelope (writes d_ap0_all[frame_begin, frame_end)); [all-gather d_ap0_all]; aperiodicity; synthesis.
+ *   begin; envelope (writes d_ap0_all[frame_begin, frame_end)); [all-gather d_ap0_all]; aperiodicity; synthesis; end
+ * (envelope / aperiodicity / synthesis may be repeated for several ranges in between).
  * The sp / ap rows given to synthesis must cover every frame a pulse reaching into the sample range
  * interpolates between: frames floor((sample_begin - fft_size) / fs / frame_period) .. ceil((sample_end +
  * fft_size) / fs / frame_period), clipped to the stream. */
@@ -213,6 +214,8 @@ int wb_pipeline_stream_aperiodicity_dev(wb_pipeline_t *p, const double *d_x, int
 int wb_pipeline_stream_synthesis_dev(wb_pipeline_t *p, int f0_length, const double *d_sp_rows, const double *d_ap_rows,
                                      int row_begin, int n_rows, int out_length, int sample_begin, int sample_end,
                                      double *d_out, void *stream);
+/* after the last range: leaves the randn() state where one reference process would have left it */
+int wb_pipeline_stream_end_dev(wb_pipeline_t *p, void *stream);
 
 /* test / bench hook: copies n_bytes of a named internal device buffer of the last run to `out` */
 int wb_pipeline_debug_read(wb_pipeline_t *p, const char *name, void *out, unsigned long long n_bytes);

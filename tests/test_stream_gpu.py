@@ -68,3 +68,25 @@ def test_sharded_harvest_matches_the_whole_stream_contour_48k(wb, signals):
     assert len(got) == len(f0) and np.array_equal(got > 0, f0 > 0)
     v = f0 > 0
     assert np.max(np.abs(got[v] - f0[v]) / f0[v]) < 1e-9
+
+
+def test_single_process_driver_with_several_shards(wb, signals):
+    """process_stream_exact() without torch.distributed, the rank's share cut into 3 shards (bounded scratch):
+    same bits as the unsharded run given the same f0, and all three exchange steps degenerate gracefully."""
+    import torch
+    from worldb200 import parallel
+    fs = 16000
+    x = signals.synth_speech(fs, 6.0, seed=34)
+    hopt, copt, dopt = _options(wb)
+    whole = wb.Pipeline(fs, hopt, copt, dopt)
+    whole.set_fresh_rng(True)
+    ref = whole.run(x)
+    t = {}
+    out = parallel.process_stream_exact(torch.from_numpy(x).cuda(), fs, hopt, copt, dopt, segment_seconds=2, halo_seconds=2,
+                                        d_f0_all=torch.from_numpy(ref["f0"]).cuda(), shards_per_rank=3, timings=t)
+    assert np.array_equal(out["y"].cpu().numpy(), ref["y"]) and np.array_equal(out["sp"].cpu().numpy(), ref["sp"])
+    assert np.array_equal(out["ap"].cpu().numpy(), ref["ap"]) and t["total"] > 0
+    # and with its own (sharded) Harvest: decisions identical to the whole-stream contour
+    out2 = parallel.process_stream_exact(torch.from_numpy(x).cuda(), fs, hopt, copt, dopt, segment_seconds=2, halo_seconds=2, shards_per_rank=2)
+    f0 = out2["f0"].cpu().numpy()
+    assert np.array_equal(f0 > 0, ref["f0"] > 0) and np.max(np.abs(f0 - ref["f0"])) < 1e-7

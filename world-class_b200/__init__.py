@@ -114,6 +114,7 @@ def _declare(L):
         "wb_pipeline_stream_envelope_dev": (ci, [vp, vp, ci, vp, ci, ci, ci, vp, vp, vp]),
         "wb_pipeline_stream_aperiodicity_dev": (ci, [vp, vp, ci, vp, vp, ci, ci, ci, vp, vp]),
         "wb_pipeline_stream_synthesis_dev": (ci, [vp, ci, vp, vp, ci, ci, ci, ci, ci, vp, vp]),
+        "wb_pipeline_stream_end_dev": (ci, [vp, vp]),
         "wb_pipeline_run_pcm16": (ci, [vp, vp, ci, vp, ci]),
         "wb_pipeline_run_f32": (ci, [vp, vp, ci, vp, vp, vp, vp, ci]),
         "wb_pcm16_to_f64_dev": (ci, [vp, ci, vp, vp]),

@@ -1056,10 +1056,21 @@ int wb_pipeline_stream_synthesis_dev(wb_pipeline_t *p, int f0_length, const doub
   WbRngState *rng = p->private_rng ? p->d_rng_private : wb_rng_global_state();
   WB_CUDA_CHECK(cudaStreamWaitEvent(stream, p->ev_tb, 0));
   WbRngCursor c;
-  c.state = rng; c.skip_in = rng_pos + 1; c.advance = true;   // moves the state past the whole stream's draws
+  c.state = rng; c.skip_in = rng_pos + 1; c.advance = false;  // (several ranges may follow: wb_pipeline_stream_end_dev moves the state)
   return wb_synthesis_render_range(&p->ws, p->fs, p->ct.fft_size, p->plan.opt.frame_period, f0_length, d_sp_rows, d_ap_rows,
                                    row_begin, n_rows, out_length, sample_begin, sample_end, d_out,
                                    p->plan.opt.f0_ceil * 1.25, c, stream);
+}
+
+// moves the randn() state past the whole stream's draws (what one reference process would leave behind)
+int wb_pipeline_stream_end_dev(wb_pipeline_t *p, void *stream_) {
+  if (!p) return WB_ERR_ARG;
+  cudaStream_t stream = pick_stream(stream_);
+  unsigned long long *rng_pos = (unsigned long long *)p->ws.get("pl_rng_pos", 0);
+  unsigned long long *d_ncount = (unsigned long long *)p->ws.get("syn_ncount", 0);
+  if (!rng_pos) return WB_ERR_ARG;
+  WbRngState *rng = p->private_rng ? p->d_rng_private : wb_rng_global_state();
+  return wb_rng_advance(rng, rng_pos + 1, d_ncount, stream);
 }
 
 // wav in -> wav out (test/test.cpp:288-384 with tools/audioio.cpp either side): 16-bit PCM crosses PCIe, the

@@ -211,22 +211,27 @@ def gather_ranges(local, ranges, total, group=None, device=None):
 
 
 class StreamWorker:
-    """One rank's share of an exactly sharded stream on its GPU (torch CUDA tensors, C-ABI calls)."""
+    """One shard of an exactly sharded stream on this process's GPU (torch CUDA tensors, C-ABI calls).  A rank
+    that owns several shards (bounded memory per step) shares one pipeline / Harvest object between them."""
 
-    def __init__(self, plan, rank, harvest_option=None, cheaptrick_option=None, d4c_option=None):
+    def __init__(self, plan, shard, harvest_option=None, cheaptrick_option=None, d4c_option=None, share=None):
         import torch
         import worldb200 as wb
-        self.wb, self.torch, self.plan, self.rank = wb, torch, plan, rank
+        self.wb, self.torch, self.plan, self.rank = wb, torch, plan, shard
         self.harvest_option = harvest_option if harvest_option is not None else wb.HarvestOption()
         assert abs(self.harvest_option.frame_period - plan.fp) < 1e-12
-        self.pipe = wb.Pipeline(plan.fs, self.harvest_option, cheaptrick_option, d4c_option)
-        self.pipe.set_fresh_rng(True)                       # the stream is one reference process
+        if share is not None:
+            self.pipe, self.harvest = share.pipe, share.harvest
+        else:
+            self.pipe = wb.Pipeline(plan.fs, self.harvest_option, cheaptrick_option, d4c_option)
+            self.pipe.set_fresh_rng(True)                       # the stream is one reference process
+            self.harvest = wb.Harvest(plan.fs, self.harvest_option)
         assert self.pipe.fft_size == plan.fft_size, "plan was made for another FFT size"
-        self.harvest = wb.Harvest(plan.fs, self.harvest_option)
         self.bins = plan.fft_size // 2 + 1
 
     def harvest_local(self, d_x):
-        """f0 of the frames this rank owns (whole-stream frame grid)."""
+        """f0 of the frames this shard owns (whole-stream frame grid)."""
+        self.torch.cuda.current_stream().synchronize()   # inputs made by torch ops; the library has its own stream
         torch, L = self.torch, self.wb.lib()
         fb, fe = self.plan.frames[self.rank]
         out = torch.zeros(fe - fb, dtype=torch.float64, device=d_x.device)
@@ -245,12 +250,15 @@ class StreamWorker:
         return out
 
     def begin(self, d_f0_all):
+        """whole-stream bookkeeping (frame times, randn() seed, time base + pulse list): once per pipeline"""
+        self.torch.cuda.current_stream().synchronize()   # inputs made by torch ops; the library has its own stream
         self.d_f0_all = d_f0_all
         self.wb._check(self.wb.lib().wb_pipeline_stream_begin_dev(self.pipe._h, d_f0_all.data_ptr(), self.plan.f0_length,
                                                                   self.plan.out_length, None), "wb_pipeline_stream_begin_dev")
 
     def envelope(self, d_x, d_ap0_all):
-        """CheapTrick + Love Train for the rows this rank needs; writes its entries of d_ap0_all."""
+        """CheapTrick + Love Train for the rows this shard needs; writes its entries of d_ap0_all."""
+        self.torch.cuda.current_stream().synchronize()   # inputs made by torch ops; the library has its own stream
         torch = self.torch
         ra, rb = self.plan.rows[self.rank]
         self.d_sp = torch.empty((rb - ra, self.bins), dtype=torch.float64, device=d_x.device)
@@ -260,6 +268,7 @@ class StreamWorker:
         self.wb.device_synchronize()
 
     def aperiodicity(self, d_x, d_ap0_all):
+        self.torch.cuda.current_stream().synchronize()   # inputs made by torch ops; the library has its own stream
         torch = self.torch
         ra, rb = self.plan.rows[self.rank]
         self.d_ap = torch.empty((rb - ra, self.bins), dtype=torch.float64, device=d_x.device)
@@ -269,6 +278,7 @@ class StreamWorker:
         self.wb.device_synchronize()
 
     def synthesis(self):
+        self.torch.cuda.current_stream().synchronize()   # inputs made by torch ops; the library has its own stream
         torch = self.torch
         ra, rb = self.plan.rows[self.rank]
         sa, sb = self.plan.samples[self.rank]
@@ -279,40 +289,87 @@ class StreamWorker:
         self.wb.device_synchronize()
         return d_y[:sb - sa]
 
+    def end(self):
+        self.wb._check(self.wb.lib().wb_pipeline_stream_end_dev(self.pipe._h, None), "wb_pipeline_stream_end_dev")
+        self.wb.device_synchronize()
+
     def owned_rows(self, d_rows):
-        """the rows of d_sp / d_ap this rank owns (without the halo rows it computed for its pulses)"""
+        """the rows of d_sp / d_ap this shard owns (without the halo rows it computed for its pulses)"""
         ra, _ = self.plan.rows[self.rank]
         fb, fe = self.plan.frames[self.rank]
         return d_rows[fb - ra:fe - ra]
 
 
 def process_stream_exact(d_x, fs, harvest_option=None, cheaptrick_option=None, d4c_option=None, segment_seconds=30,
-                         halo_seconds=2, group=None, d_f0_all=None):
+                         halo_seconds=2, group=None, d_f0_all=None, shards_per_rank=1, keep_rows=True, timings=None):
     """Analysis + re-synthesis of one long stream (a float64 CUDA tensor every rank holds) sharded over the
-    ranks of `group`.  Returns dict(f0 [whole], y [whole], sp, ap [this rank's rows], frames, worker).
-    Pass d_f0_all to skip Harvest (e.g. a contour computed elsewhere)."""
+    ranks of `group`.  Returns dict(f0 [whole], y [whole], sp, ap [this rank's rows], frames, plan).
+    Pass d_f0_all to skip Harvest (e.g. a contour computed elsewhere).  shards_per_rank > 1 processes the
+    rank's share in that many pieces (bounds the scratch memory of one step; same results).  keep_rows=False
+    drops each shard's sp / ap rows once its samples are synthesised.  `timings`: a dict that receives CUDA-event
+    milliseconds per phase."""
     import torch
     import torch.distributed as dist
     import worldb200 as wb
     distributed = dist.is_available() and dist.is_initialized()
     rank = dist.get_rank(group) if distributed else 0
     world = dist.get_world_size(group) if distributed else 1
+    k = max(1, int(shards_per_rank))
     hopt = harvest_option if harvest_option is not None else wb.HarvestOption()
     copt = cheaptrick_option if cheaptrick_option is not None else wb.CheapTrickOption()
     fft_size = copt.fft_size if copt.fft_size else wb.CheapTrick.getFFTSizeForCheapTrick(fs, copt.f0_floor)
-    plan = StreamPlan(d_x.numel(), fs, world, hopt.frame_period, fft_size, segment_seconds, halo_seconds, hopt.target_fs)
-    w = StreamWorker(plan, rank, hopt, cheaptrick_option, d4c_option)
+    plan = StreamPlan(d_x.numel(), fs, world * k, hopt.frame_period, fft_size, segment_seconds, halo_seconds, hopt.target_fs)
+    mine = list(range(rank * k, (rank + 1) * k))
+    workers = []
+    for s in mine:
+        workers.append(StreamWorker(plan, s, hopt, cheaptrick_option, d4c_option, share=workers[0] if workers else None))
+    # per-rank contiguous ranges for the exchanges
+    rank_frames = [(plan.frames[r * k][0], plan.frames[(r + 1) * k - 1][1]) for r in range(world)]
+    rank_samples = [(plan.samples[r * k][0], plan.samples[(r + 1) * k - 1][1]) for r in range(world)]
+    marks = []
+
+    def mark(name):
+        if timings is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            wb.device_synchronize()
+            ev.record()
+            marks.append((name, ev))
+
+    mark("start")
     if d_f0_all is None:
-        d_f0_all = gather_ranges(w.harvest_local(d_x), plan.frames, plan.f0_length, group)      # exchange 1
-    w.begin(d_f0_all)
+        local_f0 = torch.cat([w.harvest_local(d_x) for w in workers])
+        mark("harvest")
+        d_f0_all = gather_ranges(local_f0, rank_frames, plan.f0_length, group)                   # exchange 1
+        mark("gather_f0")
+    workers[0].begin(d_f0_all)
+    for w in workers[1:]:
+        w.d_f0_all = d_f0_all
     d_ap0 = torch.zeros(plan.f0_length, dtype=torch.float64, device=d_x.device)
-    w.envelope(d_x, d_ap0)
-    fb, fe = plan.frames[rank]
-    d_ap0 = gather_ranges(d_ap0[fb:fe].clone(), plan.frames, plan.f0_length, group)              # exchange 2
-    w.aperiodicity(d_x, d_ap0)
-    d_y = gather_ranges(w.synthesis(), plan.samples, plan.out_length, group)                    # exchange 3 (stitch)
-    return {"f0": d_f0_all, "y": d_y, "sp": w.owned_rows(w.d_sp), "ap": w.owned_rows(w.d_ap), "frames": (fb, fe),
-            "worker": w, "plan": plan}
+    for w in workers:
+        w.envelope(d_x, d_ap0)
+    mark("envelope")
+    fb, fe = rank_frames[rank]
+    d_ap0 = gather_ranges(d_ap0[fb:fe].clone(), rank_frames, plan.f0_length, group)              # exchange 2
+    mark("gather_ap0")
+    ys, sps, aps = [], [], []
+    for w in workers:
+        w.aperiodicity(d_x, d_ap0)
+        ys.append(w.synthesis())
+        if keep_rows:
+            sps.append(w.owned_rows(w.d_sp))
+            aps.append(w.owned_rows(w.d_ap))
+        w.d_sp = w.d_ap = None
+    workers[0].end()
+    mark("aperiodicity_synthesis")
+    d_y = gather_ranges(torch.cat(ys), rank_samples, plan.out_length, group)                     # exchange 3 (stitch)
+    mark("stitch")
+    if timings is not None:
+        torch.cuda.synchronize()
+        for (_, e0), (name, e1) in zip(marks[:-1], marks[1:]):
+            timings[name] = e0.elapsed_time(e1)
+        timings["total"] = marks[0][1].elapsed_time(marks[-1][1])
+    return {"f0": d_f0_all, "y": d_y, "sp": torch.cat(sps) if sps else None, "ap": torch.cat(aps) if aps else None,
+            "frames": (fb, fe), "plan": plan}
 
 
 def simulate_stream_ranks(d_x, fs, world, harvest_option=None, cheaptrick_option=None, d4c_option=None, segment_seconds=30,
