@@ -43,11 +43,15 @@ def main():
     import worldb200 as wb
     from worldb200 import parallel, signals
     wb._check(wb.lib().wb_init(local_rank), "wb_init")
-    x = signals.synth_speech(args.fs, args.seconds, seed=0)
+    # long streams: a 60 s synthetic block repeated (the generator costs ~0.2 s of host time per second of audio)
+    block = signals.synth_speech(args.fs, min(args.seconds, 60.0), seed=0)
+    n_total = int(round(args.seconds * args.fs))
+    x = np.tile(block, -(-n_total // len(block)))[:n_total].copy()
     d_x = torch.from_numpy(x).cuda()
     hopt = wb.HarvestOption(f0_floor=40.0, frame_period=5.0)
     copt, dopt = wb.CheapTrickOption(f0_floor=71.0), wb.D4COption(threshold=0.85)
     best, out, timings = None, None, None
+    keep = {}     # pipeline objects / device workspaces live across the repetitions (steady state)
     for rep in range(args.reps + 1):          # first repetition = warm-up (allocations, plan tables)
         if world > 1:
             dist.barrier()
@@ -55,7 +59,7 @@ def main():
         t = {}
         t0 = time.perf_counter()
         out = parallel.process_stream_exact(d_x, args.fs, hopt, copt, dopt, segment_seconds=args.segment_seconds, halo_seconds=2,
-                                            shards_per_rank=args.shards_per_rank, keep_rows=False, timings=t)
+                                            shards_per_rank=args.shards_per_rank, keep_rows=False, timings=t, state=keep)
         torch.cuda.synchronize()
         wall = (time.perf_counter() - t0) * 1e3
         ms = torch.tensor([t["total"]], dtype=torch.float64, device="cuda")
@@ -67,7 +71,7 @@ def main():
         wb.profile_reset()
         wb.profile(True)
         parallel.process_stream_exact(d_x, args.fs, hopt, copt, dopt, segment_seconds=args.segment_seconds, halo_seconds=2,
-                                      shards_per_rank=args.shards_per_rank, keep_rows=False)
+                                      shards_per_rank=args.shards_per_rank, keep_rows=False, state=keep)
         table = wb.profile_results()
         wb.profile(False)
         for name, (ms, cnt) in sorted(table.items(), key=lambda kv: -kv[1][0])[:24]:

@@ -99,14 +99,145 @@ __device__ __forceinline__ IncFn ps_incfn(double a, int e) {
   return f;
 }
 
-// Writes total_phase[i]; the fmod / wrap detection is done by the (fully parallel) pulse kernels.
-__global__ void __launch_bounds__(PS_THREADS) phase_scan_kernel(const double *__restrict__ incr, int n,
-                                                                double *__restrict__ wrap_phase) {
+// Block-wide EXCLUSIVE scan of per-thread composed increment functions (thread order = element order).
+// `warp_fn` is a shared array of 32 entries; afterwards warp_fn[nwarps - 1] holds the composition of the whole
+// block.  Contains two __syncthreads().
+__device__ __forceinline__ IncFn ps_block_exclusive(IncFn acc, IncFn *warp_fn) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  IncFn incl = acc;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    IncFn t;
+    t.ce = __shfl_up_sync(0xffffffffu, incl.ce, o);
+    t.co = __shfl_up_sync(0xffffffffu, incl.co, o);
+    if (lane >= o) incl = ps_compose(t, incl);
+  }
+  if (lane == 31) warp_fn[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    IncFn wi = warp_fn[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      IncFn t;
+      t.ce = __shfl_up_sync(0xffffffffu, wi.ce, o);
+      t.co = __shfl_up_sync(0xffffffffu, wi.co, o);
+      if (lane >= o) wi = ps_compose(t, wi);
+    }
+    warp_fn[lane] = wi;  // inclusive over warps
+  }
+  __syncthreads();
+  IncFn pre; pre.ce = 0ull; pre.co = 0ull;
+  if (warp > 0) pre = warp_fn[warp - 1];
+  IncFn lane_excl;
+  lane_excl.ce = __shfl_up_sync(0xffffffffu, incl.ce, 1);
+  lane_excl.co = __shfl_up_sync(0xffffffffu, incl.co, 1);
+  if (lane > 0) pre = ps_compose(pre, lane_excl);
+  return pre;
+}
+
+// The scan runs in five launches so that only O(n / PS_CHUNK) work is sequential (one hour of audio is
+// 1.7e8 samples: a single sequential pass was the Amdahl term of the sharded stream):
+//   A  ps_chunk_sum_kernel    plain fp64 sum of every chunk of PS_CHUNK increments (parallel, approximate)
+//   B  ps_binade_kernel       approximate running sum at the chunk boundaries -> the binade every chunk is
+//                             EXPECTED to stay in (or "unknown" when a boundary is near)
+//   C  ps_chunk_fn_kernel     the chunk's composed increment function for that binade (parallel, exact)
+//   D  ps_sequential_kernel   the exact running sum chunk by chunk: one composed function per chunk where the
+//                             expectation holds for the exact sum (verified), otherwise the chunk is walked
+//                             cooperatively with genuine fp64 adds at binade crossings
+//   E  ps_expand_kernel       the elements of the chunks D skipped over, from their exact start values (parallel)
+// Chunk c covers elements [1 + c PS_CHUNK, 1 + (c + 1) PS_CHUNK); element 0 is the start value.
+#define PS_E_UNKNOWN (-100000)
+
+__global__ void __launch_bounds__(PS_THREADS) ps_chunk_sum_kernel(const double *__restrict__ incr, int n, double *__restrict__ chunk_sum) {
+  __shared__ double red[32];
+  const int begin = 1 + blockIdx.x * PS_CHUNK, end = min(n, begin + PS_CHUNK);
+  double s = 0.0;
+  for (int i = begin + threadIdx.x; i < end; i += PS_THREADS) s += incr[i];
+  s = wb_block_sum(s, red);
+  if (threadIdx.x == 0) chunk_sum[blockIdx.x] = s;
+}
+
+__device__ __forceinline__ int ps_exponent(double v) { return (int)((__double_as_longlong(v) >> 52) & 0x7ff) - 1023; }
+
+__global__ void __launch_bounds__(PS_THREADS) ps_binade_kernel(const double *__restrict__ incr, const double *__restrict__ chunk_sum,
+                                                               int n_chunks, int *__restrict__ e_pred) {
+  __shared__ double s_warp[32];
+  __shared__ double s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_carry = incr[0];
+  __syncthreads();
+  for (int base = 0; base < n_chunks; base += PS_THREADS) {
+    const int c = base + tid;
+    const double a = c < n_chunks ? chunk_sum[c] : 0.0;
+    double incl = a;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    double before = s_carry;
+    for (int w = 0; w < warp; ++w) before += s_warp[w];
+    const double lo = before + (incl - a), hi = lo + a;   // approximate sums at the chunk's two ends
+    if (c < n_chunks) {
+      // relative error of these sums is far below 1e-9 (<= n eps); stay clear of binade boundaries by that much
+      const double lo_m = lo * (1.0 - 1e-9), hi_m = hi * (1.0 + 1e-9);
+      const int e_lo = ps_exponent(lo_m), e_hi = ps_exponent(hi_m);
+      const bool ok = lo_m > 0.0 && a >= 0.0 && e_lo == e_hi && e_lo > -960 && e_lo < 1000;
+      e_pred[c] = ok ? e_lo : PS_E_UNKNOWN;
+    }
+    __syncthreads();
+    if (tid == PS_THREADS - 1) s_carry = hi;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(PS_THREADS) ps_chunk_fn_kernel(const double *__restrict__ incr, int n, const int *__restrict__ e_pred,
+                                                                 IncFn *__restrict__ chunk_fn, int *__restrict__ chunk_bad) {
+  __shared__ IncFn warp_fn[32];
+  const int c = blockIdx.x;
+  const int e = e_pred[c];
+  if (e == PS_E_UNKNOWN) {
+    if (threadIdx.x == 0) chunk_bad[c] = 1;
+    return;
+  }
+  const int begin = 1 + c * PS_CHUNK, end = min(n, begin + PS_CHUNK);
+  const int base = begin + threadIdx.x * PS_PER;
+  IncFn acc; acc.ce = 0ull; acc.co = 0ull;
+  int bad = 0;
+#pragma unroll
+  for (int q = 0; q < PS_PER; ++q) {
+    const int i = base + q;
+    if (i < end) {
+      const IncFn f = ps_incfn(incr[i], e);
+      bad |= (f.ce >= (1ull << 53)) ? 1 : 0;   // does not fit the binade model: the chunk is walked instead
+      acc = ps_compose(acc, f);
+    }
+  }
+  bad = __syncthreads_or(bad);
+  (void)ps_block_exclusive(acc, warp_fn);
+  if (threadIdx.x == 0) {
+    chunk_fn[c] = warp_fn[PS_THREADS / 32 - 1];
+    chunk_bad[c] = bad;
+  }
+}
+
+// Writes total_phase[i] of the chunks it walks; the fmod / wrap detection is done by the (fully parallel)
+// pulse kernels.
+__global__ void __launch_bounds__(PS_THREADS) ps_sequential_kernel(const double *__restrict__ incr, int n,
+                                                                   double *__restrict__ wrap_phase, int n_chunks,
+                                                                   const int *__restrict__ e_pred, const IncFn *__restrict__ chunk_fn,
+                                                                   const int *__restrict__ chunk_bad, double *__restrict__ chunk_start,
+                                                                   int *__restrict__ chunk_expand) {
   __shared__ IncFn warp_fn[32];
   __shared__ int s_first_bad;
   __shared__ double s_sum;   // current running sum (exact double)
   __shared__ int s_pos;      // next element to process
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ int s_advanced;
+  __shared__ int m_e[PS_THREADS];          // metadata of the next PS_THREADS chunks
+  __shared__ IncFn m_fn[PS_THREADS];
+  const int tid = threadIdx.x;
   if (tid == 0) {
     const double s0 = incr[0];  // total_phase[0] = interpolated_f0[0] * const_val
     wrap_phase[0] = s0;
@@ -117,6 +248,42 @@ __global__ void __launch_bounds__(PS_THREADS) phase_scan_kernel(const double *__
   while (true) {
     const int pos = s_pos;
     if (pos >= n) break;
+    const int c = (pos - 1) / PS_CHUNK;
+    if ((pos - 1) % PS_CHUNK == 0) {
+      // at a chunk boundary: skip over every chunk whose composed function applies to the exact sum
+      {
+        const int cc = c + tid;
+        int e = PS_E_UNKNOWN;
+        IncFn f; f.ce = 0ull; f.co = 0ull;
+        if (cc < n_chunks && !chunk_bad[cc]) { e = e_pred[cc]; f = chunk_fn[cc]; }
+        m_e[tid] = e;
+        m_fn[tid] = f;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        double sum = s_sum;
+        int k = 0;
+        const int k_max = min(PS_THREADS, n_chunks - c);
+        while (k < k_max) {
+          const int e = m_e[k];
+          if (e == PS_E_UNKNOWN || !(sum > 0.0) || ps_exponent(sum) != e) break;
+          const unsigned long long S = ((unsigned long long)__double_as_longlong(sum) & 0xfffffffffffffull) | (1ull << 52);
+          const unsigned long long Sn = S + ((S & 1ull) ? m_fn[k].co : m_fn[k].ce);
+          if (Sn >= (1ull << 53)) break;   // would leave the binade inside the chunk (increments are >= 0: monotone)
+          chunk_start[c + k] = sum;
+          chunk_expand[c + k] = 1;
+          sum = (double)Sn * __longlong_as_double((long long)(e - 52 + 1023) << 52);
+          ++k;
+        }
+        s_sum = sum;
+        s_pos = min(n, 1 + (c + k) * PS_CHUNK);
+        s_advanced = k;
+        if (k == 0) chunk_expand[c] = 0;   // walked below
+      }
+      __syncthreads();
+      if (s_advanced > 0) continue;
+    }
+    const int chunk_end = min(n, 1 + (c + 1) * PS_CHUNK);
     const double sum = s_sum;
     const long long sbits = __double_as_longlong(sum);
     const int e = (int)((sbits >> 52) & 0x7ff) - 1023;
@@ -141,43 +308,11 @@ __global__ void __launch_bounds__(PS_THREADS) phase_scan_kernel(const double *__
 #pragma unroll
     for (int q = 0; q < PS_PER; ++q) {
       const int i = base + q;
-      if (i < n) fn[q] = ps_incfn(incr[i], e);
+      if (i < chunk_end) fn[q] = ps_incfn(incr[i], e);
       else { fn[q].ce = 0ull; fn[q].co = 0ull; }
       acc = ps_compose(acc, fn[q]);
     }
-    // block exclusive scan of the composed functions
-    IncFn incl = acc;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      IncFn t;
-      t.ce = __shfl_up_sync(0xffffffffu, incl.ce, o);
-      t.co = __shfl_up_sync(0xffffffffu, incl.co, o);
-      if (lane >= o) incl = ps_compose(t, incl);
-    }
-    if (lane == 31) warp_fn[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-      IncFn w = warp_fn[lane];
-      IncFn wi = w;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        IncFn t;
-        t.ce = __shfl_up_sync(0xffffffffu, wi.ce, o);
-        t.co = __shfl_up_sync(0xffffffffu, wi.co, o);
-        if (lane >= o) wi = ps_compose(t, wi);
-      }
-      warp_fn[lane] = wi;  // inclusive over warps
-    }
-    __syncthreads();
-    // exclusive prefix function for this thread = (warps before) then (lanes before in warp)
-    IncFn pre; pre.ce = 0ull; pre.co = 0ull;
-    if (warp > 0) pre = warp_fn[warp - 1];
-    {
-      IncFn lane_excl;
-      lane_excl.ce = __shfl_up_sync(0xffffffffu, incl.ce, 1);
-      lane_excl.co = __shfl_up_sync(0xffffffffu, incl.co, 1);
-      if (lane > 0) pre = ps_compose(pre, lane_excl);
-    }
+    const IncFn pre = ps_block_exclusive(acc, warp_fn);
     unsigned long long S = S0 + ((S0 & 1ull) ? pre.co : pre.ce);
     const unsigned long long LIMIT = 1ull << 53;
     const double ulp = __longlong_as_double((long long)(e - 52 + 1023) << 52);  // 2^(e-52), e-52 > -1023 here
@@ -187,25 +322,23 @@ __global__ void __launch_bounds__(PS_THREADS) phase_scan_kernel(const double *__
 #pragma unroll
     for (int q = 0; q < PS_PER; ++q) {
       const int i = base + q;
-      if (i < n && my_bad == 0x7fffffff) {
+      if (i < chunk_end && my_bad == 0x7fffffff) {
         S += (S & 1ull) ? fn[q].co : fn[q].ce;
         if (S >= LIMIT) my_bad = i;
         else wrap_phase[i] = (double)S * ulp;
       }
     }
-    if (my_bad != 0x7fffffff) atomicMin(&s_first_bad, my_bad);
+    if (my_bad != 0x7fffffff && my_bad < chunk_end) atomicMin(&s_first_bad, my_bad);
     __syncthreads();
     const int first_bad = s_first_bad;
-    const int chunk_end = min(n, pos + PS_CHUNK);
     if (first_bad >= chunk_end) {
-      // whole chunk valid: the last thread that owns a valid element publishes the sum
+      // whole range valid: the thread that owns its last element publishes the sum
       const int last = chunk_end - 1;
       if (last >= base && last < base + PS_PER) { s_sum = (double)S * ulp; s_pos = chunk_end; }
     } else {
       // replay element first_bad with a genuine fp64 add on top of the exact sum before it
       const int owner = (first_bad - pos) / PS_PER;
       if (tid == owner) {
-        // recompute the sum just before first_bad
         unsigned long long Sb = S0 + ((S0 & 1ull) ? pre.co : pre.ce);
         for (int q = 0; q < PS_PER; ++q) {
           const int i = base + q;
@@ -220,6 +353,38 @@ __global__ void __launch_bounds__(PS_THREADS) phase_scan_kernel(const double *__
       }
     }
     __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(PS_THREADS) ps_expand_kernel(const double *__restrict__ incr, int n, double *__restrict__ wrap_phase,
+                                                               const int *__restrict__ e_pred, const double *__restrict__ chunk_start,
+                                                               const int *__restrict__ chunk_expand) {
+  __shared__ IncFn warp_fn[32];
+  const int c = blockIdx.x;
+  if (!chunk_expand[c]) return;
+  const int e = e_pred[c];
+  const int begin = 1 + c * PS_CHUNK, end = min(n, begin + PS_CHUNK);
+  const int base = begin + threadIdx.x * PS_PER;
+  const unsigned long long S0 = ((unsigned long long)__double_as_longlong(chunk_start[c]) & 0xfffffffffffffull) | (1ull << 52);
+  IncFn fn[PS_PER];
+  IncFn acc; acc.ce = 0ull; acc.co = 0ull;
+#pragma unroll
+  for (int q = 0; q < PS_PER; ++q) {
+    const int i = base + q;
+    if (i < end) fn[q] = ps_incfn(incr[i], e);
+    else { fn[q].ce = 0ull; fn[q].co = 0ull; }
+    acc = ps_compose(acc, fn[q]);
+  }
+  const IncFn pre = ps_block_exclusive(acc, warp_fn);
+  unsigned long long S = S0 + ((S0 & 1ull) ? pre.co : pre.ce);
+  const double ulp = __longlong_as_double((long long)(e - 52 + 1023) << 52);
+#pragma unroll
+  for (int q = 0; q < PS_PER; ++q) {
+    const int i = base + q;
+    if (i < end) {
+      S += (S & 1ull) ? fn[q].co : fn[q].ce;
+      wrap_phase[i] = (double)S * ulp;   // (D verified that the chunk's last sum stays inside the binade)
+    }
   }
 }
 
@@ -556,7 +721,26 @@ int wb_synthesis_timebase(WbWorkspace *ws, int fs, int fft_size, double frame_pe
   if (!d_incr || !d_total || !d_vuv || !d_bc || !d_bo || !d_pidx || !d_pshift || !d_np || !d_ncount) return WB_ERR_CUDA;
   WB_LAUNCH("timebase_kernel", timebase_kernel<<<(out_length + 255) / 256, 256, 0, stream>>>(
       d_f0, f0_length, fs, frame_period, lowest_f0, out_length, d_incr, d_vuv));
-  WB_LAUNCH("phase_scan_kernel", phase_scan_kernel<<<1, PS_THREADS, 0, stream>>>(d_incr, out_length, d_total));
+  {
+    const int n_chunks = out_length > 1 ? (out_length - 1 + PS_CHUNK - 1) / PS_CHUNK : 0;
+    const int nc = n_chunks > 0 ? n_chunks : 1;
+    double *d_csum = (double *)ws->get("syn_ps_sum", sizeof(double) * nc);
+    double *d_cstart = (double *)ws->get("syn_ps_start", sizeof(double) * nc);
+    int *d_ce = (int *)ws->get("syn_ps_e", sizeof(int) * nc);
+    int *d_cbad = (int *)ws->get("syn_ps_bad", sizeof(int) * nc);
+    int *d_cexp = (int *)ws->get("syn_ps_expand", sizeof(int) * nc);
+    IncFn *d_cfn = (IncFn *)ws->get("syn_ps_fn", sizeof(IncFn) * nc);
+    if (!d_csum || !d_cstart || !d_ce || !d_cbad || !d_cexp || !d_cfn) return WB_ERR_CUDA;
+    if (n_chunks > 0) {
+      WB_LAUNCH("ps_chunk_sum_kernel", ps_chunk_sum_kernel<<<n_chunks, PS_THREADS, 0, stream>>>(d_incr, out_length, d_csum));
+      WB_LAUNCH("ps_binade_kernel", ps_binade_kernel<<<1, PS_THREADS, 0, stream>>>(d_incr, d_csum, n_chunks, d_ce));
+      WB_LAUNCH("ps_chunk_fn_kernel", ps_chunk_fn_kernel<<<n_chunks, PS_THREADS, 0, stream>>>(d_incr, out_length, d_ce, d_cfn, d_cbad));
+    }
+    WB_LAUNCH("phase_scan_kernel", ps_sequential_kernel<<<1, PS_THREADS, 0, stream>>>(d_incr, out_length, d_total, n_chunks, d_ce, d_cfn,
+                                                                                   d_cbad, d_cstart, d_cexp));
+    if (n_chunks > 0)
+      WB_LAUNCH("ps_expand_kernel", ps_expand_kernel<<<n_chunks, PS_THREADS, 0, stream>>>(d_incr, out_length, d_total, d_ce, d_cstart, d_cexp));
+  }
   WB_LAUNCH("pulse_count_kernel", pulse_count_kernel<<<n_blocks, PD_THREADS, 0, stream>>>(d_total, out_length, d_bc));
   int rc = wb_exclusive_scan_u64(d_bc, d_bo, n_blocks, stream);
   if (rc) return rc;

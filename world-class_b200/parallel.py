@@ -301,13 +301,16 @@ class StreamWorker:
 
 
 def process_stream_exact(d_x, fs, harvest_option=None, cheaptrick_option=None, d4c_option=None, segment_seconds=30,
-                         halo_seconds=2, group=None, d_f0_all=None, shards_per_rank=1, keep_rows=True, timings=None):
+                         halo_seconds=2, group=None, d_f0_all=None, shards_per_rank=1, keep_rows=True, timings=None,
+                         state=None):
     """Analysis + re-synthesis of one long stream (a float64 CUDA tensor every rank holds) sharded over the
     ranks of `group`.  Returns dict(f0 [whole], y [whole], sp, ap [this rank's rows], frames, plan).
     Pass d_f0_all to skip Harvest (e.g. a contour computed elsewhere).  shards_per_rank > 1 processes the
     rank's share in that many pieces (bounds the scratch memory of one step; same results).  keep_rows=False
     drops each shard's sp / ap rows once its samples are synthesised.  `timings`: a dict that receives CUDA-event
-    milliseconds per phase."""
+    milliseconds per phase.  `state`: a dict the caller keeps between calls on streams of the same shape; the
+    pipeline objects (and with them their device workspaces: several GB for long streams) are then reused
+    instead of being allocated and freed by every call."""
     import torch
     import torch.distributed as dist
     import worldb200 as wb
@@ -320,9 +323,15 @@ def process_stream_exact(d_x, fs, harvest_option=None, cheaptrick_option=None, d
     fft_size = copt.fft_size if copt.fft_size else wb.CheapTrick.getFFTSizeForCheapTrick(fs, copt.f0_floor)
     plan = StreamPlan(d_x.numel(), fs, world * k, hopt.frame_period, fft_size, segment_seconds, halo_seconds, hopt.target_fs)
     mine = list(range(rank * k, (rank + 1) * k))
-    workers = []
-    for s in mine:
-        workers.append(StreamWorker(plan, s, hopt, cheaptrick_option, d4c_option, share=workers[0] if workers else None))
+    key = (plan.n, plan.fs, world, k, plan.fp, plan.fft_size, int(segment_seconds), int(halo_seconds))
+    if state is not None and state.get("key") == key:
+        workers = state["workers"]
+    else:
+        workers = []
+        for s in mine:
+            workers.append(StreamWorker(plan, s, hopt, cheaptrick_option, d4c_option, share=workers[0] if workers else None))
+        if state is not None:
+            state.update(key=key, workers=workers)
     # per-rank contiguous ranges for the exchanges
     rank_frames = [(plan.frames[r * k][0], plan.frames[(r + 1) * k - 1][1]) for r in range(world)]
     rank_samples = [(plan.samples[r * k][0], plan.samples[(r + 1) * k - 1][1]) for r in range(world)]
