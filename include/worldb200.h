@@ -59,6 +59,7 @@ typedef struct wb_cheaptrick wb_cheaptrick_t;
 typedef struct wb_d4c wb_d4c_t;
 typedef struct wb_synthesis wb_synthesis_t;
 typedef struct wb_pipeline wb_pipeline_t;
+typedef struct wb_synthesis_stream wb_synthesis_stream_t;
 
 /* ---- library ---------------------------------------------------------------------- */
 int wb_init(int device);                /* optional; otherwise lazily on first use (current device) */
@@ -131,6 +132,23 @@ int wb_synthesis_compute(wb_synthesis_t *h, const double *f0, int f0_length,
 int wb_synthesis_compute_dev(wb_synthesis_t *h, const double *d_f0, int f0_length,
                              const double *d_spectrogram, const double *d_aperiodicity,
                              int out_length, double *d_out, double f0_upper_bound, void *stream);
+
+/* ---- streaming Synthesis (the real-time use the demo mentions, test/test.cpp:353-358; the reference itself
+ * only has the one-shot compute(), src/synthesis.cpp:77-177) ---------------------------------------------------
+ * Frames are pushed in pieces of any size; each call returns the samples that became final (no later pulse can
+ * reach them).  The phase sum, the pulse list and the randn() position are carried between calls, so the
+ * concatenation of everything returned equals wb_synthesis_compute() on all frames bit for bit.  HOST pointers;
+ * spectrogram / aperiodicity are contiguous [n_frames][fft_size/2+1].  At most out_capacity samples are written
+ * per call (what does not fit comes with the next call).  finish(): no more frames; out_length_total as in
+ * compute(); call it until *n_out == 0.  The process-global randn() stream belongs to the stream object from
+ * the first push to the last finish.  f0_upper_bound: a bound on the f0 values (sizes the pulse buffers;
+ * <= 0 = 1000 Hz). */
+int wb_synthesis_stream_create(int fs, int fft_size, double frame_period_ms, double f0_upper_bound,
+                               wb_synthesis_stream_t **out);
+void wb_synthesis_stream_destroy(wb_synthesis_stream_t *s);
+int wb_synthesis_stream_push(wb_synthesis_stream_t *s, const double *f0, const double *spectrogram,
+                             const double *aperiodicity, int n_frames, double *out, int out_capacity, int *n_out);
+int wb_synthesis_stream_finish(wb_synthesis_stream_t *s, int out_length_total, double *out, int out_capacity, int *n_out);
 
 /* ---- codec (include/codec.hpp:23-88; src/codec.cpp:211-325) ------------------------------
  * Same argument meaning as the reference's free functions; rows are separately allocated. */

@@ -27,3 +27,68 @@ def test_synthesis_matches_reference(wb, signals, fs, seconds):
     err = float(np.abs(y - ref["y"]).max() / peak)
     print("synthesis fs=%d peak %.3f max err/peak %.3e" % (fs, peak, err))
     assert err < RTOL
+
+
+# ---- streaming synthesis -----------------------------------------------------------
+def _analysis(wb, signals, fs, seconds, seed):
+    x = signals.synth_speech(fs, seconds, seed=seed)
+    pl = wb.Pipeline(fs, wb.HarvestOption(f0_floor=40.0, frame_period=5.0), wb.CheapTrickOption(f0_floor=71.0))
+    pl.set_fresh_rng(True)
+    out = pl.run(x)
+    return out["f0"], out["sp"], out["ap"], pl.fft_size, len(out["y"])
+
+
+@pytest.mark.parametrize("fs,pieces", [(16000, "random"), (16000, "single frames"), (48000, "random"), (22050, "two")])
+def test_streaming_synthesis_equals_the_one_shot_call_bit_for_bit(wb, signals, fs, pieces):
+    f0, sp, ap, fft_size, ny = _analysis(wb, signals, fs, 2.0 if fs != 48000 else 1.5, 41)
+    wb.randn_reseed()
+    want = wb.Synthesis(fs, fft_size, 5.0).compute(f0, sp, ap, ny)
+    state_after = wb.randn_get_state()
+    rng = np.random.default_rng(5)
+    L = len(f0)
+    if pieces == "random":
+        cuts = np.unique(np.concatenate([[0, L], rng.integers(1, L, size=12)]))
+    elif pieces == "single frames":
+        cuts = np.arange(L + 1)
+    else:
+        cuts = np.array([0, L // 3, L])
+    wb.randn_reseed()
+    st = wb.SynthesisStream(fs, fft_size, 5.0, 1000.0)
+    got = []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        piece = st.push(f0[a:b], sp[a:b], ap[a:b])
+        # nothing is emitted before it is final, and never more than the frames so far can determine
+        assert sum(len(g) for g in got) + len(piece) <= int((b - 1) * 5.0 / 1000.0 * fs) + 1
+        got.append(piece)
+    got.append(st.finish(ny))
+    y = np.concatenate(got)
+    assert len(y) == ny
+    bad = np.flatnonzero(y != want)
+    assert bad.size == 0, "first / count of differing samples: %d %d" % (bad[0], bad.size)
+    assert wb.randn_get_state() == state_after            # the randn() stream was consumed exactly as by compute()
+    emitted_early = sum(len(g) for g in got[:-1])
+    assert emitted_early > 0.8 * ny - 2 * fft_size          # it really streams: most samples leave before finish()
+
+
+def test_streaming_synthesis_small_output_buffers_and_errors(wb, signals):
+    fs = 16000
+    f0, sp, ap, fft_size, ny = _analysis(wb, signals, fs, 1.0, 42)
+    wb.randn_reseed()
+    want = wb.Synthesis(fs, fft_size, 5.0).compute(f0, sp, ap, ny)
+    wb.randn_reseed()
+    st = wb.SynthesisStream(fs, fft_size, 5.0)
+    got = []
+    for a in range(0, len(f0), 40):
+        got.append(st.push(f0[a:a + 40], sp[a:a + 40], ap[a:a + 40], out_capacity=333))   # fewer than a piece yields
+        assert len(got[-1]) <= 333
+    got.append(st.finish(ny, out_capacity=1000))
+    assert np.array_equal(np.concatenate(got), want)
+    with pytest.raises(wb.WorldB200Error):
+        st.push(f0[:2], sp[:2], ap[:2])                    # finished
+    st2 = wb.SynthesisStream(fs, fft_size, 5.0)
+    st2.push(f0[:100], sp[:100], ap[:100])
+    with pytest.raises(wb.WorldB200Error):
+        st2.finish(10)                                     # shorter than what is already determined
+    with pytest.raises(wb.WorldB200Error):
+        wb.SynthesisStream(fs, 1000, 5.0)                  # not a power of two
+    wb.randn_reseed()

@@ -115,6 +115,10 @@ def _declare(L):
         "wb_pipeline_stream_aperiodicity_dev": (ci, [vp, vp, ci, vp, vp, ci, ci, ci, vp, vp]),
         "wb_pipeline_stream_synthesis_dev": (ci, [vp, ci, vp, vp, ci, ci, ci, ci, ci, vp, vp]),
         "wb_pipeline_stream_end_dev": (ci, [vp, vp]),
+        "wb_synthesis_stream_create": (ci, [ci, ci, cd, cd, ctypes.POINTER(vp)]),
+        "wb_synthesis_stream_destroy": (None, [vp]),
+        "wb_synthesis_stream_push": (ci, [vp, vp, vp, vp, ci, vp, ci, ctypes.POINTER(ci)]),
+        "wb_synthesis_stream_finish": (ci, [vp, ci, vp, ci, ctypes.POINTER(ci)]),
         "wb_pipeline_run_pcm16": (ci, [vp, vp, ci, vp, ci]),
         "wb_pipeline_run_f32": (ci, [vp, vp, ci, vp, vp, vp, vp, ci]),
         "wb_pcm16_to_f64_dev": (ci, [vp, ci, vp, vp]),
@@ -365,6 +369,46 @@ class Synthesis:
         _check(lib().wb_synthesis_compute(self._h, f0.ctypes.data, len(f0), rs.ctypes.data, ra.ctypes.data,
                                           len(out), out.ctypes.data), "wb_synthesis_compute")
         return out
+
+
+class SynthesisStream:
+    """Streaming Synthesis: push frames in pieces, get the samples that became final; the concatenated output
+    equals Synthesis.compute on all frames bit for bit (phase sum, pulses and randn() position are carried)."""
+
+    def __init__(self, fs, fft_size, frame_period, f0_upper_bound=0.0):
+        self._h = ctypes.c_void_p()
+        self.fs, self.fft_size, self.frame_period = int(fs), int(fft_size), float(frame_period)
+        _check(lib().wb_synthesis_stream_create(self.fs, self.fft_size, self.frame_period, float(f0_upper_bound),
+                                                ctypes.byref(self._h)), "wb_synthesis_stream_create")
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.wb_synthesis_stream_destroy(self._h)
+            self._h = None
+
+    def push(self, f0, spectrogram, aperiodicity, out_capacity=None):
+        f0, sp, ap = _f64(f0), _f64(spectrogram), _f64(aperiodicity)
+        n = len(f0)
+        assert sp.shape == ap.shape == (n, self.fft_size // 2 + 1)
+        cap = int(out_capacity) if out_capacity is not None else int((n + 2) * self.frame_period / 1000.0 * self.fs) + 2 * self.fft_size
+        out = np.empty(cap, dtype=np.float64)
+        got = ctypes.c_int()
+        _check(lib().wb_synthesis_stream_push(self._h, f0.ctypes.data, sp.ctypes.data, ap.ctypes.data, n, out.ctypes.data, cap,
+                                              ctypes.byref(got)), "wb_synthesis_stream_push")
+        return out[:got.value]
+
+    def finish(self, out_length, out_capacity=None):
+        pieces = []
+        cap = int(out_capacity) if out_capacity is not None else max(1, int(out_length))
+        while True:
+            out = np.empty(cap, dtype=np.float64)
+            got = ctypes.c_int()
+            _check(lib().wb_synthesis_stream_finish(self._h, int(out_length), out.ctypes.data, cap, ctypes.byref(got)),
+                   "wb_synthesis_stream_finish")
+            if got.value == 0:
+                break
+            pieces.append(out[:got.value])
+        return np.concatenate(pieces) if pieces else np.empty(0)
 
 
 def synthesis_length(f0_length, frame_period, fs):

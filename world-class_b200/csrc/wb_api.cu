@@ -1073,6 +1073,37 @@ int wb_pipeline_stream_end_dev(wb_pipeline_t *p, void *stream_) {
   return wb_rng_advance(rng, rng_pos + 1, d_ncount, stream);
 }
 
+// ---- streaming synthesis (the real-time use the demo points at, test/test.cpp:353-358) -----------------------
+struct wb_synthesis_stream { WbSynStream *impl; };
+
+int wb_synthesis_stream_create(int fs, int fft_size, double frame_period_ms, double f0_upper_bound,
+                               wb_synthesis_stream_t **out) {
+  if (!out) return WB_ERR_ARG;
+  int rc = ctx_init();
+  if (rc) return rc;
+  WbSynStream *impl = wb_synstream_create(fs, fft_size, frame_period_ms, f0_upper_bound);
+  if (!impl) return WB_ERR_UNSUPPORTED;
+  wb_synthesis_stream *h = new (std::nothrow) wb_synthesis_stream();
+  if (!h) { wb_synstream_destroy(impl); return WB_ERR_ARG; }
+  h->impl = impl;
+  *out = h;
+  return WB_OK;
+}
+void wb_synthesis_stream_destroy(wb_synthesis_stream_t *s) {
+  if (!s) return;
+  wb_synstream_destroy(s->impl);
+  delete s;
+}
+int wb_synthesis_stream_push(wb_synthesis_stream_t *s, const double *f0, const double *spectrogram, const double *aperiodicity,
+                             int n_frames, double *out, int out_capacity, int *n_out) {
+  if (!s) return WB_ERR_ARG;
+  return wb_synstream_push(s->impl, f0, spectrogram, aperiodicity, n_frames, out, out_capacity, n_out, g_stream);
+}
+int wb_synthesis_stream_finish(wb_synthesis_stream_t *s, int out_length_total, double *out, int out_capacity, int *n_out) {
+  if (!s) return WB_ERR_ARG;
+  return wb_synstream_finish(s->impl, out_length_total, out, out_capacity, n_out, g_stream);
+}
+
 // wav in -> wav out (test/test.cpp:288-384 with tools/audioio.cpp either side): 16-bit PCM crosses PCIe, the
 // sample-format conversions of wavread / wavwrite run on the device (wb_io.cu)
 int wb_pipeline_run_pcm16(wb_pipeline_t *p, const short *pcm_in, int x_length, short *pcm_out, int y_length) {

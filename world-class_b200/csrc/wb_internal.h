@@ -12,6 +12,8 @@ class WbWorkspace {
   WbWorkspace();
   ~WbWorkspace();
   void *get(const std::string &name, size_t bytes);        // device memory
+  // like get(), but the first `keep_bytes` of an existing buffer survive a reallocation (synchronises `stream`)
+  void *get_keep(const std::string &name, size_t bytes, size_t keep_bytes, cudaStream_t stream);
   void *get_pinned(const std::string &name, size_t bytes);  // page-locked host memory
   int *error_flag();                                        // device int, zero-initialised
   int read_error_flag(cudaStream_t stream);                 // syncs the stream
@@ -110,3 +112,15 @@ int wb_parameter_modification_run(const double *d_f0_in, double *d_f0_out, int f
 int wb_pcm16_to_f64_run(const short *d_in, int n, double *d_out, cudaStream_t stream);
 int wb_f64_to_pcm16_run(const double *d_in, int n, short *d_out, cudaStream_t stream);
 int wb_f64_to_f32_run(const double *d_in, size_t n, float *d_out, cudaStream_t stream);
+
+// Streaming synthesis: frames arrive in pieces, samples are emitted as soon as no
+// later pulse can reach them; the concatenated output equals Synthesis::compute on all frames bit for bit
+// (phase sum, pulse list and randn() positions are carried between pieces).  wb_synthesis.cu.
+struct WbSynStream;
+WbSynStream *wb_synstream_create(int fs, int fft_size, double frame_period_ms, double f0_upper_bound);
+void wb_synstream_destroy(WbSynStream *s);
+// HOST pointers; sp / ap contiguous [n_frames][fft_size/2+1]; emits at most out_capacity samples
+int wb_synstream_push(WbSynStream *s, const double *f0, const double *sp, const double *ap, int n_frames, double *out,
+                      int out_capacity, int *n_out, cudaStream_t stream);
+// no more frames: emits the rest up to out_length_total (repeat until *n_out == 0 if out_capacity is short)
+int wb_synstream_finish(WbSynStream *s, int out_length_total, double *out, int out_capacity, int *n_out, cudaStream_t stream);

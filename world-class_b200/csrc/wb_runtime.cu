@@ -29,6 +29,26 @@ void *WbWorkspace::get(const std::string &name, size_t bytes) {
   return p;
 }
 
+void *WbWorkspace::get_keep(const std::string &name, size_t bytes, size_t keep_bytes, cudaStream_t stream) {
+  auto it = dev_.find(name);
+  if (it == dev_.end() || keep_bytes == 0 || it->second.bytes >= bytes) return get(name, bytes);
+  void *p = nullptr;
+  const size_t grow = 2 * bytes;   // geometric: an ever-growing history reallocates O(log n) times
+  if (cudaMalloc(&p, grow) != cudaSuccess) {
+    fprintf(stderr, "worldb200: cudaMalloc(%zu) failed for %s\n", grow, name.c_str());
+    return nullptr;
+  }
+  const size_t keep = keep_bytes < it->second.bytes ? keep_bytes : it->second.bytes;
+  if (cudaMemcpyAsync(p, it->second.p, keep, cudaMemcpyDeviceToDevice, stream) != cudaSuccess ||
+      cudaStreamSynchronize(stream) != cudaSuccess) {
+    cudaFree(p);
+    return nullptr;
+  }
+  cudaFree(it->second.p);
+  it->second = Buf{p, grow};
+  return p;
+}
+
 void *WbWorkspace::get_pinned(const std::string &name, size_t bytes) {
   if (bytes == 0) bytes = 8;
   auto it = pinned_.find(name);

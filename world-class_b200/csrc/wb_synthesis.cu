@@ -19,6 +19,7 @@
 #include "wb_fft.cuh"
 
 #include <math.h>
+#include <new>
 #include <vector>
 
 namespace {
@@ -26,9 +27,12 @@ namespace {
 // ---- K1: per-sample phase increment and VUV (synthesis.cpp:180-243) --------------------------
 __global__ void timebase_kernel(const double *__restrict__ f0, int f0_length, int fs, double frame_period,
                                 double lowest_f0, int y_length, double *__restrict__ incr,
-                                unsigned char *__restrict__ vuv) {
-  const int ii = blockIdx.x * blockDim.x + threadIdx.x;
+                                unsigned char *__restrict__ vuv, int sample_begin, int out_offset) {
+  // (streaming synthesis computes samples [sample_begin, y_length) into incr / vuv [out_offset ...])
+  const int ii = sample_begin + blockIdx.x * blockDim.x + threadIdx.x;
   if (ii >= y_length) return;
+  incr += out_offset - sample_begin;
+  vuv += out_offset - sample_begin;
   const double t = ii / (double)fs;
   // histc over coarse_time_axis[k] = k * frame_period, k = 0..f0_length:
   // index = first k with coarse_time_axis[k] > t, clamped to [1, f0_length]
@@ -407,7 +411,11 @@ __global__ void pulse_count_kernel(const double *__restrict__ total, int y_lengt
 
 __global__ void pulse_write_kernel(const double *__restrict__ total, int y_length, int fs,
                                    const unsigned long long *__restrict__ block_offsets,
-                                   int *__restrict__ pulse_index, double *__restrict__ pulse_shift, int max_pulses) {
+                                   int *__restrict__ pulse_index, double *__restrict__ pulse_shift, int max_pulses,
+                                   int index_offset, int slot_offset, const unsigned char *__restrict__ vuv_local,
+                                   unsigned char *__restrict__ pulse_vuv) {
+  // (streaming synthesis appends: `total` is a piece of the stream whose element 0 is sample index_offset, the
+  // pulses go to slots slot_offset + ..., and the voicing flag of the pulse's sample is kept per pulse)
   __shared__ int warp_cnt[PD_THREADS / 32];
   const int ii = blockIdx.x * PD_THREADS + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -423,14 +431,15 @@ __global__ void pulse_write_kernel(const double *__restrict__ total, int y_lengt
   int before = 0;
   for (int w = 0; w < warp; ++w) before += warp_cnt[w];
   if (flag) {
-    const long long slot = (long long)block_offsets[blockIdx.x] + before + __popc(m & ((1u << lane) - 1u));
+    const long long slot = (long long)slot_offset + (long long)block_offsets[blockIdx.x] + before + __popc(m & ((1u << lane) - 1u));
     if (slot < max_pulses) {
       const double two_pi = 2.0 * WB_PI;
       const double y1 = w0 - two_pi;
       const double y2 = w1;
       const double x = -y1 / (y2 - y1);
-      pulse_index[slot] = ii;
+      pulse_index[slot] = ii + index_offset;
       pulse_shift[slot] = x / fs;
+      if (pulse_vuv) pulse_vuv[slot] = vuv_local[ii];
     }
   }
 }
@@ -463,6 +472,7 @@ struct RespParams {
   // sample index range[2], sp / ap address frame `row_begin`; null = every pulse
   const int *range;
   int row_begin;
+  const unsigned char *pulse_vuv;   // streaming synthesis: voicing flag per pulse instead of per sample (null = use vuv)
 };
 
 // pulses whose response overlaps samples [sample_begin, sample_end), and the share of the noise stream
@@ -550,7 +560,7 @@ __global__ void __launch_bounds__(256, 3) response_kernel(RespParams p) {
       for (int i = tid; i < N; i += nt) resp[i] = 0.0;
       continue;
     }
-    const double current_vuv = p.vuv[idx] ? 1.0 : 0.0;
+    const double current_vuv = (p.pulse_vuv ? p.pulse_vuv[pulse] : p.vuv[idx]) ? 1.0 : 0.0;
     const double current_time = idx / (double)p.fs;
     const double frac_shift = p.pulse_shift[pulse];
 
@@ -695,6 +705,32 @@ static void make_dc_remover(int fft_size, std::vector<double> &r) {
   }
 }
 
+// exact running sum total[i] = fl(total[i-1] + incr[i]), total[0] = incr[0] (see the ps_* kernels)
+static int run_phase_scan(WbWorkspace *ws, const double *d_incr, int out_length, double *d_total, cudaStream_t stream) {
+  {
+    const int n_chunks = out_length > 1 ? (out_length - 1 + PS_CHUNK - 1) / PS_CHUNK : 0;
+    const int nc = n_chunks > 0 ? n_chunks : 1;
+    double *d_csum = (double *)ws->get("syn_ps_sum", sizeof(double) * nc);
+    double *d_cstart = (double *)ws->get("syn_ps_start", sizeof(double) * nc);
+    int *d_ce = (int *)ws->get("syn_ps_e", sizeof(int) * nc);
+    int *d_cbad = (int *)ws->get("syn_ps_bad", sizeof(int) * nc);
+    int *d_cexp = (int *)ws->get("syn_ps_expand", sizeof(int) * nc);
+    IncFn *d_cfn = (IncFn *)ws->get("syn_ps_fn", sizeof(IncFn) * nc);
+    if (!d_csum || !d_cstart || !d_ce || !d_cbad || !d_cexp || !d_cfn) return WB_ERR_CUDA;
+    if (n_chunks > 0) {
+      WB_LAUNCH("ps_chunk_sum_kernel", ps_chunk_sum_kernel<<<n_chunks, PS_THREADS, 0, stream>>>(d_incr, out_length, d_csum));
+      WB_LAUNCH("ps_binade_kernel", ps_binade_kernel<<<1, PS_THREADS, 0, stream>>>(d_incr, d_csum, n_chunks, d_ce));
+      WB_LAUNCH("ps_chunk_fn_kernel", ps_chunk_fn_kernel<<<n_chunks, PS_THREADS, 0, stream>>>(d_incr, out_length, d_ce, d_cfn, d_cbad));
+    }
+    WB_LAUNCH("phase_scan_kernel", ps_sequential_kernel<<<1, PS_THREADS, 0, stream>>>(d_incr, out_length, d_total, n_chunks, d_ce, d_cfn,
+                                                                                   d_cbad, d_cstart, d_cexp));
+    if (n_chunks > 0)
+      WB_LAUNCH("ps_expand_kernel", ps_expand_kernel<<<n_chunks, PS_THREADS, 0, stream>>>(d_incr, out_length, d_total, d_ce, d_cstart, d_cexp));
+  }
+  WB_CUDA_CHECK(cudaGetLastError());
+  return WB_OK;
+}
+
 // ---- host side -------------------------------------------------------------------------------
 // Part 1 (depends on f0 only): time base, exact phase scan, pulse list.  May run on a side
 // stream while CheapTrick / D4C are still busy.
@@ -720,31 +756,16 @@ int wb_synthesis_timebase(WbWorkspace *ws, int fs, int fft_size, double frame_pe
   unsigned long long *d_ncount = (unsigned long long *)ws->get("syn_ncount", sizeof(unsigned long long));
   if (!d_incr || !d_total || !d_vuv || !d_bc || !d_bo || !d_pidx || !d_pshift || !d_np || !d_ncount) return WB_ERR_CUDA;
   WB_LAUNCH("timebase_kernel", timebase_kernel<<<(out_length + 255) / 256, 256, 0, stream>>>(
-      d_f0, f0_length, fs, frame_period, lowest_f0, out_length, d_incr, d_vuv));
+      d_f0, f0_length, fs, frame_period, lowest_f0, out_length, d_incr, d_vuv, 0, 0));
   {
-    const int n_chunks = out_length > 1 ? (out_length - 1 + PS_CHUNK - 1) / PS_CHUNK : 0;
-    const int nc = n_chunks > 0 ? n_chunks : 1;
-    double *d_csum = (double *)ws->get("syn_ps_sum", sizeof(double) * nc);
-    double *d_cstart = (double *)ws->get("syn_ps_start", sizeof(double) * nc);
-    int *d_ce = (int *)ws->get("syn_ps_e", sizeof(int) * nc);
-    int *d_cbad = (int *)ws->get("syn_ps_bad", sizeof(int) * nc);
-    int *d_cexp = (int *)ws->get("syn_ps_expand", sizeof(int) * nc);
-    IncFn *d_cfn = (IncFn *)ws->get("syn_ps_fn", sizeof(IncFn) * nc);
-    if (!d_csum || !d_cstart || !d_ce || !d_cbad || !d_cexp || !d_cfn) return WB_ERR_CUDA;
-    if (n_chunks > 0) {
-      WB_LAUNCH("ps_chunk_sum_kernel", ps_chunk_sum_kernel<<<n_chunks, PS_THREADS, 0, stream>>>(d_incr, out_length, d_csum));
-      WB_LAUNCH("ps_binade_kernel", ps_binade_kernel<<<1, PS_THREADS, 0, stream>>>(d_incr, d_csum, n_chunks, d_ce));
-      WB_LAUNCH("ps_chunk_fn_kernel", ps_chunk_fn_kernel<<<n_chunks, PS_THREADS, 0, stream>>>(d_incr, out_length, d_ce, d_cfn, d_cbad));
-    }
-    WB_LAUNCH("phase_scan_kernel", ps_sequential_kernel<<<1, PS_THREADS, 0, stream>>>(d_incr, out_length, d_total, n_chunks, d_ce, d_cfn,
-                                                                                   d_cbad, d_cstart, d_cexp));
-    if (n_chunks > 0)
-      WB_LAUNCH("ps_expand_kernel", ps_expand_kernel<<<n_chunks, PS_THREADS, 0, stream>>>(d_incr, out_length, d_total, d_ce, d_cstart, d_cexp));
+    const int rc_scan = run_phase_scan(ws, d_incr, out_length, d_total, stream);
+    if (rc_scan) return rc_scan;
   }
   WB_LAUNCH("pulse_count_kernel", pulse_count_kernel<<<n_blocks, PD_THREADS, 0, stream>>>(d_total, out_length, d_bc));
   int rc = wb_exclusive_scan_u64(d_bc, d_bo, n_blocks, stream);
   if (rc) return rc;
-  WB_LAUNCH("pulse_write_kernel", pulse_write_kernel<<<n_blocks, PD_THREADS, 0, stream>>>(d_total, out_length, fs, d_bo, d_pidx, d_pshift, max_pulses));
+  WB_LAUNCH("pulse_write_kernel", pulse_write_kernel<<<n_blocks, PD_THREADS, 0, stream>>>(d_total, out_length, fs, d_bo, d_pidx, d_pshift, max_pulses,
+                                                                                        0, 0, nullptr, nullptr));
   WB_LAUNCH("pulse_finalize_kernel", pulse_finalize_kernel<<<1, 1, 0, stream>>>(d_bo, n_blocks, d_pidx, max_pulses, d_np, d_ncount, ws->error_flag()));
   WB_CUDA_CHECK(cudaGetLastError());
   if (noise_cursor) {
@@ -824,7 +845,7 @@ int wb_synthesis_render(WbWorkspace *ws, int fs, int fft_size, double frame_peri
   const size_t smem = sizeof(cplx) * (wb_fft_slots(fft_size) + binsp) + sizeof(double) * (2 * binsp + 128);
   p.max_resp_pulses = resp_pulses;
   p.error_flag = ws->error_flag();
-  p.range = nullptr; p.row_begin = 0;
+  p.range = nullptr; p.row_begin = 0; p.pulse_vuv = nullptr;
   const int grid = wb_min_i(resp_pulses, 148 * 9);
   rc = WB_DISPATCH_LOG2(log2n, 8, 13, {
     if (cudaFuncSetAttribute(response_kernel<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WB_ERR_CUDA;
@@ -861,10 +882,32 @@ static int upload_dc_remover(WbWorkspace *ws, int fft_size, double **out, cudaSt
 // stream are on `ws` (every rank computes them from the gathered f0: they are cheap and sequential); this
 // renders the pulses that reach into [sample_begin, sample_end) with their whole-stream noise positions and
 // overlap-adds them in the reference's order, so the samples equal those of an unsharded run bit for bit.
+struct PulseList {   // where the pulse list lives (workspace of a whole-stream time base, or a streaming synthesis)
+  const unsigned char *vuv; const unsigned char *pulse_vuv;
+  const int *pidx; const double *pshift; const int *np; const unsigned long long *ncount;
+};
+static int render_range_core(WbWorkspace *ws, int fs, int fft_size, double frame_period_ms, int f0_length,
+                             const double *d_sp, const double *d_ap, int row_begin, int n_rows, int out_length,
+                             int sample_begin, int sample_end, double *d_out, double f0_upper_bound,
+                             const WbRngCursor &rng, cudaStream_t stream, const PulseList &pl);
+
 int wb_synthesis_render_range(WbWorkspace *ws, int fs, int fft_size, double frame_period_ms, int f0_length,
                               const double *d_sp, const double *d_ap, int row_begin, int n_rows, int out_length,
                               int sample_begin, int sample_end, double *d_out, double f0_upper_bound,
                               const WbRngCursor &rng, cudaStream_t stream) {
+  PulseList pl;
+  pl.vuv = (unsigned char *)ws->get("syn_vuv", 0); pl.pulse_vuv = nullptr;
+  pl.pidx = (int *)ws->get("syn_pidx", 0); pl.pshift = (double *)ws->get("syn_pshift", 0);
+  pl.np = (int *)ws->get("syn_np", 0); pl.ncount = (unsigned long long *)ws->get("syn_ncount", 0);
+  if (!pl.vuv || !pl.pidx || !pl.pshift || !pl.np || !pl.ncount) return WB_ERR_CUDA;
+  return render_range_core(ws, fs, fft_size, frame_period_ms, f0_length, d_sp, d_ap, row_begin, n_rows, out_length,
+                           sample_begin, sample_end, d_out, f0_upper_bound, rng, stream, pl);
+}
+
+static int render_range_core(WbWorkspace *ws, int fs, int fft_size, double frame_period_ms, int f0_length,
+                             const double *d_sp, const double *d_ap, int row_begin, int n_rows, int out_length,
+                             int sample_begin, int sample_end, double *d_out, double f0_upper_bound,
+                             const WbRngCursor &rng, cudaStream_t stream, const PulseList &pl) {
   if (out_length <= 0) return WB_OK;
   if (sample_begin < 0 || sample_end > out_length || sample_begin > sample_end || row_begin < 0 || n_rows < 0 ||
       row_begin + n_rows > f0_length || !(f0_upper_bound > 0.0))
@@ -874,11 +917,11 @@ int wb_synthesis_render_range(WbWorkspace *ws, int fs, int fft_size, double fram
   if ((1 << log2n) != fft_size || fft_size < 128 || fft_size > 8192) return WB_ERR_UNSUPPORTED;
   const double frame_period = frame_period_ms / 1000.;
   const int n_samples = sample_end - sample_begin;
-  unsigned char *d_vuv = (unsigned char *)ws->get("syn_vuv", 0);
-  int *d_pidx = (int *)ws->get("syn_pidx", 0);
-  double *d_pshift = (double *)ws->get("syn_pshift", 0);
-  int *d_np = (int *)ws->get("syn_np", 0);
-  unsigned long long *d_ncount = (unsigned long long *)ws->get("syn_ncount", 0);
+  const unsigned char *d_vuv = pl.vuv;
+  const int *d_pidx = pl.pidx;
+  const double *d_pshift = pl.pshift;
+  const int *d_np = pl.np;
+  const unsigned long long *d_ncount = pl.ncount;
   // The pulses of the range sit in a window of n_samples + fft_size samples, and the noise of the last one
   // runs up to the next pulse: a voiced sample has f0 > lowest_f0 / 2 (interpolation towards an unvoiced
   // frame, synthesis.cpp:225-243), so pulses are less than 2 fs / lowest_f0 < 2 fft_size samples apart.
@@ -889,7 +932,7 @@ int wb_synthesis_render_range(WbWorkspace *ws, int fs, int fft_size, double fram
   double *d_dcr = nullptr;
   int rc = upload_dc_remover(ws, fft_size, &d_dcr, stream);
   if (rc) return rc;
-  if (!d_vuv || !d_pidx || !d_pshift || !d_np || !d_ncount || !d_noise || !d_range || !d_npos) return WB_ERR_CUDA;
+  if (!d_pidx || !d_pshift || !d_np || !d_noise || !d_range || !d_npos) return WB_ERR_CUDA;
   const cplx *tw_n = wb_twiddle_table(fft_size);
   const cplx *tw_2n = wb_twiddle_table(2 * fft_size);
   if (!tw_n || !tw_2n) return WB_ERR_CUDA;
@@ -911,7 +954,7 @@ int wb_synthesis_render_range(WbWorkspace *ws, int fs, int fft_size, double fram
     const size_t smem = sizeof(cplx) * (wb_fft_slots(fft_size) + binsp) + sizeof(double) * (2 * binsp + 128);
     p.max_resp_pulses = resp_pulses;
     p.error_flag = ws->error_flag();
-    p.range = d_range; p.row_begin = row_begin;
+    p.range = d_range; p.row_begin = row_begin; p.pulse_vuv = pl.pulse_vuv;
     const int grid = wb_min_i(resp_pulses, 148 * 9);
     rc = WB_DISPATCH_LOG2(log2n, 8, 13, {
       if (cudaFuncSetAttribute(response_kernel<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WB_ERR_CUDA;
@@ -933,4 +976,215 @@ int wb_synthesis_run(WbWorkspace *ws, int fs, int fft_size, double frame_period_
   if (rc) return rc;
   return wb_synthesis_render(ws, fs, fft_size, frame_period_ms, f0_length, d_sp, d_ap, out_length, d_out,
                              f0_upper_bound, rng, stream, false);
+}
+
+// ---- streaming synthesis ----------------------------------------------------------
+// Frames arrive in pieces.  Everything Synthesis::compute derives sequentially is carried between pieces --
+// the last phase sum and voicing flag of the time base (synthesis.cpp:257-264), the pulse list, the position
+// of the next pulse's noise in the randn() stream (synthesis.cpp:520) -- so the concatenated output equals one
+// compute() call on all frames, bit for bit.  Samples are emitted once no later pulse can reach them: a sample n
+// is final when every pulse up to n + fft_size/2 - 1 has been rendered, and a pulse can be rendered once its
+// successor is known (its noise segment ends there).  A sample t of the time base depends on frames
+// floor(t / frame_period) and the next one only, never on the (unknown) end of the contour, as long as the next
+// frame is a real one; the extrapolated last point (synthesis.cpp:193-199) is used at finish() only.
+struct WbSynStream {
+  int fs, fft_size;
+  double frame_period_ms, f0_bound;
+  WbWorkspace ws;
+  int frames = 0;        // frames received
+  int row_base = 0;      // first frame held in the sp / ap window
+  int tb_done = 0;       // samples whose phase sum is known
+  int out_done = 0;      // samples emitted
+  int n_pulses = 0;      // pulses found so far
+  int final_length = -1; // set by finish()
+  bool advanced = false; // randn() state moved past the stream
+  std::vector<int> h_pidx;   // host mirror of the pulse sample indices
+};
+
+WbSynStream *wb_synstream_create(int fs, int fft_size, double frame_period_ms, double f0_upper_bound) {
+  int log2n = 0;
+  while ((1 << log2n) < fft_size) ++log2n;
+  if (fs <= 0 || (1 << log2n) != fft_size || fft_size < 128 || fft_size > 8192 || !(frame_period_ms > 0.0)) return nullptr;
+  WbSynStream *s = new (std::nothrow) WbSynStream();
+  if (!s) return nullptr;
+  s->fs = fs; s->fft_size = fft_size; s->frame_period_ms = frame_period_ms;
+  s->f0_bound = f0_upper_bound > 0.0 ? f0_upper_bound : 1000.0;
+  return s;
+}
+void wb_synstream_destroy(WbSynStream *s) { delete s; }
+
+namespace {
+__global__ void synstream_count_kernel(const unsigned long long *__restrict__ block_offsets, int n_blocks, int *__restrict__ np) {
+  *np += (int)block_offsets[n_blocks];
+}
+
+// time base + exact phase sum + pulses of samples [s->tb_done, n_tb); f0_length = frames seen so far
+int synstream_timebase(WbSynStream *s, int n_tb, cudaStream_t stream) {
+  const int n_new = n_tb - s->tb_done;
+  if (n_new <= 0) return WB_OK;
+  WbWorkspace *ws = &s->ws;
+  const int off = s->tb_done > 0 ? 1 : 0;   // slot 0 of the local arrays carries the previous piece's last sample
+  const int m = n_new + off;
+  const double frame_period = s->frame_period_ms / 1000.;
+  const double lowest_f0 = s->fs / s->fft_size + 1.0;             // synthesis.cpp:97 (integer division)
+  double *d_f0 = (double *)ws->get("st_f0", 0);
+  double *d_incr = (double *)ws->get("st_incr", sizeof(double) * m);
+  double *d_total = (double *)ws->get("st_total", sizeof(double) * m);
+  unsigned char *d_vuv = (unsigned char *)ws->get("st_vuv", m);
+  double *d_carry = (double *)ws->get("st_carry", 16);             // [0] last phase sum, [1] (first byte) last voicing flag
+  const int n_blocks = (m + PD_THREADS - 1) / PD_THREADS;
+  unsigned long long *d_bc = (unsigned long long *)ws->get("syn_bcount", sizeof(unsigned long long) * (n_blocks + 1));
+  unsigned long long *d_bo = (unsigned long long *)ws->get("syn_boff", sizeof(unsigned long long) * (n_blocks + 1));
+  int *d_np = (int *)ws->get("st_np", sizeof(int) * 4);
+  // a piece of m samples holds at most m * f0_bound / fs + 2 pulses
+  const int cap_new = (int)((double)m * (s->f0_bound > WB_DEFAULT_F0 ? s->f0_bound : WB_DEFAULT_F0) / s->fs) + 4;
+  const int cap = s->n_pulses + cap_new;
+  int *d_pidx = (int *)ws->get_keep("st_pidx", sizeof(int) * cap, sizeof(int) * s->n_pulses, stream);
+  double *d_pshift = (double *)ws->get_keep("st_pshift", sizeof(double) * cap, sizeof(double) * s->n_pulses, stream);
+  unsigned char *d_pvuv = (unsigned char *)ws->get_keep("st_pvuv", cap, s->n_pulses, stream);
+  if (!d_f0 || !d_incr || !d_total || !d_vuv || !d_carry || !d_bc || !d_bo || !d_np || !d_pidx || !d_pshift || !d_pvuv) return WB_ERR_CUDA;
+  if (off) {
+    WB_CUDA_CHECK(cudaMemcpyAsync(d_incr, d_carry, sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    WB_CUDA_CHECK(cudaMemcpyAsync(d_vuv, d_carry + 1, 1, cudaMemcpyDeviceToDevice, stream));
+  }
+  WB_LAUNCH("timebase_kernel", timebase_kernel<<<(n_new + 255) / 256, 256, 0, stream>>>(
+      d_f0, s->frames, s->fs, frame_period, lowest_f0, n_tb, d_incr, d_vuv, s->tb_done, off));
+  int rc = run_phase_scan(ws, d_incr, m, d_total, stream);
+  if (rc) return rc;
+  WB_CUDA_CHECK(cudaMemcpyAsync(d_carry, d_total + (m - 1), sizeof(double), cudaMemcpyDeviceToDevice, stream));
+  WB_CUDA_CHECK(cudaMemcpyAsync(d_carry + 1, d_vuv + (m - 1), 1, cudaMemcpyDeviceToDevice, stream));
+  WB_LAUNCH("pulse_count_kernel", pulse_count_kernel<<<n_blocks, PD_THREADS, 0, stream>>>(d_total, m, d_bc));
+  if ((rc = wb_exclusive_scan_u64(d_bc, d_bo, n_blocks, stream))) return rc;
+  WB_LAUNCH("pulse_write_kernel", pulse_write_kernel<<<n_blocks, PD_THREADS, 0, stream>>>(d_total, m, s->fs, d_bo, d_pidx, d_pshift, cap,
+                                                                                      s->tb_done - off, s->n_pulses, d_vuv, d_pvuv));
+  WB_LAUNCH("synstream_count_kernel", synstream_count_kernel<<<1, 1, 0, stream>>>(d_bo, n_blocks, d_np));
+  WB_CUDA_CHECK(cudaGetLastError());
+  int h_np = 0;
+  WB_CUDA_CHECK(cudaMemcpyAsync(&h_np, d_np, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  WB_CUDA_CHECK(cudaStreamSynchronize(stream));
+  if (h_np < s->n_pulses || h_np > cap) return WB_ERR_ARG;   // f0 above the bound given at creation
+  if (h_np > s->n_pulses) {
+    s->h_pidx.resize(h_np);
+    WB_CUDA_CHECK(cudaMemcpyAsync(s->h_pidx.data() + s->n_pulses, d_pidx + s->n_pulses, sizeof(int) * (h_np - s->n_pulses),
+                                  cudaMemcpyDeviceToHost, stream));
+    WB_CUDA_CHECK(cudaStreamSynchronize(stream));
+  }
+  s->n_pulses = h_np;
+  s->tb_done = n_tb;
+  return WB_OK;
+}
+
+// renders and emits samples [s->out_done, out_new)
+int synstream_emit(WbSynStream *s, int out_new, int out_length_for_ola, double *out, cudaStream_t stream) {
+  const int count = out_new - s->out_done;
+  if (count <= 0) return WB_OK;
+  WbWorkspace *ws = &s->ws;
+  const int bins = s->fft_size / 2 + 1;
+  double *d_out = (double *)ws->get("st_out", sizeof(double) * count);
+  if (!d_out) return WB_ERR_CUDA;
+  PulseList pl;
+  pl.vuv = nullptr; pl.pulse_vuv = (unsigned char *)ws->get("st_pvuv", 0);
+  pl.pidx = (int *)ws->get("st_pidx", 0); pl.pshift = (double *)ws->get("st_pshift", 0);
+  pl.np = (int *)ws->get("st_np", 0); pl.ncount = nullptr;
+  WbRngCursor c;
+  c.state = wb_rng_global_state(); c.advance = false;   // the state moves once, when the stream is finished
+  const double *d_sp = (const double *)ws->get("st_sp", 0), *d_ap = (const double *)ws->get("st_ap", 0);
+  int rc = render_range_core(ws, s->fs, s->fft_size, s->frame_period_ms, s->frames, d_sp, d_ap, s->row_base,
+                             s->frames - s->row_base, out_length_for_ola, s->out_done, out_new, d_out, s->f0_bound, c, stream, pl);
+  if (rc) return rc;
+  WB_CUDA_CHECK(cudaMemcpyAsync(out, d_out, sizeof(double) * count, cudaMemcpyDeviceToHost, stream));
+  WB_CUDA_CHECK(cudaStreamSynchronize(stream));
+  if ((rc = ws->read_error_flag(stream))) return rc;
+  s->out_done = out_new;
+  // rows no future pulse interpolates any more (a pulse reaching into sample n sits at n - fft_size/2 or later)
+  const int keep_from = wb_max_i(0, (int)floor((double)(s->out_done - s->fft_size) / s->fs / (s->frame_period_ms / 1000.)) - 2);
+  if (keep_from > s->row_base) {
+    const size_t kept = (size_t)(s->frames - keep_from) * bins;
+    if (kept > 0) {
+      double *tmp = (double *)ws->get("st_rows_tmp", sizeof(double) * kept);
+      double *sp = (double *)ws->get("st_sp", 0), *ap = (double *)ws->get("st_ap", 0);
+      if (!tmp) return WB_ERR_CUDA;
+      const size_t shift = (size_t)(keep_from - s->row_base) * bins;
+      WB_CUDA_CHECK(cudaMemcpyAsync(tmp, sp + shift, sizeof(double) * kept, cudaMemcpyDeviceToDevice, stream));
+      WB_CUDA_CHECK(cudaMemcpyAsync(sp, tmp, sizeof(double) * kept, cudaMemcpyDeviceToDevice, stream));
+      WB_CUDA_CHECK(cudaMemcpyAsync(tmp, ap + shift, sizeof(double) * kept, cudaMemcpyDeviceToDevice, stream));
+      WB_CUDA_CHECK(cudaMemcpyAsync(ap, tmp, sizeof(double) * kept, cudaMemcpyDeviceToDevice, stream));
+    }
+    s->row_base = keep_from;
+  }
+  return WB_OK;
+}
+}  // namespace
+
+int wb_synstream_push(WbSynStream *s, const double *f0, const double *sp, const double *ap, int n_frames, double *out,
+                      int out_capacity, int *n_out, cudaStream_t stream) {
+  if (!s || !n_out || n_frames < 0 || out_capacity < 0 || (n_frames > 0 && (!f0 || !sp || !ap)) || (out_capacity > 0 && !out) ||
+      s->final_length >= 0)
+    return WB_ERR_ARG;
+  *n_out = 0;
+  WbWorkspace *ws = &s->ws;
+  const size_t bins = s->fft_size / 2 + 1;
+  if (n_frames > 0) {
+    const int total = s->frames + n_frames, held = s->frames - s->row_base;
+    double *d_f0 = (double *)ws->get_keep("st_f0", sizeof(double) * total, sizeof(double) * s->frames, stream);
+    double *d_sp = (double *)ws->get_keep("st_sp", sizeof(double) * (held + n_frames) * bins, sizeof(double) * held * bins, stream);
+    double *d_ap = (double *)ws->get_keep("st_ap", sizeof(double) * (held + n_frames) * bins, sizeof(double) * held * bins, stream);
+    int *d_np = (int *)ws->get("st_np", sizeof(int) * 4);
+    if (!d_f0 || !d_sp || !d_ap || !d_np) return WB_ERR_CUDA;
+    if (s->frames == 0) WB_CUDA_CHECK(cudaMemsetAsync(d_np, 0, sizeof(int) * 4, stream));
+    WB_CUDA_CHECK(cudaMemcpyAsync(d_f0 + s->frames, f0, sizeof(double) * n_frames, cudaMemcpyHostToDevice, stream));
+    WB_CUDA_CHECK(cudaMemcpyAsync(d_sp + (size_t)held * bins, sp, sizeof(double) * n_frames * bins, cudaMemcpyHostToDevice, stream));
+    WB_CUDA_CHECK(cudaMemcpyAsync(d_ap + (size_t)held * bins, ap, sizeof(double) * n_frames * bins, cudaMemcpyHostToDevice, stream));
+    WB_CUDA_CHECK(cudaStreamSynchronize(stream));   // the caller's buffers may be reused on return
+    s->frames = total;
+  }
+  if (s->frames < 2) return WB_OK;
+  // samples whose two frames are both real ones: t = ii / fs < (frames - 1) * frame_period, with the kernel's own expressions
+  const double frame_period = s->frame_period_ms / 1000.;
+  const double t_end = (s->frames - 1) * frame_period;
+  long long n_tb = (long long)(t_end * s->fs) - 2;
+  if (n_tb < 0) n_tb = 0;
+  while (n_tb < 2147483000LL && (double)n_tb / (double)s->fs < t_end) ++n_tb;
+  int rc = synstream_timebase(s, (int)n_tb, stream);
+  if (rc) return rc;
+  if (s->n_pulses < 2) return WB_OK;
+  // every pulse but the last known one can be rendered; samples up to (last known pulse) - fft_size/2 are final
+  int out_new = s->h_pidx[s->n_pulses - 1] - s->fft_size / 2 + 1;
+  if (out_new > s->out_done + out_capacity) out_new = s->out_done + out_capacity;
+  if (out_new <= s->out_done) return WB_OK;
+  const int before = s->out_done;
+  if ((rc = synstream_emit(s, out_new, 2147483647, out, stream))) return rc;
+  *n_out = s->out_done - before;
+  return WB_OK;
+}
+
+int wb_synstream_finish(WbSynStream *s, int out_length_total, double *out, int out_capacity, int *n_out, cudaStream_t stream) {
+  if (!s || !n_out || out_capacity < 0 || (out_capacity > 0 && !out) || s->frames < 2) return WB_ERR_ARG;
+  *n_out = 0;
+  if (s->final_length < 0) {
+    if (out_length_total < s->tb_done || out_length_total < s->out_done) return WB_ERR_ARG;   // shorter than what already went out
+    s->final_length = out_length_total;
+    int rc = synstream_timebase(s, out_length_total, stream);   // the rest, with the extrapolated last point
+    if (rc) return rc;
+  } else if (out_length_total != s->final_length) {
+    return WB_ERR_ARG;
+  }
+  int out_new = s->final_length;
+  if (out_new > s->out_done + out_capacity) out_new = s->out_done + out_capacity;
+  const int before = s->out_done;
+  int rc = synstream_emit(s, out_new, s->final_length, out, stream);
+  if (rc) return rc;
+  *n_out = s->out_done - before;
+  if (s->out_done == s->final_length && !s->advanced) {
+    // leave the randn() state where one compute() call would have left it: noise_size summed over the pulses
+    unsigned long long *h = (unsigned long long *)s->ws.get_pinned("st_ncount_h", sizeof(unsigned long long));
+    unsigned long long *d = (unsigned long long *)s->ws.get("st_ncount", sizeof(unsigned long long));
+    if (!h || !d) return WB_ERR_CUDA;
+    *h = s->n_pulses >= 2 ? (unsigned long long)(s->h_pidx[s->n_pulses - 1] - s->h_pidx[0]) : 0ull;
+    WB_CUDA_CHECK(cudaMemcpyAsync(d, h, sizeof(*h), cudaMemcpyHostToDevice, stream));
+    if ((rc = wb_rng_advance(wb_rng_global_state(), d, nullptr, stream))) return rc;
+    WB_CUDA_CHECK(cudaStreamSynchronize(stream));
+    s->advanced = true;
+  }
+  return WB_OK;
 }
