@@ -73,3 +73,37 @@ def test_device_sample_format_conversions(wb):
     assert np.array_equal(d_out.cpu().numpy(), _quantise(np.clip(x, -4, 4)))
     with np.errstate(over="ignore"):
         assert np.array_equal(d_f32.cpu().numpy(), x.astype(np.float32))
+
+
+def test_torch_tensor_front_end_matches_the_host_api(wb, signals):
+    """worldb200.tensors: the stages on CUDA tensors (device-pointer ABI on torch's current stream) give the bits
+    of the host-pointer class API."""
+    import torch
+    from worldb200 import tensors as wt
+    fs = 16000
+    x = signals.synth_speech(fs, 1.0, seed=23)
+    hopt = wb.HarvestOption(f0_floor=40.0, frame_period=5.0)
+    wb.randn_reseed()
+    tpos, f0 = wb.Harvest(fs, hopt).compute(x)
+    ct = wb.CheapTrick(fs)
+    sp = ct.compute(x, tpos, f0)
+    ap = wb.D4C(fs).compute(x, tpos, f0, ct.fft_size)
+    y = wb.Synthesis(fs, ct.fft_size, 5.0).compute(f0, sp, ap, wb.synthesis_length(len(f0), 5.0, fs))
+    csp = wb.CodeSpectralEnvelope(sp, fs, ct.fft_size, 24)
+    wb.randn_reseed()
+    d_x = torch.from_numpy(x).cuda()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):                      # a non-default torch stream: the calls must follow it
+        d_t, d_f0 = wt.harvest(d_x, fs, hopt)
+        d_sp = wt.cheaptrick(d_x, fs, d_t, d_f0)
+        d_ap = wt.d4c(d_x, fs, d_t, d_f0, ct.fft_size)
+        d_y = wt.synthesis(d_f0, d_sp, d_ap, fs, 5.0)
+        d_csp = wt.codec("code_sp", d_sp, fs, ct.fft_size, 24)
+        d_sp32 = wt.to_float32(d_sp)
+    s.synchronize()
+    assert np.array_equal(d_t.cpu().numpy(), tpos) and np.array_equal(d_f0.cpu().numpy(), f0)
+    assert np.array_equal(d_sp.cpu().numpy(), sp) and np.array_equal(d_ap.cpu().numpy(), ap)
+    assert np.array_equal(d_y.cpu().numpy(), y) and np.array_equal(d_csp.cpu().numpy(), csp)
+    assert np.array_equal(d_sp32.cpu().numpy(), sp.astype(np.float32))
+    with pytest.raises(ValueError):
+        wt.harvest(torch.zeros(10), fs)             # not a CUDA tensor
