@@ -752,6 +752,186 @@ __global__ void __launch_bounds__(RF_WARPS * 32) refine_kernel(RefineParams p) {
   }
 }
 
+// Symmetric formulation for analysis grids on which a frame time is a whole number of decimated samples
+// (actual_fs a multiple of 1000 Hz: 8 kHz for 16 / 24 / 32 / 48 / 96 kHz input).  There the window is sampled at
+// offsets j = i - (hw + 1), j = -(hw + 1) .. hw - 1, from its centre: the Blackman window is even and its
+// differentiated version odd in j, so the samples at +j and -j share one twiddle e^{i theta j}:
+//   main  += w_j [ (y_j + y_-j) cos + i (y_j - y_-j) sin ],   diff += d_j [ (y_j - y_-j) cos + i (y_j + y_-j) sin ]
+// i.e. 4 multiply-adds per PAIR and harmonic instead of 8, and one window evaluation per pair.  fixF0 only uses
+// |main|^2 and Im(conj(main) diff), which do not change when both spectra are referred to the window centre
+// instead of its first sample, so no phase factor is needed.  The five samples that have no partner or an end
+// rule (i = 0, 1, 2, hw + 1, 2 hw: harvest.cpp:794-803) are accumulated one by one.  The kernel is bound by fp64
+// issue; this removes ~40 % of its fp64 instructions.  An item whose centre is not on a sample (never on such
+// grids, checked per item) is accumulated sample by sample throughout.
+__global__ void __launch_bounds__(RF_WARPS * 32, 2) refine_sym_kernel(RefineParams p) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane & (RF_GROUP - 1), grp = lane / RF_GROUP;
+  const int nc = p.nc_and_count[0];
+  const int n_work = p.nc_and_count[1] * 7;
+  const int groups_per_warp = 32 / RF_GROUP;
+  const int total_groups = gridDim.x * RF_WARPS * groups_per_warp;
+  const double fs = p.actual_fs;
+  const double two_pi = 2.0 * WB_PI;
+  const int first = (blockIdx.x * RF_WARPS + warp) * groups_per_warp;
+  for (int base = first; base < n_work; base += total_groups) {
+    const int wi = base + grp;
+    bool active = wi < n_work;
+    const int item = active ? p.work[wi / 7] : 0;
+    const int o = wi % 7;
+    const int src = item >> 5, own_j = item & 31;
+    const int frame = (o <= 3) ? src + o : src - (o - 3);
+    const int slot = o * nc + own_j;
+    active = active && frame >= 0 && frame < p.f0_length;
+    const size_t at = (size_t)frame * p.max_candidates + slot;
+    const double current_f0 = active ? p.own[(size_t)src * p.own_cap + own_j] : 100.0;
+    const double current_position = frame * p.frame_period / 1000.0;
+    const int hw = static_cast<int>(1.5 * fs / current_f0 + 1.0);
+    const int len = active ? 2 * hw + 1 : 0;
+    const double window_length_in_time = (2.0 * hw + 1.0) / fs;
+    const int log2fft = 2 + (31 - __clz(2 * hw + 1));
+    const int fft_size = 1 << log2fft;
+    const double base_time0 = (-hw + 0) / fs;
+    const int basic_index = wb_round((current_position + base_time0) * fs + 0.001);
+    const int nh = wb_min_i(static_cast<int>(fs / 2.0 / current_f0), 6);
+    int idx[6];
+#pragma unroll
+    for (int hh = 0; hh < 6; ++hh) idx[hh] = wb_round(current_f0 * fft_size / fs * (hh + 1));
+    double mr[6], mi[6], dr[6], di[6];
+#pragma unroll
+    for (int hh = 0; hh < 6; ++hh) { mr[hh] = mi[hh] = dr[hh] = di[hh] = 0.0; }
+    const cplx *T = p.tw[log2fft];
+    const int mask = fft_size - 1;
+    double s1, c1, sg, cg;
+    sincos(two_pi / (2 * hw + 1), &s1, &c1);
+    sincos(two_pi * RF_GROUP / (2 * hw + 1), &sg, &cg);
+    const double dw_a = 0.5 * s1, dw_b = 0.16 * (2.0 * s1 * c1);   // differentiated window in closed form (see refine_kernel)
+    const int i_c = hw + 1;   // the sample the window is centred on
+    // the reference's own expression for the window argument of that sample: zero when the centre is on the grid
+    const double centre = ((basic_index + i_c) - 1.0) / fs - current_position;
+    const bool symmetric = fabs(centre) * fs < 1e-6;
+    const int y_first = basic_index - 1, y_last = p.y_length - 1;
+    // one sample, by the reference's expressions (twiddle referred to the centre sample)
+    auto single = [&](int i) {
+      const double tmp = ((basic_index + i) - 1.0) / fs - current_position;
+      double sn, cs;
+      sincos(two_pi * tmp / window_length_in_time, &sn, &cs);
+      const double yv = p.y[wb_max_i(0, wb_min_i(y_last, y_first + i))];
+      const double w_here = rf_window(cs);
+      double dwin = sn * fma(dw_b, cs, dw_a);
+      if (i == 0) dwin = -rf_window(cs * c1 - sn * s1) / 2.0;            // -w[1] / 2
+      else if (i == len - 1) dwin = rf_window(cs * c1 + sn * s1) / 2.0;  // w[len - 2] / 2
+      const double vm = w_here * yv, vd = dwin * yv;
+#pragma unroll
+      for (int hh = 0; hh < 6; ++hh) {
+        if (hh < nh) {
+          const cplx w = __ldg(&T[(idx[hh] * (i - i_c)) & mask]);
+          mr[hh] = fma(vm, w.x, mr[hh]); mi[hh] = fma(vm, w.y, mi[hh]);
+          dr[hh] = fma(vd, w.x, dr[hh]); di[hh] = fma(vd, w.y, di[hh]);
+        }
+      }
+    };
+    if (!symmetric) {
+      for (int i = sub; i < len; i += RF_GROUP) single(i);
+    } else if (len > 0) {
+      // unpaired samples and the two with an end rule (and their partners): i = 0, 1, 2, hw + 1, 2 hw
+      if (sub < 5) {
+        const int i = sub == 0 ? 0 : (sub == 1 ? 1 : (sub == 2 ? 2 : (sub == 3 ? i_c : 2 * hw)));
+        // (hw >= 2 always: f0 <= f0_ceil * 1.1 well below 1.5 fs / 2; for tiny windows some of these coincide)
+        bool dup = false;
+        if (sub == 3) dup = (i <= 2);
+        if (sub == 4) dup = (i <= 2 || i == i_c);
+        if (!dup && i < len) single(i);
+      }
+      // pairs j = 1 .. hw - 2  (samples i_c + j and i_c - j; i_c - j >= 3, i_c + j <= 2 hw - 1)
+      double sn, cs;
+      sincos(two_pi * (1 + sub) / (2 * hw + 1), &sn, &cs);
+      for (int j = 1 + sub; j <= hw - 2; j += RF_GROUP) {
+        const double yp = p.y[wb_max_i(0, wb_min_i(y_last, y_first + i_c + j))];
+        const double ym = p.y[wb_max_i(0, wb_min_i(y_last, y_first + i_c - j))];
+        const double w_here = fma(cs, fma(0.16, cs, 0.5), 0.34);
+        const double dwin = sn * fma(dw_b, cs, dw_a);
+        const double ys = yp + ym, yd = yp - ym;
+        const double a = w_here * ys, b = w_here * yd, c = dwin * yd, e = dwin * ys;
+#pragma unroll
+        for (int hh = 0; hh < 6; ++hh) {
+          if (hh < nh) {
+            const cplx w = __ldg(&T[(idx[hh] * j) & mask]);
+            mr[hh] = fma(a, w.x, mr[hh]); mi[hh] = fma(b, w.y, mi[hh]);
+            dr[hh] = fma(c, w.x, dr[hh]); di[hh] = fma(e, w.y, di[hh]);
+          }
+        }
+        const double c2 = fma(cs, cg, -(sn * sg));
+        sn = fma(sn, cg, cs * sg);
+        cs = c2;
+      }
+    }
+    // reduce-scatter over the 8 lanes and fixF0: as in refine_kernel
+    double my_mr, my_mi, my_dr, my_di;
+    {
+      const bool up4 = (sub & 4) != 0, up2 = (sub & 2) != 0, up1 = (sub & 1) != 0;
+      double a4[4][4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const double lo[4] = {mr[q], mi[q], dr[q], di[q]};
+        const bool has_hi = q < 2;
+        const int qh = has_hi ? q + 4 : 0;
+        const double hi[4] = {has_hi ? mr[qh] : 0.0, has_hi ? mi[qh] : 0.0, has_hi ? dr[qh] : 0.0, has_hi ? di[qh] : 0.0};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const double send = up4 ? lo[c] : hi[c];
+          a4[q][c] = (up4 ? hi[c] : lo[c]) + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+      }
+      double a2[2][4];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const double send = up2 ? a4[q][c] : a4[q + 2][c];
+          a2[q][c] = (up2 ? a4[q + 2][c] : a4[q][c]) + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+      }
+      double a1[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const double send = up1 ? a2[0][c] : a2[1][c];
+        a1[c] = (up1 ? a2[1][c] : a2[0][c]) + __shfl_xor_sync(0xffffffffu, send, 1);
+      }
+      my_mr = a1[0]; my_mi = a1[1]; my_dr = a1[2]; my_di = a1[3];
+    }
+    double my_inst = 0.0, my_amp = 0.0, my_dev = 0.0;
+    {
+      const double m_re = my_mr, m_im = -my_mi, d_re = my_dr, d_im = -my_di;
+      const int my_idx = wb_round(current_f0 * fft_size / fs * (sub + 1));
+      const double power = m_re * m_re + m_im * m_im;
+      const double num_i = m_re * d_im - m_im * d_re;
+      my_inst = (power == 0.0) ? 0.0
+                : static_cast<double>(my_idx) * fs / fft_size + num_i / power * fs / 2.0 / WB_PI;
+      my_amp = sqrt(power);
+      my_dev = fabs((my_inst / (sub + 1.0) - current_f0) / current_f0);
+    }
+    double numerator = 0.0, denominator = 0.0, score = 0.0;
+#pragma unroll
+    for (int hh = 0; hh < 6; ++hh) {
+      const double inst = __shfl_sync(0xffffffffu, my_inst, hh, RF_GROUP);
+      const double amp = __shfl_sync(0xffffffffu, my_amp, hh, RF_GROUP);
+      const double dev = __shfl_sync(0xffffffffu, my_dev, hh, RF_GROUP);
+      if (hh < nh) {
+        numerator += amp * inst;
+        denominator += amp * (hh + 1.0);
+        score += dev;
+      }
+    }
+    if (sub == 0 && active) {
+      double refined = numerator / (denominator + WB_SAFEGUARD);
+      double sc = 1.0 / (score / nh + WB_SAFEGUARD);
+      if (refined < p.f0_floor || refined > p.f0_ceil || sc < 2.5) { refined = 0.0; sc = 0.0; }
+      p.cand[at] = refined;
+      p.score[at] = sc;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // removeUnreliableCandidates (harvest.cpp:708-744): one thread per (frame, slot)
 // ---------------------------------------------------------------------------------------------
@@ -1021,7 +1201,14 @@ int wb_harvest_run_basic(WbHarvestPlan *pl, WbWorkspace *ws, const double *d_x, 
       p.tw[l] = wb_twiddle_table(1 << l);
       if (!p.tw[l]) return WB_ERR_CUDA;
     }
-    WB_LAUNCH("refine_kernel", refine_kernel<<<148 * 8, RF_WARPS * 32, 0, stream>>>(p));
+    // frame times fall on whole decimated samples when actual_fs is a multiple of 1000 Hz (1 ms analysis grid)
+    static const int refine_variant = getenv("WB_REFINE") ? atoi(getenv("WB_REFINE")) : 3;
+    const bool on_grid = frame_period == 1 && fabs(afs / 1000.0 - floor(afs / 1000.0 + 0.5)) < 1e-9;
+    if (refine_variant == 3 && on_grid) {
+      WB_LAUNCH("refine_kernel", refine_sym_kernel<<<148 * 8, RF_WARPS * 32, 0, stream>>>(p));
+    } else {
+      WB_LAUNCH("refine_kernel", refine_kernel<<<148 * 8, RF_WARPS * 32, 0, stream>>>(p));
+    }
     WB_CUDA_CHECK(cudaGetLastError());
   }
   WB_LAUNCH("remove_kernel", remove_kernel<<<(unsigned)((n_cs + 255) / 256), 256, 0, stream>>>(d_candA, d_scoreA, d_nc, Lb, MC, d_candB, d_scoreB));
