@@ -515,21 +515,23 @@ __device__ __forceinline__ void minimum_phase(cplx *S, cplx *MP, const cplx *tw_
   for (int i = NC + 1 + threadIdx.x; i < N; i += blockDim.x) W[wb_didx(i)] = W[wb_didx(N - i)];
   __syncthreads();
   // "inverse_fft" is a forward r2c in the reference; sign flips / doubling at :203-209
+  // The mirrored log spectrum is real and even, so its transform -- the cepstrum -- is real: the reference carries
+  // imaginary parts that are pure rounding noise (~1e-16 of the real parts) into its complex N-point transform.
+  // Dropping them makes the folded cepstrum a REAL sequence with a zero upper half, and its first N/2 + 1 bins
+  // come from a real transform (a half-size complex FFT) instead of a full complex one.
   wb_rfft_t<1, LOG2N - 1>(S, tw_n, [&](int k, cplx X) {
-    if (k == 0 || k == NC) MP[k] = make_double2(X.x, X.y * -1.0);
-    else MP[k] = make_double2(X.x * 2.0, X.y * -2.0);
+    MP[k].x = (k == 0 || k == NC) ? X.x : X.x * 2.0;
   });
-  for (int i = threadIdx.x; i < N; i += blockDim.x) S[wb_sidx(i)] = (i <= NC) ? MP[i] : make_double2(0.0, 0.0);
+  for (int i = threadIdx.x; i < N; i += blockDim.x) W[wb_didx(i)] = (i <= NC) ? MP[i].x : 0.0;
   __syncthreads();
-  wb_cfft_dif_t<1, LOG2N>(S, tw_2n);  // c2c FFT_FORWARD
-  for (int k = threadIdx.x; k <= NC; k += blockDim.x) {
-    const cplx v = S[wb_sidx(wb_brev(k, log2n))];
-    const double tmp = exp(v.x / N);
+  wb_rfft_t<1, LOG2N - 1>(S, tw_n, [&](int k, cplx X) {   // first half of the reference's c2c FFT_FORWARD
+    const double tmp = exp(X.x / N);
     double sn, cs;
-    sincos(v.y / N, &sn, &cs);
+    sincos(X.y / N, &sn, &cs);
     MP[k] = make_double2(tmp * cs, tmp * sn);
-  }
+  });
   __syncthreads();
+  (void)tw_2n; (void)log2n;
 }
 
 template <int LOG2N>
