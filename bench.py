@@ -42,6 +42,14 @@ def c2c_bytes(n):
     return 32 * n
 
 
+def r2c_flops(n):  # butterflies of one real transform (honesty note ii: the second bound is fp64)
+    return 2.5 * n * np.log2(n)
+
+
+def c2c_flops(n):
+    return 5.0 * n * np.log2(n)
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
 
@@ -274,12 +282,14 @@ def main():
         own = pl.debug_read("hv_own", (Lb, own_cap))[:, :max(nc, 1)]
         # overlapF0Candidates replicates every own candidate to frames k-3..k+3 (harvest.cpp:987-1000)
         refine_bytes = 0
+        refine_flops = 0.0
         f = own[own > 0]
         if f.size:
             hw = (1.5 * afs / f + 1.0).astype(np.int64)
             n_i = 1 << (2 + np.floor(np.log2(2 * hw + 1)).astype(np.int64))
             per = 2 * (8 * n_i + 16 * (n_i // 2 + 1))
             refine_bytes = int(7 * per.sum())   # edge frames lose a few copies: <0.1 %
+            refine_flops = float(7 * (2 * 2.5 * n_i * np.log2(n_i)).sum())
         y_len = 1 + n // r
         n_h = 1 << int(np.floor(np.log2(y_len + 4 * int(1.0 + afs / (40.0 * 0.9 * 2 ** (1 / 40.0)) / 2.0))) + 1)
         n_pulses = int(pl.debug_read("syn_np", (1,), dtype=np.int32)[0])
@@ -292,6 +302,20 @@ def main():
             "refine_kernel": refine_bytes,
             "response_kernel": n_pulses * (5 * r2c_bytes(fft_size) + 2 * c2c_bytes(fft_size)),
         }
+        alg_flops = {
+            "ct_frame_kernel": 3 * L * r2c_flops(fft_size),
+            "lt_frame_kernel": voiced_lt * r2c_flops(n_lt),
+            "d4c_body_kernel": voiced_body * (5 + n_ap) * r2c_flops(n_d4c),
+            "channel_kernel": 2 * nch * r2c_flops(n_h),
+            "yspec_kernel": r2c_flops(n_h),
+            "refine_kernel": refine_flops,
+            "response_kernel": n_pulses * (5 * r2c_flops(fft_size) + 2 * c2c_flops(fft_size)),
+        }
+        fp64_peak = None
+        try:
+            fp64_peak = wb.measure_fp64_peak()      # TFLOP/s, measured on this GPU now (MEASURED_PEAKS.json has no fp64 entry)
+        except Exception:
+            pass
         dom = max(kernel_table.items(), key=lambda kv: kv[1][0])[0] if kernel_table else None
         peaks = {}
         try:
@@ -316,6 +340,16 @@ def main():
                         "kernel_share_of_step": tot_ms / max(sum(v[0] for v in kernel_table.values()), 1e-9),
                         "algorithmic_bytes_per_step_all_kernels": int(sum(alg.values())),
                         "whole_chain_frac": (sum(alg.values()) / (ms_per_step / 1e3) / 1e9) / peak}
+            if fp64_peak:
+                f_dom = float(alg_flops.get(dom) or 0.0)
+                f_all = float(sum(alg_flops.values()))
+                roofline["fp64"] = {
+                    "peak": fp64_peak, "unit": "TFLOP/s", "peak_source": "measured now: independent DFMA chains on every SM (wb_measure_fp64_peak)",
+                    "achieved": f_dom / (avg_ms / 1e3) / 1e12, "frac": f_dom / (avg_ms / 1e3) / 1e12 / fp64_peak,
+                    "whole_chain_achieved": f_all / (ms_per_step / 1e3) / 1e12,
+                    "whole_chain_frac": f_all / (ms_per_step / 1e3) / 1e12 / fp64_peak,
+                    "algorithmic_gflop_per_step": f_all / 1e9,
+                    "model": "butterflies of the transforms the ALGORITHM executes: 2.5 N log2 N per real, 5 N log2 N per complex transform (SURVEY.md 8d)"}
 
     # ---- extra (not the headline): BASELINE configs[2]-style batch, independent 22.05 kHz / 5 s utterances on
     # concurrent streams of this GPU (each utterance == one reference process)

@@ -268,6 +268,7 @@ int wb_wavread_pcm16(const char *filename, int *fs, short *pcm);  /* the raw 16-
 
 /* ---- measurement hooks (bench.py) ------------------------------------------------------ */
 unsigned long long wb_launch_count(void);  /* kernels launched by this library so far */
+int wb_measure_fp64_peak(double *tflops);  /* dependent-free DFMA chains on every SM: the fp64 roofline of this GPU */
 void *wb_stream(void);                     /* the library's own cudaStream_t */
 void wb_profile_enable(int on);            /* bracket every kernel launch with CUDA events */
 void wb_profile_reset(void);

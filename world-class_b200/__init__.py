@@ -138,6 +138,7 @@ def _declare(L):
         "wb_wavread": (ci, [ctypes.c_char_p, ctypes.POINTER(ci), ctypes.POINTER(ci), vp]),
         "wb_wavread_pcm16": (ci, [ctypes.c_char_p, ctypes.POINTER(ci), vp]),
         "wb_launch_count": (ctypes.c_ulonglong, []),
+        "wb_measure_fp64_peak": (ci, [ctypes.POINTER(cd)]),
         "wb_stream": (vp, []),
         "wb_profile_enable": (None, [ci]),
         "wb_profile_reset": (None, []),
@@ -519,6 +520,13 @@ class Pipeline:
 # ---- measurement hooks ------------------------------------------------------------------------
 def launch_count():
     return int(lib().wb_launch_count())
+
+
+def measure_fp64_peak():
+    """fp64 multiply-add throughput of the current GPU in TFLOP/s (measured, a few milliseconds)"""
+    v = ctypes.c_double()
+    _check(lib().wb_measure_fp64_peak(ctypes.byref(v)), "wb_measure_fp64_peak")
+    return v.value
 
 
 def stream_handle():

@@ -1298,6 +1298,12 @@ int wb_pipeline_debug_read(wb_pipeline_t *p, const char *name, void *out, unsign
 }
 
 // ---- measurement hooks ---------------------------------------------------------------------
+int wb_measure_fp64_peak(double *tflops) {
+  int rc = ctx_init();
+  if (rc) return rc;
+  return wb_measure_fp64_peak_tflops(tflops);
+}
+
 unsigned long long wb_launch_count(void) { return wb_launch_counter(); }
 void *wb_stream(void) { return ctx_init() ? nullptr : (void *)g_stream; }
 void wb_profile_enable(int on) { wb_prof_set_enabled(on); }

@@ -124,3 +124,6 @@ int wb_synstream_push(WbSynStream *s, const double *f0, const double *sp, const 
                       int out_capacity, int *n_out, cudaStream_t stream);
 // no more frames: emits the rest up to out_length_total (repeat until *n_out == 0 if out_capacity is short)
 int wb_synstream_finish(WbSynStream *s, int out_length_total, double *out, int out_capacity, int *n_out, cudaStream_t stream);
+
+// measured fp64 multiply-add throughput of the current device in TFLOP/s (wb_runtime.cu)
+int wb_measure_fp64_peak_tflops(double *tflops_out);

@@ -232,3 +232,42 @@ void wb_prof_reset() {
   std::lock_guard<std::mutex> lock(g_prof_mutex);
   g_totals.clear();
 }
+
+// ---- fp64 multiply-add peak of this GPU (bench.py: the second roofline next to HBM bandwidth) ----
+namespace {
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double *__restrict__ sink, int iters, double a, double b) {
+  // eight independent chains per thread: enough to cover the fp64 pipe latency at 8 warps per scheduler
+  double x0 = threadIdx.x, x1 = x0 + 1.0, x2 = x0 + 2.0, x3 = x0 + 3.0, x4 = x0 + 4.0, x5 = x0 + 5.0, x6 = x0 + 6.0, x7 = x0 + 7.0;
+#pragma unroll 4
+  for (int i = 0; i < iters; ++i) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (s == 0.123456789) sink[0] = s;   // keeps the chains alive; practically never taken
+}
+}  // namespace
+
+int wb_measure_fp64_peak_tflops(double *tflops_out) {
+  if (!tflops_out) return WB_ERR_ARG;
+  cudaStream_t stream = nullptr;
+  double *d_sink = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (cudaMalloc(&d_sink, sizeof(double)) != cudaSuccess) return WB_ERR_CUDA;
+  if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) { cudaFree(d_sink); return WB_ERR_CUDA; }
+  const int grid = 148 * 8, threads = 256, iters = 1 << 15;
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {   // first repetition = warm-up
+    cudaEventRecord(e0, stream);
+    WB_LAUNCH("dfma_peak_kernel", dfma_peak_kernel<<<grid, threads, 0, stream>>>(d_sink, iters, 0.999999, 1e-9));
+    cudaEventRecord(e1, stream);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(d_sink); return WB_ERR_CUDA; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double tf = 2.0 * 8.0 * (double)iters * (double)grid * threads / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_sink);
+  *tflops_out = best;
+  return WB_OK;
+}
