@@ -50,13 +50,25 @@ __device__ inline int d4c_windowed_waveform(const double *__restrict__ x, int x_
     sincos(c2 * (c1 * ((int)threadIdx.x - hw)), &sn, &cs);
   }
   double s1 = 0.0, s2 = 0.0;
+  // (the waveform and noise samples of the NEXT step are requested before this step's arithmetic: the loop used
+  // to sit on these two loads)
+  double x_next = 0.0, n_next = 0.0;
+  if ((int)threadIdx.x < wlen) {
+    x_next = x[wb_min_i(x_length - 1, wb_max_i(0, origin + (int)threadIdx.x - hw))];
+    n_next = noise[threadIdx.x];
+  }
   for (int j = threadIdx.x; j < wlen; j += blockDim.x) {
+    const double x_here = x_next, n_here = n_next;
+    const int jn = j + blockDim.x;
+    if (jn < wlen) {
+      x_next = x[wb_min_i(x_length - 1, wb_max_i(0, origin + jn - hw))];
+      n_next = noise[jn];
+    }
     double w;
     if (window_type == D4C_HANNING) w = 0.5 * cs + 0.5;
     else w = 0.42 + 0.5 * cs + 0.08 * (2.0 * cs * cs - 1.0);
     win(j) = w;
-    const int idx = wb_min_i(x_length - 1, wb_max_i(0, origin + j - hw));
-    const double v = x[idx] * w + noise[j] * WB_SAFEGUARD;
+    const double v = x_here * w + n_here * WB_SAFEGUARD;
     at(j) = v;
     s1 += v;
     s2 += w;
@@ -476,14 +488,22 @@ __global__ void __launch_bounds__(D4C_BODY_THREADS, 2) d4c_body_kernel(BodyParam
       double sn = rot_sn, cs = rot_cs;
       double v[16], w[16];
       double s1 = 0.0, s2 = 0.0;
+      // all waveform / noise loads first (independent: they overlap), parked in v[] / w[] until they are used
 #pragma unroll
       for (int q = 0; q < 16; ++q) {
         const int j = tid + q * D4C_BODY_THREADS;
         v[q] = 0.0; w[q] = 0.0;
         if (j < wlen) {
+          v[q] = p.x[wb_min_i(p.x_length - 1, wb_max_i(0, origin + j - hw))];
+          w[q] = noise[j];
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const int j = tid + q * D4C_BODY_THREADS;
+        if (j < wlen) {
           const double wq = 0.42 + 0.5 * cs + 0.08 * (2.0 * cs * cs - 1.0);
-          const int idx = wb_min_i(p.x_length - 1, wb_max_i(0, origin + j - hw));
-          const double vq = p.x[idx] * wq + noise[j] * WB_SAFEGUARD;
+          const double vq = v[q] * wq + w[q] * WB_SAFEGUARD;
           v[q] = vq; w[q] = wq;
           s1 += vq;
           s2 += wq;
