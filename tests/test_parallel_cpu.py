@@ -148,3 +148,37 @@ def test_gather_ranges_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def test_stream_plan_properties_hypothesis():
+    """Randomised: any stream length / world size keeps the partition, grid-alignment and coverage invariants."""
+    hypothesis = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st
+    import worldb200  # noqa: F401
+    from worldb200 import parallel as P
+
+    @settings(max_examples=60, deadline=None)
+    @given(fs=st.sampled_from([16000, 22050, 24000, 32000, 44100, 48000]), seconds=st.floats(0.6, 400.0), world=st.integers(1, 9),
+           seg=st.integers(1, 40), halo=st.integers(1, 3), extra=st.integers(0, 11))
+    def check(fs, seconds, world, seg, halo, extra):
+        n = int(seconds * fs) + extra
+        fft = 2048 if fs >= 44100 else 1024
+        pl = P.StreamPlan(n, fs, world, 5.0, fft, segment_seconds=seg, halo_seconds=halo)
+        r = P.decimation_ratio(fs)
+        assert pl.frames[0][0] == 0 and pl.frames[-1][1] == pl.f0_length
+        assert pl.samples[0][0] == 0 and pl.samples[-1][1] == pl.out_length
+        for k in range(world):
+            fb, fe = pl.frames[k]
+            assert fb <= fe and (k == 0 or fb == pl.frames[k - 1][1])
+            sa, sb = pl.samples[k]
+            assert sa <= sb and (k == 0 or sa == pl.samples[k - 1][1])
+            covered = fb
+            for s in pl.segments[k]:
+                pa, pb = s["padded"]
+                assert s["frames"][0] == covered and pa % fs == 0 and (pb - n) % r == 0 and 0 <= pa < pb <= n
+                assert s["frames"][1] - s["frame_offset"] <= int(1000.0 * (pb - pa) / fs / 5.0) + 1
+                covered = s["frames"][1]
+            assert covered == fe
+            ra, rb = pl.rows[k]
+            assert 0 <= ra <= fb and fe <= rb <= pl.f0_length
+    check()
