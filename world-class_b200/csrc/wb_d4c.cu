@@ -431,7 +431,10 @@ struct BodyParams {
 //         in its upper half, as window scratch while only a packed real transform lives in it
 //   SC  : static centroid -> static group delay
 //   SP  : smoothed power  -> second smoothing output -> band power spectrum
-template <int LOG2N>
+// WARP_BANDS (EXPERIMENTAL, off unless WB_D4C_WARP_BANDS=1; written at the end of round 1 without GPU time left to
+// measure it -- see DESIGN.md section 8, item 1a): the band-pair transform as eight independent 512-point
+// transforms, one per warp.  Only for N = 4096 and band slices of at most N/8 + 1 samples.
+template <int LOG2N, bool WARP_BANDS = false>
 __global__ void __launch_bounds__(D4C_BODY_THREADS, 2) d4c_body_kernel(BodyParams p) {
   extern __shared__ double2 smem_raw[];
   constexpr int N = 1 << LOG2N, NC = N / 2, bins = NC + 1;
@@ -600,6 +603,55 @@ __global__ void __launch_bounds__(D4C_BODY_THREADS, 2) d4c_body_kernel(BodyParam
       int4 *h4 = reinterpret_cast<int4 *>(SP);
       for (int i = tid; i < N / 4; i += nt) h4[i] = make_int4(0, 0, 0, 0);
     }
+    if constexpr (WARP_BANDS && LOG2N == 12) {
+      // The slice z[n] has at most N/8 + 1 = 513 non-zero samples, so Z[8 q + r] = sum_n (z[n] W_N^{n r}) W_512^{n q}
+      // (+ z[512] W_N^{512 r}, which does not depend on q: it joins sample 0): warp r transforms the slice
+      // modulated by W_N^{n r} with a 512-point FFT of its own -- lane l holds samples l + 32 t, a radix-16
+      // butterfly over t, an exchange through a warp-private staging area, a radix-16 butterfly over the 32-point
+      // sub-transforms' even / odd halves and a final radix-2 by shuffle.  No block barrier inside; ¾ of the
+      // butterflies of the padded 4096-point transform.  Output in NATURAL order (model: profiles/band_fft_model.py).
+      const int r = tid >> 5, l = tid & 31;
+      const cplx *T = p.tw_2n;                       // e^{2 pi i k / 8192}
+      cplx a[16];
+#pragma unroll
+      for (int t = 0; t < 16; ++t) {
+        const int n = l + 32 * t;
+        cplx z = make_double2(0.0, 0.0);
+        if (n < wl) {
+          const double nw = __ldg(&p.nuttall[n]);
+          z.x = SC[center_a - hwl + n] * nw;
+          if (has2) z.y = SC[center_b - hwl + n] * nw;
+        }
+        if (r) z = wb_cmul(z, wb_tw<1>(T, (2 * n * r) & (2 * N - 1)));
+        a[t] = z;
+      }
+      if (l == 0 && wl > 512) {                      // sample 512 folds onto sample 0 of every residue
+        const double nw = __ldg(&p.nuttall[512]);
+        cplx z2 = make_double2(SC[center_a - hwl + 512] * nw, has2 ? SC[center_b - hwl + 512] * nw : 0.0);
+        z2 = wb_cmul(z2, wb_tw<1>(T, (1024 * r) & (2 * N - 1)));
+        a[0] = wb_cadd(a[0], z2);
+      }
+      wb_dft16<1>(a);
+      if (l) wb_apply_twiddles16<1>(T, 16 * l, a);   // a[p] *= W_512^{l p}
+      cplx *stage = S + r * 544;                     // 16 sub-transforms x (32 + 2 padding) slots per warp
+#pragma unroll
+      for (int q = 0; q < 16; ++q) stage[q * 34 + l] = a[q];
+      __syncwarp();
+      const int sub = l >> 1, h = l & 1;             // lane pair (2 sub, 2 sub + 1) owns 32-point sub-transform `sub`
+#pragma unroll
+      for (int t = 0; t < 16; ++t) a[t] = stage[sub * 34 + h + 2 * t];
+      wb_dft16<1>(a);
+      if (h) wb_apply_twiddles16<1>(T, 256, a);      // a[p2] *= W_32^{p2}
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const double ox = __shfl_xor_sync(0xffffffffu, a[q].x, 1), oy = __shfl_xor_sync(0xffffffffu, a[q].y, 1);
+        a[q] = h ? make_double2(ox - a[q].x, oy - a[q].y) : make_double2(a[q].x + ox, a[q].y + oy);
+      }
+      __syncthreads();                               // every warp has left its staging area
+#pragma unroll
+      for (int q = 0; q < 16; ++q) S[wb_sidx(8 * (sub + 16 * q + 256 * h) + r)] = a[q];
+      __syncthreads();
+    } else {
     // the windowed band slices feed the first FFT pass directly (the rest of the N points is zero padding)
     wb_cfft_dif_in_t<1, LOG2N>(S, p.tw_2n, [&](int j, int) {
       cplx z = make_double2(0.0, 0.0);
@@ -610,13 +662,16 @@ __global__ void __launch_bounds__(D4C_BODY_THREADS, 2) d4c_body_kernel(BodyParam
       }
       return z;
     });
+    }
+    // slot of spectrum bin k: natural order after the warp transforms, bit-reversed after the block-wide DIF
+    auto bin_slot = [&](int k) { return (WARP_BANDS && LOG2N == 12) ? wb_sidx(k) : wb_sidx(wb_brev(k, log2n)); };
     double tot_a = 0.0, tot_b = 0.0;
     unsigned long long and_a = ~0ull, or_a = 0ull, and_b = ~0ull, or_b = 0ull;  // select keys of the power values
     unsigned *hist16 = reinterpret_cast<unsigned *>(SP);   // (SP is free from here on: counters of the select)
     for (int k = tid; k <= NC; k += nt) {
-      const int slot = wb_sidx(wb_brev(k, log2n));
+      const int slot = bin_slot(k);
       const cplx zk = S[slot];
-      const cplx zc = S[wb_sidx(wb_brev((N - k) & (N - 1), log2n))];
+      const cplx zc = S[bin_slot((N - k) & (N - 1))];
       const double ar = 0.5 * (zk.x + zc.x), ai = 0.5 * (zk.y - zc.y);   // spectrum of band b
       const double br = 0.5 * (zk.y + zc.y), bi = -0.5 * (zk.x - zc.x);  // spectrum of band b+1
       const double pa = ar * ar + ai * ai, pb = br * br + bi * bi;
@@ -633,7 +688,7 @@ __global__ void __launch_bounds__(D4C_BODY_THREADS, 2) d4c_body_kernel(BodyParam
     wb_block_sum2(tot_a, tot_b, red);
     double low_a = 0.5 * tot_a, low_b = 0.5 * tot_b;
     if (!(p.debug_skip & 1))
-    d4c_sum_smallest2<LOG2N - 1, LOG2N>([&](int i, int w) { const cplx v = S[wb_sidx(wb_brev(i, log2n))]; return w == 0 ? v.x : v.y; },
+    d4c_sum_smallest2<LOG2N - 1, LOG2N>([&](int i, int w) { const cplx v = S[bin_slot(i)]; return w == 0 ? v.x : v.y; },
                                         bins, m_small, has2, and_a, or_a, and_b, or_b, true, reinterpret_cast<int *>(SP), ctl, red,
                                         low_a, low_b);
     if (tid == 0) {
@@ -806,7 +861,12 @@ int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int
     const size_t smem = sizeof(cplx) * wb_fft_slots(N) + sizeof(double) * (2 * binsp + 320) +
                         sizeof(unsigned long long) * (SEL_CTL_WORDS + 2 * SEL_LIST) + sizeof(double) * (D4C_MAX_AP + 2);
     p.frame_begin = row0;
-    if (!chunks || chunks->n <= 1) {
+    static const bool warp_bands_env = getenv("WB_D4C_WARP_BANDS") && atoi(getenv("WB_D4C_WARP_BANDS")) != 0;
+    if (warp_bands_env && l == 12 && window_length <= N / 8 + 1 && (!chunks || chunks->n <= 1)) {   // experimental, see the kernel
+      if (cudaFuncSetAttribute(d4c_body_kernel<12, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WB_ERR_CUDA;
+      WB_LAUNCH("d4c_body_kernel", d4c_body_kernel<12, true><<<n_rows, D4C_BODY_THREADS, smem, stream>>>(p));
+      if (chunks && chunks->n == 1) WB_CUDA_CHECK(cudaEventRecord(chunks->ev[0], stream));
+    } else if (!chunks || chunks->n <= 1) {
       rc = WB_DISPATCH_LOG2(l, 9, 13, {
         if (cudaFuncSetAttribute(d4c_body_kernel<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WB_ERR_CUDA;
         WB_LAUNCH("d4c_body_kernel", d4c_body_kernel<L2><<<n_rows, D4C_BODY_THREADS, smem, stream>>>(p));
