@@ -12,7 +12,6 @@
 #include "wb_smooth.cuh"
 
 #include <math.h>
-#include <stdlib.h>
 #include <vector>
 
 namespace {
@@ -20,7 +19,6 @@ namespace {
 #define D4C_HANNING 1
 #define D4C_BLACKMAN 2
 #define D4C_MAX_AP 8
-#define D4C_BODY_THREADS 256
 
 __device__ __forceinline__ int d4c_half_window(double ratio, int fs, double f0) {
   return wb_round(ratio * fs / f0 / 2.0);  // d4c.cpp:250
@@ -167,251 +165,111 @@ __global__ void __launch_bounds__(256) lt_frame_kernel(LtParams p) {
   if (threadIdx.x == 0) p.ap0[frame] = a / b;
 }
 
-// ---- order statistic: sum of the m smallest of v[0..n) (d4c.cpp:494-499) ----------------------
-// The reference sorts the band power spectrum and takes a cumulative sum; only
-// S[bins - boundary - 2] / S[bins - 1] is used, i.e. (sum of the m smallest) / total.  Radix select
-// on the bit patterns of the (non-negative) values, two arrays at once (the two bands of one paired
-// transform).
-//  * Keys are the bit patterns minus SEL_BIAS (the pattern of 2^-255, saturating at 0): every value in
-//    [2^-255, 2^257) then has its three top key bits clear, and the bits just below them -- nine exponent
-//    bits and the leading mantissa bits -- form a first digit that does not straddle the exponent
-//    boundary at 2.0 the way the raw patterns of a power spectrum (1e-10 .. 1e7) do.
-//  * The PRODUCER of the values counts that first digit (PRE_BITS wide, packed 16-bit counters) while it
-//    computes them; if all keys are in range the select starts from the finished histogram and needs no
-//    counting pass over the data.  Otherwise, and for further digits, counting passes with BITS-wide
-//    digits start at the first key bit that actually varies (AND / OR of the keys, also gathered by
-//    the producer).
-//  * As soon as the bucket holding the m-th smallest key has <= SEL_LIST keys, ONE pass sums everything
-//    below the bucket and collects the bucket's keys, and a single warp ranks them.
-// get(i, w) -> value i of array w.  hist: 2 << BITS ints (= 2 << PRE_BITS shorts); ctl: SEL_CTL_WORDS +
-// 2 * SEL_LIST words.
-#define SEL_LIST 32
-#define SEL_CTL_WORDS (12 + D4C_BODY_THREADS / 32)
-#define SEL_BIAS 0x3000000000000000ull
-#define SEL_PRE_TOP 61   // the pre-counted digit ends below key bit 61
-__device__ __forceinline__ unsigned long long sel_key(double v) {
-  const unsigned long long k = (unsigned long long)__double_as_longlong(v);
-  return k > SEL_BIAS ? k - SEL_BIAS : 0ull;
+// ---- block-wide reductions with ONE barrier each ----------------------------------------------
+// Two scratch buffers alternate (`par`): a buffer is rewritten only after the barrier of the reduction in
+// between, which every thread reaches after its reads of that buffer.  red: 2 * 16 * K doubles.  The
+// partials are added in warp order, so the result does not depend on scheduling.  All threads call.
+template <int K>
+__device__ __forceinline__ void d4c_block_sum(double (&v)[K], double *red, int &par) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int j = 0; j < K; ++j) v[j] = wb_warp_sum(v[j]);
+  double *buf = red + par * (16 * K);
+  par ^= 1;
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < K; ++j) buf[warp * K + j] = v[j];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < K; ++j) v[j] = buf[j];
+  for (int w = 1; w < nw; ++w) {
+#pragma unroll
+    for (int j = 0; j < K; ++j) v[j] += buf[w * K + j];
+  }
 }
-__device__ __forceinline__ double sel_val(unsigned long long key) { return __longlong_as_double((long long)(key + SEL_BIAS)); }
-// producer side: count key `k` of array w (0 / 1) in the packed histogram
-template <int PRE_BITS>
-__device__ __forceinline__ void sel_precount(unsigned *hist16, int w, unsigned long long k) {
-  const int bin = (int)((k >> (SEL_PRE_TOP - PRE_BITS)) & ((1ull << PRE_BITS) - 1ull));
-  const int at = (w << PRE_BITS) + bin;
-  atomicAdd(&hist16[at >> 1], 1u << (16 * (at & 1)));
+// two sums and two maxima (non-negative values)
+__device__ __forceinline__ void d4c_block_sum2_max2(double &sa, double &sb, double &ma, double &mb, double *red, int &par) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  sa = wb_warp_sum(sa);
+  sb = wb_warp_sum(sb);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ma = fmax(ma, __shfl_xor_sync(0xffffffffu, ma, o));
+    mb = fmax(mb, __shfl_xor_sync(0xffffffffu, mb, o));
+  }
+  double *buf = red + par * 64;
+  par ^= 1;
+  if (lane == 0) { buf[warp * 4 + 0] = sa; buf[warp * 4 + 1] = sb; buf[warp * 4 + 2] = ma; buf[warp * 4 + 3] = mb; }
+  __syncthreads();
+  sa = buf[0]; sb = buf[1]; ma = buf[2]; mb = buf[3];
+  for (int w = 1; w < nw; ++w) {
+    sa += buf[w * 4 + 0]; sb += buf[w * 4 + 1];
+    ma = fmax(ma, buf[w * 4 + 2]); mb = fmax(mb, buf[w * 4 + 3]);
+  }
 }
 
-template <int BITS, int PRE_BITS, typename Get>
-__device__ inline void d4c_sum_smallest2(Get get, int n, int m, bool has_second, unsigned long long and_a,
-                                         unsigned long long or_a, unsigned long long and_b, unsigned long long or_b,
-                                         bool precounted, int *hist, unsigned long long *ctl, double *red,
-                                         double &low_a, double &low_b) {
-  constexpr int BINS = 1 << BITS;
-  constexpr int PER = BINS >= D4C_BODY_THREADS ? BINS / D4C_BODY_THREADS : 1;  // bins per thread in the scan
-  constexpr int PRE_BINS = 1 << PRE_BITS;
-  constexpr int PRE_PER = PRE_BINS >= D4C_BODY_THREADS ? PRE_BINS / D4C_BODY_THREADS : 1;
-  constexpr int PRE_SHIFT = SEL_PRE_TOP - PRE_BITS;
-  constexpr int NW = D4C_BODY_THREADS / 32;
-  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
-  int *s_wtot = reinterpret_cast<int *>(ctl + 12);  // 2 x NW warp totals of the bucket scan (NW words)
-  unsigned long long *list = ctl + SEL_CTL_WORDS;    // 2 x SEL_LIST keys
-  // ---- AND / OR of the keys of each array
-  {
-    const unsigned full = 0xffffffffu;
-    const unsigned aah = __reduce_and_sync(full, (unsigned)(and_a >> 32)), aal = __reduce_and_sync(full, (unsigned)and_a);
-    const unsigned oah = __reduce_or_sync(full, (unsigned)(or_a >> 32)), oal = __reduce_or_sync(full, (unsigned)or_a);
-    const unsigned abh = __reduce_and_sync(full, (unsigned)(and_b >> 32)), abl = __reduce_and_sync(full, (unsigned)and_b);
-    const unsigned obh = __reduce_or_sync(full, (unsigned)(or_b >> 32)), obl = __reduce_or_sync(full, (unsigned)or_b);
-    if (tid == 0) {
-      ctl[8] = ~0ull; ctl[9] = 0ull; ctl[10] = ~0ull; ctl[11] = 0ull;
-      ctl[1] = (unsigned long long)m; ctl[5] = (unsigned long long)m;   // remaining rank (1-based)
-    }
-    __syncthreads();
-    if (lane == 0) {
-      atomicAnd(&ctl[8], ((unsigned long long)aah << 32) | aal);
-      atomicOr(&ctl[9], ((unsigned long long)oah << 32) | oal);
-      atomicAnd(&ctl[10], ((unsigned long long)abh << 32) | abl);
-      atomicOr(&ctl[11], ((unsigned long long)obh << 32) | obl);
-    }
-    __syncthreads();
-  }
-  unsigned long long prefix[2], mask[2];
-  int shift[2], width[2];
-  bool done[2];       // threshold fully determined (= prefix)
-  bool listed[2];     // bucket small enough: resolve from the collected list
-  bool counted[2];    // the first digit of this array is already in the packed histogram
-#pragma unroll
-  for (int w = 0; w < 2; ++w) {
-    const unsigned long long all_and = ctl[8 + 2 * w], all_or = ctl[9 + 2 * w];
-    const unsigned long long diff = all_and ^ all_or;
-    listed[w] = false;
-    counted[w] = false;
-    if (diff == 0ull || (w == 1 && !has_second)) {  // every key identical: that key is the threshold
-      prefix[w] = all_and; mask[w] = ~0ull; shift[w] = 0; width[w] = 0; done[w] = true;
-    } else if (precounted && (all_or >> SEL_PRE_TOP) == 0ull) {
-      prefix[w] = 0ull; mask[w] = ~((1ull << SEL_PRE_TOP) - 1ull);   // bits 61.. are zero in every key
-      shift[w] = PRE_SHIFT; width[w] = PRE_BITS; done[w] = false; counted[w] = true;
-    } else {
-      const int top = 64 - __clzll((long long)diff);  // bits [0, top) vary
-      mask[w] = (top >= 64) ? 0ull : ~((1ull << top) - 1ull);
-      prefix[w] = all_and & mask[w];
-      shift[w] = top > BITS ? top - BITS : 0;
-      width[w] = top - shift[w];
-      done[w] = false;
-    }
-  }
-  // ---- bucket holding the remaining rank: block-wide scan of the counters.  count(w, bin) reads a counter.
-  auto find_bucket = [&](auto count, int per, int nbins, bool act0, bool act1) {
-    int c[2] = {0, 0}, incl[2];
-#pragma unroll
-    for (int w = 0; w < 2; ++w) {
-      if (w == 0 ? act0 : act1)
-        for (int q = 0; q < per; ++q) c[w] += (tid * per + q < nbins) ? count(w, tid * per + q) : 0;
-      incl[w] = c[w];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl[w], o);
-        if (lane >= o) incl[w] += t;
-      }
-      if (lane == 31) s_wtot[w * NW + warp] = incl[w];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int w = 0; w < 2; ++w) {
-      if (!(w == 0 ? act0 : act1)) continue;
-      int before = 0;
-      for (int q = 0; q < warp; ++q) before += s_wtot[w * NW + q];
-      const int excl = before + incl[w] - c[w];
-      unsigned long long *c4 = ctl + w * 4;
-      const int remaining = (int)c4[1];
-      if (remaining > excl && remaining <= excl + c[w]) {
-        int r = remaining - excl;
-        int d = tid * per, hcount = 0;
-        for (int q = 0; q < per && tid * per + q < nbins; ++q) {
-          const int hv = count(w, tid * per + q);
-          if (r <= hv) { d = tid * per + q; hcount = hv; break; }
-          r -= hv;
-        }
-        c4[0] = (unsigned long long)d;
-        c4[2] = (unsigned long long)r;
-        c4[3] = (unsigned long long)hcount;
-      }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int w = 0; w < 2; ++w) {
-      if (w == 0 ? act0 : act1) {
-        prefix[w] |= ctl[w * 4 + 0] << shift[w];
-        mask[w] |= ((1ull << width[w]) - 1ull) << shift[w];
-        if (shift[w] == 0) done[w] = true;
-        else if (ctl[w * 4 + 3] <= (unsigned long long)SEL_LIST) listed[w] = true;
-        const int ns = shift[w] > BITS ? shift[w] - BITS : 0;
-        width[w] = shift[w] - ns;
-        shift[w] = ns;
-      }
-    }
-    __syncthreads();
-    if (tid == 0) { ctl[1] = ctl[2]; ctl[5] = ctl[6]; }
-  };
-  if (counted[0] || counted[1]) {
-    const unsigned *h16 = reinterpret_cast<const unsigned *>(hist);
-    find_bucket([&](int w, int bin) { const int at = (w << PRE_BITS) + bin; return (int)((h16[at >> 1] >> (16 * (at & 1))) & 0xffffu); },
-                PRE_PER, PRE_BINS, counted[0], counted[1]);
-  }
-  for (int pass = 0; pass < 64; ++pass) {
-    const bool act0 = !(done[0] || listed[0]), act1 = !(done[1] || listed[1]);
-    if (!act0 && !act1) break;
-    {
-      int4 *h4 = reinterpret_cast<int4 *>(hist);
-      for (int i = tid; i < 2 * BINS / 4; i += nt)
-        if ((i < BINS / 4) ? act0 : act1) h4[i] = make_int4(0, 0, 0, 0);
-    }
-    __syncthreads();
-    for (int i = tid; i < n; i += nt) {
-#pragma unroll
-      for (int w = 0; w < 2; ++w) {
-        if (w == 0 ? act0 : act1) {
-          const unsigned long long key = sel_key(get(i, w));
-          if ((key & mask[w]) == prefix[w])
-            atomicAdd(&hist[w * BINS + (int)((key >> shift[w]) & ((1ull << width[w]) - 1ull))], 1);
-        }
-      }
-    }
-    __syncthreads();
-    find_bucket([&](int w, int bin) { return hist[w * BINS + bin]; }, PER, BINS, act0, act1);
-  }
-  // ---- one pass: sum / count of everything below the bucket, collect the bucket's keys
-  if (tid == 0) { s_wtot[0] = 0; s_wtot[1] = 0; }
+// ---- linear smoothing (world_common.cpp:82-116, :27-52; interp1Q world_matlabfunctions.cpp:220-241) ----
+// The caller has stored P[k], k = 0..NC, at seg[b + k] (b = the boundary of this width); the smoothed values
+// of the thread's own bins k = tid + T i come back in out[].  The two interp1Q positions of bin k are
+// k + c_lo and k + c_hi with constants c (the knots are the bin grid shifted by half a bin), so the knot index
+// and the fraction are formed once instead of per bin through two divisions and a truncation; the reference's
+// per-bin expressions give the same numbers up to rounding of the fraction, and the interpolant is
+// continuous across a knot, so the results agree to an ulp of the cumulative sum.  All threads call; starts
+// with a barrier (P complete), ends WITHOUT one (seg is still being read).
+template <int T_, int NC_>
+__device__ __forceinline__ void d4c_smooth(double *seg, int b, double width, int fs, double (&out)[9], double *wt) {
+  constexpr int N_ = 2 * NC_;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int len = NC_ + 2 * b + 1;
   __syncthreads();
-  double sa = 0.0, ca = 0.0, sb = 0.0, cb = 0.0;
-  for (int i = tid; i < n; i += nt) {
-#pragma unroll
-    for (int w = 0; w < 2; ++w) {
-      if (w == 1 && !has_second) continue;
-      const double v = get(i, w);
-      const unsigned long long key = sel_key(v);
-      const unsigned long long top = key & mask[w];
-      if (top < prefix[w]) {
-        if (w == 0) { sa += v; ca += 1.0; } else { sb += v; cb += 1.0; }
-      } else if (listed[w] && top == prefix[w]) {
-        const int at = atomicAdd(&s_wtot[w], 1);
-        if (at < SEL_LIST) list[w * SEL_LIST + at] = key;
-      }
-    }
+  for (int i = tid; i < b; i += T_) {       // mirrored ends (world_common.cpp:32-47)
+    seg[i] = seg[2 * b - i];
+    seg[NC_ + b + 1 + i] = seg[NC_ + b - 1 - i];
   }
   __syncthreads();
-  // ---- rank the collected keys: warp w resolves array w (remaining rank r, 1-based, inside the bucket)
-  if ((warp == 0 && listed[0]) || (warp == 1 && listed[1])) {
-    const int w = warp;
-    const int cnt = min(s_wtot[w], SEL_LIST);
-    const int r = (int)ctl[w * 4 + 1];
-    const unsigned long long mine = lane < cnt ? list[w * SEL_LIST + lane] : ~0ull;
-    int rank = 0;
-    for (int j = 0; j < cnt; ++j) {
-      const unsigned long long other = __shfl_sync(0xffffffffu, mine, j);
-      rank += (other < mine || (other == mine && j < lane)) ? 1 : 0;
-    }
-    const unsigned hit = __ballot_sync(0xffffffffu, lane < cnt && rank == r - 1);
-    const int src = hit ? (__ffs(hit) - 1) : 0;
-    const unsigned long long thr = __shfl_sync(0xffffffffu, mine, src);
-    // bucket keys strictly below the threshold join the "below" totals; they are summed in rank order
-    // (the collection order above depends on the atomics and must not leak into the rounding)
-    __syncwarp();
-    if (lane < cnt) list[w * SEL_LIST + rank] = mine;
-    __syncwarp();
-    const unsigned long long sorted = lane < cnt ? list[w * SEL_LIST + lane] : ~0ull;
-    double ls = 0.0, lc = 0.0;
-    if (lane < cnt && sorted < thr) { ls = sel_val(sorted); lc = 1.0; }
-    ls = wb_warp_sum(ls);
-    lc = wb_warp_sum(lc);
-    if (lane == 0) {
-      ctl[w * 4 + 0] = thr;
-      ctl[w * 4 + 2] = (unsigned long long)__double_as_longlong(ls);
-      ctl[w * 4 + 3] = (unsigned long long)__double_as_longlong(lc);
-    }
-  }
-  wb_block_sum2(sa, ca, red);   // (contains the barriers that publish ctl)
-  wb_block_sum2(sb, cb, red);
-  double t[2];
+  // cumulative sum of P * fs / fft_size: sequential inside a thread's chunk, chunk offsets by a warp scan
+  const double inv_fft = 1.0 / N_;  // power of two: the product equals the reference's division
+  const int chunk = (len + T_ - 1) / T_;
+  const int bgn = wb_min_i(len, tid * chunk), end = wb_min_i(len, bgn + chunk);
+  double s = 0.0;
+  for (int i = bgn; i < end; ++i) { s += seg[i] * fs * inv_fft; seg[i] = s; }
+  double incl = s;
 #pragma unroll
-  for (int w = 0; w < 2; ++w) {
-    t[w] = sel_val(prefix[w]);
-    if (listed[w]) {
-      t[w] = sel_val(ctl[w * 4 + 0]);
-      const double ls = __longlong_as_double((long long)ctl[w * 4 + 2]), lc = __longlong_as_double((long long)ctl[w * 4 + 3]);
-      if (w == 0) { sa += ls; ca += lc; } else { sb += ls; cb += lc; }
+  for (int o = 1; o < 32; o <<= 1) {
+    const double t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) wt[warp] = incl;
+  __syncthreads();
+  double off = incl - s;
+  for (int w = 0; w < warp; ++w) off += wt[w];
+  for (int i = bgn; i < end; ++i) seg[i] += off;
+  __syncthreads();
+  const double origin = -(b - 0.5) * fs / N_;
+  const double inv_interval = static_cast<double>(N_) / fs;
+  const double q_lo = (-width / 2.0 - origin) * inv_interval, q_hi = (-width / 2.0 + width - origin) * inv_interval;
+  const int b_lo = static_cast<int>(q_lo), b_hi = static_cast<int>(q_hi);
+  const double f_lo = q_lo - b_lo, f_hi = q_hi - b_hi;
+  const double inv_width = 1.0 / width;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    const int k = tid + T_ * i;
+    out[i] = 0.0;
+    if (i < 8 || tid == 0) {
+      const double *lo = seg + k + b_lo, *hi = seg + k + b_hi;
+      const double low = lo[0] + (lo[1] - lo[0]) * f_lo;
+      const double high = hi[0] + (hi[1] - hi[0]) * f_hi;
+      out[i] = (high - low) * inv_width;
     }
   }
-  low_a = sa + (m - ca) * t[0];
-  low_b = sb + (m - cb) * t[1];
 }
 
 // ---- body (d4c.cpp:308-503 + :155-168) -------------------------------------------------------
 struct BodyParams {
   const double *x; int x_length;
   const double *tpos; const double *f0; const double *ap0; int f0_length;
-  int fs; int fft_size_d4c; int log2n; double threshold;
+  int fs; double threshold;
   int n_ap; int window_length;         // Nuttall window of the band analysis
   const double *nuttall;               // device, window_length doubles
   const cplx *tw_n;                    // fft_size_d4c entries (real transforms)
@@ -419,239 +277,282 @@ struct BodyParams {
   const double *noise; const unsigned long long *noise_off;
   int out_fft_size;                    // bins of the output rows
   double *ap;                          // [f0_length][out_fft_size/2+1]
-  int seg_capacity;
   int *error_flag;
   int frame_begin;                     // this launch covers frames frame_begin + blockIdx.x
-  int debug_skip;                      // profiling only (WB_D4C_SKIP, profiles/d4c_phases.py): phases to leave out
 };
 
+#define D4C_HIST_BINS 256
+#define D4C_SEL_WARP_LIST 32
 
-// Shared memory (N = 4096: 110 KB -> two CTAs per SM):
-//   S   : slots of an N-point complex FFT; doubles as the linear-smoothing scratch (`seg`) and,
-//         in its upper half, as window scratch while only a packed real transform lives in it
-//   SC  : static centroid -> static group delay
-//   SP  : smoothed power  -> second smoothing output -> band power spectrum
-// WARP_BANDS (EXPERIMENTAL, off unless WB_D4C_WARP_BANDS=1; written at the end of round 1 without GPU time left to
-// measure it -- see DESIGN.md section 8, item 1a): the band-pair transform as eight independent 512-point
-// transforms, one per warp.  Only for N = 4096 and band slices of at most N/8 + 1 samples.
-template <int LOG2N, bool WARP_BANDS = false>
-__global__ void __launch_bounds__(D4C_BODY_THREADS, 2) d4c_body_kernel(BodyParams p) {
+// Shared-memory footprint of the body kernel in bytes (N = D4C FFT size)
+static size_t d4c_body_smem_bytes(int N) {
+  const int binsp = ((N / 2 + 1) + 1) & ~1;
+  return sizeof(cplx) * wb_fft_slots(N) + sizeof(double) * (binsp + 2 * 16 * 5 + 32 + D4C_MAX_AP + 2 + 16) +
+         sizeof(int) * (2 * D4C_HIST_BINS + 16);
+}
+
+// One CTA of T = N/16 threads per analysed frame: every radix-16 pass of an N-point transform is exactly one
+// butterfly per thread, and thread t owns spectrum bins k = t + T i (i < 8; thread 0 also bin N/2) in every
+// elementwise step, so spectra travel between the phases in registers.  Shared memory (N = 4096: 95 KB, two
+// CTAs per SM):
+//   S    : slots of an N-point complex FFT.  While only a packed real transform lives in its lower half, the
+//          upper half (segA) is the cumulative-sum array of a linear smoothing; the lower half (segB) serves
+//          the next smoothing; the order-statistic lists of the band analysis also live in segA.
+//   SC   : static centroid, later the static group delay (random access by the band slices)
+template <int LOG2N>
+__global__ void __launch_bounds__((1 << LOG2N) / 16, ((8192 >> LOG2N) > 16 ? 16 : ((8192 >> LOG2N) < 1 ? 1 : (8192 >> LOG2N))))
+d4c_body_kernel(BodyParams p) {
   extern __shared__ double2 smem_raw[];
-  constexpr int N = 1 << LOG2N, NC = N / 2, bins = NC + 1;
+  constexpr int N = 1 << LOG2N, NC = N / 2, bins = NC + 1, T = N / 16;
   constexpr int binsp = (bins + 1) & ~1;  // keep 16-byte alignment
   cplx *S = smem_raw;
   double *SC = reinterpret_cast<double *>(S + wb_fft_slots(N));
-  double *SP = SC + binsp;
-  double *red = SP + binsp;                                       // 320
-  unsigned long long *ctl = reinterpret_cast<unsigned long long *>(red + 320);   // select: control words + 2 x SEL_LIST keys
-  double *coarse = reinterpret_cast<double *>(ctl + SEL_CTL_WORDS + 2 * SEL_LIST);  // D4C_MAX_AP + 2
+  double *red = SC + binsp;                      // 2 x 16 x 5
+  double *wt = red + 2 * 16 * 5;                 // 32: warp totals of the scans
+  double *coarse = wt + 32;                      // D4C_MAX_AP + 2 (+ 16 spare: band power ratios)
+  double *ratio = coarse + D4C_MAX_AP + 2;       // D4C_MAX_AP (+ padding)
+  int *hist = reinterpret_cast<int *>(ratio + 16);  // 2 x D4C_HIST_BINS counters
+  int *ctl = hist + 2 * D4C_HIST_BINS;           // [w]: bucket, [2+w]: rank inside, [4+w]: bucket count, [6+w]: list fill
   double *W = reinterpret_cast<double *>(S);
-  double *seg = W;                                                // 2 * slots(N) doubles available
-  const int seg_capacity = 2 * wb_fft_slots(N);
-  double *win_hi = reinterpret_cast<double *>(S + wb_fft_slots(NC) + 8);  // >= N doubles above the packed real data
+  double *segA = reinterpret_cast<double *>(S + wb_fft_slots(NC) + 8);
+  constexpr int seg_cap = 2 * (wb_fft_slots(N) - wb_fft_slots(NC) - 8);   // doubles in segA
+  double *segB = W;                                                       // 2 * slots(NC) >= seg_cap doubles
+  (void)W;
 
   const int frame = p.frame_begin + blockIdx.x;
-  const int tid = threadIdx.x, nt = blockDim.x;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
   const double f0_in = p.f0[frame];
   if (f0_in == 0 || p.ap0[frame] <= p.threshold) {
     // not analysed: the row keeps its initial value 1 - kMySafeGuardMinimum (d4c.cpp:127-132, :146)
     const int out_bins = p.out_fft_size / 2 + 1;
     double *out = p.ap + (size_t)frame * out_bins;
-    for (int i = tid; i < out_bins; i += nt) out[i] = 1.0 - WB_SAFEGUARD;
+    for (int i = tid; i < out_bins; i += T) out[i] = 1.0 - WB_SAFEGUARD;
     return;
   }
   const double f0 = f0_in > WB_FLOOR_F0_D4C ? f0_in : WB_FLOOR_F0_D4C;
   const int fs = p.fs;
   const double pos = p.tpos[frame];
   const double *noise = p.noise + p.noise_off[frame];
-  constexpr int log2n = LOG2N;
+  int par = 0;
+
+  const int hw = d4c_half_window(4.0, fs, f0);
+  const int wlen = 2 * hw + 1;
+  const int b_sp = static_cast<int>(f0 * N / fs) + 1;          // smoothing boundaries (world_common.cpp:88)
+  const int b_g1 = static_cast<int>(f0 / 2.0 * N / fs) + 1;
+  if (NC + 2 * b_sp + 1 > seg_cap || 2 + static_cast<int>(f0 * N / fs) > 4 * T) {
+    if (tid == 0) atomicExch(p.error_flag, WB_ERR_UNSUPPORTED);
+    return;
+  }
+  // the noise of the later windows is on its way to L2 while the first window is built
+  {
+    const char *nb = reinterpret_cast<const char *>(noise + wlen);
+    const int lines = (2 * wlen * 8 + 127) / 128 + 1;
+    for (int i = tid; i < lines; i += T) asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + (size_t)i * 128));
+  }
 
   // ---- static centroid: two windows at pos -/+ 0.25/f0 (d4c.cpp:339-405)
-  // The reference transforms w[n] and (n+1) w[n] separately; both are real, so one complex
-  // transform of z[n] = w[n] + i (n+1) w[n] yields both spectra.  While the window is being
-  // built the imaginary parts of the slots hold the window samples.
-  // (the window angle of sample j is the same in both windows: its rotation constants are set up once)
-  double rot_sd = 0.0, rot_cd = 1.0, rot_sn = 0.0, rot_cs = 1.0;
-  if constexpr (N == 16 * D4C_BODY_THREADS) {
-    const double c1 = 2.0 / 4.0 / fs;
-    const double c2 = WB_PI * f0;
-    sincos(c2 * c1 * D4C_BODY_THREADS, &rot_sd, &rot_cd);
-    sincos(c2 * (c1 * (tid - d4c_half_window(4.0, fs, f0))), &rot_sn, &rot_cs);
-  }
-  for (int c = 0; c < ((p.debug_skip & 8) ? 0 : 2); ++c) {
+  // The reference transforms w[n] and (n+1) w[n] separately; both are real, so one complex transform of
+  // z[n] = w[n] + i (n+1) w[n] yields both spectra.  Thread t owns samples t + T q -- exactly one radix-16
+  // butterfly of the first FFT pass -- so the windowed, mean-free, unit-power waveform (d4c.cpp:246-303,
+  // :372-380) is built in registers and handed to the transform without touching shared memory.
+  // The window angle of sample j is linear in j: one sincos at the thread's first sample (the reference's
+  // expression), then a rotation by T samples per step (<= 15 steps, ~1e-15 drift); cos(2t) = 2 cos(t)^2 - 1
+  // for the Blackman term (d4c.cpp:266-283).  The angles are the same in all three windows.
+  const double wc1 = 2.0 / 4.0 / fs, wc2 = WB_PI * f0;
+  double rot_sd, rot_cd, rot_sn, rot_cs;
+  sincos(wc2 * wc1 * T, &rot_sd, &rot_cd);
+  sincos(wc2 * (wc1 * (tid - hw)), &rot_sn, &rot_cs);
+  for (int c = 0; c < 2; ++c) {
     const double cpos = (c == 0) ? pos - 0.25 / f0 : pos + 0.25 / f0;
-    if constexpr (N == 16 * D4C_BODY_THREADS) {
-      // One radix-16 butterfly per thread in the first FFT pass: thread t owns samples t + 256 q, exactly the
-      // stride of the window loop, so the windowed, mean-free, unit-power waveform (d4c.cpp:246-303, :372-380)
-      // is built in registers and handed to the transform without touching shared memory.
-      const int hw = d4c_half_window(4.0, fs, f0);
-      const int wlen = 2 * hw + 1;
-      const int origin = wb_round(cpos * fs + 0.001);
-      const double sd = rot_sd, cd = rot_cd;
-      double sn = rot_sn, cs = rot_cs;
-      double v[16], w[16];
-      double s1 = 0.0, s2 = 0.0;
-      // all waveform / noise loads first (independent: they overlap), parked in v[] / w[] until they are used
+    const int origin = wb_round(cpos * fs + 0.001);
+    double v[16], w[16];
+    // all waveform / noise loads first (independent: they overlap), parked in v[] / w[] until they are used
 #pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        const int j = tid + q * D4C_BODY_THREADS;
-        v[q] = 0.0; w[q] = 0.0;
-        if (j < wlen) {
-          v[q] = p.x[wb_min_i(p.x_length - 1, wb_max_i(0, origin + j - hw))];
-          w[q] = noise[j];
-        }
+    for (int q = 0; q < 16; ++q) {
+      const int j = tid + q * T;
+      v[q] = 0.0; w[q] = 0.0;
+      if (j < wlen) {
+        v[q] = p.x[wb_min_i(p.x_length - 1, wb_max_i(0, origin + j - hw))];
+        w[q] = noise[j];
       }
+    }
+    double sn = rot_sn, cs = rot_cs;
+    double s[5] = {0.0, 0.0, 0.0, 0.0, 0.0};   // sum v, sum w, sum v^2, sum v w, sum w^2
 #pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        const int j = tid + q * D4C_BODY_THREADS;
-        if (j < wlen) {
-          const double wq = 0.42 + 0.5 * cs + 0.08 * (2.0 * cs * cs - 1.0);
-          const double vq = v[q] * wq + w[q] * WB_SAFEGUARD;
-          v[q] = vq; w[q] = wq;
-          s1 += vq;
-          s2 += wq;
-          const double c_next = cs * cd - sn * sd;
-          sn = sn * cd + cs * sd;
-          cs = c_next;
-        }
+    for (int q = 0; q < 16; ++q) {
+      const int j = tid + q * T;
+      if (j < wlen) {
+        const double wq = 0.42 + 0.5 * cs + 0.08 * (2.0 * cs * cs - 1.0);
+        const double vq = v[q] * wq + w[q] * WB_SAFEGUARD;
+        v[q] = vq; w[q] = wq;
+        s[0] += vq; s[1] += wq; s[2] += vq * vq; s[3] += vq * wq; s[4] += wq * wq;
+        const double c_next = cs * rot_cd - sn * rot_sd;
+        sn = sn * rot_cd + cs * rot_sd;
+        cs = c_next;
       }
-      wb_block_sum2(s1, s2, red);
-      const double coef = s1 / s2;
-      double pw = 0.0;
+    }
+    // One reduction gives the mean-removal coefficient AND the power of the mean-free waveform
+    // (sum (v - c w)^2 = sum v^2 - 2 c sum v w + c^2 sum w^2), so the unit-power scale (d4c.cpp:372-380) needs no
+    // second pass over the block; one reciprocal per window instead of a division per sample (quotients
+    // within an ulp of the reference's).
+    d4c_block_sum<5>(s, red, par);
+    const double coef = s[0] / s[1];
+    const double inv_power = 1.0 / sqrt(s[2] - 2.0 * coef * s[3] + coef * coef * s[4]);
 #pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        if (tid + q * D4C_BODY_THREADS < wlen) { v[q] -= w[q] * coef; pw += v[q] * v[q]; }
-      }
-      // unit power (d4c.cpp:372-380): one reciprocal per window instead of a division per sample (the
-      // quotients differ from the reference's by at most one ulp)
-      const double inv_power = 1.0 / sqrt(wb_block_sum(pw, red));
-      noise += wlen;
-      wb_cfft_dif_in_t<1, LOG2N>(S, p.tw_2n, [&](int j, int q) {
-        cplx z = make_double2(0.0, 0.0);
-        if (j < wlen) { z.x = v[q] * inv_power; z.y = z.x * (j + 1.0); }
-        return z;
-      });
-    } else {
-    const int wlen = d4c_windowed_waveform(p.x, p.x_length, fs, f0, cpos, D4C_BLACKMAN, 4.0, noise,
-                                           [&](int j) -> double & { return S[wb_sidx(j)].y; }, red,
-                                           [&](int j) -> double & { return S[wb_sidx(j)].x; });
+    for (int q = 0; q < 16; ++q) v[q] = (v[q] - w[q] * coef) * inv_power;   // (samples past the window stay 0)
     noise += wlen;
-    double pw = 0.0;
-    for (int j = tid; j < wlen; j += nt) { const double v = S[wb_sidx(j)].x; pw += v * v; }
-    const double power = sqrt(wb_block_sum(pw, red));
-    for (int j = tid; j < N; j += nt) {
-      cplx z = make_double2(0.0, 0.0);
-      if (j < wlen) { z.x = S[wb_sidx(j)].x / power; z.y = z.x * (j + 1.0); }
-      S[wb_sidx(j)] = z;
+    wb_cfft_dif_in_t<1, LOG2N>(S, p.tw_2n, [&](int j, int q) { return make_double2(v[q], v[q] * (j + 1.0)); });
+    // spectra of w (X1) and (n+1) w (X2) from Z[k], Z[N-k]; centroid term Re X1 Re X2 + Im X1 Im X2 (d4c.cpp:400)
+    // = (Re Z[k] Im Z[N-k] + Im Z[k] Re Z[N-k]) / 2
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const int k = tid + T * i;
+      if (i < 8 || tid == 0) {
+        const cplx zk = S[wb_sidx(wb_brev(k, LOG2N))];
+        const cplx zc = S[wb_sidx(wb_brev((N - k) & (N - 1), LOG2N))];
+        const double cen = 0.5 * (zk.x * zc.y + zk.y * zc.x);
+        SC[k] = (c == 0) ? cen : SC[k] + cen;
+      }
     }
-    __syncthreads();
-    wb_cfft_dif_t<1, LOG2N, 16>(S, p.tw_2n);
-    }
-    for (int k = tid; k <= NC; k += nt) {
-      const cplx zk = S[wb_sidx(wb_brev(k, log2n))];
-      const cplx zc = S[wb_sidx(wb_brev((N - k) & (N - 1), log2n))];
-      const double x1r = 0.5 * (zk.x + zc.x), x1i = 0.5 * (zk.y - zc.y);   // spectrum of w
-      const double x2r = 0.5 * (zk.y + zc.y), x2i = -0.5 * (zk.x - zc.x);  // spectrum of (n+1) w
-      const double cen = x2r * x1r + x1i * x2i;  // d4c.cpp:400
-      SC[k] = (c == 0) ? cen : SC[k] + cen;
-    }
-    __syncthreads();
   }
-  wb_dc_correction(SC, f0, fs, N);
 
-  // ---- smoothed power spectrum (d4c.cpp:411-434)
+  // ---- smoothed power spectrum (d4c.cpp:411-434): Hanning window at pos, real transform as a packed N/2-point
+  // complex one whose first pass is radix 8 (one butterfly per thread: packed samples t + T q, i.e. waveform
+  // samples 2 (t + T q) and the one after it, again straight from registers)
   {
-    const double rot[4] = {rot_sd, rot_cd, rot_sn, rot_cs};
-    const int wlen = d4c_windowed_waveform(p.x, p.x_length, fs, f0, pos, D4C_HANNING, 4.0, noise,
-                                           [&](int j) -> double & { return win_hi[j]; }, red,
-                                           [&](int j) -> double & { return W[wb_didx(j)]; },
-                                           (N == 16 * D4C_BODY_THREADS) ? rot : nullptr);
-    for (int j = wlen + tid; j < N; j += nt) W[wb_didx(j)] = 0.0;
+    const int origin = wb_round(pos * fs + 0.001);
+    double v[16], w[16];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = 2 * (tid + q * T) + e;
+        v[2 * q + e] = 0.0; w[2 * q + e] = 0.0;
+        if (j < wlen) {
+          v[2 * q + e] = p.x[wb_min_i(p.x_length - 1, wb_max_i(0, origin + j - hw))];
+          w[2 * q + e] = noise[j];
+        }
+      }
+    }
+    // angles: sample 2 t first, one sample further for the odd one, 2 T samples per step (double angle of the
+    // T-sample rotation)
+    double s1c, c1c, sn, cs;
+    sincos(wc2 * wc1, &s1c, &c1c);
+    sincos(wc2 * (wc1 * (2 * tid - hw)), &sn, &cs);
+    const double sd2 = 2.0 * rot_sd * rot_cd, cd2 = 2.0 * rot_cd * rot_cd - 1.0;
+    double s[2] = {0.0, 0.0};
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int j = 2 * (tid + q * T);
+      if (j < wlen) {
+        const double w0 = 0.5 * cs + 0.5;
+        const double v0 = v[2 * q] * w0 + w[2 * q] * WB_SAFEGUARD;
+        v[2 * q] = v0; w[2 * q] = w0;
+        s[0] += v0; s[1] += w0;
+        if (j + 1 < wlen) {
+          const double w1 = 0.5 * (cs * c1c - sn * s1c) + 0.5;
+          const double v1 = v[2 * q + 1] * w1 + w[2 * q + 1] * WB_SAFEGUARD;
+          v[2 * q + 1] = v1; w[2 * q + 1] = w1;
+          s[0] += v1; s[1] += w1;
+        }
+        const double c_next = cs * cd2 - sn * sd2;
+        sn = sn * cd2 + cs * sd2;
+        cs = c_next;
+      }
+    }
+    d4c_block_sum<2>(s, red, par);
+    const double coef = s[0] / s[1];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] -= w[q] * coef;
+    wb_pass_dif8<1, NC, NC>(S, p.tw_n, [&](int, int q) { return make_double2(v[2 * q], v[2 * q + 1]); });
     __syncthreads();
-    wb_rfft_t<1, LOG2N - 1, 16>(S, p.tw_n, [&](int k, cplx X) { SP[k] = X.x * X.x + X.y * X.y; });
-    wb_dc_correction(SP, f0, fs, N);
-    if (!wb_linear_smoothing(SP, SP, f0, fs, N, seg, seg_capacity, red)) {
-      if (tid == 0) atomicExch(p.error_flag, WB_ERR_UNSUPPORTED);
-      return;
+    WbDifPasses<1, NC, NC / 8, 16>::run(S, p.tw_n, WbFromSlots());
+    // split step of the real transform (see wb_rfft_t): power of bins k and NC - k, stored for the smoothing
+    double *P = segA + b_sp;
+    for (int k = tid; k <= (NC >> 1); k += T) {
+      if (k == 0) {
+        const cplx z = S[0];
+        P[0] = (z.x + z.y) * (z.x + z.y);
+        P[NC] = (z.x - z.y) * (z.x - z.y);
+      } else {
+        const cplx zk = S[wb_sidx(wb_brev(k, LOG2N - 1))];
+        const cplx zc = S[wb_sidx(wb_brev(NC - k, LOG2N - 1))];
+        const cplx E = make_double2(0.5 * (zk.x + zc.x), 0.5 * (zk.y - zc.y));
+        const cplx O = make_double2(0.5 * (zk.y + zc.y), -0.5 * (zk.x - zc.x));
+        const cplx t = wb_cmul(wb_tw<1>(p.tw_n, k), O);
+        const cplx X = wb_cadd(E, t), Y = wb_csub(E, t);
+        P[k] = X.x * X.x + X.y * X.y;
+        if (k != NC - k) P[NC - k] = Y.x * Y.x + Y.y * Y.y;
+      }
+    }
+    __syncthreads();
+    // DC correction of both spectra (world_common.cpp:61-80): bins below f0 receive the interpolated replica
+    // P(f0 - f).  (xi - f0) / (-fs / N) is formed as a product with N / fs: the quotient can differ in the last
+    // bit, the interpolant is continuous.)
+    {
+      const int upper_limit = 2 + static_cast<int>(f0 * N / fs);
+      const int n_rep = upper_limit - 1;
+      const double inv_dx = -static_cast<double>(N) / fs;
+      double rep_c[4], rep_p[4];
+      int cnt = 0;
+      for (int i = tid; i < n_rep && cnt < 4; i += T, ++cnt) {
+        const double xi = static_cast<double>(i) * fs / N;
+        const double qd = (xi - f0) * inv_dx;
+        const int base = static_cast<int>(qd);
+        const double frac = qd - base;
+        rep_c[cnt] = SC[base] + (SC[base + 1] - SC[base]) * frac;
+        rep_p[cnt] = P[base] + (P[base + 1] - P[base]) * frac;
+      }
+      __syncthreads();
+      cnt = 0;
+      for (int i = tid; i < n_rep && cnt < 4; i += T, ++cnt) { SC[i] += rep_c[cnt]; P[i] += rep_p[cnt]; }
     }
   }
+  double sgd[9], t1[9];
+  d4c_smooth<T, NC>(segA, b_sp, f0, fs, t1, wt);
 
-  // ---- static group delay (d4c.cpp:440-460)
-  for (int k = tid; k < bins; k += nt) SC[k] = SC[k] / SP[k];
-  __syncthreads();
-  if (!(p.debug_skip & 2)) {
-    wb_linear_smoothing(SC, SC, f0 / 2.0, fs, N, seg, seg_capacity, red);
-    wb_linear_smoothing(SC, SP, f0, fs, N, seg, seg_capacity, red);
+  // ---- static group delay (d4c.cpp:440-460): centroid / smoothed power, smoothed with f0 / 2, minus its own
+  // smoothing with f0
+  {
+    double *P = segB + b_g1;
+#pragma unroll
+    for (int i = 0; i < 9; ++i)
+      if (i < 8 || tid == 0) P[tid + T * i] = SC[tid + T * i] / t1[i];
   }
-  for (int k = tid; k < bins; k += nt) SC[k] -= SP[k];
+  d4c_smooth<T, NC>(segB, b_g1, f0 / 2.0, fs, sgd, wt);
+  {
+    double *P = segA + b_sp;
+#pragma unroll
+    for (int i = 0; i < 9; ++i)
+      if (i < 8 || tid == 0) P[tid + T * i] = sgd[i];
+  }
+  d4c_smooth<T, NC>(segA, b_sp, f0, fs, t1, wt);
+#pragma unroll
+  for (int i = 0; i < 9; ++i)
+    if (i < 8 || tid == 0) SC[tid + T * i] = sgd[i] - t1[i];
+  // (the barriers inside the first band transform order these writes before the slices are read: the slices are
+  // read in its first pass -- so one barrier here)
   __syncthreads();
 
   // ---- coarse aperiodicity per 3 kHz band (d4c.cpp:466-503)
   const int wl = p.window_length, hwl = wl / 2;
   const int boundary = wb_round(N * 8.0 / wl);
-  const int m_small = bins - boundary - 1;  // cumulative-sum index bins - boundary - 2
-  // Bands are transformed in pairs: band b in the real part, band b+1 in the imaginary part of ONE
-  // complex N-point transform (both are real, so the spectra separate exactly); the two power
-  // spectra are left interleaved in the FFT slots and both order statistics are resolved together.
-  for (int b = 0; b < ((p.debug_skip & 4) ? 0 : p.n_ap); b += 2) {
+  const int n_top = boundary + 1;   // the reference sorts the band's power spectrum and sums the bins - boundary - 1
+                                    // smallest values (cumulative-sum index bins - boundary - 2): all but the n_top largest
+  // Bands are transformed in pairs: band b in the real part, band b+1 in the imaginary part of ONE complex
+  // N-point transform (both are real, so the spectra separate exactly).  The power values stay in registers;
+  // the order statistic is a top-n_top selection: a histogram over the distance from the maximum in units of
+  // 2^49 key steps (1/8 of a binade), counted from the top, gives the bucket holding the n_top-th largest value;
+  // everything in lower buckets is summed directly, the bucket itself is ranked (<= 32 keys: one warp;
+  // otherwise a block-wide bitonic sort of the bucket).
+  unsigned long long *list = reinterpret_cast<unsigned long long *>(segA);   // 2 x bins keys
+  for (int b = 0; b < p.n_ap; b += 2) {
     const bool has2 = (b + 1 < p.n_ap);
     const int center_a = static_cast<int>(WB_FREQ_INTERVAL * (b + 1) * N / fs);
     const int center_b = static_cast<int>(WB_FREQ_INTERVAL * (b + 2) * N / fs);
-    // counters of the select's first digit (SP is free by now: 2 x 2^LOG2N packed 16-bit counters); the
-    // barriers inside the transform order the clear before the counting
-    {
-      int4 *h4 = reinterpret_cast<int4 *>(SP);
-      for (int i = tid; i < N / 4; i += nt) h4[i] = make_int4(0, 0, 0, 0);
-    }
-    if constexpr (WARP_BANDS && LOG2N == 12) {
-      // The slice z[n] has at most N/8 + 1 = 513 non-zero samples, so Z[8 q + r] = sum_n (z[n] W_N^{n r}) W_512^{n q}
-      // (+ z[512] W_N^{512 r}, which does not depend on q: it joins sample 0): warp r transforms the slice
-      // modulated by W_N^{n r} with a 512-point FFT of its own -- lane l holds samples l + 32 t, a radix-16
-      // butterfly over t, an exchange through a warp-private staging area, a radix-16 butterfly over the 32-point
-      // sub-transforms' even / odd halves and a final radix-2 by shuffle.  No block barrier inside; ¾ of the
-      // butterflies of the padded 4096-point transform.  Output in NATURAL order (model: profiles/band_fft_model.py).
-      const int r = tid >> 5, l = tid & 31;
-      const cplx *T = p.tw_2n;                       // e^{2 pi i k / 8192}
-      cplx a[16];
-#pragma unroll
-      for (int t = 0; t < 16; ++t) {
-        const int n = l + 32 * t;
-        cplx z = make_double2(0.0, 0.0);
-        if (n < wl) {
-          const double nw = __ldg(&p.nuttall[n]);
-          z.x = SC[center_a - hwl + n] * nw;
-          if (has2) z.y = SC[center_b - hwl + n] * nw;
-        }
-        if (r) z = wb_cmul(z, wb_tw<1>(T, (2 * n * r) & (2 * N - 1)));
-        a[t] = z;
-      }
-      if (l == 0 && wl > 512) {                      // sample 512 folds onto sample 0 of every residue
-        const double nw = __ldg(&p.nuttall[512]);
-        cplx z2 = make_double2(SC[center_a - hwl + 512] * nw, has2 ? SC[center_b - hwl + 512] * nw : 0.0);
-        z2 = wb_cmul(z2, wb_tw<1>(T, (1024 * r) & (2 * N - 1)));
-        a[0] = wb_cadd(a[0], z2);
-      }
-      wb_dft16<1>(a);
-      if (l) wb_apply_twiddles16<1>(T, 16 * l, a);   // a[p] *= W_512^{l p}
-      cplx *stage = S + r * 544;                     // 16 sub-transforms x (32 + 2 padding) slots per warp
-#pragma unroll
-      for (int q = 0; q < 16; ++q) stage[q * 34 + l] = a[q];
-      __syncwarp();
-      const int sub = l >> 1, h = l & 1;             // lane pair (2 sub, 2 sub + 1) owns 32-point sub-transform `sub`
-#pragma unroll
-      for (int t = 0; t < 16; ++t) a[t] = stage[sub * 34 + h + 2 * t];
-      wb_dft16<1>(a);
-      if (h) wb_apply_twiddles16<1>(T, 256, a);      // a[p2] *= W_32^{p2}
-#pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        const double ox = __shfl_xor_sync(0xffffffffu, a[q].x, 1), oy = __shfl_xor_sync(0xffffffffu, a[q].y, 1);
-        a[q] = h ? make_double2(ox - a[q].x, oy - a[q].y) : make_double2(a[q].x + ox, a[q].y + oy);
-      }
-      __syncthreads();                               // every warp has left its staging area
-#pragma unroll
-      for (int q = 0; q < 16; ++q) S[wb_sidx(8 * (sub + 16 * q + 256 * h) + r)] = a[q];
-      __syncthreads();
-    } else {
+    for (int i = tid; i < 2 * D4C_HIST_BINS; i += T) hist[i] = 0;
+    if (tid < 2) ctl[6 + tid] = 0;
     // the windowed band slices feed the first FFT pass directly (the rest of the N points is zero padding)
     wb_cfft_dif_in_t<1, LOG2N>(S, p.tw_2n, [&](int j, int) {
       cplx z = make_double2(0.0, 0.0);
@@ -662,51 +563,155 @@ __global__ void __launch_bounds__(D4C_BODY_THREADS, 2) d4c_body_kernel(BodyParam
       }
       return z;
     });
+    double pa[9], pb[9];
+    double tot_a = 0.0, tot_b = 0.0, max_a = 0.0, max_b = 0.0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const int k = tid + T * i;
+      pa[i] = 0.0; pb[i] = 0.0;
+      if (i < 8 || tid == 0) {
+        const cplx zk = S[wb_sidx(wb_brev(k, LOG2N))];
+        const cplx zc = S[wb_sidx(wb_brev((N - k) & (N - 1), LOG2N))];
+        const double ar = 0.5 * (zk.x + zc.x), ai = 0.5 * (zk.y - zc.y);   // spectrum of band b
+        const double br = 0.5 * (zk.y + zc.y), bi = -0.5 * (zk.x - zc.x);  // spectrum of band b+1
+        pa[i] = ar * ar + ai * ai;
+        pb[i] = br * br + bi * bi;
+        tot_a += pa[i]; tot_b += pb[i];
+        max_a = fmax(max_a, pa[i]); max_b = fmax(max_b, pb[i]);
+      }
     }
-    // slot of spectrum bin k: natural order after the warp transforms, bit-reversed after the block-wide DIF
-    auto bin_slot = [&](int k) { return (WARP_BANDS && LOG2N == 12) ? wb_sidx(k) : wb_sidx(wb_brev(k, log2n)); };
-    double tot_a = 0.0, tot_b = 0.0;
-    unsigned long long and_a = ~0ull, or_a = 0ull, and_b = ~0ull, or_b = 0ull;  // select keys of the power values
-    unsigned *hist16 = reinterpret_cast<unsigned *>(SP);   // (SP is free from here on: counters of the select)
-    for (int k = tid; k <= NC; k += nt) {
-      const int slot = bin_slot(k);
-      const cplx zk = S[slot];
-      const cplx zc = S[bin_slot((N - k) & (N - 1))];
-      const double ar = 0.5 * (zk.x + zc.x), ai = 0.5 * (zk.y - zc.y);   // spectrum of band b
-      const double br = 0.5 * (zk.y + zc.y), bi = -0.5 * (zk.x - zc.x);  // spectrum of band b+1
-      const double pa = ar * ar + ai * ai, pb = br * br + bi * bi;
-      // slots of indices > NC are only read (by the thread that owns N - k), never written: in-place is safe
-      S[slot] = make_double2(pa, pb);
-      tot_a += pa;
-      tot_b += pb;
-      // first digit of the order-statistic select, counted while the values are at hand
-      const unsigned long long ka = sel_key(pa), kb = sel_key(pb);
-      and_a &= ka; or_a |= ka; and_b &= kb; or_b |= kb;
-      sel_precount<LOG2N>(hist16, 0, ka);
-      if (has2) sel_precount<LOG2N>(hist16, 1, kb);
-    }
-    wb_block_sum2(tot_a, tot_b, red);
-    double low_a = 0.5 * tot_a, low_b = 0.5 * tot_b;
-    if (!(p.debug_skip & 1))
-    d4c_sum_smallest2<LOG2N - 1, LOG2N>([&](int i, int w) { const cplx v = S[bin_slot(i)]; return w == 0 ? v.x : v.y; },
-                                        bins, m_small, has2, and_a, or_a, and_b, or_b, true, reinterpret_cast<int *>(SP), ctl, red,
-                                        low_a, low_b);
-    if (tid == 0) {
-      const double rev = (f0 - 100) / 50.0;  // d4c.cpp:325-327
-      double ca = 10 * log10(low_a / tot_a);
-      ca = ca + rev;
-      coarse[b + 1] = ca < 0.0 ? ca : 0.0;
-      if (has2) {
-        double cb = 10 * log10(low_b / tot_b);
-        cb = cb + rev;
-        coarse[b + 2] = cb < 0.0 ? cb : 0.0;
+    d4c_block_sum2_max2(tot_a, tot_b, max_a, max_b, red, par);   // (S is free after this barrier)
+    const unsigned long long mk_a = (unsigned long long)__double_as_longlong(max_a);
+    const unsigned long long mk_b = (unsigned long long)__double_as_longlong(max_b);
+    auto digit = [](unsigned long long mk, double v) {
+      const unsigned long long d = (mk - (unsigned long long)__double_as_longlong(v)) >> 49;
+      return (int)(d < (unsigned long long)(D4C_HIST_BINS - 1) ? d : (unsigned long long)(D4C_HIST_BINS - 1));
+    };
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      if (i < 8 || tid == 0) {
+        atomicAdd(&hist[digit(mk_a, pa[i])], 1);
+        if (has2) atomicAdd(&hist[D4C_HIST_BINS + digit(mk_b, pb[i])], 1);
       }
     }
     __syncthreads();
+    // bucket of the n_top-th largest value: exclusive scan of the counters from the top
+    {
+      constexpr int PER = (D4C_HIST_BINS + T - 1) / T;
+      int cnt[2][PER], tot[2] = {0, 0}, incl[2];
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+          const int bin = tid * PER + q;
+          cnt[w][q] = bin < D4C_HIST_BINS ? hist[w * D4C_HIST_BINS + bin] : 0;
+          tot[w] += cnt[w][q];
+        }
+        incl[w] = tot[w];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl[w], o);
+          if (lane >= o) incl[w] += t;
+        }
+      }
+      int *wtot = reinterpret_cast<int *>(wt);
+      if (lane == 31) { wtot[warp] = incl[0]; wtot[16 + warp] = incl[1]; }
+      __syncthreads();
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        int excl = incl[w] - tot[w];
+        for (int q = 0; q < warp; ++q) excl += wtot[w * 16 + q];
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+          if (n_top > excl && n_top <= excl + cnt[w][q]) {
+            ctl[w] = tid * PER + q;
+            ctl[2 + w] = n_top - excl;      // that many of the bucket's largest keys are left out
+            ctl[4 + w] = cnt[w][q];
+          }
+          excl += cnt[w][q];
+        }
+      }
+      __syncthreads();
+    }
+    const int bk_a = ctl[0], bk_b = ctl[1];
+    double low_a = 0.0, low_b = 0.0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      if (i < 8 || tid == 0) {
+        const int da = digit(mk_a, pa[i]);
+        if (da > bk_a) low_a += pa[i];
+        else if (da == bk_a) list[atomicAdd(&ctl[6], 1)] = (unsigned long long)__double_as_longlong(pa[i]);
+        if (has2) {
+          const int db = digit(mk_b, pb[i]);
+          if (db > bk_b) low_b += pb[i];
+          else if (db == bk_b) list[bins + atomicAdd(&ctl[7], 1)] = (unsigned long long)__double_as_longlong(pb[i]);
+        }
+      }
+    }
+    __syncthreads();
+    // the bucket's keys in descending order; those after the first r join the sum, added in rank order (the
+    // collection order above depends on the atomics and must not leak into the rounding)
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      if (w == 1 && !has2) break;
+      const int n = ctl[4 + w], r = ctl[2 + w];
+      unsigned long long *lw = list + w * bins;
+      if (n <= D4C_SEL_WARP_LIST) {
+        if (warp == (w % (T / 32))) {
+          const unsigned long long mine = lane < n ? lw[lane] : 0ull;
+          int rank = 0;
+          for (int j = 0; j < n; ++j) {
+            const unsigned long long other = __shfl_sync(0xffffffffu, mine, j);
+            rank += (other > mine || (other == mine && j < lane)) ? 1 : 0;
+          }
+          __syncwarp();
+          if (lane < n) lw[rank] = mine;
+          __syncwarp();
+          double vsum = (lane < n && lane >= r) ? __longlong_as_double((long long)lw[lane]) : 0.0;
+          vsum = wb_warp_sum(vsum);
+          if (lane == 0) { if (w == 0) low_a += vsum; else low_b += vsum; }
+        }
+      } else {
+        int pw2 = 1;
+        while (pw2 < n) pw2 <<= 1;
+        for (int i = n + tid; i < pw2; i += T) lw[i] = 0ull;
+        __syncthreads();
+        for (int kk = 2; kk <= pw2; kk <<= 1) {
+          for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+            for (int i = tid; i < pw2; i += T) {
+              const int ixj = i ^ jj;
+              if (ixj > i) {
+                const unsigned long long x0 = lw[i], x1 = lw[ixj];
+                const bool desc = (i & kk) == 0;
+                if ((x0 < x1) == desc) { lw[i] = x1; lw[ixj] = x0; }
+              }
+            }
+            __syncthreads();
+          }
+        }
+        if (warp == 0) {   // rank order again: one warp adds the tail with a fixed association
+          double vsum = 0.0;
+          for (int i = r + lane; i < n; i += 32) vsum += __longlong_as_double((long long)lw[i]);
+          vsum = wb_warp_sum(vsum);
+          if (lane == 0) { if (w == 0) low_a += vsum; else low_b += vsum; }
+        }
+      }
+    }
+    double lows[2] = {low_a, low_b};
+    d4c_block_sum<2>(lows, red, par);
+    if (tid == 0) {
+      ratio[b] = lows[0] / tot_a;
+      if (has2) ratio[b + 1] = lows[1] / tot_b;
+    }
   }
-  if (tid == 0) {
+  __syncthreads();
+  if (tid == T - 1) {
     coarse[0] = -60.0;                      // d4c.cpp:84
     coarse[p.n_ap + 1] = -WB_SAFEGUARD;     // d4c.cpp:85
+  }
+  if (tid < p.n_ap) {                       // one band per thread (the logarithms used to run one after the other)
+    const double ca = 10 * log10(ratio[tid]) + (f0 - 100) / 50.0;  // d4c.cpp:325-327
+    coarse[tid + 1] = ca < 0.0 ? ca : 0.0;
   }
   __syncthreads();
 
@@ -714,7 +719,7 @@ __global__ void __launch_bounds__(D4C_BODY_THREADS, 2) d4c_body_kernel(BodyParam
   const int out_bins = p.out_fft_size / 2 + 1;
   double *out = p.ap + (size_t)frame * out_bins;
   const int nk = p.n_ap + 2;
-  for (int i = tid; i < out_bins; i += nt) {
+  for (int i = tid; i < out_bins; i += T) {
     const double xi = static_cast<double>(i) * fs / p.out_fft_size;
     // histc (world_matlabfunctions.cpp:136-156): first knot strictly above xi, clamped to [1, nk-1]
     int k = 1;
@@ -759,7 +764,7 @@ int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int
   const int n_rows = range ? range->end - range->begin : f0_length;
   const int N = wb_d4c_fft_size(fs), N_lt = wb_d4c_lt_fft_size(fs);
   const int l = ilog2_exact(N), l_lt = ilog2_exact(N_lt);
-  if (l < 7 || N > 8192 || l_lt < 7 || N_lt > 16384) return WB_ERR_UNSUPPORTED;
+  if (l < 9 || N > 8192 || l_lt < 7 || N_lt > 16384) return WB_ERR_UNSUPPORTED;
   const int n_ap = wb_number_of_aperiodicities(fs);
   if (n_ap < 0 || n_ap > D4C_MAX_AP) return WB_ERR_UNSUPPORTED;
   const int out_bins = out_fft_size / 2 + 1;
@@ -849,27 +854,19 @@ int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int
   if (n_rows > 0) {
     BodyParams p;
     p.x = d_x; p.x_length = x_length; p.tpos = d_tpos; p.f0 = d_f0; p.ap0 = d_ap0; p.f0_length = f0_length;
-    p.fs = fs; p.fft_size_d4c = N; p.log2n = l; p.threshold = threshold;
+    p.fs = fs; p.threshold = threshold;
     p.n_ap = n_ap; p.window_length = window_length; p.nuttall = d_nuttall;
     p.tw_n = tw_n; p.tw_2n = tw_2n; p.noise = d_noise; p.noise_off = range ? d_rel : d_offsets;
     p.out_fft_size = out_fft_size;
     p.ap = range ? d_ap - (size_t)row0 * (out_fft_size / 2 + 1) : d_ap;   // (rows are addressed by absolute frame)
-    p.seg_capacity = 0;  // the smoothing scratch aliases the FFT slots
     p.error_flag = ws->error_flag();
-    p.debug_skip = getenv("WB_D4C_SKIP") ? atoi(getenv("WB_D4C_SKIP")) : 0;
-    const int binsp = ((N / 2 + 1) + 1) & ~1;
-    const size_t smem = sizeof(cplx) * wb_fft_slots(N) + sizeof(double) * (2 * binsp + 320) +
-                        sizeof(unsigned long long) * (SEL_CTL_WORDS + 2 * SEL_LIST) + sizeof(double) * (D4C_MAX_AP + 2);
+    const size_t smem = d4c_body_smem_bytes(N);
+    const int threads = N / 16;     // one radix-16 butterfly per thread and pass
     p.frame_begin = row0;
-    static const bool warp_bands_env = getenv("WB_D4C_WARP_BANDS") && atoi(getenv("WB_D4C_WARP_BANDS")) != 0;
-    if (warp_bands_env && l == 12 && window_length <= N / 8 + 1 && (!chunks || chunks->n <= 1)) {   // experimental, see the kernel
-      if (cudaFuncSetAttribute(d4c_body_kernel<12, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WB_ERR_CUDA;
-      WB_LAUNCH("d4c_body_kernel", d4c_body_kernel<12, true><<<n_rows, D4C_BODY_THREADS, smem, stream>>>(p));
-      if (chunks && chunks->n == 1) WB_CUDA_CHECK(cudaEventRecord(chunks->ev[0], stream));
-    } else if (!chunks || chunks->n <= 1) {
+    if (!chunks || chunks->n <= 1) {
       rc = WB_DISPATCH_LOG2(l, 9, 13, {
         if (cudaFuncSetAttribute(d4c_body_kernel<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WB_ERR_CUDA;
-        WB_LAUNCH("d4c_body_kernel", d4c_body_kernel<L2><<<n_rows, D4C_BODY_THREADS, smem, stream>>>(p));
+        WB_LAUNCH("d4c_body_kernel", d4c_body_kernel<L2><<<n_rows, threads, smem, stream>>>(p));
       });
       if (rc) return rc;
       if (chunks && chunks->n == 1) WB_CUDA_CHECK(cudaEventRecord(chunks->ev[0], stream));
@@ -885,7 +882,7 @@ int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int
           rc = WB_DISPATCH_LOG2(l, 9, 13, {
             if (cudaFuncSetAttribute(d4c_body_kernel<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WB_ERR_CUDA;
             WbLaunchScope scope("d4c_body_kernel", cs);
-            d4c_body_kernel<L2><<<count, D4C_BODY_THREADS, smem, cs>>>(p);
+            d4c_body_kernel<L2><<<count, threads, smem, cs>>>(p);
           });
           if (rc) return rc;
         }

@@ -27,7 +27,7 @@
 // pattern of the real-transform split step (lanes hit slots N/32 apart) over all banks.
 __device__ __forceinline__ int wb_sidx(int i) { return i + (i >> 3) + (i >> 6) + (i >> 9); }
 // number of double2 slots needed for an NC-point complex FFT
-__host__ __device__ __forceinline__ int wb_fft_slots(int nc) { return nc + (nc >> 3) + (nc >> 6) + (nc >> 9) + 1; }
+__host__ __device__ __forceinline__ constexpr int wb_fft_slots(int nc) { return nc + (nc >> 3) + (nc >> 6) + (nc >> 9) + 1; }
 // position (in doubles) of real sample j when a real sequence is packed as z[n] = x[2n] + i x[2n+1]
 __device__ __forceinline__ int wb_didx(int j) { return 2 * wb_sidx(j >> 1) + (j & 1); }
 
