@@ -90,14 +90,3 @@ def test_parameter_modification_restatement_matches_reference():
                                                  None if np.isnan(ratio) else float(ratio))
         assert np.array_equal(f0, m["f0_" + tag]), tag
         assert _rel(sp, m["sp_" + tag]) < 1e-14, tag
-
-
-def test_band_transform_index_model():
-    """profiles/band_fft_model.py documents the index mapping of the experimental warp-level band transform of the D4C
-    body (eight 512-point transforms for one 513-sample slice in a 4096-point spectrum): it must reproduce the FFT."""
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, os.path.join(root, "profiles", "band_fft_model.py")], capture_output=True, text=True, timeout=120)
-    assert r.returncode == 0, r.stderr[-2000:]
-    assert float(r.stdout.strip().splitlines()[-1]) < 1e-12
