@@ -595,337 +595,206 @@ struct RefineParams {
 };
 
 #define RF_WARPS 8
-#define RF_GROUP 8   // lanes per candidate (4 candidates per warp)
 
 // Blackman main window at angle cosine c (harvest.cpp:770-774), cos(2t) = 2 cos(t)^2 - 1
 __device__ __forceinline__ double rf_window(double c) { return 0.42 + 0.5 * c + 0.08 * (2.0 * c * c - 1.0); }
 
-// Eight lanes per candidate.  The window angle advances by exactly 2 pi / len per sample, so a
-// lane evaluates one sincos at its first sample (with the reference's expression) and rotates
-// by RF_GROUP samples per step (<= 76 rotations, ~1e-15 drift); the neighbours needed by the
-// differentiated window (harvest.cpp:794-803) come from one more rotation by +-1 sample.
-// Nothing is staged in shared memory.
-__global__ void __launch_bounds__(RF_WARPS * 32) refine_kernel(RefineParams p) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int sub = lane & (RF_GROUP - 1), grp = lane / RF_GROUP;
-  // overlapF0Candidates (harvest.cpp:987-1000): own candidate j of frame src also becomes candidate
-  // j + nc * o of frame src + o (o = 1..3) and of frame src - (o - 3) (o = 4..6); every copy is refined at
-  // its own frame position.  Work item w = 7 * (own candidate) + o.
+// ---------------------------------------------------------------------------------------------
+// The refinement is a small dense contraction and runs on the fp64 tensor pipe.  One warp per OWN candidate: its
+// seven copies (frames src-3 .. src+3, harvest.cpp:987-1000) have the same f0, hence the same window length, the
+// same FFT size and the same harmonic bins -- only the waveform slice differs.  With
+//   A[(copy, window)][i] = window_copy(i) * y[first_copy + i]      (7 x 2 rows: main and differentiated window)
+//   B[i][(h, cos | sin)] = e^{+2 pi i idx_h i / fft_size}           (6 x 2 columns, shared by the seven copies)
+// the two spectra of every copy at the <= 6 bins fixF0 uses (harvest.cpp:809-878) are C = A B, accumulated by
+// mma.sync.m8n8k4.f64: M tile 0 = main windows (row = copy), M tile 1 = differentiated windows, N tile 0 = cosines
+// (column = harmonic), N tile 1 = sines, K = four window samples per step.  Lane (g, t) = (lane / 4, lane % 4)
+// contributes A[g][i0 + t] and B[i0 + t][g]: ONE waveform load, one window evaluation (a rotation recurrence:
+// the window angle advances by exactly 2 pi / len per sample; end rules of harvest.cpp:794-803) and one twiddle gather per lane and step feed four MMAs = 1024
+// multiply-adds, where scalar code issues 24 DFMA per lane for 24 x 32.  The accumulator fragment leaves lane
+// (g, t) with main and differentiated spectra of copy g at harmonics 2t, 2t + 1: fixF0's per-harmonic terms need
+// no exchange, the final sums over the harmonics run in the reference's order.
+// Work items are handed out through a global counter (windows are 31 .. 600 samples long).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void wb_dmma_8x8x4(double &d0, double &d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(RF_WARPS * 32, 3) refine_mma_kernel(RefineParams p, int *__restrict__ ticket) {
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
   const int nc = p.nc_and_count[0];
-  const int n_work = p.nc_and_count[1] * 7;
-  const int groups_per_warp = 32 / RF_GROUP;
-  const int total_groups = gridDim.x * RF_WARPS * groups_per_warp;
+  const int n_own = p.nc_and_count[1];
   const double fs = p.actual_fs;
   const double two_pi = 2.0 * WB_PI;
-  // all lanes of a warp iterate together (the shuffles below use the full mask)
-  const int first = (blockIdx.x * RF_WARPS + warp) * groups_per_warp;
-  for (int base = first; base < n_work; base += total_groups) {
-    const int wi = base + grp;
-    bool active = wi < n_work;
-    const int item = active ? p.work[wi / 7] : 0;
-    const int o = wi % 7;
+  for (;;) {
+    int c = 0;
+    if (lane == 0) c = atomicAdd(ticket, 1);
+    c = __shfl_sync(0xffffffffu, c, 0);
+    if (c >= n_own) break;
+    const int item = p.work[c];
     const int src = item >> 5, own_j = item & 31;
-    const int frame = (o <= 3) ? src + o : src - (o - 3);
-    const int slot = o * nc + own_j;
-    active = active && frame >= 0 && frame < p.f0_length;
-    const size_t at = (size_t)frame * p.max_candidates + slot;
-    const double current_f0 = active ? p.own[(size_t)src * p.own_cap + own_j] : 100.0;
-    const double current_position = frame * p.frame_period / 1000.0;
+    const double current_f0 = p.own[(size_t)src * p.own_cap + own_j];
     const int hw = static_cast<int>(1.5 * fs / current_f0 + 1.0);
-    const int len = active ? 2 * hw + 1 : 0;
+    const int len = 2 * hw + 1;
     const double window_length_in_time = (2.0 * hw + 1.0) / fs;
     const int log2fft = 2 + (31 - __clz(2 * hw + 1));  // 2 + int(log2(len)), len odd
     const int fft_size = 1 << log2fft;
-    const double base_time0 = (-hw + 0) / fs;
-    const int basic_index = wb_round((current_position + base_time0) * fs + 0.001);
     const int nh = wb_min_i(static_cast<int>(fs / 2.0 / current_f0), 6);
-    int idx[6];
-#pragma unroll
-    for (int hh = 0; hh < 6; ++hh) idx[hh] = wb_round(current_f0 * fft_size / fs * (hh + 1));
-    double mr[6], mi[6], dr[6], di[6];
-#pragma unroll
-    for (int hh = 0; hh < 6; ++hh) { mr[hh] = mi[hh] = dr[hh] = di[hh] = 0.0; }
     const cplx *T = p.tw[log2fft];
     const int mask = fft_size - 1;
-    // rotation constants
-    double s1, c1, sg, cg;
-    sincos(two_pi / (2 * hw + 1), &s1, &c1);
-    sincos(two_pi * RF_GROUP / (2 * hw + 1), &sg, &cg);
-    // Interior samples of the differentiated window (harvest.cpp:794-803) in closed form: with
-    // w(a) = 0.42 + 0.5 cos a + 0.08 cos 2a,  -(w(a + d) - w(a - d)) / 2 = sin a (0.5 sin d + 0.16 sin 2d cos a)
-    const double dw_a = 0.5 * s1, dw_b = 0.16 * (2.0 * s1 * c1);
-    double sn, cs;
-    {
-      const double tmp = ((basic_index + sub) - 1.0) / fs - current_position;
-      sincos(two_pi * tmp / window_length_in_time, &sn, &cs);
-    }
-#pragma unroll 2
-    for (int i = sub; i < len; i += RF_GROUP) {
-      const int safe = wb_max_i(0, wb_min_i(p.y_length - 1, basic_index + i - 1));
-      const double yv = p.y[safe];
-      const double w_here = fma(cs, fma(0.16, cs, 0.5), 0.34);  // = rf_window(cs)
-      double dwin = sn * fma(dw_b, cs, dw_a);
-      if (i == 0) dwin = -rf_window(cs * c1 - sn * s1) / 2.0;            // -w[1] / 2
-      else if (i == len - 1) dwin = rf_window(cs * c1 + sn * s1) / 2.0;  // w[len - 2] / 2
-      const double vm = w_here * yv, vd = dwin * yv;
-#pragma unroll
-      for (int hh = 0; hh < 6; ++hh) {
-        if (hh < nh) {
-          const cplx w = __ldg(&T[(idx[hh] * i) & mask]);  // e^{+2 pi i idx n / fft}
-          mr[hh] = fma(vm, w.x, mr[hh]); mi[hh] = fma(vm, w.y, mi[hh]);
-          dr[hh] = fma(vd, w.x, dr[hh]); di[hh] = fma(vd, w.y, di[hh]);
-        }
-      }
-      const double c2 = fma(cs, cg, -(sn * sg));
-      sn = fma(sn, cg, cs * sg);
-      cs = c2;
-    }
-    // Reduce-scatter over the 8 lanes of the group: three exchange steps (lane ^ 4, ^ 2, ^ 1), each lane
-    // keeping half of the harmonic slots it still holds, leave lane `sub` with the complete sums of
-    // harmonic `sub` (slots 6 and 7 are empty) -- 28 exchanges instead of 72 for a full butterfly.
-    double my_mr, my_mi, my_dr, my_di;
-    {
-      const bool up4 = (sub & 4) != 0, up2 = (sub & 2) != 0, up1 = (sub & 1) != 0;
-      double a4[4][4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const double lo[4] = {mr[q], mi[q], dr[q], di[q]};
-        const bool has_hi = q < 2;          // harmonic slots 6 and 7 do not exist
-        const int qh = has_hi ? q + 4 : 0;
-        const double hi[4] = {has_hi ? mr[qh] : 0.0, has_hi ? mi[qh] : 0.0, has_hi ? dr[qh] : 0.0, has_hi ? di[qh] : 0.0};
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const double send = up4 ? lo[c] : hi[c];
-          a4[q][c] = (up4 ? hi[c] : lo[c]) + __shfl_xor_sync(0xffffffffu, send, 4);
-        }
-      }
-      double a2[2][4];
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const double send = up2 ? a4[q][c] : a4[q + 2][c];
-          a2[q][c] = (up2 ? a4[q + 2][c] : a4[q][c]) + __shfl_xor_sync(0xffffffffu, send, 2);
-        }
-      }
-      double a1[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const double send = up1 ? a2[0][c] : a2[1][c];
-        a1[c] = (up1 ? a2[1][c] : a2[0][c]) + __shfl_xor_sync(0xffffffffu, send, 1);
-      }
-      my_mr = a1[0]; my_mi = a1[1]; my_dr = a1[2]; my_di = a1[3];
-    }
-    // fixF0 (harvest.cpp:844-878): lane `sub` evaluates harmonic `sub` (divisions, sqrt in parallel, no
-    // divergence), then every lane accumulates in the reference's order.
-    // spectra are conjugated by the reference (harvest.cpp:829-841): main = (mr, -mi), diff = (dr, -di)
-    double my_inst = 0.0, my_amp = 0.0, my_dev = 0.0;
-    {
-      const double m_re = my_mr, m_im = -my_mi, d_re = my_dr, d_im = -my_di;
-      const int my_idx = wb_round(current_f0 * fft_size / fs * (sub + 1));
-      const double power = m_re * m_re + m_im * m_im;
-      const double num_i = m_re * d_im - m_im * d_re;
-      my_inst = (power == 0.0) ? 0.0
-                : static_cast<double>(my_idx) * fs / fft_size + num_i / power * fs / 2.0 / WB_PI;
-      my_amp = sqrt(power);
-      my_dev = fabs((my_inst / (sub + 1.0) - current_f0) / current_f0);
-    }
-    double numerator = 0.0, denominator = 0.0, score = 0.0;
-#pragma unroll
-    for (int hh = 0; hh < 6; ++hh) {
-      const double inst = __shfl_sync(0xffffffffu, my_inst, hh, RF_GROUP);
-      const double amp = __shfl_sync(0xffffffffu, my_amp, hh, RF_GROUP);
-      const double dev = __shfl_sync(0xffffffffu, my_dev, hh, RF_GROUP);
-      if (hh < nh) {
-        numerator += amp * inst;
-        denominator += amp * (hh + 1.0);
-        score += dev;
-      }
-    }
-    if (sub == 0 && active) {
-      double refined = numerator / (denominator + WB_SAFEGUARD);
-      double sc = 1.0 / (score / nh + WB_SAFEGUARD);
-      if (refined < p.f0_floor || refined > p.f0_ceil || sc < 2.5) { refined = 0.0; sc = 0.0; }
-      p.cand[at] = refined;
-      p.score[at] = sc;
-    }
-  }
-}
-
-// Symmetric formulation for analysis grids on which a frame time is a whole number of decimated samples
-// (actual_fs a multiple of 1000 Hz: 8 kHz for 16 / 24 / 32 / 48 / 96 kHz input).  There the window is sampled at
-// offsets j = i - (hw + 1), j = -(hw + 1) .. hw - 1, from its centre: the Blackman window is even and its
-// differentiated version odd in j, so the samples at +j and -j share one twiddle e^{i theta j}:
-//   main  += w_j [ (y_j + y_-j) cos + i (y_j - y_-j) sin ],   diff += d_j [ (y_j - y_-j) cos + i (y_j + y_-j) sin ]
-// i.e. 4 multiply-adds per PAIR and harmonic instead of 8, and one window evaluation per pair.  fixF0 only uses
-// |main|^2 and Im(conj(main) diff), which do not change when both spectra are referred to the window centre
-// instead of its first sample, so no phase factor is needed.  The five samples that have no partner or an end
-// rule (i = 0, 1, 2, hw + 1, 2 hw: harvest.cpp:794-803) are accumulated one by one.  The kernel is bound by fp64
-// issue; this removes ~40 % of its fp64 instructions.  An item whose centre is not on a sample (never on such
-// grids, checked per item) is accumulated sample by sample throughout.
-__global__ void __launch_bounds__(RF_WARPS * 32, 2) refine_sym_kernel(RefineParams p) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int sub = lane & (RF_GROUP - 1), grp = lane / RF_GROUP;
-  const int nc = p.nc_and_count[0];
-  const int n_work = p.nc_and_count[1] * 7;
-  const int groups_per_warp = 32 / RF_GROUP;
-  const int total_groups = gridDim.x * RF_WARPS * groups_per_warp;
-  const double fs = p.actual_fs;
-  const double two_pi = 2.0 * WB_PI;
-  const int first = (blockIdx.x * RF_WARPS + warp) * groups_per_warp;
-  for (int base = first; base < n_work; base += total_groups) {
-    const int wi = base + grp;
-    bool active = wi < n_work;
-    const int item = active ? p.work[wi / 7] : 0;
-    const int o = wi % 7;
-    const int src = item >> 5, own_j = item & 31;
+    // row of this lane: copy o = g (row 7 is padding)
+    const int o = g;
     const int frame = (o <= 3) ? src + o : src - (o - 3);
-    const int slot = o * nc + own_j;
-    active = active && frame >= 0 && frame < p.f0_length;
-    const size_t at = (size_t)frame * p.max_candidates + slot;
-    const double current_f0 = active ? p.own[(size_t)src * p.own_cap + own_j] : 100.0;
+    const bool row_active = o < 7 && frame >= 0 && frame < p.f0_length;
     const double current_position = frame * p.frame_period / 1000.0;
-    const int hw = static_cast<int>(1.5 * fs / current_f0 + 1.0);
-    const int len = active ? 2 * hw + 1 : 0;
-    const double window_length_in_time = (2.0 * hw + 1.0) / fs;
-    const int log2fft = 2 + (31 - __clz(2 * hw + 1));
-    const int fft_size = 1 << log2fft;
     const double base_time0 = (-hw + 0) / fs;
     const int basic_index = wb_round((current_position + base_time0) * fs + 0.001);
-    const int nh = wb_min_i(static_cast<int>(fs / 2.0 / current_f0), 6);
-    int idx[6];
-#pragma unroll
-    for (int hh = 0; hh < 6; ++hh) idx[hh] = wb_round(current_f0 * fft_size / fs * (hh + 1));
-    double mr[6], mi[6], dr[6], di[6];
-#pragma unroll
-    for (int hh = 0; hh < 6; ++hh) { mr[hh] = mi[hh] = dr[hh] = di[hh] = 0.0; }
-    const cplx *T = p.tw[log2fft];
-    const int mask = fft_size - 1;
-    double s1, c1, sg, cg;
+    // column of this lane: harmonic g (columns 6, 7 are padding)
+    const int idx_col = g < 6 ? wb_round(current_f0 * fft_size / fs * (g + 1)) : 0;
+    double s1, c1;
     sincos(two_pi / (2 * hw + 1), &s1, &c1);
-    sincos(two_pi * RF_GROUP / (2 * hw + 1), &sg, &cg);
-    const double dw_a = 0.5 * s1, dw_b = 0.16 * (2.0 * s1 * c1);   // differentiated window in closed form (see refine_kernel)
+    // rotation by four samples from the one-sample rotation (two angle doublings; 1 - 2 sin^2 keeps the cosine accurate)
+    const double s2 = 2.0 * s1 * c1, c2a = 1.0 - 2.0 * s1 * s1;
+    const double sg = 2.0 * s2 * c2a, cg = 1.0 - 2.0 * s2 * s2;
+    const double dw_a = 0.5 * s1, dw_b = 0.16 * (2.0 * s1 * c1);   // interior samples of the differentiated window (harvest.cpp:794-803) in closed form: with w(a) = 0.42 + 0.5 cos a + 0.08 cos 2a, -(w(a + d) - w(a - d)) / 2 = sin a (0.5 sin d + 0.16 sin 2d cos a)
+    double mc0 = 0.0, mc1 = 0.0, ms0 = 0.0, ms1 = 0.0, dc0 = 0.0, dc1 = 0.0, ds0 = 0.0, ds1 = 0.0;
+    const int y_first = basic_index - 1, y_last = p.y_length - 1;
     const int i_c = hw + 1;   // the sample the window is centred on
     // the reference's own expression for the window argument of that sample: zero when the centre is on the grid
     const double centre = ((basic_index + i_c) - 1.0) / fs - current_position;
-    const bool symmetric = fabs(centre) * fs < 1e-6;
-    const int y_first = basic_index - 1, y_last = p.y_length - 1;
-    // one sample, by the reference's expressions (twiddle referred to the centre sample)
-    auto single = [&](int i) {
+    const bool symmetric = __all_sync(0xffffffffu, !row_active || fabs(centre) * fs < 1e-6);
+    // one window sample by the reference's expressions (harvest.cpp:762-803): main and differentiated window times y
+    auto sample = [&](int i, double &vm, double &vd) {
       const double tmp = ((basic_index + i) - 1.0) / fs - current_position;
       double sn, cs;
       sincos(two_pi * tmp / window_length_in_time, &sn, &cs);
-      const double yv = p.y[wb_max_i(0, wb_min_i(y_last, y_first + i))];
-      const double w_here = rf_window(cs);
+      const double yv = row_active ? p.y[wb_max_i(0, wb_min_i(y_last, y_first + i))] : 0.0;
       double dwin = sn * fma(dw_b, cs, dw_a);
       if (i == 0) dwin = -rf_window(cs * c1 - sn * s1) / 2.0;            // -w[1] / 2
       else if (i == len - 1) dwin = rf_window(cs * c1 + sn * s1) / 2.0;  // w[len - 2] / 2
-      const double vm = w_here * yv, vd = dwin * yv;
-#pragma unroll
-      for (int hh = 0; hh < 6; ++hh) {
-        if (hh < nh) {
-          const cplx w = __ldg(&T[(idx[hh] * (i - i_c)) & mask]);
-          mr[hh] = fma(vm, w.x, mr[hh]); mi[hh] = fma(vm, w.y, mi[hh]);
-          dr[hh] = fma(vd, w.x, dr[hh]); di[hh] = fma(vd, w.y, di[hh]);
-        }
-      }
+      vm = rf_window(cs) * yv;
+      vd = dwin * yv;
     };
-    if (!symmetric) {
-      for (int i = sub; i < len; i += RF_GROUP) single(i);
-    } else if (len > 0) {
-      // unpaired samples and the two with an end rule (and their partners): i = 0, 1, 2, hw + 1, 2 hw
-      if (sub < 5) {
-        const int i = sub == 0 ? 0 : (sub == 1 ? 1 : (sub == 2 ? 2 : (sub == 3 ? i_c : 2 * hw)));
-        // (hw >= 2 always: f0 <= f0_ceil * 1.1 well below 1.5 fs / 2; for tiny windows some of these coincide)
-        bool dup = false;
-        if (sub == 3) dup = (i <= 2);
-        if (sub == 4) dup = (i <= 2 || i == i_c);
-        if (!dup && i < len) single(i);
-      }
-      // pairs j = 1 .. hw - 2  (samples i_c + j and i_c - j; i_c - j >= 3, i_c + j <= 2 hw - 1)
+    if (symmetric) {
+      // Frame times on whole decimated samples (actual_fs a multiple of 1000 Hz): the window is even and its
+      // differentiated version odd about the centre sample, so the samples at +j and -j share one twiddle
+      // and K halves: with ys = y_j + y_-j, yd = y_j - y_-j,
+      //   main += w_j (ys cos + i yd sin),   diff += d_j (yd cos + i ys sin),   spectra referred to the centre sample
+      // (fixF0 only uses |main|^2 and Im(conj(main) diff), which a common phase does not change).
+      // Pairs j = 1 .. hw - 2 (samples 3 .. 2 hw - 1); the five samples without a partner or with an end rule
+      // (0, 1, 2, hw + 1, 2 hw) follow in two more steps.
       double sn, cs;
-      sincos(two_pi * (1 + sub) / (2 * hw + 1), &sn, &cs);
-      for (int j = 1 + sub; j <= hw - 2; j += RF_GROUP) {
-        const double yp = p.y[wb_max_i(0, wb_min_i(y_last, y_first + i_c + j))];
-        const double ym = p.y[wb_max_i(0, wb_min_i(y_last, y_first + i_c - j))];
+      sincos(two_pi * (1 + t) / (2 * hw + 1), &sn, &cs);
+      const int yc = y_first + i_c;
+      const int n_pairs = hw - 2;
+      int j = 1 + t;
+      double yp_next = 0.0, ym_next = 0.0;
+      if (row_active && j <= n_pairs) {
+        yp_next = p.y[wb_max_i(0, wb_min_i(y_last, yc + j))];
+        ym_next = p.y[wb_max_i(0, wb_min_i(y_last, yc - j))];
+      }
+      cplx w_next = __ldg(&T[(idx_col * j) & mask]);
+      for (int j0 = 1; j0 <= n_pairs; j0 += 4, j += 4) {
+        const double yp = yp_next, ym = ym_next;
+        const cplx w = w_next;
+        const int jn = j + 4;
+        yp_next = 0.0; ym_next = 0.0;
+        if (row_active && jn <= n_pairs) {
+          yp_next = p.y[wb_max_i(0, wb_min_i(y_last, yc + jn))];
+          ym_next = p.y[wb_max_i(0, wb_min_i(y_last, yc - jn))];
+        }
+        w_next = __ldg(&T[(idx_col * jn) & mask]);
         const double w_here = fma(cs, fma(0.16, cs, 0.5), 0.34);
         const double dwin = sn * fma(dw_b, cs, dw_a);
-        const double ys = yp + ym, yd = yp - ym;
-        const double a = w_here * ys, b = w_here * yd, c = dwin * yd, e = dwin * ys;
+        const double ys = yp + ym, yd = yp - ym;     // (both zero past the last pair)
+        wb_dmma_8x8x4(mc0, mc1, w_here * ys, w.x);
+        wb_dmma_8x8x4(ms0, ms1, w_here * yd, w.y);
+        wb_dmma_8x8x4(dc0, dc1, dwin * yd, w.x);
+        wb_dmma_8x8x4(ds0, ds1, dwin * ys, w.y);
+        const double c2 = fma(cs, cg, -(sn * sg));
+        sn = fma(sn, cg, cs * sg);
+        cs = c2;
+      }
 #pragma unroll
-        for (int hh = 0; hh < 6; ++hh) {
-          if (hh < nh) {
-            const cplx w = __ldg(&T[(idx[hh] * j) & mask]);
-            mr[hh] = fma(a, w.x, mr[hh]); mi[hh] = fma(b, w.y, mi[hh]);
-            dr[hh] = fma(c, w.x, dr[hh]); di[hh] = fma(e, w.y, di[hh]);
-          }
+      for (int step = 0; step < 2; ++step) {
+        const int i = step == 0 ? (t == 0 ? 0 : (t == 1 ? 1 : (t == 2 ? 2 : i_c))) : 2 * hw;
+        // (hw >= 2 always: f0 <= f0_ceil * 1.1 well below 1.5 fs / 2; for tiny windows some of these coincide)
+        bool use = i < len;
+        if (step == 0 && t == 3) use = use && i > 2;
+        if (step == 1) use = use && t == 0 && i > 2 && i != i_c;
+        double vm = 0.0, vd = 0.0;
+        if (use) sample(i, vm, vd);
+        const cplx w = __ldg(&T[(idx_col * (i - i_c)) & mask]);
+        wb_dmma_8x8x4(mc0, mc1, vm, w.x);
+        wb_dmma_8x8x4(ms0, ms1, vm, w.y);
+        wb_dmma_8x8x4(dc0, dc1, vd, w.x);
+        wb_dmma_8x8x4(ds0, ds1, vd, w.y);
+      }
+    } else {
+      double sn, cs;
+      {
+        const double tmp = ((basic_index + t) - 1.0) / fs - current_position;
+        sincos(two_pi * tmp / window_length_in_time, &sn, &cs);
+      }
+      double y_next = (row_active && t < len) ? p.y[wb_max_i(0, wb_min_i(y_last, y_first + t))] : 0.0;
+      cplx w_next = __ldg(&T[(idx_col * t) & mask]);
+      for (int i = t; i < len + t; i += 4) {   // (every lane makes the same number of steps: the MMAs are warp-wide)
+        const double yv = y_next;
+        const cplx w = w_next;
+        const int in = i + 4;
+        y_next = (row_active && in < len) ? p.y[wb_max_i(0, wb_min_i(y_last, y_first + in))] : 0.0;
+        w_next = __ldg(&T[(idx_col * in) & mask]);
+        double a_main = 0.0, a_diff = 0.0;
+        if (i < len) {
+          const double w_here = fma(cs, fma(0.16, cs, 0.5), 0.34);  // = rf_window(cs)
+          double dwin = sn * fma(dw_b, cs, dw_a);
+          if (i == 0) dwin = -rf_window(cs * c1 - sn * s1) / 2.0;            // -w[1] / 2
+          else if (i == len - 1) dwin = rf_window(cs * c1 + sn * s1) / 2.0;  // w[len - 2] / 2
+          a_main = w_here * yv;
+          a_diff = dwin * yv;
         }
+        wb_dmma_8x8x4(mc0, mc1, a_main, w.x);
+        wb_dmma_8x8x4(ms0, ms1, a_main, w.y);
+        wb_dmma_8x8x4(dc0, dc1, a_diff, w.x);
+        wb_dmma_8x8x4(ds0, ds1, a_diff, w.y);
         const double c2 = fma(cs, cg, -(sn * sg));
         sn = fma(sn, cg, cs * sg);
         cs = c2;
       }
     }
-    // reduce-scatter over the 8 lanes and fixF0: as in refine_kernel
-    double my_mr, my_mi, my_dr, my_di;
-    {
-      const bool up4 = (sub & 4) != 0, up2 = (sub & 2) != 0, up1 = (sub & 1) != 0;
-      double a4[4][4];
+    // fixF0 (harvest.cpp:844-878) for harmonics 2t and 2t + 1 of copy g; spectra are conjugated by the reference
+    // (harvest.cpp:829-841): main = (mr, -mi), diff = (dr, -di)
+    double inst[2], amp[2], dev[2];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const double lo[4] = {mr[q], mi[q], dr[q], di[q]};
-        const bool has_hi = q < 2;
-        const int qh = has_hi ? q + 4 : 0;
-        const double hi[4] = {has_hi ? mr[qh] : 0.0, has_hi ? mi[qh] : 0.0, has_hi ? dr[qh] : 0.0, has_hi ? di[qh] : 0.0};
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const double send = up4 ? lo[c] : hi[c];
-          a4[q][c] = (up4 ? hi[c] : lo[c]) + __shfl_xor_sync(0xffffffffu, send, 4);
-        }
-      }
-      double a2[2][4];
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const double send = up2 ? a4[q][c] : a4[q + 2][c];
-          a2[q][c] = (up2 ? a4[q + 2][c] : a4[q][c]) + __shfl_xor_sync(0xffffffffu, send, 2);
-        }
-      }
-      double a1[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const double send = up1 ? a2[0][c] : a2[1][c];
-        a1[c] = (up1 ? a2[1][c] : a2[0][c]) + __shfl_xor_sync(0xffffffffu, send, 1);
-      }
-      my_mr = a1[0]; my_mi = a1[1]; my_dr = a1[2]; my_di = a1[3];
-    }
-    double my_inst = 0.0, my_amp = 0.0, my_dev = 0.0;
-    {
-      const double m_re = my_mr, m_im = -my_mi, d_re = my_dr, d_im = -my_di;
-      const int my_idx = wb_round(current_f0 * fft_size / fs * (sub + 1));
+    for (int e = 0; e < 2; ++e) {
+      const int hh = 2 * t + e;
+      const double m_re = e ? mc1 : mc0, m_im = -(e ? ms1 : ms0), d_re = e ? dc1 : dc0, d_im = -(e ? ds1 : ds0);
+      const int my_idx = wb_round(current_f0 * fft_size / fs * (hh + 1));
       const double power = m_re * m_re + m_im * m_im;
       const double num_i = m_re * d_im - m_im * d_re;
-      my_inst = (power == 0.0) ? 0.0
-                : static_cast<double>(my_idx) * fs / fft_size + num_i / power * fs / 2.0 / WB_PI;
-      my_amp = sqrt(power);
-      my_dev = fabs((my_inst / (sub + 1.0) - current_f0) / current_f0);
+      inst[e] = (power == 0.0) ? 0.0 : static_cast<double>(my_idx) * fs / fft_size + num_i / power * fs / 2.0 / WB_PI;
+      amp[e] = sqrt(power);
+      dev[e] = fabs((inst[e] / (hh + 1.0) - current_f0) / current_f0);
     }
     double numerator = 0.0, denominator = 0.0, score = 0.0;
 #pragma unroll
     for (int hh = 0; hh < 6; ++hh) {
-      const double inst = __shfl_sync(0xffffffffu, my_inst, hh, RF_GROUP);
-      const double amp = __shfl_sync(0xffffffffu, my_amp, hh, RF_GROUP);
-      const double dev = __shfl_sync(0xffffffffu, my_dev, hh, RF_GROUP);
+      const int from = hh >> 1;   // lane t of the row's group of four
+      const double in_ = __shfl_sync(0xffffffffu, (hh & 1) ? inst[1] : inst[0], from, 4);
+      const double am_ = __shfl_sync(0xffffffffu, (hh & 1) ? amp[1] : amp[0], from, 4);
+      const double de_ = __shfl_sync(0xffffffffu, (hh & 1) ? dev[1] : dev[0], from, 4);
       if (hh < nh) {
-        numerator += amp * inst;
-        denominator += amp * (hh + 1.0);
-        score += dev;
+        numerator += am_ * in_;
+        denominator += am_ * (hh + 1.0);
+        score += de_;
       }
     }
-    if (sub == 0 && active) {
+    if (t == 0 && row_active) {
       double refined = numerator / (denominator + WB_SAFEGUARD);
       double sc = 1.0 / (score / nh + WB_SAFEGUARD);
       if (refined < p.f0_floor || refined > p.f0_ceil || sc < 2.5) { refined = 0.0; sc = 0.0; }
+      const size_t at = (size_t)frame * p.max_candidates + (o * nc + own_j);
       p.cand[at] = refined;
       p.score[at] = sc;
     }
@@ -1201,13 +1070,11 @@ int wb_harvest_run_basic(WbHarvestPlan *pl, WbWorkspace *ws, const double *d_x, 
       p.tw[l] = wb_twiddle_table(1 << l);
       if (!p.tw[l]) return WB_ERR_CUDA;
     }
-    // frame times fall on whole decimated samples when actual_fs is a multiple of 1000 Hz (1 ms analysis grid)
-    static const int refine_variant = getenv("WB_REFINE") ? atoi(getenv("WB_REFINE")) : 3;
-    const bool on_grid = frame_period == 1 && fabs(afs / 1000.0 - floor(afs / 1000.0 + 0.5)) < 1e-9;
-    if (refine_variant == 3 && on_grid) {
-      WB_LAUNCH("refine_kernel", refine_sym_kernel<<<148 * 8, RF_WARPS * 32, 0, stream>>>(p));
-    } else {
-      WB_LAUNCH("refine_kernel", refine_kernel<<<148 * 8, RF_WARPS * 32, 0, stream>>>(p));
+    {
+      int dev = 0, sms = 148;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      WB_LAUNCH("refine_kernel", refine_mma_kernel<<<sms * 8, RF_WARPS * 32, 0, stream>>>(p, d_nc + 2));
     }
     WB_CUDA_CHECK(cudaGetLastError());
   }
