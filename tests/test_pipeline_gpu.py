@@ -83,3 +83,31 @@ def test_graph_replay_is_identical(wb, signals):
         outs.append((ys[-1], d_f0.cpu().numpy().copy()))
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
     assert np.abs(outs[0][0]).max() > 0.1
+
+
+def test_graph_survives_workspace_growth(wb, signals):
+    """A captured graph must not be replayed after a longer input made the workspace reallocate its buffers
+    (ADVICE round 1): A, A (capture), B (longer, grows), A again."""
+    import torch
+    fs = 16000
+    xa = signals.synth_speech(fs, 0.6, seed=14)
+    xb = signals.synth_speech(fs, 1.5, seed=15)
+    pl = wb.Pipeline(fs, wb.HarvestOption(f0_floor=40.0, frame_period=5.0), wb.CheapTrickOption(f0_floor=71.0))
+    pl.set_fresh_rng(True)
+    pl.set_graph(True)
+    d_a, d_b = torch.from_numpy(xa).cuda(), torch.from_numpy(xb).cuda()
+
+    d_ya = torch.zeros(pl.out_length(len(xa)), dtype=torch.float64, device="cuda")
+    d_yb = torch.zeros(pl.out_length(len(xb)), dtype=torch.float64, device="cuda")
+
+    def run(d_x, n, d_y):   # (same pointers every time: the graph key matches)
+        d_y.zero_()
+        pl.run_dev(d_x.data_ptr(), n, d_y=d_y.data_ptr(), y_length=d_y.numel())
+        wb.device_synchronize()
+        return d_y.cpu().numpy().copy()
+
+    ya = [run(d_a, len(xa), d_ya) for _ in range(3)]
+    yb = run(d_b, len(xb), d_yb)
+    ya2 = run(d_a, len(xa), d_ya)
+    assert np.abs(yb).max() > 0.1
+    assert all(np.array_equal(ya[0], y) for y in ya[1:]) and np.array_equal(ya[0], ya2)

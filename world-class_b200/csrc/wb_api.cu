@@ -302,6 +302,8 @@ struct wb_pipeline {
   // After Harvest the chain forks: CheapTrick stays on the caller's stream, D4C runs on `d4c_stream`
   // and the Synthesis time base / pulse list / noise on `side`; they join before the impulse responses.
   cudaStream_t side = nullptr, d4c_stream = nullptr;
+  unsigned long long graph_generation = 0;   // ws.generation() when the graph was captured
+  int stream_f0_length = 0;          // sharded streams: the length given to wb_pipeline_stream_begin_dev
   cudaEvent_t ev_f0 = nullptr, ev_tb = nullptr, ev_ct_count = nullptr, ev_body_count = nullptr, ev_d4c = nullptr,
               ev_start = nullptr;
   // CUDA graph of one whole run (captured after a warm run with the same arguments)
@@ -707,8 +709,9 @@ int wb_harvest_compute(wb_harvest_t *h, const double *x, int x_length, double *t
 /* debug: copy the first n_bytes of a named internal device buffer of the last compute() */
 int wb_harvest_debug_read(wb_harvest_t *h, const char *name, void *out, unsigned long long n_bytes) {
   if (!h || !name || !out) return WB_ERR_ARG;
-  void *d = h->ws.get(name, 0);
-  if (!d) return WB_ERR_ARG;
+  size_t have = 0;
+  void *d = h->ws.find(name, &have);
+  if (!d || n_bytes > have) return WB_ERR_ARG;   // unknown buffer, or more than it holds
   WB_CUDA_CHECK(cudaStreamSynchronize(g_stream));
   WB_CUDA_CHECK(cudaMemcpy(out, d, n_bytes, cudaMemcpyDeviceToHost));
   return WB_OK;
@@ -769,6 +772,7 @@ int wb_pipeline_set_fresh_rng(wb_pipeline_t *p, int fresh) {
     WB_CUDA_CHECK(cudaMemcpy(p->d_rng_seed, &s0, sizeof(s0), cudaMemcpyHostToDevice));
   }
   p->private_rng = fresh != 0;
+  if (p->graph_exec) { cudaGraphExecDestroy(p->graph_exec); p->graph_exec = nullptr; }   // the captured chain names the state
   return WB_OK;
 }
 int wb_pipeline_fft_size(const wb_pipeline_t *p) { return p ? p->ct.fft_size : 0; }
@@ -808,8 +812,9 @@ int wb_pipeline_run_dev(wb_pipeline_t *p, const double *d_x, int x_length, doubl
   if (!p->use_graph || wb_prof_is_enabled())
     return pipeline_enqueue(p, d_x, x_length, d_tpos, d_f0, d_sp, d_ap, d_y, y_length, st);
   const void *key[8] = {d_x, d_tpos, d_f0, d_sp, d_ap, d_y, (const void *)st, nullptr};
+  // (the graph holds raw pointers into the workspace: stale once any of its buffers has been reallocated)
   const bool same = p->graph_exec && memcmp(key, p->graph_key, sizeof(key)) == 0 && p->graph_len[0] == x_length &&
-                    p->graph_len[1] == y_length;
+                    p->graph_len[1] == y_length && p->graph_generation == p->ws.generation();
   if (same) {
     WB_CUDA_CHECK(cudaGraphLaunch(p->graph_exec, st));
     wb_launch_counter_add(p->graph_kernels);
@@ -841,6 +846,7 @@ int wb_pipeline_run_dev(wb_pipeline_t *p, const double *d_x, int x_length, doubl
   if (e != cudaSuccess) { p->graph_exec = nullptr; p->use_graph = false; cudaGetLastError(); return pipeline_enqueue(p, d_x, x_length, d_tpos, d_f0, d_sp, d_ap, d_y, y_length, st); }
   memcpy(p->graph_key, key, sizeof(key));
   p->graph_len[0] = x_length; p->graph_len[1] = y_length;
+  p->graph_generation = p->ws.generation();
   WB_CUDA_CHECK(cudaGraphLaunch(p->graph_exec, st));
   return WB_OK;
 }
@@ -858,9 +864,14 @@ static int pipeline_enqueue(wb_pipeline_t *p, const double *d_x, int x_length, d
   if (!d_y && y_length > 0) d_y = (double *)p->ws.get("pl_y", sizeof(double) * (size_t)y_length);
   if (!d_tpos || !d_f0 || !d_sp || !d_ap) return WB_ERR_CUDA;
   int rc, Lb = 0;
+  WbRngState *rng = wb_rng_global_state();
+  if (p->private_rng) {
+    rng = p->d_rng_private;
+    WB_CUDA_CHECK(cudaMemcpyAsync(rng, p->d_rng_seed, sizeof(WbRngState), cudaMemcpyDeviceToDevice, st));
+  }
+  WB_CUDA_CHECK(cudaEventRecord(p->ev_start, st));
   // (side stream, joined with the pulse list further down: warm L2 with the randn jump tables while Harvest runs)
   if (y_length > 0 && !wb_prof_is_enabled()) {
-    WB_CUDA_CHECK(cudaEventRecord(p->ev_start, st));
     WB_CUDA_CHECK(cudaStreamWaitEvent(p->side, p->ev_start, 0));
     if ((rc = wb_rng_prefetch_tables(p->side))) return rc;
   }
@@ -884,11 +895,6 @@ static int pipeline_enqueue(wb_pipeline_t *p, const double *d_x, int x_length, d
     if (!d_mod) return WB_ERR_CUDA;
     if ((rc = wb_parameter_modification_run(d_f0, d_mod, f0_length, nullptr, fs, p->ct.fft_size, p->mod_f0_shift, 0.0, st))) return rc;
     d_f0_syn = d_mod;
-  }
-  WbRngState *rng = wb_rng_global_state();
-  if (p->private_rng) {
-    rng = p->d_rng_private;
-    WB_CUDA_CHECK(cudaMemcpyAsync(rng, p->d_rng_seed, sizeof(WbRngState), cudaMemcpyDeviceToDevice, st));
   }
   // Fork.  Everything below depends on f0 only until the impulse responses need sp, ap and the pulses.
   // The randn() stream is consumed in the reference's serial order CheapTrick -> Love Train -> D4C body
@@ -995,6 +1001,7 @@ int wb_pipeline_stream_begin_dev(wb_pipeline_t *p, const double *d_f0_all, int f
   if (!d_tpos || !rng_pos) return WB_ERR_CUDA;
   WB_LAUNCH("frame_times_kernel", frame_times_kernel<<<(f0_length + 255) / 256, 256, 0, stream>>>(d_tpos, f0_length, fp));
   WB_CUDA_CHECK(cudaGetLastError());
+  p->stream_f0_length = f0_length;
   if (p->private_rng)
     WB_CUDA_CHECK(cudaMemcpyAsync(p->d_rng_private, p->d_rng_seed, sizeof(WbRngState), cudaMemcpyDeviceToDevice, stream));
   // the time base / exact phase scan / pulse list of the whole stream depend on f0 only: side stream
@@ -1013,9 +1020,10 @@ int wb_pipeline_stream_envelope_dev(wb_pipeline_t *p, const double *d_x, int x_l
                                     double *d_ap0_all, void *stream_) {
   if (!p || !d_x || !d_f0_all || !d_sp_rows || !d_ap0_all || x_length <= 0) return WB_ERR_ARG;
   cudaStream_t stream = pick_stream(stream_);
-  double *d_tpos = (double *)p->ws.get("st_tpos", 0);
-  unsigned long long *rng_pos = (unsigned long long *)p->ws.get("pl_rng_pos", 0);
-  if (!d_tpos || !rng_pos) return WB_ERR_ARG;   // begin has not been called
+  double *d_tpos = (double *)p->ws.find("st_tpos");
+  unsigned long long *rng_pos = (unsigned long long *)p->ws.find("pl_rng_pos");
+  if (!d_tpos || !rng_pos || f0_length != p->stream_f0_length) return WB_ERR_ARG;   // begin has not been called (with this length)
+  if (frame_begin < 0 || frame_end > f0_length || frame_begin > frame_end) return WB_ERR_ARG;
   WbRngState *rng = p->private_rng ? p->d_rng_private : wb_rng_global_state();
   const WbFrameRange range = {frame_begin, frame_end};
   WbRngCursor c_ct;
@@ -1035,9 +1043,10 @@ int wb_pipeline_stream_aperiodicity_dev(wb_pipeline_t *p, const double *d_x, int
                                         double *d_ap_rows, void *stream_) {
   if (!p || !d_x || !d_f0_all || !d_ap_rows || !d_ap0_all || x_length <= 0) return WB_ERR_ARG;
   cudaStream_t stream = pick_stream(stream_);
-  double *d_tpos = (double *)p->ws.get("st_tpos", 0);
-  unsigned long long *rng_pos = (unsigned long long *)p->ws.get("pl_rng_pos", 0);
-  if (!d_tpos || !rng_pos) return WB_ERR_ARG;
+  double *d_tpos = (double *)p->ws.find("st_tpos");
+  unsigned long long *rng_pos = (unsigned long long *)p->ws.find("pl_rng_pos");
+  if (!d_tpos || !rng_pos || f0_length != p->stream_f0_length) return WB_ERR_ARG;
+  if (frame_begin < 0 || frame_end > f0_length || frame_begin > frame_end) return WB_ERR_ARG;
   WbRngState *rng = p->private_rng ? p->d_rng_private : wb_rng_global_state();
   const WbFrameRange range = {frame_begin, frame_end};
   WbRngCursor c;
@@ -1051,8 +1060,8 @@ int wb_pipeline_stream_synthesis_dev(wb_pipeline_t *p, int f0_length, const doub
                                      double *d_out, void *stream_) {
   if (!p || !d_sp_rows || !d_ap_rows || !d_out || out_length <= 0) return WB_ERR_ARG;
   cudaStream_t stream = pick_stream(stream_);
-  unsigned long long *rng_pos = (unsigned long long *)p->ws.get("pl_rng_pos", 0);
-  if (!rng_pos || !p->ws.get("syn_pidx", 0)) return WB_ERR_ARG;   // begin (with out_length > 0) has not been called
+  unsigned long long *rng_pos = (unsigned long long *)p->ws.find("pl_rng_pos");
+  if (!rng_pos || !p->ws.find("syn_pidx") || f0_length != p->stream_f0_length) return WB_ERR_ARG;   // begin (with out_length > 0) has not been called
   WbRngState *rng = p->private_rng ? p->d_rng_private : wb_rng_global_state();
   WB_CUDA_CHECK(cudaStreamWaitEvent(stream, p->ev_tb, 0));
   WbRngCursor c;
@@ -1066,8 +1075,8 @@ int wb_pipeline_stream_synthesis_dev(wb_pipeline_t *p, int f0_length, const doub
 int wb_pipeline_stream_end_dev(wb_pipeline_t *p, void *stream_) {
   if (!p) return WB_ERR_ARG;
   cudaStream_t stream = pick_stream(stream_);
-  unsigned long long *rng_pos = (unsigned long long *)p->ws.get("pl_rng_pos", 0);
-  unsigned long long *d_ncount = (unsigned long long *)p->ws.get("syn_ncount", 0);
+  unsigned long long *rng_pos = (unsigned long long *)p->ws.find("pl_rng_pos");
+  unsigned long long *d_ncount = (unsigned long long *)p->ws.find("syn_ncount");
   if (!rng_pos) return WB_ERR_ARG;
   WbRngState *rng = p->private_rng ? p->d_rng_private : wb_rng_global_state();
   return wb_rng_advance(rng, rng_pos + 1, d_ncount, stream);
@@ -1290,8 +1299,9 @@ int wb_codec_dev(int kind, const double *d_in, int f0_length, int fs, int fft_si
 /* test / bench hook: copies n_bytes of a named internal device buffer of the last run */
 int wb_pipeline_debug_read(wb_pipeline_t *p, const char *name, void *out, unsigned long long n_bytes) {
   if (!p || !name || !out) return WB_ERR_ARG;
-  void *d = p->ws.get(name, 0);
-  if (!d) return WB_ERR_ARG;
+  size_t have = 0;
+  void *d = p->ws.find(name, &have);
+  if (!d || n_bytes > have) return WB_ERR_ARG;   // unknown buffer, or more than it holds
   WB_CUDA_CHECK(cudaDeviceSynchronize());
   WB_CUDA_CHECK(cudaMemcpy(out, d, n_bytes, cudaMemcpyDeviceToHost));
   return WB_OK;

@@ -997,7 +997,7 @@ int wb_harvest_run_basic(WbHarvestPlan *pl, WbWorkspace *ws, const double *d_x, 
   if (!d_ecount || !d_seg || !d_segc) return WB_ERR_CUDA;
   {
     ChanParams p;
-    p.Yb = d_Yb; p.Hc = (const cplx *)ws->get("hv_Hc", 0); p.half_len = (const int *)ws->get("hv_hl", 0);
+    p.Yb = d_Yb; p.Hc = (const cplx *)ws->find("hv_Hc"); p.half_len = (const int *)ws->find("hv_hl");
     p.n_blocks = n_blocks; p.NB = NB; p.log2nc = log2nc; p.V = pl->V; p.h_max = pl->h_max; p.y_length = y_length;
     p.tw = tw; p.seg_edges = d_seg; p.seg_count = d_segc; p.bcap = bcap;
     dim3 grid(n_blocks, nch);
@@ -1044,7 +1044,7 @@ int wb_harvest_run_basic(WbHarvestPlan *pl, WbWorkspace *ws, const double *d_x, 
   WB_CUDA_CHECK(cudaStreamWaitEvent(stream, pl->aux_join, 0));   // the table clears issued at the top
   {
     CandParams p;
-    p.contour = d_contour; p.ecount = d_ecount; p.boundary_f0 = (const double *)ws->get("hv_bf", 0);
+    p.contour = d_contour; p.ecount = d_ecount; p.boundary_f0 = (const double *)ws->find("hv_bf");
     p.nch = nch; p.f0_length = Lb; p.f0_floor = pl->opt.f0_floor; p.f0_ceil = pl->opt.f0_ceil;
     p.raw = d_raw; p.own = d_own; p.own_cap = own_cap; p.nc_max = d_nc; p.work = d_work;
     const size_t smem = sizeof(double) * (size_t)nch * CD_PITCH;

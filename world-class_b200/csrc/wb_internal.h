@@ -11,7 +11,12 @@ class WbWorkspace {
  public:
   WbWorkspace();
   ~WbWorkspace();
-  void *get(const std::string &name, size_t bytes);        // device memory
+  void *get(const std::string &name, size_t bytes);        // device memory (allocates / grows)
+  // look-up only: the buffer and its size if `name` exists, else null (never allocates)
+  void *find(const std::string &name, size_t *bytes_out = nullptr) const;
+  // bumped whenever a device buffer is freed (a buffer had to grow): captured CUDA graphs that hold raw
+  // pointers into the workspace are stale once this differs from the value at capture time
+  unsigned long long generation() const { return generation_; }
   // like get(), but the first `keep_bytes` of an existing buffer survive a reallocation (synchronises `stream`)
   void *get_keep(const std::string &name, size_t bytes, size_t keep_bytes, cudaStream_t stream);
   void *get_pinned(const std::string &name, size_t bytes);  // page-locked host memory
@@ -20,6 +25,7 @@ class WbWorkspace {
  private:
   struct Buf { void *p; size_t bytes; };
   std::map<std::string, Buf> dev_, pinned_;
+  unsigned long long generation_;
   int *d_err_;
 };
 

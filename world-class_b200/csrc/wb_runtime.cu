@@ -6,7 +6,7 @@
 #include <mutex>
 #include <vector>
 
-WbWorkspace::WbWorkspace() : d_err_(nullptr) {}
+WbWorkspace::WbWorkspace() : generation_(0), d_err_(nullptr) {}
 
 WbWorkspace::~WbWorkspace() {
   for (auto &kv : dev_) cudaFree(kv.second.p);
@@ -18,7 +18,7 @@ void *WbWorkspace::get(const std::string &name, size_t bytes) {
   if (bytes == 0) bytes = 8;
   auto it = dev_.find(name);
   if (it != dev_.end() && it->second.bytes >= bytes) return it->second.p;
-  if (it != dev_.end()) { cudaFree(it->second.p); dev_.erase(it); }
+  if (it != dev_.end()) { cudaFree(it->second.p); dev_.erase(it); ++generation_; }
   void *p = nullptr;
   const size_t grow = bytes + bytes / 8;  // a little slack so slowly growing inputs do not realloc every call
   if (cudaMalloc(&p, grow) != cudaSuccess) {
@@ -45,8 +45,16 @@ void *WbWorkspace::get_keep(const std::string &name, size_t bytes, size_t keep_b
     return nullptr;
   }
   cudaFree(it->second.p);
+  ++generation_;
   it->second = Buf{p, grow};
   return p;
+}
+
+void *WbWorkspace::find(const std::string &name, size_t *bytes_out) const {
+  auto it = dev_.find(name);
+  if (it == dev_.end()) { if (bytes_out) *bytes_out = 0; return nullptr; }
+  if (bytes_out) *bytes_out = it->second.bytes;
+  return it->second.p;
 }
 
 void *WbWorkspace::get_pinned(const std::string &name, size_t bytes) {

@@ -792,11 +792,11 @@ int wb_synthesis_render(WbWorkspace *ws, int fs, int fft_size, double frame_peri
   if ((1 << log2n) != fft_size || fft_size < 128 || fft_size > 8192) return WB_ERR_UNSUPPORTED;
   const double frame_period = frame_period_ms / 1000.;
   const int max_pulses = out_length / 4 + 16;
-  unsigned char *d_vuv = (unsigned char *)ws->get("syn_vuv", 0);
-  int *d_pidx = (int *)ws->get("syn_pidx", 0);
-  double *d_pshift = (double *)ws->get("syn_pshift", 0);
-  int *d_np = (int *)ws->get("syn_np", 0);
-  unsigned long long *d_ncount = (unsigned long long *)ws->get("syn_ncount", 0);
+  unsigned char *d_vuv = (unsigned char *)ws->find("syn_vuv");
+  int *d_pidx = (int *)ws->find("syn_pidx");
+  double *d_pshift = (double *)ws->find("syn_pshift");
+  int *d_np = (int *)ws->find("syn_np");
+  unsigned long long *d_ncount = (unsigned long long *)ws->find("syn_ncount");
   double *d_noise = (double *)ws->get("noise_syn", sizeof(double) * out_length);
   double *d_dcr = (double *)ws->get("syn_dcr", sizeof(double) * fft_size);
   if (!d_vuv || !d_pidx || !d_pshift || !d_np || !d_ncount || !d_noise || !d_dcr) return WB_ERR_CUDA;
@@ -898,9 +898,9 @@ int wb_synthesis_render_range(WbWorkspace *ws, int fs, int fft_size, double fram
                               int sample_begin, int sample_end, double *d_out, double f0_upper_bound,
                               const WbRngCursor &rng, cudaStream_t stream) {
   PulseList pl;
-  pl.vuv = (unsigned char *)ws->get("syn_vuv", 0); pl.pulse_vuv = nullptr;
-  pl.pidx = (int *)ws->get("syn_pidx", 0); pl.pshift = (double *)ws->get("syn_pshift", 0);
-  pl.np = (int *)ws->get("syn_np", 0); pl.ncount = (unsigned long long *)ws->get("syn_ncount", 0);
+  pl.vuv = (unsigned char *)ws->find("syn_vuv"); pl.pulse_vuv = nullptr;
+  pl.pidx = (int *)ws->find("syn_pidx"); pl.pshift = (double *)ws->find("syn_pshift");
+  pl.np = (int *)ws->find("syn_np"); pl.ncount = (unsigned long long *)ws->find("syn_ncount");
   if (!pl.vuv || !pl.pidx || !pl.pshift || !pl.np || !pl.ncount) return WB_ERR_CUDA;
   return render_range_core(ws, fs, fft_size, frame_period_ms, f0_length, d_sp, d_ap, row_begin, n_rows, out_length,
                            sample_begin, sample_end, d_out, f0_upper_bound, rng, stream, pl);
@@ -1029,7 +1029,7 @@ int synstream_timebase(WbSynStream *s, int n_tb, cudaStream_t stream) {
   const int m = n_new + off;
   const double frame_period = s->frame_period_ms / 1000.;
   const double lowest_f0 = s->fs / s->fft_size + 1.0;             // synthesis.cpp:97 (integer division)
-  double *d_f0 = (double *)ws->get("st_f0", 0);
+  double *d_f0 = (double *)ws->find("st_f0");
   double *d_incr = (double *)ws->get("st_incr", sizeof(double) * m);
   double *d_total = (double *)ws->get("st_total", sizeof(double) * m);
   unsigned char *d_vuv = (unsigned char *)ws->get("st_vuv", m);
@@ -1085,12 +1085,12 @@ int synstream_emit(WbSynStream *s, int out_new, int out_length_for_ola, double *
   double *d_out = (double *)ws->get("st_out", sizeof(double) * count);
   if (!d_out) return WB_ERR_CUDA;
   PulseList pl;
-  pl.vuv = nullptr; pl.pulse_vuv = (unsigned char *)ws->get("st_pvuv", 0);
-  pl.pidx = (int *)ws->get("st_pidx", 0); pl.pshift = (double *)ws->get("st_pshift", 0);
-  pl.np = (int *)ws->get("st_np", 0); pl.ncount = nullptr;
+  pl.vuv = nullptr; pl.pulse_vuv = (unsigned char *)ws->find("st_pvuv");
+  pl.pidx = (int *)ws->find("st_pidx"); pl.pshift = (double *)ws->find("st_pshift");
+  pl.np = (int *)ws->find("st_np"); pl.ncount = nullptr;
   WbRngCursor c;
   c.state = wb_rng_global_state(); c.advance = false;   // the state moves once, when the stream is finished
-  const double *d_sp = (const double *)ws->get("st_sp", 0), *d_ap = (const double *)ws->get("st_ap", 0);
+  const double *d_sp = (const double *)ws->find("st_sp"), *d_ap = (const double *)ws->find("st_ap");
   int rc = render_range_core(ws, s->fs, s->fft_size, s->frame_period_ms, s->frames, d_sp, d_ap, s->row_base,
                              s->frames - s->row_base, out_length_for_ola, s->out_done, out_new, d_out, s->f0_bound, c, stream, pl);
   if (rc) return rc;
@@ -1104,7 +1104,7 @@ int synstream_emit(WbSynStream *s, int out_new, int out_length_for_ola, double *
     const size_t kept = (size_t)(s->frames - keep_from) * bins;
     if (kept > 0) {
       double *tmp = (double *)ws->get("st_rows_tmp", sizeof(double) * kept);
-      double *sp = (double *)ws->get("st_sp", 0), *ap = (double *)ws->get("st_ap", 0);
+      double *sp = (double *)ws->find("st_sp"), *ap = (double *)ws->find("st_ap");
       if (!tmp) return WB_ERR_CUDA;
       const size_t shift = (size_t)(keep_from - s->row_base) * bins;
       WB_CUDA_CHECK(cudaMemcpyAsync(tmp, sp + shift, sizeof(double) * kept, cudaMemcpyDeviceToDevice, stream));
