@@ -34,6 +34,13 @@ METRIC = "frames/sec, full Harvest->CheapTrick->D4C->Synthesis @48kHz/5ms"
 WORKLOAD = "single 10 s utterance @48 kHz, 5 ms frame period, FFT size 2048 (BASELINE configs[1])"
 
 
+def bench_config(frames):
+    """The `config` object of the JSON line: identical in both arms (ours / --impl reference)."""
+    return {"workload": WORKLOAD, "frames_per_step_per_gpu": frames, "utterances_per_step_per_gpu": 1,
+            "parallelism": "one utterance per GPU, no data-path collective",
+            "l2": "256 MiB device memset between timed iterations (flush); inputs 3.8 MB"}
+
+
 def r2c_bytes(n):  # SURVEY.md 8d: fp64 input + output of one real transform
     return 8 * n + 16 * (n // 2 + 1)
 
@@ -114,7 +121,8 @@ def run_reference_arm(args):
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "x_realtime": SECONDS / (ms_per_step / 1e3),
-        "config": {"workload": WORKLOAD, "note": "reference OpenMP build (Makefile flags -O3 -mavx -fopenmp) of /root/reference, one utterance per step"},
+        "config": bench_config(res["frames"]),
+        "impl_note": "reference OpenMP build (Makefile flags -O3 -mavx -fopenmp) of /root/reference, one utterance per step, host cores only",
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": res["threads"], "kind": "reference",
                          "sample": "%d x one 10 s / 48 kHz utterance through refrun_omp (all host threads)" % args.steps},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -219,10 +227,14 @@ def main():
     synthesis = wb.Synthesis(FS, cheaptrick.fft_size, FRAME_PERIOD)
     x_np = x_pinned.numpy()
 
-    # caller-owned host outputs, allocated once like test/test.cpp:102-104,146-149,170-173
-    h_tpos, h_f0 = np.empty(L), np.empty(L)
-    h_sp, h_ap = np.empty((L, bins)), np.empty((L, bins))
-    h_y = np.empty(ny)
+    # caller-owned host buffers, allocated once like test/test.cpp:102-104,146-149,170-173 -- page-locked
+    # (torch pin_memory), each matrix one block: the library then DMAs straight from / into them
+    def pinned(*shape):
+        return torch.empty(shape, dtype=torch.float64).pin_memory().numpy()
+
+    h_tpos, h_f0 = pinned(L), pinned(L)
+    h_sp, h_ap = pinned(L, bins), pinned(L, bins)
+    h_y = pinned(ny)
 
     def step_e2e():
         harvest.compute(x_np, h_tpos, h_f0)
@@ -415,12 +427,10 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "x_realtime": world * SECONDS / (ms_per_step / 1e3),
-            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": L, "utterances_per_step_per_gpu": 1,
-                       "parallelism": "one utterance per GPU, no data-path collective",
-                       "l2": "256 MiB device memset between timed iterations (flush); inputs 3.8 MB"},
+            "config": bench_config(L),
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps, "x_realtime": world * SECONDS / (e2e_ms / args.steps / 1e3),
-                    "path": "Harvest/CheapTrick/D4C/Synthesis compute() with host buffers (pinned x, caller-owned pageable outputs), 4 calls per step"},
+                    "path": "Harvest/CheapTrick/D4C/Synthesis compute() with host buffers (caller-owned page-locked x, f0, sp, ap, y), 4 calls per step"},
             "gpu_launches": launches,
             "clocks": sampler.summary(),
             "roofline": roofline,

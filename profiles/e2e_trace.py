@@ -14,8 +14,11 @@ hopt = wb.HarvestOption(f0_floor=40.0, frame_period=5.0)
 hv, ct, d4 = wb.Harvest(fs, hopt), wb.CheapTrick(fs, wb.CheapTrickOption(f0_floor=71.0)), wb.D4C(fs, wb.D4COption(threshold=0.85))
 sy = wb.Synthesis(fs, ct.fft_size, 5.0)
 L = hv.getSamples(fs, len(x)); bins = ct.fft_size // 2 + 1; ny = len(x)
-tp, f0, sp, ap, y = np.empty(L), np.empty(L), np.empty((L, bins)), np.empty((L, bins)), np.empty(ny)
-for it in range(4):
+pin = lambda *shape: torch.empty(shape, dtype=torch.float64).pin_memory().numpy()
+if os.environ.get("PAGEABLE"):
+    pin = lambda *shape: np.empty(shape)
+tp, f0, sp, ap, y = pin(L), pin(L), pin(L, bins), pin(L, bins), pin(ny)
+for it in range(6):
     t = [time.perf_counter()]
     hv.compute(xp, tp, f0); t.append(time.perf_counter())
     ct.compute(xp, tp, f0, sp); t.append(time.perf_counter())

@@ -112,9 +112,16 @@ class CopyPool {
     int r0 = 0, n = 0, parts = 0;
     unsigned long long gen = 0;
   };
+  // Helper threads = this process's share of the host's cores (one process per GPU: LOCAL_WORLD_SIZE of them
+  // share the box; WB_COPY_THREADS overrides), minus the calling thread, at most 11.  Eight ranks with 11 spinning
+  // helpers each on a 32-core box were what collapsed the host API at N = 8 in round 1.
   CopyPool() {
     unsigned hc = std::thread::hardware_concurrency();
-    const int n = (int)std::max(1u, std::min(hc > 1 ? hc - 1 : 1u, 11u));
+    unsigned ranks = 1;
+    if (const char *e = getenv("LOCAL_WORLD_SIZE")) { const int v = atoi(e); if (v > 1) ranks = (unsigned)v; }
+    unsigned share = hc / ranks;
+    int n = (int)std::min(share > 1 ? share - 1 : 0u, 11u);
+    if (const char *e = getenv("WB_COPY_THREADS")) { const int v = atoi(e); if (v >= 1 && v <= 64) n = v - 1; }
     for (int i = 0; i < n; ++i) workers_.emplace_back([this]() { worker(); });
   }
   ~CopyPool() {
@@ -145,10 +152,10 @@ class CopyPool {
   void worker() {
     unsigned long long seen = 0;
     for (;;) {
-      // spin for a while, then sleep
+      // a short spin (the chunks of one matrix follow each other within microseconds), then sleep
       bool got = false;
       const auto t0 = std::chrono::steady_clock::now();
-      while (std::chrono::steady_clock::now() - t0 < std::chrono::microseconds(300)) {
+      while (std::chrono::steady_clock::now() - t0 < std::chrono::microseconds(40)) {
         if (generation_.load(std::memory_order_acquire) != seen) { got = true; break; }
       }
       Job job;
@@ -177,9 +184,38 @@ void parallel_rows(int r0, int r1, F f) {
   CopyPool::get().parallel_for(r0, r1, [&](int b, int e) { for (int i = b; i < e; ++i) f(i); });
 }
 
+// The reference's callers allocate every row separately (test/test.cpp:146-149), but a matrix handed over as
+// row pointers into ONE block (numpy / torch / a C++ arena) is just as common.  If the rows are contiguous AND the
+// block is page-locked (cudaHostAlloc / cudaHostRegister by its owner, torch pin_memory()), the DMA engine reads /
+// writes the caller's memory directly: no bounce buffer, no host memcpy, no helper threads.
+template <typename P>
+bool rows_contiguous(P rows, int n_rows, int cols) {
+  for (int i = 1; i < n_rows; ++i)
+    if (rows[i] != rows[i - 1] + cols) return false;
+  return n_rows > 0;
+}
+bool host_range_pinned(const void *ptr, size_t bytes) {
+  if (!ptr || bytes == 0) return false;
+  cudaPointerAttributes a0, a1;
+  if (cudaPointerGetAttributes(&a0, ptr) != cudaSuccess || cudaPointerGetAttributes(&a1, (const char *)ptr + bytes - 1) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a0.type == cudaMemoryTypeHost && a1.type == cudaMemoryTypeHost;
+}
+template <typename P>
+bool rows_direct(P rows, int n_rows, int cols) {
+  return rows_contiguous(rows, n_rows, cols) && host_range_pinned(rows[0], sizeof(double) * (size_t)n_rows * cols);
+}
+
 // copy a contiguous [rows][cols] device matrix into separately allocated host rows
 int rows_to_host(WbWorkspace *ws, const double *d_src, int rows, int cols, double **dst, cudaStream_t st) {
   const size_t bytes = sizeof(double) * (size_t)rows * cols;
+  if (rows_direct(dst, rows, cols)) {
+    WB_CUDA_CHECK(cudaMemcpyAsync(dst[0], d_src, bytes, cudaMemcpyDeviceToHost, st));
+    WB_CUDA_CHECK(cudaStreamSynchronize(st));
+    return WB_OK;
+  }
   double *stage = (double *)ws->get_pinned("rows_stage", bytes);
   if (!stage) return WB_ERR_CUDA;
   cudaEvent_t ev[kRowChunks];
@@ -204,6 +240,10 @@ int rows_to_host(WbWorkspace *ws, const double *d_src, int rows, int cols, doubl
 int rows_to_device(WbWorkspace *ws, const char *name, const double *const *src, int rows, int cols,
                    double *d_dst, cudaStream_t st) {
   const size_t bytes = sizeof(double) * (size_t)rows * cols;
+  if (rows_direct(src, rows, cols)) {
+    WB_CUDA_CHECK(cudaMemcpyAsync(d_dst, src[0], bytes, cudaMemcpyHostToDevice, st));
+    return WB_OK;
+  }
   double *stage = (double *)ws->get_pinned(name, bytes);
   if (!stage) return WB_ERR_CUDA;
   for (int c = 0; c < kRowChunks; ++c) {
@@ -252,6 +292,16 @@ struct RowPipeline {
   // download range c as soon as ev[c] fires, scatter it to the caller's rows while the next ranges compute
   int download(WbWorkspace *ws, const WbRowChunks &ch, const double *d_src, int cols, double **dst) {
     const int rows = ch.bounds[ch.n];
+    if (rows_direct(dst, rows, cols)) {
+      // straight into the caller's page-locked block, range by range as the frame kernels finish
+      for (int c = 0; c < ch.n; ++c) {
+        const size_t off = (size_t)ch.bounds[c] * cols, cnt = (size_t)(ch.bounds[c + 1] - ch.bounds[c]) * cols;
+        WB_CUDA_CHECK(cudaStreamWaitEvent(copy, ch.ev[c], 0));
+        if (cnt) WB_CUDA_CHECK(cudaMemcpyAsync(dst[0] + off, d_src + off, sizeof(double) * cnt, cudaMemcpyDeviceToHost, copy));
+      }
+      WB_CUDA_CHECK(cudaStreamSynchronize(copy));
+      return WB_OK;
+    }
     double *stage = (double *)ws->get_pinned("rows_stage", sizeof(double) * (size_t)rows * cols);
     if (!stage) return WB_ERR_CUDA;
     for (int c = 0; c < ch.n; ++c) {
