@@ -139,6 +139,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="headline line only (development)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -335,9 +336,14 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        traffic = None
+        traffic, traffic_stale = None, None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dom)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            traffic = tj.get(dom)
+            sys.path.insert(0, os.path.join(ROOT, "profiles"))
+            from summarize import csrc_sha1
+            # the ncu capture the figure comes from was made on other kernel sources than the ones timed here
+            traffic_stale = tj.get("_csrc_sha1_by_kernel", {}).get(dom) != csrc_sha1()
         except Exception:
             pass
         if dom is not None:
@@ -346,7 +352,7 @@ def main():
             a_bytes = alg.get(dom)
             achieved = (a_bytes / (avg_ms / 1e3) / 1e9) if a_bytes else None
             roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                        "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                        "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_stale": traffic_stale,
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                         "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": a_bytes,
                         "kernel_share_of_step": tot_ms / max(sum(v[0] for v in kernel_table.values()), 1e-9),
@@ -363,52 +369,145 @@ def main():
                     "algorithmic_gflop_per_step": f_all / 1e9,
                     "model": "butterflies of the transforms the ALGORITHM executes: 2.5 N log2 N per real, 5 N log2 N per complex transform (SURVEY.md 8d)"}
 
-    # ---- extra (not the headline): BASELINE configs[2]-style batch, independent 22.05 kHz / 5 s utterances on
-    # concurrent streams of this GPU (each utterance == one reference process)
+    # ---- extra (not the headline): BASELINE configs[2] -- 256 independent 22.05 kHz / 5 s utterances on this GPU
+    # (each utterance == one reference process; 32 distinct signals, each used eight times: the generator costs
+    # 0.35 s of host time per utterance)
     batch_extra = None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not args.no_extras:
         try:
-            n_utt, bfs, bsec = 32, 22050, 5.0
-            bxs = [torch.from_numpy(signals.synth_speech(bfs, bsec, seed=1000 + i)).cuda() for i in range(n_utt)]
-            bp = wb.BatchPipeline(bfs, n_streams=8, harvest_option=wb.HarvestOption(f0_floor=40.0, frame_period=FRAME_PERIOD),
+            n_utt, n_distinct, bfs, bsec, n_streams, reps = 256, 32, 22050, 5.0, 16, 6
+            distinct = [torch.from_numpy(signals.synth_speech(bfs, bsec, seed=1000 + i)).cuda() for i in range(n_distinct)]
+            bxs = [distinct[i % n_distinct] for i in range(n_utt)]
+            bp = wb.BatchPipeline(bfs, n_streams=n_streams, harvest_option=wb.HarvestOption(f0_floor=40.0, frame_period=FRAME_PERIOD),
                                   cheaptrick_option=copt, d4c_option=dopt)
             for _ in range(2):
-                bp.run(bxs)
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            reps = 3
-            for _ in range(reps):
                 outs = bp.run(bxs)
-            e1.record()
             torch.cuda.synchronize()
-            bms = e0.elapsed_time(e1) / reps
             frames = sum(int(o["f0"].numel()) for o in outs)
-            batch_extra = {"workload": "%d x %.0f s utterances @%d Hz, 8 concurrent streams, 1 GPU" % (n_utt, bsec, bfs),
-                           "ms_per_batch": bms, "frames_per_s": frames / (bms / 1e3), "x_realtime": n_utt * bsec / (bms / 1e3)}
-            del bp, bxs, outs
+            del outs
+            bms = []
+            for _ in range(reps):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                outs = bp.run(bxs)
+                e1.record()
+                torch.cuda.synchronize()
+                bms.append(e0.elapsed_time(e1))
+                del outs
+            med = float(np.median(bms))
+            batch_extra = {"workload": "%d x %.0f s utterances @%d Hz (%d distinct signals), %d concurrent pipelines, graph replay, results copied out, 1 GPU"
+                                       % (n_utt, bsec, bfs, n_distinct, n_streams),
+                           "ms_per_batch": med, "ms_per_batch_all": [round(v, 3) for v in bms],
+                           "spread": (max(bms) - min(bms)) / med, "frames_per_s": frames / (med / 1e3),
+                           "x_realtime": n_utt * bsec / (med / 1e3)}
+            del bp, bxs, distinct
         except Exception as exc:  # the headline line must not depend on the extra
             batch_extra = {"error": repr(exc)}
 
-    # ---- extra (not the headline): BASELINE configs[3]-shaped work at N = 1 -- one continuous 60 s stream through the
-    # exact sharding path (two shards on this GPU; the N = 2 / 4 / 8 runs over NCCL are profiles/stream_*.json)
-    stream_extra = None
-    if rank == 0 and world == 1:
+    # ---- extra (not the headline): BASELINE configs[4] -- codec round trip (codec.cpp:216-325) of 1024 frames at
+    # 48 kHz / fft 2048, 60 mel-cepstral dimensions, device resident; HBM roofline with SURVEY 8d's bytes per frame
+    codec_extra = None
+    if rank == 0 and world == 1 and not args.no_extras:
         try:
-            from worldb200 import parallel
-            sx = torch.from_numpy(np.tile(x_host, 6)).cuda()          # 6 x the 10 s utterance
-            keep, best = {}, None
-            for rep in range(3):
-                t = {}
-                so = parallel.process_stream_exact(sx, FS, hopt, copt, dopt, segment_seconds=30, halo_seconds=2, shards_per_rank=2,
-                                                   keep_rows=False, timings=t, state=keep)
-                if rep > 0:
-                    best = t["total"] if best is None else min(best, t["total"])
-            stream_extra = {"workload": "one continuous 60 s stream @%d Hz, exact sharding path, 2 shards on 1 GPU" % FS,
-                            "ms": best, "frames_per_s": so["plan"].f0_length / (best / 1e3), "x_realtime": 60.0 / (best / 1e3),
-                            "multi_gpu": "profiles/stream_3600s_n{1,2,4,8}.json (one hour, strong scaling over NCCL)"}
-            del sx, so, keep
-        except Exception as exc:  # the headline line must not depend on the extra
+            from worldb200 import tensors as wt
+            n_ap_c = wb.lib().wb_get_number_of_aperiodicities(FS)
+            res = {}
+            for n_fr in (1024, 65536):
+                g = torch.Generator(device="cuda").manual_seed(5)
+                sp_c = torch.exp(torch.rand((n_fr, bins), dtype=torch.float64, device="cuda", generator=g) * 18.0 - 16.0)  # log-uniform
+                ap_c = torch.rand((n_fr, bins), dtype=torch.float64, device="cuda", generator=g) * 0.998 + 0.001
+
+                def round_trip():
+                    with torch.cuda.stream(lib_stream):
+                        c_sp = wt.codec("code_sp", sp_c, FS, fft_size, 60)
+                        d_sp_c = wt.codec("decode_sp", c_sp, FS, fft_size, 60)
+                        c_ap = wt.codec("code_ap", ap_c, FS, fft_size)
+                        d_ap_c = wt.codec("decode_ap", c_ap, FS, fft_size)
+                    return d_sp_c, d_ap_c
+
+                for _ in range(3):
+                    round_trip()
+                torch.cuda.synchronize()
+                reps = 20 if n_fr <= 4096 else 5
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(lib_stream)
+                for _ in range(reps):
+                    round_trip()
+                e1.record(lib_stream)
+                torch.cuda.synchronize()
+                cms = e0.elapsed_time(e1) / reps
+                bytes_per_frame = 2 * (2 * 8 * bins + 8 * (60 + n_ap_c))
+                gbs = n_fr * bytes_per_frame / (cms / 1e3) / 1e9
+                peak_c = 6538.0
+                try:
+                    peak_c = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6538.0))
+                except Exception:
+                    pass
+                res[str(n_fr)] = {"ms_per_round_trip": cms, "frames_per_s": n_fr / (cms / 1e3), "algorithmic_GB_per_s": gbs,
+                                  "roofline_frac_hbm": gbs / peak_c}
+                del sp_c, ap_c
+            codec_extra = {"workload": "CodeSpectralEnvelope -> Decode -> CodeAperiodicity -> Decode, 1025 bins, 60 dimensions, %d band aperiodicities; 1024 frames (configs[4]) and 65536 frames (bandwidth regime)" % n_ap_c,
+                           "bytes_per_frame": 2 * (2 * 8 * bins + 8 * (60 + n_ap_c)), "by_frames": res}
+        except Exception as exc:
+            codec_extra = {"error": repr(exc)}
+
+    # ---- extra (not the headline): BASELINE configs[3] -- one continuous 48 kHz stream, frames sharded over ALL
+    # ranks (strong scaling: the same 600 s at every N) with the exact exchange steps of worldb200/parallel.py; plus a
+    # 30 s stream through the same sharded path checked against ONE reference process on rank 0
+    stream_extra = None
+    try:
+        if args.no_extras:
+            raise RuntimeError("skipped (--no-extras)")
+        import hashlib
+        from worldb200 import parallel
+        from oracle import refbin
+        total_shards = 16
+        k_shards = max(1, total_shards // world)
+        s_seconds = 600
+        block = signals.synth_speech(FS, 60.0, seed=0)
+        sx = torch.from_numpy(np.tile(block, s_seconds // 60)).cuda()
+        keep, best, best_t = {}, None, None
+        for rep in range(3):               # first repetition = warm-up (allocations, plan tables)
+            barrier()
+            t = {}
+            so = parallel.process_stream_exact(sx, FS, hopt, copt, dopt, segment_seconds=30, halo_seconds=2,
+                                               shards_per_rank=k_shards, keep_rows=False, timings=t, state=keep)
+            tot = torch.tensor([t["total"]], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+            if rep > 0 and (best is None or float(tot.item()) < best):
+                best, best_t = float(tot.item()), dict(t)
+        sha_f0 = hashlib.sha1(so["f0"].cpu().numpy().tobytes()).hexdigest()
+        sha_y = hashlib.sha1(so["y"].cpu().numpy().tobytes()).hexdigest()
+        s_frames = so["plan"].f0_length
+        del sx, so, keep
+        # parity of the sharded path: 30 s through all ranks vs one reference process (serial build: its waveform is
+        # reproducible, the OpenMP build's is not)
+        cx = block[:30 * FS].copy()
+        co = parallel.process_stream_exact(torch.from_numpy(cx).cuda(), FS, hopt, copt, dopt, segment_seconds=5, halo_seconds=2,
+                                           shards_per_rank=max(1, 6 // world), keep_rows=True)
+        check = None
+        if rank == 0 and refbin.available():
+            ref, _ = refbin.run_reference(cx, FS, stages="hcds")
+            f0c, yc = co["f0"].cpu().numpy(), co["y"].cpu().numpy()
+            v = ref["f0"] > 0
+            fb_c, fe_c = co["frames"]
+            check = {"seconds": 30, "voicing_identical": bool(np.array_equal(f0c > 0, v)),
+                     "f0_rel": float(np.max(np.abs(f0c[v] - ref["f0"][v]) / ref["f0"][v])),
+                     "sp_rel_rank0_rows": float(np.max(np.abs(co["sp"].cpu().numpy() - ref["sp"][fb_c:fe_c]) / ref["sp"][fb_c:fe_c])),
+                     "ap_rel_rank0_rows": float(np.max(np.abs(co["ap"].cpu().numpy() - ref["ap"][fb_c:fe_c]) / ref["ap"][fb_c:fe_c])),
+                     "y_over_peak": float(np.max(np.abs(yc - ref["y"])) / np.abs(ref["y"]).max())}
+        del co
+        if rank == 0:
+            exposed = sum(best_t.get(k2, 0.0) for k2 in ("gather_f0", "wait_ap0", "stitch_tail"))
+            stream_extra = {"workload": "one continuous %d s stream @%d Hz, exact sharding over %d GPU(s), %d shards per rank (strong scaling: same stream at every N)"
+                                        % (s_seconds, FS, world, k_shards),
+                            "n_gpus": world, "ms": best, "frames_per_s": s_frames / (best / 1e3), "x_realtime": s_seconds / (best / 1e3),
+                            "phases_ms_rank0": {k2: round(v2, 3) for k2, v2 in best_t.items()},
+                            "exposed_collective_ms_rank0": exposed, "exposed_collective_frac": exposed / best_t["total"],
+                            "sha1_f0": sha_f0, "sha1_y": sha_y, "check_vs_reference": check}
+    except Exception as exc:  # the headline line must not depend on the extra
+        if rank == 0:
             stream_extra = {"error": repr(exc)}
 
     # ---- CPU baseline: the reference's OpenMP build on this host, bounded sample
@@ -439,6 +538,7 @@ def main():
             "wall_s_timed_region": t_wall,
             "batch_config3_extra": batch_extra,
             "stream_config4_extra": stream_extra,
+            "codec_config5_extra": codec_extra,
         }
         print(json.dumps(line))
     if world > 1:

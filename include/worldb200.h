@@ -226,6 +226,11 @@ int wb_pipeline_stream_begin_dev(wb_pipeline_t *p, const double *d_f0_all, int f
 int wb_pipeline_stream_envelope_dev(wb_pipeline_t *p, const double *d_x, int x_length, const double *d_f0_all,
                                     int f0_length, int frame_begin, int frame_end, double *d_sp_rows,
                                     double *d_ap0_all, void *stream);
+/* the envelope call in two halves: Love Train first (so that the exchange of its decisions overlaps CheapTrick) */
+int wb_pipeline_stream_lovetrain_dev(wb_pipeline_t *p, const double *d_x, int x_length, const double *d_f0_all,
+                                     int f0_length, int frame_begin, int frame_end, double *d_ap0_all, void *stream);
+int wb_pipeline_stream_cheaptrick_dev(wb_pipeline_t *p, const double *d_x, int x_length, const double *d_f0_all,
+                                      int f0_length, int frame_begin, int frame_end, double *d_sp_rows, void *stream);
 int wb_pipeline_stream_aperiodicity_dev(wb_pipeline_t *p, const double *d_x, int x_length, const double *d_f0_all,
                                         const double *d_ap0_all, int f0_length, int frame_begin, int frame_end,
                                         double *d_ap_rows, void *stream);

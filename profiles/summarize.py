@@ -32,6 +32,17 @@ METRICS = [
 ]
 
 
+def csrc_sha1():
+    """SHA-1 over the kernel sources (world-class_b200/csrc, sorted by name)"""
+    import hashlib
+    d = os.path.join(HERE, "..", "world-class_b200", "csrc")
+    h = hashlib.sha1()
+    for name in sorted(os.listdir(d)):
+        h.update(name.encode())
+        h.update(open(os.path.join(d, name), "rb").read())
+    return h.hexdigest()
+
+
 def main():
     rep, tag = sys.argv[1], sys.argv[2]
     if rep.endswith(".csv"):   # a `--page raw --csv` export made on the GPU box (profiles/capture.sh)
@@ -71,8 +82,21 @@ def main():
         w.writerow(cols)
         for rec in out_rows:
             w.writerow([rec.get(c, "") if not isinstance(rec.get(c), float) else "%.4g" % rec[c] for c in cols])
-    with open(os.path.join(HERE, "ncu_traffic.json"), "w") as f:
-        json.dump({k: max(v) for k, v in traffic.items()}, f, indent=1, sort_keys=True)
+    # merged into the existing file (a capture usually covers a few kernels), stamped with a hash of the kernel
+    # sources: bench.py reports `traffic_stale` when the sources have changed since
+    path = os.path.join(HERE, "ncu_traffic.json")
+    merged = {}
+    if os.path.exists(path):
+        try:
+            merged = json.load(open(path))
+        except Exception:
+            merged = {}
+    stamp = csrc_sha1()
+    for k, v in traffic.items():
+        merged[k] = max(v)
+        merged.setdefault("_csrc_sha1_by_kernel", {})[k] = stamp
+    with open(path, "w") as f:
+        json.dump(merged, f, indent=1, sort_keys=True)
     for rec in out_rows:
         print(" | ".join("%s" % (("%.4g" % rec[c]) if isinstance(rec.get(c), float) else rec.get(c, "")) for c in cols))
 

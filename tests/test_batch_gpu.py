@@ -10,8 +10,11 @@ pytestmark = pytest.mark.gpu
 
 
 def test_batch_of_utterances_matches_reference(wb, signals):
-    fs, seconds, n_utt = 22050, 5.0, 6
-    xs = [signals.synth_speech(fs, seconds, seed=1000 + i) for i in range(n_utt)]   # SURVEY 8d seeds
+    # nine utterances on three pipelines: each pipeline sees a first run (ordinary launches), the run that captures
+    # its CUDA graph and a replay; one utterance of another length in between (ragged batch: its own buffers, a
+    # new capture afterwards)
+    fs, seconds, n_utt = 22050, 5.0, 9
+    xs = [signals.synth_speech(fs, 3.0 if i == 4 else seconds, seed=1000 + i) for i in range(n_utt)]   # SURVEY 8d seeds
     bp = wb.BatchPipeline(fs, n_streams=3, harvest_option=wb.HarvestOption(f0_floor=40.0, frame_period=5.0),
                           cheaptrick_option=wb.CheapTrickOption(f0_floor=71.0), d4c_option=wb.D4COption(threshold=0.85))
     outs = bp.run([torch.from_numpy(x).cuda() for x in xs])

@@ -132,7 +132,13 @@ def _gather_worker(rank, world, port, q):
     b, e = ranges[rank]
     full = torch.arange(13, dtype=torch.float64) * 1.5 + 0.25
     got = P.gather_ranges(full[b:e].clone(), ranges, 13)
-    q.put((rank, bool(torch.equal(got, full))))
+    # the same exchange in flight (the stream path issues it, enqueues other work, and collects it later), two at once
+    pg1 = P.PendingGather(full[b:e].clone(), ranges)
+    pg2 = P.PendingGather(-full[b:e].clone(), ranges)
+    out2 = torch.zeros(13, dtype=torch.float64)
+    pg2.finish_into(out2)
+    got1 = pg1.finish(13)
+    q.put((rank, bool(torch.equal(got, full) and torch.equal(got1, full) and torch.equal(out2, -full))))
     dist.destroy_process_group()
 
 

@@ -112,6 +112,8 @@ def _declare(L):
         "wb_pipeline_debug_read": (ci, [vp, ctypes.c_char_p, vp, ctypes.c_ulonglong]),
         "wb_pipeline_stream_begin_dev": (ci, [vp, vp, ci, ci, vp]),
         "wb_pipeline_stream_envelope_dev": (ci, [vp, vp, ci, vp, ci, ci, ci, vp, vp, vp]),
+        "wb_pipeline_stream_lovetrain_dev": (ci, [vp, vp, ci, vp, ci, ci, ci, vp, vp]),
+        "wb_pipeline_stream_cheaptrick_dev": (ci, [vp, vp, ci, vp, ci, ci, ci, vp, vp]),
         "wb_pipeline_stream_aperiodicity_dev": (ci, [vp, vp, ci, vp, vp, ci, ci, ci, vp, vp]),
         "wb_pipeline_stream_synthesis_dev": (ci, [vp, ci, vp, vp, ci, ci, ci, ci, ci, vp, vp]),
         "wb_pipeline_stream_end_dev": (ci, [vp, vp]),
@@ -679,7 +681,12 @@ class BatchPipeline:
 
     Each utterance is processed exactly like one reference process (fresh randn() stream).  Inputs and
     outputs are torch CUDA tensors; utterance i runs on stream i % n_streams, so the small,
-    latency-bound kernels of one utterance overlap with the wide kernels of the others."""
+    latency-bound kernels of one utterance overlap with the wide kernels of the others.
+
+    A pipeline keeps persistent input / output buffers per utterance length, so that every utterance of a
+    length it has seen before is ONE replay of the captured CUDA graph of the whole chain (~50 kernels) between a
+    device copy of the waveform in and device copies of the results out: the batch is bound by the GPU, not by
+    the host's launch rate."""
 
     def __init__(self, fs, n_streams=8, harvest_option=None, cheaptrick_option=None, d4c_option=None):
         import torch
@@ -687,28 +694,46 @@ class BatchPipeline:
         self.pipes = [Pipeline(fs, harvest_option, cheaptrick_option, d4c_option) for _ in range(n_streams)]
         for p in self.pipes:
             p.set_fresh_rng(True)
+            p.set_graph(True)
         self.streams = [torch.cuda.Stream() for _ in range(n_streams)]
         self.fft_size = self.pipes[0].fft_size
+        self._bufs = [dict() for _ in range(n_streams)]   # per pipeline: utterance length -> persistent tensors
 
-    def run(self, xs):
-        """xs: list of 1-D float64 CUDA tensors -> list of dict(f0, sp, ap, y) of CUDA tensors."""
+    def _slot(self, k, n, device):
+        torch = self._torch
+        b = self._bufs[k].get(n)
+        if b is None:
+            pl = self.pipes[k]
+            L, ny, bins = pl.f0_length(n), pl.out_length(n), self.fft_size // 2 + 1
+            f = dict(dtype=torch.float64, device=device)
+            b = {"x": torch.empty(n, **f), "tpos": torch.empty(L, **f), "f0": torch.empty(L, **f),
+                 "sp": torch.empty((L, bins), **f), "ap": torch.empty((L, bins), **f), "y": torch.empty(ny, **f)}
+            self._bufs[k][n] = b
+        return b
+
+    def run(self, xs, copy_out=True):
+        """xs: list of 1-D float64 CUDA tensors -> list of dict(tpos, f0, sp, ap, y) of CUDA tensors.
+        copy_out=False returns views of the pipelines' persistent buffers instead of copies: they are only valid
+        until the same pipeline processes its next utterance (for consumers that reduce the results on the fly)."""
         torch = self._torch
         outs = []
         cur = torch.cuda.current_stream()
-        for i, x in enumerate(xs):
-            pl, st = self.pipes[i % len(self.pipes)], self.streams[i % len(self.streams)]
-            n = x.numel()
-            L, ny, bins = pl.f0_length(n), pl.out_length(n), self.fft_size // 2 + 1
-            o = {"tpos": torch.empty(L, dtype=torch.float64, device=x.device),
-                 "f0": torch.empty(L, dtype=torch.float64, device=x.device),
-                 "sp": torch.empty((L, bins), dtype=torch.float64, device=x.device),
-                 "ap": torch.empty((L, bins), dtype=torch.float64, device=x.device),
-                 "y": torch.empty(ny, dtype=torch.float64, device=x.device)}
+        for st in self.streams:
             st.wait_stream(cur)
-            pl.run_dev(x.data_ptr(), n, d_y=o["y"].data_ptr(), y_length=ny, stream=st.cuda_stream,
-                       d_tpos=o["tpos"].data_ptr(), d_f0=o["f0"].data_ptr(), d_sp=o["sp"].data_ptr(),
-                       d_ap=o["ap"].data_ptr())
-            outs.append(o)
+        for i, x in enumerate(xs):
+            k = i % len(self.pipes)
+            pl, st = self.pipes[k], self.streams[k]
+            n = x.numel()
+            b = self._slot(k, n, x.device)
+            with torch.cuda.stream(st):
+                b["x"].copy_(x, non_blocking=True)
+                pl.run_dev(b["x"].data_ptr(), n, d_y=b["y"].data_ptr(), y_length=b["y"].numel(), stream=st.cuda_stream,
+                           d_tpos=b["tpos"].data_ptr(), d_f0=b["f0"].data_ptr(), d_sp=b["sp"].data_ptr(),
+                           d_ap=b["ap"].data_ptr())
+                if copy_out:
+                    outs.append({key: b[key].clone() for key in ("tpos", "f0", "sp", "ap", "y")})
+                else:
+                    outs.append({key: b[key] for key in ("tpos", "f0", "sp", "ap", "y")})
         for st in self.streams:
             cur.wait_stream(st)
         return outs

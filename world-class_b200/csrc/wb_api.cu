@@ -1088,6 +1088,49 @@ int wb_pipeline_stream_envelope_dev(wb_pipeline_t *p, const double *d_x, int x_l
                     c_lt, stream, nullptr, &range, 1, d_ap0_all);
 }
 
+// The two halves of the envelope call, for callers that want the Love Train decisions (8 bytes per frame, but
+// the all-gather that distributes them waits for the slowest rank) on their way BEFORE the longer CheapTrick
+// work starts: Love Train only needs CheapTrick's draw COUNT for its position in the randn() stream.
+int wb_pipeline_stream_lovetrain_dev(wb_pipeline_t *p, const double *d_x, int x_length, const double *d_f0_all,
+                                     int f0_length, int frame_begin, int frame_end, double *d_ap0_all, void *stream_) {
+  if (!p || !d_x || !d_f0_all || !d_ap0_all || x_length <= 0) return WB_ERR_ARG;
+  cudaStream_t stream = pick_stream(stream_);
+  double *d_tpos = (double *)p->ws.find("st_tpos");
+  unsigned long long *rng_pos = (unsigned long long *)p->ws.find("pl_rng_pos");
+  if (!d_tpos || !rng_pos || f0_length != p->stream_f0_length) return WB_ERR_ARG;   // begin has not been called (with this length)
+  if (frame_begin < 0 || frame_end > f0_length || frame_begin > frame_end) return WB_ERR_ARG;
+  WbRngState *rng = p->private_rng ? p->d_rng_private : wb_rng_global_state();
+  // CheapTrick's count of the whole stream -> rng_pos[0] (an empty row range: bookkeeping only)
+  const WbFrameRange none = {frame_begin, frame_begin};
+  WbRngCursor c_ct;
+  c_ct.state = rng; c_ct.skip_out = rng_pos + 0; c_ct.advance = false;
+  int rc;
+  if ((rc = wb_cheaptrick_run(&p->ws, p->fs, p->ct.fft_size, p->ct.q1, p->ct_f0_floor_internal, d_x, x_length, d_tpos,
+                              d_f0_all, f0_length, nullptr, c_ct, stream, nullptr, &none)))
+    return rc;
+  const WbFrameRange range = {frame_begin, frame_end};
+  WbRngCursor c_lt;
+  c_lt.state = rng; c_lt.skip_in = rng_pos + 0; c_lt.advance = false;
+  return wb_d4c_run(&p->ws, p->fs, p->d4c.threshold, d_x, x_length, d_tpos, d_f0_all, f0_length, p->ct.fft_size, nullptr,
+                    c_lt, stream, nullptr, &range, 1, d_ap0_all);
+}
+
+int wb_pipeline_stream_cheaptrick_dev(wb_pipeline_t *p, const double *d_x, int x_length, const double *d_f0_all,
+                                      int f0_length, int frame_begin, int frame_end, double *d_sp_rows, void *stream_) {
+  if (!p || !d_x || !d_f0_all || !d_sp_rows || x_length <= 0) return WB_ERR_ARG;
+  cudaStream_t stream = pick_stream(stream_);
+  double *d_tpos = (double *)p->ws.find("st_tpos");
+  unsigned long long *rng_pos = (unsigned long long *)p->ws.find("pl_rng_pos");
+  if (!d_tpos || !rng_pos || f0_length != p->stream_f0_length) return WB_ERR_ARG;
+  if (frame_begin < 0 || frame_end > f0_length || frame_begin > frame_end) return WB_ERR_ARG;
+  WbRngState *rng = p->private_rng ? p->d_rng_private : wb_rng_global_state();
+  const WbFrameRange range = {frame_begin, frame_end};
+  WbRngCursor c_ct;
+  c_ct.state = rng; c_ct.skip_out = rng_pos + 0; c_ct.advance = false;
+  return wb_cheaptrick_run(&p->ws, p->fs, p->ct.fft_size, p->ct.q1, p->ct_f0_floor_internal, d_x, x_length, d_tpos,
+                           d_f0_all, f0_length, d_sp_rows, c_ct, stream, nullptr, &range);
+}
+
 int wb_pipeline_stream_aperiodicity_dev(wb_pipeline_t *p, const double *d_x, int x_length, const double *d_f0_all,
                                         const double *d_ap0_all, int f0_length, int frame_begin, int frame_end,
                                         double *d_ap_rows, void *stream_) {

@@ -181,7 +181,7 @@ int wb_cheaptrick_run(WbWorkspace *ws, int fs, int fft_size, double q1, double f
   p.x = d_x; p.x_length = x_length; p.tpos = d_tpos; p.f0 = d_f0; p.f0_length = f0_length;
   p.fs = fs; p.fft_size = fft_size; p.log2nc = log2n - 1; p.q1 = q1; p.f0_floor = f0_floor_internal;
   p.twiddle = tw; p.noise = d_noise; p.noise_off = d_noise_off;
-  p.sp = range ? d_sp - (size_t)range->begin * bins : d_sp;   // (rows are addressed by absolute frame)
+  p.sp = (range && d_sp) ? d_sp - (size_t)range->begin * bins : d_sp;   // (rows are addressed by absolute frame)
   p.seg_capacity = fft_size / 2 + fft_size / 4 + 8;
   p.error_flag = ws->error_flag();
   const size_t smem = wb_cheaptrick_smem_bytes(fft_size, p.seg_capacity);

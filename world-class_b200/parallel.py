@@ -210,6 +210,46 @@ def gather_ranges(local, ranges, total, group=None, device=None):
     return out
 
 
+class PendingGather:
+    """An all-gather of per-rank contiguous pieces in flight (NCCL: on the communicator's stream, beside whatever
+    the caller enqueues next on the library's stream).  finish() / finish_into() wait for it and place the
+    pieces."""
+
+    def __init__(self, local, ranges, group=None):
+        import torch
+        import torch.distributed as dist
+        self.ranges, self.local, self.handle, self.gathered = ranges, local, None, None
+        world = len(ranges)
+        if world == 1 or not (dist.is_available() and dist.is_initialized()):
+            assert len(local) == ranges[0][1] - ranges[0][0]
+            return
+        rank = dist.get_rank(group)
+        assert ranges[rank][1] - ranges[rank][0] == len(local)
+        width = max(e - b for b, e in ranges)
+        mine = torch.zeros(width, dtype=local.dtype, device=local.device)
+        mine[:len(local)] = local
+        self.gathered = torch.empty((world, width), dtype=local.dtype, device=local.device)
+        if dist.get_backend(group) == "nccl":
+            self.handle = dist.all_gather_into_tensor(self.gathered.view(-1), mine, group=group, async_op=True)
+        else:
+            self.handle = dist.all_gather([self.gathered[k] for k in range(world)], mine, group=group, async_op=True)
+        self._mine = mine   # keep alive until the collective is done
+
+    def finish_into(self, out):
+        if self.gathered is None:
+            b, e = self.ranges[0]
+            out[b:e] = self.local
+            return out
+        self.handle.wait()
+        for k, (b, e) in enumerate(self.ranges):
+            out[b:e] = self.gathered[k, :e - b]
+        return out
+
+    def finish(self, total):
+        import torch
+        return self.finish_into(torch.empty(total, dtype=self.local.dtype, device=self.local.device))
+
+
 class StreamWorker:
     """One shard of an exactly sharded stream on this process's GPU (torch CUDA tensors, C-ABI calls).  A rank
     that owns several shards (bounded memory per step) shares one pipeline / Harvest object between them."""
@@ -266,6 +306,27 @@ class StreamWorker:
                                                                      self.plan.f0_length, ra, rb, self.d_sp.data_ptr(),
                                                                      d_ap0_all.data_ptr(), None), "wb_pipeline_stream_envelope_dev")
         self.wb.device_synchronize()
+
+    def lovetrain(self, d_x, d_ap0_all):
+        """first half of envelope(): Love Train for the rows this shard needs; writes its entries of d_ap0_all"""
+        self.torch.cuda.current_stream().synchronize()
+        ra, rb = self.plan.rows[self.rank]
+        self.wb._check(self.wb.lib().wb_pipeline_stream_lovetrain_dev(self.pipe._h, d_x.data_ptr(), self.plan.n, self.d_f0_all.data_ptr(),
+                                                                      self.plan.f0_length, ra, rb, d_ap0_all.data_ptr(), None),
+                       "wb_pipeline_stream_lovetrain_dev")
+        self.wb.device_synchronize()
+
+    def cheaptrick(self, d_x, sync=True):
+        """second half of envelope(): the spectral envelope rows this shard needs"""
+        self.torch.cuda.current_stream().synchronize()
+        torch = self.torch
+        ra, rb = self.plan.rows[self.rank]
+        self.d_sp = torch.empty((rb - ra, self.bins), dtype=torch.float64, device=d_x.device)
+        self.wb._check(self.wb.lib().wb_pipeline_stream_cheaptrick_dev(self.pipe._h, d_x.data_ptr(), self.plan.n, self.d_f0_all.data_ptr(),
+                                                                       self.plan.f0_length, ra, rb, self.d_sp.data_ptr(), None),
+                       "wb_pipeline_stream_cheaptrick_dev")
+        if sync:
+            self.wb.device_synchronize()
 
     def aperiodicity(self, d_x, d_ap0_all):
         self.torch.cuda.current_stream().synchronize()   # inputs made by torch ops; the library has its own stream
@@ -353,25 +414,38 @@ def process_stream_exact(d_x, fs, harvest_option=None, cheaptrick_option=None, d
     workers[0].begin(d_f0_all)
     for w in workers[1:]:
         w.d_f0_all = d_f0_all
+    # Love Train first: its decisions (8 bytes per frame) travel while CheapTrick -- the longer half of the
+    # envelope work -- runs, so the ranks do not sit in the exchange waiting for the slowest of them
     d_ap0 = torch.zeros(plan.f0_length, dtype=torch.float64, device=d_x.device)
     for w in workers:
-        w.envelope(d_x, d_ap0)
-    mark("envelope")
+        w.lovetrain(d_x, d_ap0)
+    mark("lovetrain")
     fb, fe = rank_frames[rank]
-    d_ap0 = gather_ranges(d_ap0[fb:fe].clone(), rank_frames, plan.f0_length, group)              # exchange 2
-    mark("gather_ap0")
-    ys, sps, aps = [], [], []
+    pending_ap0 = PendingGather(d_ap0[fb:fe].clone(), rank_frames, group)                        # exchange 2 (in flight)
     for w in workers:
+        w.cheaptrick(d_x)
+    mark("cheaptrick")
+    d_ap0 = pending_ap0.finish(plan.f0_length)
+    torch.cuda.current_stream().synchronize()
+    mark("wait_ap0")
+    # shard by shard: aperiodicity + synthesis, and the shard's samples go into the exchange (the stitch) while
+    # the next shard computes; only the last shard's exchange is exposed
+    pending, sps, aps = [], [], []
+    for j, w in enumerate(workers):
         w.aperiodicity(d_x, d_ap0)
-        ys.append(w.synthesis())
+        y_j = w.synthesis()
+        pending.append(PendingGather(y_j, [plan.samples[r * k + j] for r in range(world)], group))   # exchange 3
         if keep_rows:
             sps.append(w.owned_rows(w.d_sp))
             aps.append(w.owned_rows(w.d_ap))
         w.d_sp = w.d_ap = None
     workers[0].end()
     mark("aperiodicity_synthesis")
-    d_y = gather_ranges(torch.cat(ys), rank_samples, plan.out_length, group)                     # exchange 3 (stitch)
-    mark("stitch")
+    d_y = torch.empty(plan.out_length, dtype=torch.float64, device=d_x.device)
+    for pg in pending:
+        pg.finish_into(d_y)
+    torch.cuda.current_stream().synchronize()
+    mark("stitch_tail")
     if timings is not None:
         torch.cuda.synchronize()
         for (_, e0), (name, e1) in zip(marks[:-1], marks[1:]):
