@@ -56,6 +56,11 @@ inline void interp1Q(double x, double shift, const double *y, int x_length, cons
   }
 }
 
+// zero-phase IIR low-pass + pick of every r-th sample (world_matlabfunctions.cpp:184-210, coefficients :27-125), on
+// the GPU with the kernels Harvest uses; r = 2 .. 12; y holds the ceil((x_length + 9 - nbeg) / r) samples the
+// reference writes (nbeg = r - r * (x_length / r + 1) + x_length)
+inline void decimate(const double *x, int x_length, int r, double *y) { (void)wb_decimate(x, x_length, r, y); }
+
 // next value of the library's randn() stream (same sequence as the reference's generator)
 inline double randn(void) {
   double v = 0.0;

@@ -90,6 +90,9 @@ int wb_harvest_get_samples(int fs, int x_length, double frame_period);          
 int wb_harvest_create(int fs, const WbHarvestOption *opt_or_null, wb_harvest_t **out); /* src/harvest.cpp:69-103 */
 void wb_harvest_destroy(wb_harvest_t *h);
 /* src/harvest.cpp:183-208; temporal_positions and f0 hold wb_harvest_get_samples() entries */
+/* One call analyses up to about 117 s of audio (128 overlap-save blocks at the 8 kHz analysis rate): longer
+ * inputs return WB_ERR_UNSUPPORTED before anything is launched; process them in segments (worldb200.parallel,
+ * DESIGN.md section 5).  The reference accepts any length. */
 int wb_harvest_compute(wb_harvest_t *h, const double *x, int x_length, double *temporal_positions, double *f0);
 int wb_harvest_compute_dev(wb_harvest_t *h, const double *d_x, int x_length, double *d_temporal_positions,
                            double *d_f0, void *stream);
@@ -273,6 +276,22 @@ int wb_wavread_pcm16(const char *filename, int *fs, short *pcm);  /* the raw 16-
 
 /* ---- measurement hooks (bench.py) ------------------------------------------------------ */
 unsigned long long wb_launch_count(void);  /* kernels launched by this library so far */
+/* decimate() of /root/reference/include/world_matlabfunctions.hpp:81 (src/world_matlabfunctions.cpp:184-210) on the
+ * GPU: zero-phase third-order IIR low-pass, every r-th sample; r = 2 .. 12.  HOST pointers; y receives
+ * wb_decimate_length(x_length, r) samples. */
+int wb_decimate_length(int x_length, int r);
+int wb_decimate(const double *x, int x_length, int r, double *y);
+/* Errors detected on the device (more pulses than the f0 bound allows for, a smoothing width beyond the scratch
+ * capacity) are flagged in a per-handle word.  Host-pointer entry points return it themselves; after asynchronous
+ * *_dev calls ask here: waits for `stream` (NULL = the library's), returns WB_OK or the flagged status, clears it. */
+int wb_harvest_last_error(wb_harvest_t *h, void *stream);
+int wb_cheaptrick_last_error(wb_cheaptrick_t *h, void *stream);
+int wb_d4c_last_error(wb_d4c_t *h, void *stream);
+int wb_synthesis_last_error(wb_synthesis_t *h, void *stream);
+int wb_pipeline_last_error(wb_pipeline_t *p, void *stream);
+/* sharded streams with an f0 contour that does not come from Harvest: upper bound of its values (sizes the pulse
+ * buffers); <= 0 = Harvest's f0_ceil * 1.25 */
+int wb_pipeline_set_stream_f0_bound(wb_pipeline_t *p, double f0_upper_bound);
 int wb_measure_fp64_peak(double *tflops);  /* dependent-free DFMA chains on every SM: the fp64 roofline of this GPU */
 void *wb_stream(void);                     /* the library's own cudaStream_t */
 void wb_profile_enable(int on);            /* bracket every kernel launch with CUDA events */

@@ -112,6 +112,14 @@ def _declare(L):
         "wb_pipeline_debug_read": (ci, [vp, ctypes.c_char_p, vp, ctypes.c_ulonglong]),
         "wb_pipeline_stream_begin_dev": (ci, [vp, vp, ci, ci, vp]),
         "wb_pipeline_stream_envelope_dev": (ci, [vp, vp, ci, vp, ci, ci, ci, vp, vp, vp]),
+        "wb_decimate_length": (ci, [ci, ci]),
+        "wb_decimate": (ci, [ctypes.POINTER(cd), ci, ci, ctypes.POINTER(cd)]),
+        "wb_harvest_last_error": (ci, [vp, vp]),
+        "wb_cheaptrick_last_error": (ci, [vp, vp]),
+        "wb_d4c_last_error": (ci, [vp, vp]),
+        "wb_synthesis_last_error": (ci, [vp, vp]),
+        "wb_pipeline_last_error": (ci, [vp, vp]),
+        "wb_pipeline_set_stream_f0_bound": (ci, [vp, cd]),
         "wb_pipeline_stream_lovetrain_dev": (ci, [vp, vp, ci, vp, ci, ci, ci, vp, vp]),
         "wb_pipeline_stream_cheaptrick_dev": (ci, [vp, vp, ci, vp, ci, ci, ci, vp, vp]),
         "wb_pipeline_stream_aperiodicity_dev": (ci, [vp, vp, ci, vp, vp, ci, ci, ci, vp, vp]),
@@ -518,6 +526,14 @@ class Pipeline:
         _check(lib().wb_pipeline_run_dev(self._h, d_x, int(x_length), d_tpos or None, d_f0 or None, d_sp or None,
                                          d_ap or None, d_y or None, ny, stream or None), "wb_pipeline_run_dev")
 
+    def check_errors(self, stream=0):
+        """After asynchronous calls (run_dev, the stream_* calls): waits for `stream` and raises if a kernel flagged a
+        condition it could not handle (e.g. more pulses than the f0 bound allows for); the flag is cleared."""
+        _check(lib().wb_pipeline_last_error(self._h, stream or None), "device-side error of an earlier asynchronous call")
+
+    def set_stream_f0_bound(self, f0_upper_bound):
+        _check(lib().wb_pipeline_set_stream_f0_bound(self._h, float(f0_upper_bound)), "wb_pipeline_set_stream_f0_bound")
+
 
 # ---- measurement hooks ------------------------------------------------------------------------
 def launch_count():
@@ -737,3 +753,8 @@ class BatchPipeline:
         for st in self.streams:
             cur.wait_stream(st)
         return outs
+
+    def check_errors(self):
+        """Waits for the pipelines' streams and raises if a kernel of an earlier run() flagged an error."""
+        for pl, st in zip(self.pipes, self.streams):
+            pl.check_errors(st.cuda_stream)

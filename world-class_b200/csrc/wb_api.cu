@@ -354,6 +354,7 @@ struct wb_pipeline {
   cudaStream_t side = nullptr, d4c_stream = nullptr;
   unsigned long long graph_generation = 0;   // ws.generation() when the graph was captured
   int stream_f0_length = 0;          // sharded streams: the length given to wb_pipeline_stream_begin_dev
+  double stream_f0_bound = 0.0;      // sharded streams: upper bound of an external f0 contour (<= 0: f0_ceil * 1.25)
   cudaEvent_t ev_f0 = nullptr, ev_tb = nullptr, ev_ct_count = nullptr, ev_body_count = nullptr, ev_d4c = nullptr,
               ev_start = nullptr;
   // CUDA graph of one whole run (captured after a warm run with the same arguments)
@@ -403,6 +404,16 @@ struct wb_synthesis {
     if (side) cudaStreamDestroy(side);
   }
 };
+
+// option checks shared by wb_harvest_create and wb_pipeline_create (NaNs fail every comparison)
+static int check_harvest_option(const WbHarvestOption &o) {
+  if (o.use_cos_table) return WB_ERR_UNSUPPORTED;  // approximate window table: not offered (exact path only)
+  if (!(o.f0_floor > 0) || !(o.f0_ceil > o.f0_floor) || !(o.frame_period > 0) || !(o.target_fs > 0) ||
+      !(o.channels_in_octave > 0) || !(o.f0_ceil < 1e6) || !(o.frame_period < 1e6) || !(o.channels_in_octave < 1e4))
+    return WB_ERR_ARG;
+  return WB_OK;
+}
+static bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
 
 extern "C" {
 
@@ -533,6 +544,11 @@ int wb_cheaptrick_create(int fs, const WbCheapTrickOption *opt, wb_cheaptrick_t 
   h->fs = fs;
   wb_cheaptrick_option_default(&h->opt);
   if (opt) { h->opt.q1 = opt->q1; h->opt.f0_floor = opt->f0_floor; h->opt.fft_size = opt->fft_size; }
+  if (!(h->opt.f0_floor > 0) || h->opt.fft_size < 0 ||
+      (h->opt.fft_size != 0 && (!is_pow2(h->opt.fft_size) || h->opt.fft_size < 128 || h->opt.fft_size > 16384))) {
+    delete h;
+    return WB_ERR_ARG;
+  }
   if (h->opt.fft_size == 0) h->opt.fft_size = wb_cheaptrick_get_fft_size(fs, h->opt.f0_floor);
   h->f0_floor_internal = wb_cheaptrick_get_f0_floor(fs, h->opt.fft_size);
   *out = h;
@@ -703,10 +719,7 @@ int wb_harvest_create(int fs, const WbHarvestOption *opt, wb_harvest_t **out) {
   WbHarvestOption o;
   wb_harvest_option_default(&o);
   if (opt) o = *opt;
-  if (o.use_cos_table) return WB_ERR_UNSUPPORTED;  // approximate window table: not offered (exact path only)
-  if (!(o.f0_floor > 0) || !(o.f0_ceil > o.f0_floor) || !(o.frame_period > 0) || !(o.target_fs > 0) ||
-      !(o.channels_in_octave > 0))
-    return WB_ERR_ARG;
+  if ((rc = check_harvest_option(o))) return rc;
   wb_harvest *h = new (std::nothrow) wb_harvest();
   if (!h) return WB_ERR_ARG;
   WbHarvestOptionInternal oi = {o.f0_floor, o.f0_ceil, o.frame_period, o.target_fs, o.channels_in_octave};
@@ -776,7 +789,10 @@ int wb_pipeline_create(int fs, const WbHarvestOption *hopt, const WbCheapTrickOp
   WbHarvestOption ho;
   wb_harvest_option_default(&ho);
   if (hopt) ho = *hopt;
-  if (ho.use_cos_table) return WB_ERR_UNSUPPORTED;
+  if ((rc = check_harvest_option(ho))) return rc;
+  if (copt && (!(copt->f0_floor > 0) || copt->fft_size < 0 || (copt->fft_size != 0 && (!is_pow2(copt->fft_size) || copt->fft_size < 128 || copt->fft_size > 16384))))
+    return WB_ERR_ARG;
+  if (dopt && !(dopt->threshold >= 0.0 && dopt->threshold <= 1.0)) return WB_ERR_ARG;
   wb_pipeline *p = new (std::nothrow) wb_pipeline();
   if (!p) return WB_ERR_ARG;
   p->fs = fs;
@@ -1161,7 +1177,7 @@ int wb_pipeline_stream_synthesis_dev(wb_pipeline_t *p, int f0_length, const doub
   c.state = rng; c.skip_in = rng_pos + 1; c.advance = false;  // (several ranges may follow: wb_pipeline_stream_end_dev moves the state)
   return wb_synthesis_render_range(&p->ws, p->fs, p->ct.fft_size, p->plan.opt.frame_period, f0_length, d_sp_rows, d_ap_rows,
                                    row_begin, n_rows, out_length, sample_begin, sample_end, d_out,
-                                   p->plan.opt.f0_ceil * 1.25, c, stream);
+                                   p->stream_f0_bound > 0.0 ? p->stream_f0_bound : p->plan.opt.f0_ceil * 1.25, c, stream);
 }
 
 // moves the randn() state past the whole stream's draws (what one reference process would leave behind)
@@ -1303,7 +1319,9 @@ int wb_parameter_modification(double *f0, int f0_length, double **spectrogram, i
   if (rc) return rc;
   if (f0_length < 0 || fs <= 0 || fft_size < 4) return WB_ERR_ARG;
   if (f0_length == 0) return WB_OK;
-  static WbWorkspace ws;   // a free function in the reference's demo: one shared workspace
+  static WbWorkspace ws;   // a free function in the reference's demo: one shared workspace ...
+  static std::mutex ws_mutex;   // ... so concurrent callers take turns (the reference's function is stateless)
+  std::lock_guard<std::mutex> lock(ws_mutex);
   cudaStream_t st = g_stream;
   const int bins = fft_size / 2 + 1;
   const bool do_f0 = f0 && f0_shift == f0_shift, do_sp = spectrogram && ratio > 0.0;
@@ -1337,6 +1355,8 @@ static int codec_rows(int kind, const double *const *in, int in_cols, int f0_len
   if (f0_length == 0) return WB_OK;
   if (in_cols <= 0 || out_cols <= 0) return WB_ERR_UNSUPPORTED;
   WbWorkspace *ws = codec_ws();
+  static std::mutex ws_mutex;   // the reference's codec functions are stateless: concurrent callers take turns on the staging buffers
+  std::lock_guard<std::mutex> lock(ws_mutex);
   cudaStream_t st = g_stream;
   double *d_in = (double *)ws->get("codec_in", sizeof(double) * (size_t)f0_length * in_cols);
   double *d_out = (double *)ws->get("codec_out", sizeof(double) * (size_t)f0_length * out_cols);
@@ -1397,6 +1417,26 @@ int wb_pipeline_debug_read(wb_pipeline_t *p, const char *name, void *out, unsign
   if (!d || n_bytes > have) return WB_ERR_ARG;   // unknown buffer, or more than it holds
   WB_CUDA_CHECK(cudaDeviceSynchronize());
   WB_CUDA_CHECK(cudaMemcpy(out, d, n_bytes, cudaMemcpyDeviceToHost));
+  return WB_OK;
+}
+
+// ---- errors detected on the device ---------------------------------------------------------------
+// Kernels flag conditions they cannot handle (more pulses than the f0 bound allows for, a smoothing width beyond
+// the scratch capacity) in a per-handle device word.  The host-pointer entry points read it before they return;
+// the asynchronous device-pointer entry points cannot, so their callers ask here once they have synchronised
+// (or want to): waits for `stream`, returns WB_OK or the flagged status, and clears the flag.
+int wb_harvest_last_error(wb_harvest_t *h, void *stream) { return h ? h->ws.read_error_flag(pick_stream(stream)) : WB_ERR_ARG; }
+int wb_cheaptrick_last_error(wb_cheaptrick_t *h, void *stream) { return h ? h->ws.read_error_flag(pick_stream(stream)) : WB_ERR_ARG; }
+int wb_d4c_last_error(wb_d4c_t *h, void *stream) { return h ? h->ws.read_error_flag(pick_stream(stream)) : WB_ERR_ARG; }
+int wb_synthesis_last_error(wb_synthesis_t *h, void *stream) { return h ? h->ws.read_error_flag(pick_stream(stream)) : WB_ERR_ARG; }
+int wb_pipeline_last_error(wb_pipeline_t *p, void *stream) { return p ? p->ws.read_error_flag(pick_stream(stream)) : WB_ERR_ARG; }
+
+/* Sharded streams whose f0 contour does not come from Harvest (wb_pipeline_stream_begin_dev with an external
+ * contour): upper bound of its values, which sizes the pulse buffers of the synthesis calls.  <= 0: Harvest's
+ * f0_ceil * 1.25 (the default). */
+int wb_pipeline_set_stream_f0_bound(wb_pipeline_t *p, double f0_upper_bound) {
+  if (!p || f0_upper_bound != f0_upper_bound) return WB_ERR_ARG;
+  p->stream_f0_bound = f0_upper_bound;
   return WB_OK;
 }
 

@@ -14,6 +14,8 @@
 #include "wb_fft.cuh"
 
 #include <math.h>
+#include <map>
+#include <mutex>
 #include <vector>
 
 namespace {
@@ -215,36 +217,85 @@ int wb_decode_aperiodicity_dev(const double *d_coded, int f0_length, int fs, int
   return WB_OK;
 }
 
+// Interpolation / weight tables of the spectral-envelope codec: functions of (fs, fft_size) -- and of the number
+// of dimensions on the decoding side -- only.  Built once per key with the reference's host expressions
+// (GetParametersForCoding codec.cpp:156-175, GetParametersForDecoding codec.cpp:180-207), uploaded once, never
+// freed or rewritten: calls on any thread / stream share them read-only and a call is launches only (no
+// synchronisation, no upload).
+namespace {
+struct CodecTables { int *k; double *s; cplx *w; };
+struct CodecKey {
+  bool decode; int fs, fft_size, nd;
+  bool operator<(const CodecKey &o) const {
+    if (decode != o.decode) return decode < o.decode;
+    if (fs != o.fs) return fs < o.fs;
+    if (fft_size != o.fft_size) return fft_size < o.fft_size;
+    return nd < o.nd;
+  }
+};
+std::mutex g_codec_mutex;
+std::map<CodecKey, CodecTables> g_codec_tables;
+
+const CodecTables *codec_tables(bool decode, int fs, int fft_size, int nd) {
+  const CodecKey key = {decode, fs, fft_size, decode ? nd : 0};
+  std::lock_guard<std::mutex> lock(g_codec_mutex);
+  auto it = g_codec_tables.find(key);
+  if (it != g_codec_tables.end()) return &it->second;
+  const int M = fft_size / 2, bins = M + 1;
+  const double floor_mel = FrequencyToMel(kFloorFrequency);
+  const double ceil_f = (fs / 2.0 < kCeilFrequency) ? fs / 2.0 : kCeilFrequency;
+  const double ceil_mel = FrequencyToMel(ceil_f);
+  std::vector<int> k;
+  std::vector<double> s;
+  std::vector<cplx> weight;
+  if (!decode) {
+    std::vector<double> mel_axis(M), frequency_axis(M + 1, 0.0);  // frequency_axis[M] is never set (zero-filled, Q12)
+    weight.resize(M);
+    for (int i = 0; i < M; ++i) {
+      mel_axis[i] = (ceil_mel - floor_mel) * i / M + floor_mel;
+      weight[i].x = 2.0 * cos(i * WB_PI / fft_size) / sqrt((double)fft_size);
+      weight[i].y = 2.0 * sin(i * WB_PI / fft_size) / sqrt((double)fft_size);
+    }
+    weight[0].x /= sqrt(2.0);
+    for (int i = 0; i < M; ++i) frequency_axis[i] = FrequencyToMel(static_cast<double>(i) * fs / fft_size);
+    interp1_table(frequency_axis, mel_axis, k, s);
+  } else {
+    weight.resize(nd);
+    for (int i = 0; i < nd; ++i) {
+      weight[i].x = cos(i * WB_PI / fft_size) * sqrt((double)fft_size);
+      weight[i].y = sin(i * WB_PI / fft_size) * sqrt((double)fft_size);
+    }
+    weight[0].x /= sqrt(2.0);
+    std::vector<double> mel_axis(M + 2), frequency_axis(bins);
+    for (int i = 0; i < M; ++i) mel_axis[i + 1] = MelToFrequency((ceil_mel - floor_mel) * i / M + floor_mel);
+    mel_axis[0] = 0;
+    mel_axis[M + 1] = fs / 2.0;
+    for (int i = 0; i < bins; ++i) frequency_axis[i] = static_cast<double>(i) * fs / fft_size;
+    interp1_table(mel_axis, frequency_axis, k, s);
+  }
+  CodecTables t = {nullptr, nullptr, nullptr};
+  if (cudaMalloc(&t.k, sizeof(int) * k.size()) != cudaSuccess || cudaMalloc(&t.s, sizeof(double) * s.size()) != cudaSuccess ||
+      cudaMalloc(&t.w, sizeof(cplx) * weight.size()) != cudaSuccess)
+    return nullptr;
+  if (cudaMemcpy(t.k, k.data(), sizeof(int) * k.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(t.s, s.data(), sizeof(double) * s.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(t.w, weight.data(), sizeof(cplx) * weight.size(), cudaMemcpyHostToDevice) != cudaSuccess)
+    return nullptr;
+  return &(g_codec_tables[key] = t);
+}
+}  // namespace
+
 int wb_code_spectral_envelope_dev(WbWorkspace *ws, const double *d_sp, int f0_length, int fs, int fft_size, int nd,
                                   double *d_coded, cudaStream_t stream) {
   if (f0_length <= 0) return WB_OK;
   const int M = fft_size / 2, l = ilog2_exact(M);
   if (l < 7 || l > 12 || nd < 1 || nd > M) return WB_ERR_UNSUPPORTED;
-  // GetParametersForCoding (codec.cpp:156-175)
-  const double floor_mel = FrequencyToMel(kFloorFrequency);
-  const double ceil_f = (fs / 2.0 < kCeilFrequency) ? fs / 2.0 : kCeilFrequency;
-  const double ceil_mel = FrequencyToMel(ceil_f);
-  std::vector<double> mel_axis(M), frequency_axis(M + 1, 0.0);  // frequency_axis[M] is never set (zero-filled, Q12)
-  std::vector<cplx> weight(M);
-  for (int i = 0; i < M; ++i) {
-    mel_axis[i] = (ceil_mel - floor_mel) * i / M + floor_mel;
-    weight[i].x = 2.0 * cos(i * WB_PI / fft_size) / sqrt((double)fft_size);
-    weight[i].y = 2.0 * sin(i * WB_PI / fft_size) / sqrt((double)fft_size);
-  }
-  weight[0].x /= sqrt(2.0);
-  for (int i = 0; i < M; ++i) frequency_axis[i] = FrequencyToMel(static_cast<double>(i) * fs / fft_size);
-  std::vector<int> k;
-  std::vector<double> s;
-  interp1_table(frequency_axis, mel_axis, k, s);
-  int *d_k = (int *)ws->get("codec_k", sizeof(int) * M);
-  double *d_s = (double *)ws->get("codec_s", sizeof(double) * M);
-  cplx *d_w = (cplx *)ws->get("codec_w", sizeof(cplx) * M);
-  if (!d_k || !d_s || !d_w) return WB_ERR_CUDA;
-  // pageable host vectors: synchronous copies (tables are tiny and only depend on fs / fft_size)
-  WB_CUDA_CHECK(cudaStreamSynchronize(stream));
-  WB_CUDA_CHECK(cudaMemcpy(d_k, k.data(), sizeof(int) * M, cudaMemcpyHostToDevice));
-  WB_CUDA_CHECK(cudaMemcpy(d_s, s.data(), sizeof(double) * M, cudaMemcpyHostToDevice));
-  WB_CUDA_CHECK(cudaMemcpy(d_w, weight.data(), sizeof(cplx) * M, cudaMemcpyHostToDevice));
+  const CodecTables *tab = codec_tables(false, fs, fft_size, nd);
+  if (!tab) return WB_ERR_CUDA;
+  int *d_k = tab->k;
+  double *d_s = tab->s;
+  cplx *d_w = tab->w;
+  (void)ws;
   CodeSpParams p;
   p.sp = d_sp; p.f0_length = f0_length; p.fft_size = fft_size; p.nd = nd; p.k = d_k; p.s = d_s; p.weight = d_w;
   p.tw = wb_twiddle_table(M);
@@ -265,32 +316,12 @@ int wb_decode_spectral_envelope_dev(WbWorkspace *ws, const double *d_coded, int 
   if (f0_length <= 0) return WB_OK;
   const int M = fft_size / 2, l = ilog2_exact(M), bins = M + 1;
   if (l < 7 || l > 12 || nd < 1 || nd > M) return WB_ERR_UNSUPPORTED;
-  // GetParametersForDecoding (codec.cpp:180-207)
-  const double floor_mel = FrequencyToMel(kFloorFrequency);
-  const double ceil_f = (fs / 2.0 < kCeilFrequency) ? fs / 2.0 : kCeilFrequency;
-  const double ceil_mel = FrequencyToMel(ceil_f);
-  std::vector<cplx> weight(nd);
-  for (int i = 0; i < nd; ++i) {
-    weight[i].x = cos(i * WB_PI / fft_size) * sqrt((double)fft_size);
-    weight[i].y = sin(i * WB_PI / fft_size) * sqrt((double)fft_size);
-  }
-  weight[0].x /= sqrt(2.0);
-  std::vector<double> mel_axis(M + 2), frequency_axis(bins);
-  for (int i = 0; i < M; ++i) mel_axis[i + 1] = MelToFrequency((ceil_mel - floor_mel) * i / M + floor_mel);
-  mel_axis[0] = 0;
-  mel_axis[M + 1] = fs / 2.0;
-  for (int i = 0; i < bins; ++i) frequency_axis[i] = static_cast<double>(i) * fs / fft_size;
-  std::vector<int> k;
-  std::vector<double> s;
-  interp1_table(mel_axis, frequency_axis, k, s);
-  int *d_k = (int *)ws->get("codec_dk", sizeof(int) * bins);
-  double *d_s = (double *)ws->get("codec_ds", sizeof(double) * bins);
-  cplx *d_w = (cplx *)ws->get("codec_dw", sizeof(cplx) * nd);
-  if (!d_k || !d_s || !d_w) return WB_ERR_CUDA;
-  WB_CUDA_CHECK(cudaStreamSynchronize(stream));
-  WB_CUDA_CHECK(cudaMemcpy(d_k, k.data(), sizeof(int) * bins, cudaMemcpyHostToDevice));
-  WB_CUDA_CHECK(cudaMemcpy(d_s, s.data(), sizeof(double) * bins, cudaMemcpyHostToDevice));
-  WB_CUDA_CHECK(cudaMemcpy(d_w, weight.data(), sizeof(cplx) * nd, cudaMemcpyHostToDevice));
+  const CodecTables *tab = codec_tables(true, fs, fft_size, nd);
+  if (!tab) return WB_ERR_CUDA;
+  int *d_k = tab->k;
+  double *d_s = tab->s;
+  cplx *d_w = tab->w;
+  (void)ws; (void)bins;
   DecodeSpParams p;
   p.coded = d_coded; p.f0_length = f0_length; p.fft_size = fft_size; p.nd = nd; p.k = d_k; p.s = d_s; p.weight = d_w;
   p.tw = wb_twiddle_table(2 * M);

@@ -931,6 +931,9 @@ int wb_harvest_run_basic(WbHarvestPlan *pl, WbWorkspace *ws, const double *d_x, 
   const int Lb = static_cast<int>(1000.0 * x_length / fs / frame_period) + 1;            // harvest.cpp:173-176
   *f0_length_out = Lb;
   const int nch = pl->nch, MC = pl->max_candidates, own_cap = MC / 7;
+  // one call handles up to IV_MAX_BLOCKS overlap-save blocks (~117 s at the 8 kHz analysis rate): checked before
+  // anything is enqueued; longer streams go through the segmenting path (worldb200/parallel.py)
+  if ((y_length + pl->V - 1) / pl->V > IV_MAX_BLOCKS) return WB_ERR_UNSUPPORTED;
 
   // ---- clears of the candidate tables: nothing before the candidate stage touches them, so they run on
   // the auxiliary stream beside the chain
@@ -1083,4 +1086,48 @@ int wb_harvest_run_basic(WbHarvestPlan *pl, WbWorkspace *ws, const double *d_x, 
 
   // ---- contour fixing + smoothing
   return wb_harvest_tail(ws, d_candB, d_scoreB, d_nc, Lb, MC, d_f0_basic, stream);
+}
+
+// ---- decimate() as a stand-alone call (include/world_matlabfunctions.hpp; world_matlabfunctions.cpp:184-210) ----
+extern "C" int wb_decimate_length(int x_length, int r) {
+  if (x_length <= 0 || r < 1) return 0;
+  const int nout = x_length / r + 1;
+  const int nbeg = r - r * nout + x_length;
+  return (x_length + DEC_NFACT - nbeg + r - 1) / r;
+}
+
+extern "C" int wb_decimate(const double *x, int x_length, int r, double *y) {
+  if (!x || !y || x_length < 2 * DEC_NFACT) return WB_ERR_ARG;
+  DecimCoef dc;
+  if (!decimate_coefficients(r, &dc)) return WB_ERR_UNSUPPORTED;
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return WB_ERR_CUDA;
+  const int y_length = wb_decimate_length(x_length, r);
+  const int len1 = x_length, len2 = len1 + 2 * DEC_NFACT;
+  double *d_x = nullptr, *d_fwd = nullptr, *d_y = nullptr;
+  unsigned long long *d_absmax = nullptr;
+  cudaStream_t stream = nullptr;
+  int rc = WB_OK;
+  if (cudaMalloc(&d_x, sizeof(double) * x_length) != cudaSuccess || cudaMalloc(&d_fwd, sizeof(double) * len2) != cudaSuccess ||
+      cudaMalloc(&d_y, sizeof(double) * y_length) != cudaSuccess || cudaMalloc(&d_absmax, 16) != cudaSuccess)
+    rc = WB_ERR_CUDA;
+  if (!rc) {
+    const int n_tiles = (len2 + DEC_TILE - 1) / DEC_TILE;
+    const size_t smem_f = sizeof(double) * (dec_pad_host(DEC_TILE + DEC_WARM) + 1 + dec_pad_host(DEC_TILE) + 1);
+    const size_t smem_b = sizeof(double) * (dec_pad_host(DEC_TILE + DEC_WARM) + 1);
+    cudaError_t e = cudaMemcpy(d_x, x, sizeof(double) * x_length, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(d_absmax, 0, 16);
+    if (e == cudaSuccess) e = cudaMemset(d_y, 0, sizeof(double) * y_length);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(dec_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(dec_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
+    if (e == cudaSuccess) {
+      WB_LAUNCH("dec_forward_kernel", dec_forward_kernel<<<n_tiles, DEC_BLOCK, smem_f, stream>>>(d_x, x_length, 0, len1, len2, dc, d_fwd));
+      WB_LAUNCH("dec_backward_kernel", dec_backward_kernel<<<n_tiles, DEC_BLOCK, smem_b, stream>>>(d_fwd, len1, len2, r, 0, dc, y_length, d_y, d_absmax));
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(y, d_y, sizeof(double) * y_length, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = WB_ERR_CUDA;
+  }
+  cudaFree(d_x); cudaFree(d_fwd); cudaFree(d_y); cudaFree(d_absmax);
+  return rc;
 }

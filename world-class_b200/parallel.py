@@ -353,6 +353,7 @@ class StreamWorker:
     def end(self):
         self.wb._check(self.wb.lib().wb_pipeline_stream_end_dev(self.pipe._h, None), "wb_pipeline_stream_end_dev")
         self.wb.device_synchronize()
+        self.pipe.check_errors()     # (conditions a kernel of the asynchronous calls above could not handle)
 
     def owned_rows(self, d_rows):
         """the rows of d_sp / d_ap this shard owns (without the halo rows it computed for its pulses)"""
@@ -406,11 +407,17 @@ def process_stream_exact(d_x, fs, harvest_option=None, cheaptrick_option=None, d
             marks.append((name, ev))
 
     mark("start")
+    external_f0 = d_f0_all is not None
     if d_f0_all is None:
         local_f0 = torch.cat([w.harvest_local(d_x) for w in workers])
         mark("harvest")
         d_f0_all = gather_ranges(local_f0, rank_frames, plan.f0_length, group)                   # exchange 1
         mark("gather_f0")
+    if external_f0:
+        # the contour is the caller's: size the pulse buffers by its maximum instead of Harvest's ceiling
+        workers[0].pipe.set_stream_f0_bound(float(d_f0_all.max().item()) + 1.0)
+    else:
+        workers[0].pipe.set_stream_f0_bound(0.0)
     workers[0].begin(d_f0_all)
     for w in workers[1:]:
         w.d_f0_all = d_f0_all

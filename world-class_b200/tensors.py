@@ -114,3 +114,16 @@ def to_float32(t):
     out = torch.empty(t.shape, dtype=torch.float32, device=t.device)
     wb._check(wb.lib().wb_f64_to_f32_dev(t.data_ptr(), t.numel(), out.data_ptr(), _stream()), "wb_f64_to_f32_dev")
     return out
+
+
+def check_errors():
+    """The functions above are asynchronous on torch's current stream and cannot report what a kernel flags on the
+    device (e.g. synthesis() with an f0_upper_bound below the contour's maximum drops pulses).  This waits for the
+    current stream and raises if any of the cached stage objects flagged an error since the last check."""
+    kinds = {"harvest": "wb_harvest_last_error", "cheaptrick": "wb_cheaptrick_last_error", "d4c": "wb_d4c_last_error",
+             "synthesis": "wb_synthesis_last_error"}
+    for k, h in list(_objects.items()):
+        kind = k[0]
+        fn = kinds.get(kind)
+        if fn is not None:
+            wb._check(getattr(wb.lib(), fn)(h._h, _stream()), "device-side error of an earlier %s call" % kind)
