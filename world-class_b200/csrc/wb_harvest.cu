@@ -303,6 +303,7 @@ struct ChanParams {
 };
 
 #define CH_THREADS 256
+#define CH_MASK_WORDS 5   /* flags of up to 80 samples per thread (the run is V / 256 | 1 <= 65 samples for blocks of 2^14) */
 
 // flags of sample n for the four zero-crossing kinds (harvest.cpp:1179-1255):
 // bit 0: negative-going of f, 1: of -f, 2: of d = f[n+1]-f[n] (peaks), 3: of -d (dips)
@@ -345,12 +346,32 @@ __global__ void __launch_bounds__(CH_THREADS, 3) channel_kernel(ChanParams p) {
   const int n_end = min(n0 + p.V, p.y_length);
   // each thread owns a contiguous run of samples (odd length: conflict-free shared-memory reads)
   int chunk = (p.V + CH_THREADS - 1) / CH_THREADS;
-  chunk |= 1;
+  chunk |= 1;   // (<= 16 * CH_MASK_WORDS: V <= 2^14)
   const int my_begin = n0 + tid * chunk, my_end = min(n_end, my_begin + chunk);
+  // (a three-sample window slides over the run: one shared-memory read and one padded-index computation per
+  // sample instead of three; the flags of the run are kept as a bit mask, so the second pass only visits the
+  // samples that have a crossing -- a few per thread)
   int cnt[4] = {0, 0, 0, 0};
-  for (int n = my_begin; n < my_end; ++n) {
-    const unsigned m = ch_flags(W[wb_didx(n + off)], W[wb_didx(n + 1 + off)], W[wb_didx(n + 2 + off)], n, p.y_length);
-    cnt[0] += m & 1u; cnt[1] += (m >> 1) & 1u; cnt[2] += (m >> 2) & 1u; cnt[3] += (m >> 3) & 1u;
+  unsigned long long mask[CH_MASK_WORDS];
+#pragma unroll
+  for (int w = 0; w < CH_MASK_WORDS; ++w) mask[w] = 0ull;
+  if (my_begin < my_end) {
+    double a = W[wb_didx(my_begin + off)], bb = W[wb_didx(my_begin + 1 + off)];
+#pragma unroll
+    for (int w = 0; w < CH_MASK_WORDS; ++w) {
+      if (my_begin + w * 16 >= my_end) break;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const int n = my_begin + w * 16 + q;
+        if (n < my_end) {
+          const double cc = W[wb_didx(n + 2 + off)];
+          const unsigned m = ch_flags(a, bb, cc, n, p.y_length);
+          mask[w] |= (unsigned long long)m << (4 * q);
+          cnt[0] += m & 1u; cnt[1] += (m >> 1) & 1u; cnt[2] += (m >> 2) & 1u; cnt[3] += (m >> 3) & 1u;
+          a = bb; bb = cc;
+        }
+      }
+    }
   }
   int pre[4];
 #pragma unroll
@@ -377,19 +398,27 @@ __global__ void __launch_bounds__(CH_THREADS, 3) channel_kernel(ChanParams p) {
   }
   double *dst = p.seg_edges + ((size_t)c * 4 * p.n_blocks + b) * p.bcap;
   const size_t tstride = (size_t)p.n_blocks * p.bcap;
-  for (int n = my_begin; n < my_end; ++n) {
-    const double a = W[wb_didx(n + off)], bb = W[wb_didx(n + 1 + off)], cc = W[wb_didx(n + 2 + off)];
-    const unsigned m = ch_flags(a, bb, cc, n, p.y_length);
-    if (m & 3u) {
-      const double fine = (n + 1) - a / (bb - a);
-      if (m & 1u) { if (pre[0] < p.bcap) dst[pre[0]] = fine; ++pre[0]; }
-      if (m & 2u) { if (pre[1] < p.bcap) dst[tstride + pre[1]] = fine; ++pre[1]; }
-    }
-    if (m & 12u) {
-      const double d0 = bb - a, d1 = cc - bb;
-      const double fine = (n + 1) - d0 / (d1 - d0);
-      if (m & 4u) { if (pre[2] < p.bcap) dst[2 * tstride + pre[2]] = fine; ++pre[2]; }
-      if (m & 8u) { if (pre[3] < p.bcap) dst[3 * tstride + pre[3]] = fine; ++pre[3]; }
+#pragma unroll
+  for (int w = 0; w < CH_MASK_WORDS; ++w) {
+    unsigned long long left = mask[w];
+    while (left) {
+      const int q = (__ffsll((long long)left) - 1) >> 2;
+      const unsigned m = (unsigned)(left >> (4 * q)) & 15u;
+      left &= ~(15ull << (4 * q));
+      const int n = my_begin + w * 16 + q;
+      const double a = W[wb_didx(n + off)], bb = W[wb_didx(n + 1 + off)];
+      if (m & 3u) {
+        const double fine = (n + 1) - a / (bb - a);
+        if (m & 1u) { if (pre[0] < p.bcap) dst[pre[0]] = fine; ++pre[0]; }
+        if (m & 2u) { if (pre[1] < p.bcap) dst[tstride + pre[1]] = fine; ++pre[1]; }
+      }
+      if (m & 12u) {
+        const double cc = W[wb_didx(n + 2 + off)];
+        const double d0 = bb - a, d1 = cc - bb;
+        const double fine = (n + 1) - d0 / (d1 - d0);
+        if (m & 4u) { if (pre[2] < p.bcap) dst[2 * tstride + pre[2]] = fine; ++pre[2]; }
+        if (m & 8u) { if (pre[3] < p.bcap) dst[3 * tstride + pre[3]] = fine; ++pre[3]; }
+      }
     }
   }
 }
