@@ -53,6 +53,8 @@ template <int LOG2N>
 __global__ void __launch_bounds__(256) ct_frame_kernel(CtParams p) {
   extern __shared__ double2 smem_raw[];
   constexpr int N = 1 << LOG2N, NC = N / 2, bins = NC + 1;
+  // one radix-8 butterfly per thread and pass (the launch uses min(256, N / 8) threads, at least 64): warp-local late passes
+  constexpr bool WL = (NC / 8 <= 256);
   cplx *S = smem_raw;                                         // FFT slots
   double *A = reinterpret_cast<double *>(S + wb_fft_slots(NC));  // N + 2 doubles
   double *B = A + (N + 2);                                    // seg_capacity doubles
@@ -96,7 +98,7 @@ __global__ void __launch_bounds__(256) ct_frame_kernel(CtParams p) {
   __syncthreads();
 
   // ---- power spectrum (cheaptrick.cpp:198-218)
-  wb_rfft_t<1, LOG2N - 1>(S, p.twiddle, [&](int k, cplx X) { A[k] = X.x * X.x + X.y * X.y; });
+  wb_rfft_t<1, LOG2N - 1, WB_FFT_DEFAULT_RADIX, WL>(S, p.twiddle, [&](int k, cplx X) { A[k] = X.x * X.x + X.y * X.y; });
   wb_dc_correction(A, f0, fs, N);
 
   // ---- linear smoothing with width 2 f0 / 3 (cheaptrick.cpp:124-125)
@@ -115,7 +117,7 @@ __global__ void __launch_bounds__(256) ct_frame_kernel(CtParams p) {
 
   // ---- liftering in the cepstral domain (cheaptrick.cpp:238-269)
   const double q1 = p.q1;
-  wb_rfft_t<1, LOG2N - 1>(S, p.twiddle, [&](int k, cplx X) {
+  wb_rfft_t<1, LOG2N - 1, WB_FFT_DEFAULT_RADIX, WL>(S, p.twiddle, [&](int k, cplx X) {
     double sl = 1.0, cl = (1.0 - 2.0 * q1) + 2.0 * q1;
     if (k > 0) {
       const double quefrency = static_cast<double>(k) / fs;
@@ -124,7 +126,7 @@ __global__ void __launch_bounds__(256) ct_frame_kernel(CtParams p) {
     }
     A[k] = X.x * sl * cl / N;
   });
-  wb_irfft_t<-1, LOG2N - 1>(S, p.twiddle, [&](int k) { return make_double2(A[k], 0.0); });
+  wb_irfft_t<-1, LOG2N - 1, WB_FFT_DEFAULT_RADIX, WL>(S, p.twiddle, [&](int k) { return make_double2(A[k], 0.0); });
 
   double *out = p.sp + (size_t)frame * bins;
   for (int i = tid; i < bins; i += nt) out[i] = exp(W[wb_didx(i)]);

@@ -402,7 +402,7 @@ d4c_body_kernel(BodyParams p) {
 #pragma unroll
     for (int q = 0; q < 16; ++q) v[q] = (v[q] - w[q] * coef) * inv_power;   // (samples past the window stay 0)
     noise += wlen;
-    wb_cfft_dif_in_t<1, LOG2N>(S, p.tw_2n, [&](int j, int q) { return make_double2(v[q], v[q] * (j + 1.0)); });
+    wb_cfft_dif_in_t<1, LOG2N, 16, true>(S, p.tw_2n, [&](int j, int q) { return make_double2(v[q], v[q] * (j + 1.0)); });
     // spectra of w (X1) and (n+1) w (X2) from Z[k], Z[N-k]; centroid term Re X1 Re X2 + Im X1 Im X2 (d4c.cpp:400)
     // = (Re Z[k] Im Z[N-k] + Im Z[k] Re Z[N-k]) / 2
 #pragma unroll
@@ -467,7 +467,7 @@ d4c_body_kernel(BodyParams p) {
     for (int q = 0; q < 16; ++q) v[q] -= w[q] * coef;
     wb_pass_dif8<1, NC, NC>(S, p.tw_n, [&](int, int q) { return make_double2(v[2 * q], v[2 * q + 1]); });
     __syncthreads();
-    WbDifPasses<1, NC, NC / 8, 16>::run(S, p.tw_n, WbFromSlots());
+    WbDifPasses<1, NC, NC / 8, 16, true>::run(S, p.tw_n, WbFromSlots());
     // split step of the real transform (see wb_rfft_t): power of bins k and NC - k, stored for the smoothing
     double *P = segA + b_sp;
     for (int k = tid; k <= (NC >> 1); k += T) {
@@ -554,7 +554,7 @@ d4c_body_kernel(BodyParams p) {
     for (int i = tid; i < 2 * D4C_HIST_BINS; i += T) hist[i] = 0;
     if (tid < 2) ctl[6 + tid] = 0;
     // the windowed band slices feed the first FFT pass directly (the rest of the N points is zero padding)
-    wb_cfft_dif_in_t<1, LOG2N>(S, p.tw_2n, [&](int j, int) {
+    wb_cfft_dif_in_t<1, LOG2N, 16, true>(S, p.tw_2n, [&](int j, int) {
       cplx z = make_double2(0.0, 0.0);
       if (j < wl) {
         const double nw = __ldg(&p.nuttall[j]);

@@ -148,10 +148,15 @@ __device__ __forceinline__ void wb_twiddles8(const cplx *__restrict__ T, int t1,
 struct WbFromSlots {};
 
 // ---- one DIF pass over sub-blocks of size M (radix 8), in place; table has 2N entries -------
-template <int SIGN, int N, int M, typename In = WbFromSlots>
+// OWN16: clean-up pass (M = 8) of the radix-16 plan in WL mode: thread t takes the two butterflies inside its 16 points
+template <int SIGN, int N, int M, typename In = WbFromSlots, bool OWN16 = false>
 __device__ __forceinline__ void wb_pass_dif8(cplx *s, const cplx *__restrict__ T, In in = In()) {
   constexpr int m8 = M / 8, tstep = 2 * N / M;
-  for (int u = threadIdx.x; u < N / 8; u += blockDim.x) {
+  static_assert(!OWN16 || M == 8, "ownership mapping is for the twiddle-free clean-up pass");
+  const int u_begin = OWN16 ? 2 * (int)threadIdx.x : (int)threadIdx.x;
+  const int u_step = OWN16 ? 1 : (int)blockDim.x;
+  const int u_end = OWN16 ? (((int)threadIdx.x < N / 16) ? u_begin + 2 : u_begin) : N / 8;
+  for (int u = u_begin; u < u_end; u += u_step) {
     const int j = u & (m8 - 1);
     const int base = ((u - j) << 3) + j;  // (u / m8) * M + j
     cplx *sp = s + wb_sidx(base);
@@ -245,9 +250,33 @@ __device__ __forceinline__ void wb_pass_dit16(cplx *s, const cplx *__restrict__ 
   }
 }
 
+// Warp-local late passes (template flag WL of the plans below).  With ONE radix-R butterfly per thread and pass
+// (N / R <= blockDim, butterfly u on thread u), the butterflies of a sub-block of M <= 32 R points sit on M / R
+// consecutive threads of one warp, and so do all butterflies of the later (DIF) / earlier (DIT) passes inside that
+// sub-block: between those passes __syncwarp() orders the shared-memory traffic and the block-wide barrier is
+// only needed around the passes that span warps.  The radix-8 / 4 / 2 clean-up pass has more butterflies than
+// threads; in WL mode thread t takes the ones inside its own R consecutive points [R t, R (t + 1)).
+// OWN = points per thread = R of the plan; RL = radix of the clean-up pass.
+template <int OWN, int RL>
+__device__ __forceinline__ int wb_wl_first(int k) { return (int)threadIdx.x * (OWN / RL) + k; }
+
 // final radix-4 / radix-2 pass (sub-block size 4 or 2: no twiddles)
-template <int SIGN, int N>
+template <int SIGN, int N, int OWN = 0>
 __device__ __forceinline__ void wb_pass_dif4_last(cplx *s) {
+  if constexpr (OWN > 0) {
+    if ((int)threadIdx.x < N / OWN) {
+#pragma unroll
+      for (int k = 0; k < OWN / 4; ++k) {
+        cplx *sp = s + wb_sidx(4 * wb_wl_first<OWN, 4>(k));
+        cplx a[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a[q] = sp[q];
+        wb_dft4<SIGN>(a);
+        sp[0] = a[0]; sp[1] = a[2]; sp[2] = a[1]; sp[3] = a[3];
+      }
+    }
+    return;
+  }
   for (int u = threadIdx.x; u < N / 4; u += blockDim.x) {
     cplx *sp = s + wb_sidx(4 * u);
     cplx a[4];
@@ -257,8 +286,20 @@ __device__ __forceinline__ void wb_pass_dif4_last(cplx *s) {
     sp[0] = a[0]; sp[1] = a[2]; sp[2] = a[1]; sp[3] = a[3];
   }
 }
-template <int SIGN, int N>
+template <int SIGN, int N, int OWN = 0>
 __device__ __forceinline__ void wb_pass_dif2_last(cplx *s) {
+  if constexpr (OWN > 0) {
+    if ((int)threadIdx.x < N / OWN) {
+#pragma unroll
+      for (int k = 0; k < OWN / 2; ++k) {
+        cplx *sp = s + wb_sidx(2 * wb_wl_first<OWN, 2>(k));
+        const cplx a0 = sp[0], a1 = sp[1];
+        sp[0] = wb_cadd(a0, a1);
+        sp[1] = wb_csub(a0, a1);
+      }
+    }
+    return;
+  }
   for (int u = threadIdx.x; u < N / 2; u += blockDim.x) {
     cplx *sp = s + wb_sidx(2 * u);
     const cplx a0 = sp[0], a1 = sp[1];
@@ -268,10 +309,14 @@ __device__ __forceinline__ void wb_pass_dif2_last(cplx *s) {
 }
 
 // ---- DIT passes (transpose of the above) --------------------------------------------
-template <int SIGN, int N, int M>
+template <int SIGN, int N, int M, bool OWN16 = false>
 __device__ __forceinline__ void wb_pass_dit8(cplx *s, const cplx *__restrict__ T) {
   constexpr int m8 = M / 8, tstep = 2 * N / M;
-  for (int u = threadIdx.x; u < N / 8; u += blockDim.x) {
+  static_assert(!OWN16 || M == 8, "ownership mapping is for the twiddle-free first pass");
+  const int u_begin = OWN16 ? 2 * (int)threadIdx.x : (int)threadIdx.x;
+  const int u_step = OWN16 ? 1 : (int)blockDim.x;
+  const int u_end = OWN16 ? (((int)threadIdx.x < N / 16) ? u_begin + 2 : u_begin) : N / 8;
+  for (int u = u_begin; u < u_end; u += u_step) {
     const int j = u & (m8 - 1);
     const int base = ((u - j) << 3) + j;
     cplx *sp = s + wb_sidx(base);
@@ -290,8 +335,22 @@ __device__ __forceinline__ void wb_pass_dit8(cplx *s, const cplx *__restrict__ T
     for (int p = 0; p < 8; ++p) sp[WB_OFF(p, m8)] = a[p];
   }
 }
-template <int SIGN, int N>
+template <int SIGN, int N, int OWN = 0>
 __device__ __forceinline__ void wb_pass_dit4_first(cplx *s) {
+  if constexpr (OWN > 0) {
+    if ((int)threadIdx.x < N / OWN) {
+#pragma unroll
+      for (int k = 0; k < OWN / 4; ++k) {
+        cplx *sp = s + wb_sidx(4 * wb_wl_first<OWN, 4>(k));
+        cplx a[4];
+        a[0] = sp[0]; a[2] = sp[1]; a[1] = sp[2]; a[3] = sp[3];
+        wb_dft4<SIGN>(a);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) sp[p] = a[p];
+      }
+    }
+    return;
+  }
   for (int u = threadIdx.x; u < N / 4; u += blockDim.x) {
     cplx *sp = s + wb_sidx(4 * u);
     cplx a[4];
@@ -301,8 +360,20 @@ __device__ __forceinline__ void wb_pass_dit4_first(cplx *s) {
     for (int p = 0; p < 4; ++p) sp[p] = a[p];
   }
 }
-template <int SIGN, int N>
+template <int SIGN, int N, int OWN = 0>
 __device__ __forceinline__ void wb_pass_dit2_first(cplx *s) {
+  if constexpr (OWN > 0) {
+    if ((int)threadIdx.x < N / OWN) {
+#pragma unroll
+      for (int k = 0; k < OWN / 2; ++k) {
+        cplx *sp = s + wb_sidx(2 * wb_wl_first<OWN, 2>(k));
+        const cplx a0 = sp[0], a1 = sp[1];
+        sp[0] = wb_cadd(a0, a1);
+        sp[1] = wb_csub(a0, a1);
+      }
+    }
+    return;
+  }
   for (int u = threadIdx.x; u < N / 2; u += blockDim.x) {
     cplx *sp = s + wb_sidx(2 * u);
     const cplx a0 = sp[0], a1 = sp[1];
@@ -320,43 +391,55 @@ __device__ __forceinline__ void wb_pass_dit2_first(cplx *s) {
 #ifndef WB_FFT_DEFAULT_RADIX
 #define WB_FFT_DEFAULT_RADIX 8
 #endif
-template <int SIGN, int N, int M, int R>
+// sync between the pass that has just produced sub-blocks of M / R points... (WL: see above)
+template <bool WARP>
+__device__ __forceinline__ void wb_fft_sync() {
+  if constexpr (WARP) __syncwarp(); else __syncthreads();
+}
+
+template <int SIGN, int N, int M, int R, bool WL = false>
 struct WbDifPasses {
   template <typename In>
   static __device__ __forceinline__ void run(cplx *s, const cplx *__restrict__ T, In in) {
+    // after a pass over sub-blocks of M points the next pass works inside sub-blocks of M / radix points: warp-local
+    // when the M-point sub-block already sits on one warp (M <= 32 R) -- except after the LAST pass (callers
+    // read across the whole transform)
     if constexpr (R == 16 && M >= 16) {
       wb_pass_dif16<SIGN, N, M>(s, T, in);
-      __syncthreads();
-      WbDifPasses<SIGN, N, M / 16, R>::run(s, T, WbFromSlots());
+      wb_fft_sync<(WL && M <= 32 * 16 && M > 16)>();
+      WbDifPasses<SIGN, N, M / 16, R, WL>::run(s, T, WbFromSlots());
     } else {
       static_assert(M >= 8 || std::is_same<In, WbFromSlots>::value, "fused input needs N >= 8");
       if constexpr (M >= 8) {
-        wb_pass_dif8<SIGN, N, M>(s, T, in);
-        __syncthreads();
-        WbDifPasses<SIGN, N, M / 8, R>::run(s, T, WbFromSlots());
+        constexpr bool own16 = WL && R == 16 && M == 8;        // clean-up pass of the radix-16 plan
+        wb_pass_dif8<SIGN, N, M, In, own16>(s, T, in);
+        wb_fft_sync<(WL && R == 8 && M <= 32 * 8 && M > 8)>();
+        WbDifPasses<SIGN, N, M / 8, R, WL>::run(s, T, WbFromSlots());
       } else if constexpr (M == 4) {
-        wb_pass_dif4_last<SIGN, N>(s);
+        wb_pass_dif4_last<SIGN, N, (WL ? R : 0)>(s);
         __syncthreads();
       } else if constexpr (M == 2) {
-        wb_pass_dif2_last<SIGN, N>(s);
+        wb_pass_dif2_last<SIGN, N, (WL ? R : 0)>(s);
         __syncthreads();
       }
     }
   }
 };
 
-template <int SIGN, int N, int M, int R>  // M = sub-block size produced by the passes done so far
+template <int SIGN, int N, int M, int R, bool WL = false>  // M = sub-block size produced by the passes done so far
 struct WbDitPasses {
   static __device__ __forceinline__ void run(cplx *s, const cplx *__restrict__ T) {
     if constexpr (M < N) {
+      // the pass below reads sub-blocks of M points and produces sub-blocks of M R points; the pass after it is
+      // warp-local with it when those M R points sit on one warp and it is not the last pass
       if constexpr (R == 16) {
         wb_pass_dit16<SIGN, N, M * 16>(s, T);
-        __syncthreads();
-        WbDitPasses<SIGN, N, M * 16, R>::run(s, T);
+        wb_fft_sync<(WL && M * 16 * 16 <= 32 * 16 && M * 16 < N)>();
+        WbDitPasses<SIGN, N, M * 16, R, WL>::run(s, T);
       } else {
         wb_pass_dit8<SIGN, N, M * 8>(s, T);
-        __syncthreads();
-        WbDitPasses<SIGN, N, M * 8, R>::run(s, T);
+        wb_fft_sync<(WL && M * 8 * 8 <= 32 * 8 && M * 8 < N)>();
+        WbDitPasses<SIGN, N, M * 8, R, WL>::run(s, T);
       }
     }
   }
@@ -365,33 +448,35 @@ struct WbDitPasses {
 // ---- complex transforms: N = 2^LOG2N points, table T with 2N entries -------------------------
 // natural order in, bit-reversed order out.  Ends with __syncthreads().
 // Caller must __syncthreads() after filling `s`.
-template <int SIGN, int LOG2N, int R = WB_FFT_DEFAULT_RADIX>
+// WL (all transforms below): warp-local late passes, see above; the caller guarantees N / R <= blockDim.
+template <int SIGN, int LOG2N, int R = WB_FFT_DEFAULT_RADIX, bool WL = false>
 __device__ __forceinline__ void wb_cfft_dif_t(cplx *s, const cplx *__restrict__ T) {
-  WbDifPasses<SIGN, (1 << LOG2N), (1 << LOG2N), R>::run(s, T, WbFromSlots());
+  WbDifPasses<SIGN, (1 << LOG2N), (1 << LOG2N), R, WL>::run(s, T, WbFromSlots());
 }
 
 // Radix-16 plan with element i of the input coming from in(i, q) instead of the slots (LOG2N >= 4).  The slots
 // are only written: the caller must make sure nobody still reads them (a __syncthreads() after their last use).
-template <int SIGN, int LOG2N, int R = 16, typename In>
+template <int SIGN, int LOG2N, int R = 16, bool WL = false, typename In>
 __device__ __forceinline__ void wb_cfft_dif_in_t(cplx *s, const cplx *__restrict__ T, In in) {
-  WbDifPasses<SIGN, (1 << LOG2N), (1 << LOG2N), R>::run(s, T, in);
+  WbDifPasses<SIGN, (1 << LOG2N), (1 << LOG2N), R, WL>::run(s, T, in);
 }
 
 // bit-reversed order in, natural order out.  Ends with __syncthreads().
-template <int SIGN, int LOG2N, int R = WB_FFT_DEFAULT_RADIX>
+template <int SIGN, int LOG2N, int R = WB_FFT_DEFAULT_RADIX, bool WL = false>
 __device__ __forceinline__ void wb_cfft_dit_t(cplx *s, const cplx *__restrict__ T) {
   constexpr int N = 1 << LOG2N;
+  // (the pass after the clean-up pass works inside sub-blocks of at most 128 points: always on one warp)
   if constexpr (R == 16) {
     constexpr int rem = LOG2N % 4;
-    if constexpr (rem == 3) { wb_pass_dit8<SIGN, N, 8>(s, T); __syncthreads(); }
-    if constexpr (rem == 2) { wb_pass_dit4_first<SIGN, N>(s); __syncthreads(); }
-    if constexpr (rem == 1) { wb_pass_dit2_first<SIGN, N>(s); __syncthreads(); }
-    WbDitPasses<SIGN, N, (1 << rem), R>::run(s, T);
+    if constexpr (rem == 3) { wb_pass_dit8<SIGN, N, 8, WL>(s, T); wb_fft_sync<(WL && N > 8)>(); }
+    if constexpr (rem == 2) { wb_pass_dit4_first<SIGN, N, (WL ? 16 : 0)>(s); wb_fft_sync<(WL && N > 4)>(); }
+    if constexpr (rem == 1) { wb_pass_dit2_first<SIGN, N, (WL ? 16 : 0)>(s); wb_fft_sync<(WL && N > 2)>(); }
+    WbDitPasses<SIGN, N, (1 << rem), R, WL>::run(s, T);
   } else {
     constexpr int rem = LOG2N % 3;
-    if constexpr (rem == 2) { wb_pass_dit4_first<SIGN, N>(s); __syncthreads(); }
-    if constexpr (rem == 1) { wb_pass_dit2_first<SIGN, N>(s); __syncthreads(); }
-    WbDitPasses<SIGN, N, (1 << rem), R>::run(s, T);
+    if constexpr (rem == 2) { wb_pass_dit4_first<SIGN, N, (WL ? 8 : 0)>(s); wb_fft_sync<(WL && N > 4)>(); }
+    if constexpr (rem == 1) { wb_pass_dit2_first<SIGN, N, (WL ? 8 : 0)>(s); wb_fft_sync<(WL && N > 2)>(); }
+    WbDitPasses<SIGN, N, (1 << rem), R, WL>::run(s, T);
   }
 }
 
@@ -403,10 +488,10 @@ __device__ __forceinline__ int wb_brev(int k, int bits) { return (int)(__brev((u
 // After the complex DIF transform, `emit(k, X)` is called exactly once for every k = 0..NC
 // (X[k] of the real transform, forward sign).  T has 2 NC entries.
 // The slots are left untouched by the post-processing (emit must not write to s).
-template <int SIGN, int LOG2NC, int R = WB_FFT_DEFAULT_RADIX, typename Emit>
+template <int SIGN, int LOG2NC, int R = WB_FFT_DEFAULT_RADIX, bool WL = false, typename Emit>
 __device__ __forceinline__ void wb_rfft_t(cplx *s, const cplx *__restrict__ T, Emit emit) {
   constexpr int NC = 1 << LOG2NC;
-  wb_cfft_dif_t<SIGN, LOG2NC, R>(s, T);
+  wb_cfft_dif_t<SIGN, LOG2NC, R, WL>(s, T);
   for (int k = threadIdx.x; k <= (NC >> 1); k += blockDim.x) {
     if (k == 0) {
       const cplx z = s[0];
@@ -429,7 +514,7 @@ __device__ __forceinline__ void wb_rfft_t(cplx *s, const cplx *__restrict__ T, E
 // c2r (SIGN = -1 for the reference's backward transform): `get(k)` returns X[k] for
 // k = 0..NC (Hermitian half; imaginary parts of X[0], X[NC] are ignored like Ooura's
 // rdft).  On return real output sample j is at double index wb_didx(j) of `s`.
-template <int SIGN, int LOG2NC, int R = WB_FFT_DEFAULT_RADIX, typename Get>
+template <int SIGN, int LOG2NC, int R = WB_FFT_DEFAULT_RADIX, bool WL = false, typename Get>
 __device__ __forceinline__ void wb_irfft_t(cplx *s, const cplx *__restrict__ T, Get get) {
   constexpr int NC = 1 << LOG2NC;
   for (int k = threadIdx.x; k <= (NC >> 1); k += blockDim.x) {
@@ -446,7 +531,7 @@ __device__ __forceinline__ void wb_irfft_t(cplx *s, const cplx *__restrict__ T, 
     }
   }
   __syncthreads();
-  wb_cfft_dit_t<SIGN, LOG2NC, R>(s, T);
+  wb_cfft_dit_t<SIGN, LOG2NC, R, WL>(s, T);
 }
 
 // ---- host-side dispatch helper: call F.template operator()<LOG2N>() for a runtime log2n ------

@@ -336,7 +336,8 @@ __global__ void __launch_bounds__(CH_THREADS, 3) channel_kernel(ChanParams p) {
   const int h = p.half_len[c];
   const cplx *H = p.Hc + (size_t)c * (NC + 1);
   const cplx *Y = p.Yb + (size_t)b * (NC + 1);
-  wb_irfft_t<-1, LOG2NB - 1, 16>(S, p.tw, [&](int k) {
+  // (one radix-16 butterfly per thread and pass when the block spectrum has 4096 complex points: warp-local late passes)
+  wb_irfft_t<-1, LOG2NB - 1, 16, (NC / 16 <= CH_THREADS)>(S, p.tw, [&](int k) {
     const cplx yv = Y[k], hv = H[k];
     return make_double2(yv.x * hv.x - yv.y * hv.y, yv.x * hv.y + yv.y * hv.x);
   });

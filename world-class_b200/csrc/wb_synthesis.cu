@@ -508,7 +508,7 @@ __global__ void pulse_range_kernel(const int *__restrict__ pulse_index, const in
 // MinimumPhaseAnalysis::compute (world_common.cpp:192-233).  On entry the packed real view W of
 // S holds log_spectrum[0..NC] (this function mirrors it); on exit MP[k], k = 0..NC, holds the
 // minimum phase spectrum.  S needs wb_fft_slots(N) slots.
-template <int LOG2N>
+template <int LOG2N, bool WL = false>
 __device__ __forceinline__ void minimum_phase(cplx *S, cplx *MP, const cplx *tw_n, const cplx *tw_2n) {
   constexpr int N = 1 << LOG2N, NC = N / 2, log2n = LOG2N;
   double *W = reinterpret_cast<double *>(S);
@@ -519,12 +519,12 @@ __device__ __forceinline__ void minimum_phase(cplx *S, cplx *MP, const cplx *tw_
   // imaginary parts that are pure rounding noise (~1e-16 of the real parts) into its complex N-point transform.
   // Dropping them makes the folded cepstrum a REAL sequence with a zero upper half, and its first N/2 + 1 bins
   // come from a real transform (a half-size complex FFT) instead of a full complex one.
-  wb_rfft_t<1, LOG2N - 1>(S, tw_n, [&](int k, cplx X) {
+  wb_rfft_t<1, LOG2N - 1, WB_FFT_DEFAULT_RADIX, WL>(S, tw_n, [&](int k, cplx X) {
     MP[k].x = (k == 0 || k == NC) ? X.x : X.x * 2.0;
   });
   for (int i = threadIdx.x; i < N; i += blockDim.x) W[wb_didx(i)] = (i <= NC) ? MP[i].x : 0.0;
   __syncthreads();
-  wb_rfft_t<1, LOG2N - 1>(S, tw_n, [&](int k, cplx X) {   // first half of the reference's c2c FFT_FORWARD
+  wb_rfft_t<1, LOG2N - 1, WB_FFT_DEFAULT_RADIX, WL>(S, tw_n, [&](int k, cplx X) {   // first half of the reference's c2c FFT_FORWARD
     const double tmp = exp(X.x / N);
     double sn, cs;
     sincos(X.y / N, &sn, &cs);
@@ -538,6 +538,7 @@ template <int LOG2N>
 __global__ void __launch_bounds__(256, 3) response_kernel(RespParams p) {
   extern __shared__ double2 smem_raw[];
   constexpr int N = 1 << LOG2N, NC = N / 2, bins = NC + 1;
+  constexpr bool WL = (NC / 8 <= 256);        // one radix-8 butterfly per thread and pass (256 threads): warp-local late passes
   const int binsp = (bins + 1) & ~1;
   cplx *S = smem_raw;                         // wb_fft_slots(N)
   cplx *MP = S + wb_fft_slots(N);             // bins: minimum-phase spectrum (x noise spectrum for the aperiodic part)
@@ -595,9 +596,9 @@ __global__ void __launch_bounds__(256, 3) response_kernel(RespParams p) {
     if (periodic_on) {
       for (int k = tid; k < bins; k += nt) W[wb_didx(k)] = log(SE[k] * (1.0 - AR[k]) + WB_SAFEGUARD) / 2.0;
       __syncthreads();
-      minimum_phase<LOG2N>(S, MP, p.tw_n, p.tw_2n);
+      minimum_phase<LOG2N, WL>(S, MP, p.tw_n, p.tw_2n);
       const double coefficient = 2.0 * WB_PI * frac_shift * p.fs / N;
-      wb_irfft_t<-1, LOG2N - 1>(S, p.tw_n, [&](int k) {
+      wb_irfft_t<-1, LOG2N - 1, WB_FFT_DEFAULT_RADIX, WL>(S, p.tw_n, [&](int k) {
         const cplx v = MP[k];
         const double re2 = cos(coefficient * k);
         const double im2 = sqrt(1.0 - re2 * re2);  // Q8: always >= 0
@@ -629,17 +630,17 @@ __global__ void __launch_bounds__(256, 3) response_kernel(RespParams p) {
         for (int k = tid; k < bins; k += nt) W[wb_didx(k)] = log(SE[k]) / 2.0;
       }
       __syncthreads();
-      minimum_phase<LOG2N>(S, MP, p.tw_n, p.tw_2n);
+      minimum_phase<LOG2N, WL>(S, MP, p.tw_n, p.tw_2n);
       double part = 0.0;
       for (int i = tid; i < noise_size; i += nt) part += nz[i];
       const double average = wb_block_sum(part, red) / noise_size;
       for (int i = tid; i < N; i += nt) W[wb_didx(i)] = (i < noise_size) ? nz[i] - average : 0.0;
       __syncthreads();
-      wb_rfft_t<1, LOG2N - 1>(S, p.tw_n, [&](int k, cplx X) {
+      wb_rfft_t<1, LOG2N - 1, WB_FFT_DEFAULT_RADIX, WL>(S, p.tw_n, [&](int k, cplx X) {
         const cplx a = MP[k];
         MP[k] = make_double2(a.x * X.x - a.y * X.y, a.x * X.y + a.y * X.x);
       });
-      wb_irfft_t<-1, LOG2N - 1>(S, p.tw_n, [&](int k) { return MP[k]; });
+      wb_irfft_t<-1, LOG2N - 1, WB_FFT_DEFAULT_RADIX, WL>(S, p.tw_n, [&](int k) { return MP[k]; });
     }
     // ---- combine (synthesis.cpp:339-343) with the aperiodic fftshift folded in
     const double sqrt_noise_size = sqrt((double)noise_size);
