@@ -657,14 +657,18 @@ __global__ void __launch_bounds__(RF_WARPS * 32, 3) refine_mma_kernel(RefinePara
   const int n_own = p.nc_and_count[1];
   const double fs = p.actual_fs;
   const double two_pi = 2.0 * WB_PI;
-  for (;;) {
-    int c = 0;
-    if (lane == 0) c = atomicAdd(ticket, 1);
-    c = __shfl_sync(0xffffffffu, c, 0);
-    if (c >= n_own) break;
-    const int item = p.work[c];
+  // The ticket of the NEXT candidate, its work item and its f0 are requested while the current candidate is set up and
+  // accumulated (the chain atomic -> work[] -> own[] is three dependent round trips to L2): the atomic is issued at the
+  // top of an iteration, its result is used after the set-up arithmetic, the item after the accumulation loop.
+  int c = 0;
+  if (lane == 0) c = atomicAdd(ticket, 1);
+  c = __shfl_sync(0xffffffffu, c, 0);
+  int item = c < n_own ? p.work[c] : 0;
+  double current_f0 = c < n_own ? p.own[(size_t)(item >> 5) * p.own_cap + (item & 31)] : 100.0;
+  while (c < n_own) {
     const int src = item >> 5, own_j = item & 31;
-    const double current_f0 = p.own[(size_t)src * p.own_cap + own_j];
+    int tick = 0;
+    if (lane == 0) tick = atomicAdd(ticket, 1);
     const int hw = static_cast<int>(1.5 * fs / current_f0 + 1.0);
     const int len = 2 * hw + 1;
     const double window_length_in_time = (2.0 * hw + 1.0) / fs;
@@ -706,6 +710,8 @@ __global__ void __launch_bounds__(RF_WARPS * 32, 3) refine_mma_kernel(RefinePara
       vm = rf_window(cs) * yv;
       vd = dwin * yv;
     };
+    const int c_next = __shfl_sync(0xffffffffu, tick, 0);
+    const int item_next = c_next < n_own ? p.work[c_next] : 0;
     if (symmetric) {
       // Frame times on whole decimated samples (actual_fs a multiple of 1000 Hz): the window is even and its
       // differentiated version odd about the centre sample, so the samples at +j and -j share one twiddle
@@ -714,18 +720,19 @@ __global__ void __launch_bounds__(RF_WARPS * 32, 3) refine_mma_kernel(RefinePara
       // (fixF0 only uses |main|^2 and Im(conj(main) diff), which a common phase does not change).
       // Pairs j = 1 .. hw - 2 (samples 3 .. 2 hw - 1); the five samples without a partner or with an end rule
       // (0, 1, 2, hw + 1, 2 hw) follow in two more steps.
+      // (pair index j = 0 is the centre sample itself: window 1, differentiated window 0, no partner)
       double sn, cs;
-      sincos(two_pi * (1 + t) / (2 * hw + 1), &sn, &cs);
+      sincos(two_pi * t / (2 * hw + 1), &sn, &cs);
       const int yc = y_first + i_c;
       const int n_pairs = hw - 2;
-      int j = 1 + t;
+      int j = t;
       double yp_next = 0.0, ym_next = 0.0;
       if (row_active && j <= n_pairs) {
         yp_next = p.y[wb_max_i(0, wb_min_i(y_last, yc + j))];
-        ym_next = p.y[wb_max_i(0, wb_min_i(y_last, yc - j))];
+        ym_next = j > 0 ? p.y[wb_max_i(0, wb_min_i(y_last, yc - j))] : 0.0;
       }
       cplx w_next = __ldg(&T[(idx_col * j) & mask]);
-      for (int j0 = 1; j0 <= n_pairs; j0 += 4, j += 4) {
+      for (int j0 = 0; j0 <= n_pairs; j0 += 4, j += 4) {
         const double yp = yp_next, ym = ym_next;
         const cplx w = w_next;
         const int jn = j + 4;
@@ -746,13 +753,12 @@ __global__ void __launch_bounds__(RF_WARPS * 32, 3) refine_mma_kernel(RefinePara
         sn = fma(sn, cg, cs * sg);
         cs = c2;
       }
-#pragma unroll
-      for (int step = 0; step < 2; ++step) {
-        const int i = step == 0 ? (t == 0 ? 0 : (t == 1 ? 1 : (t == 2 ? 2 : i_c))) : 2 * hw;
+      {
+        // the four samples with an end rule or without a partner: i = 0, 1, 2 and 2 hw, one per lane of the row's group
         // (hw >= 2 always: f0 <= f0_ceil * 1.1 well below 1.5 fs / 2; for tiny windows some of these coincide)
-        bool use = i < len;
-        if (step == 0 && t == 3) use = use && i > 2;
-        if (step == 1) use = use && t == 0 && i > 2 && i != i_c;
+        const int i = t < 3 ? t : 2 * hw;
+        bool use = i < len && i != i_c;
+        if (t == 3) use = use && i > 2;
         double vm = 0.0, vd = 0.0;
         if (use) sample(i, vm, vd);
         const cplx w = __ldg(&T[(idx_col * (i - i_c)) & mask]);
@@ -793,6 +799,7 @@ __global__ void __launch_bounds__(RF_WARPS * 32, 3) refine_mma_kernel(RefinePara
         cs = c2;
       }
     }
+    const double f0_next = c_next < n_own ? p.own[(size_t)(item_next >> 5) * p.own_cap + (item_next & 31)] : 100.0;
     // fixF0 (harvest.cpp:844-878) for harmonics 2t and 2t + 1 of copy g; spectra are conjugated by the reference
     // (harvest.cpp:829-841): main = (mr, -mi), diff = (dr, -di)
     double inst[2], amp[2], dev[2];
@@ -807,20 +814,29 @@ __global__ void __launch_bounds__(RF_WARPS * 32, 3) refine_mma_kernel(RefinePara
       amp[e] = sqrt(power);
       dev[e] = fabs((inst[e] / (hh + 1.0) - current_f0) / current_f0);
     }
+    // the sums over the harmonics in the reference's order (hh = 0 .. nh - 1): lane t adds its two terms to the running
+    // sums and hands them to lane t + 1 of the row's group; lane 2 ends up with the totals
     double numerator = 0.0, denominator = 0.0, score = 0.0;
 #pragma unroll
-    for (int hh = 0; hh < 6; ++hh) {
-      const int from = hh >> 1;   // lane t of the row's group of four
-      const double in_ = __shfl_sync(0xffffffffu, (hh & 1) ? inst[1] : inst[0], from, 4);
-      const double am_ = __shfl_sync(0xffffffffu, (hh & 1) ? amp[1] : amp[0], from, 4);
-      const double de_ = __shfl_sync(0xffffffffu, (hh & 1) ? dev[1] : dev[0], from, 4);
-      if (hh < nh) {
-        numerator += am_ * in_;
-        denominator += am_ * (hh + 1.0);
-        score += de_;
+    for (int hop = 0; hop < 3; ++hop) {
+      if (hop > 0) {
+        numerator = __shfl_up_sync(0xffffffffu, numerator, 1, 4);
+        denominator = __shfl_up_sync(0xffffffffu, denominator, 1, 4);
+        score = __shfl_up_sync(0xffffffffu, score, 1, 4);
+      }
+      if (t == hop) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int hh = 2 * hop + e;
+          if (hh < nh) {
+            numerator += amp[e] * inst[e];
+            denominator += amp[e] * (hh + 1.0);
+            score += dev[e];
+          }
+        }
       }
     }
-    if (t == 0 && row_active) {
+    if (t == 2 && row_active) {
       double refined = numerator / (denominator + WB_SAFEGUARD);
       double sc = 1.0 / (score / nh + WB_SAFEGUARD);
       if (refined < p.f0_floor || refined > p.f0_ceil || sc < 2.5) { refined = 0.0; sc = 0.0; }
@@ -828,49 +844,64 @@ __global__ void __launch_bounds__(RF_WARPS * 32, 3) refine_mma_kernel(RefinePara
       p.cand[at] = refined;
       p.score[at] = sc;
     }
+    c = c_next; item = item_next; current_f0 = f0_next;
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // removeUnreliableCandidates (harvest.cpp:708-744): one thread per (frame, slot)
 // ---------------------------------------------------------------------------------------------
-__global__ void remove_kernel(const double *__restrict__ cand_in, const double *__restrict__ score_in,
-                              const int *__restrict__ nc_ptr, int f0_length, int max_candidates,
-                              double *__restrict__ cand_out, double *__restrict__ score_out) {
-  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= (long long)f0_length * max_candidates) return;
-  const int i = (int)(g / max_candidates), j = (int)(g % max_candidates);
+// RM_FRAMES frames per CTA: the candidate rows of the tile and of its two neighbours are staged in shared memory once
+// (a neighbour row is scanned by every slot of the frames next to it).
+#define RM_FRAMES 8
+#define RM_THREADS 256
+__global__ void __launch_bounds__(RM_THREADS) remove_kernel(const double *__restrict__ cand_in, const double *__restrict__ score_in,
+                                                            const int *__restrict__ nc_ptr, int f0_length, int max_candidates,
+                                                            double *__restrict__ cand_out, double *__restrict__ score_out) {
+  extern __shared__ double rm_rows[];   // [RM_FRAMES + 2][nc7]: frames first - 1 .. first + RM_FRAMES
   const int nc7 = *nc_ptr * 7;
-  if (j >= nc7) {  // beyond the populated slots: nothing was ever stored there
-    cand_out[g] = 0.0;
-    score_out[g] = 0.0;
-    return;
+  const int first = blockIdx.x * RM_FRAMES;
+  const int n_frames = min(RM_FRAMES, f0_length - first);
+  for (int e = threadIdx.x; e < (RM_FRAMES + 2) * nc7; e += RM_THREADS) {
+    const int r = e / nc7, k = e - r * nc7;
+    const int frame = first - 1 + r;
+    // tmp_f0_candidates_ rows 0 and f0_length-1 are never filled (zero)
+    const bool live = frame > 0 && frame < f0_length - 1;
+    rm_rows[e] = live ? cand_in[(size_t)frame * max_candidates + k] : 0.0;
   }
-  double c = cand_in[g], s = score_in[g];
-  if (i >= 1 && i < f0_length - 1 && c != 0) {
-    const double reference_f0 = c;
-    double err[2];
-#pragma unroll
-    for (int side = 0; side < 2; ++side) {
-      const int nb = (side == 0) ? i + 1 : i - 1;
-      // tmp_f0_candidates_ rows 0 and f0_length-1 are never filled (zero)
-      const bool zero_row = (nb == 0 || nb == f0_length - 1);
-      const double *row = cand_in + (size_t)nb * max_candidates;
-      // min_k fl(|ref - v_k| / ref) = fl(min_k |ref - v_k| / ref): rounded division by a positive
-      // constant is monotone, so one division reproduces selectBestF0's running minimum bit for bit
-      double dmin = fabs(reference_f0 - (zero_row ? 0.0 : row[0]));
-      for (int k = 1; k < nc7; ++k) {
-        const double d = fabs(reference_f0 - (zero_row ? 0.0 : row[k]));
-        dmin = d < dmin ? d : dmin;
-      }
-      const double e = dmin / reference_f0;
-      err[side] = e > 1.0 ? 1.0 : e;
+  __syncthreads();
+  for (int e = threadIdx.x; e < n_frames * max_candidates; e += RM_THREADS) {
+    const int fi = e / max_candidates, j = e - fi * max_candidates;
+    const int i = first + fi;
+    const size_t g = (size_t)i * max_candidates + j;
+    if (j >= nc7) {  // beyond the populated slots: nothing was ever stored there
+      cand_out[g] = 0.0;
+      score_out[g] = 0.0;
+      continue;
     }
-    const double min_error = err[0] < err[1] ? err[0] : err[1];
-    if (min_error > 0.05) { c = 0; s = 0; }
+    double c = cand_in[g], sc = score_in[g];
+    if (i >= 1 && i < f0_length - 1 && c != 0) {
+      const double reference_f0 = c;
+      double err[2];
+#pragma unroll
+      for (int side = 0; side < 2; ++side) {
+        const double *row = rm_rows + (size_t)(fi + (side == 0 ? 2 : 0)) * nc7;   // frame i + 1 / i - 1
+        // min_k fl(|ref - v_k| / ref) = fl(min_k |ref - v_k| / ref): rounded division by a positive
+        // constant is monotone, so one division reproduces selectBestF0's running minimum bit for bit
+        double dmin = fabs(reference_f0 - row[0]);
+        for (int k = 1; k < nc7; ++k) {
+          const double d = fabs(reference_f0 - row[k]);
+          dmin = d < dmin ? d : dmin;
+        }
+        const double e2 = dmin / reference_f0;
+        err[side] = e2 > 1.0 ? 1.0 : e2;
+      }
+      const double min_error = err[0] < err[1] ? err[0] : err[1];
+      if (min_error > 0.05) { c = 0; sc = 0; }
+    }
+    cand_out[g] = c;
+    score_out[g] = sc;
   }
-  cand_out[g] = c;
-  score_out[g] = s;
 }
 
 int ilog2_exact(int n) {
@@ -1111,7 +1142,8 @@ int wb_harvest_run_basic(WbHarvestPlan *pl, WbWorkspace *ws, const double *d_x, 
     }
     WB_CUDA_CHECK(cudaGetLastError());
   }
-  WB_LAUNCH("remove_kernel", remove_kernel<<<(unsigned)((n_cs + 255) / 256), 256, 0, stream>>>(d_candA, d_scoreA, d_nc, Lb, MC, d_candB, d_scoreB));
+  (void)n_cs;
+  WB_LAUNCH("remove_kernel", remove_kernel<<<(Lb + RM_FRAMES - 1) / RM_FRAMES, RM_THREADS, sizeof(double) * (RM_FRAMES + 2) * MC, stream>>>(d_candA, d_scoreA, d_nc, Lb, MC, d_candB, d_scoreB));
   WB_CUDA_CHECK(cudaGetLastError());
 
   // ---- contour fixing + smoothing
