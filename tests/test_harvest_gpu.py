@@ -58,3 +58,34 @@ def test_harvest_matches_reference(wb, signals, fs, seconds, seed):
     err = float(np.max(np.abs(f0[v] - ref["f0"][v]) / ref["f0"][v]))
     print("harvest fs=%d voiced %d/%d max rel err %.3e" % (fs, v.sum(), len(v), err))
     assert err < RTOL
+
+
+def test_harvest_is_a_function_of_its_input_alone(wb, signals):
+    """Grow-only workspaces keep stale data beyond the current sizes, and the refinement hands out work through
+    atomics: the contour must not depend on either (same segment on a fresh object, twice, after a longer and after
+    a shorter input)."""
+    import torch
+    fs = 16000
+    a = torch.from_numpy(signals.synth_speech(fs, 2.0, seed=30)).cuda()
+    b = torch.from_numpy(signals.synth_speech(fs, 3.5, seed=31)).cuda()
+    c = torch.from_numpy(signals.synth_speech(fs, 0.7, seed=32)).cuda()
+    opt = wb.HarvestOption(f0_floor=40.0, frame_period=5.0)
+
+    def run(h, x):
+        n = h.getSamples(fs, x.numel())
+        t = torch.empty(n, dtype=torch.float64, device="cuda")
+        f = torch.empty(n, dtype=torch.float64, device="cuda")
+        wb._check(wb.lib().wb_harvest_compute_dev(h._h, x.data_ptr(), x.numel(), t.data_ptr(), f.data_ptr(), None), "harvest")
+        wb.device_synchronize()
+        return f.cpu().numpy()
+
+    h1 = wb.Harvest(fs, opt)
+    f1, f1b = run(h1, a), run(h1, a)
+    h2 = wb.Harvest(fs, opt)
+    run(h2, b)
+    f2 = run(h2, a)
+    h3 = wb.Harvest(fs, opt)
+    run(h3, c)
+    f3 = run(h3, a)
+    assert (f1 > 0).sum() > 50
+    assert np.array_equal(f1, f1b) and np.array_equal(f1, f2) and np.array_equal(f1, f3)
