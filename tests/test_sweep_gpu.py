@@ -115,3 +115,43 @@ def test_empty_and_bad_arguments(wb):
     ct = wb.CheapTrick(16000)
     sp = ct.compute(np.zeros(100), np.zeros(0), np.zeros(0))   # zero frames: nothing to do
     assert sp.shape == (0, ct.fft_size // 2 + 1)
+
+
+def test_create_time_validation_and_async_error_reporting(wb, signals):
+    """Options are checked when a handle is created (NaN / zero periods, floors above ceilings, FFT sizes that are
+    not powers of two); conditions a kernel of an ASYNCHRONOUS call cannot handle are flagged on the device and
+    readable afterwards."""
+    import torch
+    from worldb200 import tensors as wt
+    fs = 16000
+    for bad in (wb.HarvestOption(frame_period=0.0), wb.HarvestOption(frame_period=float("nan")),
+                wb.HarvestOption(f0_floor=900.0, f0_ceil=800.0), wb.HarvestOption(f0_floor=-1.0)):
+        with pytest.raises(wb.WorldB200Error):
+            wb.Pipeline(fs, bad)
+        with pytest.raises(wb.WorldB200Error):
+            wb.Harvest(fs, bad)
+    with pytest.raises(wb.WorldB200Error):
+        wb.Pipeline(fs, None, wb.CheapTrickOption(fft_size=1000))
+    with pytest.raises(wb.WorldB200Error):
+        wb.CheapTrick(fs, wb.CheapTrickOption(fft_size=1000))
+    with pytest.raises(wb.WorldB200Error):
+        wb.Pipeline(fs, None, None, wb.D4COption(threshold=float("nan")))
+    # a too small f0 bound makes the synthesis kernels drop pulses: the asynchronous tensor call cannot return that ...
+    x = signals.synth_speech(fs, 1.0, seed=40)
+    out = wb.Pipeline(fs, wb.HarvestOption(f0_floor=40.0, frame_period=5.0), wb.CheapTrickOption(f0_floor=71.0)).run(x)
+    f0, sp, ap = (torch.from_numpy(out[k]).cuda() for k in ("f0", "sp", "ap"))
+    wt.check_errors()                                            # nothing pending
+    y_ok = wt.synthesis(f0, sp, ap, fs, 5.0, f0_upper_bound=900.0)
+    wt.check_errors()
+    wt.synthesis(f0, sp, ap, fs, 5.0, f0_upper_bound=20.0)       # far below the contour (~140 Hz)
+    with pytest.raises(wb.WorldB200Error):
+        wt.check_errors()                                        # ... but it is there to be asked for
+    wt.check_errors()                                            # and cleared by the query
+    assert float(y_ok.abs().max()) > 0.05
+    # debug_read is bounded by the buffer it names
+    pl = wb.Pipeline(fs, wb.HarvestOption(f0_floor=40.0, frame_period=5.0))
+    pl.run(x)
+    with pytest.raises(wb.WorldB200Error):
+        pl.debug_read("no_such_buffer", (4,))
+    with pytest.raises(wb.WorldB200Error):
+        pl.debug_read("hv_nc", (1 << 20,), dtype=np.int32)
