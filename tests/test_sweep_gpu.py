@@ -143,7 +143,8 @@ def test_create_time_validation_and_async_error_reporting(wb, signals):
     wt.check_errors()                                            # nothing pending
     y_ok = wt.synthesis(f0, sp, ap, fs, 5.0, f0_upper_bound=900.0)
     wt.check_errors()
-    wt.synthesis(f0, sp, ap, fs, 5.0, f0_upper_bound=20.0)       # far below the contour (~140 Hz)
+    f0_high = torch.full_like(f0, 760.0)                         # more pulses than a bound of 500 Hz (the unvoiced rate) allows for
+    wt.synthesis(f0_high, sp, ap, fs, 5.0, f0_upper_bound=100.0)
     with pytest.raises(wb.WorldB200Error):
         wt.check_errors()                                        # ... but it is there to be asked for
     wt.check_errors()                                            # and cleared by the query
