@@ -92,3 +92,33 @@ def test_streaming_synthesis_small_output_buffers_and_errors(wb, signals):
     with pytest.raises(wb.WorldB200Error):
         wb.SynthesisStream(fs, 1000, 5.0)                  # not a power of two
     wb.randn_reseed()
+
+
+def test_pinned_contiguous_matrices_take_the_direct_pipelined_path(wb, signals):
+    """Page-locked, contiguous caller matrices are DMAed directly and Synthesis::compute renders sample ranges under the
+    remaining uploads (four ranges, each with its own pulses at their whole-waveform noise positions): the waveform and
+    the randn() state afterwards equal the ordinary path's (separately allocated / pageable rows) bit for bit; the same
+    for the outputs of CheapTrick::compute / D4C::compute written straight into page-locked memory."""
+    import torch
+    fs = 48000
+    x = signals.synth_speech(fs, 2.0, seed=9)
+    tpos, f0 = wb.Harvest(fs, wb.HarvestOption(f0_floor=40.0, frame_period=5.0)).compute(x)
+    ct = wb.CheapTrick(fs, wb.CheapTrickOption(f0_floor=71.0))
+    d4 = wb.D4C(fs, wb.D4COption(threshold=0.85))
+    L, bins = len(f0), ct.fft_size // 2 + 1
+    ny = wb.synthesis_length(L, 5.0, fs)
+    pin = lambda *shape: torch.empty(shape, dtype=torch.float64).pin_memory().numpy()
+    res = []
+    for pinned in (False, True):
+        wb.randn_reseed()
+        sp = pin(L, bins) if pinned else np.empty((L, bins))
+        ap = pin(L, bins) if pinned else np.empty((L, bins))
+        y = pin(ny) if pinned else np.empty(ny)
+        ct.compute(x, tpos, f0, sp)
+        d4.compute(x, tpos, f0, ct.fft_size, ap)
+        wb.Synthesis(fs, ct.fft_size, 5.0).compute(f0, sp, ap, ny, y)
+        res.append((sp.copy(), ap.copy(), y.copy(), wb.randn_get_state()))
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    assert np.array_equal(res[0][2], res[1][2])
+    assert res[0][3] == res[1][3]
+    assert np.abs(res[0][2]).max() > 0.05

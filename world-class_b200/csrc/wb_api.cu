@@ -76,6 +76,7 @@ struct HostTrace {
 // staged through pinned memory in a few chunks: the DMA of chunk k+1 overlaps the (multi-threaded)
 // host memcpy of chunk k.
 const int kRowChunks = 8;
+const int kSynRanges = 4;   // sample ranges of the pipelined host Synthesis::compute
 
 // Persistent helper threads for the row copies (spawning threads per chunk cost more than the copies).
 // Workers spin briefly between jobs -- the chunks of one matrix follow each other within microseconds --
@@ -395,13 +396,18 @@ struct wb_synthesis {
   int fft_size;
   double frame_period_ms;
   WbWorkspace ws;
-  // host-pointer compute(): the pulse list (f0 only) is built on `side` while sp / ap are still uploading
-  cudaStream_t side = nullptr;
-  cudaEvent_t ev_f0 = nullptr, ev_tb = nullptr;
+  // host-pointer compute(): the pulse list (f0 only) is built on `side` while sp / ap are still uploading; page-locked
+  // contiguous matrices are uploaded on `copy` in row ranges and every sample range is rendered as soon as its rows
+  // have landed
+  cudaStream_t side = nullptr, copy = nullptr;
+  cudaEvent_t ev_f0 = nullptr, ev_tb = nullptr, ev_rows[kSynRanges] = {nullptr}, ev_start = nullptr;
   ~wb_synthesis() {
     if (ev_f0) cudaEventDestroy(ev_f0);
     if (ev_tb) cudaEventDestroy(ev_tb);
+    if (ev_start) cudaEventDestroy(ev_start);
+    for (int c = 0; c < kSynRanges; ++c) if (ev_rows[c]) cudaEventDestroy(ev_rows[c]);
     if (side) cudaStreamDestroy(side);
+    if (copy) cudaStreamDestroy(copy);
   }
 };
 
@@ -651,9 +657,13 @@ int wb_synthesis_create(int fs, int fft_size, double frame_period_ms, wb_synthes
   wb_synthesis *h = new (std::nothrow) wb_synthesis();
   if (!h) return WB_ERR_ARG;
   h->fs = fs; h->fft_size = fft_size; h->frame_period_ms = frame_period_ms;
-  if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->ev_f0, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->ev_tb, cudaEventDisableTiming) != cudaSuccess) {
+  bool ok = cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&h->ev_f0, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&h->ev_tb, cudaEventDisableTiming) == cudaSuccess;
+  for (int c = 0; ok && c < kSynRanges; ++c) ok = cudaEventCreateWithFlags(&h->ev_rows[c], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) {
     delete h;
     return WB_ERR_CUDA;
   }
@@ -687,6 +697,55 @@ int wb_synthesis_compute(wb_synthesis_t *h, const double *f0, int f0_length, con
   double *d_out = (double *)h->ws.get("h_out", sizeof(double) * (size_t)out_length);
   if (!d_sp || !d_ap || !d_out) return WB_ERR_CUDA;
   HostTrace tr("synthesis_compute");
+  const double hop = h->frame_period_ms / 1000.0 * h->fs;   // samples per frame
+  if (rows_direct(spectrogram, f0_length, bins) && rows_direct(aperiodicity, f0_length, bins) && hop >= 1.0 &&
+      out_length >= 8 * kSynRanges * h->fft_size) {
+    // Page-locked contiguous matrices: the rows go up on the copy stream in kSynRanges row ranges (spectrogram and
+    // aperiodicity of a range back to back) and every sample range is rendered -- its own pulses at their
+    // whole-waveform noise positions, like a shard of a long stream -- as soon as the rows its pulses interpolate
+    // between have landed: the impulse responses run under the remaining uploads.
+    WbRngCursor cur = global_cursor();
+    cur.advance = false;
+    WB_CUDA_CHECK(cudaEventRecord(h->ev_f0, st));
+    WB_CUDA_CHECK(cudaStreamWaitEvent(h->side, h->ev_f0, 0));
+    if ((rc = wb_synthesis_timebase(&h->ws, h->fs, h->fft_size, h->frame_period_ms, d_f, f0_length, out_length, h->side, nullptr)))
+      return rc;
+    WB_CUDA_CHECK(cudaEventRecord(h->ev_tb, h->side));
+    WB_CUDA_CHECK(cudaEventRecord(h->ev_start, st));            // (d_sp / d_ap may still be read by the previous call's kernels)
+    WB_CUDA_CHECK(cudaStreamWaitEvent(h->copy, h->ev_start, 0));
+    int row_done = 0;
+    int s_end[kSynRanges];
+    for (int c = 0; c < kSynRanges; ++c) {
+      s_end[c] = (int)((long long)out_length * (c + 1) / kSynRanges);
+      // every frame a pulse reaching into [.., s_end) interpolates between (see StreamPlan.rows)
+      int row_hi = (c == kSynRanges - 1) ? f0_length : (int)((s_end[c] + h->fft_size) / hop) + 3;
+      if (row_hi > f0_length) row_hi = f0_length;
+      if (row_hi > row_done) {
+        const size_t off = (size_t)row_done * bins, cnt = (size_t)(row_hi - row_done) * bins;
+        WB_CUDA_CHECK(cudaMemcpyAsync(d_sp + off, spectrogram[0] + off, sizeof(double) * cnt, cudaMemcpyHostToDevice, h->copy));
+        WB_CUDA_CHECK(cudaMemcpyAsync(d_ap + off, aperiodicity[0] + off, sizeof(double) * cnt, cudaMemcpyHostToDevice, h->copy));
+        row_done = row_hi;
+      }
+      WB_CUDA_CHECK(cudaEventRecord(h->ev_rows[c], h->copy));
+    }
+    tr.mark("uploads enqueued");
+    WB_CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_tb, 0));
+    for (int c = 0; c < kSynRanges; ++c) {
+      const int s_begin = c == 0 ? 0 : s_end[c - 1];
+      WB_CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_rows[c], 0));
+      if ((rc = wb_synthesis_render_range(&h->ws, h->fs, h->fft_size, h->frame_period_ms, f0_length, d_sp, d_ap, 0, f0_length,
+                                          out_length, s_begin, s_end[c], d_out + s_begin, max_f0 + 1.0, cur, st)))
+        return rc;
+      // (each range goes home while the next one is rendered: the waveform is small next to the matrices)
+    }
+    unsigned long long *d_ncount = (unsigned long long *)h->ws.find("syn_ncount");
+    if (!d_ncount) return WB_ERR_CUDA;
+    if ((rc = wb_rng_advance(cur.state, d_ncount, nullptr, st))) return rc;   // what one compute() call draws
+    WB_CUDA_CHECK(cudaMemcpyAsync(out, d_out, sizeof(double) * out_length, cudaMemcpyDeviceToHost, st));
+    WB_CUDA_CHECK(cudaStreamSynchronize(st));
+    tr.mark("done");
+    return h->ws.read_error_flag(st);
+  }
   // pulse list + excitation noise on the side stream (needs f0 only), overlapping the row uploads below
   WbRngCursor cur = global_cursor();
   WB_CUDA_CHECK(cudaEventRecord(h->ev_f0, st));
