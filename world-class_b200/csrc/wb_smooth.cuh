@@ -11,7 +11,9 @@ __device__ inline void wb_dc_correction(double *P, double f0, int fs, int fft_si
   const int upper_limit = 2 + static_cast<int>(f0 * fft_size / fs);
   const int n_rep = upper_limit - 1;
   const double x0 = f0;  // f0 - low_frequency_axis[0]
-  const double dx = -static_cast<double>(fs) / fft_size;
+  // (xi - f0) / (-fs / fft_size) is formed as a product with -fft_size / fs: the quotient can differ in the last bit,
+  // the interpolant is continuous
+  const double inv_dx = -static_cast<double>(fft_size) / fs;
   // Each thread may own several replica points (n_rep can exceed blockDim for huge f0).
   // Read phase and write phase are separated by a barrier because both touch P[0..upper_limit].
   const int nt = blockDim.x;
@@ -19,8 +21,9 @@ __device__ inline void wb_dc_correction(double *P, double f0, int fs, int fft_si
   int cnt = 0;
   for (int i = threadIdx.x; i < n_rep && cnt < 4; i += nt, ++cnt) {
     const double xi = static_cast<double>(i) * fs / fft_size;
-    const int base = static_cast<int>((xi - x0) / dx);
-    const double frac = (xi - x0) / dx - base;
+    const double qd = (xi - x0) * inv_dx;
+    const int base = static_cast<int>(qd);
+    const double frac = qd - base;
     // delta_y[x_length - 1] = 0 with x_length = upper_limit + 1 (never reached: base <= upper_limit - 2)
     const double dy = (base >= upper_limit) ? 0.0 : P[base + 1] - P[base];
     rep[cnt] = P[base] + dy * frac;
@@ -52,25 +55,20 @@ __device__ inline bool wb_linear_smoothing(const double *in, double *out, double
   __syncthreads();
   wb_block_inclusive_scan(seg, len, red);  // mirroring_segment
   const double origin = -(boundary - 0.5) * fs / fft_size;
-  // interp1Q (world_matlabfunctions.cpp:220-241) divides by the knot interval fs / fft_size and the result by
-  // the width; both are loop invariants here, so their reciprocals are formed once.  The quotients can
-  // differ from the reference's in the last bit; the interpolant is continuous across the knot index, so
-  // even a flipped truncation only moves the result by an ulp.
+  // interp1Q (world_matlabfunctions.cpp:220-241) divides by the knot interval fs / fft_size and the result by the
+  // width.  The knots are the bin grid shifted by half a bin, so the two positions of bin i are i + c_lo and i + c_hi
+  // with constants c: knot index and fraction are formed once (with the reference's expression for bin 0) instead of
+  // per bin through a product and a truncation.  The reference's per-bin values equal these up to rounding of the
+  // fraction; the interpolant is continuous across a knot, so the results agree to an ulp of the cumulative sum.
   const double inv_interval = static_cast<double>(fft_size) / fs;
   const double inv_width = 1.0 / width;
+  const double q_lo = (-width / 2.0 - origin) * inv_interval, q_hi = (-width / 2.0 + width - origin) * inv_interval;
+  const int b_lo = static_cast<int>(q_lo), b_hi = static_cast<int>(q_hi);
+  const double f_lo = q_lo - b_lo, f_hi = q_hi - b_hi;
   for (int i = threadIdx.x; i <= nc; i += blockDim.x) {
-    double fa = static_cast<double>(i) * inv_fft * fs - width / 2.0;
-    double q = (fa - origin) * inv_interval;
-    int base = static_cast<int>(q);
-    double frac = q - base;
-    double dy = (base >= len - 1) ? 0.0 : seg[base + 1] - seg[base];
-    const double low = seg[base] + dy * frac;
-    fa += width;
-    q = (fa - origin) * inv_interval;
-    base = static_cast<int>(q);
-    frac = q - base;
-    dy = (base >= len - 1) ? 0.0 : seg[base + 1] - seg[base];
-    const double high = seg[base] + dy * frac;
+    const double *lo = seg + i + b_lo, *hi = seg + i + b_hi;
+    const double low = lo[0] + (lo[1] - lo[0]) * f_lo;
+    const double high = hi[0] + (hi[1] - hi[0]) * f_hi;
     out[i] = (high - low) * inv_width;
   }
   __syncthreads();
