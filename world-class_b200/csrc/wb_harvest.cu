@@ -1134,12 +1134,7 @@ int wb_harvest_run_basic(WbHarvestPlan *pl, WbWorkspace *ws, const double *d_x, 
       p.tw[l] = wb_twiddle_table(1 << l);
       if (!p.tw[l]) return WB_ERR_CUDA;
     }
-    {
-      int dev = 0, sms = 148;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      WB_LAUNCH("refine_kernel", refine_mma_kernel<<<sms * 8, RF_WARPS * 32, 0, stream>>>(p, d_nc + 2));
-    }
+    WB_LAUNCH("refine_kernel", refine_mma_kernel<<<wb_sm_count() * 8, RF_WARPS * 32, 0, stream>>>(p, d_nc + 2));
     WB_CUDA_CHECK(cudaGetLastError());
   }
   (void)n_cs;

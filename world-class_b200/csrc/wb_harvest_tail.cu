@@ -739,7 +739,7 @@ int wb_harvest_tail(WbWorkspace *ws, const double *d_cand, const double *d_score
     // work items (TL_CHUNK outputs each) are bounded by the padded length plus one partial chunk and one
     // lag of forward outputs per section; the kernels stride over the actual count
     const long long max_items = ((long long)L + 2 * TL_LAG + (long long)TL_LAG * p.maxsec) / TL_CHUNK + p.maxsec + 1;
-    const int grid = (int)std::min<long long>((max_items + SM_WARPS - 1) / SM_WARPS, 148 * 8);
+    const int grid = (int)std::min<long long>((max_items + SM_WARPS - 1) / SM_WARPS, (long long)wb_sm_count() * 8);
     WB_LAUNCH("smooth_forward_kernel", smooth_forward_kernel<<<grid, SM_THREADS, 0, stream>>>(q));
     WB_LAUNCH("smooth_backward_kernel", smooth_backward_kernel<<<grid, SM_THREADS, 0, stream>>>(q));
     WB_CUDA_CHECK(cudaGetLastError());

@@ -29,6 +29,9 @@ class WbWorkspace {
   int *d_err_;
 };
 
+// number of SMs of the current device (queried once; grids of persistent kernels are multiples of it)
+int wb_sm_count();
+
 // e^{+2 pi i k / n}, k = 0..n-1, on the device; cached per n (power of two).
 const cplx *wb_twiddle_table(int n);
 

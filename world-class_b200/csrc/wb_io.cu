@@ -158,7 +158,7 @@ int wb_f64_to_pcm16_run(const double *d_in, int n, short *d_out, cudaStream_t st
 int wb_f64_to_f32_run(const double *d_in, size_t n, float *d_out, cudaStream_t stream) {
   if (n == 0) return WB_OK;
   const size_t blocks = (n + 255) / 256;
-  WB_LAUNCH("f64_to_f32_kernel", f64_to_f32_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, stream>>>(d_in, n, d_out));
+  WB_LAUNCH("f64_to_f32_kernel", f64_to_f32_kernel<<<(unsigned)(blocks < (size_t)wb_sm_count() * 16 ? blocks : (size_t)wb_sm_count() * 16), 256, 0, stream>>>(d_in, n, d_out));
   WB_CUDA_CHECK(cudaGetLastError());
   return WB_OK;
 }

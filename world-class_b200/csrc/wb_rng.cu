@@ -1,5 +1,6 @@
 // randn() stream service: jump-ahead tables, fill and advance kernels.  See wb_rng.cuh.
 #include "wb_rng.cuh"
+#include "wb_internal.h"
 
 #include <string.h>
 #include <mutex>
@@ -171,7 +172,7 @@ int wb_rng_fill(const WbRngState *d_state, const unsigned long long *d_skip_or_n
                 cudaStream_t stream) {
   if (max_count == 0) return WB_OK;
   const unsigned long long tiles = (max_count + RNG_TILE - 1) / RNG_TILE;
-  const unsigned long long cap = 148ull * 5ull;  // persistent: 5 CTAs (40 KB of tables each) per SM
+  const unsigned long long cap = (unsigned long long)wb_sm_count() * 5ull;  // persistent: 5 CTAs (40 KB of tables each) per SM
   const unsigned long long grid = tiles < cap ? tiles : cap;
   WB_LAUNCH("rng_fill_kernel", rng_fill_kernel<<<(unsigned)grid, RNG_THREADS, 0, stream>>>(d_state, g_d_pow, d_skip_or_null, d_count_or_null, max_count, d_out));
   WB_CUDA_CHECK(cudaGetLastError());

@@ -103,6 +103,16 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_u64_kernel(const unsigned l
 }
 }  // namespace
 
+int wb_sm_count() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sms = v;
+    else sms = 148;   // B200
+  }
+  return sms;
+}
+
 const cplx *wb_twiddle_table(int n) {
   std::lock_guard<std::mutex> lock(g_tw_mutex);
   auto it = g_tw.find(n);
@@ -263,7 +273,7 @@ int wb_measure_fp64_peak_tflops(double *tflops_out) {
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (cudaMalloc(&d_sink, sizeof(double)) != cudaSuccess) return WB_ERR_CUDA;
   if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) { cudaFree(d_sink); return WB_ERR_CUDA; }
-  const int grid = 148 * 8, threads = 256, iters = 1 << 15;
+  const int grid = wb_sm_count() * 8, threads = 256, iters = 1 << 15;
   double best = 0.0;
   for (int rep = 0; rep < 4; ++rep) {   // first repetition = warm-up
     cudaEventRecord(e0, stream);

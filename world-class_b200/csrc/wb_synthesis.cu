@@ -849,7 +849,7 @@ int wb_synthesis_render(WbWorkspace *ws, int fs, int fft_size, double frame_peri
   p.max_resp_pulses = resp_pulses;
   p.error_flag = ws->error_flag();
   p.range = nullptr; p.row_begin = 0; p.pulse_vuv = nullptr;
-  const int grid = wb_min_i(resp_pulses, 148 * 9);
+  const int grid = wb_min_i(resp_pulses, wb_sm_count() * 9);
   rc = WB_DISPATCH_LOG2(log2n, 8, 13, {
     if (cudaFuncSetAttribute(response_kernel<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WB_ERR_CUDA;
     WB_LAUNCH("response_kernel", response_kernel<L2><<<grid, 256, smem, stream>>>(p));
@@ -958,7 +958,7 @@ static int render_range_core(WbWorkspace *ws, int fs, int fft_size, double frame
     p.max_resp_pulses = resp_pulses;
     p.error_flag = ws->error_flag();
     p.range = d_range; p.row_begin = row_begin; p.pulse_vuv = pl.pulse_vuv;
-    const int grid = wb_min_i(resp_pulses, 148 * 9);
+    const int grid = wb_min_i(resp_pulses, wb_sm_count() * 9);
     rc = WB_DISPATCH_LOG2(log2n, 8, 13, {
       if (cudaFuncSetAttribute(response_kernel<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WB_ERR_CUDA;
       WB_LAUNCH("response_kernel", response_kernel<L2><<<grid, 256, smem, stream>>>(p));
