@@ -50,7 +50,7 @@ struct CtParams {
 };
 
 template <int LOG2N>
-__global__ void __launch_bounds__(256) ct_frame_kernel(CtParams p) {
+__global__ void __launch_bounds__(256, 4) ct_frame_kernel(CtParams p) {
   extern __shared__ double2 smem_raw[];
   constexpr int N = 1 << LOG2N, NC = N / 2, bins = NC + 1;
   // one radix-8 butterfly per thread and pass (the launch uses min(256, N / 8) threads, at least 64): warp-local late passes
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(256) ct_frame_kernel(CtParams p) {
   cplx *S = smem_raw;                                         // FFT slots
   double *A = reinterpret_cast<double *>(S + wb_fft_slots(NC));  // N + 2 doubles
   double *B = A + (N + 2);                                    // seg_capacity doubles
-  double *red = B + p.seg_capacity;                           // 1024 + 64
+  double *red = B + p.seg_capacity;                           // 256 + 64 (one entry per thread for the scan, 64 for the block sums)
   double *W = reinterpret_cast<double *>(S);                  // packed real waveform view
 
   const int frame = p.frame_begin + blockIdx.x;
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(256) ct_frame_kernel(CtParams p) {
 }  // namespace
 
 size_t wb_cheaptrick_smem_bytes(int fft_size, int seg_capacity) {
-  return sizeof(cplx) * wb_fft_slots(fft_size / 2) + sizeof(double) * ((fft_size + 2) + seg_capacity + 1024 + 64);
+  return sizeof(cplx) * wb_fft_slots(fft_size / 2) + sizeof(double) * ((fft_size + 2) + seg_capacity + 256 + 64);
 }
 
 // d_x, d_tpos, d_f0: device.  d_sp: device [f0_length][fft_size/2+1].

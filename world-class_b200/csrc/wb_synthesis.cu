@@ -507,7 +507,7 @@ __global__ void pulse_range_kernel(const int *__restrict__ pulse_index, const in
 
 // MinimumPhaseAnalysis::compute (world_common.cpp:192-233).  On entry the packed real view W of
 // S holds log_spectrum[0..NC] (this function mirrors it); on exit MP[k], k = 0..NC, holds the
-// minimum phase spectrum.  S needs wb_fft_slots(N) slots.
+// minimum phase spectrum.  S needs wb_fft_slots(N / 2) slots (packed real transforms only).
 template <int LOG2N, bool WL = false>
 __device__ __forceinline__ void minimum_phase(cplx *S, cplx *MP, const cplx *tw_n, const cplx *tw_2n) {
   constexpr int N = 1 << LOG2N, NC = N / 2, log2n = LOG2N;
@@ -535,13 +535,13 @@ __device__ __forceinline__ void minimum_phase(cplx *S, cplx *MP, const cplx *tw_
 }
 
 template <int LOG2N>
-__global__ void __launch_bounds__(256, 3) response_kernel(RespParams p) {
+__global__ void __launch_bounds__(256, 4) response_kernel(RespParams p) {
   extern __shared__ double2 smem_raw[];
   constexpr int N = 1 << LOG2N, NC = N / 2, bins = NC + 1;
   constexpr bool WL = (NC / 8 <= 256);        // one radix-8 butterfly per thread and pass (256 threads): warp-local late passes
   const int binsp = (bins + 1) & ~1;
-  cplx *S = smem_raw;                         // wb_fft_slots(N)
-  cplx *MP = S + wb_fft_slots(N);             // bins: minimum-phase spectrum (x noise spectrum for the aperiodic part)
+  cplx *S = smem_raw;                         // wb_fft_slots(NC): every transform here is a real one (packed N/2-point complex)
+  cplx *MP = S + wb_fft_slots(NC);            // bins: minimum-phase spectrum (x noise spectrum for the aperiodic part)
   double *SE = reinterpret_cast<double *>(MP + binsp);  // spectral envelope
   double *AR = SE + binsp;                    // aperiodic ratio
   double *red = AR + binsp;                   // 128
@@ -845,7 +845,7 @@ int wb_synthesis_render(WbWorkspace *ws, int fs, int fft_size, double frame_peri
   p.frame_period = frame_period; p.pulse_index = d_pidx; p.pulse_shift = d_pshift; p.vuv = d_vuv;
   p.n_pulses = d_np; p.noise = d_noise; p.dc_remover = d_dcr; p.tw_n = tw_n; p.tw_2n = tw_2n; p.response = d_resp;
   const int binsp = ((fft_size / 2 + 1) + 1) & ~1;
-  const size_t smem = sizeof(cplx) * (wb_fft_slots(fft_size) + binsp) + sizeof(double) * (2 * binsp + 128);
+  const size_t smem = sizeof(cplx) * (wb_fft_slots(fft_size / 2) + binsp) + sizeof(double) * (2 * binsp + 128);
   p.max_resp_pulses = resp_pulses;
   p.error_flag = ws->error_flag();
   p.range = nullptr; p.row_begin = 0; p.pulse_vuv = nullptr;
@@ -954,7 +954,7 @@ static int render_range_core(WbWorkspace *ws, int fs, int fft_size, double frame
     p.frame_period = frame_period; p.pulse_index = d_pidx; p.pulse_shift = d_pshift; p.vuv = d_vuv;
     p.n_pulses = d_np; p.noise = d_noise; p.dc_remover = d_dcr; p.tw_n = tw_n; p.tw_2n = tw_2n; p.response = d_resp;
     const int binsp = ((fft_size / 2 + 1) + 1) & ~1;
-    const size_t smem = sizeof(cplx) * (wb_fft_slots(fft_size) + binsp) + sizeof(double) * (2 * binsp + 128);
+    const size_t smem = sizeof(cplx) * (wb_fft_slots(fft_size / 2) + binsp) + sizeof(double) * (2 * binsp + 128);
     p.max_resp_pulses = resp_pulses;
     p.error_flag = ws->error_flag();
     p.range = d_range; p.row_begin = row_begin; p.pulse_vuv = pl.pulse_vuv;
