@@ -24,63 +24,6 @@ __device__ __forceinline__ int d4c_half_window(double ratio, int fs, double f0) 
   return wb_round(ratio * fs / f0 / 2.0);  // d4c.cpp:250
 }
 
-// d4c.cpp:246-303.  at(j) -> reference to destination sample j; win(j) -> reference to scratch for
-// window sample j.  All threads must call; ends with __syncthreads().  Returns the window length.
-template <typename At, typename Win>
-__device__ inline int d4c_windowed_waveform(const double *__restrict__ x, int x_length, int fs, double f0,
-                                            double position_s, int window_type, double ratio,
-                                            const double *__restrict__ noise, Win win, double *red, At at,
-                                            const double *rot = nullptr) {
-  const int hw = d4c_half_window(ratio, fs, f0);
-  const int wlen = 2 * hw + 1;
-  const int origin = wb_round(position_s * fs + 0.001);
-  const double c1 = 2.0 / ratio / fs;
-  const double c2 = WB_PI * f0;
-  // The window angle c2 * c1 * (j - hw) is linear in j: one sincos at the thread's first sample (the
-  // reference's expression), then a rotation by blockDim samples per step (<= 32 steps, ~1e-15 drift);
-  // cos(2t) = 2 cos(t)^2 - 1 for the Blackman term (d4c.cpp:266-283).
-  // (`rot`: the four rotation constants, if the caller already has them for this f0 and ratio)
-  double sd, cd, sn, cs;
-  if (rot) {
-    sd = rot[0]; cd = rot[1]; sn = rot[2]; cs = rot[3];
-  } else {
-    sincos(c2 * c1 * blockDim.x, &sd, &cd);
-    sincos(c2 * (c1 * ((int)threadIdx.x - hw)), &sn, &cs);
-  }
-  double s1 = 0.0, s2 = 0.0;
-  // (the waveform and noise samples of the NEXT step are requested before this step's arithmetic: the loop used
-  // to sit on these two loads)
-  double x_next = 0.0, n_next = 0.0;
-  if ((int)threadIdx.x < wlen) {
-    x_next = x[wb_min_i(x_length - 1, wb_max_i(0, origin + (int)threadIdx.x - hw))];
-    n_next = noise[threadIdx.x];
-  }
-  for (int j = threadIdx.x; j < wlen; j += blockDim.x) {
-    const double x_here = x_next, n_here = n_next;
-    const int jn = j + blockDim.x;
-    if (jn < wlen) {
-      x_next = x[wb_min_i(x_length - 1, wb_max_i(0, origin + jn - hw))];
-      n_next = noise[jn];
-    }
-    double w;
-    if (window_type == D4C_HANNING) w = 0.5 * cs + 0.5;
-    else w = 0.42 + 0.5 * cs + 0.08 * (2.0 * cs * cs - 1.0);
-    win(j) = w;
-    const double v = x_here * w + n_here * WB_SAFEGUARD;
-    at(j) = v;
-    s1 += v;
-    s2 += w;
-    const double c_next = cs * cd - sn * sd;
-    sn = sn * cd + cs * sd;
-    cs = c_next;
-  }
-  wb_block_sum2(s1, s2, red);
-  const double coef = s1 / s2;
-  for (int j = threadIdx.x; j < wlen; j += blockDim.x) at(j) -= win(j) * coef;
-  __syncthreads();
-  return wlen;
-}
-
 // ---- randn() call counts and the frames' positions in the stream -------------------------------
 __global__ void __launch_bounds__(1024) lt_count_scan_kernel(const double *__restrict__ f0, int n, int fs,
                                                              double lowest_f0, unsigned long long *__restrict__ offsets,
@@ -130,41 +73,6 @@ struct LtParams {
   int frame_begin;   // this launch covers frames frame_begin + blockIdx.x
 };
 
-template <int LOG2N>
-__global__ void __launch_bounds__(256) lt_frame_kernel(LtParams p) {
-  extern __shared__ double2 smem_raw[];
-  constexpr int N = 1 << LOG2N, NC = N / 2;
-  cplx *S = smem_raw;
-  double *win = reinterpret_cast<double *>(S + wb_fft_slots(NC));  // N doubles
-  double *red = win + N;                                          // 128
-  double *W = reinterpret_cast<double *>(S);
-  const int frame = p.frame_begin + blockIdx.x;
-  const double f0 = p.f0[frame];
-  if (f0 == 0.0) {
-    if (threadIdx.x == 0) p.ap0[frame] = 0.0;
-    return;
-  }
-  const double cf0 = f0 > p.lowest_f0 ? f0 : p.lowest_f0;
-  const int wlen = d4c_windowed_waveform(p.x, p.x_length, p.fs, cf0, p.tpos[frame], D4C_BLACKMAN, 3.0,
-                                         p.noise + p.noise_off[frame], [&](int j) -> double & { return win[j]; }, red,
-                                         [&](int j) -> double & { return W[wb_didx(j)]; });
-  for (int j = wlen + threadIdx.x; j < N; j += blockDim.x) W[wb_didx(j)] = 0.0;
-  __syncthreads();
-  // power in (boundary0, boundary1] and (boundary0, boundary2]; bins above N/2 count as zero
-  double a = 0.0, b = 0.0;
-  const int b0 = p.boundary0, b1 = p.boundary1, b2 = p.boundary2;
-  // wb_rfft's emit runs once per k on some thread: accumulate per thread, reduce afterwards
-  wb_rfft_t<1, LOG2N - 1>(S, p.twiddle, [&](int k, cplx X) {
-    if (k > b0 && k <= b2) {
-      const double pw = X.x * X.x + X.y * X.y;
-      b += pw;
-      if (k <= b1) a += pw;
-    }
-  });
-  wb_block_sum2(a, b, red);
-  if (threadIdx.x == 0) p.ap0[frame] = a / b;
-}
-
 // ---- block-wide reductions with ONE barrier each ----------------------------------------------
 // Two scratch buffers alternate (`par`): a buffer is rewritten only after the barrier of the reduction in
 // between, which every thread reaches after its reads of that buffer.  red: 2 * 16 * K doubles.  The
@@ -207,6 +115,126 @@ __device__ __forceinline__ void d4c_block_sum2_max2(double &sa, double &sb, doub
     sa += buf[w * 4 + 0]; sb += buf[w * 4 + 1];
     ma = fmax(ma, buf[w * 4 + 2]); mb = fmax(mb, buf[w * 4 + 3]);
   }
+}
+
+// ---- Love Train frames (d4c.cpp:181-240) -------------------------------------------------------------------
+// One CTA of T = N/16 threads per frame: the packed real transform (N/2 complex points) has exactly one radix-8
+// butterfly per thread and pass, and thread t owns packed samples t + T q, i.e. waveform samples 2 (t + T q) and the
+// one after it -- the Blackman window (three periods), the mean removal and the first FFT pass work on registers;
+// shared memory only holds the FFT slots (N = 4096: 38 KB, four CTAs per SM at 64 registers).
+template <int LOG2N>
+__global__ void __launch_bounds__((1 << LOG2N) / 16, ((16384 >> LOG2N) > 16 ? 16 : ((16384 >> LOG2N) < 1 ? 1 : (16384 >> LOG2N))))
+lt_frame_kernel(LtParams p) {
+  extern __shared__ double2 smem_raw[];
+  constexpr int N = 1 << LOG2N, NC = N / 2, T = N / 16;
+  cplx *S = smem_raw;
+  double *red = reinterpret_cast<double *>(S + wb_fft_slots(NC));   // 2 x 16 x 2
+  const int frame = p.frame_begin + blockIdx.x;
+  const int tid = threadIdx.x;
+  const double f0 = p.f0[frame];
+  if (f0 == 0.0) {
+    if (tid == 0) p.ap0[frame] = 0.0;
+    return;
+  }
+  const int fs = p.fs;
+  const double cf0 = f0 > p.lowest_f0 ? f0 : p.lowest_f0;
+  const int hw = d4c_half_window(3.0, fs, cf0);
+  const int wlen = 2 * hw + 1;
+  const int origin = wb_round(p.tpos[frame] * fs + 0.001);
+  const double *noise = p.noise + p.noise_off[frame];
+  int par = 0;
+  double v[16];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int j = 2 * (tid + q * T) + e;
+      v[2 * q + e] = 0.0;
+      if (j < wlen) v[2 * q + e] = p.x[wb_min_i(p.x_length - 1, wb_max_i(0, origin + j - hw))];
+    }
+  }
+  // window angle of sample j: pi f0 (2 / 3 / fs) (j - hw) (d4c.cpp:246-283): one sincos at the thread's first sample
+  // (the reference's expression), a rotation by one sample for the odd one and by 2 T samples per step (<= 7 steps).
+  // The window values are needed twice (windowing, then the mean removal): the recurrence is run twice instead of
+  // keeping sixteen more doubles in registers.
+  const double wc1 = 2.0 / 3.0 / fs, wc2 = WB_PI * cf0;
+  double sd, cd, s1c, c1c, sn0, cs0;
+  sincos(wc2 * wc1 * (2 * T), &sd, &cd);
+  sincos(wc2 * wc1, &s1c, &c1c);
+  sincos(wc2 * (wc1 * (2 * tid - hw)), &sn0, &cs0);
+  double s[2] = {0.0, 0.0};
+  {
+    double sn = sn0, cs = cs0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int j = 2 * (tid + q * T);
+      if (j < wlen) {
+        const double w0 = 0.42 + 0.5 * cs + 0.08 * (2.0 * cs * cs - 1.0);
+        const double v0 = v[2 * q] * w0 + noise[j] * WB_SAFEGUARD;
+        v[2 * q] = v0;
+        s[0] += v0; s[1] += w0;
+        if (j + 1 < wlen) {
+          const double c1 = cs * c1c - sn * s1c;
+          const double w1 = 0.42 + 0.5 * c1 + 0.08 * (2.0 * c1 * c1 - 1.0);
+          const double v1 = v[2 * q + 1] * w1 + noise[j + 1] * WB_SAFEGUARD;
+          v[2 * q + 1] = v1;
+          s[0] += v1; s[1] += w1;
+        }
+        const double c_next = cs * cd - sn * sd;
+        sn = sn * cd + cs * sd;
+        cs = c_next;
+      }
+    }
+  }
+  d4c_block_sum<2>(s, red, par);
+  const double coef = s[0] / s[1];
+  {
+    double sn = sn0, cs = cs0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int j = 2 * (tid + q * T);
+      if (j < wlen) {
+        v[2 * q] -= (0.42 + 0.5 * cs + 0.08 * (2.0 * cs * cs - 1.0)) * coef;
+        if (j + 1 < wlen) {
+          const double c1 = cs * c1c - sn * s1c;
+          v[2 * q + 1] -= (0.42 + 0.5 * c1 + 0.08 * (2.0 * c1 * c1 - 1.0)) * coef;
+        }
+        const double c_next = cs * cd - sn * sd;
+        sn = sn * cd + cs * sd;
+        cs = c_next;
+      }
+    }
+  }
+  wb_pass_dif8<1, NC, NC>(S, p.twiddle, [&](int, int q) { return make_double2(v[2 * q], v[2 * q + 1]); });
+  __syncthreads();
+  WbDifPasses<1, NC, NC / 8, 8, true>::run(S, p.twiddle, WbFromSlots());
+  // power in (boundary0, boundary1] and (boundary0, boundary2]; bins above N/2 count as zero
+  double pw[2] = {0.0, 0.0};
+  const int b0 = p.boundary0, b1 = p.boundary1, b2 = p.boundary2;
+  auto take = [&](int k, cplx X) {
+    if (k > b0 && k <= b2) {
+      const double e2 = X.x * X.x + X.y * X.y;
+      pw[1] += e2;
+      if (k <= b1) pw[0] += e2;
+    }
+  };
+  for (int k = tid; k <= (NC >> 1); k += T) {   // split step of the real transform (see wb_rfft_t)
+    if (k == 0) {
+      const cplx z = S[0];
+      take(0, make_double2(z.x + z.y, 0.0));
+      take(NC, make_double2(z.x - z.y, 0.0));
+    } else {
+      const cplx zk = S[wb_sidx(wb_brev(k, LOG2N - 1))];
+      const cplx zc = S[wb_sidx(wb_brev(NC - k, LOG2N - 1))];
+      const cplx E = make_double2(0.5 * (zk.x + zc.x), 0.5 * (zk.y - zc.y));
+      const cplx O = make_double2(0.5 * (zk.y + zc.y), -0.5 * (zk.x - zc.x));
+      const cplx t = wb_cmul(wb_tw<1>(p.twiddle, k), O);
+      take(k, wb_cadd(E, t));
+      if (k != NC - k) take(NC - k, wb_conj(wb_csub(E, t)));
+    }
+  }
+  d4c_block_sum<2>(pw, red, par);
+  if (tid == 0) p.ap0[frame] = pw[0] / pw[1];
 }
 
 // ---- linear smoothing (world_common.cpp:82-116, :27-52; interp1Q world_matlabfunctions.cpp:220-241) ----
@@ -832,10 +860,10 @@ int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int
     p.boundary2 = static_cast<int>(ceil(7900.0 * N_lt / fs));
     p.twiddle = tw_lt; p.noise = d_noise; p.noise_off = range ? d_rel : d_offsets; p.ap0 = d_ap0;
     p.frame_begin = row0;
-    const size_t smem = sizeof(cplx) * wb_fft_slots(N_lt / 2) + sizeof(double) * (N_lt + 128);
+    const size_t smem = sizeof(cplx) * wb_fft_slots(N_lt / 2) + sizeof(double) * (2 * 16 * 2);
     rc = WB_DISPATCH_LOG2(l_lt, 9, 14, {
       if (cudaFuncSetAttribute(lt_frame_kernel<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WB_ERR_CUDA;
-      WB_LAUNCH("lt_frame_kernel", lt_frame_kernel<L2><<<n_rows, 256, smem, stream>>>(p));
+      WB_LAUNCH("lt_frame_kernel", lt_frame_kernel<L2><<<n_rows, N_lt / 16, smem, stream>>>(p));   // one radix-8 butterfly per thread and pass
     });
     if (rc) return rc;
     WB_CUDA_CHECK(cudaGetLastError());
