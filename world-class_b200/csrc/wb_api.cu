@@ -353,6 +353,7 @@ struct wb_pipeline {
   // After Harvest the chain forks: CheapTrick stays on the caller's stream, D4C runs on `d4c_stream`
   // and the Synthesis time base / pulse list / noise on `side`; they join before the impulse responses.
   cudaStream_t side = nullptr, d4c_stream = nullptr;
+  WbStageSplit d4c_split;            // second stream of the D4C stage (halves of the rows, see WbStageSplit)
   unsigned long long graph_generation = 0;   // ws.generation() when the graph was captured
   int stream_f0_length = 0;          // sharded streams: the length given to wb_pipeline_stream_begin_dev
   double stream_f0_bound = 0.0;      // sharded streams: upper bound of an external f0 contour (<= 0: f0_ceil * 1.25)
@@ -378,6 +379,11 @@ struct wb_pipeline {
     if (ev_start) cudaEventDestroy(ev_start);
     if (side) cudaStreamDestroy(side);
     if (d4c_stream) cudaStreamDestroy(d4c_stream);
+    if (d4c_split.alt) cudaStreamDestroy(d4c_split.alt);
+    for (int k = 0; k < 2; ++k) {
+      if (d4c_split.fork[k]) cudaEventDestroy(d4c_split.fork[k]);
+      if (d4c_split.join[k]) cudaEventDestroy(d4c_split.join[k]);
+    }
     if (d_rng_private) cudaFree(d_rng_private);
     if (d_rng_seed) cudaFree(d_rng_seed);
     if (graph_exec) cudaGraphExecDestroy(graph_exec);
@@ -869,6 +875,11 @@ int wb_pipeline_create(int fs, const WbHarvestOption *hopt, const WbCheapTrickOp
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
   if (cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithPriority(&p->d4c_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&p->d4c_split.alt, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+      cudaEventCreateWithFlags(&p->d4c_split.fork[0], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&p->d4c_split.fork[1], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&p->d4c_split.join[0], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&p->d4c_split.join[1], cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&p->ev_f0, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&p->ev_ct_count, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&p->ev_body_count, cudaEventDisableTiming) != cudaSuccess ||
@@ -1049,7 +1060,7 @@ static int pipeline_enqueue(wb_pipeline_t *p, const double *d_x, int x_length, d
   c_d4c.state = rng; c_d4c.skip_in = rng_pos + 0; c_d4c.skip_out = rng_pos + 1; c_d4c.advance = false;
   c_d4c.wait_skip_in = p->ev_ct_count; c_d4c.record_skip_out = p->ev_body_count;
   if ((rc = wb_d4c_run(&p->ws, fs, p->d4c.threshold, d_x, x_length, d_tpos, d_f0, f0_length, p->ct.fft_size, d_ap,
-                       c_d4c, s_d4c)))
+                       c_d4c, s_d4c, nullptr, nullptr, 0, nullptr, fork ? &p->d4c_split : nullptr)))
     return rc;
   WB_CUDA_CHECK(cudaEventRecord(p->ev_d4c, s_d4c));
   if (y_length > 0) {

@@ -69,6 +69,7 @@ struct LtParams {
   int boundary0, boundary1, boundary2;
   const cplx *twiddle;
   const double *noise; const unsigned long long *noise_off;
+  int noise_origin;   // >= 0: the noise buffer starts at the draws of this frame (offsets are taken relative to it)
   double *ap0;
   int frame_begin;   // this launch covers frames frame_begin + blockIdx.x
 };
@@ -141,7 +142,7 @@ lt_frame_kernel(LtParams p) {
   const int hw = d4c_half_window(3.0, fs, cf0);
   const int wlen = 2 * hw + 1;
   const int origin = wb_round(p.tpos[frame] * fs + 0.001);
-  const double *noise = p.noise + p.noise_off[frame];
+  const double *noise = p.noise + (p.noise_off[frame] - (p.noise_origin >= 0 ? p.noise_off[p.noise_origin] : 0ull));
   int par = 0;
   double v[16];
 #pragma unroll
@@ -303,6 +304,7 @@ struct BodyParams {
   const cplx *tw_n;                    // fft_size_d4c entries (real transforms)
   const cplx *tw_2n;                   // 2*fft_size_d4c entries (complex transform of size N)
   const double *noise; const unsigned long long *noise_off;
+  int noise_origin;                    // >= 0: the noise buffer starts at the draws of this frame (offsets relative to it)
   int out_fft_size;                    // bins of the output rows
   double *ap;                          // [f0_length][out_fft_size/2+1]
   int *error_flag;
@@ -361,7 +363,7 @@ d4c_body_kernel(BodyParams p) {
   const double f0 = f0_in > WB_FLOOR_F0_D4C ? f0_in : WB_FLOOR_F0_D4C;
   const int fs = p.fs;
   const double pos = p.tpos[frame];
-  const double *noise = p.noise + p.noise_off[frame];
+  const double *noise = p.noise + (p.noise_off[frame] - (p.noise_origin >= 0 ? p.noise_off[p.noise_origin] : 0ull));
   int par = 0;
 
   const int hw = d4c_half_window(4.0, fs, f0);
@@ -784,8 +786,10 @@ int wb_number_of_aperiodicities(int fs) {  // d4c.cpp:65-67, codec.cpp:211-214
 
 int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int x_length, const double *d_tpos,
                const double *d_f0, int f0_length, int out_fft_size, double *d_ap, const WbRngCursor &rng,
-               cudaStream_t stream, const WbRowChunks *chunks, const WbFrameRange *range, int phase, double *d_ap0_ext) {
+               cudaStream_t stream, const WbRowChunks *chunks, const WbFrameRange *range, int phase, double *d_ap0_ext,
+               const WbStageSplit *split) {
   if (f0_length <= 0) return WB_OK;
+  if (split && (range || chunks || phase != 0 || f0_length < 64)) split = nullptr;   // whole-utterance calls only
   if (range && (range->begin < 0 || range->end > f0_length || range->begin > range->end || chunks)) return WB_ERR_ARG;
   if (phase < 0 || phase > 2 || (phase != 0 && !d_ap0_ext)) return WB_ERR_ARG;
   const int row0 = range ? range->begin : 0;
@@ -846,27 +850,52 @@ int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int
   WB_CUDA_CHECK(cudaGetLastError());
   if (rng.wait_skip_in) WB_CUDA_CHECK(cudaStreamWaitEvent(stream, rng.wait_skip_in, 0));
   int rc;
+  // second noise buffer of a split stage (the halves draw concurrently)
+  double *d_noise_b = nullptr;
+  const int half = f0_length / 2;
+  if (split) {
+    d_noise_b = (double *)ws->get("noise_d4c_b", sizeof(double) * (unsigned long long)(f0_length - half) * 3ull * N);
+    if (!d_noise_b) return WB_ERR_CUDA;
+  }
   if (phase != 2) {
-  if (range) {
-    if ((rc = wb_range_offsets(d_offsets, *range, d_rel, rng.skip_in, d_pos, d_pos + 1, stream))) return rc;
-    if (n_rows > 0 && (rc = wb_rng_fill(rng.state, d_pos, d_pos + 1, max_noise_lt, d_noise, stream))) return rc;
-  } else if ((rc = wb_rng_fill(rng.state, rng.skip_in, d_offsets + f0_length, max_noise_lt, d_noise, stream))) return rc;
-  if (n_rows > 0) {
-    LtParams p;
-    p.x = d_x; p.x_length = x_length; p.tpos = d_tpos; p.f0 = d_f0; p.f0_length = f0_length;
-    p.fs = fs; p.fft_size = N_lt; p.log2nc = l_lt - 1; p.lowest_f0 = 40.0;
-    p.boundary0 = static_cast<int>(ceil(100.0 * N_lt / fs));
-    p.boundary1 = static_cast<int>(ceil(4000.0 * N_lt / fs));
-    p.boundary2 = static_cast<int>(ceil(7900.0 * N_lt / fs));
-    p.twiddle = tw_lt; p.noise = d_noise; p.noise_off = range ? d_rel : d_offsets; p.ap0 = d_ap0;
-    p.frame_begin = row0;
-    const size_t smem = sizeof(cplx) * wb_fft_slots(N_lt / 2) + sizeof(double) * (2 * 16 * 2);
-    rc = WB_DISPATCH_LOG2(l_lt, 9, 14, {
+  LtParams p;
+  p.x = d_x; p.x_length = x_length; p.tpos = d_tpos; p.f0 = d_f0; p.f0_length = f0_length;
+  p.fs = fs; p.fft_size = N_lt; p.log2nc = l_lt - 1; p.lowest_f0 = 40.0;
+  p.boundary0 = static_cast<int>(ceil(100.0 * N_lt / fs));
+  p.boundary1 = static_cast<int>(ceil(4000.0 * N_lt / fs));
+  p.boundary2 = static_cast<int>(ceil(7900.0 * N_lt / fs));
+  p.twiddle = tw_lt; p.ap0 = d_ap0;
+  const size_t smem = sizeof(cplx) * wb_fft_slots(N_lt / 2) + sizeof(double) * (2 * 16 * 2);
+  auto launch_lt = [&](int begin, int count, const double *noise, const unsigned long long *off, int origin, cudaStream_t cs) -> int {
+    if (count <= 0) return WB_OK;
+    p.noise = noise; p.noise_off = off; p.noise_origin = origin; p.frame_begin = begin;
+    int r2 = WB_DISPATCH_LOG2(l_lt, 9, 14, {
       if (cudaFuncSetAttribute(lt_frame_kernel<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WB_ERR_CUDA;
-      WB_LAUNCH("lt_frame_kernel", lt_frame_kernel<L2><<<n_rows, N_lt / 16, smem, stream>>>(p));   // one radix-8 butterfly per thread and pass
+      WbLaunchScope scope("lt_frame_kernel", cs);
+      lt_frame_kernel<L2><<<count, N_lt / 16, smem, cs>>>(p);   // one radix-8 butterfly per thread and pass
     });
-    if (rc) return rc;
+    if (r2) return r2;
     WB_CUDA_CHECK(cudaGetLastError());
+    return WB_OK;
+  };
+  if (split) {
+    // two halves of the rows: the fill of the second half runs beside the frames of the first
+    WB_CUDA_CHECK(cudaEventRecord(split->fork[0], stream));
+    WB_CUDA_CHECK(cudaStreamWaitEvent(split->alt, split->fork[0], 0));
+    if ((rc = wb_rng_fill(rng.state, rng.skip_in, d_offsets + half, (unsigned long long)half * N_lt, d_noise, stream))) return rc;
+    if ((rc = launch_lt(0, half, d_noise, d_offsets, -1, stream))) return rc;
+    if ((rc = wb_rng_fill(rng.state, rng.skip_in, d_offsets + f0_length, (unsigned long long)(f0_length - half) * N_lt, d_noise_b, split->alt,
+                          d_offsets + half, d_offsets + half)))
+      return rc;
+    if ((rc = launch_lt(half, f0_length - half, d_noise_b, d_offsets, half, split->alt))) return rc;
+    WB_CUDA_CHECK(cudaEventRecord(split->join[0], split->alt));
+    WB_CUDA_CHECK(cudaStreamWaitEvent(stream, split->join[0], 0));
+  } else {
+    if (range) {
+      if ((rc = wb_range_offsets(d_offsets, *range, d_rel, rng.skip_in, d_pos, d_pos + 1, stream))) return rc;
+      if (n_rows > 0 && (rc = wb_rng_fill(rng.state, d_pos, d_pos + 1, max_noise_lt, d_noise, stream))) return rc;
+    } else if ((rc = wb_rng_fill(rng.state, rng.skip_in, d_offsets + f0_length, max_noise_lt, d_noise, stream))) return rc;
+    if ((rc = launch_lt(row0, n_rows, d_noise, range ? d_rel : d_offsets, -1, stream))) return rc;
   }
   }
   if (phase == 1) return WB_OK;   // (the stream bookkeeping is done by the body phase)
@@ -875,7 +904,15 @@ int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int
                                                                                   rng.skip_in, d_lt_total, d_skip_mid, d_skip_end));
   WB_CUDA_CHECK(cudaGetLastError());
   if (rng.record_skip_out) WB_CUDA_CHECK(cudaEventRecord(rng.record_skip_out, stream));
-  if (range) {
+  if (split) {
+    // first half's draws on the caller's stream, second half's on the other one (its fill runs beside the first half's frames)
+    WB_CUDA_CHECK(cudaEventRecord(split->fork[1], stream));
+    WB_CUDA_CHECK(cudaStreamWaitEvent(split->alt, split->fork[1], 0));
+    if ((rc = wb_rng_fill(rng.state, d_skip_mid, d_offsets + half, (unsigned long long)half * 3ull * N, d_noise, stream))) return rc;
+    if ((rc = wb_rng_fill(rng.state, d_skip_mid, d_offsets + f0_length, (unsigned long long)(f0_length - half) * 3ull * N, d_noise_b, split->alt,
+                          d_offsets + half, d_offsets + half)))
+      return rc;
+  } else if (range) {
     if ((rc = wb_range_offsets(d_offsets, *range, d_rel, d_skip_mid, d_pos, d_pos + 1, stream))) return rc;
     if (n_rows > 0 && (rc = wb_rng_fill(rng.state, d_pos, d_pos + 1, max_noise_body, d_noise, stream))) return rc;
   } else if ((rc = wb_rng_fill(rng.state, d_skip_mid, d_offsets + f0_length, max_noise_body, d_noise, stream))) return rc;
@@ -884,13 +921,30 @@ int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int
     p.x = d_x; p.x_length = x_length; p.tpos = d_tpos; p.f0 = d_f0; p.ap0 = d_ap0; p.f0_length = f0_length;
     p.fs = fs; p.threshold = threshold;
     p.n_ap = n_ap; p.window_length = window_length; p.nuttall = d_nuttall;
-    p.tw_n = tw_n; p.tw_2n = tw_2n; p.noise = d_noise; p.noise_off = range ? d_rel : d_offsets;
+    p.tw_n = tw_n; p.tw_2n = tw_2n; p.noise = d_noise; p.noise_off = range ? d_rel : d_offsets; p.noise_origin = -1;
     p.out_fft_size = out_fft_size;
     p.ap = range ? d_ap - (size_t)row0 * (out_fft_size / 2 + 1) : d_ap;   // (rows are addressed by absolute frame)
     p.error_flag = ws->error_flag();
     const size_t smem = d4c_body_smem_bytes(N);
     const int threads = N / 16;     // one radix-16 butterfly per thread and pass
     p.frame_begin = row0;
+    if (split) {
+      for (int hh = 0; hh < 2; ++hh) {
+        cudaStream_t cs = hh ? split->alt : stream;
+        const int count = hh ? f0_length - half : half;
+        p.frame_begin = hh ? half : 0;
+        p.noise = hh ? d_noise_b : d_noise;
+        p.noise_origin = hh ? half : -1;
+        rc = WB_DISPATCH_LOG2(l, 9, 13, {
+          if (cudaFuncSetAttribute(d4c_body_kernel<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WB_ERR_CUDA;
+          WbLaunchScope scope("d4c_body_kernel", cs);
+          d4c_body_kernel<L2><<<count, threads, smem, cs>>>(p);
+        });
+        if (rc) return rc;
+      }
+      WB_CUDA_CHECK(cudaEventRecord(split->join[1], split->alt));
+      WB_CUDA_CHECK(cudaStreamWaitEvent(stream, split->join[1], 0));
+    } else
     if (!chunks || chunks->n <= 1) {
       rc = WB_DISPATCH_LOG2(l, 9, 13, {
         if (cudaFuncSetAttribute(d4c_body_kernel<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WB_ERR_CUDA;

@@ -275,8 +275,7 @@ __device__ __forceinline__ void wb_pass_dif4_last(cplx *s) {
         sp[0] = a[0]; sp[1] = a[2]; sp[2] = a[1]; sp[3] = a[3];
       }
     }
-    return;
-  }
+  } else {
   for (int u = threadIdx.x; u < N / 4; u += blockDim.x) {
     cplx *sp = s + wb_sidx(4 * u);
     cplx a[4];
@@ -284,6 +283,7 @@ __device__ __forceinline__ void wb_pass_dif4_last(cplx *s) {
     for (int q = 0; q < 4; ++q) a[q] = sp[q];
     wb_dft4<SIGN>(a);
     sp[0] = a[0]; sp[1] = a[2]; sp[2] = a[1]; sp[3] = a[3];
+  }
   }
 }
 template <int SIGN, int N, int OWN = 0>
@@ -298,13 +298,13 @@ __device__ __forceinline__ void wb_pass_dif2_last(cplx *s) {
         sp[1] = wb_csub(a0, a1);
       }
     }
-    return;
-  }
+  } else {
   for (int u = threadIdx.x; u < N / 2; u += blockDim.x) {
     cplx *sp = s + wb_sidx(2 * u);
     const cplx a0 = sp[0], a1 = sp[1];
     sp[0] = wb_cadd(a0, a1);
     sp[1] = wb_csub(a0, a1);
+  }
   }
 }
 
@@ -349,8 +349,7 @@ __device__ __forceinline__ void wb_pass_dit4_first(cplx *s) {
         for (int p = 0; p < 4; ++p) sp[p] = a[p];
       }
     }
-    return;
-  }
+  } else {
   for (int u = threadIdx.x; u < N / 4; u += blockDim.x) {
     cplx *sp = s + wb_sidx(4 * u);
     cplx a[4];
@@ -358,6 +357,7 @@ __device__ __forceinline__ void wb_pass_dit4_first(cplx *s) {
     wb_dft4<SIGN>(a);
 #pragma unroll
     for (int p = 0; p < 4; ++p) sp[p] = a[p];
+  }
   }
 }
 template <int SIGN, int N, int OWN = 0>
@@ -372,13 +372,13 @@ __device__ __forceinline__ void wb_pass_dit2_first(cplx *s) {
         sp[1] = wb_csub(a0, a1);
       }
     }
-    return;
-  }
+  } else {
   for (int u = threadIdx.x; u < N / 2; u += blockDim.x) {
     cplx *sp = s + wb_sidx(2 * u);
     const cplx a0 = sp[0], a1 = sp[1];
     sp[0] = wb_cadd(a0, a1);
     sp[1] = wb_csub(a0, a1);
+  }
   }
 }
 

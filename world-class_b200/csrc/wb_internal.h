@@ -72,6 +72,13 @@ int wb_cheaptrick_run(WbWorkspace *ws, int fs, int fft_size, double q1, double f
 // stand-alone batched transforms (wb_fftapi.cu); kind 0 r2c, 1 c2r, 2 c2c fwd, 3 c2c bwd
 int wb_fft_batch_dev(int kind, const void *d_in, int n, int batch, void *d_out, cudaStream_t stream);
 
+// Two halves of a stage's rows on two streams: the randn() fill of the second half runs beside the frame kernel of
+// the first (integer work beside fp64 work) instead of in front of it.  `alt` forks from and joins the caller's stream.
+struct WbStageSplit {
+  cudaStream_t alt = nullptr;
+  cudaEvent_t fork[2] = {nullptr, nullptr}, join[2] = {nullptr, nullptr};   // [0] Love Train, [1] body
+};
+
 // D4C (wb_d4c.cu)
 int wb_d4c_fft_size(int fs);
 int wb_d4c_lt_fft_size(int fs);
@@ -82,7 +89,7 @@ int wb_number_of_aperiodicities(int fs);
 int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int x_length, const double *d_tpos,
                const double *d_f0, int f0_length, int out_fft_size, double *d_ap, const WbRngCursor &rng,
                cudaStream_t stream, const WbRowChunks *chunks = nullptr, const WbFrameRange *range = nullptr,
-               int phase = 0, double *d_ap0_ext = nullptr);
+               int phase = 0, double *d_ap0_ext = nullptr, const WbStageSplit *split = nullptr);
 
 // Synthesis (wb_synthesis.cu)
 // Samples [sample_begin, sample_end) of the whole stream's waveform.  Must follow wb_synthesis_timebase (whole

@@ -84,15 +84,17 @@ __global__ void __launch_bounds__(RNG_THREADS) rng_fill_kernel(const WbRngState 
                                                                const uint4 *__restrict__ pow_tables,
                                                                const unsigned long long *__restrict__ d_skip,
                                                                const unsigned long long *__restrict__ d_count,
-                                                               unsigned long long max_count, double *__restrict__ out) {
+                                                               unsigned long long max_count, double *__restrict__ out,
+                                                               const unsigned long long *__restrict__ d_skip2,
+                                                               const unsigned long long *__restrict__ d_count_sub) {
   __shared__ uint4 s_tab[RNG_LANE_TABLES * WB_RNG_TAB_ENTRIES];  // M^(chunk * 2^j), j = 0..4
-  const unsigned long long count = d_count ? min(*d_count, max_count) : max_count;
+  const unsigned long long count = d_count ? min(*d_count - (d_count_sub ? *d_count_sub : 0ull), max_count) : max_count;
   const unsigned long long n_tiles = (count + RNG_TILE - 1) / RNG_TILE;
   if ((unsigned long long)blockIdx.x >= n_tiles) return;
   for (int i = threadIdx.x; i < RNG_LANE_TABLES * WB_RNG_TAB_ENTRIES; i += RNG_THREADS)
     s_tab[i] = pow_tables[(size_t)WB_RNG_LOG2_CHUNK * WB_RNG_TAB_ENTRIES + i];
   __syncthreads();
-  const unsigned long long skip = d_skip ? *d_skip : 0ull;
+  const unsigned long long skip = (d_skip ? *d_skip : 0ull) + (d_skip2 ? *d_skip2 : 0ull);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t s0 = state->s[0], s1 = state->s[1], s2 = state->s[2], s3 = state->s[3];
   for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -169,12 +171,12 @@ void wb_rng_host_jump(uint32_t s[4], unsigned long long n) {
 
 int wb_rng_fill(const WbRngState *d_state, const unsigned long long *d_skip_or_null,
                 const unsigned long long *d_count_or_null, unsigned long long max_count, double *d_out,
-                cudaStream_t stream) {
+                cudaStream_t stream, const unsigned long long *d_skip2, const unsigned long long *d_count_sub) {
   if (max_count == 0) return WB_OK;
   const unsigned long long tiles = (max_count + RNG_TILE - 1) / RNG_TILE;
   const unsigned long long cap = (unsigned long long)wb_sm_count() * 5ull;  // persistent: 5 CTAs (40 KB of tables each) per SM
   const unsigned long long grid = tiles < cap ? tiles : cap;
-  WB_LAUNCH("rng_fill_kernel", rng_fill_kernel<<<(unsigned)grid, RNG_THREADS, 0, stream>>>(d_state, g_d_pow, d_skip_or_null, d_count_or_null, max_count, d_out));
+  WB_LAUNCH("rng_fill_kernel", rng_fill_kernel<<<(unsigned)grid, RNG_THREADS, 0, stream>>>(d_state, g_d_pow, d_skip_or_null, d_count_or_null, max_count, d_out, d_skip2, d_count_sub));
   WB_CUDA_CHECK(cudaGetLastError());
   return WB_OK;
 }

@@ -106,9 +106,12 @@ WbRngState *wb_rng_global_state();         // device pointer to the global state
 void wb_rng_host_jump(uint32_t s[4], unsigned long long n);
 // out[i] = value of the (*d_skip + i + 1)-th randn() call after state *d_state (d_skip null = 0); does not
 // advance the state.
+// d_skip2 (added to the skip) and d_count_sub (subtracted from the count) position a fill on a sub-range of a stage's
+// draws straight from its offsets array: skip2 = count_sub = &offsets[begin], count = &offsets[end].
 int wb_rng_fill(const WbRngState *d_state, const unsigned long long *d_skip_or_null,
                 const unsigned long long *d_count_or_null, unsigned long long max_count, double *d_out,
-                cudaStream_t stream);
+                cudaStream_t stream, const unsigned long long *d_skip2 = nullptr,
+                const unsigned long long *d_count_sub = nullptr);
 // *d_state <- M^(*d_count + *d_count2) *d_state (either pointer may be null = 0)
 int wb_rng_advance(WbRngState *d_state, const unsigned long long *d_count, const unsigned long long *d_count2_or_null,
                    cudaStream_t stream);
