@@ -650,44 +650,106 @@ __device__ __forceinline__ void wb_dmma_8x8x4(double &d0, double &d1, double a, 
                : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(RF_WARPS * 32, 3) refine_mma_kernel(RefineParams p, int *__restrict__ ticket) {
+// Per-candidate constants of the refinement, computed by ONE THREAD per own candidate (refine_setup_kernel) instead of
+// redundantly by the 32 lanes of the warp that accumulates the candidate: window half length, FFT size, harmonic bins,
+// the first window sample of each of the seven copies, the window's one-sample rotation and -- on grids where the
+// windows are symmetric about a sample -- the starting rotations of the four pair sequences and the window angles of
+// the four samples with an end rule.
+struct RefineSetup {
+  double f0, s1, c1;            // candidate; sin / cos of 2 pi / window length
+  double init_sn[4], init_cs[4];  // symmetric case: sin / cos of 2 pi t / window length, t = 0 .. 3
+  double edge_sn[4], edge_cs[4];  // symmetric case: window angle of samples 0, 1, 2, 2 hw (the reference's expression)
+  int src, own_j, hw, log2fft, nh, symmetric, active, pad;
+  int idx[8];                   // harmonic bins (6 used)
+  int basic_index[8];           // first window sample of copy o (7 used)
+};
+
+__global__ void __launch_bounds__(128) refine_setup_kernel(RefineParams p, RefineSetup *__restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= p.nc_and_count[1]) return;
+  const double fs = p.actual_fs;
+  const double two_pi = 2.0 * WB_PI;
+  RefineSetup r;
+  const int item = p.work[c];
+  r.src = item >> 5; r.own_j = item & 31;
+  const double current_f0 = p.own[(size_t)r.src * p.own_cap + r.own_j];
+  r.f0 = current_f0;
+  const int hw = static_cast<int>(1.5 * fs / current_f0 + 1.0);
+  r.hw = hw;
+  const double window_length_in_time = (2.0 * hw + 1.0) / fs;
+  r.log2fft = 2 + (31 - __clz(2 * hw + 1));  // 2 + int(log2(len)), len odd
+  const int fft_size = 1 << r.log2fft;
+  r.nh = wb_min_i(static_cast<int>(fs / 2.0 / current_f0), 6);
+  for (int g = 0; g < 8; ++g) r.idx[g] = g < 6 ? wb_round(current_f0 * fft_size / fs * (g + 1)) : 0;
+  sincos(two_pi / (2 * hw + 1), &r.s1, &r.c1);
+  const int i_c = hw + 1;
+  r.active = 0; r.symmetric = 1; r.pad = 0;
+  int ref_bi = 0;
+  double ref_pos = 0.0;
+  bool have_ref = false;
+  for (int o = 0; o < 8; ++o) {
+    const int frame = (o <= 3) ? r.src + o : r.src - (o - 3);
+    const bool act = o < 7 && frame >= 0 && frame < p.f0_length;
+    const double current_position = frame * p.frame_period / 1000.0;
+    const double base_time0 = (-hw + 0) / fs;
+    const int bi = wb_round((current_position + base_time0) * fs + 0.001);
+    r.basic_index[o] = bi;
+    if (act) {
+      r.active |= 1 << o;
+      // the reference's own expression for the window argument of the centre sample: zero when it is on the grid
+      const double centre = ((bi + i_c) - 1.0) / fs - current_position;
+      if (!(fabs(centre) * fs < 1e-6)) r.symmetric = 0;
+      if (!have_ref) { have_ref = true; ref_bi = bi; ref_pos = current_position; }
+    }
+  }
+  for (int t = 0; t < 4; ++t) {
+    r.init_sn[t] = 0.0; r.init_cs[t] = 1.0; r.edge_sn[t] = 0.0; r.edge_cs[t] = 1.0;
+    if (r.symmetric) {
+      sincos(two_pi * t / (2 * hw + 1), &r.init_sn[t], &r.init_cs[t]);
+      const int i = t < 3 ? t : 2 * hw;
+      const double tmp = ((ref_bi + i) - 1.0) / fs - ref_pos;
+      sincos(two_pi * tmp / window_length_in_time, &r.edge_sn[t], &r.edge_cs[t]);
+    }
+  }
+  out[c] = r;
+}
+
+__global__ void __launch_bounds__(RF_WARPS * 32, 3) refine_mma_kernel(RefineParams p, const RefineSetup *__restrict__ setup,
+                                                                       int *__restrict__ ticket) {
   const int lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int nc = p.nc_and_count[0];
   const int n_own = p.nc_and_count[1];
   const double fs = p.actual_fs;
   const double two_pi = 2.0 * WB_PI;
-  // The ticket of the NEXT candidate, its work item and its f0 are requested while the current candidate is set up and
-  // accumulated (the chain atomic -> work[] -> own[] is three dependent round trips to L2): the atomic is issued at the
-  // top of an iteration, its result is used after the set-up arithmetic, the item after the accumulation loop.
+  // The ticket of the NEXT candidate is requested at the top of an iteration and used at its end (the atomic is a
+  // round trip to L2).
   int c = 0;
   if (lane == 0) c = atomicAdd(ticket, 1);
   c = __shfl_sync(0xffffffffu, c, 0);
-  int item = c < n_own ? p.work[c] : 0;
-  double current_f0 = c < n_own ? p.own[(size_t)(item >> 5) * p.own_cap + (item & 31)] : 100.0;
   while (c < n_own) {
-    const int src = item >> 5, own_j = item & 31;
     int tick = 0;
     if (lane == 0) tick = atomicAdd(ticket, 1);
-    const int hw = static_cast<int>(1.5 * fs / current_f0 + 1.0);
+    const RefineSetup *rs = setup + c;
+    const int src = rs->src, own_j = rs->own_j;
+    const double current_f0 = rs->f0;
+    const int hw = rs->hw;
     const int len = 2 * hw + 1;
     const double window_length_in_time = (2.0 * hw + 1.0) / fs;
-    const int log2fft = 2 + (31 - __clz(2 * hw + 1));  // 2 + int(log2(len)), len odd
+    const int log2fft = rs->log2fft;
     const int fft_size = 1 << log2fft;
-    const int nh = wb_min_i(static_cast<int>(fs / 2.0 / current_f0), 6);
+    const int nh = rs->nh;
     const cplx *T = p.tw[log2fft];
     const int mask = fft_size - 1;
     // row of this lane: copy o = g (row 7 is padding)
     const int o = g;
     const int frame = (o <= 3) ? src + o : src - (o - 3);
-    const bool row_active = o < 7 && frame >= 0 && frame < p.f0_length;
+    const bool row_active = (rs->active >> o) & 1;
     const double current_position = frame * p.frame_period / 1000.0;
-    const double base_time0 = (-hw + 0) / fs;
-    const int basic_index = wb_round((current_position + base_time0) * fs + 0.001);
+    const int basic_index = rs->basic_index[o];
     // column of this lane: harmonic g (columns 6, 7 are padding)
-    const int idx_col = g < 6 ? wb_round(current_f0 * fft_size / fs * (g + 1)) : 0;
-    double s1, c1;
-    sincos(two_pi / (2 * hw + 1), &s1, &c1);
+    const int idx_col = rs->idx[g];
+    const double s1 = rs->s1, c1 = rs->c1;
     // rotation by four samples from the one-sample rotation (two angle doublings; 1 - 2 sin^2 keeps the cosine accurate)
     const double s2 = 2.0 * s1 * c1, c2a = 1.0 - 2.0 * s1 * s1;
     const double sg = 2.0 * s2 * c2a, cg = 1.0 - 2.0 * s2 * s2;
@@ -695,14 +757,9 @@ __global__ void __launch_bounds__(RF_WARPS * 32, 3) refine_mma_kernel(RefinePara
     double mc0 = 0.0, mc1 = 0.0, ms0 = 0.0, ms1 = 0.0, dc0 = 0.0, dc1 = 0.0, ds0 = 0.0, ds1 = 0.0;
     const int y_first = basic_index - 1, y_last = p.y_length - 1;
     const int i_c = hw + 1;   // the sample the window is centred on
-    // the reference's own expression for the window argument of that sample: zero when the centre is on the grid
-    const double centre = ((basic_index + i_c) - 1.0) / fs - current_position;
-    const bool symmetric = __all_sync(0xffffffffu, !row_active || fabs(centre) * fs < 1e-6);
-    // one window sample by the reference's expressions (harvest.cpp:762-803): main and differentiated window times y
-    auto sample = [&](int i, double &vm, double &vd) {
-      const double tmp = ((basic_index + i) - 1.0) / fs - current_position;
-      double sn, cs;
-      sincos(two_pi * tmp / window_length_in_time, &sn, &cs);
+    const bool symmetric = rs->symmetric != 0;
+    // main and differentiated window times y for window sample i at window angle (sn, cs) (harvest.cpp:762-803)
+    auto sample_at = [&](int i, double sn, double cs, double &vm, double &vd) {
       const double yv = row_active ? p.y[wb_max_i(0, wb_min_i(y_last, y_first + i))] : 0.0;
       double dwin = sn * fma(dw_b, cs, dw_a);
       if (i == 0) dwin = -rf_window(cs * c1 - sn * s1) / 2.0;            // -w[1] / 2
@@ -710,8 +767,6 @@ __global__ void __launch_bounds__(RF_WARPS * 32, 3) refine_mma_kernel(RefinePara
       vm = rf_window(cs) * yv;
       vd = dwin * yv;
     };
-    const int c_next = __shfl_sync(0xffffffffu, tick, 0);
-    const int item_next = c_next < n_own ? p.work[c_next] : 0;
     if (symmetric) {
       // Frame times on whole decimated samples (actual_fs a multiple of 1000 Hz): the window is even and its
       // differentiated version odd about the centre sample, so the samples at +j and -j share one twiddle
@@ -721,8 +776,7 @@ __global__ void __launch_bounds__(RF_WARPS * 32, 3) refine_mma_kernel(RefinePara
       // Pairs j = 1 .. hw - 2 (samples 3 .. 2 hw - 1); the five samples without a partner or with an end rule
       // (0, 1, 2, hw + 1, 2 hw) follow in two more steps.
       // (pair index j = 0 is the centre sample itself: window 1, differentiated window 0, no partner)
-      double sn, cs;
-      sincos(two_pi * t / (2 * hw + 1), &sn, &cs);
+      double sn = rs->init_sn[t], cs = rs->init_cs[t];
       const int yc = y_first + i_c;
       const int n_pairs = hw - 2;
       int j = t;
@@ -760,7 +814,7 @@ __global__ void __launch_bounds__(RF_WARPS * 32, 3) refine_mma_kernel(RefinePara
         bool use = i < len && i != i_c;
         if (t == 3) use = use && i > 2;
         double vm = 0.0, vd = 0.0;
-        if (use) sample(i, vm, vd);
+        if (use) sample_at(i, rs->edge_sn[t], rs->edge_cs[t], vm, vd);
         const cplx w = __ldg(&T[(idx_col * (i - i_c)) & mask]);
         wb_dmma_8x8x4(mc0, mc1, vm, w.x);
         wb_dmma_8x8x4(ms0, ms1, vm, w.y);
@@ -799,7 +853,6 @@ __global__ void __launch_bounds__(RF_WARPS * 32, 3) refine_mma_kernel(RefinePara
         cs = c2;
       }
     }
-    const double f0_next = c_next < n_own ? p.own[(size_t)(item_next >> 5) * p.own_cap + (item_next & 31)] : 100.0;
     // fixF0 (harvest.cpp:844-878) for harmonics 2t and 2t + 1 of copy g; spectra are conjugated by the reference
     // (harvest.cpp:829-841): main = (mr, -mi), diff = (dr, -di)
     double inst[2], amp[2], dev[2];
@@ -844,7 +897,7 @@ __global__ void __launch_bounds__(RF_WARPS * 32, 3) refine_mma_kernel(RefinePara
       p.cand[at] = refined;
       p.score[at] = sc;
     }
-    c = c_next; item = item_next; current_f0 = f0_next;
+    c = __shfl_sync(0xffffffffu, tick, 0);
   }
 }
 
@@ -1134,7 +1187,11 @@ int wb_harvest_run_basic(WbHarvestPlan *pl, WbWorkspace *ws, const double *d_x, 
       p.tw[l] = wb_twiddle_table(1 << l);
       if (!p.tw[l]) return WB_ERR_CUDA;
     }
-    WB_LAUNCH("refine_kernel", refine_mma_kernel<<<wb_sm_count() * 8, RF_WARPS * 32, 0, stream>>>(p, d_nc + 2));
+    // per-candidate constants by one thread per candidate, then the accumulation by one warp per candidate
+    RefineSetup *d_setup = (RefineSetup *)ws->get("hv_refine_setup", sizeof(RefineSetup) * (size_t)Lb * own_cap);
+    if (!d_setup) return WB_ERR_CUDA;
+    WB_LAUNCH("refine_setup_kernel", refine_setup_kernel<<<(Lb * own_cap + 127) / 128, 128, 0, stream>>>(p, d_setup));
+    WB_LAUNCH("refine_kernel", refine_mma_kernel<<<wb_sm_count() * 8, RF_WARPS * 32, 0, stream>>>(p, d_setup, d_nc + 2));
     WB_CUDA_CHECK(cudaGetLastError());
   }
   (void)n_cs;
