@@ -664,54 +664,66 @@ struct RefineSetup {
   int basic_index[8];           // first window sample of copy o (7 used)
 };
 
+// eight threads per candidate: thread k takes copy k and harmonic k, threads 0 .. 3 one starting rotation and one
+// edge-sample angle each
 __global__ void __launch_bounds__(128) refine_setup_kernel(RefineParams p, RefineSetup *__restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= p.nc_and_count[1]) return;
+  const int lane = threadIdx.x & 31, k = lane & 7;
+  const int n_own = p.nc_and_count[1];
   const double fs = p.actual_fs;
   const double two_pi = 2.0 * WB_PI;
-  RefineSetup r;
-  const int item = p.work[c];
-  r.src = item >> 5; r.own_j = item & 31;
-  const double current_f0 = p.own[(size_t)r.src * p.own_cap + r.own_j];
-  r.f0 = current_f0;
+  // a warp takes four candidates per step (the loop bound is warp-uniform: the ballots below need the whole warp)
+  const int warp_first = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 4;
+  const int warp_stride = ((gridDim.x * blockDim.x) >> 5) * 4;
+  for (int c0 = warp_first; c0 < n_own; c0 += warp_stride) {
+  const int c = c0 + (lane >> 3);
+  const bool live = c < n_own;
+  const int item = live ? p.work[c] : 0;
+  const int src = item >> 5, own_j = item & 31;
+  const double current_f0 = live ? p.own[(size_t)src * p.own_cap + own_j] : 100.0;
   const int hw = static_cast<int>(1.5 * fs / current_f0 + 1.0);
-  r.hw = hw;
   const double window_length_in_time = (2.0 * hw + 1.0) / fs;
-  r.log2fft = 2 + (31 - __clz(2 * hw + 1));  // 2 + int(log2(len)), len odd
-  const int fft_size = 1 << r.log2fft;
-  r.nh = wb_min_i(static_cast<int>(fs / 2.0 / current_f0), 6);
-  for (int g = 0; g < 8; ++g) r.idx[g] = g < 6 ? wb_round(current_f0 * fft_size / fs * (g + 1)) : 0;
-  sincos(two_pi / (2 * hw + 1), &r.s1, &r.c1);
+  const int log2fft = 2 + (31 - __clz(2 * hw + 1));  // 2 + int(log2(len)), len odd
+  const int fft_size = 1 << log2fft;
   const int i_c = hw + 1;
-  r.active = 0; r.symmetric = 1; r.pad = 0;
-  int ref_bi = 0;
-  double ref_pos = 0.0;
-  bool have_ref = false;
-  for (int o = 0; o < 8; ++o) {
-    const int frame = (o <= 3) ? r.src + o : r.src - (o - 3);
-    const bool act = o < 7 && frame >= 0 && frame < p.f0_length;
-    const double current_position = frame * p.frame_period / 1000.0;
-    const double base_time0 = (-hw + 0) / fs;
-    const int bi = wb_round((current_position + base_time0) * fs + 0.001);
-    r.basic_index[o] = bi;
-    if (act) {
-      r.active |= 1 << o;
-      // the reference's own expression for the window argument of the centre sample: zero when it is on the grid
-      const double centre = ((bi + i_c) - 1.0) / fs - current_position;
-      if (!(fabs(centre) * fs < 1e-6)) r.symmetric = 0;
-      if (!have_ref) { have_ref = true; ref_bi = bi; ref_pos = current_position; }
-    }
-  }
-  for (int t = 0; t < 4; ++t) {
-    r.init_sn[t] = 0.0; r.init_cs[t] = 1.0; r.edge_sn[t] = 0.0; r.edge_cs[t] = 1.0;
-    if (r.symmetric) {
-      sincos(two_pi * t / (2 * hw + 1), &r.init_sn[t], &r.init_cs[t]);
-      const int i = t < 3 ? t : 2 * hw;
+  // copy k (row 7 is padding)
+  const int frame = (k <= 3) ? src + k : src - (k - 3);
+  const bool act = live && k < 7 && frame >= 0 && frame < p.f0_length;
+  const double current_position = frame * p.frame_period / 1000.0;
+  const double base_time0 = (-hw + 0) / fs;
+  const int bi = wb_round((current_position + base_time0) * fs + 0.001);
+  // the reference's own expression for the window argument of the centre sample: zero when it is on the grid
+  const double centre = ((bi + i_c) - 1.0) / fs - current_position;
+  const unsigned grp = 0xffu << (lane & 24);
+  const unsigned act_bits = (__ballot_sync(0xffffffffu, act) & grp) >> (lane & 24);
+  const unsigned off_bits = (__ballot_sync(0xffffffffu, act && !(fabs(centre) * fs < 1e-6)) & grp) >> (lane & 24);
+  const int symmetric = off_bits == 0u ? 1 : 0;
+  // the first active copy supplies the edge-sample angles of the symmetric case (they are the same for every copy there)
+  const int ref_lane = (lane & 24) + (act_bits ? __ffs(act_bits) - 1 : 0);
+  const int ref_bi = __shfl_sync(0xffffffffu, bi, ref_lane);
+  const double ref_pos = __shfl_sync(0xffffffffu, current_position, ref_lane);
+  if (!live) continue;
+  RefineSetup *r = out + c;
+  r->idx[k] = k < 6 ? wb_round(current_f0 * fft_size / fs * (k + 1)) : 0;
+  r->basic_index[k] = bi;
+  if (k < 4) {
+    double sn = 0.0, cs = 1.0, esn = 0.0, ecs = 1.0;
+    if (symmetric) {
+      sincos(two_pi * k / (2 * hw + 1), &sn, &cs);
+      const int i = k < 3 ? k : 2 * hw;
       const double tmp = ((ref_bi + i) - 1.0) / fs - ref_pos;
-      sincos(two_pi * tmp / window_length_in_time, &r.edge_sn[t], &r.edge_cs[t]);
+      sincos(two_pi * tmp / window_length_in_time, &esn, &ecs);
     }
+    r->init_sn[k] = sn; r->init_cs[k] = cs; r->edge_sn[k] = esn; r->edge_cs[k] = ecs;
+  } else if (k == 4) {
+    double s1, c1;
+    sincos(two_pi / (2 * hw + 1), &s1, &c1);
+    r->f0 = current_f0; r->s1 = s1; r->c1 = c1;
+  } else if (k == 5) {
+    r->src = src; r->own_j = own_j; r->hw = hw; r->log2fft = log2fft;
+    r->nh = wb_min_i(static_cast<int>(fs / 2.0 / current_f0), 6);
+    r->symmetric = symmetric; r->active = (int)act_bits; r->pad = 0;
   }
-  out[c] = r;
+  }
 }
 
 __global__ void __launch_bounds__(RF_WARPS * 32, 3) refine_mma_kernel(RefineParams p, const RefineSetup *__restrict__ setup,
@@ -1190,7 +1202,7 @@ int wb_harvest_run_basic(WbHarvestPlan *pl, WbWorkspace *ws, const double *d_x, 
     // per-candidate constants by one thread per candidate, then the accumulation by one warp per candidate
     RefineSetup *d_setup = (RefineSetup *)ws->get("hv_refine_setup", sizeof(RefineSetup) * (size_t)Lb * own_cap);
     if (!d_setup) return WB_ERR_CUDA;
-    WB_LAUNCH("refine_setup_kernel", refine_setup_kernel<<<(Lb * own_cap + 127) / 128, 128, 0, stream>>>(p, d_setup));
+    WB_LAUNCH("refine_setup_kernel", refine_setup_kernel<<<wb_sm_count() * 8, 128, 0, stream>>>(p, d_setup));
     WB_LAUNCH("refine_kernel", refine_mma_kernel<<<wb_sm_count() * 8, RF_WARPS * 32, 0, stream>>>(p, d_setup, d_nc + 2));
     WB_CUDA_CHECK(cudaGetLastError());
   }
