@@ -75,6 +75,22 @@ def test_long_utterance(wb, signals):
     _compare(_chain(wb, x, fs), ref, "70 s utterance")
 
 
+def test_harvest_beyond_128_overlap_save_blocks(wb, signals):
+    """150 s in one Harvest call (188 overlap-save blocks): the per-block edge runs are concatenated by a prefix sum
+    over up to 1024 blocks; past that (a little over 16 minutes) the call refuses before launching anything."""
+    fs = 16000
+    x = signals.synth_speech(fs, 150.0, seed=26)
+    ref, _ = refbin.run_reference(x, fs, stages="h")
+    h = wb.Harvest(fs, wb.HarvestOption(f0_floor=40.0, f0_ceil=800.0, frame_period=5.0))
+    tpos, f0 = h.compute(x)
+    assert np.array_equal(tpos, ref["tpos"])
+    assert np.array_equal(f0 > 0, ref["f0"] > 0), "voicing decisions differ"
+    np.testing.assert_allclose(f0, ref["f0"], rtol=1e-4, atol=0)   # BASELINE.json tolerance (1e-4 relative)
+    too_long = np.zeros(8000 * 20 * 60)
+    with pytest.raises(wb.WorldB200Error):
+        wb.Harvest(8000).compute(too_long)
+
+
 def test_ragged_lengths(wb, signals):
     """Lengths that are not multiples of the decimation ratio / frame hop."""
     fs = 48000

@@ -77,6 +77,7 @@ struct HostTrace {
 // host memcpy of chunk k.
 const int kRowChunks = 8;
 const int kSynRanges = 4;   // sample ranges of the pipelined host Synthesis::compute
+const double kSynRangeEnd[kSynRanges] = {0.30, 0.58, 0.82, 1.0};   // (a range costs ~0.1 ms whatever its size: few, the last one short)
 
 // Persistent helper threads for the row copies (spawning threads per chunk cost more than the copies).
 // Workers spin briefly between jobs -- the chunks of one matrix follow each other within microseconds --
@@ -712,17 +713,23 @@ int wb_synthesis_compute(wb_synthesis_t *h, const double *f0, int f0_length, con
     // between have landed: the impulse responses run under the remaining uploads.
     WbRngCursor cur = global_cursor();
     cur.advance = false;
+    // (WB_TRACE: device-side timeline of the call)
+    cudaEvent_t tev[4 + 2 * kSynRanges] = {nullptr};
+    if (tr.on) for (auto &e : tev) cudaEventCreate(&e);
+    if (tr.on) cudaEventRecord(tev[0], st);
+    if ((rc = wb_synthesis_prepare(&h->ws, h->fft_size, st))) return rc;
     WB_CUDA_CHECK(cudaEventRecord(h->ev_f0, st));
     WB_CUDA_CHECK(cudaStreamWaitEvent(h->side, h->ev_f0, 0));
     if ((rc = wb_synthesis_timebase(&h->ws, h->fs, h->fft_size, h->frame_period_ms, d_f, f0_length, out_length, h->side, nullptr)))
       return rc;
     WB_CUDA_CHECK(cudaEventRecord(h->ev_tb, h->side));
+    if (tr.on) cudaEventRecord(tev[1], h->side);
     WB_CUDA_CHECK(cudaEventRecord(h->ev_start, st));            // (d_sp / d_ap may still be read by the previous call's kernels)
     WB_CUDA_CHECK(cudaStreamWaitEvent(h->copy, h->ev_start, 0));
     int row_done = 0;
     int s_end[kSynRanges];
     for (int c = 0; c < kSynRanges; ++c) {
-      s_end[c] = (int)((long long)out_length * (c + 1) / kSynRanges);
+      s_end[c] = c == kSynRanges - 1 ? out_length : (int)(out_length * kSynRangeEnd[c]);
       // every frame a pulse reaching into [.., s_end) interpolates between (see StreamPlan.rows)
       int row_hi = (c == kSynRanges - 1) ? f0_length : (int)((s_end[c] + h->fft_size) / hop) + 3;
       if (row_hi > f0_length) row_hi = f0_length;
@@ -733,23 +740,41 @@ int wb_synthesis_compute(wb_synthesis_t *h, const double *f0, int f0_length, con
         row_done = row_hi;
       }
       WB_CUDA_CHECK(cudaEventRecord(h->ev_rows[c], h->copy));
+      if (tr.on) cudaEventRecord(tev[4 + c], h->copy);
     }
     tr.mark("uploads enqueued");
+    // The ranges alternate between the library stream and the (by then idle) time-base stream, a scratch set each:
+    // a range is rendered while the one before it still is, and goes home as soon as it is complete, so after the
+    // last rows have landed only one short range and its download remain.
     WB_CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_tb, 0));
     for (int c = 0; c < kSynRanges; ++c) {
       const int s_begin = c == 0 ? 0 : s_end[c - 1];
-      WB_CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_rows[c], 0));
+      cudaStream_t cs = (c & 1) ? h->side : st;
       if ((rc = wb_synthesis_render_range(&h->ws, h->fs, h->fft_size, h->frame_period_ms, f0_length, d_sp, d_ap, 0, f0_length,
-                                          out_length, s_begin, s_end[c], d_out + s_begin, max_f0 + 1.0, cur, st)))
+                                          out_length, s_begin, s_end[c], d_out + s_begin, max_f0 + 1.0, cur, cs, c & 1, h->ev_rows[c])))
         return rc;
-      // (each range goes home while the next one is rendered: the waveform is small next to the matrices)
+      if (s_end[c] > s_begin)
+        WB_CUDA_CHECK(cudaMemcpyAsync(out + s_begin, d_out + s_begin, sizeof(double) * (size_t)(s_end[c] - s_begin), cudaMemcpyDeviceToHost, cs));
+      if (tr.on) cudaEventRecord(tev[4 + kSynRanges + c], cs);
     }
+    WB_CUDA_CHECK(cudaEventRecord(h->ev_f0, h->side));
+    WB_CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_f0, 0));
     unsigned long long *d_ncount = (unsigned long long *)h->ws.find("syn_ncount");
     if (!d_ncount) return WB_ERR_CUDA;
     if ((rc = wb_rng_advance(cur.state, d_ncount, nullptr, st))) return rc;   // what one compute() call draws
-    WB_CUDA_CHECK(cudaMemcpyAsync(out, d_out, sizeof(double) * out_length, cudaMemcpyDeviceToHost, st));
+    if (tr.on) cudaEventRecord(tev[2], st);
     WB_CUDA_CHECK(cudaStreamSynchronize(st));
     tr.mark("done");
+    if (tr.on) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, tev[0], tev[1]); fprintf(stderr, "[wb_trace]   device: time base done  %7.3f ms\n", ms);
+      for (int c = 0; c < kSynRanges; ++c) {
+        cudaEventElapsedTime(&ms, tev[0], tev[4 + c]); fprintf(stderr, "[wb_trace]   device: rows %d landed    %7.3f ms\n", c, ms);
+        cudaEventElapsedTime(&ms, tev[0], tev[4 + kSynRanges + c]); fprintf(stderr, "[wb_trace]   device: range %d home     %7.3f ms\n", c, ms);
+      }
+      cudaEventElapsedTime(&ms, tev[0], tev[2]); fprintf(stderr, "[wb_trace]   device: all joined      %7.3f ms\n", ms);
+      for (auto &e : tev) if (e) cudaEventDestroy(e);
+    }
     return h->ws.read_error_flag(st);
   }
   // pulse list + excitation noise on the side stream (needs f0 only), overlapping the row uploads below

@@ -43,6 +43,7 @@ struct CtParams {
   const cplx *twiddle;              // fft_size entries
   const double *noise;              // randn stream segment of this call
   const unsigned long long *noise_off;  // exclusive offsets per frame
+  int noise_origin;                     // >= 0: the noise buffer starts at the draws of this frame (offsets relative to it)
   double *sp;                       // [f0_length][fft_size/2+1]
   int seg_capacity;
   int *error_flag;
@@ -67,7 +68,7 @@ __global__ void __launch_bounds__(256, 4) ct_frame_kernel(CtParams p) {
   const int fs = p.fs;
   const int hw = wb_round(1.5 * fs / f0);
   const int wlen = 2 * hw + 1;
-  const double *noise = p.noise + p.noise_off[frame];
+  const double *noise = p.noise + (p.noise_off[frame] - (p.noise_origin >= 0 ? p.noise_off[p.noise_origin] : 0ull));
 
   // ---- F0-adaptive windowing (cheaptrick.cpp:137-196)
   const int origin = wb_round(p.tpos[frame] * fs + 0.001);
@@ -159,6 +160,16 @@ int wb_cheaptrick_run(WbWorkspace *ws, int fs, int fft_size, double q1, double f
   double *d_noise = (double *)ws->get("noise_ct", sizeof(double) * max_noise);
   if (!d_offsets || !d_noise) return WB_ERR_CUDA;
 
+  // Row chunks (host API: every finished chunk goes home while the next ones compute) alternate between two streams
+  // with a noise buffer each: the randn() fill of a chunk runs beside the frames of the chunk before it.
+  const bool row_chunks = chunks && chunks->n > 1 && !range && f0_length >= 64;
+  double *d_noise_b = nullptr;
+  if (row_chunks) {
+    int widest = 0;
+    for (int c = 0; c < chunks->n; ++c) widest = wb_max_i(widest, chunks->bounds[c + 1] - chunks->bounds[c]);
+    d_noise_b = (double *)ws->get("noise_ct_b", sizeof(double) * (unsigned long long)widest * (unsigned long long)(fft_size + bins));
+    if (!d_noise_b) return WB_ERR_CUDA;
+  }
   if (rng.wait_skip_in) WB_CUDA_CHECK(cudaStreamWaitEvent(stream, rng.wait_skip_in, 0));
   WB_LAUNCH("ct_count_scan_kernel", ct_count_scan_kernel<<<1, 1024, 0, stream>>>(d_f0, f0_length, fs, fft_size, f0_floor_internal,
                                                                               d_offsets, rng.skip_in, rng.skip_out));  // d_offsets[f0_length] = total
@@ -174,7 +185,7 @@ int wb_cheaptrick_run(WbWorkspace *ws, int fs, int fft_size, double q1, double f
     if ((rc = wb_range_offsets(d_offsets, *range, d_rel, rng.skip_in, d_pos, d_pos + 1, stream))) return rc;
     if (n_rows > 0 && (rc = wb_rng_fill(rng.state, d_pos, d_pos + 1, max_noise, d_noise, stream))) return rc;
     d_noise_off = d_rel;
-  } else {
+  } else if (!row_chunks) {
     rc = wb_rng_fill(rng.state, rng.skip_in, d_offsets + f0_length, max_noise, d_noise, stream);
     if (rc) return rc;
   }
@@ -182,7 +193,7 @@ int wb_cheaptrick_run(WbWorkspace *ws, int fs, int fft_size, double q1, double f
   CtParams p;
   p.x = d_x; p.x_length = x_length; p.tpos = d_tpos; p.f0 = d_f0; p.f0_length = f0_length;
   p.fs = fs; p.fft_size = fft_size; p.log2nc = log2n - 1; p.q1 = q1; p.f0_floor = f0_floor_internal;
-  p.twiddle = tw; p.noise = d_noise; p.noise_off = d_noise_off;
+  p.twiddle = tw; p.noise = d_noise; p.noise_off = d_noise_off; p.noise_origin = -1;
   p.sp = (range && d_sp) ? d_sp - (size_t)range->begin * bins : d_sp;   // (rows are addressed by absolute frame)
   p.seg_capacity = fft_size / 2 + fft_size / 4 + 8;
   p.error_flag = ws->error_flag();
@@ -191,26 +202,32 @@ int wb_cheaptrick_run(WbWorkspace *ws, int fs, int fft_size, double q1, double f
   p.frame_begin = range ? range->begin : 0;
   if (n_rows <= 0) {
     // (an empty range still takes part in the stream bookkeeping below)
-  } else if (!chunks || chunks->n <= 1) {
+  } else if (!row_chunks) {
     rc = WB_DISPATCH_LOG2(log2n, 8, 13, {
       if (cudaFuncSetAttribute(ct_frame_kernel<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WB_ERR_CUDA;
       WB_LAUNCH("ct_frame_kernel", ct_frame_kernel<L2><<<n_rows, threads, smem, stream>>>(p));
     });
     if (rc) return rc;
-    if (chunks && chunks->n == 1) WB_CUDA_CHECK(cudaEventRecord(chunks->ev[0], stream));
+    if (chunks) for (int c = 0; c < chunks->n; ++c) WB_CUDA_CHECK(cudaEventRecord(chunks->ev[c], stream));
   } else {
-    // row ranges on alternating streams (see WbRowChunks); everything before this point is on `stream`
+    // everything before this point is on `stream`
     WB_CUDA_CHECK(cudaEventRecord(chunks->ev_ready, stream));
     WB_CUDA_CHECK(cudaStreamWaitEvent(chunks->alt, chunks->ev_ready, 0));
     for (int c = 0; c < chunks->n; ++c) {
       cudaStream_t cs = (c & 1) ? chunks->alt : stream;
-      const int count = chunks->bounds[c + 1] - chunks->bounds[c];
-      p.frame_begin = chunks->bounds[c];
-      if (count > 0) {
+      double *nb = (c & 1) ? d_noise_b : d_noise;
+      const int cb = chunks->bounds[c], ce = chunks->bounds[c + 1];
+      if ((rc = wb_rng_fill(rng.state, rng.skip_in, d_offsets + ce, (unsigned long long)(ce - cb) * (unsigned long long)(fft_size + bins), nb, cs,
+                            d_offsets + cb, d_offsets + cb)))
+        return rc;
+      if (ce > cb) {
+        p.frame_begin = cb;
+        p.noise = nb;
+        p.noise_origin = cb;
         rc = WB_DISPATCH_LOG2(log2n, 8, 13, {
           if (cudaFuncSetAttribute(ct_frame_kernel<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WB_ERR_CUDA;
           WbLaunchScope scope("ct_frame_kernel", cs);
-          ct_frame_kernel<L2><<<count, threads, smem, cs>>>(p);
+          ct_frame_kernel<L2><<<ce - cb, threads, smem, cs>>>(p);
         });
         if (rc) return rc;
       }

@@ -851,10 +851,22 @@ int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int
   WB_CUDA_CHECK(cudaGetLastError());
   if (rng.wait_skip_in) WB_CUDA_CHECK(cudaStreamWaitEvent(stream, rng.wait_skip_in, 0));
   int rc;
-  // second noise buffer of a split stage (the halves draw concurrently)
+  // Row chunks of a whole-utterance call alternate between two streams, one noise buffer each: the randn() fill of a
+  // chunk runs beside the frames of the chunk before it (integer work beside fp64 work) instead of in front of them.
+  // Two users: the fused pipeline (WbStageSplit: D4C_SPLIT chunks) and the host API's chunked download (WbRowChunks:
+  // an event per chunk for the copy stream).
+  const bool row_chunks = chunks && chunks->n > 1 && !range && phase == 0 && f0_length >= 64;
+  const int n_chunks = split ? D4C_SPLIT : row_chunks ? chunks->n : 1;
+  cudaStream_t alt = split ? split->alt : row_chunks ? chunks->alt : nullptr;
+  auto chunk_bound = [&](int c) -> int {
+    return split ? (int)((long long)f0_length * c / D4C_SPLIT) : chunks->bounds[c];
+  };
   double *d_noise_b = nullptr;
-  if (split) {
-    d_noise_b = (double *)ws->get("noise_d4c_b", sizeof(double) * (unsigned long long)(f0_length / D4C_SPLIT + 2) * 3ull * N);
+  if (n_chunks > 1) {
+    int widest = 0;
+    for (int c = 0; c < n_chunks; ++c) widest = max(widest, chunk_bound(c + 1) - chunk_bound(c));
+    const unsigned long long need_lt = (unsigned long long)(f0_length / 2 + 2) * N_lt, need_body = (unsigned long long)widest * 3ull * N;
+    d_noise_b = (double *)ws->get("noise_d4c_b", sizeof(double) * (need_lt > need_body ? need_lt : need_body));
     if (!d_noise_b) return WB_ERR_CUDA;
   }
   if (phase != 2) {
@@ -878,21 +890,21 @@ int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int
     WB_CUDA_CHECK(cudaGetLastError());
     return WB_OK;
   };
-  if (split) {
-    // D4C_SPLIT chunks of the rows alternate between two streams (one noise buffer each): the fill of a chunk runs
-    // beside the frames of the chunk before it
-    WB_CUDA_CHECK(cudaEventRecord(split->fork[0], stream));
-    WB_CUDA_CHECK(cudaStreamWaitEvent(split->alt, split->fork[0], 0));
-    for (int c = 0; c < D4C_SPLIT; ++c) {
-      const int cb = (int)((long long)f0_length * c / D4C_SPLIT), ce = (int)((long long)f0_length * (c + 1) / D4C_SPLIT);
-      cudaStream_t cs = (c & 1) ? split->alt : stream;
+  if (n_chunks > 1) {
+    // two halves (the decisions of all rows are needed before the body's draws can be counted)
+    cudaEvent_t fork = split ? split->fork[0] : chunks->ev_ready, join = split ? split->join[0] : chunks->ev[0];
+    WB_CUDA_CHECK(cudaEventRecord(fork, stream));
+    WB_CUDA_CHECK(cudaStreamWaitEvent(alt, fork, 0));
+    for (int c = 0; c < 2; ++c) {
+      const int cb = (int)((long long)f0_length * c / 2), ce = (int)((long long)f0_length * (c + 1) / 2);
+      cudaStream_t cs = (c & 1) ? alt : stream;
       double *nb = (c & 1) ? d_noise_b : d_noise;
       if ((rc = wb_rng_fill(rng.state, rng.skip_in, d_offsets + ce, (unsigned long long)(ce - cb) * N_lt, nb, cs, d_offsets + cb, d_offsets + cb)))
         return rc;
       if ((rc = launch_lt(cb, ce - cb, nb, d_offsets, cb, cs))) return rc;
     }
-    WB_CUDA_CHECK(cudaEventRecord(split->join[0], split->alt));
-    WB_CUDA_CHECK(cudaStreamWaitEvent(stream, split->join[0], 0));
+    WB_CUDA_CHECK(cudaEventRecord(join, alt));
+    WB_CUDA_CHECK(cudaStreamWaitEvent(stream, join, 0));
   } else {
     if (range) {
       if ((rc = wb_range_offsets(d_offsets, *range, d_rel, rng.skip_in, d_pos, d_pos + 1, stream))) return rc;
@@ -907,9 +919,10 @@ int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int
                                                                                   rng.skip_in, d_lt_total, d_skip_mid, d_skip_end));
   WB_CUDA_CHECK(cudaGetLastError());
   if (rng.record_skip_out) WB_CUDA_CHECK(cudaEventRecord(rng.record_skip_out, stream));
-  if (split) {
-    WB_CUDA_CHECK(cudaEventRecord(split->fork[1], stream));
-    WB_CUDA_CHECK(cudaStreamWaitEvent(split->alt, split->fork[1], 0));
+  if (n_chunks > 1) {
+    cudaEvent_t fork = split ? split->fork[1] : chunks->ev_ready;
+    WB_CUDA_CHECK(cudaEventRecord(fork, stream));
+    WB_CUDA_CHECK(cudaStreamWaitEvent(alt, fork, 0));
     // (the fills are enqueued chunk by chunk together with the frame kernels below)
   } else if (range) {
     if ((rc = wb_range_offsets(d_offsets, *range, d_rel, d_skip_mid, d_pos, d_pos + 1, stream))) return rc;
@@ -927,53 +940,40 @@ int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int
     const size_t smem = d4c_body_smem_bytes(N);
     const int threads = N / 16;     // one radix-16 butterfly per thread and pass
     p.frame_begin = row0;
-    if (split) {
-      for (int c = 0; c < D4C_SPLIT; ++c) {
-        const int cb = (int)((long long)f0_length * c / D4C_SPLIT), ce = (int)((long long)f0_length * (c + 1) / D4C_SPLIT);
-        cudaStream_t cs = (c & 1) ? split->alt : stream;
+    if (n_chunks > 1) {
+      for (int c = 0; c < n_chunks; ++c) {
+        const int cb = chunk_bound(c), ce = chunk_bound(c + 1);
+        cudaStream_t cs = (c & 1) ? alt : stream;
         double *nb = (c & 1) ? d_noise_b : d_noise;
         if ((rc = wb_rng_fill(rng.state, d_skip_mid, d_offsets + ce, (unsigned long long)(ce - cb) * 3ull * N, nb, cs, d_offsets + cb, d_offsets + cb)))
           return rc;
-        if (ce <= cb) continue;
-        p.frame_begin = cb;
-        p.noise = nb;
-        p.noise_origin = cb;
-        rc = WB_DISPATCH_LOG2(l, 9, 13, {
-          if (cudaFuncSetAttribute(d4c_body_kernel<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WB_ERR_CUDA;
-          WbLaunchScope scope("d4c_body_kernel", cs);
-          d4c_body_kernel<L2><<<ce - cb, threads, smem, cs>>>(p);
-        });
-        if (rc) return rc;
+        if (ce > cb) {
+          p.frame_begin = cb;
+          p.noise = nb;
+          p.noise_origin = cb;
+          rc = WB_DISPATCH_LOG2(l, 9, 13, {
+            if (cudaFuncSetAttribute(d4c_body_kernel<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WB_ERR_CUDA;
+            WbLaunchScope scope("d4c_body_kernel", cs);
+            d4c_body_kernel<L2><<<ce - cb, threads, smem, cs>>>(p);
+          });
+          if (rc) return rc;
+        }
+        if (!split) WB_CUDA_CHECK(cudaEventRecord(chunks->ev[c], cs));   // range c may go home
       }
-      WB_CUDA_CHECK(cudaEventRecord(split->join[1], split->alt));
-      WB_CUDA_CHECK(cudaStreamWaitEvent(stream, split->join[1], 0));
-    } else
-    if (!chunks || chunks->n <= 1) {
+      // the caller's stream continues (randn bookkeeping, later calls) after every chunk
+      if (split) {
+        WB_CUDA_CHECK(cudaEventRecord(split->join[1], alt));
+        WB_CUDA_CHECK(cudaStreamWaitEvent(stream, split->join[1], 0));
+      } else {
+        for (int c = 1; c < n_chunks; c += 2) WB_CUDA_CHECK(cudaStreamWaitEvent(stream, chunks->ev[c], 0));
+      }
+    } else {
       rc = WB_DISPATCH_LOG2(l, 9, 13, {
         if (cudaFuncSetAttribute(d4c_body_kernel<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WB_ERR_CUDA;
         WB_LAUNCH("d4c_body_kernel", d4c_body_kernel<L2><<<n_rows, threads, smem, stream>>>(p));
       });
       if (rc) return rc;
-      if (chunks && chunks->n == 1) WB_CUDA_CHECK(cudaEventRecord(chunks->ev[0], stream));
-    } else {
-      // row ranges on alternating streams (see WbRowChunks); everything before this point is on `stream`
-      WB_CUDA_CHECK(cudaEventRecord(chunks->ev_ready, stream));
-      WB_CUDA_CHECK(cudaStreamWaitEvent(chunks->alt, chunks->ev_ready, 0));
-      for (int c = 0; c < chunks->n; ++c) {
-        cudaStream_t cs = (c & 1) ? chunks->alt : stream;
-        const int count = chunks->bounds[c + 1] - chunks->bounds[c];
-        p.frame_begin = chunks->bounds[c];
-        if (count > 0) {
-          rc = WB_DISPATCH_LOG2(l, 9, 13, {
-            if (cudaFuncSetAttribute(d4c_body_kernel<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WB_ERR_CUDA;
-            WbLaunchScope scope("d4c_body_kernel", cs);
-            d4c_body_kernel<L2><<<count, threads, smem, cs>>>(p);
-          });
-          if (rc) return rc;
-        }
-        WB_CUDA_CHECK(cudaEventRecord(chunks->ev[c], cs));
-      }
-      for (int c = 1; c < chunks->n; c += 2) WB_CUDA_CHECK(cudaStreamWaitEvent(stream, chunks->ev[c], 0));
+      if (chunks) for (int c = 0; c < chunks->n; ++c) WB_CUDA_CHECK(cudaEventRecord(chunks->ev[c], stream));
     }
     WB_CUDA_CHECK(cudaGetLastError());
   }

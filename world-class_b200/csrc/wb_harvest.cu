@@ -460,20 +460,21 @@ __global__ void frame_time_kernel(int n, int frame_period, double *__restrict__ 
 }
 
 #define IV_THREADS 512
-#define IV_MAX_BLOCKS 128   /* overlap-save blocks per utterance: ~117 s of audio at the 8 kHz analysis rate */
+#define IV_MAX_BLOCKS 1024   /* overlap-save blocks per utterance: ~15 min of audio at the 8 kHz analysis rate */
 #define IV_PER_ITER ((IV_THREADS / 32) * 31)
 __global__ void __launch_bounds__(IV_THREADS) interval_kernel(IntervalParams p) {
   __shared__ int s_off[IV_MAX_BLOCKS + 1];
   // channel * 4 + kind; the high channels have the most zero crossings: schedule them first
   const int ct = gridDim.x - 1 - blockIdx.x;
   const int *cnt = p.seg_count + (size_t)ct * p.n_blocks;
+  const int nb = p.n_blocks;
   if (threadIdx.x < 32) {
     // exclusive offsets of the per-block edge runs (n_blocks <= IV_MAX_BLOCKS): the ordered edge list of
-    // this (channel, kind) is their concatenation.  Lane l owns blocks 4 l .. 4 l + 3.
+    // this (channel, kind) is their concatenation.  Lane l owns the blocks [l per, (l + 1) per).
     const int lane = threadIdx.x;
-    int c[4], sum = 0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) { c[q] = (4 * lane + q < p.n_blocks) ? cnt[4 * lane + q] : 0; sum += c[q]; }
+    const int per = (nb + 31) >> 5, b0 = lane * per, b1 = min(b0 + per, nb);
+    int sum = 0;
+    for (int b = b0; b < b1; ++b) sum += cnt[b];
     int incl = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -481,17 +482,16 @@ __global__ void __launch_bounds__(IV_THREADS) interval_kernel(IntervalParams p) 
       if (lane >= o) incl += t;
     }
     int run = incl - sum;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) { s_off[4 * lane + q] = run; run += c[q]; }
-    if (lane == 31) { s_off[IV_MAX_BLOCKS] = run; p.ecount[ct] = min(run, p.ecap); }
+    for (int b = b0; b < b1; ++b) { s_off[b] = run; run += cnt[b]; }
+    if (lane == 31) { s_off[nb] = incl; p.ecount[ct] = min(incl, p.ecap); }
   }
   __syncthreads();
-  const int total = min(s_off[IV_MAX_BLOCKS], p.ecap);
+  const int total = min(s_off[nb], p.ecap);
   const int ni = total < 2 ? 0 : total - 1;  // number of intervals
   const double *seg = p.seg_edges + (size_t)ct * p.n_blocks * p.bcap;
-  // edge k of the concatenated list: last block b with s_off[b] <= k (blocks beyond n_blocks hold the total)
+  // edge k of the concatenated list: last block b with s_off[b] <= k
   auto edge = [&](int k) -> double {
-    int lo = 0, hi = IV_MAX_BLOCKS - 1;
+    int lo = 0, hi = nb - 1;
     while (lo < hi) {
       const int mid = (lo + hi + 1) >> 1;
       if (s_off[mid] <= k) lo = mid; else hi = mid - 1;
@@ -1057,7 +1057,7 @@ int wb_harvest_run_basic(WbHarvestPlan *pl, WbWorkspace *ws, const double *d_x, 
   const int Lb = static_cast<int>(1000.0 * x_length / fs / frame_period) + 1;            // harvest.cpp:173-176
   *f0_length_out = Lb;
   const int nch = pl->nch, MC = pl->max_candidates, own_cap = MC / 7;
-  // one call handles up to IV_MAX_BLOCKS overlap-save blocks (~117 s at the 8 kHz analysis rate): checked before
+  // one call handles up to IV_MAX_BLOCKS overlap-save blocks (~15 min at the 8 kHz analysis rate): checked before
   // anything is enqueued; longer streams go through the segmenting path (worldb200/parallel.py)
   if ((y_length + pl->V - 1) / pl->V > IV_MAX_BLOCKS) return WB_ERR_UNSUPPORTED;
 
@@ -1119,7 +1119,7 @@ int wb_harvest_run_basic(WbHarvestPlan *pl, WbWorkspace *ws, const double *d_x, 
   // ---- H5: channels
   const int ecap = y_length / 2 + 4;
   const int bcap = pl->V / 2 + 2;
-  if (n_blocks > IV_MAX_BLOCKS) return WB_ERR_UNSUPPORTED;  // ~117 s; longer streams are processed in segments (parallel.py)
+  if (n_blocks > IV_MAX_BLOCKS) return WB_ERR_UNSUPPORTED;  // ~15 min; longer streams are processed in segments (parallel.py)
   int *d_ecount = (int *)ws->get("hv_ecount", sizeof(int) * nch * 4);
   double *d_seg = (double *)ws->get("hv_seg_edges", sizeof(double) * (size_t)nch * 4 * n_blocks * bcap);
   int *d_segc = (int *)ws->get("hv_seg_count", sizeof(int) * (size_t)nch * 4 * n_blocks);

@@ -98,7 +98,8 @@ int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int
 int wb_synthesis_render_range(WbWorkspace *ws, int fs, int fft_size, double frame_period_ms, int f0_length,
                               const double *d_sp, const double *d_ap, int row_begin, int n_rows, int out_length,
                               int sample_begin, int sample_end, double *d_out, double f0_upper_bound,
-                              const WbRngCursor &rng, cudaStream_t stream);
+                              const WbRngCursor &rng, cudaStream_t stream, int slot = 0, cudaEvent_t rows_ready = nullptr);
+int wb_synthesis_prepare(WbWorkspace *ws, int fft_size, cudaStream_t stream);
 int wb_synthesis_run(WbWorkspace *ws, int fs, int fft_size, double frame_period_ms, const double *d_f0,
                      int f0_length, const double *d_sp, const double *d_ap, int out_length, double *d_out,
                      double f0_upper_bound, const WbRngCursor &rng, cudaStream_t stream);

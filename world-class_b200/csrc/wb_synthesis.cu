@@ -881,6 +881,13 @@ static int upload_dc_remover(WbWorkspace *ws, int fft_size, double **out, cudaSt
   return WB_OK;
 }
 
+// Plan-time tables of the render calls, uploaded on `stream` (callers that render ranges on several streams order
+// those streams after this call).
+int wb_synthesis_prepare(WbWorkspace *ws, int fft_size, cudaStream_t stream) {
+  double *d_dcr = nullptr;
+  return upload_dc_remover(ws, fft_size, &d_dcr, stream);
+}
+
 // One rank's share of a long stream: the time base and the pulse list of the WHOLE
 // stream are on `ws` (every rank computes them from the gathered f0: they are cheap and sequential); this
 // renders the pulses that reach into [sample_begin, sample_end) with their whole-stream noise positions and
@@ -892,25 +899,27 @@ struct PulseList {   // where the pulse list lives (workspace of a whole-stream 
 static int render_range_core(WbWorkspace *ws, int fs, int fft_size, double frame_period_ms, int f0_length,
                              const double *d_sp, const double *d_ap, int row_begin, int n_rows, int out_length,
                              int sample_begin, int sample_end, double *d_out, double f0_upper_bound,
-                             const WbRngCursor &rng, cudaStream_t stream, const PulseList &pl);
+                             const WbRngCursor &rng, cudaStream_t stream, const PulseList &pl, int slot = 0,
+                             cudaEvent_t rows_ready = nullptr);
 
 int wb_synthesis_render_range(WbWorkspace *ws, int fs, int fft_size, double frame_period_ms, int f0_length,
                               const double *d_sp, const double *d_ap, int row_begin, int n_rows, int out_length,
                               int sample_begin, int sample_end, double *d_out, double f0_upper_bound,
-                              const WbRngCursor &rng, cudaStream_t stream) {
+                              const WbRngCursor &rng, cudaStream_t stream, int slot, cudaEvent_t rows_ready) {
   PulseList pl;
   pl.vuv = (unsigned char *)ws->find("syn_vuv"); pl.pulse_vuv = nullptr;
   pl.pidx = (int *)ws->find("syn_pidx"); pl.pshift = (double *)ws->find("syn_pshift");
   pl.np = (int *)ws->find("syn_np"); pl.ncount = (unsigned long long *)ws->find("syn_ncount");
   if (!pl.vuv || !pl.pidx || !pl.pshift || !pl.np || !pl.ncount) return WB_ERR_CUDA;
   return render_range_core(ws, fs, fft_size, frame_period_ms, f0_length, d_sp, d_ap, row_begin, n_rows, out_length,
-                           sample_begin, sample_end, d_out, f0_upper_bound, rng, stream, pl);
+                           sample_begin, sample_end, d_out, f0_upper_bound, rng, stream, pl, slot, rows_ready);
 }
 
 static int render_range_core(WbWorkspace *ws, int fs, int fft_size, double frame_period_ms, int f0_length,
                              const double *d_sp, const double *d_ap, int row_begin, int n_rows, int out_length,
                              int sample_begin, int sample_end, double *d_out, double f0_upper_bound,
-                             const WbRngCursor &rng, cudaStream_t stream, const PulseList &pl) {
+                             const WbRngCursor &rng, cudaStream_t stream, const PulseList &pl, int slot,
+                             cudaEvent_t rows_ready) {
   if (out_length <= 0) return WB_OK;
   if (sample_begin < 0 || sample_end > out_length || sample_begin > sample_end || row_begin < 0 || n_rows < 0 ||
       row_begin + n_rows > f0_length || !(f0_upper_bound > 0.0))
@@ -929,9 +938,11 @@ static int render_range_core(WbWorkspace *ws, int fs, int fft_size, double frame
   // runs up to the next pulse: a voiced sample has f0 > lowest_f0 / 2 (interpolation towards an unvoiced
   // frame, synthesis.cpp:225-243), so pulses are less than 2 fs / lowest_f0 < 2 fft_size samples apart.
   const int span = n_samples + 3 * fft_size + 8;
-  double *d_noise = (double *)ws->get("noise_syn_range", sizeof(double) * (size_t)span);
-  int *d_range = (int *)ws->get("syn_range", sizeof(int) * 4);
-  unsigned long long *d_npos = (unsigned long long *)ws->get("syn_range_pos", sizeof(unsigned long long) * 2);
+  // (slot: scratch set of the call -- ranges rendered concurrently on different streams use different slots)
+  const std::string sfx = slot ? "#" + std::to_string(slot) : std::string();
+  double *d_noise = (double *)ws->get("noise_syn_range" + sfx, sizeof(double) * (size_t)span);
+  int *d_range = (int *)ws->get("syn_range" + sfx, sizeof(int) * 4);
+  unsigned long long *d_npos = (unsigned long long *)ws->get("syn_range_pos" + sfx, sizeof(unsigned long long) * 2);
   double *d_dcr = nullptr;
   int rc = upload_dc_remover(ws, fft_size, &d_dcr, stream);
   if (rc) return rc;
@@ -947,7 +958,7 @@ static int render_range_core(WbWorkspace *ws, int fs, int fft_size, double frame
     if ((rc = wb_rng_fill(rng.state, d_npos, d_npos + 1, (unsigned long long)span, d_noise, stream))) return rc;
     const double fmax = f0_upper_bound > WB_DEFAULT_F0 ? f0_upper_bound : WB_DEFAULT_F0;
     const int resp_pulses = (int)((double)span * fmax / fs + 4.0);
-    double *d_resp = (double *)ws->get("syn_resp", sizeof(double) * (size_t)resp_pulses * fft_size);
+    double *d_resp = (double *)ws->get("syn_resp" + sfx, sizeof(double) * (size_t)resp_pulses * fft_size);
     if (!d_resp) return WB_ERR_CUDA;
     RespParams p;
     p.sp = d_sp; p.ap = d_ap; p.f0_length = f0_length; p.fs = fs; p.fft_size = fft_size; p.log2n = log2n;
@@ -959,6 +970,8 @@ static int render_range_core(WbWorkspace *ws, int fs, int fft_size, double frame
     p.error_flag = ws->error_flag();
     p.range = d_range; p.row_begin = row_begin; p.pulse_vuv = pl.pulse_vuv;
     const int grid = wb_min_i(resp_pulses, wb_sm_count() * 9);
+    // (rows_ready: the pulse range and its noise above need the time base only; sp / ap rows may still be landing)
+    if (rows_ready) WB_CUDA_CHECK(cudaStreamWaitEvent(stream, rows_ready, 0));
     rc = WB_DISPATCH_LOG2(log2n, 8, 13, {
       if (cudaFuncSetAttribute(response_kernel<L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WB_ERR_CUDA;
       WB_LAUNCH("response_kernel", response_kernel<L2><<<grid, 256, smem, stream>>>(p));
