@@ -160,7 +160,10 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     import worldb200 as wb
-    from worldb200 import signals
+    from worldb200 import parallel, signals
+    # one process per GPU, on the CPUs of the GPU's NUMA node (before any page-locked buffer is allocated)
+    cpus_at_start = os.sched_getaffinity(0)
+    host_binding = parallel.bind_to_gpu_node(local_rank)
     wb._check(wb.lib().wb_init(local_rank), "wb_init")
     lib_stream = torch.cuda.ExternalStream(wb.stream_handle())
 
@@ -513,6 +516,7 @@ def main():
     # ---- CPU baseline: the reference's OpenMP build on this host, bounded sample
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:   # (N = 1 only, as the contract says)
+        os.sched_setaffinity(0, cpus_at_start)    # the reference's OpenMP build gets every host core
         res = cpu_reference_run(x_host, repeat=3, omp=True)
         if res is not None:
             ms = float(np.median(res["ms"]))
@@ -533,7 +537,7 @@ def main():
             "gpu_launches": launches,
             "clocks": sampler.summary(),
             "roofline": roofline,
-            "cpu_baseline": cpu_baseline,
+            "cpu_baseline": cpu_baseline, "host_binding": host_binding,
             "kernels_ms_per_step": {k: v[0] / args.steps for k, v in sorted(kernel_table.items(), key=lambda kv: -kv[1][0])},
             "wall_s_timed_region": t_wall,
             "batch_config3_extra": batch_extra,

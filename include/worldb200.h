@@ -226,6 +226,12 @@ int wb_pipeline_run_f32(wb_pipeline_t *p, const double *x, int x_length, float *
  * interpolates between: frames floor((sample_begin - fft_size) / fs / frame_period) .. ceil((sample_end +
  * fft_size) / fs / frame_period), clipped to the stream. */
 int wb_pipeline_stream_begin_dev(wb_pipeline_t *p, const double *d_f0_all, int f0_length, int out_length, void *stream);
+/* The same with the sample range [sample_begin, sample_end) this rank will synthesise (the union of the ranges of its
+ * later wb_pipeline_stream_synthesis_dev calls): the exact phase sum still runs over the whole stream, but the
+ * per-sample passes that turn it into a pulse list are restricted to that range (two thirds of the replicated work).
+ * sample_end < 0 = the whole stream. */
+int wb_pipeline_stream_begin_range_dev(wb_pipeline_t *p, const double *d_f0_all, int f0_length, int out_length,
+                                       int sample_begin, int sample_end, void *stream);
 int wb_pipeline_stream_envelope_dev(wb_pipeline_t *p, const double *d_x, int x_length, const double *d_f0_all,
                                     int f0_length, int frame_begin, int frame_end, double *d_sp_rows,
                                     double *d_ap0_all, void *stream);

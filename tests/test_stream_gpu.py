@@ -33,6 +33,15 @@ def test_ranges_are_bit_identical_to_the_unsharded_run(wb, signals, fs, seconds,
     bad = np.flatnonzero(y != ref["y"])
     assert bad.size == 0, "first / last / count of differing samples: %d %d %d, samples per rank %r" % (
         bad[0], bad[-1], bad.size, out["plan"].samples)
+    # every rank builds its pulse list for its own samples only, yet knows the first pulse of the whole stream (the
+    # origin of the excitation's randn() positions) and the number of draws the whole stream makes
+    first = int(whole.debug_read("syn_np", (2,), dtype=np.int32)[1])
+    draws = int(whole.debug_read("syn_ncount", (1,), dtype=np.uint64)[0])
+    pulses = int(whole.debug_read("syn_np", (2,), dtype=np.int32)[0])
+    for w in out["workers"]:
+        np_w = w.pipe.debug_read("syn_np", (2,), dtype=np.int32)
+        assert int(np_w[1]) == first and int(w.pipe.debug_read("syn_ncount", (1,), dtype=np.uint64)[0]) == draws
+        assert 0 < int(np_w[0]) < pulses, "a rank's pulse list covers its own window of the stream"
 
 
 def test_sharded_harvest_and_chain_match_the_reference_process(wb, signals):

@@ -111,6 +111,7 @@ def _declare(L):
         "wb_pipeline_run": (ci, [vp, vp, ci, vp, vp, vp, vp, vp, ci]),
         "wb_pipeline_debug_read": (ci, [vp, ctypes.c_char_p, vp, ctypes.c_ulonglong]),
         "wb_pipeline_stream_begin_dev": (ci, [vp, vp, ci, ci, vp]),
+        "wb_pipeline_stream_begin_range_dev": (ci, [vp, vp, ci, ci, ci, ci, vp]),
         "wb_pipeline_stream_envelope_dev": (ci, [vp, vp, ci, vp, ci, ci, ci, vp, vp, vp]),
         "wb_decimate_length": (ci, [ci, ci]),
         "wb_decimate": (ci, [ctypes.POINTER(cd), ci, ci, ctypes.POINTER(cd)]),

@@ -357,6 +357,7 @@ struct wb_pipeline {
   WbStageSplit d4c_split;            // second stream of the D4C stage (halves of the rows, see WbStageSplit)
   unsigned long long graph_generation = 0;   // ws.generation() when the graph was captured
   int stream_f0_length = 0;          // sharded streams: the length given to wb_pipeline_stream_begin_dev
+  int stream_samples[2] = {0, 0};    // sharded streams: the sample range the time base of this rank was built for
   double stream_f0_bound = 0.0;      // sharded streams: upper bound of an external f0 contour (<= 0: f0_ceil * 1.25)
   cudaEvent_t ev_f0 = nullptr, ev_tb = nullptr, ev_ct_count = nullptr, ev_body_count = nullptr, ev_d4c = nullptr,
               ev_start = nullptr;
@@ -1154,7 +1155,13 @@ __global__ void frame_times_kernel(double *__restrict__ tpos, int n, double fram
 }  // namespace
 
 int wb_pipeline_stream_begin_dev(wb_pipeline_t *p, const double *d_f0_all, int f0_length, int out_length, void *stream_) {
+  return wb_pipeline_stream_begin_range_dev(p, d_f0_all, f0_length, out_length, 0, -1, stream_);
+}
+
+int wb_pipeline_stream_begin_range_dev(wb_pipeline_t *p, const double *d_f0_all, int f0_length, int out_length,
+                                       int sample_begin, int sample_end, void *stream_) {
   if (!p || !d_f0_all || f0_length < 2 || out_length < 0) return WB_ERR_ARG;
+  if (sample_end >= 0 && (sample_begin < 0 || sample_begin > sample_end || sample_end > out_length)) return WB_ERR_ARG;
   cudaStream_t stream = pick_stream(stream_);
   const double fp = p->plan.opt.frame_period;
   double *d_tpos = (double *)p->ws.get("st_tpos", sizeof(double) * f0_length);
@@ -1169,10 +1176,13 @@ int wb_pipeline_stream_begin_dev(wb_pipeline_t *p, const double *d_f0_all, int f
   if (out_length > 0) {
     WB_CUDA_CHECK(cudaEventRecord(p->ev_f0, stream));
     WB_CUDA_CHECK(cudaStreamWaitEvent(p->side, p->ev_f0, 0));
-    int rc = wb_synthesis_timebase(&p->ws, p->fs, p->ct.fft_size, fp, d_f0_all, f0_length, out_length, p->side, nullptr);
+    int rc = wb_synthesis_timebase(&p->ws, p->fs, p->ct.fft_size, fp, d_f0_all, f0_length, out_length, p->side, nullptr,
+                                   sample_begin, sample_end);
     if (rc) return rc;
     WB_CUDA_CHECK(cudaEventRecord(p->ev_tb, p->side));
   }
+  p->stream_samples[0] = sample_end >= 0 ? sample_begin : 0;
+  p->stream_samples[1] = sample_end >= 0 ? sample_end : out_length;
   return WB_OK;
 }
 
@@ -1266,6 +1276,7 @@ int wb_pipeline_stream_synthesis_dev(wb_pipeline_t *p, int f0_length, const doub
   cudaStream_t stream = pick_stream(stream_);
   unsigned long long *rng_pos = (unsigned long long *)p->ws.find("pl_rng_pos");
   if (!rng_pos || !p->ws.find("syn_pidx") || f0_length != p->stream_f0_length) return WB_ERR_ARG;   // begin (with out_length > 0) has not been called
+  if (sample_begin < p->stream_samples[0] || sample_end > p->stream_samples[1]) return WB_ERR_ARG;     // outside the range begin was given
   WbRngState *rng = p->private_rng ? p->d_rng_private : wb_rng_global_state();
   WB_CUDA_CHECK(cudaStreamWaitEvent(stream, p->ev_tb, 0));
   WbRngCursor c;

@@ -105,7 +105,7 @@ int wb_synthesis_run(WbWorkspace *ws, int fs, int fft_size, double frame_period_
                      double f0_upper_bound, const WbRngCursor &rng, cudaStream_t stream);
 int wb_synthesis_timebase(WbWorkspace *ws, int fs, int fft_size, double frame_period_ms, const double *d_f0,
                           int f0_length, int out_length, cudaStream_t stream,
-                          const WbRngCursor *noise_cursor = nullptr);
+                          const WbRngCursor *noise_cursor = nullptr, int sample_begin = 0, int sample_end = -1);
 int wb_synthesis_render(WbWorkspace *ws, int fs, int fft_size, double frame_period_ms, int f0_length,
                         const double *d_sp, const double *d_ap, int out_length, double *d_out,
                         double f0_upper_bound, const WbRngCursor &rng, cudaStream_t stream,

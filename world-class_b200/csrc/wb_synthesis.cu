@@ -362,9 +362,9 @@ __global__ void __launch_bounds__(PS_THREADS) ps_sequential_kernel(const double 
 
 __global__ void __launch_bounds__(PS_THREADS) ps_expand_kernel(const double *__restrict__ incr, int n, double *__restrict__ wrap_phase,
                                                                const int *__restrict__ e_pred, const double *__restrict__ chunk_start,
-                                                               const int *__restrict__ chunk_expand) {
+                                                               const int *__restrict__ chunk_expand, int chunk_offset) {
   __shared__ IncFn warp_fn[32];
-  const int c = blockIdx.x;
+  const int c = blockIdx.x + chunk_offset;
   if (!chunk_expand[c]) return;
   const int e = e_pred[c];
   const int begin = 1 + c * PS_CHUNK, end = min(n, begin + PS_CHUNK);
@@ -451,8 +451,35 @@ __global__ void pulse_finalize_kernel(const unsigned long long *__restrict__ blo
                                       int *__restrict__ error_flag) {
   unsigned long long P = block_offsets[n_blocks];
   if (P > (unsigned long long)max_pulses) { P = max_pulses; atomicExch(error_flag, WB_ERR_UNSUPPORTED); }
-  *n_pulses = (int)P;
+  n_pulses[0] = (int)P;
+  n_pulses[1] = P >= 1 ? pulse_index[0] : 0;   // the sample the randn() stream of the excitation starts at
   *noise_count = (P >= 2) ? (unsigned long long)(pulse_index[P - 1] - pulse_index[0]) : 0ull;
+}
+
+// Range-restricted time base (one rank of a sharded stream): the pulse list holds the pulses of a sample window
+// only, so the first and the last pulse of the WHOLE stream -- the origin of the excitation's randn() positions and
+// the number of draws the stream makes (synthesis.cpp:520) -- are found in its first / last `span` samples.
+__global__ void __launch_bounds__(1024) pulse_ends_kernel(const double *__restrict__ total, int y_length, int span,
+                                                          const unsigned long long *__restrict__ block_offsets, int n_blocks,
+                                                          int max_pulses, int *__restrict__ n_pulses,
+                                                          unsigned long long *__restrict__ noise_count, int *__restrict__ error_flag) {
+  __shared__ int s_first, s_last;
+  if (threadIdx.x == 0) { s_first = 0x7fffffff; s_last = -1; }
+  __syncthreads();
+  const double two_pi = 2.0 * WB_PI;
+  auto pulse_at = [&](int ii) { return fabs(fmod(total[ii + 1], two_pi) - fmod(total[ii], two_pi)) > WB_PI; };
+  const int head_end = min(span, y_length - 1), tail_begin = max(0, y_length - 1 - span);
+  for (int ii = threadIdx.x; ii < head_end; ii += blockDim.x) if (pulse_at(ii)) { atomicMin(&s_first, ii); break; }
+  for (int ii = y_length - 2 - threadIdx.x; ii >= tail_begin; ii -= blockDim.x) if (pulse_at(ii)) { atomicMax(&s_last, ii); break; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long P = block_offsets[n_blocks];
+    if (P > (unsigned long long)max_pulses) { P = max_pulses; atomicExch(error_flag, WB_ERR_UNSUPPORTED); }
+    if (s_first == 0x7fffffff || s_last < 0) { atomicExch(error_flag, WB_ERR_UNSUPPORTED); s_first = 0; s_last = 0; }
+    n_pulses[0] = (int)P;
+    n_pulses[1] = s_first;
+    *noise_count = s_last > s_first ? (unsigned long long)(s_last - s_first) : 0ull;
+  }
 }
 
 // ---- K5: impulse response per pulse -----------------------------------------------------------
@@ -478,7 +505,8 @@ struct RespParams {
 // pulses whose response overlaps samples [sample_begin, sample_end), and the share of the noise stream
 // they read: range = {first pulse, one past the last, sample index of the first pulse}; *noise_skip /
 // *noise_count position the randn() fill
-__global__ void pulse_range_kernel(const int *__restrict__ pulse_index, const int *__restrict__ n_pulses, int fft_size,
+__global__ void pulse_range_kernel(const int *__restrict__ pulse_index, const int *__restrict__ n_pulses,
+                                   const int *__restrict__ first_pulse, int fft_size,
                                    int sample_begin, int sample_end, const unsigned long long *__restrict__ skip_in,
                                    int *__restrict__ range, unsigned long long *__restrict__ noise_skip,
                                    unsigned long long *__restrict__ noise_count) {
@@ -501,7 +529,7 @@ __global__ void pulse_range_kernel(const int *__restrict__ pulse_index, const in
   const int idx_lo = pulse_index[p_lo];
   const int idx_end = pulse_index[p_hi < P ? p_hi : P - 1];   // the last pulse of the stream draws nothing (Q11)
   range[2] = idx_lo;
-  *noise_skip = (skip_in ? *skip_in : 0ull) + (unsigned long long)(idx_lo - pulse_index[0]);
+  *noise_skip = (skip_in ? *skip_in : 0ull) + (unsigned long long)(idx_lo - *first_pulse);   // (first pulse of the WHOLE stream)
   *noise_count = (unsigned long long)(idx_end - idx_lo);
 }
 
@@ -709,7 +737,10 @@ static void make_dc_remover(int fft_size, std::vector<double> &r) {
 }
 
 // exact running sum total[i] = fl(total[i-1] + incr[i]), total[0] = incr[0] (see the ps_* kernels)
-static int run_phase_scan(WbWorkspace *ws, const double *d_incr, int out_length, double *d_total, cudaStream_t stream) {
+// `windows` (optional, up to 3 sample windows [lo, hi)): only the chunks that hold these samples are expanded -- the
+// rest of d_total stays unwritten (range-restricted time base of a sharded stream).
+static int run_phase_scan(WbWorkspace *ws, const double *d_incr, int out_length, double *d_total, cudaStream_t stream,
+                          const int (*windows)[2] = nullptr, int n_windows = 0) {
   {
     const int n_chunks = out_length > 1 ? (out_length - 1 + PS_CHUNK - 1) / PS_CHUNK : 0;
     const int nc = n_chunks > 0 ? n_chunks : 1;
@@ -727,8 +758,15 @@ static int run_phase_scan(WbWorkspace *ws, const double *d_incr, int out_length,
     }
     WB_LAUNCH("phase_scan_kernel", ps_sequential_kernel<<<1, PS_THREADS, 0, stream>>>(d_incr, out_length, d_total, n_chunks, d_ce, d_cfn,
                                                                                    d_cbad, d_cstart, d_cexp));
-    if (n_chunks > 0)
-      WB_LAUNCH("ps_expand_kernel", ps_expand_kernel<<<n_chunks, PS_THREADS, 0, stream>>>(d_incr, out_length, d_total, d_ce, d_cstart, d_cexp));
+    if (n_chunks > 0 && !windows)
+      WB_LAUNCH("ps_expand_kernel", ps_expand_kernel<<<n_chunks, PS_THREADS, 0, stream>>>(d_incr, out_length, d_total, d_ce, d_cstart, d_cexp, 0));
+    for (int w = 0; n_chunks > 0 && w < n_windows; ++w) {
+      // chunk c holds elements [1 + c PS_CHUNK, 1 + (c + 1) PS_CHUNK); element 0 is written by the sequential kernel
+      const int lo = windows[w][0] < 1 ? 1 : windows[w][0], hi = windows[w][1] > out_length ? out_length : windows[w][1];
+      if (hi <= lo) continue;
+      const int c0 = (lo - 1) / PS_CHUNK, c1 = (hi - 2) / PS_CHUNK;
+      WB_LAUNCH("ps_expand_kernel", ps_expand_kernel<<<c1 - c0 + 1, PS_THREADS, 0, stream>>>(d_incr, out_length, d_total, d_ce, d_cstart, d_cexp, c0));
+    }
   }
   WB_CUDA_CHECK(cudaGetLastError());
   return WB_OK;
@@ -737,20 +775,36 @@ static int run_phase_scan(WbWorkspace *ws, const double *d_incr, int out_length,
 // ---- host side -------------------------------------------------------------------------------
 // Part 1 (depends on f0 only): time base, exact phase scan, pulse list.  May run on a side
 // stream while CheapTrick / D4C are still busy.
+// sample_begin / sample_end (a rank of a sharded stream): the pulse list is built for the pulses that reach into
+// [sample_begin, sample_end) only -- the per-sample passes over the rest of the stream (chunk expansion, pulse
+// detection, compaction: two thirds of the time base) are skipped; sample_end < 0 = the whole stream.
 int wb_synthesis_timebase(WbWorkspace *ws, int fs, int fft_size, double frame_period_ms, const double *d_f0,
-                          int f0_length, int out_length, cudaStream_t stream, const WbRngCursor *noise_cursor) {
+                          int f0_length, int out_length, cudaStream_t stream, const WbRngCursor *noise_cursor,
+                          int sample_begin, int sample_end) {
   if (out_length <= 0) return WB_OK;
   if (f0_length < 2) return WB_ERR_ARG;
+  // pulses wanted: idx in (sample_begin + fft/2 - 1 - fft, sample_end + fft/2 - 2], plus the pulse after the last one
+  // (its noise ends there); pulses are less than 2 fft_size samples apart (see render_range_core)
+  const int span = 2 * fft_size + 64;
+  int win_lo = 0, win_hi = out_length;
+  if (sample_end >= 0) {
+    if (sample_begin < 0 || sample_end > out_length || sample_begin > sample_end || noise_cursor) return WB_ERR_ARG;
+    win_lo = sample_begin - fft_size - 8 < 0 ? 0 : sample_begin - fft_size - 8;
+    win_hi = sample_end + 3 * fft_size + 8 > out_length || sample_end + 3 * fft_size + 8 < 0 ? out_length : sample_end + 3 * fft_size + 8;
+  }
+  const bool ranged = sample_end >= 0 && out_length > 4 * span && (win_lo > 0 || win_hi < out_length);
+  if (!ranged) { win_lo = 0; win_hi = out_length; }
   const double frame_period = frame_period_ms / 1000.;      // synthesis.cpp:31
   const double lowest_f0 = fs / fft_size + 1.0;             // synthesis.cpp:97 (integer division)
   // Every pulse needs a 2 pi phase advance and one sample adds at most 2 pi max(f0, 500) / fs,
   // so pulses <= out_length * max(f0_max, 500) / fs + 1.  The index/shift lists are sized for
   // f0 <= fs / 4; the response buffer for the tighter bound (or the exact count).
-  const int max_pulses = out_length / 4 + 16;
+  const int win = win_hi - win_lo;
+  const int max_pulses = win / 4 + 16;
   double *d_incr = (double *)ws->get("syn_incr", sizeof(double) * out_length);
   double *d_total = (double *)ws->get("syn_wrap", sizeof(double) * out_length);
   unsigned char *d_vuv = (unsigned char *)ws->get("syn_vuv", out_length);
-  const int n_blocks = (out_length + PD_THREADS - 1) / PD_THREADS;
+  const int n_blocks = (win + PD_THREADS - 1) / PD_THREADS;
   unsigned long long *d_bc = (unsigned long long *)ws->get("syn_bcount", sizeof(unsigned long long) * (n_blocks + 1));
   unsigned long long *d_bo = (unsigned long long *)ws->get("syn_boff", sizeof(unsigned long long) * (n_blocks + 1));
   int *d_pidx = (int *)ws->get("syn_pidx", sizeof(int) * max_pulses);
@@ -761,15 +815,22 @@ int wb_synthesis_timebase(WbWorkspace *ws, int fs, int fft_size, double frame_pe
   WB_LAUNCH("timebase_kernel", timebase_kernel<<<(out_length + 255) / 256, 256, 0, stream>>>(
       d_f0, f0_length, fs, frame_period, lowest_f0, out_length, d_incr, d_vuv, 0, 0));
   {
-    const int rc_scan = run_phase_scan(ws, d_incr, out_length, d_total, stream);
+    const int windows[3][2] = {{win_lo, win_hi}, {0, span + 1}, {out_length - span - 2, out_length}};
+    const int rc_scan = ranged ? run_phase_scan(ws, d_incr, out_length, d_total, stream, windows, 3)
+                               : run_phase_scan(ws, d_incr, out_length, d_total, stream);
     if (rc_scan) return rc_scan;
   }
-  WB_LAUNCH("pulse_count_kernel", pulse_count_kernel<<<n_blocks, PD_THREADS, 0, stream>>>(d_total, out_length, d_bc));
+  // (a window is a piece of the stream whose element 0 is sample win_lo, like a piece of a streaming synthesis)
+  WB_LAUNCH("pulse_count_kernel", pulse_count_kernel<<<n_blocks, PD_THREADS, 0, stream>>>(d_total + win_lo, win, d_bc));
   int rc = wb_exclusive_scan_u64(d_bc, d_bo, n_blocks, stream);
   if (rc) return rc;
-  WB_LAUNCH("pulse_write_kernel", pulse_write_kernel<<<n_blocks, PD_THREADS, 0, stream>>>(d_total, out_length, fs, d_bo, d_pidx, d_pshift, max_pulses,
-                                                                                        0, 0, nullptr, nullptr));
-  WB_LAUNCH("pulse_finalize_kernel", pulse_finalize_kernel<<<1, 1, 0, stream>>>(d_bo, n_blocks, d_pidx, max_pulses, d_np, d_ncount, ws->error_flag()));
+  WB_LAUNCH("pulse_write_kernel", pulse_write_kernel<<<n_blocks, PD_THREADS, 0, stream>>>(d_total + win_lo, win, fs, d_bo, d_pidx, d_pshift, max_pulses,
+                                                                                        win_lo, 0, nullptr, nullptr));
+  if (ranged)
+    WB_LAUNCH("pulse_ends_kernel", pulse_ends_kernel<<<1, 1024, 0, stream>>>(d_total, out_length, span, d_bo, n_blocks, max_pulses, d_np, d_ncount,
+                                                                          ws->error_flag()));
+  else
+    WB_LAUNCH("pulse_finalize_kernel", pulse_finalize_kernel<<<1, 1, 0, stream>>>(d_bo, n_blocks, d_pidx, max_pulses, d_np, d_ncount, ws->error_flag()));
   WB_CUDA_CHECK(cudaGetLastError());
   if (noise_cursor) {
     // the aperiodic excitation only needs the pulse span: draw it here, off the critical path
@@ -895,6 +956,7 @@ int wb_synthesis_prepare(WbWorkspace *ws, int fft_size, cudaStream_t stream) {
 struct PulseList {   // where the pulse list lives (workspace of a whole-stream time base, or a streaming synthesis)
   const unsigned char *vuv; const unsigned char *pulse_vuv;
   const int *pidx; const double *pshift; const int *np; const unsigned long long *ncount;
+  const int *first;   // sample index of the first pulse of the WHOLE stream (the list may hold a window of it)
 };
 static int render_range_core(WbWorkspace *ws, int fs, int fft_size, double frame_period_ms, int f0_length,
                              const double *d_sp, const double *d_ap, int row_begin, int n_rows, int out_length,
@@ -911,6 +973,7 @@ int wb_synthesis_render_range(WbWorkspace *ws, int fs, int fft_size, double fram
   pl.pidx = (int *)ws->find("syn_pidx"); pl.pshift = (double *)ws->find("syn_pshift");
   pl.np = (int *)ws->find("syn_np"); pl.ncount = (unsigned long long *)ws->find("syn_ncount");
   if (!pl.vuv || !pl.pidx || !pl.pshift || !pl.np || !pl.ncount) return WB_ERR_CUDA;
+  pl.first = pl.np + 1;
   return render_range_core(ws, fs, fft_size, frame_period_ms, f0_length, d_sp, d_ap, row_begin, n_rows, out_length,
                            sample_begin, sample_end, d_out, f0_upper_bound, rng, stream, pl, slot, rows_ready);
 }
@@ -951,7 +1014,7 @@ static int render_range_core(WbWorkspace *ws, int fs, int fft_size, double frame
   const cplx *tw_2n = wb_twiddle_table(2 * fft_size);
   if (!tw_n || !tw_2n) return WB_ERR_CUDA;
   if (rng.wait_skip_in) WB_CUDA_CHECK(cudaStreamWaitEvent(stream, rng.wait_skip_in, 0));
-  WB_LAUNCH("pulse_range_kernel", pulse_range_kernel<<<1, 1, 0, stream>>>(d_pidx, d_np, fft_size, sample_begin, sample_end, rng.skip_in,
+  WB_LAUNCH("pulse_range_kernel", pulse_range_kernel<<<1, 1, 0, stream>>>(d_pidx, d_np, pl.first, fft_size, sample_begin, sample_end, rng.skip_in,
                                                                      d_range, d_npos, d_npos + 1));
   WB_CUDA_CHECK(cudaGetLastError());
   if (n_samples > 0) {
@@ -1101,7 +1164,7 @@ int synstream_emit(WbSynStream *s, int out_new, int out_length_for_ola, double *
   PulseList pl;
   pl.vuv = nullptr; pl.pulse_vuv = (unsigned char *)ws->find("st_pvuv");
   pl.pidx = (int *)ws->find("st_pidx"); pl.pshift = (double *)ws->find("st_pshift");
-  pl.np = (int *)ws->find("st_np"); pl.ncount = nullptr;
+  pl.np = (int *)ws->find("st_np"); pl.ncount = nullptr; pl.first = pl.pidx;   // (the list starts at the stream's first pulse)
   WbRngCursor c;
   c.state = wb_rng_global_state(); c.advance = false;   // the state moves once, when the stream is finished
   const double *d_sp = (const double *)ws->find("st_sp"), *d_ap = (const double *)ws->find("st_ap");

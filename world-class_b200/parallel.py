@@ -121,6 +121,35 @@ def process_batch(items, process_item, group=None):
 # wb_pipeline_stream_* entry points.
 
 
+def bind_to_gpu_node(device_index):
+    """One process per GPU: keep this process -- and the threads it creates from here on (the library's copy pool) --
+    on the CPUs NVML reports as local to the GPU's NUMA node, so page-locked buffers allocated afterwards and the
+    host side of every H2D / D2H copy stay off the inter-socket link.  Call before allocating pinned memory.
+    Returns a dict describing what was done (`bound` False when NVML or the affinity call is unavailable, or the
+    node's CPUs are outside this process's cpuset); never raises."""
+    import os
+    info = {"bound": False}
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        prop = torch.cuda.get_device_properties(device_index)
+        bus_id = "%08x:%02x:%02x.0" % (prop.pci_domain_id, prop.pci_bus_id, prop.pci_device_id)
+        handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus_id.encode())
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinityWithinScope(handle, (n_cpu + 63) // 64, pynvml.NVML_AFFINITY_SCOPE_NODE)
+        local = {64 * w + b for w, mask in enumerate(words) for b in range(64) if (int(mask) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = sorted(local & allowed)
+        info.update(pci=bus_id, node_cpus=len(local), allowed_cpus=len(allowed))
+        if cpus and len(cpus) < len(allowed):
+            os.sched_setaffinity(0, cpus)
+            info.update(bound=True, cpus=len(cpus), first_cpu=cpus[0], last_cpu=cpus[-1])
+    except Exception as e:   # noqa: BLE001 (a missing NVML / an odd cpuset must not stop the job)
+        info["error"] = "%s: %s" % (type(e).__name__, e)
+    return info
+
+
 def decimation_ratio(fs, target_fs=8000.0):
     """Harvest's decimation ratio (src/harvest.cpp:81-82)."""
     r = int(fs / target_fs + 0.5)          # matlab_round of a positive number
@@ -289,12 +318,16 @@ class StreamWorker:
             out[cfb - fb:cfe - fb] = d_f[cfb - off:cfe - off]
         return out
 
-    def begin(self, d_f0_all):
-        """whole-stream bookkeeping (frame times, randn() seed, time base + pulse list): once per pipeline"""
+    def begin(self, d_f0_all, samples=None):
+        """whole-stream bookkeeping (frame times, randn() seed, time base + pulse list): once per pipeline.
+        `samples`: the sample range the shards of this pipeline will synthesise (default: this shard's) -- the
+        pulse list is built for it only."""
         self.torch.cuda.current_stream().synchronize()   # inputs made by torch ops; the library has its own stream
         self.d_f0_all = d_f0_all
-        self.wb._check(self.wb.lib().wb_pipeline_stream_begin_dev(self.pipe._h, d_f0_all.data_ptr(), self.plan.f0_length,
-                                                                  self.plan.out_length, None), "wb_pipeline_stream_begin_dev")
+        sa, sb = samples if samples is not None else self.plan.samples[self.rank]
+        self.wb._check(self.wb.lib().wb_pipeline_stream_begin_range_dev(self.pipe._h, d_f0_all.data_ptr(), self.plan.f0_length,
+                                                                        self.plan.out_length, int(sa), int(sb), None),
+                       "wb_pipeline_stream_begin_range_dev")
 
     def envelope(self, d_x, d_ap0_all):
         """CheapTrick + Love Train for the rows this shard needs; writes its entries of d_ap0_all."""
@@ -418,7 +451,7 @@ def process_stream_exact(d_x, fs, harvest_option=None, cheaptrick_option=None, d
         workers[0].pipe.set_stream_f0_bound(float(d_f0_all.max().item()) + 1.0)
     else:
         workers[0].pipe.set_stream_f0_bound(0.0)
-    workers[0].begin(d_f0_all)
+    workers[0].begin(d_f0_all, rank_samples[rank])
     for w in workers[1:]:
         w.d_f0_all = d_f0_all
     # Love Train first: its decisions (8 bytes per frame) travel while CheapTrick -- the longer half of the
@@ -490,4 +523,4 @@ def simulate_stream_ranks(d_x, fs, world, harvest_option=None, cheaptrick_option
         w.aperiodicity(d_x, d_ap0)
     d_y = torch.cat([w.synthesis() for w in workers])
     return {"f0": d_f0_all, "y": d_y, "sp": torch.cat([w.owned_rows(w.d_sp) for w in workers]),
-            "ap": torch.cat([w.owned_rows(w.d_ap) for w in workers]), "ap0": d_ap0, "plan": plan}
+            "ap": torch.cat([w.owned_rows(w.d_ap) for w in workers]), "ap0": d_ap0, "plan": plan, "workers": workers}
