@@ -90,9 +90,9 @@ int wb_harvest_get_samples(int fs, int x_length, double frame_period);          
 int wb_harvest_create(int fs, const WbHarvestOption *opt_or_null, wb_harvest_t **out); /* src/harvest.cpp:69-103 */
 void wb_harvest_destroy(wb_harvest_t *h);
 /* src/harvest.cpp:183-208; temporal_positions and f0 hold wb_harvest_get_samples() entries */
-/* One call analyses up to about 117 s of audio (128 overlap-save blocks at the 8 kHz analysis rate): longer
- * inputs return WB_ERR_UNSUPPORTED before anything is launched; process them in segments (worldb200.parallel,
- * DESIGN.md section 5).  The reference accepts any length. */
+/* One call analyses up to about 16 minutes of audio (1024 overlap-save blocks at the 8 kHz analysis rate; its
+ * scratch grows with the length, about 32 MB per second of audio).  Longer inputs return WB_ERR_UNSUPPORTED before anything is
+ * launched; process them in segments (worldb200.parallel).  The reference accepts any length. */
 int wb_harvest_compute(wb_harvest_t *h, const double *x, int x_length, double *temporal_positions, double *f0);
 int wb_harvest_compute_dev(wb_harvest_t *h, const double *d_x, int x_length, double *d_temporal_positions,
                            double *d_f0, void *stream);

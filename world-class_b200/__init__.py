@@ -204,11 +204,22 @@ def _out_array(arr, shape):
     return arr
 
 
+_row_pointer_cache = {}
+
+
 def _row_pointers(mat):
-    """A C `double **` (array of row pointers) into a C-contiguous 2-D float64 array."""
+    """A C `double **` (array of row pointers) into a C-contiguous 2-D float64 array.  The pointer table is a
+    function of (base address, rows, row stride) only: callers that reuse their matrices (test/test.cpp allocates
+    them once) get the cached table."""
     assert mat.flags["C_CONTIGUOUS"] and mat.dtype == np.float64 and mat.ndim == 2
-    addr = mat.ctypes.data + np.arange(mat.shape[0], dtype=np.uint64) * np.uint64(mat.strides[0])
-    return np.ascontiguousarray(addr, dtype=np.uint64)
+    key = (mat.ctypes.data, mat.shape[0], mat.strides[0])
+    rows = _row_pointer_cache.get(key)
+    if rows is None:
+        if len(_row_pointer_cache) >= 32:
+            _row_pointer_cache.clear()
+        addr = key[0] + np.arange(mat.shape[0], dtype=np.uint64) * np.uint64(mat.strides[0])
+        rows = _row_pointer_cache[key] = np.ascontiguousarray(addr, dtype=np.uint64)
+    return rows
 
 
 # ---- randn stream -----------------------------------------------------------------------

@@ -20,7 +20,7 @@ class WbWorkspace {
   // like get(), but the first `keep_bytes` of an existing buffer survive a reallocation (synchronises `stream`)
   void *get_keep(const std::string &name, size_t bytes, size_t keep_bytes, cudaStream_t stream);
   void *get_pinned(const std::string &name, size_t bytes);  // page-locked host memory
-  int *error_flag();                                        // device int, zero-initialised
+  int *error_flag();                                        // mapped page-locked int (device-writable, host-readable), starts at 0
   int read_error_flag(cudaStream_t stream);                 // syncs the stream
  private:
   struct Buf { void *p; size_t bytes; };

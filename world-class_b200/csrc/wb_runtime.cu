@@ -11,7 +11,7 @@ WbWorkspace::WbWorkspace() : generation_(0), d_err_(nullptr) {}
 WbWorkspace::~WbWorkspace() {
   for (auto &kv : dev_) cudaFree(kv.second.p);
   for (auto &kv : pinned_) cudaFreeHost(kv.second.p);
-  if (d_err_) cudaFree(d_err_);
+  if (d_err_) cudaFreeHost(d_err_);
 }
 
 void *WbWorkspace::get(const std::string &name, size_t bytes) {
@@ -73,20 +73,25 @@ void *WbWorkspace::get_pinned(const std::string &name, size_t bytes) {
   return p;
 }
 
+// The flag lives in page-locked host memory mapped into the device's address space (the same pointer on both sides,
+// UVA): kernels set it on their -- rare -- error paths, and the host reads it after a stream synchronisation
+// without another device-to-host copy (the class API checks it at the end of every compute() call).
 int *WbWorkspace::error_flag() {
   if (!d_err_) {
-    if (cudaMalloc(&d_err_, sizeof(int)) != cudaSuccess) return nullptr;
-    cudaMemset(d_err_, 0, sizeof(int));
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) return nullptr;
+    d_err_ = static_cast<int *>(p);
+    *d_err_ = 0;
   }
   return d_err_;
 }
 
 int WbWorkspace::read_error_flag(cudaStream_t stream) {
   if (!d_err_) return WB_OK;
-  int h = 0;
-  if (cudaMemcpyAsync(&h, d_err_, sizeof(int), cudaMemcpyDeviceToHost, stream) != cudaSuccess) return WB_ERR_CUDA;
   if (cudaStreamSynchronize(stream) != cudaSuccess) return WB_ERR_CUDA;
-  if (h != 0) cudaMemsetAsync(d_err_, 0, sizeof(int), stream);
+  volatile int *flag = d_err_;
+  const int h = *flag;
+  if (h != 0) *flag = 0;
   return h;
 }
 
