@@ -473,7 +473,7 @@ def main():
         for rep in range(3):               # first repetition = warm-up (allocations, plan tables)
             barrier()
             t = {}
-            so = parallel.process_stream_exact(sx, FS, hopt, copt, dopt, segment_seconds=30, halo_seconds=2,
+            so = parallel.process_stream_exact(sx, FS, hopt, copt, dopt, segment_seconds=120, halo_seconds=2,
                                                shards_per_rank=k_shards, keep_rows=False, timings=t, state=keep)
             tot = torch.tensor([t["total"]], dtype=torch.float64, device="cuda")
             if world > 1:

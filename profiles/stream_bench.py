@@ -28,7 +28,7 @@ def main():
     ap.add_argument("--fs", type=int, default=48000)
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--shards-per-rank", type=int, default=1)
-    ap.add_argument("--segment-seconds", type=int, default=30)
+    ap.add_argument("--segment-seconds", type=int, default=120)
     ap.add_argument("--profile", action="store_true", help="one extra run with per-kernel CUDA-event timing (stderr)")
     args = ap.parse_args()
     if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):

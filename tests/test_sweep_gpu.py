@@ -68,11 +68,12 @@ def test_loud_input_takes_the_truncating_dc_path(wb, signals):
 
 
 def test_long_utterance(wb, signals):
-    """70 s in one piece: 88 overlap-save blocks in Harvest, contour buffers beyond shared memory."""
+    """90 s in one piece: 113 overlap-save blocks in Harvest, contour buffers beyond shared memory, and 18 001 frames --
+    past the 16 384 up to which the frames' randn() positions are scanned by one CTA (wb_scan.cuh: grid-wide above)."""
     fs = 16000
-    x = signals.synth_speech(fs, 70.0, seed=25)
+    x = signals.synth_speech(fs, 90.0, seed=25)
     ref, _ = refbin.run_reference(x, fs, stages="hcds")
-    _compare(_chain(wb, x, fs), ref, "70 s utterance")
+    _compare(_chain(wb, x, fs), ref, "90 s utterance")
 
 
 def test_harvest_beyond_128_overlap_save_blocks(wb, signals):

@@ -7,6 +7,7 @@
 //   addInfinitesimalNoise :220-228, smoothingWithRecovery :230-276.
 #include "wb_internal.h"
 #include "wb_fft.cuh"
+#include "wb_scan.cuh"
 #include "wb_smooth.cuh"
 
 namespace {
@@ -28,6 +29,16 @@ __global__ void __launch_bounds__(1024) ct_count_scan_kernel(const double *__res
     return (unsigned long long)(2 * hw + 1) + (unsigned long long)(fft_size / 2 + 1);
   }, f0_length, offsets, skip_in, skip_out);
 }
+
+// the same count as a functor, for the grid-wide scan of long streams (wb_scan.cuh)
+struct CtCountFn {
+  const double *f0; int fs, fft_size; double f0_floor;
+  __device__ unsigned long long operator()(int i) const {
+    const double cf0 = ct_current_f0(f0[i], f0_floor);
+    const int hw = wb_round(1.5 * fs / cf0);
+    return (unsigned long long)(2 * hw + 1) + (unsigned long long)(fft_size / 2 + 1);
+  }
+};
 
 struct CtParams {
   const double *x;
@@ -171,10 +182,15 @@ int wb_cheaptrick_run(WbWorkspace *ws, int fs, int fft_size, double q1, double f
     if (!d_noise_b) return WB_ERR_CUDA;
   }
   if (rng.wait_skip_in) WB_CUDA_CHECK(cudaStreamWaitEvent(stream, rng.wait_skip_in, 0));
-  WB_LAUNCH("ct_count_scan_kernel", ct_count_scan_kernel<<<1, 1024, 0, stream>>>(d_f0, f0_length, fs, fft_size, f0_floor_internal,
-                                                                              d_offsets, rng.skip_in, rng.skip_out));  // d_offsets[f0_length] = total
-  WB_CUDA_CHECK(cudaGetLastError());
   int rc;
+  if (f0_length > WB_SCAN_SINGLE_CTA_MAX) {
+    CtCountFn fn = {d_f0, fs, fft_size, f0_floor_internal};
+    if ((rc = wb_count_scan_tiles(fn, f0_length, d_offsets, rng.skip_in, nullptr, nullptr, rng.skip_out, ws, "ct_scan_tiles", stream))) return rc;
+  } else {
+    WB_LAUNCH("ct_count_scan_kernel", ct_count_scan_kernel<<<1, 1024, 0, stream>>>(d_f0, f0_length, fs, fft_size, f0_floor_internal,
+                                                                                d_offsets, rng.skip_in, rng.skip_out));  // d_offsets[f0_length] = total
+    WB_CUDA_CHECK(cudaGetLastError());
+  }
   if (rng.record_skip_out) WB_CUDA_CHECK(cudaEventRecord(rng.record_skip_out, stream));
   const unsigned long long *d_noise_off = d_offsets;
   if (range) {

@@ -9,6 +9,7 @@
 //   getCoarseAperiodicity :466-503.
 #include "wb_internal.h"
 #include "wb_fft.cuh"
+#include "wb_scan.cuh"
 #include "wb_smooth.cuh"
 
 #include <math.h>
@@ -60,6 +61,24 @@ __global__ void __launch_bounds__(1024) body_count_scan_kernel(const double *__r
     return c;
   }, n, offsets, skip_in, skip_out);
 }
+
+// the same counts as functors, for the grid-wide scan of long streams (wb_scan.cuh)
+struct LtCountFn {
+  const double *f0; int fs; double lowest_f0;
+  __device__ unsigned long long operator()(int i) const {
+    if (f0[i] == 0.0) return 0ull;
+    const double cf0 = f0[i] > lowest_f0 ? f0[i] : lowest_f0;
+    return 2ull * d4c_half_window(3.0, fs, cf0) + 1ull;
+  }
+};
+struct BodyCountFn {
+  const double *f0; const double *ap0; int fs; double threshold;
+  __device__ unsigned long long operator()(int i) const {
+    if (f0[i] == 0 || ap0[i] <= threshold) return 0ull;
+    const double cf0 = f0[i] > WB_FLOOR_F0_D4C ? f0[i] : WB_FLOOR_F0_D4C;
+    return 3ull * (2ull * d4c_half_window(4.0, fs, cf0) + 1ull);
+  }
+};
 
 // ---- Love Train (d4c.cpp:181-240) ---------------------------------------------------------
 struct LtParams {
@@ -847,10 +866,15 @@ int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int
   // ---- Love Train (its frame offsets do not depend on the stream position: only the draw itself waits)
   unsigned long long *d_lt_total = (unsigned long long *)ws->get("d4c_lt_total", sizeof(unsigned long long));
   if (!d_lt_total) return WB_ERR_CUDA;
-  WB_LAUNCH("lt_count_scan_kernel", lt_count_scan_kernel<<<1, 1024, 0, stream>>>(d_f0, f0_length, fs, 40.0, d_offsets, nullptr, d_lt_total));
-  WB_CUDA_CHECK(cudaGetLastError());
-  if (rng.wait_skip_in) WB_CUDA_CHECK(cudaStreamWaitEvent(stream, rng.wait_skip_in, 0));
   int rc;
+  if (f0_length > WB_SCAN_SINGLE_CTA_MAX) {
+    LtCountFn fn = {d_f0, fs, 40.0};
+    if ((rc = wb_count_scan_tiles(fn, f0_length, d_offsets, nullptr, nullptr, nullptr, d_lt_total, ws, "d4c_scan_tiles", stream))) return rc;
+  } else {
+    WB_LAUNCH("lt_count_scan_kernel", lt_count_scan_kernel<<<1, 1024, 0, stream>>>(d_f0, f0_length, fs, 40.0, d_offsets, nullptr, d_lt_total));
+    WB_CUDA_CHECK(cudaGetLastError());
+  }
+  if (rng.wait_skip_in) WB_CUDA_CHECK(cudaStreamWaitEvent(stream, rng.wait_skip_in, 0));
   // Row chunks of a whole-utterance call alternate between two streams, one noise buffer each: the randn() fill of a
   // chunk runs beside the frames of the chunk before it (integer work beside fp64 work) instead of in front of them.
   // Two users: the fused pipeline (WbStageSplit: D4C_SPLIT chunks) and the host API's chunked download (WbRowChunks:
@@ -915,9 +939,14 @@ int wb_d4c_run(WbWorkspace *ws, int fs, double threshold, const double *d_x, int
   }
   if (phase == 1) return WB_OK;   // (the stream bookkeeping is done by the body phase)
   // ---- body
-  WB_LAUNCH("body_count_scan_kernel", body_count_scan_kernel<<<1, 1024, 0, stream>>>(d_f0, d_ap0, f0_length, fs, threshold, d_offsets,
-                                                                                  rng.skip_in, d_lt_total, d_skip_mid, d_skip_end));
-  WB_CUDA_CHECK(cudaGetLastError());
+  if (f0_length > WB_SCAN_SINGLE_CTA_MAX) {
+    BodyCountFn fn = {d_f0, d_ap0, fs, threshold};
+    if ((rc = wb_count_scan_tiles(fn, f0_length, d_offsets, rng.skip_in, d_lt_total, d_skip_mid, d_skip_end, ws, "d4c_scan_tiles", stream))) return rc;
+  } else {
+    WB_LAUNCH("body_count_scan_kernel", body_count_scan_kernel<<<1, 1024, 0, stream>>>(d_f0, d_ap0, f0_length, fs, threshold, d_offsets,
+                                                                                    rng.skip_in, d_lt_total, d_skip_mid, d_skip_end));
+    WB_CUDA_CHECK(cudaGetLastError());
+  }
   if (rng.record_skip_out) WB_CUDA_CHECK(cudaEventRecord(rng.record_skip_out, stream));
   if (n_chunks > 1) {
     cudaEvent_t fork = split ? split->fork[1] : chunks->ev_ready;

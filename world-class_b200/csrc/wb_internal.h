@@ -37,9 +37,10 @@ const cplx *wb_twiddle_table(int n);
 
 // offsets[0..n] <- exclusive prefix sums of counts[0..n) (offsets[n] = total); optionally publishes
 // *d_skip_out = *d_skip_in + total (randn stream bookkeeping, see WbRngCursor)
+// (ws: scratch for the grid-wide version used above 16384 items; null = always one CTA)
 int wb_exclusive_scan_u64(const unsigned long long *d_counts, unsigned long long *d_offsets, int n,
                           cudaStream_t stream, const unsigned long long *d_skip_in = nullptr,
-                          unsigned long long *d_skip_out = nullptr);
+                          unsigned long long *d_skip_out = nullptr, WbWorkspace *ws = nullptr);
 
 // Host-pointer entry points overlap the device -> host transfer of finished output rows with the frames
 // still being computed: the frame kernel is launched in `n` row ranges [bounds[c], bounds[c+1]) that

@@ -1,5 +1,6 @@
 // Host runtime: workspaces, twiddle tables, small utility kernels.
 #include "wb_internal.h"
+#include "wb_scan.cuh"
 
 #include <math.h>
 #include <string.h>
@@ -145,8 +146,54 @@ const cplx *wb_twiddle_table(int n) {
   return d;
 }
 
+namespace {
+struct CountsFn {
+  const unsigned long long *counts;
+  __device__ unsigned long long operator()(int i) const { return counts[i]; }
+};
+
+// one CTA: tile_off <- exclusive scan of tile_sum, stream bookkeeping (see wb_scan.cuh)
+__global__ void __launch_bounds__(SCAN_THREADS) tile_scan_kernel(const unsigned long long *__restrict__ tile_sum, int n_tiles,
+                                                                 unsigned long long *__restrict__ tile_off,
+                                                                 unsigned long long *__restrict__ total_out,
+                                                                 const unsigned long long *__restrict__ skip_in,
+                                                                 const unsigned long long *__restrict__ skip_add,
+                                                                 unsigned long long *__restrict__ skip_mid,
+                                                                 unsigned long long *__restrict__ skip_out) {
+  wb_block_count_scan([&](int i) { return tile_sum[i]; }, n_tiles, tile_off, nullptr, nullptr);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long total = tile_off[n_tiles];
+    const unsigned long long base = (skip_in ? *skip_in : 0ull) + (skip_add ? *skip_add : 0ull);
+    *total_out = total;
+    if (skip_mid) *skip_mid = base;
+    if (skip_out) *skip_out = base + total;
+  }
+}
+
+__global__ void tile_add_kernel(unsigned long long *__restrict__ offsets, int n, const unsigned long long *__restrict__ tile_off) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) offsets[i] += tile_off[i / WB_SCAN_TILE];
+}
+}  // namespace
+
+int wb_tile_scan_finish(unsigned long long *d_offsets, int n, unsigned long long *d_tile_sum, unsigned long long *d_tile_off,
+                        int n_tiles, const unsigned long long *d_skip_in, const unsigned long long *d_skip_add,
+                        unsigned long long *d_skip_mid, unsigned long long *d_skip_out, cudaStream_t stream) {
+  WB_LAUNCH("tile_scan_kernel", tile_scan_kernel<<<1, SCAN_THREADS, 0, stream>>>(d_tile_sum, n_tiles, d_tile_off, d_offsets + n, d_skip_in,
+                                                                              d_skip_add, d_skip_mid, d_skip_out));
+  WB_LAUNCH("tile_add_kernel", tile_add_kernel<<<(n + 255) / 256, 256, 0, stream>>>(d_offsets, n, d_tile_off));
+  WB_CUDA_CHECK(cudaGetLastError());
+  return WB_OK;
+}
+
 int wb_exclusive_scan_u64(const unsigned long long *d_counts, unsigned long long *d_offsets, int n,
-                          cudaStream_t stream, const unsigned long long *d_skip_in, unsigned long long *d_skip_out) {
+                          cudaStream_t stream, const unsigned long long *d_skip_in, unsigned long long *d_skip_out,
+                          WbWorkspace *ws) {
+  if (ws && n > WB_SCAN_SINGLE_CTA_MAX) {   // long streams: the whole GPU instead of one CTA
+    CountsFn fn = {d_counts};
+    return wb_count_scan_tiles(fn, n, d_offsets, d_skip_in, nullptr, nullptr, d_skip_out, ws, "scan_u64_tiles", stream);
+  }
   WB_LAUNCH("scan_u64_kernel", scan_u64_kernel<<<1, SCAN_THREADS, 0, stream>>>(d_counts, d_offsets, n, d_skip_in, d_skip_out));
   WB_CUDA_CHECK(cudaGetLastError());
   return WB_OK;

@@ -822,7 +822,7 @@ int wb_synthesis_timebase(WbWorkspace *ws, int fs, int fft_size, double frame_pe
   }
   // (a window is a piece of the stream whose element 0 is sample win_lo, like a piece of a streaming synthesis)
   WB_LAUNCH("pulse_count_kernel", pulse_count_kernel<<<n_blocks, PD_THREADS, 0, stream>>>(d_total + win_lo, win, d_bc));
-  int rc = wb_exclusive_scan_u64(d_bc, d_bo, n_blocks, stream);
+  int rc = wb_exclusive_scan_u64(d_bc, d_bo, n_blocks, stream, nullptr, nullptr, ws);
   if (rc) return rc;
   WB_LAUNCH("pulse_write_kernel", pulse_write_kernel<<<n_blocks, PD_THREADS, 0, stream>>>(d_total + win_lo, win, fs, d_bo, d_pidx, d_pshift, max_pulses,
                                                                                         win_lo, 0, nullptr, nullptr));

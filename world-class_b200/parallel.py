@@ -165,7 +165,7 @@ class StreamPlan:
     a segment is congruent to n_samples modulo the decimation ratio, which gives the segment the
     whole-stream decimation phase (decimate() starts at x_length % r - 1, world_matlabfunctions.cpp:201-206)."""
 
-    def __init__(self, n_samples, fs, world, frame_period=5.0, fft_size=2048, segment_seconds=30, halo_seconds=2,
+    def __init__(self, n_samples, fs, world, frame_period=5.0, fft_size=2048, segment_seconds=120, halo_seconds=2,
                  target_fs=8000.0):
         fps = 1000.0 / frame_period
         if abs(fps - round(fps)) > 1e-9:
@@ -189,9 +189,12 @@ class StreamPlan:
             fe = self.f0_length if k == self.world - 1 else min(self.f0_length, s1 * self.fps)
             self.frames.append((fb, fe))
             segs = []
+            # the rank's seconds in the fewest pieces of at most `seg` seconds, evenly long (every piece pays its halo)
+            n_seg = max(1, -(-(s1 - s0) // seg))
+            step = max(1, -(-(s1 - s0) // n_seg))
             a = s0
             while a < s1:
-                b = min(s1, a + seg)
+                b = min(s1, a + step)
                 pa = max(0, a - halo) * self.fs
                 pb = min(self.n, (b + halo) * self.fs)
                 pb -= (pb - self.n) % self.r                  # whole-stream decimation phase
@@ -395,7 +398,7 @@ class StreamWorker:
         return d_rows[fb - ra:fe - ra]
 
 
-def process_stream_exact(d_x, fs, harvest_option=None, cheaptrick_option=None, d4c_option=None, segment_seconds=30,
+def process_stream_exact(d_x, fs, harvest_option=None, cheaptrick_option=None, d4c_option=None, segment_seconds=120,
                          halo_seconds=2, group=None, d_f0_all=None, shards_per_rank=1, keep_rows=True, timings=None,
                          state=None):
     """Analysis + re-synthesis of one long stream (a float64 CUDA tensor every rank holds) sharded over the
@@ -495,7 +498,7 @@ def process_stream_exact(d_x, fs, harvest_option=None, cheaptrick_option=None, d
             "frames": (fb, fe), "plan": plan}
 
 
-def simulate_stream_ranks(d_x, fs, world, harvest_option=None, cheaptrick_option=None, d4c_option=None, segment_seconds=30,
+def simulate_stream_ranks(d_x, fs, world, harvest_option=None, cheaptrick_option=None, d4c_option=None, segment_seconds=120,
                           halo_seconds=2, d_f0_all=None):
     """The same computation as process_stream_exact() with `world` VIRTUAL ranks run one after the other in
     this process (one worker object each, as separate processes would have); the exchanges become plain
