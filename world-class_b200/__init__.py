@@ -306,6 +306,11 @@ class Harvest:
                "wb_harvest_compute")
         return tpos, f0
 
+    def check_errors(self, stream=0):
+        """After asynchronous wb_harvest_compute_dev calls on `stream`: waits for it and raises if a kernel flagged
+        a condition it could not handle; the flag is cleared."""
+        _check(lib().wb_harvest_last_error(self._h, stream or None), "device-side error of an earlier Harvest call")
+
     def debug_read(self, name, shape, dtype=np.float64):
         out = np.empty(shape, dtype=dtype)
         _check(lib().wb_harvest_debug_read(self._h, name.encode(), out.ctypes.data, out.nbytes), "wb_harvest_debug_read")

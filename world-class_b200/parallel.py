@@ -13,7 +13,11 @@ Two cases:
 
 torch.distributed is used for the plumbing only (NCCL on GPUs, gloo in the CPU tests).
 """
+import ctypes
 import numpy as np
+
+
+HARVESTS_IN_FLIGHT = 3   # Harvest segments of a rank analysed concurrently (one Harvest object + stream each)
 
 
 def shard_indices(n_items, rank, world):
@@ -293,33 +297,21 @@ class StreamWorker:
         self.harvest_option = harvest_option if harvest_option is not None else wb.HarvestOption()
         assert abs(self.harvest_option.frame_period - plan.fp) < 1e-12
         if share is not None:
-            self.pipe, self.harvest = share.pipe, share.harvest
+            self.pipe, self.harvests, self.streams = share.pipe, share.harvests, share.streams
         else:
             self.pipe = wb.Pipeline(plan.fs, self.harvest_option, cheaptrick_option, d4c_option)
             self.pipe.set_fresh_rng(True)                       # the stream is one reference process
-            self.harvest = wb.Harvest(plan.fs, self.harvest_option)
+            # two Harvest objects on two streams: consecutive segments overlap (the one-CTA contour tail of one
+            # runs beside the band-pass bank of the other)
+            self.harvests = [wb.Harvest(plan.fs, self.harvest_option) for _ in range(HARVESTS_IN_FLIGHT)]
+            self.streams = [torch.cuda.Stream() for _ in range(HARVESTS_IN_FLIGHT)]
+        self.harvest = self.harvests[0]
         assert self.pipe.fft_size == plan.fft_size, "plan was made for another FFT size"
         self.bins = plan.fft_size // 2 + 1
 
     def harvest_local(self, d_x):
         """f0 of the frames this shard owns (whole-stream frame grid)."""
-        self.torch.cuda.current_stream().synchronize()   # inputs made by torch ops; the library has its own stream
-        torch, L = self.torch, self.wb.lib()
-        fb, fe = self.plan.frames[self.rank]
-        out = torch.zeros(fe - fb, dtype=torch.float64, device=d_x.device)
-        for seg in self.plan.segments[self.rank]:
-            pa, pb = seg["padded"]
-            n = pb - pa
-            n_local = self.harvest.getSamples(self.plan.fs, n)
-            d_t = torch.empty(n_local, dtype=torch.float64, device=d_x.device)
-            d_f = torch.empty(n_local, dtype=torch.float64, device=d_x.device)
-            self.wb._check(L.wb_harvest_compute_dev(self.harvest._h, d_x.data_ptr() + 8 * pa, n, d_t.data_ptr(), d_f.data_ptr(), None),
-                           "wb_harvest_compute_dev")
-            self.wb.device_synchronize()
-            cfb, cfe = seg["frames"]
-            off = seg["frame_offset"]
-            out[cfb - fb:cfe - fb] = d_f[cfb - off:cfe - off]
-        return out
+        return harvest_shards([self], d_x)
 
     def begin(self, d_f0_all, samples=None):
         """whole-stream bookkeeping (frame times, randn() seed, time base + pulse list): once per pipeline.
@@ -398,6 +390,37 @@ class StreamWorker:
         return d_rows[fb - ra:fe - ra]
 
 
+def harvest_shards(workers, d_x):
+    """f0 of the frames the given shards of one rank own (consecutive shards sharing their Harvest objects), as one
+    tensor.  The padded segments of all of them go round-robin over HARVESTS_IN_FLIGHT Harvest objects / streams
+    and are waited for once."""
+    w0 = workers[0]
+    torch, wb, plan = w0.torch, w0.wb, w0.plan
+    torch.cuda.current_stream().synchronize()   # inputs made by torch ops; the library calls run on their own streams
+    L = wb.lib()
+    fb, fe = plan.frames[workers[0].rank][0], plan.frames[workers[-1].rank][1]
+    out = torch.zeros(fe - fb, dtype=torch.float64, device=d_x.device)
+    done = []
+    k = len(w0.harvests)
+    for seg in [s for w in workers for s in plan.segments[w.rank]]:
+        pa, pb = seg["padded"]
+        n = pb - pa
+        h, st = w0.harvests[len(done) % k], w0.streams[len(done) % k]
+        n_local = h.getSamples(plan.fs, n)
+        d_t = torch.empty(n_local, dtype=torch.float64, device=d_x.device)
+        d_f = torch.empty(n_local, dtype=torch.float64, device=d_x.device)
+        wb._check(L.wb_harvest_compute_dev(h._h, d_x.data_ptr() + 8 * pa, n, d_t.data_ptr(), d_f.data_ptr(),
+                                           ctypes.c_void_p(st.cuda_stream)), "wb_harvest_compute_dev")
+        done.append((seg, d_f, d_t))
+    for h, st in zip(w0.harvests, w0.streams):
+        h.check_errors(st.cuda_stream)       # (waits for the stream)
+    for seg, d_f, _ in done:
+        cfb, cfe = seg["frames"]
+        off = seg["frame_offset"]
+        out[cfb - fb:cfe - fb] = d_f[cfb - off:cfe - off]
+    return out
+
+
 def process_stream_exact(d_x, fs, harvest_option=None, cheaptrick_option=None, d4c_option=None, segment_seconds=120,
                          halo_seconds=2, group=None, d_f0_all=None, shards_per_rank=1, keep_rows=True, timings=None,
                          state=None):
@@ -445,7 +468,7 @@ def process_stream_exact(d_x, fs, harvest_option=None, cheaptrick_option=None, d
     mark("start")
     external_f0 = d_f0_all is not None
     if d_f0_all is None:
-        local_f0 = torch.cat([w.harvest_local(d_x) for w in workers])
+        local_f0 = harvest_shards(workers, d_x)
         mark("harvest")
         d_f0_all = gather_ranges(local_f0, rank_frames, plan.f0_length, group)                   # exchange 1
         mark("gather_f0")
