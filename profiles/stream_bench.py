@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--shards-per-rank", type=int, default=1)
     ap.add_argument("--segment-seconds", type=int, default=120)
+    ap.add_argument("--pipelines", type=int, default=1, help="groups of the rank's shards in flight (one pipeline + stream each)")
     ap.add_argument("--profile", action="store_true", help="one extra run with per-kernel CUDA-event timing (stderr)")
     args = ap.parse_args()
     if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
@@ -58,7 +59,7 @@ def main():
         torch.cuda.synchronize()
         t = {}
         t0 = time.perf_counter()
-        out = parallel.process_stream_exact(d_x, args.fs, hopt, copt, dopt, segment_seconds=args.segment_seconds, halo_seconds=2,
+        out = parallel.process_stream_exact(d_x, args.fs, hopt, copt, dopt, segment_seconds=args.segment_seconds, halo_seconds=2, pipelines_in_flight=args.pipelines,
                                             shards_per_rank=args.shards_per_rank, keep_rows=False, timings=t, state=keep)
         torch.cuda.synchronize()
         wall = (time.perf_counter() - t0) * 1e3
@@ -70,7 +71,7 @@ def main():
     if args.profile and rank == 0:
         wb.profile_reset()
         wb.profile(True)
-        parallel.process_stream_exact(d_x, args.fs, hopt, copt, dopt, segment_seconds=args.segment_seconds, halo_seconds=2,
+        parallel.process_stream_exact(d_x, args.fs, hopt, copt, dopt, segment_seconds=args.segment_seconds, halo_seconds=2, pipelines_in_flight=args.pipelines,
                                       shards_per_rank=args.shards_per_rank, keep_rows=False, state=keep)
         table = wb.profile_results()
         wb.profile(False)

@@ -288,26 +288,51 @@ class PendingGather:
 
 class StreamWorker:
     """One shard of an exactly sharded stream on this process's GPU (torch CUDA tensors, C-ABI calls).  A rank
-    that owns several shards (bounded memory per step) shares one pipeline / Harvest object between them."""
+    that owns several shards (bounded memory per step) shares pipeline / Harvest objects between them:
+    `share` = a worker whose pipeline this one uses too (their stages then run one after the other), `harvests_of`
+    = a worker whose Harvest objects it uses.  `stream`: a torch stream every stage of this worker is enqueued on
+    WITHOUT waiting for it (the caller orders streams and waits once; workers of different pipelines then overlap
+    on the GPU); None = the library's own stream, every stage waited for (simple, serial)."""
 
-    def __init__(self, plan, shard, harvest_option=None, cheaptrick_option=None, d4c_option=None, share=None):
+    def __init__(self, plan, shard, harvest_option=None, cheaptrick_option=None, d4c_option=None, share=None,
+                 harvests_of=None, stream=None):
         import torch
         import worldb200 as wb
-        self.wb, self.torch, self.plan, self.rank = wb, torch, plan, shard
+        self.wb, self.torch, self.plan, self.rank, self.stream = wb, torch, plan, shard, stream
         self.harvest_option = harvest_option if harvest_option is not None else wb.HarvestOption()
         assert abs(self.harvest_option.frame_period - plan.fp) < 1e-12
         if share is not None:
-            self.pipe, self.harvests, self.streams = share.pipe, share.harvests, share.streams
+            self.pipe = share.pipe
         else:
             self.pipe = wb.Pipeline(plan.fs, self.harvest_option, cheaptrick_option, d4c_option)
             self.pipe.set_fresh_rng(True)                       # the stream is one reference process
-            # two Harvest objects on two streams: consecutive segments overlap (the one-CTA contour tail of one
-            # runs beside the band-pass bank of the other)
+        src = harvests_of if harvests_of is not None else share
+        if src is not None:
+            self.harvests, self.streams = src.harvests, src.streams
+        else:
+            # several Harvest objects on their own streams: consecutive segments overlap (the one-CTA contour tail
+            # of one runs beside the band-pass bank of the other)
             self.harvests = [wb.Harvest(plan.fs, self.harvest_option) for _ in range(HARVESTS_IN_FLIGHT)]
             self.streams = [torch.cuda.Stream() for _ in range(HARVESTS_IN_FLIGHT)]
         self.harvest = self.harvests[0]
         assert self.pipe.fft_size == plan.fft_size, "plan was made for another FFT size"
         self.bins = plan.fft_size // 2 + 1
+
+    # every stage: (serial mode) wait for torch's stream, run on the library's, wait for the device;
+    # (stream mode) allocate and run on self.stream, wait for nothing
+    def _enter(self):
+        if self.stream is None:
+            self.torch.cuda.current_stream().synchronize()   # inputs made by torch ops; the library has its own stream
+            return None
+        return ctypes.c_void_p(self.stream.cuda_stream)
+
+    def _leave(self):
+        if self.stream is None:
+            self.wb.device_synchronize()
+
+    def _on_stream(self):
+        import contextlib
+        return self.torch.cuda.stream(self.stream) if self.stream is not None else contextlib.nullcontext()
 
     def harvest_local(self, d_x):
         """f0 of the frames this shard owns (whole-stream frame grid)."""
@@ -317,71 +342,79 @@ class StreamWorker:
         """whole-stream bookkeeping (frame times, randn() seed, time base + pulse list): once per pipeline.
         `samples`: the sample range the shards of this pipeline will synthesise (default: this shard's) -- the
         pulse list is built for it only."""
-        self.torch.cuda.current_stream().synchronize()   # inputs made by torch ops; the library has its own stream
+        st = self._enter()
         self.d_f0_all = d_f0_all
         sa, sb = samples if samples is not None else self.plan.samples[self.rank]
         self.wb._check(self.wb.lib().wb_pipeline_stream_begin_range_dev(self.pipe._h, d_f0_all.data_ptr(), self.plan.f0_length,
-                                                                        self.plan.out_length, int(sa), int(sb), None),
+                                                                        self.plan.out_length, int(sa), int(sb), st),
                        "wb_pipeline_stream_begin_range_dev")
 
     def envelope(self, d_x, d_ap0_all):
         """CheapTrick + Love Train for the rows this shard needs; writes its entries of d_ap0_all."""
-        self.torch.cuda.current_stream().synchronize()   # inputs made by torch ops; the library has its own stream
+        st = self._enter()
         torch = self.torch
         ra, rb = self.plan.rows[self.rank]
-        self.d_sp = torch.empty((rb - ra, self.bins), dtype=torch.float64, device=d_x.device)
+        with self._on_stream():
+            self.d_sp = torch.empty((rb - ra, self.bins), dtype=torch.float64, device=d_x.device)
         self.wb._check(self.wb.lib().wb_pipeline_stream_envelope_dev(self.pipe._h, d_x.data_ptr(), self.plan.n, self.d_f0_all.data_ptr(),
                                                                      self.plan.f0_length, ra, rb, self.d_sp.data_ptr(),
-                                                                     d_ap0_all.data_ptr(), None), "wb_pipeline_stream_envelope_dev")
-        self.wb.device_synchronize()
+                                                                     d_ap0_all.data_ptr(), st), "wb_pipeline_stream_envelope_dev")
+        self._leave()
 
     def lovetrain(self, d_x, d_ap0_all):
         """first half of envelope(): Love Train for the rows this shard needs; writes its entries of d_ap0_all"""
-        self.torch.cuda.current_stream().synchronize()
+        st = self._enter()
         ra, rb = self.plan.rows[self.rank]
         self.wb._check(self.wb.lib().wb_pipeline_stream_lovetrain_dev(self.pipe._h, d_x.data_ptr(), self.plan.n, self.d_f0_all.data_ptr(),
-                                                                      self.plan.f0_length, ra, rb, d_ap0_all.data_ptr(), None),
+                                                                      self.plan.f0_length, ra, rb, d_ap0_all.data_ptr(), st),
                        "wb_pipeline_stream_lovetrain_dev")
-        self.wb.device_synchronize()
+        self._leave()
 
     def cheaptrick(self, d_x, sync=True):
         """second half of envelope(): the spectral envelope rows this shard needs"""
-        self.torch.cuda.current_stream().synchronize()
+        st = self._enter()
         torch = self.torch
         ra, rb = self.plan.rows[self.rank]
-        self.d_sp = torch.empty((rb - ra, self.bins), dtype=torch.float64, device=d_x.device)
+        with self._on_stream():
+            self.d_sp = torch.empty((rb - ra, self.bins), dtype=torch.float64, device=d_x.device)
         self.wb._check(self.wb.lib().wb_pipeline_stream_cheaptrick_dev(self.pipe._h, d_x.data_ptr(), self.plan.n, self.d_f0_all.data_ptr(),
-                                                                       self.plan.f0_length, ra, rb, self.d_sp.data_ptr(), None),
+                                                                       self.plan.f0_length, ra, rb, self.d_sp.data_ptr(), st),
                        "wb_pipeline_stream_cheaptrick_dev")
         if sync:
-            self.wb.device_synchronize()
+            self._leave()
 
     def aperiodicity(self, d_x, d_ap0_all):
-        self.torch.cuda.current_stream().synchronize()   # inputs made by torch ops; the library has its own stream
+        st = self._enter()
         torch = self.torch
         ra, rb = self.plan.rows[self.rank]
-        self.d_ap = torch.empty((rb - ra, self.bins), dtype=torch.float64, device=d_x.device)
+        with self._on_stream():
+            self.d_ap = torch.empty((rb - ra, self.bins), dtype=torch.float64, device=d_x.device)
         self.wb._check(self.wb.lib().wb_pipeline_stream_aperiodicity_dev(self.pipe._h, d_x.data_ptr(), self.plan.n, self.d_f0_all.data_ptr(),
                                                                          d_ap0_all.data_ptr(), self.plan.f0_length, ra, rb,
-                                                                         self.d_ap.data_ptr(), None), "wb_pipeline_stream_aperiodicity_dev")
-        self.wb.device_synchronize()
+                                                                         self.d_ap.data_ptr(), st), "wb_pipeline_stream_aperiodicity_dev")
+        self._leave()
 
     def synthesis(self):
-        self.torch.cuda.current_stream().synchronize()   # inputs made by torch ops; the library has its own stream
+        st = self._enter()
         torch = self.torch
         ra, rb = self.plan.rows[self.rank]
         sa, sb = self.plan.samples[self.rank]
-        d_y = torch.zeros(max(1, sb - sa), dtype=torch.float64, device=self.d_sp.device)
+        with self._on_stream():
+            d_y = torch.zeros(max(1, sb - sa), dtype=torch.float64, device=self.d_sp.device)
         self.wb._check(self.wb.lib().wb_pipeline_stream_synthesis_dev(self.pipe._h, self.plan.f0_length, self.d_sp.data_ptr(),
                                                                       self.d_ap.data_ptr(), ra, rb - ra, self.plan.out_length, sa, sb,
-                                                                      d_y.data_ptr(), None), "wb_pipeline_stream_synthesis_dev")
-        self.wb.device_synchronize()
+                                                                      d_y.data_ptr(), st), "wb_pipeline_stream_synthesis_dev")
+        self._leave()
         return d_y[:sb - sa]
 
     def end(self):
-        self.wb._check(self.wb.lib().wb_pipeline_stream_end_dev(self.pipe._h, None), "wb_pipeline_stream_end_dev")
-        self.wb.device_synchronize()
-        self.pipe.check_errors()     # (conditions a kernel of the asynchronous calls above could not handle)
+        st = self._enter()
+        self.wb._check(self.wb.lib().wb_pipeline_stream_end_dev(self.pipe._h, st), "wb_pipeline_stream_end_dev")
+        if self.stream is None:
+            self.wb.device_synchronize()
+            self.pipe.check_errors()     # (conditions a kernel of the asynchronous calls above could not handle)
+        else:
+            self.pipe.check_errors(self.stream.cuda_stream)    # (waits for the stream)
 
     def owned_rows(self, d_rows):
         """the rows of d_sp / d_ap this shard owns (without the halo rows it computed for its pulses)"""
@@ -423,7 +456,7 @@ def harvest_shards(workers, d_x):
 
 def process_stream_exact(d_x, fs, harvest_option=None, cheaptrick_option=None, d4c_option=None, segment_seconds=120,
                          halo_seconds=2, group=None, d_f0_all=None, shards_per_rank=1, keep_rows=True, timings=None,
-                         state=None):
+                         state=None, pipelines_in_flight=1):
     """Analysis + re-synthesis of one long stream (a float64 CUDA tensor every rank holds) sharded over the
     ranks of `group`.  Returns dict(f0 [whole], y [whole], sp, ap [this rank's rows], frames, plan).
     Pass d_f0_all to skip Harvest (e.g. a contour computed elsewhere).  shards_per_rank > 1 processes the
@@ -431,7 +464,11 @@ def process_stream_exact(d_x, fs, harvest_option=None, cheaptrick_option=None, d
     drops each shard's sp / ap rows once its samples are synthesised.  `timings`: a dict that receives CUDA-event
     milliseconds per phase.  `state`: a dict the caller keeps between calls on streams of the same shape; the
     pipeline objects (and with them their device workspaces: several GB for long streams) are then reused
-    instead of being allocated and freed by every call."""
+    instead of being allocated and freed by every call.  pipelines_in_flight: how many groups of the rank's shards
+    run concurrently (one pipeline object and CUDA stream each; at most shards_per_rank).  Measured on one hour of
+    48 kHz audio on one B200: 1 / 2 / 4 / 8 groups take 464.5 / 465.9 / 467.4 / 473.4 ms -- the frame kernels of a
+    long shard each fill the register file of every SM, so a second pipeline finds nothing to overlap with (unlike
+    batches of short utterances, cf. BatchPipeline); the default is therefore 1."""
     import torch
     import torch.distributed as dist
     import worldb200 as wb
@@ -444,18 +481,43 @@ def process_stream_exact(d_x, fs, harvest_option=None, cheaptrick_option=None, d
     fft_size = copt.fft_size if copt.fft_size else wb.CheapTrick.getFFTSizeForCheapTrick(fs, copt.f0_floor)
     plan = StreamPlan(d_x.numel(), fs, world * k, hopt.frame_period, fft_size, segment_seconds, halo_seconds, hopt.target_fs)
     mine = list(range(rank * k, (rank + 1) * k))
-    key = (plan.n, plan.fs, world, k, plan.fp, plan.fft_size, int(segment_seconds), int(halo_seconds))
+    # The rank's shards form `n_groups` contiguous groups; a group shares one pipeline object (its shards run one
+    # after the other: bounded scratch) on its own CUDA stream; groups may overlap on the GPU (see the docstring).
+    n_groups = max(1, min(k, int(pipelines_in_flight)))
+    key = (plan.n, plan.fs, world, k, n_groups, plan.fp, plan.fft_size, int(segment_seconds), int(halo_seconds))
     if state is not None and state.get("key") == key:
-        workers = state["workers"]
+        groups = state["groups"]
     else:
-        workers = []
-        for s in mine:
-            workers.append(StreamWorker(plan, s, hopt, cheaptrick_option, d4c_option, share=workers[0] if workers else None))
+        groups = []
+        for g in range(n_groups):
+            members = mine[(k * g) // n_groups:(k * (g + 1)) // n_groups]
+            stream = torch.cuda.Stream()
+            ws = []
+            for s in members:
+                ws.append(StreamWorker(plan, s, hopt, cheaptrick_option, d4c_option, share=ws[0] if ws else None,
+                                       harvests_of=groups[0][0] if groups else (ws[0] if ws else None), stream=stream))
+            groups.append(ws)
         if state is not None:
-            state.update(key=key, workers=workers)
+            state.update(key=key, groups=groups)
+    workers = [w for ws in groups for w in ws]
+    main = torch.cuda.current_stream()
+
+    def fork():      # the group streams see what torch's stream has produced so far
+        for ws in groups:
+            ws[0].stream.wait_stream(main)
+
+    def join():      # ... and torch's stream what the groups have produced
+        for ws in groups:
+            main.wait_stream(ws[0].stream)
+
+    def round_robin():   # shard order that keeps every group's stream fed: first shards of all groups, then the second ...
+        for j in range(max(len(ws) for ws in groups)):
+            for ws in groups:
+                if j < len(ws):
+                    yield ws[j]
+
     # per-rank contiguous ranges for the exchanges
     rank_frames = [(plan.frames[r * k][0], plan.frames[(r + 1) * k - 1][1]) for r in range(world)]
-    rank_samples = [(plan.samples[r * k][0], plan.samples[(r + 1) * k - 1][1]) for r in range(world)]
     marks = []
 
     def mark(name):
@@ -472,45 +534,57 @@ def process_stream_exact(d_x, fs, harvest_option=None, cheaptrick_option=None, d
         mark("harvest")
         d_f0_all = gather_ranges(local_f0, rank_frames, plan.f0_length, group)                   # exchange 1
         mark("gather_f0")
-    if external_f0:
-        # the contour is the caller's: size the pulse buffers by its maximum instead of Harvest's ceiling
-        workers[0].pipe.set_stream_f0_bound(float(d_f0_all.max().item()) + 1.0)
-    else:
-        workers[0].pipe.set_stream_f0_bound(0.0)
-    workers[0].begin(d_f0_all, rank_samples[rank])
-    for w in workers[1:]:
-        w.d_f0_all = d_f0_all
+    # (an external contour is the caller's: size the pulse buffers by its maximum instead of Harvest's ceiling)
+    f0_bound = float(d_f0_all.max().item()) + 1.0 if external_f0 else 0.0
+    d_ap0 = torch.zeros(plan.f0_length, dtype=torch.float64, device=d_x.device)
+    fork()
+    for ws in groups:
+        ws[0].pipe.set_stream_f0_bound(f0_bound)
+        ws[0].begin(d_f0_all, (plan.samples[ws[0].rank][0], plan.samples[ws[-1].rank][1]))
+        for w in ws[1:]:
+            w.d_f0_all = d_f0_all
     # Love Train first: its decisions (8 bytes per frame) travel while CheapTrick -- the longer half of the
     # envelope work -- runs, so the ranks do not sit in the exchange waiting for the slowest of them
-    d_ap0 = torch.zeros(plan.f0_length, dtype=torch.float64, device=d_x.device)
-    for w in workers:
+    for w in round_robin():
         w.lovetrain(d_x, d_ap0)
+    join()
     mark("lovetrain")
     fb, fe = rank_frames[rank]
     pending_ap0 = PendingGather(d_ap0[fb:fe].clone(), rank_frames, group)                        # exchange 2 (in flight)
-    for w in workers:
+    for w in round_robin():
         w.cheaptrick(d_x)
+    join()
     mark("cheaptrick")
     d_ap0 = pending_ap0.finish(plan.f0_length)
-    torch.cuda.current_stream().synchronize()
+    main.synchronize()
     mark("wait_ap0")
+    fork()
     # shard by shard: aperiodicity + synthesis, and the shard's samples go into the exchange (the stitch) while
-    # the next shard computes; only the last shard's exchange is exposed
-    pending, sps, aps = [], [], []
-    for j, w in enumerate(workers):
+    # the other shards compute; only the last exchanges are exposed
+    done = {}
+    for w in round_robin():
         w.aperiodicity(d_x, d_ap0)
-        y_j = w.synthesis()
-        pending.append(PendingGather(y_j, [plan.samples[r * k + j] for r in range(world)], group))   # exchange 3
+        y = w.synthesis()
+        ev = torch.cuda.Event()
+        ev.record(w.stream)
+        done[w.rank] = (y, ev)
+    pending, sps, aps = [], [], []
+    for j, s in enumerate(mine):                                   # (the same order on every rank)
+        w = workers[j]
+        y, ev = done[s]
+        main.wait_event(ev)
+        pending.append(PendingGather(y, [plan.samples[r * k + j] for r in range(world)], group))   # exchange 3
         if keep_rows:
             sps.append(w.owned_rows(w.d_sp))
             aps.append(w.owned_rows(w.d_ap))
         w.d_sp = w.d_ap = None
-    workers[0].end()
+    for ws in groups:
+        ws[0].end()
     mark("aperiodicity_synthesis")
     d_y = torch.empty(plan.out_length, dtype=torch.float64, device=d_x.device)
     for pg in pending:
         pg.finish_into(d_y)
-    torch.cuda.current_stream().synchronize()
+    main.synchronize()
     mark("stitch_tail")
     if timings is not None:
         torch.cuda.synchronize()
