@@ -70,6 +70,35 @@ def test_streaming_synthesis_equals_the_one_shot_call_bit_for_bit(wb, signals, f
     assert emitted_early > 0.8 * ny - 2 * fft_size          # it really streams: most samples leave before finish()
 
 
+def test_long_waveform_pulse_scan_matches_the_piecewise_one(wb):
+    """90 s at 48 kHz in one compute(): 4.32 M samples = 16 875 pulse-count blocks, past the 16 384 items one CTA
+    scans (wb_scan.cuh: grid-wide above).  The streaming synthesis sees the same frames in pieces of 1500 (its scans
+    stay on one CTA) and must give the same waveform and randn() state bit for bit."""
+    fs, fft_size, L = 48000, 2048, 18001
+    bins = fft_size // 2 + 1
+    rng = np.random.default_rng(5)
+    t = np.arange(L) * 0.005
+    f0 = 140.0 + 50.0 * np.sin(2 * np.pi * 0.31 * t) + 20.0 * np.sin(2 * np.pi * 2.3 * t)
+    f0[(t % 3.7) > 2.9] = 0.0                                   # unvoiced stretches
+    env = np.exp(-np.arange(bins) / 300.0)[None, :]
+    sp = (env * (0.5 + rng.random((L, 1)))) ** 2 + 1e-12
+    ap = np.clip(0.05 + 0.9 * (np.arange(bins)[None, :] / bins) * (0.5 + 0.5 * rng.random((L, 1))), 0.001, 0.999)
+    ny = wb.synthesis_length(L, 5.0, fs)
+    wb.randn_reseed()
+    want = wb.Synthesis(fs, fft_size, 5.0).compute(f0, sp, ap, ny)
+    state_after = wb.randn_get_state()
+    wb.randn_reseed()
+    st = wb.SynthesisStream(fs, fft_size, 5.0, 1000.0)
+    got = [st.push(f0[a:a + 1500], sp[a:a + 1500], ap[a:a + 1500]) for a in range(0, L, 1500)]
+    got.append(st.finish(ny))
+    y = np.concatenate(got)
+    assert len(y) == ny and np.abs(want).max() > 1e-3
+    bad = np.flatnonzero(y != want)
+    assert bad.size == 0, "first / count of differing samples: %d %d" % (bad[0], bad.size)
+    assert wb.randn_get_state() == state_after
+    wb.randn_reseed()
+
+
 def test_streaming_synthesis_small_output_buffers_and_errors(wb, signals):
     fs = 16000
     f0, sp, ap, fft_size, ny = _analysis(wb, signals, fs, 1.0, 42)
