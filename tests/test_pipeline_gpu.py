@@ -111,3 +111,29 @@ def test_graph_survives_workspace_growth(wb, signals):
     ya2 = run(d_a, len(xa), d_ya)
     assert np.abs(yb).max() > 0.1
     assert all(np.array_equal(ya[0], y) for y in ya[1:]) and np.array_equal(ya[0], ya2)
+
+
+def test_page_locked_outputs_are_downloaded_inside_the_chain(wb, signals):
+    """wb_pipeline_run with page-locked caller buffers sends every result home as soon as its stage is done (f0 after
+    Harvest, the spectrogram beside D4C, the aperiodicity beside the impulse responses): same bits as the ordinary
+    pageable path, with and without graph replay, also when the caller rotates between two sets of buffers."""
+    import torch
+    fs = 16000
+    x = signals.synth_speech(fs, 1.3, seed=77)
+    pl = wb.Pipeline(fs, wb.HarvestOption(f0_floor=40.0, frame_period=5.0), wb.CheapTrickOption(f0_floor=71.0), wb.D4COption(threshold=0.85))
+    pl.set_fresh_rng(True)
+    want = pl.run(x)
+    L, bins, ny = len(want["f0"]), want["sp"].shape[1], len(want["y"])
+    pin = lambda *shape: torch.zeros(shape, dtype=torch.float64).pin_memory().numpy()
+    sets = [dict(tpos=pin(L), f0=pin(L), sp=pin(L, bins), ap=pin(L, bins), y=pin(ny)) for _ in range(2)]
+    for graph in (False, True):
+        pl.set_graph(graph)
+        for k in (0, 0, 0, 1, 0, 1, 1, 1):          # repeats (graph captured and replayed) and rotations (plain launches)
+            for a in sets[k].values():
+                a[...] = -1.0
+            got = pl.run(x, out=sets[k])
+            for name in ("tpos", "f0", "sp", "ap", "y"):
+                assert np.array_equal(got[name], want[name]), (graph, k, name)
+    pl.set_graph(False)
+    only_y = pl.run(x, want_params=False, out={"y": sets[0]["y"]})
+    assert np.array_equal(only_y["y"], want["y"])

@@ -495,15 +495,25 @@ class Pipeline:
     def out_length(self, x_length):
         return lib().wb_pipeline_out_length(self._h, int(x_length))
 
-    def run(self, x, want_params=True):
-        """host x -> dict(tpos, f0, sp, ap, y) on the host"""
+    def run(self, x, want_params=True, out=None):
+        """host x -> dict(tpos, f0, sp, ap, y) on the host.  `out`: a dict of caller-owned C-contiguous float64 arrays
+        to fill instead (keys y and, with want_params, tpos, f0, sp, ap).  When all of them are page-locked (e.g.
+        torch pin_memory().numpy()) every result is downloaded as soon as its stage is done, beside the rest of the
+        chain."""
         x = _f64(x)
         L, bins, ny = self.f0_length(len(x)), self.fft_size // 2 + 1, self.out_length(len(x))
-        y = np.empty(ny, dtype=np.float64)
-        out = {"y": y}
         ptr = lambda a: a.ctypes.data if a is not None else None
-        if want_params:
-            out.update(tpos=np.empty(L), f0=np.empty(L), sp=np.empty((L, bins)), ap=np.empty((L, bins)))
+        if out is not None:
+            shapes = {"y": (ny,)}
+            if want_params:
+                shapes.update(tpos=(L,), f0=(L,), sp=(L, bins), ap=(L, bins))
+            out = {k: _out_array(out[k], shp) for k, shp in shapes.items()}
+            y = out["y"]
+        else:
+            y = np.empty(ny, dtype=np.float64)
+            out = {"y": y}
+            if want_params:
+                out.update(tpos=np.empty(L), f0=np.empty(L), sp=np.empty((L, bins)), ap=np.empty((L, bins)))
         _check(lib().wb_pipeline_run(self._h, x.ctypes.data, len(x), ptr(out.get("tpos")), ptr(out.get("f0")),
                                      ptr(out.get("sp")), ptr(out.get("ap")), y.ctypes.data, ny), "wb_pipeline_run")
         return out

@@ -365,7 +365,13 @@ struct wb_pipeline {
   bool use_graph = false;
   cudaGraphExec_t graph_exec = nullptr;
   unsigned long long graph_kernels = 0;
-  const void *graph_key[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  const void *graph_key[13] = {nullptr}, *warm_key[13] = {nullptr};
+  // wb_pipeline_run with page-locked host outputs: every result goes home on `copy` as soon as its stage is done
+  // (f0 after Harvest, the spectrogram beside D4C, the aperiodicity beside the impulse responses) instead of after
+  // the whole chain; null pointers = no in-chain downloads
+  struct HostOut { double *tpos = nullptr, *f0 = nullptr, *sp = nullptr, *ap = nullptr, *y = nullptr; } host_out;
+  cudaStream_t copy = nullptr;
+  cudaEvent_t ev_ct_done = nullptr, ev_copy_done = nullptr;
   int graph_len[2] = {0, 0};
   int warm_len[2] = {0, 0};
   double mod_f0_shift = NAN, mod_ratio = 0.0;   // parameter modification between analysis and synthesis (off)
@@ -379,6 +385,9 @@ struct wb_pipeline {
     if (ev_body_count) cudaEventDestroy(ev_body_count);
     if (ev_d4c) cudaEventDestroy(ev_d4c);
     if (ev_start) cudaEventDestroy(ev_start);
+    if (ev_ct_done) cudaEventDestroy(ev_ct_done);
+    if (ev_copy_done) cudaEventDestroy(ev_copy_done);
+    if (copy) cudaStreamDestroy(copy);
     if (side) cudaStreamDestroy(side);
     if (d4c_stream) cudaStreamDestroy(d4c_stream);
     if (d4c_split.alt) cudaStreamDestroy(d4c_split.alt);
@@ -911,6 +920,9 @@ int wb_pipeline_create(int fs, const WbHarvestOption *hopt, const WbCheapTrickOp
       cudaEventCreateWithFlags(&p->ev_body_count, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&p->ev_d4c, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&p->ev_start, cudaEventDisableTiming) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&p->copy, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&p->ev_ct_done, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&p->ev_copy_done, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&p->ev_tb, cudaEventDisableTiming) != cudaSuccess) {
     delete p;
     return WB_ERR_CUDA;
@@ -973,7 +985,8 @@ int wb_pipeline_run_dev(wb_pipeline_t *p, const double *d_x, int x_length, doubl
   cudaStream_t st = pick_stream(stream);
   if (!p->use_graph || wb_prof_is_enabled())
     return pipeline_enqueue(p, d_x, x_length, d_tpos, d_f0, d_sp, d_ap, d_y, y_length, st);
-  const void *key[8] = {d_x, d_tpos, d_f0, d_sp, d_ap, d_y, (const void *)st, nullptr};
+  const void *key[13] = {d_x, d_tpos, d_f0, d_sp, d_ap, d_y, (const void *)st, nullptr,
+                         p->host_out.tpos, p->host_out.f0, p->host_out.sp, p->host_out.ap, p->host_out.y};
   // (the graph holds raw pointers into the workspace: stale once any of its buffers has been reallocated)
   const bool same = p->graph_exec && memcmp(key, p->graph_key, sizeof(key)) == 0 && p->graph_len[0] == x_length &&
                     p->graph_len[1] == y_length && p->graph_generation == p->ws.generation();
@@ -982,10 +995,12 @@ int wb_pipeline_run_dev(wb_pipeline_t *p, const double *d_x, int x_length, doubl
     wb_launch_counter_add(p->graph_kernels);
     return WB_OK;
   }
-  if (p->warm_len[0] != x_length || p->warm_len[1] != y_length) {
-    // first run with these sizes: ordinary enqueue (allocations, plan-time tables, lazy initialisation)
+  if (p->warm_len[0] != x_length || p->warm_len[1] != y_length || memcmp(key, p->warm_key, sizeof(key)) != 0) {
+    // first run with these sizes and buffers: ordinary enqueue (allocations, plan-time tables, lazy initialisation).
+    // A graph is captured only when a call repeats the previous one's arguments, so callers that rotate their
+    // buffers run on plain launches instead of re-capturing every time.
     int rc = pipeline_enqueue(p, d_x, x_length, d_tpos, d_f0, d_sp, d_ap, d_y, y_length, st);
-    if (!rc) { p->warm_len[0] = x_length; p->warm_len[1] = y_length; }
+    if (!rc) { p->warm_len[0] = x_length; p->warm_len[1] = y_length; memcpy(p->warm_key, key, sizeof(key)); }
     return rc;
   }
   if (p->graph_exec) { cudaGraphExecDestroy(p->graph_exec); p->graph_exec = nullptr; }
@@ -1065,13 +1080,19 @@ static int pipeline_enqueue(wb_pipeline_t *p, const double *d_x, int x_length, d
   // (Per-kernel event timing needs one stream: profiling runs the branches back to back.)
   const bool fork = !wb_prof_is_enabled();
   cudaStream_t s_d4c = fork ? p->d4c_stream : st, s_side = fork ? p->side : st;
+  const wb_pipeline::HostOut &ho = p->host_out;
+  const bool downloads = ho.tpos || ho.f0 || ho.sp || ho.ap || ho.y;
+  cudaStream_t s_copy = fork ? p->copy : st;
   unsigned long long *rng_pos = (unsigned long long *)p->ws.get("pl_rng_pos", sizeof(unsigned long long) * 4);
   if (!rng_pos) return WB_ERR_CUDA;
   WB_CUDA_CHECK(cudaEventRecord(p->ev_f0, st));
   if (fork) {
     WB_CUDA_CHECK(cudaStreamWaitEvent(s_d4c, p->ev_f0, 0));
     if (y_length > 0) WB_CUDA_CHECK(cudaStreamWaitEvent(s_side, p->ev_f0, 0));
+    if (downloads) WB_CUDA_CHECK(cudaStreamWaitEvent(s_copy, p->ev_f0, 0));
   }
+  if (ho.tpos) WB_CUDA_CHECK(cudaMemcpyAsync(ho.tpos, d_tpos, sizeof(double) * f0_length, cudaMemcpyDeviceToHost, s_copy));
+  if (ho.f0 && !mod_f0) WB_CUDA_CHECK(cudaMemcpyAsync(ho.f0, d_f0, sizeof(double) * f0_length, cudaMemcpyDeviceToHost, s_copy));
   // CheapTrick (caller's stream)
   WbRngCursor c_ct;
   c_ct.state = rng; c_ct.skip_out = rng_pos + 0; c_ct.advance = false; c_ct.record_skip_out = p->ev_ct_count;
@@ -1081,6 +1102,13 @@ static int pipeline_enqueue(wb_pipeline_t *p, const double *d_x, int x_length, d
   if (p->mod_ratio > 0.0 &&
       (rc = wb_parameter_modification_run(nullptr, nullptr, f0_length, d_sp, fs, p->ct.fft_size, NAN, p->mod_ratio, st)))
     return rc;
+  if (ho.sp) {
+    if (fork) {
+      WB_CUDA_CHECK(cudaEventRecord(p->ev_ct_done, st));
+      WB_CUDA_CHECK(cudaStreamWaitEvent(s_copy, p->ev_ct_done, 0));
+    }
+    WB_CUDA_CHECK(cudaMemcpyAsync(ho.sp, d_sp, sizeof(double) * (size_t)f0_length * bins, cudaMemcpyDeviceToHost, s_copy));
+  }
   // D4C
   WbRngCursor c_d4c;
   c_d4c.state = rng; c_d4c.skip_in = rng_pos + 0; c_d4c.skip_out = rng_pos + 1; c_d4c.advance = false;
@@ -1089,6 +1117,10 @@ static int pipeline_enqueue(wb_pipeline_t *p, const double *d_x, int x_length, d
                        c_d4c, s_d4c, nullptr, nullptr, 0, nullptr, fork ? &p->d4c_split : nullptr)))
     return rc;
   WB_CUDA_CHECK(cudaEventRecord(p->ev_d4c, s_d4c));
+  if (ho.ap) {
+    if (fork) WB_CUDA_CHECK(cudaStreamWaitEvent(s_copy, p->ev_d4c, 0));
+    WB_CUDA_CHECK(cudaMemcpyAsync(ho.ap, d_ap, sizeof(double) * (size_t)f0_length * bins, cudaMemcpyDeviceToHost, s_copy));
+  }
   if (y_length > 0) {
     if (!d_y) return WB_ERR_CUDA;
     // Synthesis, part 1 (pulse list) on the side stream
@@ -1111,6 +1143,14 @@ static int pipeline_enqueue(wb_pipeline_t *p, const double *d_x, int x_length, d
   // the caller sees the modified f0, like the demo's world_parameters after ParameterModification (D4C, the
   // last reader of the estimated contour, has been joined above)
   if (mod_f0) WB_CUDA_CHECK(cudaMemcpyAsync(d_f0, d_f0_syn, sizeof(double) * f0_length, cudaMemcpyDeviceToDevice, st));
+  if (downloads) {
+    if (ho.y && y_length > 0) WB_CUDA_CHECK(cudaMemcpyAsync(ho.y, d_y, sizeof(double) * (size_t)y_length, cudaMemcpyDeviceToHost, st));
+    if (ho.f0 && mod_f0) WB_CUDA_CHECK(cudaMemcpyAsync(ho.f0, d_f0, sizeof(double) * f0_length, cudaMemcpyDeviceToHost, st));
+    if (fork) {   // the copy stream rejoins the caller's
+      WB_CUDA_CHECK(cudaEventRecord(p->ev_copy_done, s_copy));
+      WB_CUDA_CHECK(cudaStreamWaitEvent(st, p->ev_copy_done, 0));
+    }
+  }
   return WB_OK;
 }
 
@@ -1129,6 +1169,19 @@ int wb_pipeline_run(wb_pipeline_t *p, const double *x, int x_length, double *tpo
   double *d_ap = (double *)p->ws.get("pl_ap", sizeof(double) * (size_t)f0_length * bins);
   double *d_y = (double *)p->ws.get("pl_y", sizeof(double) * (size_t)(y_length > 0 ? y_length : 1));
   if (!d_t || !d_f || !d_sp || !d_ap || !d_y) return WB_ERR_CUDA;
+  // Page-locked outputs are downloaded inside the chain, each as soon as its stage is done (see HostOut)
+  const size_t mat = sizeof(double) * (size_t)f0_length * bins;
+  const bool in_chain = (!tpos || host_range_pinned(tpos, sizeof(double) * f0_length)) &&
+                        (!f0 || host_range_pinned(f0, sizeof(double) * f0_length)) && (!sp || host_range_pinned(sp, mat)) &&
+                        (!ap || host_range_pinned(ap, mat)) && (y_length == 0 || host_range_pinned(y, sizeof(double) * (size_t)y_length));
+  if (in_chain) {
+    p->host_out.tpos = tpos; p->host_out.f0 = f0; p->host_out.sp = sp; p->host_out.ap = ap; p->host_out.y = y_length > 0 ? y : nullptr;
+    rc = wb_pipeline_run_dev(p, d_x, x_length, d_t, d_f, d_sp, d_ap, d_y, y_length, st);
+    p->host_out = wb_pipeline::HostOut();
+    if (rc) return rc;
+    WB_CUDA_CHECK(cudaStreamSynchronize(st));
+    return p->ws.read_error_flag(st);
+  }
   if ((rc = wb_pipeline_run_dev(p, d_x, x_length, d_t, d_f, d_sp, d_ap, d_y, y_length, st))) return rc;
   if (tpos) WB_CUDA_CHECK(cudaMemcpyAsync(tpos, d_t, sizeof(double) * f0_length, cudaMemcpyDeviceToHost, st));
   if (f0) WB_CUDA_CHECK(cudaMemcpyAsync(f0, d_f, sizeof(double) * f0_length, cudaMemcpyDeviceToHost, st));
