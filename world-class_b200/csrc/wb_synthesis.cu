@@ -785,7 +785,7 @@ int wb_synthesis_timebase(WbWorkspace *ws, int fs, int fft_size, double frame_pe
   if (f0_length < 2) return WB_ERR_ARG;
   // pulses wanted: idx in (sample_begin + fft/2 - 1 - fft, sample_end + fft/2 - 2], plus the pulse after the last one
   // (its noise ends there); pulses are less than 2 fft_size samples apart (see render_range_core)
-  const int span = 2 * fft_size + 64;
+  const int span = 3 * fft_size + 64;   // (head / tail searched for the stream's first / last pulse: a pulse period is < 2 fft_size samples)
   int win_lo = 0, win_hi = out_length;
   if (sample_end >= 0) {
     if (sample_begin < 0 || sample_end > out_length || sample_begin > sample_end || noise_cursor) return WB_ERR_ARG;

@@ -562,22 +562,27 @@ def process_stream_exact(d_x, fs, harvest_option=None, cheaptrick_option=None, d
     # shard by shard: aperiodicity + synthesis, and the shard's samples go into the exchange (the stitch) while
     # the other shards compute; only the last exchanges are exposed
     done = {}
+    pending, sps, aps = [], [], []
+
+    def exchange_finished_shards():      # in shard order (the same on every rank), as far as they have been enqueued
+        while len(pending) < k and mine[len(pending)] in done:
+            j = len(pending)
+            w = workers[j]
+            y, ev = done.pop(mine[j])
+            main.wait_event(ev)
+            pending.append(PendingGather(y, [plan.samples[r * k + j] for r in range(world)], group))   # exchange 3
+            if keep_rows:
+                sps.append(w.owned_rows(w.d_sp))
+                aps.append(w.owned_rows(w.d_ap))
+            w.d_sp = w.d_ap = None
+
     for w in round_robin():
         w.aperiodicity(d_x, d_ap0)
         y = w.synthesis()
         ev = torch.cuda.Event()
         ev.record(w.stream)
         done[w.rank] = (y, ev)
-    pending, sps, aps = [], [], []
-    for j, s in enumerate(mine):                                   # (the same order on every rank)
-        w = workers[j]
-        y, ev = done[s]
-        main.wait_event(ev)
-        pending.append(PendingGather(y, [plan.samples[r * k + j] for r in range(world)], group))   # exchange 3
-        if keep_rows:
-            sps.append(w.owned_rows(w.d_sp))
-            aps.append(w.owned_rows(w.d_ap))
-        w.d_sp = w.d_ap = None
+        exchange_finished_shards()
     for ws in groups:
         ws[0].end()
     mark("aperiodicity_synthesis")
