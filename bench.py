@@ -370,7 +370,7 @@ def main():
             sys.path.insert(0, os.path.join(ROOT, "profiles"))
             from summarize import csrc_sha1
             # the ncu capture the figure comes from was made on other kernel sources than the ones timed here
-            traffic_stale = tj.get("_csrc_sha1_by_kernel", {}).get(dom) != csrc_sha1()
+            traffic_stale = tj.get("_csrc_sha1_by_kernel", {}).get(dom) != csrc_sha1(dom)
         except Exception:
             pass
         if dom is not None:

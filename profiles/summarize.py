@@ -32,12 +32,23 @@ METRICS = [
 ]
 
 
-def csrc_sha1():
-    """SHA-1 over the kernel sources (world-class_b200/csrc, sorted by name)"""
+def csrc_sha1(kernel=None):
+    """SHA-1 over the sources a kernel is compiled from: the .cu file that defines it plus every header of
+    world-class_b200/csrc (sorted by name).  Without a kernel name (or when no file defines it): all sources."""
     import hashlib
+    import re
     d = os.path.join(HERE, "..", "world-class_b200", "csrc")
+    names = sorted(os.listdir(d))
+    files = names
+    if kernel:
+        base = re.sub(r"<.*", "", kernel)
+        owners = [n for n in names if n.endswith(".cu") and re.search(r"\b%s\b" % re.escape(base), open(os.path.join(d, n)).read())]
+        # (the file that DEFINES it: a __global__ definition, not a mention in a comment of another file)
+        owners = [n for n in owners if re.search(r"__global__[^;{]*\b%s\s*\(" % re.escape(base), open(os.path.join(d, n)).read(), re.S)] or owners
+        if owners:
+            files = sorted(set(owners) | {n for n in names if n.endswith((".cuh", ".h"))})
     h = hashlib.sha1()
-    for name in sorted(os.listdir(d)):
+    for name in files:
         h.update(name.encode())
         h.update(open(os.path.join(d, name), "rb").read())
     return h.hexdigest()
@@ -91,10 +102,9 @@ def main():
             merged = json.load(open(path))
         except Exception:
             merged = {}
-    stamp = csrc_sha1()
     for k, v in traffic.items():
         merged[k] = max(v)
-        merged.setdefault("_csrc_sha1_by_kernel", {})[k] = stamp
+        merged.setdefault("_csrc_sha1_by_kernel", {})[k] = csrc_sha1(k)
     with open(path, "w") as f:
         json.dump(merged, f, indent=1, sort_keys=True)
     for rec in out_rows:
