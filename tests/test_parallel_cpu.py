@@ -85,7 +85,8 @@ def test_single_process_fallback_matches():
 
 # ---- exact stream sharding: planning and the exchange step (no GPU) ----------------------------------------
 @pytest.mark.parametrize("n,fs,world,seg", [(480000, 48000, 2, 4), (60 * 48000 + 1234, 48000, 3, 30), (22050 * 7 + 5, 22050, 2, 3),
-                                            (16000, 16000, 1, 30), (3600 * 48000, 48000, 8, 30), (16000 * 3, 16000, 8, 1)])
+                                            (16000, 16000, 1, 30), (3600 * 48000, 48000, 8, 30), (16000 * 3, 16000, 8, 1),
+                                            (3600 * 48000, 48000, 16, 120), (600 * 48000, 48000, 16, 120)])
 def test_stream_plan_covers_the_stream_and_keeps_the_analysis_grid(n, fs, world, seg):
     import worldb200  # noqa: F401
     from worldb200 import parallel as P
@@ -200,3 +201,16 @@ def test_numa_binding_helper_never_raises():
     if not info["bound"]:
         assert os.sched_getaffinity(0) == before
     os.sched_setaffinity(0, before)
+
+
+def test_stream_plan_cuts_a_shard_into_the_fewest_even_segments():
+    """One hour over 16 shards: 225 s each, Harvest segments of at most 120 s -> two pieces of 113 and 112 s (not 120 +
+    105): every piece pays its halo, and the longest one bounds the scratch of a Harvest call."""
+    import worldb200  # noqa: F401
+    from worldb200 import parallel as P
+    pl = P.StreamPlan(3600 * 48000, 48000, 16, 5.0, 2048, segment_seconds=120, halo_seconds=2)
+    for segs in pl.segments:
+        cores = [(s["frames"][1] - s["frames"][0]) / 200.0 for s in segs]
+        assert len(segs) == 2 and max(cores) <= 120.0 + 0.005 and abs(cores[0] - cores[1]) <= 1.0 + 0.005
+    one = P.StreamPlan(600 * 48000, 48000, 16, 5.0, 2048, segment_seconds=120, halo_seconds=2)
+    assert all(len(segs) == 1 for segs in one.segments)
